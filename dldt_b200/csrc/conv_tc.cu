@@ -1,0 +1,286 @@
+// Implicit-GEMM convolution / GEMM on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+//   D[M, Cout] = im2col(X)[M, K] * Wp[Cout, K]^T   (+ bias, activation, residual, activation)
+//
+// replaces dnnl::convolution_forward / inner_product_forward with post-ops as configured by
+// MKLDNNConvolutionNode::setPostOps (inference-engine/src/mkldnn_plugin/nodes/mkldnn_conv_node.cpp:355-403)
+// and MKLDNNFullyConnectedNode (nodes/mkldnn_fullyconnected_node.cpp:123-132).  The arithmetic
+// contract is ngraph/core/reference/include/ngraph/runtime/reference/convolution.hpp:89-186
+// (cross-correlation, zero padding, fp32 accumulation).
+//
+// Structure of one CTA (one 128 x BN output tile, 160 threads, 2 CTAs resident per SM so one CTA's
+// epilogue overlaps the other's main loop):
+//   warps 0-3  producers: gather the A tile (128 output pixels x 64 K-elements) straight from the
+//              NHWC activation tensor with 16-byte cp.async (zero-fill for padding/tails) into the
+//              128B-swizzled K-major layout the UMMA descriptor expects, same for the weight tile;
+//              afterwards the same warps run the epilogue (TMEM -> registers -> bias/act/residual -> HBM)
+//   warp 4     TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit releases smem stages
+// Synchronisation is mbarrier only: full[s] (producers -> MMA), empty[s] (MMA commit -> producers),
+// tmem_full (MMA commit -> epilogue).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "act.cuh"
+#include "common.h"
+#include "kernels.h"
+#include "ptx_sm100.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // 64 x 2 B = 128 B = one swizzle row
+constexpr int A_STAGE_BYTES = BM * 128;
+constexpr int NUM_PRODUCERS = 128;
+
+template <int BN> struct TcCfg;
+template <> struct TcCfg<64>  { static constexpr int STAGES = 4, LAG = 2; };
+template <> struct TcCfg<128> { static constexpr int STAGES = 3, LAG = 1; };
+
+template <int BN>
+constexpr int tc_smem_bytes() {
+  return TcCfg<BN>::STAGES * (A_STAGE_BYTES + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+
+template <typename T> struct TcType;
+template <> struct TcType<__nv_bfloat16> { static constexpr int is_bf16 = 1; };
+template <> struct TcType<__half> { static constexpr int is_bf16 = 0; };
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+
+template <typename T>
+__device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <typename T>
+__device__ __forceinline__ void unpack2(uint32_t u, float& a, float& b);
+template <> __device__ __forceinline__ void unpack2<__nv_bfloat16>(uint32_t u, float& a, float& b) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  a = __low2float(v); b = __high2float(v);
+}
+template <> __device__ __forceinline__ void unpack2<__half>(uint32_t u, float& a, float& b) {
+  __half2 v = *reinterpret_cast<__half2*>(&u);
+  a = __low2float(v); b = __high2float(v);
+}
+
+template <typename T, int BN>
+__global__ void __launch_bounds__(160, 2) conv_tc_kernel(const ConvParams p) {
+  constexpr int STAGES = TcCfg<BN>::STAGES;
+  constexpr int LAG = TcCfg<BN>::LAG;
+  constexpr int B_STAGE_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_al + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = p.Cout_alloc / BN;
+  const int n_tile = blockIdx.x % n_tiles;
+  const int m_tile = blockIdx.x / n_tiles;
+  const int m0 = m_tile * BM;
+  const int n0 = n_tile * BN;
+  const int nkb = p.Ktot / BK;
+  const int bz = blockIdx.z;
+
+  const T* __restrict__ xg = reinterpret_cast<const T*>(p.x) + (int64_t)bz * p.x_bs;
+  const T* __restrict__ wg = reinterpret_cast<const T*>(p.w) + (int64_t)bz * p.w_bs;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], NUM_PRODUCERS);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 4) {
+    ptx::tmem_alloc(tmem_slot, BN);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== producers =====================
+    const int t = threadIdx.x;
+    const int c = t & 7;          // 16-byte chunk within the 128-byte K row
+    const int r0 = t >> 3;        // first row handled by this thread (rows r0 + 16*i)
+    const uint32_t sw_off = (uint32_t)((c ^ (r0 & 7)) << 4);
+    const int HoWo = p.Ho * p.Wo;
+    int hi0[8], wi0[8];
+    int64_t xoff[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int m = m0 + r0 + 16 * i;
+      bool rv = m < p.M;
+      int mm = rv ? m : 0;
+      int n = mm / HoWo;
+      int rem = mm - n * HoWo;
+      int ho = rem / p.Wo;
+      int wo = rem - ho * p.Wo;
+      hi0[i] = rv ? ho * p.sh - p.pt : -(1 << 28);   // invalid rows never pass the bounds test
+      wi0[i] = wo * p.sw - p.pl;
+      xoff[i] = (int64_t)n * p.H * p.W * p.Cin_p;
+    }
+    const int cpc = p.Cin_p >> 3;       // 16-byte chunks per filter tap
+    const int taps = p.kh * p.kw;
+    int cc = c, tap = 0, fr = 0, fs = 0;  // chunk within tap, tap index, filter row/col
+    while (cc >= cpc) { cc -= cpc; ++tap; if (++fs == p.kw) { fs = 0; ++fr; } }
+
+    for (int kb = 0; kb < nkb + LAG; ++kb) {
+      if (kb < nkb) {
+        const int s = kb % STAGES;
+        ptx::mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+        const uint32_t a_dst = smem_base + s * STAGE_BYTES + r0 * 128 + sw_off;
+        const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+        const bool kvalid = tap < taps;
+        const int dh_off = fr * p.dh, dw_off = fs * p.dw;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int hi = hi0[i] + dh_off, wi = wi0[i] + dw_off;
+          bool ok = kvalid && (unsigned)hi < (unsigned)p.H && (unsigned)wi < (unsigned)p.W;
+          const T* src = ok ? xg + xoff[i] + ((int64_t)hi * p.W + wi) * p.Cin_p + cc * 8 : xg;
+          ptx::cp_async16(a_dst + i * (16 * 128), src, ok ? 16u : 0u);
+        }
+        const int wk = kb * BK + c * 8;
+        const bool wk_ok = wk < p.w_k;
+        const T* wsrc = wg + (int64_t)(n0 + r0) * p.w_ld + wk;
+#pragma unroll
+        for (int j = 0; j < BN / 16; ++j) {
+          const bool ok = wk_ok && (n0 + r0 + 16 * j) < p.w_rows;
+          ptx::cp_async16(b_dst + j * (16 * 128), ok ? wsrc + (int64_t)j * 16 * p.w_ld : wg, ok ? 16u : 0u);
+        }
+        // advance (tap, chunk) by one K block = 8 chunks
+        cc += 8;
+        while (cc >= cpc) { cc -= cpc; ++tap; if (++fs == p.kw) { fs = 0; ++fr; } }
+      }
+      ptx::cp_async_commit();
+      if (kb >= LAG) {
+        ptx::cp_async_wait<LAG>();
+        ptx::fence_proxy_async();
+        ptx::mbar_arrive(&full_bar[(kb - LAG) % STAGES]);
+      }
+    }
+
+    // ===================== epilogue =====================
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after();
+    const int row = warp * 32 + lane;
+    const int m = m0 + row;
+    const bool row_ok = m < p.M;
+    const int64_t yrow = (int64_t)bz * p.y_bs + (int64_t)m * p.ldy;
+    const float* __restrict__ bias = p.bias;
+#pragma unroll 1
+    for (int j = 0; j < BN / 32; ++j) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), v);
+      ptx::tmem_ld_wait();
+      const int nb = n0 + j * 32;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {   // groups of 8 output channels
+        const int n8 = nb + q * 8;
+        if (!row_ok || n8 >= p.Cout_p) continue;
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          f[e] = __uint_as_float(v[q * 8 + e]) + __ldg(bias + n8 + e);
+          f[e] = act_apply(f[e], p.act1, p.a1, p.b1);
+        }
+        if (p.res != nullptr) {
+          const uint4 rv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.res) + yrow + n8));
+          float r[8];
+          unpack2<T>(rv.x, r[0], r[1]); unpack2<T>(rv.y, r[2], r[3]);
+          unpack2<T>(rv.z, r[4], r[5]); unpack2<T>(rv.w, r[6], r[7]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = act_apply(f[e] + r[e], p.act2, p.a2, p.b2);
+        }
+        if (p.out_f32) {
+          float* yo = reinterpret_cast<float*>(p.y) + yrow + n8;
+          *reinterpret_cast<float4*>(yo) = make_float4(f[0], f[1], f[2], f[3]);
+          *reinterpret_cast<float4*>(yo + 4) = make_float4(f[4], f[5], f[6], f[7]);
+        } else {
+          uint4 o;
+          o.x = pack2<T>(f[0], f[1]); o.y = pack2<T>(f[2], f[3]);
+          o.z = pack2<T>(f[4], f[5]); o.w = pack2<T>(f[6], f[7]);
+          *reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.y) + yrow + n8) = o;
+        }
+      }
+    }
+  } else if (lane == 0) {
+    // ===================== MMA issuer (one thread) =====================
+    constexpr uint32_t idesc = ptx::make_idesc_f16(TcType<T>::is_bf16, BM, BN);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      ptx::mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+      ptx::tc_fence_after();
+      const uint32_t a_addr = smem_base + s * STAGE_BYTES;
+      const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+      for (int k = 0; k < BK / 16; ++k) {
+        const uint64_t da = ptx::make_smem_desc_sw128(a_addr + k * 32);
+        const uint64_t db = ptx::make_smem_desc_sw128(b_addr + k * 32);
+        ptx::umma_f16(tmem_base, da, db, idesc, (kb | k) ? 1u : 0u);
+      }
+      ptx::umma_commit(&empty_bar[s]);   // frees this smem stage once the MMAs above have read it
+    }
+    ptx::umma_commit(tmem_full_bar);     // accumulator complete -> epilogue
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) ptx::tmem_dealloc(tmem_base, BN);
+}
+
+template <typename T, int BN>
+void launch_tc(const ConvParams& p, cudaStream_t s) {
+  constexpr int smem = tc_smem_bytes<BN>();
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int n_tiles = p.Cout_alloc / BN;
+  dim3 grid((unsigned)(m_tiles * n_tiles), 1, (unsigned)p.batch);
+  conv_tc_kernel<T, BN><<<grid, 160, smem, s>>>(p);
+}
+
+}  // namespace
+
+int conv_tc_pick_bn(int cout_p) { return cout_p <= 64 ? 64 : 128; }
+
+// Opt in to >48 KB dynamic shared memory on the current device (called once per device at compile).
+void conv_tc_init_device() {
+  cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<64>());
+  cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<128>());
+  cudaFuncSetAttribute(conv_tc_kernel<__half, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<64>());
+  cudaFuncSetAttribute(conv_tc_kernel<__half, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<128>());
+}
+
+void launch_conv_tc(const ConvParams& p, int dtype, int bn, cudaStream_t s) {
+  B200_CHECK(p.Ktot % BK == 0 && p.Cin_p % 8 == 0 && p.Cout_alloc % bn == 0 && p.Cout_p % 8 == 0 && p.ldy % 8 == 0 &&
+                 p.w_ld % 8 == 0 && p.w_k % 8 == 0,
+             B200_ERR_INVALID, "conv_tc: bad geometry");
+  if (dtype == B200_BF16) {
+    if (bn == 64) launch_tc<__nv_bfloat16, 64>(p, s); else launch_tc<__nv_bfloat16, 128>(p, s);
+  } else if (dtype == B200_F16) {
+    if (bn == 64) launch_tc<__half, 64>(p, s); else launch_tc<__half, 128>(p, s);
+  } else {
+    B200_THROW(B200_ERR_UNSUPPORTED, "conv_tc: dtype must be bf16/f16");
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,120 @@
+// Host-callable launchers of every CUDA kernel in the library.  All of them enqueue on the given
+// stream and never allocate or synchronise.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace b200 {
+
+struct ActSpec;
+
+// ---- implicit-GEMM convolution / GEMM on tcgen05 tensor cores (conv_tc.cu) -----------------
+// GEMM view: D[M, Cout] = A[M, K] * W[Cout, K]^T with M = N*Ho*Wo output pixels and
+// K = kh*kw*Cin_p gathered on the fly from the NHWC8 activation tensor.
+struct ConvParams {
+  const void* x = nullptr;     // activations NHWC [N,H,W,Cin_p], Cin_p % 8 == 0
+  const void* w = nullptr;     // packed weights [Cout_alloc][Ktot], K order = (tap, cin), zero padded
+  const float* bias = nullptr; // [Cout_alloc] fp32
+  const void* res = nullptr;   // optional residual, same geometry as y
+  void* y = nullptr;           // output [M, ldy]
+  int N = 1, H = 1, W = 1, Cin_p = 8, Ho = 1, Wo = 1, Cout_p = 8;
+  int kh = 1, kw = 1, sh = 1, sw = 1, dh = 1, dw = 1, pt = 0, pl = 0;
+  int M = 0, Ktot = 0;
+  int Cout_alloc = 0;          // N extent covered by tiles / entries of bias (multiple of the N tile)
+  int w_ld = 0;                // weight row pitch in elements
+  int w_rows = 0;              // valid weight rows (rows >= w_rows are read as zero)
+  int w_k = 0;                 // valid K per weight row (k >= w_k is read as zero)
+  int ldy = 0;                 // output row pitch in elements (>= Cout_p)
+  int act1 = 0, act2 = 0;
+  float a1 = 0, b1 = 0, a2 = 0, b2 = 0;
+  int out_f32 = 0;             // write fp32 instead of the compute type
+  int batch = 1;               // blockIdx.z batches (batched MatMul); strides in elements
+  int64_t x_bs = 0, w_bs = 0, y_bs = 0;
+};
+// dtype: B200_BF16 or B200_F16.  bn: N tile (64 or 128).
+void launch_conv_tc(const ConvParams& p, int dtype, int bn, cudaStream_t s);
+int conv_tc_pick_bn(int cout_p);
+void conv_tc_init_device();
+// CUDA-core fp32 path (fp32 mode: 1e-4 parity; also the reference for tcgen05 unit tests).
+// Same parameter block; x/w/res/y are fp32, weights [Cout_alloc][Ktot] fp32.
+void launch_conv_f32(const ConvParams& p, cudaStream_t s);
+
+// ---- depthwise convolution (memory bound, CUDA cores) --------------------------------------
+struct DwParams {
+  const void* x; const void* w; const float* bias; void* y;  // w: [kh*kw][Cp] in compute type
+  int N, H, W, Cp, Ho, Wo, kh, kw, sh, sw, dh, dw, pt, pl;
+  int act; float a, b;
+};
+void launch_dwconv(const DwParams& p, int dtype, cudaStream_t s);
+
+// ---- pooling ---------------------------------------------------------------------------------
+struct PoolParams {
+  const void* x; void* y;
+  int N, H, W, Cp, Ho, Wo, kh, kw, sh, sw, pt, pl, pb, pr;
+  int is_avg, exclude_pad;
+};
+void launch_pool(const PoolParams& p, int dtype, cudaStream_t s);
+void launch_global_avgpool(const void* x, void* y, int N, int HW, int Cp, int dtype, cudaStream_t s);
+
+// ---- elementwise -------------------------------------------------------------------------------
+// unary activation over n physical elements
+void launch_unary(const void* x, void* y, int64_t n, int dtype, int act, float a, float b, cudaStream_t s);
+// binary with numpy broadcasting over logical row-major tensors (rank <= 8)
+struct BinaryParams {
+  const void* a; const void* b; void* y;
+  int rank; int64_t oshape[8]; int64_t astride[8]; int64_t bstride[8];  // element strides, 0 = broadcast
+  int64_t n; int op; int act; float aa, ab;
+};
+void launch_binary(const BinaryParams& p, int dtype, cudaStream_t s);
+// same-shape fast path (any layout, physical element count), optional fused activation
+void launch_binary_same(const void* a, const void* b, void* y, int64_t n, int dtype, int op, int act, float aa, float ab, cudaStream_t s);
+// y[.., c] = act(x[.., c] * scale[c] + shift[c]) over NHWC8 (Cp) or rows of length Cp
+void launch_scale_shift(const void* x, const float* scale, const float* shift, void* y, int64_t rows, int Cp, int dtype, int act,
+                        float aa, float ab, cudaStream_t s);
+
+// ---- softmax / MVN / gather ------------------------------------------------------------------
+void launch_softmax(const void* x, void* y, int64_t outer, int64_t axis, int64_t inner, int dtype, cudaStream_t s);
+void launch_mvn(const void* x, void* y, const float* gamma, const float* beta, int64_t rows, int64_t cols, int normalize_variance,
+                int eps_outside, float eps, int dtype, cudaStream_t s);
+void launch_gather_rows(const void* table, const int32_t* idx, void* y, int64_t n_idx, int64_t row_elems, int64_t table_rows,
+                        int dtype, cudaStream_t s);
+void launch_reduce(const void* x, void* y, int64_t outer, int64_t axis, int64_t inner, int dtype, int kind /*0 mean 1 sum 2 max*/, cudaStream_t s);
+
+// ---- layout / dtype conversion ---------------------------------------------------------------
+enum PhysLayout : int { PL_ROWMAJOR = 0, PL_NHWC8 = 1, PL_NHWC_DENSE = 2 };
+// rank-4 logical [N,C,H,W]; converts dtype and layout in one pass
+void launch_convert4(const void* src, int sdtype, int slayout, void* dst, int ddtype, int dlayout, int N, int C, int H, int W, cudaStream_t s);
+// flat dtype conversion
+void launch_convert_flat(const void* src, int sdtype, void* dst, int ddtype, int64_t n, cudaStream_t s);
+// generic permute of a dense row-major tensor: out[idx] = in[perm(idx)]
+struct PermuteParams {
+  const void* x; void* y; int rank; int64_t oshape[8]; int64_t istride[8]; int64_t n;
+};
+void launch_permute(const PermuteParams& p, int elem_size, cudaStream_t s);
+// strided 2D copy: rows x row_bytes from src (pitch) to dst (pitch); used by concat / split
+void launch_copy2d(const void* src, int64_t spitch, void* dst, int64_t dpitch, int64_t row_bytes, int64_t rows, cudaStream_t s);
+void launch_fill_zero(void* dst, int64_t bytes, cudaStream_t s);
+
+// ---- TopK / NMS / DetectionOutput (fp32 + i32, bit-exact ordering rules) ---------------------
+void launch_topk(const float* x, float* vals, int32_t* idx, int64_t outer, int64_t axis, int64_t inner, int k, int mode_min, int sort_mode,
+                 cudaStream_t s);
+struct NmsParams {
+  const float* boxes; const float* scores; int32_t* sel_idx; float* sel_scores; int32_t* valid;
+  int B, C, Nb, max_out, center_format, sort_desc; float iou_thr, score_thr, soft_sigma;
+  void* workspace; int64_t workspace_bytes;
+};
+int64_t nms_workspace_bytes(int B, int C, int Nb, int max_out);
+void launch_nms(const NmsParams& p, cudaStream_t s);
+struct DetOutParams {
+  const float* loc; const float* conf; const float* priors; float* out;
+  int N, num_priors, num_classes, background, top_k, keep_top_k, code_center, share_location, var_in_target, normalized,
+      clip_before, clip_after, input_h, input_w, decrease_label_id, num_loc_classes, priors_batch;
+  float nms_thr, conf_thr;
+  int64_t out_rows;
+  void* workspace; int64_t workspace_bytes;
+};
+int64_t detout_workspace_bytes(const DetOutParams& p);
+void launch_detection_output(const DetOutParams& p, cudaStream_t s);
+
+}  // namespace b200

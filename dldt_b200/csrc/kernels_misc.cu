@@ -1,0 +1,653 @@
+// Memory-bound CUDA-core kernels: depthwise convolution, pooling, elementwise, softmax, MVN,
+// gather, reductions, layout/dtype conversion, permute, TopK.  All activation tensors of rank 4
+// are NHWC with the channel count padded to a multiple of 8 ("NHWC8") so that every access is a
+// 128-bit vector; everything else is dense row-major.  Reference semantics are cited per kernel.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cfloat>
+
+#include "act.cuh"
+#include "common.h"
+#include "kernels.h"
+
+namespace b200 {
+namespace {
+
+// ---- typed 8-wide vector access ---------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float ldf(const T* p, int64_t i);
+template <> __device__ __forceinline__ float ldf<float>(const float* p, int64_t i) { return p[i]; }
+template <> __device__ __forceinline__ float ldf<__half>(const __half* p, int64_t i) { return __half2float(p[i]); }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p, int64_t i) { return __bfloat162float(p[i]); }
+template <> __device__ __forceinline__ float ldf<int32_t>(const int32_t* p, int64_t i) { return (float)p[i]; }
+template <> __device__ __forceinline__ float ldf<uint8_t>(const uint8_t* p, int64_t i) { return (float)p[i]; }
+template <typename T> __device__ __forceinline__ void stf(T* p, int64_t i, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, int64_t i, float v) { p[i] = v; }
+template <> __device__ __forceinline__ void stf<__half>(__half* p, int64_t i, float v) { p[i] = __float2half_rn(v); }
+template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, int64_t i, float v) { p[i] = __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ void stf<int32_t>(int32_t* p, int64_t i, float v) { p[i] = (int32_t)v; }
+template <> __device__ __forceinline__ void stf<uint8_t>(uint8_t* p, int64_t i, float v) { p[i] = (uint8_t)fminf(fmaxf(v, 0.f), 255.f); }
+
+template <typename T> __device__ __forceinline__ void load8(const T* p, float (&f)[8]);
+template <> __device__ __forceinline__ void load8<float>(const float* p, float (&f)[8]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8<__half>(const __half* p, float (&f)[8]) {
+  uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __low2float(h[i]); f[2 * i + 1] = __high2float(h[i]); }
+}
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __low2float(h[i]); f[2 * i + 1] = __high2float(h[i]); }
+}
+template <typename T> __device__ __forceinline__ void store8(T* p, const float (&f)[8]);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float (&f)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+template <> __device__ __forceinline__ void store8<__half>(__half* p, const float (&f)[8]) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+#define B200_DISPATCH_FLOAT(dtype, T, ...)                                             \
+  do {                                                                                 \
+    if ((dtype) == B200_F32) { using T = float; __VA_ARGS__; }                         \
+    else if ((dtype) == B200_BF16) { using T = __nv_bfloat16; __VA_ARGS__; }           \
+    else if ((dtype) == B200_F16) { using T = __half; __VA_ARGS__; }                   \
+    else B200_THROW(B200_ERR_UNSUPPORTED, "kernel: unsupported dtype " << (dtype));    \
+  } while (0)
+
+inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide reductions (blockDim.x <= 1024), result broadcast to all threads
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = l < nw ? sh[l] : 0.f;
+  return warp_sum(r);
+}
+__device__ __forceinline__ float block_max(float v, float* sh) {
+  v = warp_max(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = l < nw ? sh[l] : -FLT_MAX;
+  return warp_max(r);
+}
+
+// ---- depthwise convolution ---------------------------------------------------------------------
+// GroupConvolution with G == C (nodes/mkldnn_conv_node.cpp:78-100); one thread = one output pixel
+// x 8 channels; weights [tap][Cp]; bias + activation fused.
+template <typename T>
+__global__ void dwconv_kernel(const DwParams p) {
+  const int cpc = p.Cp >> 3;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)p.N * p.Ho * p.Wo * cpc;
+  if (idx >= total) return;
+  int c8 = (int)(idx % cpc);
+  int64_t pix = idx / cpc;
+  int wo = (int)(pix % p.Wo);
+  int64_t t = pix / p.Wo;
+  int ho = (int)(t % p.Ho);
+  int n = (int)(t / p.Ho);
+  const T* x = reinterpret_cast<const T*>(p.x) + (int64_t)n * p.H * p.W * p.Cp + c8 * 8;
+  const T* w = reinterpret_cast<const T*>(p.w) + c8 * 8;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = __ldg(p.bias + c8 * 8 + e);
+  for (int r = 0; r < p.kh; ++r) {
+    int hi = ho * p.sh - p.pt + r * p.dh;
+    if ((unsigned)hi >= (unsigned)p.H) continue;
+    for (int s = 0; s < p.kw; ++s) {
+      int wi = wo * p.sw - p.pl + s * p.dw;
+      if ((unsigned)wi >= (unsigned)p.W) continue;
+      float xv[8], wv[8];
+      load8<T>(x + ((int64_t)hi * p.W + wi) * p.Cp, xv);
+      load8<T>(w + (int64_t)(r * p.kw + s) * p.Cp, wv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(xv[e], wv[e], acc[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = act_apply(acc[e], p.act, p.a, p.b);
+  store8<T>(reinterpret_cast<T*>(p.y) + pix * p.Cp + c8 * 8, acc);
+}
+
+// ---- pooling ------------------------------------------------------------------------------------
+// MaxPool ignores padding; AvgPool divisor = kh*kw iff !exclude_pad and some pad != 0 (window clipped
+// to the padded extent), else the number of in-bounds elements
+// (reference/max_pool.hpp:74-117, reference/avg_pool.hpp:215-262).
+template <typename T>
+__global__ void pool_kernel(const PoolParams p) {
+  const int cpc = p.Cp >> 3;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)p.N * p.Ho * p.Wo * cpc;
+  if (idx >= total) return;
+  int c8 = (int)(idx % cpc);
+  int64_t pix = idx / cpc;
+  int wo = (int)(pix % p.Wo);
+  int64_t t = pix / p.Wo;
+  int ho = (int)(t % p.Ho);
+  int n = (int)(t / p.Ho);
+  const T* x = reinterpret_cast<const T*>(p.x) + (int64_t)n * p.H * p.W * p.Cp + c8 * 8;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = p.is_avg ? 0.f : -FLT_MAX;
+  int h0 = ho * p.sh - p.pt, w0 = wo * p.sw - p.pl;
+  int cnt_in = 0, cnt_pad = 0;
+  for (int r = 0; r < p.kh; ++r) {
+    int hi = h0 + r;
+    bool h_in = (unsigned)hi < (unsigned)p.H;
+    bool h_padded = hi >= -p.pt && hi < p.H + p.pb;   // inside the padded extent
+    for (int s = 0; s < p.kw; ++s) {
+      int wi = w0 + s;
+      bool w_in = (unsigned)wi < (unsigned)p.W;
+      bool w_padded = wi >= -p.pl && wi < p.W + p.pr;
+      if (h_padded && w_padded) ++cnt_pad;
+      if (!(h_in && w_in)) continue;
+      ++cnt_in;
+      float xv[8];
+      load8<T>(x + ((int64_t)hi * p.W + wi) * p.Cp, xv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = p.is_avg ? acc[e] + xv[e] : fmaxf(acc[e], xv[e]);
+    }
+  }
+  if (p.is_avg) {
+    bool any_pad = (p.pt | p.pl | p.pb | p.pr) != 0;
+    int div = (!p.exclude_pad && any_pad) ? cnt_pad : cnt_in;
+    float inv = div > 0 ? 1.f / (float)div : 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= inv;
+  } else if (cnt_in == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  }
+  store8<T>(reinterpret_cast<T*>(p.y) + pix * p.Cp + c8 * 8, acc);
+}
+
+template <typename T>
+__global__ void global_avgpool_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int HW, int Cp) {
+  const int cpc = Cp >> 3;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * cpc) return;
+  int c8 = (int)(idx % cpc);
+  int n = (int)(idx / cpc);
+  const T* px = x + (int64_t)n * HW * Cp + c8 * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < HW; ++i) {
+    float v[8];
+    load8<T>(px + (int64_t)i * Cp, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += v[e];
+  }
+  float inv = 1.f / (float)HW;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] *= inv;
+  store8<T>(y + (int64_t)n * Cp + c8 * 8, acc);
+}
+
+// ---- elementwise ---------------------------------------------------------------------------------
+__device__ __forceinline__ float binop(float a, float b, int op) {
+  switch (op) {
+    case B200_OP_ADD: return a + b;
+    case B200_OP_SUBTRACT: return a - b;
+    case B200_OP_MULTIPLY: return a * b;
+    case B200_OP_DIVIDE: return a / b;
+    case B200_OP_MAXIMUM: return fmaxf(a, b);
+    case B200_OP_MINIMUM: return fminf(a, b);
+    case B200_OP_POWER: return powf(a, b);
+    case B200_OP_SQUARED_DIFFERENCE: return (a - b) * (a - b);
+    case B200_OP_PRELU: return a >= 0.f ? a : a * b;
+  }
+  return a;
+}
+
+template <typename T>
+__global__ void unary_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, int act, float a, float b) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    float v[8];
+    load8<T>(x + i, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = act_apply(v[e], act, a, b);
+    store8<T>(y + i, v);
+  } else {
+    for (; i < n; ++i) stf<T>(y, i, act_apply(ldf<T>(x, i), act, a, b));
+  }
+}
+
+template <typename T>
+__global__ void binary_same_kernel(const T* __restrict__ pa, const T* __restrict__ pb, T* __restrict__ y, int64_t n, int op, int act,
+                                   float aa, float ab) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    float u[8], v[8];
+    load8<T>(pa + i, u);
+    load8<T>(pb + i, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) u[e] = act_apply(binop(u[e], v[e], op), act, aa, ab);
+    store8<T>(y + i, u);
+  } else {
+    for (; i < n; ++i) stf<T>(y, i, act_apply(binop(ldf<T>(pa, i), ldf<T>(pb, i), op), act, aa, ab));
+  }
+}
+
+template <typename T>
+__global__ void binary_bcast_kernel(const BinaryParams p) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  int64_t rem = i, ao = 0, bo = 0;
+#pragma unroll 1
+  for (int d = p.rank - 1; d >= 0; --d) {
+    int64_t c = rem % p.oshape[d];
+    rem /= p.oshape[d];
+    ao += c * p.astride[d];
+    bo += c * p.bstride[d];
+  }
+  float r = binop(ldf<T>(reinterpret_cast<const T*>(p.a), ao), ldf<T>(reinterpret_cast<const T*>(p.b), bo), p.op);
+  stf<T>(reinterpret_cast<T*>(p.y), i, act_apply(r, p.act, p.aa, p.ab));
+}
+
+template <typename T>
+__global__ void scale_shift_kernel(const T* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                                   T* __restrict__ y, int64_t rows, int Cp, int act, float aa, float ab) {
+  const int cpc = Cp >> 3;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cpc) return;
+  int c8 = (int)(idx % cpc);
+  float v[8];
+  load8<T>(x + idx * 8, v);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = act_apply(fmaf(v[e], __ldg(scale + c8 * 8 + e), __ldg(shift + c8 * 8 + e)), act, aa, ab);
+  store8<T>(y + idx * 8, v);
+}
+
+// ---- softmax: exp(x - max) / sum (reference/softmax.hpp:19-47) ----------------------------------
+template <typename T>
+__global__ void softmax_rows_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int64_t cols) {
+  __shared__ float sh[32];
+  int64_t row = blockIdx.x;
+  const T* px = x + row * cols;
+  T* py = y + row * cols;
+  float m = -FLT_MAX;
+  for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, ldf<T>(px, c));
+  m = block_max(m, sh);
+  float s = 0.f;
+  for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) s += expf(ldf<T>(px, c) - m);
+  s = block_sum(s, sh);
+  float inv = 1.f / s;
+  for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) stf<T>(py, c, expf(ldf<T>(px, c) - m) * inv);
+}
+template <typename T>
+__global__ void softmax_strided_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t outer, int64_t axis, int64_t inner) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= outer * inner) return;
+  int64_t o = i / inner, in = i % inner;
+  const T* px = x + o * axis * inner + in;
+  T* py = y + o * axis * inner + in;
+  float m = -FLT_MAX;
+  for (int64_t a = 0; a < axis; ++a) m = fmaxf(m, ldf<T>(px, a * inner));
+  float s = 0.f;
+  for (int64_t a = 0; a < axis; ++a) s += expf(ldf<T>(px, a * inner) - m);
+  float inv = 1.f / s;
+  for (int64_t a = 0; a < axis; ++a) stf<T>(py, a * inner, expf(ldf<T>(px, a * inner) - m) * inv);
+}
+
+// ---- MVN / LayerNorm over the last `cols` elements (reference/mvn.hpp:66-118) --------------------
+template <typename T>
+__global__ void mvn_rows_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int64_t cols, int normalize_variance, int eps_outside, float eps) {
+  __shared__ float sh[32];
+  int64_t row = blockIdx.x;
+  const T* px = x + row * cols;
+  T* py = y + row * cols;
+  float s = 0.f;
+  for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) s += ldf<T>(px, c);
+  float mean = block_sum(s, sh) / (float)cols;
+  float scale = 1.f;
+  if (normalize_variance) {
+    float v = 0.f;
+    for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) { float d = ldf<T>(px, c) - mean; v += d * d; }
+    float var = block_sum(v, sh) / (float)cols;
+    scale = eps_outside ? 1.f / (sqrtf(var) + eps) : 1.f / sqrtf(var + eps);
+  }
+  for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) {
+    float r = (ldf<T>(px, c) - mean) * scale;
+    if (gamma) r *= __ldg(gamma + c);
+    if (beta) r += __ldg(beta + c);
+    stf<T>(py, c, r);
+  }
+}
+
+template <typename T>
+__global__ void gather_rows_kernel(const T* __restrict__ table, const int32_t* __restrict__ idx, T* __restrict__ y, int64_t n_idx,
+                                   int64_t row_elems, int64_t table_rows) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_idx * row_elems) return;
+  int64_t r = i / row_elems, c = i % row_elems;
+  int64_t src = idx[r];
+  if (src < 0) src += table_rows;
+  y[i] = (src >= 0 && src < table_rows) ? table[src * row_elems + c] : T(0);
+}
+
+template <typename T>
+__global__ void reduce_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t outer, int64_t axis, int64_t inner, int kind) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= outer * inner) return;
+  int64_t o = i / inner, in = i % inner;
+  const T* px = x + o * axis * inner + in;
+  float acc = kind == 2 ? -FLT_MAX : 0.f;
+  for (int64_t a = 0; a < axis; ++a) {
+    float v = ldf<T>(px, a * inner);
+    acc = kind == 2 ? fmaxf(acc, v) : acc + v;
+  }
+  if (kind == 0) acc /= (float)axis;
+  stf<T>(y, i, acc);
+}
+
+// ---- layout + dtype conversion -------------------------------------------------------------------
+// logical [N,C,H,W]; physical: ROWMAJOR = NCHW dense, NHWC8 = [N,H,W,round_up(C,8)], NHWC_DENSE = [N,H,W,C]
+__device__ __forceinline__ int64_t phys_index(int layout, int n, int c, int h, int w, int C, int H, int W) {
+  switch (layout) {
+    case PL_ROWMAJOR: return (((int64_t)n * C + c) * H + h) * W + w;
+    case PL_NHWC8: return (((int64_t)n * H + h) * W + w) * ((C + 7) & ~7) + c;
+    default: return (((int64_t)n * H + h) * W + w) * C + c;
+  }
+}
+// One thread per destination element of the padded extent; channel-fastest destinations read
+// the NCHW source with stride H*W (L2 absorbs it: each 32-byte sector is reused by 8 neighbours
+// in w, which are adjacent threads when C is small, e.g. the 3-channel network input).
+template <typename S, typename D>
+__global__ void convert4_kernel(const S* __restrict__ src, int slayout, D* __restrict__ dst, int dlayout, int N, int C, int H, int W) {
+  const int Cd = dlayout == PL_NHWC8 ? ((C + 7) & ~7) : C;
+  int64_t total = (int64_t)N * Cd * H * W;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int n, c, h, w;
+  if (dlayout == PL_ROWMAJOR) {
+    w = (int)(i % W); int64_t t = i / W; h = (int)(t % H); t /= H; c = (int)(t % C); n = (int)(t / C);
+  } else {
+    c = (int)(i % Cd); int64_t t = i / Cd; w = (int)(t % W); t /= W; h = (int)(t % H); n = (int)(t / H);
+  }
+  float v = c < C ? ldf<S>(src, phys_index(slayout, n, c, h, w, C, H, W)) : 0.f;
+  stf<D>(dst, i, v);
+}
+template <typename S, typename D>
+__global__ void convert_flat_kernel(const S* __restrict__ src, D* __restrict__ dst, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) stf<D>(dst, i, ldf<S>(src, i));
+}
+__global__ void copy_i32_kernel(const int32_t* __restrict__ src, int32_t* __restrict__ dst, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+template <typename E>
+__global__ void permute_kernel(const PermuteParams p) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  int64_t rem = i, so = 0;
+#pragma unroll 1
+  for (int d = p.rank - 1; d >= 0; --d) {
+    int64_t c = rem % p.oshape[d];
+    rem /= p.oshape[d];
+    so += c * p.istride[d];
+  }
+  reinterpret_cast<E*>(p.y)[i] = reinterpret_cast<const E*>(p.x)[so];
+}
+
+template <typename V>
+__global__ void copy2d_kernel(const char* __restrict__ src, int64_t spitch, char* __restrict__ dst, int64_t dpitch, int64_t row_vecs,
+                              int64_t rows) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * row_vecs) return;
+  int64_t r = i / row_vecs, c = i % row_vecs;
+  reinterpret_cast<V*>(dst + r * dpitch)[c] = reinterpret_cast<const V*>(src + r * spitch)[c];
+}
+
+// ---- TopK -----------------------------------------------------------------------------------------
+// Order: MAX -> (value desc, index asc); MIN -> (value asc, index asc)
+// (reference/topk.hpp:22-40 compare_max/compare_min; nodes/mkldnn_topk_node.cpp:405-463 strict compare).
+// One block per (outer, inner) slice; k rounds of a block-wide arg-best over the elements that come
+// strictly after the previously selected one in that total order.
+__device__ __forceinline__ bool topk_before(float va, int ia, float vb, int ib, int mode_min) {
+  if (va != vb) return mode_min ? va < vb : va > vb;
+  return ia < ib;
+}
+__global__ void topk_kernel(const float* __restrict__ x, float* __restrict__ vals, int32_t* __restrict__ idx, int64_t axis, int64_t inner,
+                            int k, int mode_min, int sort_mode) {
+  extern __shared__ unsigned char topk_smem[];
+  float* sv = reinterpret_cast<float*>(topk_smem);      // [nwarps]
+  int* si = reinterpret_cast<int*>(sv + 32);            // [nwarps]
+  float* outv = reinterpret_cast<float*>(si + 32);      // [k]
+  int* outi = reinterpret_cast<int*>(outv + k);         // [k]
+  __shared__ float last_v;
+  __shared__ int last_i;
+  int64_t slice = blockIdx.x;
+  int64_t o = slice / inner, in = slice % inner;
+  const float* px = x + o * axis * inner + in;
+  const int nw = (blockDim.x + 31) >> 5;
+  for (int r = 0; r < k; ++r) {
+    float bv = 0.f;
+    int bi = -1;
+    for (int64_t a = threadIdx.x; a < axis; a += blockDim.x) {
+      float v = px[a * inner];
+      if (r > 0 && !topk_before(last_v, last_i, v, (int)a, mode_min)) continue;  // already selected or earlier
+      if (bi < 0 || topk_before(v, (int)a, bv, bi, mode_min)) { bv = v; bi = (int)a; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (oi >= 0 && (bi < 0 || topk_before(ov, oi, bv, bi, mode_min))) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float fv = sv[0];
+      int fi = si[0];
+      for (int w = 1; w < nw; ++w)
+        if (si[w] >= 0 && (fi < 0 || topk_before(sv[w], si[w], fv, fi, mode_min))) { fv = sv[w]; fi = si[w]; }
+      last_v = fv; last_i = fi;
+      outv[r] = fv; outi[r] = fi;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && sort_mode == 2) {  // SORT_INDICES: ascending index
+    for (int a = 1; a < k; ++a) {
+      float v = outv[a]; int id = outi[a]; int b = a - 1;
+      while (b >= 0 && outi[b] > id) { outv[b + 1] = outv[b]; outi[b + 1] = outi[b]; --b; }
+      outv[b + 1] = v; outi[b + 1] = id;
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < k; r += blockDim.x) {
+    int64_t off = o * k * inner + (int64_t)r * inner + in;
+    vals[off] = outv[r];
+    idx[off] = outi[r];
+  }
+}
+
+}  // namespace
+
+// ================================= launchers ==========================================================
+void launch_dwconv(const DwParams& p, int dtype, cudaStream_t s) {
+  int64_t total = (int64_t)p.N * p.Ho * p.Wo * (p.Cp / 8);
+  B200_DISPATCH_FLOAT(dtype, T, (dwconv_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(p)));
+}
+void launch_pool(const PoolParams& p, int dtype, cudaStream_t s) {
+  int64_t total = (int64_t)p.N * p.Ho * p.Wo * (p.Cp / 8);
+  B200_DISPATCH_FLOAT(dtype, T, (pool_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(p)));
+}
+void launch_global_avgpool(const void* x, void* y, int N, int HW, int Cp, int dtype, cudaStream_t s) {
+  int64_t total = (int64_t)N * (Cp / 8);
+  B200_DISPATCH_FLOAT(dtype, T, (global_avgpool_kernel<T><<<grid_for(total, 128), 128, 0, s>>>((const T*)x, (T*)y, N, HW, Cp)));
+}
+void launch_unary(const void* x, void* y, int64_t n, int dtype, int act, float a, float b, cudaStream_t s) {
+  if (n == 0) return;
+  B200_DISPATCH_FLOAT(dtype, T, (unary_kernel<T><<<grid_for((n + 7) / 8, 256), 256, 0, s>>>((const T*)x, (T*)y, n, act, a, b)));
+}
+void launch_binary_same(const void* a, const void* b, void* y, int64_t n, int dtype, int op, int act, float aa, float ab, cudaStream_t s) {
+  if (n == 0) return;
+  B200_DISPATCH_FLOAT(dtype, T,
+                      (binary_same_kernel<T><<<grid_for((n + 7) / 8, 256), 256, 0, s>>>((const T*)a, (const T*)b, (T*)y, n, op, act, aa, ab)));
+}
+void launch_binary(const BinaryParams& p, int dtype, cudaStream_t s) {
+  if (p.n == 0) return;
+  B200_DISPATCH_FLOAT(dtype, T, (binary_bcast_kernel<T><<<grid_for(p.n, 256), 256, 0, s>>>(p)));
+}
+void launch_scale_shift(const void* x, const float* scale, const float* shift, void* y, int64_t rows, int Cp, int dtype, int act,
+                        float aa, float ab, cudaStream_t s) {
+  int64_t total = rows * (Cp / 8);
+  if (total == 0) return;
+  B200_DISPATCH_FLOAT(dtype, T,
+                      (scale_shift_kernel<T><<<grid_for(total, 256), 256, 0, s>>>((const T*)x, scale, shift, (T*)y, rows, Cp, act, aa, ab)));
+}
+void launch_softmax(const void* x, void* y, int64_t outer, int64_t axis, int64_t inner, int dtype, cudaStream_t s) {
+  if (outer * axis * inner == 0) return;
+  if (inner == 1) {
+    int block = axis >= 512 ? 256 : (axis >= 128 ? 128 : 32);
+    B200_DISPATCH_FLOAT(dtype, T, (softmax_rows_kernel<T><<<(unsigned)outer, block, 0, s>>>((const T*)x, (T*)y, outer, axis)));
+  } else {
+    B200_DISPATCH_FLOAT(dtype, T,
+                        (softmax_strided_kernel<T><<<grid_for(outer * inner, 128), 128, 0, s>>>((const T*)x, (T*)y, outer, axis, inner)));
+  }
+}
+void launch_mvn(const void* x, void* y, const float* gamma, const float* beta, int64_t rows, int64_t cols, int normalize_variance,
+                int eps_outside, float eps, int dtype, cudaStream_t s) {
+  if (rows * cols == 0) return;
+  int block = cols >= 1024 ? 256 : (cols >= 256 ? 128 : 32);
+  B200_DISPATCH_FLOAT(dtype, T,
+                      (mvn_rows_kernel<T><<<(unsigned)rows, block, 0, s>>>((const T*)x, (T*)y, gamma, beta, cols, normalize_variance,
+                                                                          eps_outside, eps)));
+}
+void launch_gather_rows(const void* table, const int32_t* idx, void* y, int64_t n_idx, int64_t row_elems, int64_t table_rows, int dtype,
+                        cudaStream_t s) {
+  int64_t total = n_idx * row_elems;
+  if (total == 0) return;
+  if (dtype == B200_I32) {
+    gather_rows_kernel<int32_t><<<grid_for(total, 256), 256, 0, s>>>((const int32_t*)table, idx, (int32_t*)y, n_idx, row_elems, table_rows);
+    return;
+  }
+  B200_DISPATCH_FLOAT(dtype, T,
+                      (gather_rows_kernel<T><<<grid_for(total, 256), 256, 0, s>>>((const T*)table, idx, (T*)y, n_idx, row_elems, table_rows)));
+}
+void launch_reduce(const void* x, void* y, int64_t outer, int64_t axis, int64_t inner, int dtype, int kind, cudaStream_t s) {
+  if (outer * inner == 0) return;
+  B200_DISPATCH_FLOAT(dtype, T,
+                      (reduce_kernel<T><<<grid_for(outer * inner, 128), 128, 0, s>>>((const T*)x, (T*)y, outer, axis, inner, kind)));
+}
+
+template <typename S>
+static void convert4_dst(const void* src, int slayout, void* dst, int ddtype, int dlayout, int N, int C, int H, int W, cudaStream_t s) {
+  int Cd = dlayout == PL_NHWC8 ? (int)round_up(C, 8) : C;
+  int64_t total = (int64_t)N * Cd * H * W;
+  if (total == 0) return;
+  unsigned g = grid_for(total, 256);
+  switch (ddtype) {
+    case B200_F32: convert4_kernel<S, float><<<g, 256, 0, s>>>((const S*)src, slayout, (float*)dst, dlayout, N, C, H, W); break;
+    case B200_F16: convert4_kernel<S, __half><<<g, 256, 0, s>>>((const S*)src, slayout, (__half*)dst, dlayout, N, C, H, W); break;
+    case B200_BF16: convert4_kernel<S, __nv_bfloat16><<<g, 256, 0, s>>>((const S*)src, slayout, (__nv_bfloat16*)dst, dlayout, N, C, H, W); break;
+    case B200_I32: convert4_kernel<S, int32_t><<<g, 256, 0, s>>>((const S*)src, slayout, (int32_t*)dst, dlayout, N, C, H, W); break;
+    case B200_U8: convert4_kernel<S, uint8_t><<<g, 256, 0, s>>>((const S*)src, slayout, (uint8_t*)dst, dlayout, N, C, H, W); break;
+    default: B200_THROW(B200_ERR_UNSUPPORTED, "convert4: dst dtype " << ddtype);
+  }
+}
+void launch_convert4(const void* src, int sdtype, int slayout, void* dst, int ddtype, int dlayout, int N, int C, int H, int W, cudaStream_t s) {
+  switch (sdtype) {
+    case B200_F32: convert4_dst<float>(src, slayout, dst, ddtype, dlayout, N, C, H, W, s); break;
+    case B200_F16: convert4_dst<__half>(src, slayout, dst, ddtype, dlayout, N, C, H, W, s); break;
+    case B200_BF16: convert4_dst<__nv_bfloat16>(src, slayout, dst, ddtype, dlayout, N, C, H, W, s); break;
+    case B200_I32: convert4_dst<int32_t>(src, slayout, dst, ddtype, dlayout, N, C, H, W, s); break;
+    case B200_U8: convert4_dst<uint8_t>(src, slayout, dst, ddtype, dlayout, N, C, H, W, s); break;
+    default: B200_THROW(B200_ERR_UNSUPPORTED, "convert4: src dtype " << sdtype);
+  }
+}
+template <typename S>
+static void convert_flat_dst(const void* src, void* dst, int ddtype, int64_t n, cudaStream_t s) {
+  unsigned g = grid_for(n, 256);
+  switch (ddtype) {
+    case B200_F32: convert_flat_kernel<S, float><<<g, 256, 0, s>>>((const S*)src, (float*)dst, n); break;
+    case B200_F16: convert_flat_kernel<S, __half><<<g, 256, 0, s>>>((const S*)src, (__half*)dst, n); break;
+    case B200_BF16: convert_flat_kernel<S, __nv_bfloat16><<<g, 256, 0, s>>>((const S*)src, (__nv_bfloat16*)dst, n); break;
+    case B200_I32: convert_flat_kernel<S, int32_t><<<g, 256, 0, s>>>((const S*)src, (int32_t*)dst, n); break;
+    case B200_U8: convert_flat_kernel<S, uint8_t><<<g, 256, 0, s>>>((const S*)src, (uint8_t*)dst, n); break;
+    default: B200_THROW(B200_ERR_UNSUPPORTED, "convert: dst dtype " << ddtype);
+  }
+}
+void launch_convert_flat(const void* src, int sdtype, void* dst, int ddtype, int64_t n, cudaStream_t s) {
+  if (n == 0) return;
+  if (sdtype == B200_I32 && ddtype == B200_I32) {
+    copy_i32_kernel<<<grid_for(n, 256), 256, 0, s>>>((const int32_t*)src, (int32_t*)dst, n);
+    return;
+  }
+  switch (sdtype) {
+    case B200_F32: convert_flat_dst<float>(src, dst, ddtype, n, s); break;
+    case B200_F16: convert_flat_dst<__half>(src, dst, ddtype, n, s); break;
+    case B200_BF16: convert_flat_dst<__nv_bfloat16>(src, dst, ddtype, n, s); break;
+    case B200_I32: convert_flat_dst<int32_t>(src, dst, ddtype, n, s); break;
+    case B200_U8: convert_flat_dst<uint8_t>(src, dst, ddtype, n, s); break;
+    default: B200_THROW(B200_ERR_UNSUPPORTED, "convert: src dtype " << sdtype);
+  }
+}
+void launch_permute(const PermuteParams& p, int elem_size, cudaStream_t s) {
+  if (p.n == 0) return;
+  unsigned g = grid_for(p.n, 256);
+  if (elem_size == 4) permute_kernel<uint32_t><<<g, 256, 0, s>>>(p);
+  else if (elem_size == 2) permute_kernel<uint16_t><<<g, 256, 0, s>>>(p);
+  else if (elem_size == 1) permute_kernel<uint8_t><<<g, 256, 0, s>>>(p);
+  else B200_THROW(B200_ERR_UNSUPPORTED, "permute: element size " << elem_size);
+}
+void launch_copy2d(const void* src, int64_t spitch, void* dst, int64_t dpitch, int64_t row_bytes, int64_t rows, cudaStream_t s) {
+  if (row_bytes * rows == 0) return;
+  bool v16 = row_bytes % 16 == 0 && spitch % 16 == 0 && dpitch % 16 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0;
+  bool v4 = row_bytes % 4 == 0 && spitch % 4 == 0 && dpitch % 4 == 0 && (uintptr_t)src % 4 == 0 && (uintptr_t)dst % 4 == 0;
+  bool v2 = row_bytes % 2 == 0 && spitch % 2 == 0 && dpitch % 2 == 0 && (uintptr_t)src % 2 == 0 && (uintptr_t)dst % 2 == 0;
+  if (v16) copy2d_kernel<uint4><<<grid_for(rows * (row_bytes / 16), 256), 256, 0, s>>>((const char*)src, spitch, (char*)dst, dpitch, row_bytes / 16, rows);
+  else if (v4) copy2d_kernel<uint32_t><<<grid_for(rows * (row_bytes / 4), 256), 256, 0, s>>>((const char*)src, spitch, (char*)dst, dpitch, row_bytes / 4, rows);
+  else if (v2) copy2d_kernel<uint16_t><<<grid_for(rows * (row_bytes / 2), 256), 256, 0, s>>>((const char*)src, spitch, (char*)dst, dpitch, row_bytes / 2, rows);
+  else copy2d_kernel<uint8_t><<<grid_for(rows * row_bytes, 256), 256, 0, s>>>((const char*)src, spitch, (char*)dst, dpitch, row_bytes, rows);
+}
+void launch_fill_zero(void* dst, int64_t bytes, cudaStream_t s) {
+  if (bytes > 0) cudaMemsetAsync(dst, 0, (size_t)bytes, s);
+}
+void launch_topk(const float* x, float* vals, int32_t* idx, int64_t outer, int64_t axis, int64_t inner, int k, int mode_min, int sort_mode,
+                 cudaStream_t s) {
+  if (outer * inner == 0) return;
+  int block = axis >= 2048 ? 256 : (axis >= 256 ? 128 : 32);
+  size_t smem = (32 + 32) * 4 + (size_t)k * 8;
+  B200_CHECK(smem <= 48 * 1024, B200_ERR_UNSUPPORTED, "TopK: k=" << k << " too large");
+  topk_kernel<<<(unsigned)(outer * inner), block, smem, s>>>(x, vals, idx, axis, inner, k, mode_min, sort_mode);
+}
+
+}  // namespace b200
