@@ -139,15 +139,17 @@ struct ActSpec {
 };
 int act_from_op(const Node& n, ActSpec& spec);  // returns 1 if n is a fusable activation
 
+struct ArenaBox;
 struct RunCtx {
   char* arena = nullptr;
+  const int64_t* box_offset = nullptr;  // planned offset of every arena box
   char* weights = nullptr;
   std::vector<char*> io_in;
   std::vector<char*> io_out;
   void* stream = nullptr;  // cudaStream_t
   inline char* ptr(const BufRef& r) const {
     switch (r.space) {
-      case SP_ARENA: return arena + r.offset;
+      case SP_ARENA: return arena + box_offset[r.box] + r.offset;
       case SP_WEIGHTS: return weights + r.offset;
       case SP_IO_IN: return io_in[r.index] + r.offset;
       case SP_IO_OUT: return io_out[r.index] + r.offset;

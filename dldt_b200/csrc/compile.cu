@@ -1,0 +1,1271 @@
+// Graph compiler: lowers the op graph built through b200_graph_add into a fused schedule of kernel
+// launches over a statically planned HBM arena.
+//
+// What it mirrors in the reference (structure, not code):
+//   * fusion legality: MKLDNNGraphOptimizer::ApplyCommonGraphOptimizations
+//     (inference-engine/src/mkldnn_plugin/mkldnn_graph_optimizer.cpp:53-148): conv + bias (:150-182),
+//     conv/FC + simple activation (:587-629, :809-852), conv + sum (+ activation) (:958-1130),
+//     MVN + scale/shift (:1132-1168); BatchNorm folding as BatchNormDecomposition + ConvolutionMultiplyFusion
+//     (transformations/op_conversions/batch_norm_decomposition.cpp:33-80, common_optimizations/conv_mul_fusion.cpp:20-80)
+//   * MatMul with constant weights -> FullyConnected (ngraph_transformations/convert_matmul_to_fc_or_gemm.cpp:32-130)
+//   * layout selection + reorder insertion (mkldnn_graph.cpp:455-511): rank-4 activations are NHWC with channels
+//     padded to 8 ("NHWC8") wherever a layout-aware kernel exists, dense row-major elsewhere, conversion kernels
+//     are inserted on demand
+//   * weights are repacked once at compile time (ExecuteConstantNodesOnly, mkldnn_graph.cpp:322-351)
+#include <algorithm>
+#include <cmath>
+#include <set>
+
+#include "engine.h"
+
+namespace b200 {
+
+int64_t LTensor::phys_elems() const {
+  if (layout == L_NHWC8 && shape.size() == 4) return shape[0] * shape[2] * shape[3] * round_up(shape[1], 8);
+  return numel(shape);
+}
+int64_t LTensor::bytes() const { return phys_elems() * (int64_t)dtype_size(dtype); }
+
+namespace {
+
+// ---- host-side scalar conversions ----------------------------------------------------------------
+uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)((u >> 16) | ((u & 0xffff) ? 0x40 : 0));
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+uint16_t f32_to_f16(float f) {
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  uint32_t sign = (x >> 16) & 0x8000u;
+  int32_t exp = (int32_t)((x >> 23) & 0xff) - 127 + 15;
+  uint32_t man = x & 0x7fffffu;
+  if (((x >> 23) & 0xff) == 0xff) return (uint16_t)(sign | 0x7c00u | (man ? 0x200u : 0));
+  if (exp >= 31) return (uint16_t)(sign | 0x7c00u);
+  if (exp <= 0) {
+    if (exp < -10) return (uint16_t)sign;
+    man |= 0x800000u;
+    int shift = 14 - exp;
+    uint32_t r = man >> shift;
+    uint32_t rem = man & ((1u << shift) - 1), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (r & 1))) ++r;
+    return (uint16_t)(sign | r);
+  }
+  uint32_t r = (uint32_t)(exp << 10) | (man >> 13);
+  uint32_t rem = man & 0x1fffu;
+  if (rem > 0x1000u || (rem == 0x1000u && (r & 1))) ++r;
+  return (uint16_t)(sign | r);
+}
+void store_float(uint8_t* dst, int64_t i, float v, int dtype) {
+  if (dtype == B200_F32) reinterpret_cast<float*>(dst)[i] = v;
+  else if (dtype == B200_BF16) reinterpret_cast<uint16_t*>(dst)[i] = f32_to_bf16(v);
+  else reinterpret_cast<uint16_t*>(dst)[i] = f32_to_f16(v);
+}
+
+struct FusedConv {
+  int root = -1;                 // conv / group conv / matmul node
+  std::vector<int> absorbed;     // node ids folded in (in order)
+  std::vector<float> scale, shift;  // per output channel
+  ActSpec act1, act2;
+  int res_value = -1;
+  int out_value = -1;            // value produced by the last absorbed node
+  int emit_at = -1;              // node id at whose position the kernel is emitted
+};
+struct FusedMvn {
+  int root = -1;
+  std::vector<int> absorbed;
+  int gamma_value = -1, beta_value = -1;
+  int out_value = -1, emit_at = -1;
+};
+struct FusedElt {  // binary / unary followed by one activation
+  int root = -1;
+  ActSpec act;
+  int out_value = -1, emit_at = -1;
+  int absorbed = -1;
+};
+
+class Lowerer {
+ public:
+  Lowerer(const b200_graph& g, const b200_compile_options& o, b200_network& n) : g_(g), opts_(o), net_(n) {
+    cd_ = o.precision == B200_PREC_BF16 ? B200_BF16 : (o.precision == B200_PREC_FP16 ? B200_F16 : B200_F32);
+    net_.cdtype = cd_;
+    net_.precision = o.precision;
+    use_tc_ = cd_ != B200_F32 && o.conv_impl == 0;
+  }
+  void run();
+
+ private:
+  const b200_graph& g_;
+  const b200_compile_options& opts_;
+  b200_network& net_;
+  int cd_;
+  bool use_tc_;
+  std::map<int, LTensor> vt_;                       // value -> primary lowered tensor
+  std::map<std::pair<int, int>, LTensor> alt_;      // (value, layout) -> converted copy
+  std::vector<int> absorbed_by_;                    // node -> fused record owner (-1 none)
+  std::map<int, FusedConv> fconv_;                  // emit_at -> record
+  std::map<int, FusedMvn> fmvn_;
+  std::map<int, FusedElt> felt_;
+
+  // ---- small helpers ----
+  const Node& node(int id) const { return g_.nodes[id]; }
+  const Value& val(int id) const { return g_.values[id]; }
+  const Node* const_node(int value) const {
+    const Node& p = node(val(value).producer);
+    return p.op == B200_OP_CONSTANT ? &p : nullptr;
+  }
+  int storage_dtype(int graph_dtype) const { return dtype_is_float(graph_dtype) ? cd_ : (graph_dtype == B200_I64 ? B200_I32 : graph_dtype); }
+  std::vector<float> const_floats(int value) const {
+    const Node* c = const_node(value);
+    B200_CHECK(c, B200_ERR_UNSUPPORTED, "expected a constant input for value " << val(value).name);
+    int64_t n = numel(c->shape);
+    std::vector<float> out(n);
+    if (c->dtype == B200_F32) memcpy(out.data(), c->data.data(), n * 4);
+    else if (c->dtype == B200_I32) for (int64_t i = 0; i < n; ++i) out[i] = (float)reinterpret_cast<const int32_t*>(c->data.data())[i];
+    else for (int64_t i = 0; i < n; ++i) out[i] = (float)c->data[i];
+    return out;
+  }
+  int new_box(int64_t bytes, bool pinned = false) {
+    ArenaBox b;
+    b.bytes = round_up(std::max<int64_t>(bytes, 16), 1024);
+    b.pinned = pinned;
+    net_.boxes.push_back(b);
+    return (int)net_.boxes.size() - 1;
+  }
+  LTensor alloc(const Shape& shape, int dtype, int layout, bool pinned = false) {
+    LTensor t;
+    t.shape = shape; t.dtype = dtype; t.layout = layout;
+    t.buf.space = SP_ARENA;
+    t.buf.box = new_box(t.bytes(), pinned);
+    return t;
+  }
+  int64_t add_weights(const void* data, int64_t bytes) {
+    int64_t off = round_up((int64_t)net_.weights_host.size(), 1024);
+    net_.weights_host.resize(off + round_up(bytes, 16));
+    if (data) memcpy(net_.weights_host.data() + off, data, bytes);
+    return off;
+  }
+  BufRef weights_ref(int64_t off) { BufRef r; r.space = SP_WEIGHTS; r.offset = off; return r; }
+  // fp32 per-channel vector in the weights blob
+  BufRef add_f32_vector(const std::vector<float>& v) { return weights_ref(add_weights(v.data(), (int64_t)v.size() * 4)); }
+
+  void emit(Step&& s, std::initializer_list<const LTensor*> reads, std::initializer_list<const LTensor*> writes) {
+    for (auto* t : reads) if (t && t->buf.space == SP_ARENA) s.reads.push_back(t->buf.box);
+    for (auto* t : writes) if (t && t->buf.space == SP_ARENA) s.writes.push_back(t->buf.box);
+    if (writes.size()) {
+      s.out = **writes.begin();
+      s.out_precision = dtype_name(s.out.dtype);
+      s.out_layout = s.out.layout == L_NHWC8 ? "nhwc8" : "rowmajor";
+    }
+    net_.flops += s.flops;
+    net_.bytes += s.bytes;
+    net_.steps.push_back(std::move(s));
+  }
+
+  // ---- tensors ----
+  LTensor materialize_const(int value, int layout);
+  LTensor get(int value, int layout /* -1 any */);
+  LTensor to_dtype(const LTensor& t, int dtype, const std::string& why);
+  void set(int value, const LTensor& t) { vt_[value] = t; }
+  bool prefers_nhwc8(int value) const;
+
+  // ---- passes ----
+  void fuse();
+  bool per_channel_const(int value, int64_t C, bool matmul_style, std::vector<float>& out) const;
+  void lower_node(const Node& n);
+  void lower_conv(const FusedConv& f);
+  void lower_matmul_general(const Node& n, const FusedConv* f);
+  void lower_binary(const Node& n, const ActSpec& act, int out_value);
+  void lower_unary(const Node& n, const ActSpec& act);
+  void lower_pool(const Node& n);
+  void lower_reduce(const Node& n);
+  void lower_mvn(const Node& n, const FusedMvn* f);
+  void lower_concat(const Node& n);
+  void lower_split(const Node& n);
+  void lower_transpose(const Node& n);
+  void lower_detection(const Node& n);
+  void conv_launch_step(const std::string& name, const std::string& type, const std::string& fused, ConvParams p, BufRef x, BufRef w,
+                        BufRef bias, BufRef res, BufRef y, const LTensor* tx, const LTensor* tres, const LTensor* ty, double flops,
+                        double bytes, bool tc);
+};
+
+bool Lowerer::prefers_nhwc8(int value) const {
+  const Value& v = val(value);
+  if (v.shape.size() != 4 || !dtype_is_float(v.dtype)) return false;
+  for (int c : v.consumers) {
+    int op = node(c).op;
+    if (op == B200_OP_CONVOLUTION || op == B200_OP_GROUP_CONVOLUTION || op == B200_OP_MAX_POOL || op == B200_OP_AVG_POOL ||
+        op == B200_OP_BATCH_NORM)
+      return true;
+  }
+  return false;
+}
+
+LTensor Lowerer::materialize_const(int value, int layout) {
+  const Node* c = const_node(value);
+  LTensor t;
+  t.shape = c->shape;
+  t.dtype = storage_dtype(c->dtype);
+  t.layout = (layout == L_NHWC8 && c->shape.size() == 4 && dtype_is_float(c->dtype)) ? L_NHWC8 : L_ROWMAJOR;
+  int64_t n = numel(c->shape);
+  std::vector<uint8_t> buf(std::max<int64_t>(t.bytes(), 16), 0);
+  if (dtype_is_float(c->dtype)) {
+    const float* src = reinterpret_cast<const float*>(c->data.data());
+    if (t.layout == L_NHWC8) {
+      int64_t N = t.shape[0], C = t.shape[1], H = t.shape[2], W = t.shape[3], Cp = round_up(C, 8);
+      for (int64_t in = 0; in < N; ++in)
+        for (int64_t ic = 0; ic < C; ++ic)
+          for (int64_t h = 0; h < H; ++h)
+            for (int64_t w = 0; w < W; ++w)
+              store_float(buf.data(), ((in * H + h) * W + w) * Cp + ic, src[((in * C + ic) * H + h) * W + w], t.dtype);
+    } else {
+      for (int64_t i = 0; i < n; ++i) store_float(buf.data(), i, src[i], t.dtype);
+    }
+  } else {
+    memcpy(buf.data(), c->data.data(), std::min<size_t>(buf.size(), c->data.size()));
+  }
+  t.buf = weights_ref(add_weights(buf.data(), (int64_t)buf.size()));
+  return t;
+}
+
+LTensor Lowerer::get(int value, int layout) {
+  auto it = vt_.find(value);
+  if (it == vt_.end()) {
+    B200_CHECK(const_node(value), B200_ERR_INVALID, "value '" << val(value).name << "' used before it is produced");
+    auto key = std::make_pair(value, layout == L_NHWC8 ? L_NHWC8 : L_ROWMAJOR);
+    auto a = alt_.find(key);
+    if (a != alt_.end()) return a->second;
+    LTensor t = materialize_const(value, layout);
+    alt_[std::make_pair(value, t.layout)] = t;
+    return t;
+  }
+  LTensor t = it->second;
+  if (layout < 0 || t.layout == layout) return t;
+  auto a = alt_.find(std::make_pair(value, layout));
+  if (a != alt_.end()) return a->second;
+  B200_CHECK(t.shape.size() == 4, B200_ERR_INVALID, "layout conversion needs rank 4 (" << val(value).name << ")");
+  const int64_t N = t.shape[0], C = t.shape[1], H = t.shape[2], W = t.shape[3];
+  LTensor o;
+  if (layout == L_ROWMAJOR && H == 1 && W == 1 && C % 8 == 0) {  // [N,1,1,C] NHWC8 is bit-identical to [N,C,1,1] dense
+    o = t;
+    o.layout = L_ROWMAJOR;
+  } else if (layout == L_NHWC8 && H == 1 && W == 1 && C % 8 == 0) {
+    o = t;
+    o.layout = L_NHWC8;
+  } else {
+    o = alloc(t.shape, t.dtype, layout);
+    Step s;
+    s.name = val(value).name + (layout == L_NHWC8 ? "_to_nhwc8" : "_to_nchw");
+    s.type = "Reorder";
+    s.impl = layout == L_NHWC8 ? "nchw_to_nhwc8" : "nhwc8_to_nchw";
+    s.bytes = (double)t.bytes() + (double)o.bytes();
+    BufRef src = t.buf, dst = o.buf;
+    int dt = t.dtype, sl = t.layout == L_NHWC8 ? PL_NHWC8 : PL_ROWMAJOR, dl = layout == L_NHWC8 ? PL_NHWC8 : PL_ROWMAJOR;
+    s.launch = [=](const RunCtx& c) {
+      launch_convert4(c.ptr(src), dt, sl, c.ptr(dst), dt, dl, (int)N, (int)C, (int)H, (int)W, (cudaStream_t)c.stream);
+    };
+    emit(std::move(s), {&t}, {&o});
+  }
+  alt_[std::make_pair(value, layout)] = o;
+  return o;
+}
+
+LTensor Lowerer::to_dtype(const LTensor& t, int dtype, const std::string& why) {
+  if (t.dtype == dtype) return t;
+  B200_CHECK(t.layout == L_ROWMAJOR, B200_ERR_INVALID, "dtype conversion expects row-major tensor");
+  LTensor o = alloc(t.shape, dtype, L_ROWMAJOR);
+  Step s;
+  s.name = why + "_convert";
+  s.type = "Convert";
+  s.impl = std::string(dtype_name(t.dtype)) + "_to_" + dtype_name(dtype);
+  s.bytes = (double)t.bytes() + (double)o.bytes();
+  BufRef src = t.buf, dst = o.buf;
+  int sd = t.dtype;
+  int64_t n = numel(t.shape);
+  s.launch = [=](const RunCtx& c) { launch_convert_flat(c.ptr(src), sd, c.ptr(dst), dtype, n, (cudaStream_t)c.stream); };
+  emit(std::move(s), {&t}, {&o});
+  return o;
+}
+
+// Is `value` a constant that broadcasts per output channel?  conv style: scalar, [C,1,1], [1,C,1,1];
+// matmul style: scalar, [N], [1,N], [1,1,N] ...
+bool Lowerer::per_channel_const(int value, int64_t C, bool matmul_style, std::vector<float>& out) const {
+  const Node* c = const_node(value);
+  if (!c || !(dtype_is_float(c->dtype) || c->dtype == B200_I32)) return false;
+  int64_t n = numel(c->shape);
+  std::vector<float> v = const_floats(value);
+  if (n == 1) { out.assign(C, v[0]); return true; }
+  if (n != C) return false;
+  const Shape& s = c->shape;
+  if (matmul_style) {
+    if (s.back() != C) return false;
+  } else {
+    // the C extent must sit at the channel position counting from the right: [.., C, 1, 1]
+    if (s.size() < 3 || s[s.size() - 3] != C) return false;
+  }
+  out = v;
+  return true;
+}
+
+void Lowerer::fuse() {
+  absorbed_by_.assign(g_.nodes.size(), -1);
+  auto single_consumer = [&](int value) -> int {
+    const Value& v = val(value);
+    return v.consumers.size() == 1 ? v.consumers[0] : -1;
+  };
+  for (const Node& n : g_.nodes) {
+    if (absorbed_by_[n.id] >= 0) continue;
+    bool is_conv = n.op == B200_OP_CONVOLUTION || n.op == B200_OP_GROUP_CONVOLUTION;
+    bool is_fc = n.op == B200_OP_MATMUL && const_node(n.inputs[1]) != nullptr && n.i[0] == 0;
+    bool is_mm = n.op == B200_OP_MATMUL && !is_fc;
+    if (is_conv && !const_node(n.inputs[1])) continue;  // dynamic weights: not supported by the fused path
+    if (is_conv || is_fc || is_mm) {
+      FusedConv f;
+      f.root = n.id;
+      const Shape& os = val(n.outputs[0]).shape;
+      const int64_t C = is_conv ? os[1] : os.back();
+      f.scale.assign(C, 1.f);
+      f.shift.assign(C, 0.f);
+      bool dw = false;
+      if (n.op == B200_OP_GROUP_CONVOLUTION) {
+        const Shape& w = val(n.inputs[1]).shape;
+        dw = w[1] == 1 && w[2] == 1;
+      }
+      int cur = n.outputs[0];
+      bool pre = true;  // still allowed to fold linear per-channel ops into weights/bias
+      while (true) {
+        int u = single_consumer(cur);
+        if (u < 0 || absorbed_by_[u] >= 0) break;
+        const Node& U = node(u);
+        std::vector<float> cv;
+        ActSpec as;
+        if (pre && !is_mm && U.op == B200_OP_BATCH_NORM && U.inputs[0] == cur && const_node(U.inputs[1]) && const_node(U.inputs[2]) &&
+            const_node(U.inputs[3]) && const_node(U.inputs[4]) && is_conv) {
+          auto ga = const_floats(U.inputs[1]), be = const_floats(U.inputs[2]), mu = const_floats(U.inputs[3]), va = const_floats(U.inputs[4]);
+          if ((int64_t)ga.size() != C) break;
+          for (int64_t c = 0; c < C; ++c) {
+            float gsc = ga[c] / std::sqrt(va[c] + U.f[0]);
+            f.scale[c] *= gsc;
+            f.shift[c] = f.shift[c] * gsc + (be[c] - mu[c] * gsc);
+          }
+        } else if (pre && !is_mm && (U.op == B200_OP_MULTIPLY || U.op == B200_OP_ADD || U.op == B200_OP_SUBTRACT) &&
+                   per_channel_const(U.inputs[0] == cur ? U.inputs[1] : U.inputs[0], C, !is_conv, cv) &&
+                   !(U.op == B200_OP_SUBTRACT && U.inputs[0] != cur) && val(U.outputs[0]).shape == val(cur).shape) {
+          for (int64_t c = 0; c < C; ++c) {
+            if (U.op == B200_OP_MULTIPLY) { f.scale[c] *= cv[c]; f.shift[c] *= cv[c]; }
+            else if (U.op == B200_OP_ADD) f.shift[c] += cv[c];
+            else f.shift[c] -= cv[c];
+          }
+        } else if (act_from_op(U, as) && f.res_value < 0 && f.act1.kind == ACT_NONE && !(U.op == B200_OP_SWISH && U.inputs.size() > 1)) {
+          f.act1 = as;
+          pre = false;
+        } else if (act_from_op(U, as) && f.res_value >= 0 && f.act2.kind == ACT_NONE && !(U.op == B200_OP_SWISH && U.inputs.size() > 1)) {
+          f.act2 = as;
+          f.absorbed.push_back(u);
+          absorbed_by_[u] = n.id;
+          cur = U.outputs[0];
+          break;
+        } else if (U.op == B200_OP_ADD && f.res_value < 0 && !dw && U.inputs[0] != U.inputs[1]) {
+          int other = U.inputs[0] == cur ? U.inputs[1] : U.inputs[0];
+          if (const_node(other) || val(other).shape != val(cur).shape || val(U.outputs[0]).shape != val(cur).shape) break;
+          f.res_value = other;
+          pre = false;
+        } else {
+          break;
+        }
+        f.absorbed.push_back(u);
+        absorbed_by_[u] = n.id;
+        cur = U.outputs[0];
+      }
+      f.out_value = cur;
+      f.emit_at = f.absorbed.empty() ? n.id : f.absorbed.back();
+      absorbed_by_[n.id] = n.id;
+      fconv_[f.emit_at] = f;
+      continue;
+    }
+    if (n.op == B200_OP_MVN) {
+      FusedMvn f;
+      f.root = n.id;
+      const Shape& xs = val(n.inputs[0]).shape;
+      int cur = n.outputs[0];
+      int na = n.i[2];
+      // only a normalisation over the last axis can take per-element gamma/beta of that axis
+      bool last_axis_only = na == 1 && ((n.i[3] < 0 ? n.i[3] + (int)xs.size() : n.i[3]) == (int)xs.size() - 1);
+      if (last_axis_only) {
+        int u = single_consumer(cur);
+        std::vector<float> cv;
+        if (u >= 0 && absorbed_by_[u] < 0 && node(u).op == B200_OP_MULTIPLY) {
+          const Node& U = node(u);
+          int other = U.inputs[0] == cur ? U.inputs[1] : U.inputs[0];
+          if (per_channel_const(other, xs.back(), true, cv) && val(U.outputs[0]).shape == xs) {
+            f.gamma_value = other; f.absorbed.push_back(u); absorbed_by_[u] = n.id; cur = U.outputs[0];
+            int u2 = single_consumer(cur);
+            if (u2 >= 0 && absorbed_by_[u2] < 0 && node(u2).op == B200_OP_ADD) {
+              const Node& U2 = node(u2);
+              int o2 = U2.inputs[0] == cur ? U2.inputs[1] : U2.inputs[0];
+              if (per_channel_const(o2, xs.back(), true, cv) && val(U2.outputs[0]).shape == xs) {
+                f.beta_value = o2; f.absorbed.push_back(u2); absorbed_by_[u2] = n.id; cur = U2.outputs[0];
+              }
+            }
+          }
+        }
+      }
+      f.out_value = cur;
+      f.emit_at = f.absorbed.empty() ? n.id : f.absorbed.back();
+      absorbed_by_[n.id] = n.id;
+      fmvn_[f.emit_at] = f;
+      continue;
+    }
+    if (is_binary_eltwise(n.op) || n.op == B200_OP_BATCH_NORM) {
+      FusedElt f;
+      f.root = n.id;
+      f.out_value = n.outputs[0];
+      f.emit_at = n.id;
+      int u = single_consumer(n.outputs[0]);
+      ActSpec as;
+      if (u >= 0 && absorbed_by_[u] < 0 && act_from_op(node(u), as) && !(node(u).op == B200_OP_SWISH && node(u).inputs.size() > 1)) {
+        f.act = as; f.absorbed = u; absorbed_by_[u] = n.id; f.out_value = node(u).outputs[0]; f.emit_at = u;
+      }
+      absorbed_by_[n.id] = n.id;
+      felt_[f.emit_at] = f;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+void Lowerer::conv_launch_step(const std::string& name, const std::string& type, const std::string& fused, ConvParams p, BufRef x, BufRef w,
+                               BufRef bias, BufRef res, BufRef y, const LTensor* tx, const LTensor* tres, const LTensor* ty, double flops,
+                               double bytes, bool tc) {
+  Step s;
+  s.name = name; s.type = type; s.fused = fused; s.flops = flops; s.bytes = bytes;
+  const int dt = cd_;
+  int bn = 0;
+  if (tc) {
+    bn = conv_tc_pick_bn(p.Cout_p);
+    s.impl = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_128x" + std::to_string(bn) + "x64";
+  } else {
+    s.impl = "simt_fp32_128x64x16";
+  }
+  const bool has_res = res.space != SP_NONE;
+  s.launch = [=](const RunCtx& c) {
+    ConvParams q = p;
+    q.x = c.ptr(x); q.w = c.ptr(w); q.bias = reinterpret_cast<const float*>(c.ptr(bias));
+    q.res = has_res ? c.ptr(res) : nullptr;
+    q.y = c.ptr(y);
+    if (tc) launch_conv_tc(q, dt, bn, (cudaStream_t)c.stream);
+    else launch_conv_f32(q, (cudaStream_t)c.stream);
+  };
+  emit(std::move(s), {tx, tres}, {ty});
+}
+
+void Lowerer::lower_conv(const FusedConv& f) {
+  const Node& n = node(f.root);
+  std::string fused = n.name;
+  for (int a : f.absorbed) fused += "," + node(a).name;
+  const std::string out_name = val(f.out_value).name;
+
+  if (n.op == B200_OP_MATMUL) {
+    if (!const_node(n.inputs[1])) { lower_matmul_general(n, &f); return; }
+    // ---- FullyConnected: Y[M,N] = X[M,K] * W^T (+bias, act, residual) ----
+    LTensor x = get(n.inputs[0], L_ROWMAJOR);
+    const Shape& ws = val(n.inputs[1]).shape;
+    B200_CHECK(ws.size() == 2, B200_ERR_UNSUPPORTED, "MatMul '" << n.name << "': constant weights must be 2-D");
+    const bool tb = n.i[1] != 0;
+    const int64_t K = tb ? ws[1] : ws[0], Nn = tb ? ws[0] : ws[1];
+    B200_CHECK(x.shape.back() == K, B200_ERR_INVALID, "MatMul '" << n.name << "': K mismatch");
+    B200_CHECK(K % 8 == 0, B200_ERR_UNSUPPORTED, "MatMul '" << n.name << "': K=" << K << " must be a multiple of 8");
+    const int64_t M = numel(x.shape) / K;
+    const bool tc = use_tc_;
+    const int64_t Np = round_up(Nn, 8);
+    const int bn = tc ? conv_tc_pick_bn((int)Np) : 64;
+    const int64_t Nalloc = round_up(Np, bn), Ktot = round_up(K, 64);
+    std::vector<float> wsrc = const_floats(n.inputs[1]);
+    std::vector<uint8_t> wp((size_t)(Nalloc * Ktot) * dtype_size(cd_), 0);
+    for (int64_t o = 0; o < Nn; ++o)
+      for (int64_t k = 0; k < K; ++k) store_float(wp.data(), o * Ktot + k, (tb ? wsrc[o * K + k] : wsrc[k * Nn + o]) * f.scale[o], cd_);
+    std::vector<float> bias(Nalloc, 0.f);
+    for (int64_t o = 0; o < Nn; ++o) bias[o] = f.shift[o];
+    BufRef wref = weights_ref(add_weights(wp.data(), (int64_t)wp.size()));
+    BufRef bref = add_f32_vector(bias);
+    Shape oshape = val(f.out_value).shape;
+    LTensor out_dense = alloc(oshape, cd_, L_ROWMAJOR);
+    LTensor out_k = out_dense;
+    if (Nn % 8 != 0) {  // kernel rows are 16-byte granular: write a padded scratch, then compact
+      Shape ps = {M, Np};
+      out_k = alloc(ps, cd_, L_ROWMAJOR);
+    }
+    LTensor res;
+    BufRef rref;
+    if (f.res_value >= 0) {
+      B200_CHECK(Nn % 8 == 0, B200_ERR_UNSUPPORTED, "FC residual with N % 8 != 0");
+      res = get(f.res_value, L_ROWMAJOR);
+      rref = res.buf;
+    }
+    ConvParams p;
+    p.N = (int)M; p.H = p.W = p.Ho = p.Wo = 1; p.Cin_p = (int)K; p.Cout_p = (int)Np;
+    p.M = (int)M; p.Ktot = (int)Ktot; p.Cout_alloc = (int)Nalloc; p.ldy = (int)Np;
+    p.w_ld = (int)Ktot; p.w_rows = (int)Nalloc; p.w_k = (int)Ktot;
+    p.act1 = f.act1.kind; p.a1 = f.act1.a; p.b1 = f.act1.b; p.act2 = f.act2.kind; p.a2 = f.act2.a; p.b2 = f.act2.b;
+    double flops = 2.0 * M * K * Nn;
+    double bytes = (double)x.bytes() + (double)out_dense.bytes() + (double)Nn * K * dtype_size(cd_) + (f.res_value >= 0 ? (double)out_dense.bytes() : 0);
+    conv_launch_step(out_name, "FullyConnected", fused, p, x.buf, wref, bref, rref, out_k.buf, &x, f.res_value >= 0 ? &res : nullptr, &out_k,
+                     flops, bytes, tc);
+    if (Nn % 8 != 0) {
+      Step s;
+      s.name = out_name + "_compact"; s.type = "Reorder"; s.impl = "copy2d";
+      BufRef src = out_k.buf, dst = out_dense.buf;
+      int64_t es = dtype_size(cd_);
+      s.launch = [=](const RunCtx& c) { launch_copy2d(c.ptr(src), Np * es, c.ptr(dst), Nn * es, Nn * es, M, (cudaStream_t)c.stream); };
+      emit(std::move(s), {&out_k}, {&out_dense});
+    }
+    set(f.out_value, out_dense);
+    return;
+  }
+
+  // ---- Convolution / GroupConvolution ----
+  LTensor x = get(n.inputs[0], L_NHWC8);
+  const Shape& xs = x.shape;
+  const Shape& ws = val(n.inputs[1]).shape;
+  const Shape os = val(n.outputs[0]).shape;
+  const bool grouped = n.op == B200_OP_GROUP_CONVOLUTION;
+  const int64_t G = grouped ? ws[0] : 1;
+  const int64_t Og = grouped ? ws[1] : ws[0], Ig = grouped ? ws[2] : ws[1];
+  const int64_t kh = ws[grouped ? 3 : 2], kw = ws[grouped ? 4 : 3];
+  const int64_t Cin = xs[1], Cout = os[1], Cin_p = round_up(Cin, 8), Cout_p = round_up(Cout, 8);
+  std::vector<float> wsrc = const_floats(n.inputs[1]);
+  LTensor out = alloc(val(f.out_value).shape, cd_, L_NHWC8);
+  const int64_t Mrows = os[0] * os[2] * os[3];
+
+  if (grouped && Og == 1 && Ig == 1) {
+    // depthwise: weights [tap][Cp]
+    std::vector<uint8_t> wp((size_t)(kh * kw * Cin_p) * dtype_size(cd_), 0);
+    for (int64_t c = 0; c < Cout; ++c)
+      for (int64_t t = 0; t < kh * kw; ++t) store_float(wp.data(), t * Cin_p + c, wsrc[c * kh * kw + t] * f.scale[c], cd_);
+    std::vector<float> bias(Cout_p, 0.f);
+    for (int64_t c = 0; c < Cout; ++c) bias[c] = f.shift[c];
+    BufRef wref = weights_ref(add_weights(wp.data(), (int64_t)wp.size()));
+    BufRef bref = add_f32_vector(bias);
+    DwParams p{};
+    p.N = (int)xs[0]; p.H = (int)xs[2]; p.W = (int)xs[3]; p.Cp = (int)Cin_p; p.Ho = (int)os[2]; p.Wo = (int)os[3];
+    p.kh = (int)kh; p.kw = (int)kw; p.sh = n.i[0]; p.sw = n.i[1]; p.dh = n.i[2]; p.dw = n.i[3]; p.pt = n.i[4]; p.pl = n.i[5];
+    p.act = f.act1.kind; p.a = f.act1.a; p.b = f.act1.b;
+    Step s;
+    s.name = out_name; s.type = "Convolution"; s.impl = "dw_nhwc8_cuda_core"; s.fused = fused;
+    s.flops = 2.0 * Mrows * Cout * kh * kw;
+    s.bytes = (double)x.bytes() + (double)out.bytes() + (double)wp.size();
+    BufRef xr = x.buf, yr = out.buf;
+    int dt = cd_;
+    s.launch = [=](const RunCtx& c) {
+      DwParams q = p;
+      q.x = c.ptr(xr); q.w = c.ptr(wref); q.bias = reinterpret_cast<const float*>(c.ptr(bref)); q.y = c.ptr(yr);
+      launch_dwconv(q, dt, (cudaStream_t)c.stream);
+    };
+    emit(std::move(s), {&x}, {&out});
+    set(f.out_value, out);
+    return;
+  }
+
+  const bool tc = use_tc_;
+  const int bn = tc ? conv_tc_pick_bn((int)Cout_p) : 64;
+  const int64_t Cout_alloc = round_up(Cout_p, bn);
+  const int64_t Ktot = round_up(kh * kw * Cin_p, 64);
+  std::vector<uint8_t> wp((size_t)(Cout_alloc * Ktot) * dtype_size(cd_), 0);
+  // K order = (filter row, filter col, padded input channel); grouped convs become block diagonal
+  for (int64_t o = 0; o < Cout; ++o) {
+    int64_t grp = o / Og;
+    for (int64_t ig = 0; ig < Ig; ++ig) {
+      int64_t ci = grp * Ig + ig;
+      for (int64_t r = 0; r < kh; ++r)
+        for (int64_t s2 = 0; s2 < kw; ++s2) {
+          float v = grouped ? wsrc[(((grp * Og + (o % Og)) * Ig + ig) * kh + r) * kw + s2] : wsrc[((o * Ig + ig) * kh + r) * kw + s2];
+          store_float(wp.data(), o * Ktot + (r * kw + s2) * Cin_p + ci, v * f.scale[o], cd_);
+        }
+    }
+  }
+  std::vector<float> bias(Cout_alloc, 0.f);
+  for (int64_t o = 0; o < Cout; ++o) bias[o] = f.shift[o];
+  BufRef wref = weights_ref(add_weights(wp.data(), (int64_t)wp.size()));
+  BufRef bref = add_f32_vector(bias);
+  LTensor res;
+  BufRef rref;
+  if (f.res_value >= 0) { res = get(f.res_value, L_NHWC8); rref = res.buf; }
+  ConvParams p;
+  p.N = (int)xs[0]; p.H = (int)xs[2]; p.W = (int)xs[3]; p.Cin_p = (int)Cin_p; p.Ho = (int)os[2]; p.Wo = (int)os[3]; p.Cout_p = (int)Cout_p;
+  p.kh = (int)kh; p.kw = (int)kw; p.sh = n.i[0]; p.sw = n.i[1]; p.dh = n.i[2]; p.dw = n.i[3]; p.pt = n.i[4]; p.pl = n.i[5];
+  p.M = (int)Mrows; p.Ktot = (int)Ktot; p.Cout_alloc = (int)Cout_alloc; p.ldy = (int)Cout_p;
+  p.w_ld = (int)Ktot; p.w_rows = (int)Cout_alloc; p.w_k = (int)Ktot;
+  p.act1 = f.act1.kind; p.a1 = f.act1.a; p.b1 = f.act1.b; p.act2 = f.act2.kind; p.a2 = f.act2.a; p.b2 = f.act2.b;
+  B200_CHECK(Mrows < (1ll << 31) && Mrows * Cout_p < (1ll << 40), B200_ERR_UNSUPPORTED, "conv too large");
+  double flops = 2.0 * Mrows * Cout * (Cin / G) * kh * kw;
+  double bytes = (double)x.bytes() + (double)out.bytes() + (double)Cout * (Cin / G) * kh * kw * dtype_size(cd_) +
+                 (f.res_value >= 0 ? (double)out.bytes() : 0);
+  conv_launch_step(out_name, "Convolution", fused, p, x.buf, wref, bref, rref, out.buf, &x, f.res_value >= 0 ? &res : nullptr, &out, flops,
+                   bytes, tc);
+  set(f.out_value, out);
+}
+
+// MatMul of two activations (attention scores / context): batched GEMM through the same kernels.
+// A must be [.., M, K] row-major and B [.., N, K] (K-major); transposes are materialised with the
+// permute kernel where the flags say otherwise (nodes/mkldnn_matmul_node.cpp:225-262 loops a gemm
+// over the batch dims the same way).
+void Lowerer::lower_matmul_general(const Node& n, const FusedConv* f) {
+  LTensor a = get(n.inputs[0], L_ROWMAJOR), b = get(n.inputs[1], L_ROWMAJOR);
+  B200_CHECK(a.shape.size() >= 2 && b.shape.size() >= 2, B200_ERR_UNSUPPORTED, "MatMul '" << n.name << "': rank < 2");
+  auto permute_last2 = [&](const LTensor& t, const std::string& nm) {
+    Shape os = t.shape;
+    std::swap(os[os.size() - 1], os[os.size() - 2]);
+    LTensor o = alloc(os, t.dtype, L_ROWMAJOR);
+    PermuteParams pp{};
+    pp.rank = (int)os.size();
+    pp.n = numel(os);
+    std::vector<int64_t> istr(os.size());
+    int64_t st = 1;
+    for (int d = (int)t.shape.size() - 1; d >= 0; --d) { istr[d] = st; st *= t.shape[d]; }
+    for (size_t d = 0; d < os.size(); ++d) pp.oshape[d] = os[d];
+    for (size_t d = 0; d < os.size(); ++d) pp.istride[d] = istr[d];
+    std::swap(pp.istride[os.size() - 1], pp.istride[os.size() - 2]);
+    Step s;
+    s.name = nm; s.type = "Transpose"; s.impl = "permute";
+    s.bytes = 2.0 * (double)t.bytes();
+    BufRef src = t.buf, dst = o.buf;
+    int es = (int)dtype_size(t.dtype);
+    s.launch = [=](const RunCtx& c) { PermuteParams q = pp; q.x = c.ptr(src); q.y = c.ptr(dst); launch_permute(q, es, (cudaStream_t)c.stream); };
+    emit(std::move(s), {&t}, {&o});
+    return o;
+  };
+  if (n.i[0]) a = permute_last2(a, n.name + "_At");
+  if (!n.i[1]) b = permute_last2(b, n.name + "_Bt");   // need [.., N, K]
+  const int64_t M = a.shape[a.shape.size() - 2], K = a.shape.back(), Nn = b.shape[b.shape.size() - 2];
+  B200_CHECK(b.shape.back() == K, B200_ERR_INVALID, "MatMul '" << n.name << "': K mismatch");
+  B200_CHECK(K % 8 == 0 && Nn % 8 == 0, B200_ERR_UNSUPPORTED, "MatMul '" << n.name << "': K and N must be multiples of 8");
+  const int64_t batch_a = numel(a.shape) / (M * K), batch_b = numel(b.shape) / (Nn * K);
+  B200_CHECK(batch_a == batch_b || batch_b == 1, B200_ERR_UNSUPPORTED, "MatMul '" << n.name << "': unsupported batch broadcast");
+  B200_CHECK(batch_a <= 65535, B200_ERR_UNSUPPORTED, "MatMul batch too large");
+  const int out_value = f ? f->out_value : n.outputs[0];
+  LTensor out = alloc(val(out_value).shape, cd_, L_ROWMAJOR);
+  const bool tc = use_tc_;
+  const int bn = tc ? conv_tc_pick_bn((int)Nn) : 64;
+  std::vector<float> bias(round_up(Nn, bn), 0.f);
+  BufRef bref = add_f32_vector(bias);
+  ConvParams p;
+  p.N = (int)M; p.H = p.W = p.Ho = p.Wo = 1; p.Cin_p = (int)K; p.Cout_p = (int)Nn;
+  p.M = (int)M; p.Ktot = (int)round_up(K, 64); p.Cout_alloc = (int)round_up(Nn, bn); p.ldy = (int)Nn;
+  p.w_ld = (int)K; p.w_rows = (int)Nn; p.w_k = (int)K;
+  p.batch = (int)batch_a; p.x_bs = M * K; p.w_bs = batch_b == 1 ? 0 : Nn * K; p.y_bs = M * Nn;
+  LTensor res;
+  BufRef rref;
+  std::string fused = n.name;
+  if (f) {
+    p.act1 = f->act1.kind; p.a1 = f->act1.a; p.b1 = f->act1.b; p.act2 = f->act2.kind; p.a2 = f->act2.a; p.b2 = f->act2.b;
+    if (f->res_value >= 0) { res = get(f->res_value, L_ROWMAJOR); rref = res.buf; }
+    for (int ab : f->absorbed) fused += "," + node(ab).name;
+  }
+  double flops = 2.0 * batch_a * M * K * Nn;
+  double bytes = (double)a.bytes() + (double)b.bytes() + (double)out.bytes();
+  conv_launch_step(val(out_value).name, "MatMul", fused, p, a.buf, b.buf, bref, rref, out.buf, &a, (f && f->res_value >= 0) ? &res : &b, &out,
+                   flops, bytes, tc);
+  // conv_launch_step only records one extra read; make sure b stays alive too
+  net_.steps.back().reads.push_back(b.buf.box);
+  set(out_value, out);
+}
+
+void Lowerer::lower_binary(const Node& n, const ActSpec& act, int out_value) {
+  const Shape& os = val(n.outputs[0]).shape;
+  if (n.op == B200_OP_BATCH_NORM) {
+    // standalone BatchNormInference: per-channel scale/shift (batch_norm_decomposition.cpp:33-80)
+    auto ga = const_floats(n.inputs[1]), be = const_floats(n.inputs[2]), mu = const_floats(n.inputs[3]), va = const_floats(n.inputs[4]);
+    B200_CHECK(os.size() == 4, B200_ERR_UNSUPPORTED, "BatchNorm '" << n.name << "': rank 4 only");
+    int64_t C = os[1], Cp = round_up(C, 8);
+    std::vector<float> sc(Cp, 0.f), sh(Cp, 0.f);
+    for (int64_t c = 0; c < C; ++c) { sc[c] = ga[c] / std::sqrt(va[c] + n.f[0]); sh[c] = be[c] - mu[c] * sc[c]; }
+    LTensor x = get(n.inputs[0], L_NHWC8);
+    LTensor out = alloc(os, cd_, L_NHWC8);
+    BufRef s1 = add_f32_vector(sc), s2 = add_f32_vector(sh), xr = x.buf, yr = out.buf;
+    int64_t rows = os[0] * os[2] * os[3];
+    int dt = cd_;
+    Step s;
+    s.name = val(out_value).name; s.type = "Eltwise"; s.impl = "scale_shift_nhwc8"; s.fused = n.name;
+    s.bytes = (double)x.bytes() + (double)out.bytes();
+    s.launch = [=](const RunCtx& c) {
+      launch_scale_shift(c.ptr(xr), (const float*)c.ptr(s1), (const float*)c.ptr(s2), c.ptr(yr), rows, (int)Cp, dt, act.kind, act.a, act.b,
+                         (cudaStream_t)c.stream);
+    };
+    emit(std::move(s), {&x}, {&out});
+    set(out_value, out);
+    return;
+  }
+  const Value& va = val(n.inputs[0]);
+  const Value& vb = val(n.inputs[1]);
+  const bool ints = !dtype_is_float(va.dtype);
+  B200_CHECK(!ints, B200_ERR_UNSUPPORTED, "integer eltwise '" << n.name << "' not supported");
+  const bool ca = const_node(n.inputs[0]) != nullptr, cb = const_node(n.inputs[1]) != nullptr;
+  // (1) NHWC8 tensor (op) per-channel constant -> scale/shift kernel
+  if (os.size() == 4 && (ca != cb) && (n.op == B200_OP_ADD || n.op == B200_OP_MULTIPLY || (n.op == B200_OP_SUBTRACT && cb))) {
+    std::vector<float> cv;
+    int tv = ca ? n.inputs[1] : n.inputs[0], cvv = ca ? n.inputs[0] : n.inputs[1];
+    auto it = vt_.find(tv);
+    if (it != vt_.end() && it->second.layout == L_NHWC8 && val(tv).shape == os && per_channel_const(cvv, os[1], false, cv)) {
+      int64_t C = os[1], Cp = round_up(C, 8);
+      std::vector<float> sc(Cp, 0.f), sh(Cp, 0.f);
+      for (int64_t c = 0; c < C; ++c) {
+        if (n.op == B200_OP_MULTIPLY) { sc[c] = cv[c]; sh[c] = 0.f; }
+        else if (n.op == B200_OP_ADD) { sc[c] = 1.f; sh[c] = cv[c]; }
+        else { sc[c] = 1.f; sh[c] = -cv[c]; }
+      }
+      LTensor x = it->second;
+      LTensor out = alloc(os, cd_, L_NHWC8);
+      BufRef s1 = add_f32_vector(sc), s2 = add_f32_vector(sh), xr = x.buf, yr = out.buf;
+      int64_t rows = os[0] * os[2] * os[3];
+      int dt = cd_;
+      Step s;
+      s.name = val(out_value).name; s.type = "Eltwise"; s.impl = "scale_shift_nhwc8"; s.fused = n.name;
+      s.bytes = (double)x.bytes() + (double)out.bytes();
+      s.launch = [=](const RunCtx& c) {
+        launch_scale_shift(c.ptr(xr), (const float*)c.ptr(s1), (const float*)c.ptr(s2), c.ptr(yr), rows, (int)Cp, dt, act.kind, act.a, act.b,
+                           (cudaStream_t)c.stream);
+      };
+      emit(std::move(s), {&x}, {&out});
+      set(out_value, out);
+      return;
+    }
+  }
+  // (2) same-shape activations: operate on the physical buffers in a common layout
+  if (!ca && !cb && va.shape == vb.shape && va.shape == os) {
+    int layout = L_ROWMAJOR;
+    auto ia = vt_.find(n.inputs[0]), ib = vt_.find(n.inputs[1]);
+    bool pad_unsafe = (n.op == B200_OP_DIVIDE || n.op == B200_OP_POWER) && os.size() == 4 && os[1] % 8 != 0;
+    if (!pad_unsafe && ((ia != vt_.end() && ia->second.layout == L_NHWC8) || (ib != vt_.end() && ib->second.layout == L_NHWC8))) layout = L_NHWC8;
+    LTensor a = get(n.inputs[0], layout), b = get(n.inputs[1], layout);
+    LTensor out = alloc(os, cd_, layout);
+    BufRef ar = a.buf, br = b.buf, yr = out.buf;
+    int64_t cnt = out.phys_elems();
+    int dt = cd_, op = n.op;
+    Step s;
+    s.name = val(out_value).name; s.type = "Eltwise"; s.impl = "binary_vec8"; s.fused = n.name;
+    s.bytes = 3.0 * (double)out.bytes();
+    s.launch = [=](const RunCtx& c) { launch_binary_same(c.ptr(ar), c.ptr(br), c.ptr(yr), cnt, dt, op, act.kind, act.a, act.b, (cudaStream_t)c.stream); };
+    emit(std::move(s), {&a, &b}, {&out});
+    set(out_value, out);
+    return;
+  }
+  // (3) general numpy broadcast over dense row-major tensors
+  LTensor a = get(n.inputs[0], L_ROWMAJOR), b = get(n.inputs[1], L_ROWMAJOR);
+  LTensor out = alloc(os, cd_, L_ROWMAJOR);
+  BinaryParams bp{};
+  bp.rank = (int)os.size();
+  B200_CHECK(bp.rank <= 8, B200_ERR_UNSUPPORTED, "eltwise rank > 8");
+  bp.n = numel(os);
+  auto fill = [&](const Shape& s, int64_t* strides) {
+    int64_t st = 1;
+    int off = (int)os.size() - (int)s.size();
+    for (int d = (int)os.size() - 1; d >= 0; --d) {
+      if (d - off >= 0) {
+        int64_t dim = s[d - off];
+        strides[d] = dim == 1 ? 0 : st;
+        st *= dim;
+      } else strides[d] = 0;
+    }
+  };
+  for (int d = 0; d < bp.rank; ++d) bp.oshape[d] = os[d];
+  fill(a.shape, bp.astride);
+  fill(b.shape, bp.bstride);
+  bp.op = n.op; bp.act = act.kind; bp.aa = act.a; bp.ab = act.b;
+  BufRef ar = a.buf, br = b.buf, yr = out.buf;
+  int dt = cd_;
+  Step s;
+  s.name = val(out_value).name; s.type = "Eltwise"; s.impl = "binary_broadcast"; s.fused = n.name;
+  s.bytes = (double)a.bytes() + (double)b.bytes() + (double)out.bytes();
+  s.launch = [=](const RunCtx& c) { BinaryParams q = bp; q.a = c.ptr(ar); q.b = c.ptr(br); q.y = c.ptr(yr); launch_binary(q, dt, (cudaStream_t)c.stream); };
+  emit(std::move(s), {&a, &b}, {&out});
+  set(out_value, out);
+}
+
+void Lowerer::lower_unary(const Node& n, const ActSpec& act) {
+  LTensor x = get(n.inputs[0], -1);
+  B200_CHECK(dtype_is_float(x.dtype), B200_ERR_UNSUPPORTED, "activation on non-float tensor");
+  ActSpec a = act;
+  if (n.op == B200_OP_SWISH && n.inputs.size() > 1) {
+    auto bv = const_floats(n.inputs[1]);  // beta as second input must be constant
+    a.a = bv.empty() ? 1.f : bv[0];
+  }
+  LTensor out = alloc(x.shape, x.dtype, x.layout);
+  BufRef xr = x.buf, yr = out.buf;
+  int64_t cnt = out.phys_elems();
+  int dt = x.dtype;
+  Step s;
+  s.name = n.name; s.type = "Eltwise"; s.impl = "unary_vec8"; s.fused = n.name;
+  s.bytes = 2.0 * (double)out.bytes();
+  s.launch = [=](const RunCtx& c) { launch_unary(c.ptr(xr), c.ptr(yr), cnt, dt, a.kind, a.a, a.b, (cudaStream_t)c.stream); };
+  emit(std::move(s), {&x}, {&out});
+  set(n.outputs[0], out);
+}
+
+void Lowerer::lower_pool(const Node& n) {
+  LTensor x = get(n.inputs[0], L_NHWC8);
+  const Shape os = val(n.outputs[0]).shape;
+  LTensor out = alloc(os, x.dtype, L_NHWC8);
+  const bool avg = n.op == B200_OP_AVG_POOL;
+  const int64_t Cp = round_up(os[1], 8);
+  BufRef xr = x.buf, yr = out.buf;
+  int dt = x.dtype;
+  Step s;
+  s.name = n.name; s.type = "Pooling"; s.fused = n.name;
+  s.bytes = (double)x.bytes() + (double)out.bytes();
+  const bool global = avg && n.i[0] == x.shape[2] && n.i[1] == x.shape[3] && !(n.i[4] | n.i[5] | n.i[6] | n.i[7]) && os[2] == 1 && os[3] == 1;
+  if (global) {
+    s.impl = "global_avg_nhwc8";
+    int N = (int)x.shape[0], HW = (int)(x.shape[2] * x.shape[3]);
+    s.launch = [=](const RunCtx& c) { launch_global_avgpool(c.ptr(xr), c.ptr(yr), N, HW, (int)Cp, dt, (cudaStream_t)c.stream); };
+  } else {
+    PoolParams p{};
+    p.N = (int)x.shape[0]; p.H = (int)x.shape[2]; p.W = (int)x.shape[3]; p.Cp = (int)Cp; p.Ho = (int)os[2]; p.Wo = (int)os[3];
+    p.kh = n.i[0]; p.kw = n.i[1]; p.sh = n.i[2]; p.sw = n.i[3]; p.pt = n.i[4]; p.pl = n.i[5]; p.pb = n.i[6]; p.pr = n.i[7];
+    p.is_avg = avg; p.exclude_pad = avg ? n.i[9] : 0;
+    s.impl = avg ? "avg_nhwc8" : "max_nhwc8";
+    s.launch = [=](const RunCtx& c) { PoolParams q = p; q.x = c.ptr(xr); q.y = c.ptr(yr); launch_pool(q, dt, (cudaStream_t)c.stream); };
+  }
+  emit(std::move(s), {&x}, {&out});
+  set(n.outputs[0], out);
+}
+
+void Lowerer::lower_reduce(const Node& n) {
+  const Shape& xs = val(n.inputs[0]).shape;
+  const Shape os = val(n.outputs[0]).shape;
+  const bool keep = n.i[0] != 0;
+  const int na = n.i[1];
+  std::vector<int> axes;
+  for (int k = 0; k < na; ++k) axes.push_back(n.i[2 + k] < 0 ? n.i[2 + k] + (int)xs.size() : n.i[2 + k]);
+  std::sort(axes.begin(), axes.end());
+  const int kind = n.op == B200_OP_REDUCE_MEAN ? 0 : (n.op == B200_OP_REDUCE_SUM ? 1 : 2);
+  auto it = vt_.find(n.inputs[0]);
+  // spatial mean of an NHWC8 tensor = global average pooling
+  if (kind == 0 && xs.size() == 4 && axes == std::vector<int>({2, 3}) && it != vt_.end() && it->second.layout == L_NHWC8) {
+    LTensor x = it->second;
+    Shape s4 = {xs[0], xs[1], 1, 1};
+    LTensor o4 = alloc(s4, x.dtype, L_NHWC8);
+    BufRef xr = x.buf, yr = o4.buf;
+    int N = (int)xs[0], HW = (int)(xs[2] * xs[3]), Cp = (int)round_up(xs[1], 8), dt = x.dtype;
+    Step s;
+    s.name = n.name; s.type = "Pooling"; s.impl = "global_avg_nhwc8"; s.fused = n.name;
+    s.bytes = (double)x.bytes() + (double)o4.bytes();
+    s.launch = [=](const RunCtx& c) { launch_global_avgpool(c.ptr(xr), c.ptr(yr), N, HW, Cp, dt, (cudaStream_t)c.stream); };
+    emit(std::move(s), {&x}, {&o4});
+    if (keep) { set(n.outputs[0], o4); return; }
+    // drop the unit dims: go through the dense view
+    set(n.outputs[0], o4);
+    LTensor d = get(n.outputs[0], L_ROWMAJOR);
+    alt_.erase(std::make_pair(n.outputs[0], (int)L_ROWMAJOR));
+    d.shape = os;
+    set(n.outputs[0], d);
+    return;
+  }
+  // contiguous block of axes over a dense tensor
+  for (size_t k = 1; k < axes.size(); ++k) B200_CHECK(axes[k] == axes[k - 1] + 1, B200_ERR_UNSUPPORTED, "Reduce '" << n.name << "': non-contiguous axes");
+  B200_CHECK(!axes.empty(), B200_ERR_INVALID, "Reduce without axes");
+  LTensor x = get(n.inputs[0], L_ROWMAJOR);
+  int64_t outer = 1, ax = 1, inner = 1;
+  for (int d = 0; d < (int)xs.size(); ++d) {
+    if (d < axes.front()) outer *= xs[d];
+    else if (d <= axes.back()) ax *= xs[d];
+    else inner *= xs[d];
+  }
+  LTensor out = alloc(os, x.dtype, L_ROWMAJOR);
+  BufRef xr = x.buf, yr = out.buf;
+  int dt = x.dtype;
+  Step s;
+  s.name = n.name; s.type = "Reduce"; s.impl = "reduce_strided"; s.fused = n.name;
+  s.bytes = (double)x.bytes() + (double)out.bytes();
+  s.launch = [=](const RunCtx& c) { launch_reduce(c.ptr(xr), c.ptr(yr), outer, ax, inner, dt, kind, (cudaStream_t)c.stream); };
+  emit(std::move(s), {&x}, {&out});
+  set(n.outputs[0], out);
+}
+
+void Lowerer::lower_mvn(const Node& n, const FusedMvn* f) {
+  const Shape& xs = val(n.inputs[0]).shape;
+  const int na = n.i[2];
+  std::vector<int> axes;
+  for (int k = 0; k < na; ++k) axes.push_back(n.i[3 + k] < 0 ? n.i[3 + k] + (int)xs.size() : n.i[3 + k]);
+  std::sort(axes.begin(), axes.end());
+  B200_CHECK(!axes.empty() && axes.back() == (int)xs.size() - 1, B200_ERR_UNSUPPORTED, "MVN '" << n.name << "': axes must be trailing");
+  for (size_t k = 1; k < axes.size(); ++k) B200_CHECK(axes[k] == axes[k - 1] + 1, B200_ERR_UNSUPPORTED, "MVN '" << n.name << "': axes must be contiguous");
+  int64_t cols = 1;
+  for (int a : axes) cols *= xs[a];
+  const int64_t rows = numel(xs) / cols;
+  LTensor x = get(n.inputs[0], L_ROWMAJOR);
+  const int out_value = f ? f->out_value : n.outputs[0];
+  LTensor out = alloc(xs, x.dtype, L_ROWMAJOR);
+  BufRef gr, br;
+  std::string fused = n.name;
+  if (f && f->gamma_value >= 0) { std::vector<float> g; per_channel_const(f->gamma_value, cols, true, g); gr = add_f32_vector(g); }
+  if (f && f->beta_value >= 0) { std::vector<float> b; per_channel_const(f->beta_value, cols, true, b); br = add_f32_vector(b); }
+  if (f) for (int a : f->absorbed) fused += "," + node(a).name;
+  BufRef xr = x.buf, yr = out.buf;
+  int dt = x.dtype, nv = n.i[0], eo = n.i[1];
+  float eps = n.f[0];
+  Step s;
+  s.name = val(out_value).name; s.type = "MVN"; s.impl = "mvn_rows"; s.fused = fused;
+  s.bytes = 2.0 * (double)x.bytes();
+  s.launch = [=](const RunCtx& c) {
+    launch_mvn(c.ptr(xr), c.ptr(yr), gr.space ? (const float*)c.ptr(gr) : nullptr, br.space ? (const float*)c.ptr(br) : nullptr, rows, cols, nv, eo,
+               eps, dt, (cudaStream_t)c.stream);
+  };
+  emit(std::move(s), {&x}, {&out});
+  set(out_value, out);
+}
+
+void Lowerer::lower_concat(const Node& n) {
+  const Shape os = val(n.outputs[0]).shape;
+  int ax = n.i[0] < 0 ? n.i[0] + (int)os.size() : n.i[0];
+  int sdt = storage_dtype(val(n.outputs[0]).dtype);
+  const int64_t es = dtype_size(sdt);
+  // channel concat of NHWC8 tensors whose channel counts are multiples of 8: pure strided copies
+  bool nhwc = os.size() == 4 && ax == 1;
+  if (nhwc)
+    for (int v : n.inputs) {
+      auto it = vt_.find(v);
+      if (it == vt_.end() || it->second.layout != L_NHWC8 || val(v).shape[1] % 8 != 0) nhwc = false;
+    }
+  const int layout = nhwc ? L_NHWC8 : L_ROWMAJOR;
+  LTensor out = alloc(os, sdt, layout);
+  int64_t outer = 1, inner = 1;
+  if (nhwc) { outer = os[0] * os[2] * os[3]; inner = 1; }
+  else {
+    for (int d = 0; d < ax; ++d) outer *= os[d];
+    for (int d = ax + 1; d < (int)os.size(); ++d) inner *= os[d];
+  }
+  const int64_t dpitch = os[ax] * inner * es;
+  int64_t off = 0;
+  for (int v : n.inputs) {
+    LTensor x = get(v, layout);
+    const int64_t row_bytes = val(v).shape[ax] * inner * es;
+    BufRef xr = x.buf, yr = out.buf;
+    Step s;
+    s.name = n.name; s.type = "Concat"; s.impl = "copy2d"; s.fused = n.name;
+    s.bytes = 2.0 * (double)x.bytes();
+    int64_t o = off;
+    s.launch = [=](const RunCtx& c) { launch_copy2d(c.ptr(xr), row_bytes, c.ptr(yr) + o, dpitch, row_bytes, outer, (cudaStream_t)c.stream); };
+    emit(std::move(s), {&x}, {&out});
+    off += row_bytes;
+  }
+  set(n.outputs[0], out);
+}
+
+void Lowerer::lower_split(const Node& n) {
+  LTensor x = get(n.inputs[0], L_ROWMAJOR);
+  const Shape& xs = x.shape;
+  int ax = n.i[0] < 0 ? n.i[0] + (int)xs.size() : n.i[0];
+  const int64_t es = dtype_size(x.dtype);
+  int64_t outer = 1, inner = 1;
+  for (int d = 0; d < ax; ++d) outer *= xs[d];
+  for (int d = ax + 1; d < (int)xs.size(); ++d) inner *= xs[d];
+  const int64_t spitch = xs[ax] * inner * es;
+  int64_t off = 0;
+  for (size_t k = 0; k < n.outputs.size(); ++k) {
+    const Shape os = val(n.outputs[k]).shape;
+    LTensor out = alloc(os, x.dtype, L_ROWMAJOR);
+    const int64_t row_bytes = os[ax] * inner * es;
+    BufRef xr = x.buf, yr = out.buf;
+    int64_t o = off;
+    Step s;
+    s.name = val(n.outputs[k]).name; s.type = "Split"; s.impl = "copy2d"; s.fused = n.name;
+    s.bytes = 2.0 * (double)out.bytes();
+    s.launch = [=](const RunCtx& c) { launch_copy2d(c.ptr(xr) + o, spitch, c.ptr(yr), row_bytes, row_bytes, outer, (cudaStream_t)c.stream); };
+    emit(std::move(s), {&x}, {&out});
+    set(n.outputs[k], out);
+    off += row_bytes;
+  }
+}
+
+void Lowerer::lower_transpose(const Node& n) {
+  const Shape& xs = val(n.inputs[0]).shape;
+  const Shape os = val(n.outputs[0]).shape;
+  const int r = (int)xs.size();
+  bool identity = true;
+  for (int d = 0; d < r; ++d) identity &= n.i[d] == d;
+  auto it = vt_.find(n.inputs[0]);
+  // NCHW -> NHWC of a tensor that already lives channel-last: a view, or a pad-dropping copy
+  if (r == 4 && n.i[0] == 0 && n.i[1] == 2 && n.i[2] == 3 && n.i[3] == 1 && it != vt_.end() && it->second.layout == L_NHWC8) {
+    LTensor x = it->second;
+    const int64_t C = xs[1], Cp = round_up(C, 8);
+    if (C == Cp) {
+      LTensor v = x;
+      v.shape = os; v.layout = L_ROWMAJOR;
+      set(n.outputs[0], v);
+      return;
+    }
+    LTensor out = alloc(os, x.dtype, L_ROWMAJOR);
+    const int64_t es = dtype_size(x.dtype), rows = xs[0] * xs[2] * xs[3];
+    BufRef xr = x.buf, yr = out.buf;
+    Step s;
+    s.name = n.name; s.type = "Transpose"; s.impl = "nhwc8_compact"; s.fused = n.name;
+    s.bytes = (double)x.bytes() + (double)out.bytes();
+    s.launch = [=](const RunCtx& c) { launch_copy2d(c.ptr(xr), Cp * es, c.ptr(yr), C * es, C * es, rows, (cudaStream_t)c.stream); };
+    emit(std::move(s), {&x}, {&out});
+    set(n.outputs[0], out);
+    return;
+  }
+  LTensor x = get(n.inputs[0], L_ROWMAJOR);
+  if (identity) { LTensor v = x; v.shape = os; set(n.outputs[0], v); return; }
+  LTensor out = alloc(os, x.dtype, L_ROWMAJOR);
+  PermuteParams pp{};
+  pp.rank = r;
+  pp.n = numel(os);
+  std::vector<int64_t> istr(r);
+  int64_t st = 1;
+  for (int d = r - 1; d >= 0; --d) { istr[d] = st; st *= xs[d]; }
+  for (int d = 0; d < r; ++d) { pp.oshape[d] = os[d]; pp.istride[d] = istr[n.i[d]]; }
+  BufRef xr = x.buf, yr = out.buf;
+  int es = (int)dtype_size(x.dtype);
+  Step s;
+  s.name = n.name; s.type = "Transpose"; s.impl = "permute"; s.fused = n.name;
+  s.bytes = 2.0 * (double)x.bytes();
+  s.launch = [=](const RunCtx& c) { PermuteParams q = pp; q.x = c.ptr(xr); q.y = c.ptr(yr); launch_permute(q, es, (cudaStream_t)c.stream); };
+  emit(std::move(s), {&x}, {&out});
+  set(n.outputs[0], out);
+}
+
+void Lowerer::lower_detection(const Node& n) {
+  if (n.op == B200_OP_TOPK) {
+    LTensor x = to_dtype(get(n.inputs[0], L_ROWMAJOR), B200_F32, n.name);
+    const Shape& xs = x.shape;
+    int ax = n.i[1] < 0 ? n.i[1] + (int)xs.size() : n.i[1];
+    int64_t outer = 1, inner = 1;
+    for (int d = 0; d < ax; ++d) outer *= xs[d];
+    for (int d = ax + 1; d < (int)xs.size(); ++d) inner *= xs[d];
+    const Shape os = val(n.outputs[0]).shape;
+    LTensor ov = alloc(os, B200_F32, L_ROWMAJOR), oi = alloc(os, B200_I32, L_ROWMAJOR);
+    BufRef xr = x.buf, vr = ov.buf, ir = oi.buf;
+    int64_t axis = xs[ax];
+    int k = n.i[0], mode = n.i[2], sort = n.i[3];
+    Step s;
+    s.name = n.name; s.type = "TopK"; s.impl = "block_select"; s.fused = n.name;
+    s.bytes = (double)x.bytes();
+    s.launch = [=](const RunCtx& c) {
+      launch_topk((const float*)c.ptr(xr), (float*)c.ptr(vr), (int32_t*)c.ptr(ir), outer, axis, inner, k, mode, sort, (cudaStream_t)c.stream);
+    };
+    emit(std::move(s), {&x}, {&ov, &oi});
+    set(n.outputs[0], ov);
+    set(n.outputs[1], oi);
+    return;
+  }
+  if (n.op == B200_OP_NMS) {
+    LTensor boxes = to_dtype(get(n.inputs[0], L_ROWMAJOR), B200_F32, n.name + "_boxes");
+    LTensor scores = to_dtype(get(n.inputs[1], L_ROWMAJOR), B200_F32, n.name + "_scores");
+    NmsParams p{};
+    p.B = (int)scores.shape[0]; p.C = (int)scores.shape[1]; p.Nb = (int)scores.shape[2];
+    p.max_out = (int)std::min<int64_t>(n.i[0], p.Nb); p.center_format = n.i[1]; p.sort_desc = n.i[2];
+    p.iou_thr = n.f[0]; p.score_thr = n.f[1]; p.soft_sigma = n.f[2];
+    LTensor o0 = alloc(val(n.outputs[0]).shape, B200_I32, L_ROWMAJOR), o1 = alloc(val(n.outputs[1]).shape, B200_F32, L_ROWMAJOR),
+            o2 = alloc(val(n.outputs[2]).shape, B200_I32, L_ROWMAJOR);
+    int64_t wsb = nms_workspace_bytes(p.B, p.C, p.Nb, p.max_out);
+    Shape wshape = {wsb};
+    LTensor ws = alloc(wshape, B200_U8, L_ROWMAJOR);
+    p.workspace_bytes = wsb;
+    BufRef br = boxes.buf, sr = scores.buf, r0 = o0.buf, r1 = o1.buf, r2 = o2.buf, wr = ws.buf;
+    Step s;
+    s.name = n.name; s.type = "NonMaxSuppression"; s.impl = "nms5_sort_greedy"; s.fused = n.name;
+    s.bytes = (double)boxes.bytes() + (double)scores.bytes();
+    s.launch = [=](const RunCtx& c) {
+      NmsParams q = p;
+      q.boxes = (const float*)c.ptr(br); q.scores = (const float*)c.ptr(sr); q.sel_idx = (int32_t*)c.ptr(r0);
+      q.sel_scores = (float*)c.ptr(r1); q.valid = (int32_t*)c.ptr(r2); q.workspace = c.ptr(wr);
+      launch_nms(q, (cudaStream_t)c.stream);
+    };
+    emit(std::move(s), {&boxes, &scores}, {&o0, &o1, &o2, &ws});
+    set(n.outputs[0], o0); set(n.outputs[1], o1); set(n.outputs[2], o2);
+    return;
+  }
+  // DetectionOutput
+  LTensor loc = to_dtype(get(n.inputs[0], L_ROWMAJOR), B200_F32, n.name + "_loc");
+  LTensor conf = to_dtype(get(n.inputs[1], L_ROWMAJOR), B200_F32, n.name + "_conf");
+  LTensor pri = to_dtype(get(n.inputs[2], L_ROWMAJOR), B200_F32, n.name + "_priors");
+  DetOutParams p{};
+  p.N = (int)loc.shape[0];
+  p.num_classes = n.i[0]; p.background = n.i[1]; p.top_k = n.i[2]; p.keep_top_k = n.i[3]; p.code_center = n.i[4];
+  p.share_location = n.i[5]; p.var_in_target = n.i[6]; p.normalized = n.i[7]; p.clip_before = n.i[8]; p.clip_after = n.i[9];
+  p.input_h = n.i[10]; p.input_w = n.i[11]; p.decrease_label_id = n.i[12];
+  p.nms_thr = n.f[0]; p.conf_thr = n.f[1];
+  const int prior_size = p.normalized ? 4 : 5;
+  p.num_priors = (int)(pri.shape[2] / prior_size);
+  p.num_loc_classes = p.share_location ? 1 : p.num_classes;
+  p.priors_batch = (int)pri.shape[0];
+  B200_CHECK(loc.shape[1] == (int64_t)p.num_priors * p.num_loc_classes * 4, B200_ERR_INVALID, "DetectionOutput '" << n.name << "': loc size mismatch");
+  B200_CHECK(conf.shape[1] == (int64_t)p.num_priors * p.num_classes, B200_ERR_INVALID, "DetectionOutput '" << n.name << "': conf size mismatch");
+  const Shape os = val(n.outputs[0]).shape;
+  p.out_rows = os[2];
+  LTensor out = alloc(os, B200_F32, L_ROWMAJOR);
+  int64_t wsb = detout_workspace_bytes(p);
+  Shape wshape = {wsb};
+  LTensor ws = alloc(wshape, B200_U8, L_ROWMAJOR);
+  p.workspace_bytes = wsb;
+  BufRef lr = loc.buf, cr = conf.buf, pr = pri.buf, orf = out.buf, wr = ws.buf;
+  Step s;
+  s.name = n.name; s.type = "DetectionOutput"; s.impl = "decode_sort_nms_topk"; s.fused = n.name;
+  s.bytes = (double)loc.bytes() + (double)conf.bytes();
+  s.launch = [=](const RunCtx& c) {
+    DetOutParams q = p;
+    q.loc = (const float*)c.ptr(lr); q.conf = (const float*)c.ptr(cr); q.priors = (const float*)c.ptr(pr);
+    q.out = (float*)c.ptr(orf); q.workspace = c.ptr(wr);
+    launch_detection_output(q, (cudaStream_t)c.stream);
+  };
+  emit(std::move(s), {&loc, &conf, &pri}, {&out, &ws});
+  set(n.outputs[0], out);
+}
+
+void Lowerer::lower_node(const Node& n) {
+  // fused records are emitted at the position of their last absorbed node
+  auto fc = fconv_.find(n.id);
+  if (fc != fconv_.end()) { lower_conv(fc->second); return; }
+  auto fm = fmvn_.find(n.id);
+  if (fm != fmvn_.end()) { lower_mvn(node(fm->second.root), &fm->second); return; }
+  auto fe = felt_.find(n.id);
+  if (fe != felt_.end()) { lower_binary(node(fe->second.root), fe->second.act, fe->second.out_value); return; }
+  if (absorbed_by_[n.id] >= 0) return;  // folded into another kernel, emitted elsewhere
+
+  switch (n.op) {
+    case B200_OP_PARAMETER: {
+      const Value& v = val(n.outputs[0]);
+      LTensor t = alloc(v.shape, storage_dtype(v.dtype), prefers_nhwc8(v.id) ? L_NHWC8 : L_ROWMAJOR, /*pinned=*/true);
+      set(v.id, t);
+      IOBinding b;
+      b.name = n.name; b.shape = v.shape; b.graph_dtype = v.dtype; b.value_id = v.id;
+      net_.inputs.push_back(b);
+      net_.in_tensors.push_back(t);
+      break;
+    }
+    case B200_OP_CONSTANT:
+      break;  // materialised lazily by get()
+    case B200_OP_RESULT: {
+      LTensor t = get(n.inputs[0], -1);
+      IOBinding b;
+      // output name = producer friendly name (+ .port) - mkldnn_graph.cpp:230-241
+      b.name = val(n.inputs[0]).name; b.shape = t.shape; b.graph_dtype = val(n.inputs[0]).dtype; b.value_id = n.inputs[0];
+      net_.outputs.push_back(b);
+      net_.out_tensors.push_back(t);
+      break;
+    }
+    case B200_OP_MAX_POOL: case B200_OP_AVG_POOL: lower_pool(n); break;
+    case B200_OP_REDUCE_MEAN: case B200_OP_REDUCE_SUM: case B200_OP_REDUCE_MAX: lower_reduce(n); break;
+    case B200_OP_SOFTMAX: {
+      LTensor x = get(n.inputs[0], L_ROWMAJOR);
+      const Shape& xs = x.shape;
+      int64_t outer = 1, inner = 1;
+      for (int d = 0; d < n.i[0]; ++d) outer *= xs[d];
+      for (int d = n.i[0] + 1; d < (int)xs.size(); ++d) inner *= xs[d];
+      LTensor out = alloc(xs, x.dtype, L_ROWMAJOR);
+      BufRef xr = x.buf, yr = out.buf;
+      int64_t axis = xs[n.i[0]];
+      int dt = x.dtype;
+      Step s;
+      s.name = n.name; s.type = "Softmax"; s.impl = inner == 1 ? "softmax_rows" : "softmax_strided"; s.fused = n.name;
+      s.bytes = 2.0 * (double)x.bytes();
+      s.launch = [=](const RunCtx& c) { launch_softmax(c.ptr(xr), c.ptr(yr), outer, axis, inner, dt, (cudaStream_t)c.stream); };
+      emit(std::move(s), {&x}, {&out});
+      set(n.outputs[0], out);
+      break;
+    }
+    case B200_OP_RESHAPE: {
+      LTensor x = get(n.inputs[0], L_ROWMAJOR);
+      LTensor v = x;
+      v.shape = val(n.outputs[0]).shape;
+      set(n.outputs[0], v);
+      break;
+    }
+    case B200_OP_TRANSPOSE: lower_transpose(n); break;
+    case B200_OP_CONCAT: lower_concat(n); break;
+    case B200_OP_SPLIT: lower_split(n); break;
+    case B200_OP_GATHER: {
+      int ax = n.i[0] < 0 ? n.i[0] + (int)val(n.inputs[0]).shape.size() : n.i[0];
+      B200_CHECK(ax == 0, B200_ERR_UNSUPPORTED, "Gather '" << n.name << "': only axis 0 is supported");
+      LTensor table = get(n.inputs[0], L_ROWMAJOR), idx = get(n.inputs[1], L_ROWMAJOR);
+      B200_CHECK(idx.dtype == B200_I32, B200_ERR_UNSUPPORTED, "Gather '" << n.name << "': indices must be i32/i64");
+      const Shape os = val(n.outputs[0]).shape;
+      LTensor out = alloc(os, table.dtype, L_ROWMAJOR);
+      int64_t rows = table.shape[0], row_elems = numel(table.shape) / std::max<int64_t>(rows, 1), n_idx = numel(idx.shape);
+      BufRef tr = table.buf, ir = idx.buf, yr = out.buf;
+      int dt = table.dtype;
+      Step s;
+      s.name = n.name; s.type = "Gather"; s.impl = "gather_rows"; s.fused = n.name;
+      s.bytes = 2.0 * (double)out.bytes();
+      s.launch = [=](const RunCtx& c) { launch_gather_rows(c.ptr(tr), (const int32_t*)c.ptr(ir), c.ptr(yr), n_idx, row_elems, rows, dt, (cudaStream_t)c.stream); };
+      emit(std::move(s), {&table, &idx}, {&out});
+      set(n.outputs[0], out);
+      break;
+    }
+    case B200_OP_TOPK: case B200_OP_NMS: case B200_OP_DETECTION_OUTPUT: lower_detection(n); break;
+    case B200_OP_CONVERT: {
+      LTensor x = get(n.inputs[0], -1);
+      int target = storage_dtype(n.dtype);
+      if (x.dtype == target) { set(n.outputs[0], x); break; }
+      LTensor xr = get(n.inputs[0], L_ROWMAJOR);
+      set(n.outputs[0], to_dtype(xr, target, n.name));
+      break;
+    }
+    case B200_OP_CONVOLUTION: case B200_OP_GROUP_CONVOLUTION:
+      B200_THROW(B200_ERR_UNSUPPORTED, "Convolution '" << n.name << "' with non-constant weights is not supported");
+    default: {
+      ActSpec as;
+      if (act_from_op(n, as)) { lower_unary(n, as); break; }
+      B200_THROW(B200_ERR_UNSUPPORTED, "no kernel for op " << op_name(n.op) << " ('" << n.name << "')");
+    }
+  }
+}
+
+void Lowerer::run() {
+  net_.name = g_.name;
+  B200_CHECK(!g_.results.empty(), B200_ERR_INVALID, "graph has no Result");
+  fuse();
+  for (const Node& n : g_.nodes) lower_node(n);
+  // live ranges: parameters live from before step 0, results until after the last step
+  const int nsteps = (int)net_.steps.size();
+  for (int si = 0; si < nsteps; ++si) {
+    for (int b : net_.steps[si].reads) { auto& bx = net_.boxes[b]; bx.first = std::min(bx.first, si); bx.last = std::max(bx.last, si); }
+    for (int b : net_.steps[si].writes) { auto& bx = net_.boxes[b]; bx.first = std::min(bx.first, si); bx.last = std::max(bx.last, si); }
+  }
+  for (auto& t : net_.in_tensors) if (t.buf.space == SP_ARENA) { net_.boxes[t.buf.box].first = -1; net_.boxes[t.buf.box].last = std::max(net_.boxes[t.buf.box].last, 0); }
+  for (auto& t : net_.out_tensors) if (t.buf.space == SP_ARENA) { net_.boxes[t.buf.box].last = nsteps; net_.boxes[t.buf.box].first = std::min(net_.boxes[t.buf.box].first, nsteps); }
+  plan_arena(net_.boxes, net_.arena_bytes);
+  net_.box_offsets.resize(net_.boxes.size());
+  for (size_t b = 0; b < net_.boxes.size(); ++b) net_.box_offsets[b] = net_.boxes[b].offset;
+}
+
+}  // namespace
+
+// Greedy best-fit over live ranges, largest boxes first: the formulation of MemorySolver
+// (inference-engine/src/mkldnn_plugin/mkldnn_memory_solver.cpp:51-96) with 1 KiB alignment.
+void plan_arena(std::vector<ArenaBox>& boxes, int64_t& total) {
+  std::vector<int> order(boxes.size());
+  for (size_t i = 0; i < boxes.size(); ++i) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return boxes[a].bytes > boxes[b].bytes; });
+  std::vector<int> placed;
+  total = 0;
+  for (int id : order) {
+    ArenaBox& b = boxes[id];
+    if (b.last < b.first) { b.offset = 0; continue; }  // never used
+    std::vector<std::pair<int64_t, int64_t>> busy;
+    for (int pid : placed) {
+      const ArenaBox& q = boxes[pid];
+      bool overlap_time = b.pinned || q.pinned || !(b.last < q.first || q.last < b.first);
+      if (overlap_time) busy.emplace_back(q.offset, q.offset + q.bytes);
+    }
+    std::sort(busy.begin(), busy.end());
+    int64_t off = 0;
+    for (auto& iv : busy) {
+      if (off + b.bytes <= iv.first) break;
+      off = std::max(off, iv.second);
+    }
+    b.offset = off;
+    total = std::max(total, off + b.bytes);
+    placed.push_back(id);
+  }
+  total = round_up(total + 1024, 1 << 20);
+}
+
+void lower_graph(const b200_graph& g, const b200_compile_options& opts, b200_network& net) {
+  Lowerer l(g, opts, net);
+  l.run();
+}
+
+}  // namespace b200

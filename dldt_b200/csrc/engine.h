@@ -22,6 +22,7 @@ struct b200_network {
   int cdtype = B200_F32;  // compute dtype of float activations
   std::vector<b200::Step> steps;
   std::vector<b200::ArenaBox> boxes;
+  std::vector<int64_t> box_offsets;
   int64_t arena_bytes = 0;
   std::vector<uint8_t> weights_host;
   char* weights_dev = nullptr;

@@ -116,5 +116,6 @@ struct DetOutParams {
 };
 int64_t detout_workspace_bytes(const DetOutParams& p);
 void launch_detection_output(const DetOutParams& p, cudaStream_t s);
+void detect_init_device();
 
 }  // namespace b200

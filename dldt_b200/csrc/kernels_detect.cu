@@ -1,0 +1,403 @@
+// NonMaxSuppression-5 and DetectionOutput-1 on the GPU, fp32 + i32, reproducing the reference
+// ordering rules bit for bit (compiled with -fmad=false so the box arithmetic is not contracted):
+//   NMS:  inference-engine/src/mkldnn_plugin/nodes/mkldnn_non_max_suppression_node.cpp:134-238 (execute),
+//         :240-273 (intersectionOverUnion), :336-376 (nmsWithoutSoftSigma)
+//   DetectionOutput: nodes/mkldnn_detection_output_node.cpp:129-352 (execute), :366-401 (JaccardOverlap),
+//         :403-503 (decodeBBoxes), :505-536 (nms_cf)
+// Per (image, class) the candidates are ordered by a block-wide bitonic sort of 64-bit keys
+// (orderable score bits << 32 | ~index) in shared memory - score descending, index ascending - and
+// the greedy suppression runs on one warp with the kept list checked 32 boxes at a time.
+#include <algorithm>
+#include <cfloat>
+
+#include "common.h"
+#include "kernels.h"
+
+namespace b200 {
+namespace {
+
+constexpr int SORT_MAX = 16384;                 // keys per block-level sort in shared memory
+constexpr int SORT_SMEM = SORT_MAX * 8;         // 128 KB
+
+__device__ __forceinline__ uint32_t ord_f32(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ uint64_t make_key(float score, uint32_t idx) { return ((uint64_t)ord_f32(score) << 32) | (uint64_t)(0xFFFFFFFFu - idx); }
+__device__ __forceinline__ uint32_t key_idx(uint64_t k) { return 0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFu); }
+
+// sorts keys[0..n) descending; n must be a power of two; all threads of the block participate
+__device__ void bitonic_sort_desc(uint64_t* keys, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          uint64_t a = keys[i], b = keys[ixj];
+          bool desc_seg = (i & k) == 0;
+          if ((a < b) == desc_seg) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// ---------------------------------------------------------------------------------------------
+// NMS-5
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float nms_iou(const float* bi, const float* bj, int center) {
+  float yminI, xminI, ymaxI, xmaxI, yminJ, xminJ, ymaxJ, xmaxJ;
+  if (center) {
+    yminI = bi[1] - bi[3] / 2.f; xminI = bi[0] - bi[2] / 2.f; ymaxI = bi[1] + bi[3] / 2.f; xmaxI = bi[0] + bi[2] / 2.f;
+    yminJ = bj[1] - bj[3] / 2.f; xminJ = bj[0] - bj[2] / 2.f; ymaxJ = bj[1] + bj[3] / 2.f; xmaxJ = bj[0] + bj[2] / 2.f;
+  } else {
+    yminI = fminf(bi[0], bi[2]); xminI = fminf(bi[1], bi[3]); ymaxI = fmaxf(bi[0], bi[2]); xmaxI = fmaxf(bi[1], bi[3]);
+    yminJ = fminf(bj[0], bj[2]); xminJ = fminf(bj[1], bj[3]); ymaxJ = fmaxf(bj[0], bj[2]); xmaxJ = fmaxf(bj[1], bj[3]);
+  }
+  float areaI = (ymaxI - yminI) * (xmaxI - xminI);
+  float areaJ = (ymaxJ - yminJ) * (xmaxJ - xminJ);
+  if (areaI <= 0.f || areaJ <= 0.f) return 0.f;
+  float inter = fmaxf(fminf(ymaxI, ymaxJ) - fmaxf(yminI, yminJ), 0.f) * fmaxf(fminf(xmaxI, xmaxJ) - fmaxf(xminI, xminJ), 0.f);
+  return inter / (areaI + areaJ - inter);
+}
+
+// one block per (batch, class)
+__global__ void nms_select_kernel(NmsParams p, int n_pad, int32_t* sel, int32_t* cnt) {
+  extern __shared__ uint64_t nms_keys[];
+  __shared__ int s_count;
+  const int b = blockIdx.x / p.C, c = blockIdx.x % p.C;
+  const float* scores = p.scores + ((int64_t)b * p.C + c) * p.Nb;
+  const float* boxes = p.boxes + (int64_t)b * p.Nb * 4;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  int local = 0;
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+    uint64_t k = 0;
+    if (i < p.Nb && scores[i] > p.score_thr) { k = make_key(scores[i], (uint32_t)i); ++local; }
+    nms_keys[i] = k;
+  }
+  atomicAdd(&s_count, local);
+  __syncthreads();
+  bitonic_sort_desc(nms_keys, n_pad);
+  const int count = s_count;
+  int32_t* my_sel = sel + (int64_t)blockIdx.x * p.max_out;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int nsel = 0;
+    for (int i = 0; i < count && nsel < p.max_out; ++i) {
+      const int idx = (int)key_idx(nms_keys[i]);
+      bool sup = false;
+      for (int k = lane; k < nsel; k += 32)
+        if (nms_iou(boxes + (int64_t)idx * 4, boxes + (int64_t)my_sel[k] * 4, p.center_format) >= p.iou_thr) sup = true;
+      sup = __any_sync(0xffffffffu, sup);
+      if (!sup) {
+        if (lane == 0) my_sel[nsel] = idx;
+        ++nsel;
+      }
+      __syncwarp();
+    }
+    if (lane == 0) cnt[blockIdx.x] = nsel;
+  }
+}
+
+// single block: gather, (optionally) global sort, write padded outputs
+__global__ void nms_finalize_kernel(NmsParams p, const int32_t* sel, const int32_t* cnt, uint64_t* keys, int n_pad, int64_t out_rows) {
+  __shared__ int s_total;
+  const int BC = p.B * p.C;
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < BC; ++i) t += cnt[i];
+    s_total = t;
+  }
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) keys[i] = 0;
+  __syncthreads();
+  const int total = s_total;
+  // position of every selected box in (batch, class, selection order); key low word keeps that order when unsorted
+  for (int bc = threadIdx.x; bc < BC; bc += blockDim.x) {
+    int base = 0;
+    for (int i = 0; i < bc; ++i) base += cnt[i];
+    for (int k = 0; k < cnt[bc]; ++k) {
+      int box = sel[(int64_t)bc * p.max_out + k];
+      float sc = p.scores[(int64_t)bc * p.Nb + box];
+      uint32_t lin = (uint32_t)((int64_t)bc * p.Nb + box);
+      keys[base + k] = p.sort_desc ? make_key(sc, lin) : (((uint64_t)(0xFFFFFFFFu - (uint32_t)(base + k))) << 32) | (uint64_t)lin;
+    }
+  }
+  __syncthreads();
+  if (p.sort_desc) bitonic_sort_desc(keys, n_pad);
+  const int valid = (int)min((int64_t)total, out_rows);
+  for (int64_t r = threadIdx.x; r < out_rows; r += blockDim.x) {
+    if (r < valid) {
+      uint32_t lin = p.sort_desc ? key_idx(keys[r]) : (uint32_t)(keys[r] & 0xFFFFFFFFu);
+      int box = (int)(lin % (uint32_t)p.Nb);
+      int bc = (int)(lin / (uint32_t)p.Nb);
+      int bb = bc / p.C, cc = bc % p.C;
+      p.sel_idx[r * 3 + 0] = bb; p.sel_idx[r * 3 + 1] = cc; p.sel_idx[r * 3 + 2] = box;
+      p.sel_scores[r * 3 + 0] = (float)bb; p.sel_scores[r * 3 + 1] = (float)cc; p.sel_scores[r * 3 + 2] = p.scores[(int64_t)bc * p.Nb + box];
+    } else {
+      p.sel_idx[r * 3 + 0] = -1; p.sel_idx[r * 3 + 1] = -1; p.sel_idx[r * 3 + 2] = -1;
+      p.sel_scores[r * 3 + 0] = -1.f; p.sel_scores[r * 3 + 1] = -1.f; p.sel_scores[r * 3 + 2] = -1.f;
+    }
+  }
+  if (threadIdx.x == 0) p.valid[0] = valid;
+}
+
+// ---------------------------------------------------------------------------------------------
+// DetectionOutput
+// ---------------------------------------------------------------------------------------------
+__global__ void detout_decode_kernel(DetOutParams p, float* boxes, float* sizes) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)p.N * p.num_loc_classes * p.num_priors;
+  if (i >= total) return;
+  const int pr = (int)(i % p.num_priors);
+  const int c = (int)((i / p.num_priors) % p.num_loc_classes);
+  const int n = (int)(i / ((int64_t)p.num_priors * p.num_loc_classes));
+  const int prior_size = p.normalized ? 4 : 5, offs = p.normalized ? 0 : 1;
+  const float* ppriors = p.priors;
+  const float* pvar = p.priors + (int64_t)p.num_priors * prior_size;
+  if (p.priors_batch > 1) {
+    ppriors += p.var_in_target ? (int64_t)n * p.num_priors * prior_size : (int64_t)2 * n * p.num_priors * prior_size;
+    pvar += p.var_in_target ? 0 : (int64_t)2 * n * p.num_priors * prior_size;
+  }
+  const float* loc = p.loc + (int64_t)n * 4 * p.num_loc_classes * p.num_priors + (int64_t)4 * pr * p.num_loc_classes + (int64_t)c * 4;
+  float pxmin = ppriors[pr * prior_size + 0 + offs], pymin = ppriors[pr * prior_size + 1 + offs];
+  float pxmax = ppriors[pr * prior_size + 2 + offs], pymax = ppriors[pr * prior_size + 3 + offs];
+  float lxmin = loc[0], lymin = loc[1], lxmax = loc[2], lymax = loc[3];
+  if (!p.normalized) {
+    pxmin /= (float)p.input_w; pymin /= (float)p.input_h; pxmax /= (float)p.input_w; pymax /= (float)p.input_h;
+  }
+  float nxmin = 0.f, nymin = 0.f, nxmax = 0.f, nymax = 0.f;
+  if (!p.code_center) {
+    if (p.var_in_target) { nxmin = pxmin + lxmin; nymin = pymin + lymin; nxmax = pxmax + lxmax; nymax = pymax + lymax; }
+    else {
+      nxmin = pxmin + pvar[pr * 4 + 0] * lxmin; nymin = pymin + pvar[pr * 4 + 1] * lymin;
+      nxmax = pxmax + pvar[pr * 4 + 2] * lxmax; nymax = pymax + pvar[pr * 4 + 3] * lymax;
+    }
+  } else {
+    float pw = pxmax - pxmin, ph = pymax - pymin;
+    float pcx = (pxmin + pxmax) / 2.0f, pcy = (pymin + pymax) / 2.0f;
+    float cx, cy, w, h;
+    if (p.var_in_target) {
+      cx = lxmin * pw + pcx; cy = lymin * ph + pcy; w = expf(lxmax) * pw; h = expf(lymax) * ph;
+    } else {
+      cx = pvar[pr * 4 + 0] * lxmin * pw + pcx; cy = pvar[pr * 4 + 1] * lymin * ph + pcy;
+      w = expf(pvar[pr * 4 + 2] * lxmax) * pw; h = expf(pvar[pr * 4 + 3] * lymax) * ph;
+    }
+    nxmin = cx - w / 2.0f; nymin = cy - h / 2.0f; nxmax = cx + w / 2.0f; nymax = cy + h / 2.0f;
+  }
+  if (p.clip_before) {
+    nxmin = fmaxf(0.f, fminf(1.f, nxmin)); nymin = fmaxf(0.f, fminf(1.f, nymin));
+    nxmax = fmaxf(0.f, fminf(1.f, nxmax)); nymax = fmaxf(0.f, fminf(1.f, nymax));
+  }
+  // decoded layout [N][loc_class][prior][4]
+  float* o = boxes + (((int64_t)n * p.num_loc_classes + c) * p.num_priors + pr) * 4;
+  o[0] = nxmin; o[1] = nymin; o[2] = nxmax; o[3] = nymax;
+  sizes[((int64_t)n * p.num_loc_classes + c) * p.num_priors + pr] = (nxmax - nxmin) * (nymax - nymin);
+}
+
+__device__ __forceinline__ float jaccard(const float* bb, const float* sz, int i1, int i2) {
+  float xmin1 = bb[i1 * 4 + 0], ymin1 = bb[i1 * 4 + 1], xmax1 = bb[i1 * 4 + 2], ymax1 = bb[i1 * 4 + 3];
+  float xmin2 = bb[i2 * 4 + 0], ymin2 = bb[i2 * 4 + 1], xmax2 = bb[i2 * 4 + 2], ymax2 = bb[i2 * 4 + 3];
+  if (xmin2 > xmax1 || xmax2 < xmin1 || ymin2 > ymax1 || ymax2 < ymin1) return 0.f;
+  float iw = fminf(xmax1, xmax2) - fmaxf(xmin1, xmin2);
+  float ih = fminf(ymax1, ymax2) - fmaxf(ymin1, ymin2);
+  if (iw <= 0.f || ih <= 0.f) return 0.f;
+  float inter = iw * ih;
+  return inter / (sz[i1] + sz[i2] - inter);
+}
+
+// one block per (image, class): candidate filter, sort, top_k, greedy NMS (nms_cf)
+__global__ void detout_nms_kernel(DetOutParams p, const float* boxes, const float* sizes, int n_pad, int max_keep, int32_t* kept, int32_t* cnt) {
+  extern __shared__ uint64_t det_keys[];
+  __shared__ int s_count;
+  const int n = blockIdx.x / p.num_classes, c = blockIdx.x % p.num_classes;
+  if (c == p.background) { if (threadIdx.x == 0) cnt[blockIdx.x] = 0; return; }
+  const float* conf = p.conf + (int64_t)n * p.num_priors * p.num_classes;   // [prior][class]
+  const int lc = p.share_location ? 0 : c;
+  const float* bb = boxes + ((int64_t)n * p.num_loc_classes + lc) * p.num_priors * 4;
+  const float* sz = sizes + ((int64_t)n * p.num_loc_classes + lc) * p.num_priors;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  int local = 0;
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+    uint64_t k = 0;
+    if (i < p.num_priors) {
+      float s = conf[(int64_t)i * p.num_classes + c];
+      if (s > p.conf_thr) { k = make_key(s, (uint32_t)i); ++local; }
+    }
+    det_keys[i] = k;
+  }
+  atomicAdd(&s_count, local);
+  __syncthreads();
+  bitonic_sort_desc(det_keys, n_pad);
+  const int count = s_count;
+  const int num_scores = p.top_k == -1 ? count : min(p.top_k, count);
+  int32_t* my = kept + (int64_t)blockIdx.x * max_keep;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int det = 0;
+    for (int i = 0; i < num_scores; ++i) {
+      const int idx = (int)key_idx(det_keys[i]);
+      bool sup = false;
+      for (int k = lane; k < det; k += 32)
+        if (jaccard(bb, sz, idx, my[k]) > p.nms_thr) sup = true;
+      sup = __any_sync(0xffffffffu, sup);
+      if (!sup) {
+        if (lane == 0) my[det] = idx;
+        ++det;
+      }
+      __syncwarp();
+    }
+    if (lane == 0) cnt[blockIdx.x] = det;
+  }
+}
+
+// one block per image: keep_top_k across classes (global sort by score), lists re-stored per class
+__global__ void detout_keep_kernel(DetOutParams p, int n_pad, int max_keep, int32_t* kept, int32_t* cnt, int32_t* totals) {
+  extern __shared__ uint64_t keep_keys[];
+  __shared__ int s_total;
+  const int n = blockIdx.x;
+  int32_t* my_cnt = cnt + (int64_t)n * p.num_classes;
+  int32_t* my_kept = kept + (int64_t)n * p.num_classes * max_keep;
+  const float* conf = p.conf + (int64_t)n * p.num_priors * p.num_classes;
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int c = 0; c < p.num_classes; ++c) t += my_cnt[c];
+    s_total = t;
+  }
+  __syncthreads();
+  const int total = s_total;
+  if (!(p.keep_top_k > -1 && total > p.keep_top_k)) {
+    if (threadIdx.x == 0) totals[n] = total;
+    return;
+  }
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) keep_keys[i] = 0;
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.num_classes; c += blockDim.x) {
+    int base = 0;
+    for (int k = 0; k < c; ++k) base += my_cnt[k];
+    for (int k = 0; k < my_cnt[c]; ++k) {
+      int idx = my_kept[(int64_t)c * max_keep + k];
+      keep_keys[base + k] = make_key(conf[(int64_t)idx * p.num_classes + c], (uint32_t)(c * p.num_priors + idx));
+    }
+  }
+  __syncthreads();
+  bitonic_sort_desc(keep_keys, n_pad);
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < p.num_classes; ++c) my_cnt[c] = 0;
+    for (int j = 0; j < p.keep_top_k; ++j) {
+      uint32_t lin = key_idx(keep_keys[j]);
+      int label = (int)(lin / (uint32_t)p.num_priors), idx = (int)(lin % (uint32_t)p.num_priors);
+      my_kept[(int64_t)label * max_keep + my_cnt[label]] = idx;
+      my_cnt[label]++;
+    }
+    totals[n] = p.keep_top_k;
+  }
+}
+
+// single block: rows [image_id, label, conf, xmin, ymin, xmax, ymax] grouped by image, class, list order
+__global__ void detout_pack_kernel(DetOutParams p, const float* boxes, int max_keep, const int32_t* kept, const int32_t* cnt,
+                                   const int32_t* totals) {
+  __shared__ int s_count;
+  for (int64_t i = threadIdx.x; i < p.out_rows * 7; i += blockDim.x) p.out[i] = 0.f;
+  __syncthreads();
+  for (int nc = threadIdx.x; nc < p.N * p.num_classes; nc += blockDim.x) {
+    const int n = nc / p.num_classes, c = nc % p.num_classes;
+    int base = 0;
+    for (int i = 0; i < n; ++i) base += totals[i];
+    for (int k = 0; k < c; ++k) base += cnt[n * p.num_classes + k];
+    const float* conf = p.conf + (int64_t)n * p.num_priors * p.num_classes;
+    const int lc = p.share_location ? 0 : c;
+    const float* bb = boxes + ((int64_t)n * p.num_loc_classes + lc) * p.num_priors * 4;
+    for (int k = 0; k < cnt[nc]; ++k) {
+      int64_t row = base + k;
+      if (row >= p.out_rows) break;
+      int idx = kept[(int64_t)nc * max_keep + k];
+      float xmin = bb[idx * 4 + 0], ymin = bb[idx * 4 + 1], xmax = bb[idx * 4 + 2], ymax = bb[idx * 4 + 3];
+      if (p.clip_after) {
+        xmin = fmaxf(0.f, fminf(1.f, xmin)); ymin = fmaxf(0.f, fminf(1.f, ymin));
+        xmax = fmaxf(0.f, fminf(1.f, xmax)); ymax = fmaxf(0.f, fminf(1.f, ymax));
+      }
+      float* o = p.out + row * 7;
+      o[0] = (float)n; o[1] = (float)(p.decrease_label_id ? c - 1 : c); o[2] = conf[(int64_t)idx * p.num_classes + c];
+      o[3] = xmin; o[4] = ymin; o[5] = xmax; o[6] = ymax;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < p.N; ++i) t += totals[i];
+    s_count = t;
+    if (t < p.out_rows) p.out[(int64_t)t * 7] = -1.f;   // end-of-list marker
+  }
+}
+
+int detout_max_keep(const DetOutParams& p) { return p.top_k > 0 ? std::min(p.top_k, p.num_priors) : p.num_priors; }
+
+}  // namespace
+
+void detect_init_device() {
+  cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM);
+  cudaFuncSetAttribute(detout_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM);
+  cudaFuncSetAttribute(detout_keep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM);
+}
+
+int64_t nms_workspace_bytes(int B, int C, int Nb, int max_out) {
+  int64_t sel = round_up((int64_t)B * C * max_out * 4, 256);
+  int64_t cnt = round_up((int64_t)B * C * 4, 256);
+  int64_t keys = (int64_t)next_pow2((int)std::min<int64_t>((int64_t)B * C * max_out, 1 << 30)) * 8;
+  return sel + cnt + keys + 1024;
+}
+
+void launch_nms(const NmsParams& p, cudaStream_t s) {
+  B200_CHECK(p.soft_sigma == 0.f, B200_ERR_UNSUPPORTED, "NonMaxSuppression: soft_nms_sigma > 0 is not supported");
+  B200_CHECK(p.Nb <= SORT_MAX, B200_ERR_UNSUPPORTED, "NonMaxSuppression: more than " << SORT_MAX << " boxes per batch");
+  B200_CHECK((int64_t)p.B * p.C * p.Nb < (1ll << 32), B200_ERR_UNSUPPORTED, "NonMaxSuppression: problem too large");
+  if (p.B * p.C == 0 || p.max_out == 0) return;
+  char* ws = (char*)p.workspace;
+  int32_t* sel = (int32_t*)ws;
+  int64_t off = round_up((int64_t)p.B * p.C * p.max_out * 4, 256);
+  int32_t* cnt = (int32_t*)(ws + off);
+  off += round_up((int64_t)p.B * p.C * 4, 256);
+  uint64_t* keys = (uint64_t*)(ws + off);
+  const int n_pad = next_pow2(std::max(p.Nb, 2));
+  nms_select_kernel<<<p.B * p.C, 512, (size_t)n_pad * 8, s>>>(p, n_pad, sel, cnt);
+  const int64_t out_rows = (int64_t)p.B * p.C * p.max_out;
+  const int tot_pad = next_pow2((int)std::max<int64_t>(out_rows, 2));
+  nms_finalize_kernel<<<1, 1024, 0, s>>>(p, sel, cnt, keys, tot_pad, out_rows);
+}
+
+int64_t detout_workspace_bytes(const DetOutParams& p) {
+  int64_t boxes = round_up((int64_t)p.N * p.num_loc_classes * p.num_priors * 16, 256);
+  int64_t sizes = round_up((int64_t)p.N * p.num_loc_classes * p.num_priors * 4, 256);
+  int64_t kept = round_up((int64_t)p.N * p.num_classes * detout_max_keep(p) * 4, 256);
+  int64_t cnt = round_up((int64_t)p.N * p.num_classes * 4, 256);
+  int64_t totals = round_up((int64_t)p.N * 4, 256);
+  return boxes + sizes + kept + cnt + totals + 1024;
+}
+
+void launch_detection_output(const DetOutParams& p, cudaStream_t s) {
+  B200_CHECK(!p.decrease_label_id, B200_ERR_UNSUPPORTED, "DetectionOutput: decrease_label_id (MXNet style) is not supported");
+  B200_CHECK(p.num_priors <= SORT_MAX, B200_ERR_UNSUPPORTED, "DetectionOutput: more than " << SORT_MAX << " priors");
+  const int max_keep = detout_max_keep(p);
+  const int64_t all = (int64_t)p.num_classes * max_keep;
+  B200_CHECK(p.keep_top_k < 0 || all <= SORT_MAX, B200_ERR_UNSUPPORTED, "DetectionOutput: num_classes*top_k > " << SORT_MAX);
+  char* ws = (char*)p.workspace;
+  int64_t off = 0;
+  float* boxes = (float*)(ws + off); off += round_up((int64_t)p.N * p.num_loc_classes * p.num_priors * 16, 256);
+  float* sizes = (float*)(ws + off); off += round_up((int64_t)p.N * p.num_loc_classes * p.num_priors * 4, 256);
+  int32_t* kept = (int32_t*)(ws + off); off += round_up((int64_t)p.N * p.num_classes * max_keep * 4, 256);
+  int32_t* cnt = (int32_t*)(ws + off); off += round_up((int64_t)p.N * p.num_classes * 4, 256);
+  int32_t* totals = (int32_t*)(ws + off);
+  int64_t nd = (int64_t)p.N * p.num_loc_classes * p.num_priors;
+  detout_decode_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, s>>>(p, boxes, sizes);
+  const int n_pad = next_pow2(std::max(p.num_priors, 2));
+  detout_nms_kernel<<<p.N * p.num_classes, 512, (size_t)n_pad * 8, s>>>(p, boxes, sizes, n_pad, max_keep, kept, cnt);
+  const int keep_pad = next_pow2((int)std::max<int64_t>(std::min<int64_t>(all, SORT_MAX), 2));
+  detout_keep_kernel<<<p.N, 1024, (size_t)keep_pad * 8, s>>>(p, keep_pad, max_keep, kept, cnt, totals);
+  detout_pack_kernel<<<1, 1024, 0, s>>>(p, boxes, max_keep, kept, cnt, totals);
+}
+
+}  // namespace b200

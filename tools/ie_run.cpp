@@ -1,0 +1,98 @@
+// ie_run: load an IR with the reference Inference Engine (built by oracle/build_ref.sh), run it on a
+// device ("CPU" = the MKLDNNPlugin oracle, "B200" = this repository's plugin, "MULTI:..."), feed raw
+// input files and dump raw outputs + a JSON manifest.  Used by tools/make_golden.py (golden vectors)
+// and by the GPU parity tests that drive the B200 plugin through the unmodified Core API
+// (Core::ReadNetwork / LoadNetwork / CreateInferRequest / StartAsync / Wait).
+#include <inference_engine.hpp>
+
+#include <chrono>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+using namespace InferenceEngine;
+
+static std::vector<std::string> split(const std::string& s, char d) {
+  std::vector<std::string> out;
+  std::stringstream ss(s);
+  std::string item;
+  while (std::getline(ss, item, d)) out.push_back(item);
+  return out;
+}
+
+int main(int argc, char** argv) {
+  std::string model, device = "CPU", outdir = ".", plugins_xml;
+  std::map<std::string, std::string> config, inputs, in_prec;
+  int niter = 1;
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i];
+    auto next = [&]() { return std::string(i + 1 < argc ? argv[++i] : ""); };
+    if (a == "--model") model = next();
+    else if (a == "--device") device = next();
+    else if (a == "--output-dir") outdir = next();
+    else if (a == "--plugins") plugins_xml = next();
+    else if (a == "--niter") niter = std::stoi(next());
+    else if (a == "--config") { for (auto& kv : split(next(), ',')) { auto p = kv.find('='); if (p != std::string::npos) config[kv.substr(0, p)] = kv.substr(p + 1); } }
+    else if (a == "--input") { auto kv = next(); auto p = kv.find('='); inputs[kv.substr(0, p)] = kv.substr(p + 1); }
+    else if (a == "--input-precision") { auto kv = next(); auto p = kv.find('='); in_prec[kv.substr(0, p)] = kv.substr(p + 1); }
+    else { std::cerr << "unknown argument " << a << "\n"; return 2; }
+  }
+  try {
+    Core core(plugins_xml);
+    CNNNetwork net = core.ReadNetwork(model);
+    for (auto& in : net.getInputsInfo()) {
+      auto it = in_prec.find(in.first);
+      if (it != in_prec.end()) in.second->setPrecision(Precision::FromStr(it->second));
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    ExecutableNetwork exe = core.LoadNetwork(net, device, config);
+    auto t1 = std::chrono::steady_clock::now();
+    InferRequest req = exe.CreateInferRequest();
+    for (auto& in : net.getInputsInfo()) {
+      Blob::Ptr b = req.GetBlob(in.first);
+      auto mb = as<MemoryBlob>(b);
+      auto h = mb->wmap();
+      char* dst = h.as<char*>();
+      auto it = inputs.find(in.first);
+      if (it == inputs.end()) { std::cerr << "no file for input " << in.first << "\n"; return 2; }
+      std::ifstream f(it->second, std::ios::binary);
+      f.read(dst, (std::streamsize)b->byteSize());
+      if ((size_t)f.gcount() != b->byteSize()) { std::cerr << "input " << in.first << ": expected " << b->byteSize() << " bytes, got " << f.gcount() << "\n"; return 2; }
+    }
+    std::vector<double> ms;
+    for (int it = 0; it < niter; ++it) {
+      auto a0 = std::chrono::steady_clock::now();
+      req.StartAsync();
+      req.Wait(InferRequest::WaitMode::RESULT_READY);
+      ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a0).count());
+    }
+    std::ofstream man(outdir + "/manifest.json");
+    man << "{\"device\": \"" << device << "\", \"load_ms\": " << std::chrono::duration<double, std::milli>(t1 - t0).count() << ", \"infer_ms\": [";
+    for (size_t k = 0; k < ms.size(); ++k) man << (k ? ", " : "") << ms[k];
+    man << "], \"outputs\": {";
+    bool first = true;
+    for (auto& out : net.getOutputsInfo()) {
+      Blob::Ptr b = req.GetBlob(out.first);
+      auto mb = as<MemoryBlob>(b);
+      auto h = mb->rmap();
+      std::string fname = out.first;
+      for (auto& ch : fname) if (ch == '/' || ch == ':') ch = '_';
+      std::ofstream f(outdir + "/" + fname + ".bin", std::ios::binary);
+      f.write(h.as<const char*>(), (std::streamsize)b->byteSize());
+      man << (first ? "" : ", ") << "\"" << out.first << "\": {\"file\": \"" << fname << ".bin\", \"precision\": \"" << b->getTensorDesc().getPrecision().name()
+          << "\", \"shape\": [";
+      auto dims = b->getTensorDesc().getDims();
+      for (size_t k = 0; k < dims.size(); ++k) man << (k ? ", " : "") << dims[k];
+      man << "]}";
+      first = false;
+    }
+    man << "}}\n";
+  } catch (const std::exception& e) {
+    std::cerr << "ie_run: " << e.what() << "\n";
+    return 1;
+  }
+  return 0;
+}
