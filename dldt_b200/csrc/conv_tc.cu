@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(160, 2) conv_tc_kernel(const ConvParams p) {
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_al + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* res_bar = tmem_full_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(160, 2) conv_tc_kernel(const ConvParams p) {
       ptx::mbar_init(&empty_bar[s], 1);
     }
     ptx::mbar_init(tmem_full_bar, 1);
+    ptx::mbar_init(res_bar, NUM_PRODUCERS);
     ptx::fence_mbar_init();
   }
   if (warp == 4) {
@@ -181,48 +183,79 @@ __global__ void __launch_bounds__(160, 2) conv_tc_kernel(const ConvParams p) {
     }
 
     // ===================== epilogue =====================
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tc_fence_after();
+    // TMEM -> registers -> (bias, act, + residual, act) -> padded staging tile in the (now idle) pipeline
+    // smem -> one bulk async store per output row.  The residual tile comes in the same way (bulk async
+    // loads, one per row), so every HBM access of the epilogue is a full, coalesced row segment.
     const int row = warp * 32 + lane;
     const int m = m0 + row;
     const bool row_ok = m < p.M;
-    const int64_t yrow = (int64_t)bz * p.y_bs + (int64_t)m * p.ldy;
-    const float* __restrict__ bias = p.bias;
+    const int ncols = min(BN, p.Cout_p - n0);                 // valid output channels of this tile (multiple of 8)
+    const uint32_t esz = p.out_f32 ? 4u : 2u;
+    const uint32_t out_stride = BN * esz + 16u;               // +16 B: conflict-free 16-byte row-strided smem access
+    const uint32_t res_stride = BN * 2u + 16u;
+    const uint32_t srow = smem_base + row * out_stride;
+    const uint32_t rrow = smem_base + BM * out_stride + row * res_stride;
+    const int64_t yoff = (int64_t)bz * p.y_bs + (int64_t)m * p.ldy + n0;
+    const bool has_res = p.res != nullptr;
+    if (has_res && row_ok) ptx::bulk_prefetch_l2(reinterpret_cast<const T*>(p.res) + yoff, (uint32_t)ncols * 2u);
+
+    ptx::mbar_wait(tmem_full_bar, 0);   // all MMAs retired: accumulator ready, smem stages free
+    ptx::tc_fence_after();
+    if (has_res) {
+      if (row_ok) {
+        ptx::mbar_arrive_expect_tx(res_bar, (uint32_t)ncols * 2u);
+        ptx::bulk_load(rrow, reinterpret_cast<const T*>(p.res) + yoff, (uint32_t)ncols * 2u, res_bar);
+      } else {
+        ptx::mbar_arrive(res_bar);
+      }
+    }
+    const float* __restrict__ bias = p.bias + n0;
+    bool res_ready = !has_res;
 #pragma unroll 1
     for (int j = 0; j < BN / 32; ++j) {
+      if (j * 32 >= ncols) break;       // warp-uniform
       uint32_t v[32];
       ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), v);
       ptx::tmem_ld_wait();
-      const int nb = n0 + j * 32;
+      if (!res_ready) { ptx::mbar_wait(res_bar, 0); res_ready = true; }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {   // groups of 8 output channels
-        const int n8 = nb + q * 8;
-        if (!row_ok || n8 >= p.Cout_p) continue;
-        float f[8];
+      for (int q = 0; q < 4; ++q) {     // groups of 8 output channels
+        const int c0 = j * 32 + q * 8;
+        if (c0 < ncols) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
+          float f[8];
+          f[0] = __uint_as_float(v[q * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[q * 8 + 1]) + b0.y;
+          f[2] = __uint_as_float(v[q * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[q * 8 + 3]) + b0.w;
+          f[4] = __uint_as_float(v[q * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[q * 8 + 5]) + b1.y;
+          f[6] = __uint_as_float(v[q * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[q * 8 + 7]) + b1.w;
+          if (p.act1 != ACT_NONE) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          f[e] = __uint_as_float(v[q * 8 + e]) + __ldg(bias + n8 + e);
-          f[e] = act_apply(f[e], p.act1, p.a1, p.b1);
-        }
-        if (p.res != nullptr) {
-          const uint4 rv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.res) + yrow + n8));
-          float r[8];
-          unpack2<T>(rv.x, r[0], r[1]); unpack2<T>(rv.y, r[2], r[3]);
-          unpack2<T>(rv.z, r[4], r[5]); unpack2<T>(rv.w, r[6], r[7]);
+            for (int e = 0; e < 8; ++e) f[e] = act_apply(f[e], p.act1, p.a1, p.b1);
+          }
+          if (has_res) {
+            const uint4 rv = ptx::ld_shared_v4(rrow + (uint32_t)c0 * 2u);
+            float r[8];
+            unpack2<T>(rv.x, r[0], r[1]); unpack2<T>(rv.y, r[2], r[3]);
+            unpack2<T>(rv.z, r[4], r[5]); unpack2<T>(rv.w, r[6], r[7]);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = act_apply(f[e] + r[e], p.act2, p.a2, p.b2);
-        }
-        if (p.out_f32) {
-          float* yo = reinterpret_cast<float*>(p.y) + yrow + n8;
-          *reinterpret_cast<float4*>(yo) = make_float4(f[0], f[1], f[2], f[3]);
-          *reinterpret_cast<float4*>(yo + 4) = make_float4(f[4], f[5], f[6], f[7]);
-        } else {
-          uint4 o;
-          o.x = pack2<T>(f[0], f[1]); o.y = pack2<T>(f[2], f[3]);
-          o.z = pack2<T>(f[4], f[5]); o.w = pack2<T>(f[6], f[7]);
-          *reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.y) + yrow + n8) = o;
+            for (int e = 0; e < 8; ++e) f[e] = act_apply(f[e] + r[e], p.act2, p.a2, p.b2);
+          }
+          if (p.out_f32) {
+            ptx::st_shared_v4(srow + (uint32_t)c0 * 4u, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+            ptx::st_shared_v4(srow + (uint32_t)c0 * 4u + 16u, make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
+          } else {
+            ptx::st_shared_v4(srow + (uint32_t)c0 * 2u, make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7])));
+          }
         }
       }
+    }
+    ptx::fence_proxy_async();           // this thread's staging row -> visible to the bulk-copy engine
+    if (row_ok) {
+      char* ydst = reinterpret_cast<char*>(p.y) + yoff * (int64_t)esz;
+      ptx::bulk_store(ydst, srow, (uint32_t)ncols * esz);
+      ptx::bulk_commit();
+      ptx::bulk_wait_read0();           // smem must stay intact until the copy engine has read it
     }
   } else if (lane == 0) {
     // ===================== MMA issuer (one thread) =====================
@@ -271,6 +304,7 @@ void conv_tc_init_device() {
 }
 
 void launch_conv_tc(const ConvParams& p, int dtype, int bn, cudaStream_t s) {
+  B200_CHECK(!(p.out_f32 && p.res), B200_ERR_UNSUPPORTED, "conv_tc: fp32 output with a residual input");
   B200_CHECK(p.Ktot % BK == 0 && p.Cin_p % 8 == 0 && p.Cout_alloc % bn == 0 && p.Cout_p % 8 == 0 && p.ldy % 8 == 0 &&
                  p.w_ld % 8 == 0 && p.w_k % 8 == 0,
              B200_ERR_INVALID, "conv_tc: bad geometry");
