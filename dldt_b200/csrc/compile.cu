@@ -1227,6 +1227,7 @@ void Lowerer::run() {
   for (auto& t : net_.in_tensors) if (t.buf.space == SP_ARENA) { net_.boxes[t.buf.box].first = -1; net_.boxes[t.buf.box].last = std::max(net_.boxes[t.buf.box].last, 0); }
   for (auto& t : net_.out_tensors) if (t.buf.space == SP_ARENA) { net_.boxes[t.buf.box].last = nsteps; net_.boxes[t.buf.box].first = std::min(net_.boxes[t.buf.box].first, nsteps); }
   plan_arena(net_.boxes, net_.arena_bytes);
+  net_.arena_bytes = round_up(net_.arena_bytes + 1024, 1 << 20);
   net_.box_offsets.resize(net_.boxes.size());
   for (size_t b = 0; b < net_.boxes.size(); ++b) net_.box_offsets[b] = net_.boxes[b].offset;
 }
@@ -1260,7 +1261,6 @@ void plan_arena(std::vector<ArenaBox>& boxes, int64_t& total) {
     total = std::max(total, off + b.bytes);
     placed.push_back(id);
   }
-  total = round_up(total + 1024, 1 << 20);
 }
 
 void lower_graph(const b200_graph& g, const b200_compile_options& opts, b200_network& net) {
@@ -1269,3 +1269,30 @@ void lower_graph(const b200_graph& g, const b200_compile_options& opts, b200_net
 }
 
 }  // namespace b200
+
+// The planner on its own (unit-testable without a device): boxes are (first, last, bytes) over execution
+// indices, last < 0 = "lives to the end" (MemorySolver::Box, mkldnn_memory_solver.hpp:52-69).
+extern "C" int b200_plan_arena(int32_t n_boxes, const int64_t* bytes, const int32_t* first, const int32_t* last, int64_t* offsets,
+                               int64_t* total_bytes) {
+  if (n_boxes < 0 || (n_boxes > 0 && (!bytes || !first || !last || !offsets)) || !total_bytes) {
+    b200::set_last_error("b200_plan_arena: null argument");
+    return B200_ERR_INVALID;
+  }
+  std::vector<b200::ArenaBox> boxes((size_t)n_boxes);
+  int max_idx = 0;
+  for (int i = 0; i < n_boxes; ++i) max_idx = std::max(max_idx, std::max(first[i], last[i]));
+  for (int i = 0; i < n_boxes; ++i) {
+    if (bytes[i] < 0 || first[i] < 0) {
+      b200::set_last_error("b200_plan_arena: negative size or start");
+      return B200_ERR_INVALID;
+    }
+    boxes[i].bytes = bytes[i];
+    boxes[i].first = first[i];
+    boxes[i].last = last[i] < 0 ? max_idx + 1 : last[i];
+  }
+  int64_t total = 0;
+  b200::plan_arena(boxes, total);
+  for (int i = 0; i < n_boxes; ++i) offsets[i] = boxes[i].offset;
+  *total_bytes = total;
+  return B200_OK;
+}

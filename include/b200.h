@@ -195,6 +195,12 @@ B200_API int b200_network_exec_node(const b200_network* net, int index, b200_exe
 /* key in {"arena_bytes","weight_bytes","flops","bytes","num_kernels","device","precision"} */
 B200_API int b200_network_stat(const b200_network* net, const char* key, double* value);
 
+/* The static activation-memory planner on its own: boxes (first, last, bytes) over execution indices,
+ * last < 0 = lives to the end; writes the offset of every box and the arena size.  Replaces
+ * MemorySolver::solve/getOffset (inference-engine/src/mkldnn_plugin/mkldnn_memory_solver.cpp:51-96,126-131). */
+B200_API int b200_plan_arena(int32_t n_boxes, const int64_t* bytes, const int32_t* first, const int32_t* last, int64_t* offsets,
+                             int64_t* total_bytes);
+
 /* ---- infer requests --------------------------------------------------------------------- */
 B200_API int b200_request_create(b200_network* net, b200_request** out);
 B200_API void b200_request_destroy(b200_request* req);
