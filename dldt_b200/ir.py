@@ -42,7 +42,7 @@ def serialize(func, xml_path, bin_path=None):
     out_port = {}   # (value id) -> (layer id, port id)
 
     def add_const(arr, name):
-        arr = np.ascontiguousarray(arr)
+        arr = np.asarray(arr, order="C")   # keeps rank 0 (ascontiguousarray would promote scalars to rank 1)
         et, prec = _NP_PREC[str(arr.dtype)]
         off = len(blob)
         blob.extend(arr.tobytes())

@@ -24,7 +24,7 @@ if [ ! -d "$REF/inference-engine" ]; then
   echo "build_ref.sh: $REF not present (GPU box?) - using prebuilt oracle/_ref if any" >&2
   [ -f "$OUT/lib/libinference_engine.so" ] && exit 0 || exit 3
 fi
-if [ -f "$OUT/lib/libMKLDNNPlugin.so" ] && [ -f "$OUT/bin/benchmark_app" ] && [ "${FORCE:-0}" != 1 ]; then
+if [ -f "$OUT/lib/libMKLDNNPlugin.so" ] && [ -f "$OUT/bin/benchmark_app" ] && [ -f "$OUT/bin/ie_run" ] && [ "${FORCE:-0}" != 1 ]; then
   echo "build_ref.sh: oracle/_ref already built (FORCE=1 to rebuild)"; exit 0
 fi
 
@@ -81,6 +81,10 @@ cat > "$OUT/lib/plugins.xml" <<XML
     </plugins>
 </ie>
 XML
+# ie_run: the small driver (tools/ie_run.cpp, OUR source) that feeds raw inputs through the reference's public API;
+# compiled against the reference headers where they lie, linked to the libraries built above
+/usr/bin/g++ -O2 -std=c++14 -include cstdint -w -I"$REF/inference-engine/include" -I"$REF/ngraph/core/include" \
+    "$HERE/../tools/ie_run.cpp" -o "$OUT/bin/ie_run" -L"$OUT/lib" -linference_engine -lngraph -Wl,-rpath,'$ORIGIN/../lib'
 echo "$WORK/src" > "$OUT/BUILT_FROM.txt"
 date -u +%FT%TZ >> "$OUT/BUILT_FROM.txt"
 [ "${KEEP_REF_BUILD:-1}" = 1 ] || rm -rf "$WORK"

@@ -1,0 +1,44 @@
+"""The CUDA path (through the C ABI) against the committed reference outputs (tests/golden/ref_cases.npz, produced
+by the unmodified reference CPU plugin).  fp32 mode: rel-L2 <= 1e-4 and bit-exact indices (north star); bf16: <= 1e-2
+(3e-2 on the deep tiny nets, whose random-init logits are small differences of large sums)."""
+import numpy as np
+import pytest
+
+from tests import golden_cases
+from tests.test_oracle_golden import compare, compare_detections, golden_outputs
+from tests.util import run_b200
+
+pytestmark = pytest.mark.gpu
+
+# integer-valued inputs: exact in bf16/fp16 too, so the index outputs must still match
+LOWP_SKIP = {"nms_corner_sorted", "nms_center_unsorted", "nms_score_ties", "nms_keep_nothing", "detout_ssd_like", "detout_corner_clip",
+             "detout_not_shared", "detout_var_in_target", "net_tiny_ssd", "topk_imagenet_top5"}
+LOWP_TOL = {"net_tiny_resnet": 3e-2, "net_tiny_mobilenet": 3e-2, "net_tiny_bert": 3e-2, "unary_activations": 2e-2, "binary_broadcast": 2e-2}
+
+
+@pytest.mark.parametrize("case", sorted(golden_cases.CASES))
+def test_fp32_matches_reference_cpu_plugin(case):
+    f, inputs = golden_cases.CASES[case]()
+    ref = golden_outputs("cpu", case)
+    got, _ = run_b200(f, inputs, "FP32")
+    assert set(got) == set(ref)
+    for k in ref:
+        if "det" in k and ref[k].shape[-1] == 7:
+            compare_detections(got[k], ref[k], "%s/%s" % (case, k), tol=1e-4)
+        else:
+            compare(got[k], ref[k], "%s/%s" % (case, k), tol=1e-4)
+
+
+@pytest.mark.parametrize("precision", ["BF16", "FP16"])
+@pytest.mark.parametrize("case", sorted(set(golden_cases.CASES) - LOWP_SKIP))
+def test_low_precision_matches_reference_cpu_plugin(case, precision):
+    f, inputs = golden_cases.CASES[case]()
+    ref = golden_outputs("cpu", case)
+    got, _ = run_b200(f, inputs, precision)
+    tol = LOWP_TOL.get(case, 1e-2)
+    for k in ref:
+        if golden_cases.is_index_output(ref[k]):
+            if case.startswith("topk_ties") or case == "topk_axis0":
+                np.testing.assert_array_equal(got[k], ref[k])
+            continue
+        compare(got[k], ref[k], "%s/%s" % (case, k), tol=tol)
