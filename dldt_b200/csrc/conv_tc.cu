@@ -24,10 +24,13 @@
 #include "common.h"
 #include "kernels.h"
 #include "ptx_sm100.cuh"
+#include "tc_common.cuh"
 
 namespace b200 {
 
 namespace {
+
+using namespace tc;
 
 constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 x 2 B = 128 B = one swizzle row
@@ -43,38 +46,8 @@ constexpr int tc_smem_bytes() {
   return TcCfg<BN>::STAGES * (A_STAGE_BYTES + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
-template <typename T> struct TcType;
-template <> struct TcType<__nv_bfloat16> { static constexpr int is_bf16 = 1; };
-template <> struct TcType<__half> { static constexpr int is_bf16 = 0; };
-
-template <typename T>
-__device__ __forceinline__ float to_f32(T v);
-template <> __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
-template <> __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
-
-template <typename T>
-__device__ __forceinline__ uint32_t pack2(float a, float b);
-template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
-  __half2 v = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-template <typename T>
-__device__ __forceinline__ void unpack2(uint32_t u, float& a, float& b);
-template <> __device__ __forceinline__ void unpack2<__nv_bfloat16>(uint32_t u, float& a, float& b) {
-  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
-  a = __low2float(v); b = __high2float(v);
-}
-template <> __device__ __forceinline__ void unpack2<__half>(uint32_t u, float& a, float& b) {
-  __half2 v = *reinterpret_cast<__half2*>(&u);
-  a = __low2float(v); b = __high2float(v);
-}
-
-template <typename T, int BN>
-__global__ void __launch_bounds__(160, 2) conv_tc_kernel(const ConvParams p) {
+template <typename T, int BN, bool GEN>
+__global__ void __launch_bounds__(160, 2) conv_tc_kernel(const ConvParams p, const EpiAct e1, const EpiAct e2) {
   constexpr int STAGES = TcCfg<BN>::STAGES;
   constexpr int LAG = TcCfg<BN>::LAG;
   constexpr int B_STAGE_BYTES = BN * 128;
@@ -229,17 +202,15 @@ __global__ void __launch_bounds__(160, 2) conv_tc_kernel(const ConvParams p) {
           f[2] = __uint_as_float(v[q * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[q * 8 + 3]) + b0.w;
           f[4] = __uint_as_float(v[q * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[q * 8 + 5]) + b1.y;
           f[6] = __uint_as_float(v[q * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[q * 8 + 7]) + b1.w;
-          if (p.act1 != ACT_NONE) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = act_apply(f[e], p.act1, p.a1, p.b1);
-          }
+          epi_act8<GEN>(f, e1);
           if (has_res) {
             const uint4 rv = ptx::ld_shared_v4(rrow + (uint32_t)c0 * 2u);
             float r[8];
             unpack2<T>(rv.x, r[0], r[1]); unpack2<T>(rv.y, r[2], r[3]);
             unpack2<T>(rv.z, r[4], r[5]); unpack2<T>(rv.w, r[6], r[7]);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = act_apply(f[e] + r[e], p.act2, p.a2, p.b2);
+            for (int e = 0; e < 8; ++e) f[e] += r[e];
+            epi_act8<GEN>(f, e2);
           }
           if (p.out_f32) {
             ptx::st_shared_v4(srow + (uint32_t)c0 * 4u, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
@@ -288,7 +259,15 @@ void launch_tc(const ConvParams& p, cudaStream_t s) {
   const int m_tiles = (p.M + BM - 1) / BM;
   const int n_tiles = p.Cout_alloc / BN;
   dim3 grid((unsigned)(m_tiles * n_tiles), 1, (unsigned)p.batch);
-  conv_tc_kernel<T, BN><<<grid, 160, smem, s>>>(p);
+  auto epi = [](int kind, float a, float b) {
+    EpiAct e;
+    e.kind = kind; e.a = a; e.b = b;
+    e.lo = kind == ACT_RELU ? 0.f : a;
+    e.hi = kind == ACT_RELU ? __builtin_huge_valf() : b;
+    return e;
+  };
+  if (conv_acts_are_clamps(p)) conv_tc_kernel<T, BN, false><<<grid, 160, smem, s>>>(p, epi(p.act1, p.a1, p.b1), epi(p.act2, p.a2, p.b2));
+  else conv_tc_kernel<T, BN, true><<<grid, 160, smem, s>>>(p, epi(p.act1, p.a1, p.b1), epi(p.act2, p.a2, p.b2));
 }
 
 }  // namespace
@@ -297,10 +276,15 @@ int conv_tc_pick_bn(int cout_p) { return cout_p <= 64 ? 64 : 128; }
 
 // Opt in to >48 KB dynamic shared memory on the current device (called once per device at compile).
 void conv_tc_init_device() {
-  cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<64>());
-  cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<128>());
-  cudaFuncSetAttribute(conv_tc_kernel<__half, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<64>());
-  cudaFuncSetAttribute(conv_tc_kernel<__half, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<128>());
+  auto opt_in = [](auto kernel, int bytes) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); };
+  opt_in(conv_tc_kernel<__nv_bfloat16, 64, false>, tc_smem_bytes<64>());
+  opt_in(conv_tc_kernel<__nv_bfloat16, 64, true>, tc_smem_bytes<64>());
+  opt_in(conv_tc_kernel<__nv_bfloat16, 128, false>, tc_smem_bytes<128>());
+  opt_in(conv_tc_kernel<__nv_bfloat16, 128, true>, tc_smem_bytes<128>());
+  opt_in(conv_tc_kernel<__half, 64, false>, tc_smem_bytes<64>());
+  opt_in(conv_tc_kernel<__half, 64, true>, tc_smem_bytes<64>());
+  opt_in(conv_tc_kernel<__half, 128, false>, tc_smem_bytes<128>());
+  opt_in(conv_tc_kernel<__half, 128, true>, tc_smem_bytes<128>());
 }
 
 void launch_conv_tc(const ConvParams& p, int dtype, int bn, cudaStream_t s) {

@@ -1,0 +1,424 @@
+// Persistent, warp-specialised implicit-GEMM convolution / GEMM on tcgen05 (sm_100a), version 2.
+//
+//   D[M, Cout] = im2col(X)[M, K] * Wp[Cout, K]^T  (+ bias, activation, + residual, activation)
+//
+// Same arithmetic contract as conv_tc.cu (ngraph reference/convolution.hpp:89-186; post-op chain of
+// nodes/mkldnn_conv_node.cpp:355-403); what changes is how the SM is kept busy:
+//
+//   * one CTA per SM, looping over output tiles (static round-robin; n-tiles of one m-tile run on
+//     neighbouring SMs at the same time so the activation tile is shared through L2)
+//   * TMEM holds TWO accumulators (2 x BN fp32 columns): the epilogue of tile i overlaps the main loop of tile i+1
+//   * operand feed by TMA wherever the operand is a plain matrix: weights always ([Cout_alloc][Ktot], 128B-swizzled
+//     boxes of 64 x BN); activations too when the convolution is a GEMM (1x1, stride 1, no padding, and FullyConnected).
+//     Other geometries gather the A tile with 16-byte cp.async (zero-fill for padding) exactly as conv_tc.cu does.
+//   * epilogue: TMEM -> registers -> bias/act/residual -> 128B-swizzled staging tile -> ONE TMA tensor store per 64
+//     output channels (clipped at the M / Cout tails by the tensor map); the residual tile arrives through a TMA load
+//     issued at the START of the tile (double buffered), so its HBM latency hides behind the main loop
+//
+//   warp 0-3  A producers (cp.async gather; idle in TMA-A mode)        warp 8  MMA issuer (one elected lane)
+//   warp 4-7  epilogue (TMEM lane quarter = warp % 4)                  warp 9  TMA issuer (weights, residual, A)
+//
+// mbarriers: full[s]/empty[s] (operand stages), tfull[a]/tempty[a] (accumulators), rfull[b]/rempty[b] (residual tiles).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <mutex>
+
+#include "act.cuh"
+#include "common.h"
+#include "kernels.h"
+#include "ptx_sm100.cuh"
+#include "tc_common.cuh"
+
+namespace b200 {
+
+namespace {
+
+using namespace tc;
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_BYTES = BM * 128;        // 128 rows x 64 elements x 2 B
+constexpr int SLAB_BYTES = BM * 128;     // one 64-channel slab of the output / residual tile
+constexpr int NUM_A_PRODUCERS = 128;
+constexpr int NUM_THREADS = 320;
+constexpr int LAG = 2;                   // cp.async groups in flight before the oldest is published
+
+template <int BN> struct Cfg2;
+template <> struct Cfg2<64>  { static constexpr int STAGES = 6; };
+template <> struct Cfg2<128> { static constexpr int STAGES = 4; };
+
+template <int BN>
+constexpr int tc2_smem_bytes() {
+  return Cfg2<BN>::STAGES * (A_BYTES + BN * 128) + (BN / 64) * SLAB_BYTES /*out*/ + 2 * (BN / 64) * SLAB_BYTES /*residual x2*/ +
+         1024 /*align slack*/ + 256 /*barriers*/;
+}
+
+struct Tc2Args {
+  CUtensorMap tm_a;   // activations as [M][Cin_p]   (TMA-A mode only)
+  CUtensorMap tm_w;   // packed weights [Cout_alloc][Ktot]
+  CUtensorMap tm_y;   // output [M][Cout_p], row pitch ldy
+  CUtensorMap tm_r;   // residual, same geometry as the output
+  ConvParams p;
+  EpiAct e1, e2;      // activation after bias / after the residual sum
+  int a_tma;
+  int num_tiles, n_tiles;
+};
+
+template <typename T, int BN, bool GEN>
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_constant__ Tc2Args args) {
+  constexpr int STAGES = Cfg2<BN>::STAGES;
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int SLABS = BN / 64;
+  constexpr uint32_t OUT_OFF = STAGES * STAGE_BYTES;
+  constexpr uint32_t RES_OFF = OUT_OFF + SLABS * SLAB_BYTES;
+  constexpr uint32_t BAR_OFF = RES_OFF + 2 * SLABS * SLAB_BYTES;
+  const ConvParams& p = args.p;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_al + BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* rfull_bar = tempty_bar + 2;
+  uint64_t* rempty_bar = rfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nkb = p.Ktot / BK;
+  const int num_tiles = args.num_tiles, n_tiles = args.n_tiles;
+  const bool a_tma = args.a_tma != 0;
+  const bool has_res = p.res != nullptr;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], a_tma ? 1u : (uint32_t)NUM_A_PRODUCERS + 1u);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull_bar[a], 1);
+      ptx::mbar_init(&tempty_bar[a], 4);
+      ptx::mbar_init(&rfull_bar[a], 1);
+      ptx::mbar_init(&rempty_bar[a], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 9 && lane == 0) {
+    ptx::tma_prefetch_desc(&args.tm_w);
+    ptx::tma_prefetch_desc(&args.tm_y);
+    if (a_tma) ptx::tma_prefetch_desc(&args.tm_a);
+    if (has_res) ptx::tma_prefetch_desc(&args.tm_r);
+  }
+  if (warp == 8) {
+    ptx::tmem_alloc(tmem_slot, 2 * BN);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== A producers: cp.async gather (skipped when TMA feeds A) =====================
+    if (!a_tma) {
+      const T* __restrict__ xg = reinterpret_cast<const T*>(p.x);
+      const int t = threadIdx.x;
+      const int c = t & 7;          // 16-byte chunk within the 128-byte K row
+      const int r0 = t >> 3;        // first row of this thread (rows r0 + 16*i)
+      const uint32_t sw_off = (uint32_t)((c ^ (r0 & 7)) << 4);
+      const int HoWo = p.Ho * p.Wo;
+      const int cpc = p.Cin_p >> 3;       // 16-byte chunks per filter tap
+      const int taps = p.kh * p.kw;
+      uint32_t kbg = 0;                   // k-blocks issued so far (all tiles)
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * BM;
+        int hi0[8], wi0[8];
+        int64_t xoff[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int m = m0 + r0 + 16 * i;
+          bool rv = m < p.M;
+          int mm = rv ? m : 0;
+          int n = mm / HoWo;
+          int rem = mm - n * HoWo;
+          int ho = rem / p.Wo;
+          int wo = rem - ho * p.Wo;
+          hi0[i] = rv ? ho * p.sh - p.pt : -(1 << 28);   // invalid rows never pass the bounds test
+          wi0[i] = wo * p.sw - p.pl;
+          xoff[i] = (int64_t)n * p.H * p.W * p.Cin_p;
+        }
+        int cc = c, tap = 0, fr = 0, fs = 0;  // chunk within tap, tap index, filter row/col
+        while (cc >= cpc) { cc -= cpc; ++tap; if (++fs == p.kw) { fs = 0; ++fr; } }
+        for (int kb = 0; kb < nkb + LAG; ++kb) {
+          if (kb < nkb) {
+            const uint32_t g = kbg + (uint32_t)kb;
+            const int s = (int)(g % STAGES);
+            ptx::mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
+            const uint32_t a_dst = smem_base + s * STAGE_BYTES + r0 * 128 + sw_off;
+            const bool kvalid = tap < taps;
+            const int dh_off = fr * p.dh, dw_off = fs * p.dw;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              int hi = hi0[i] + dh_off, wi = wi0[i] + dw_off;
+              bool ok = kvalid && (unsigned)hi < (unsigned)p.H && (unsigned)wi < (unsigned)p.W;
+              const T* src = ok ? xg + xoff[i] + ((int64_t)hi * p.W + wi) * p.Cin_p + cc * 8 : xg;
+              ptx::cp_async16(a_dst + i * (16 * 128), src, ok ? 16u : 0u);
+            }
+            cc += 8;
+            while (cc >= cpc) { cc -= cpc; ++tap; if (++fs == p.kw) { fs = 0; ++fr; } }
+          }
+          ptx::cp_async_commit();
+          if (kb >= LAG) {
+            ptx::cp_async_wait<LAG>();
+            ptx::fence_proxy_async();
+            ptx::mbar_arrive(&full_bar[(kbg + (uint32_t)(kb - LAG)) % STAGES]);
+          }
+        }
+        kbg += (uint32_t)nkb;
+      }
+    }
+  } else if (warp < 8) {
+    // ===================== epilogue =====================
+    const int q = warp - 4;                     // TMEM lane quarter of this warp (== warp % 4)
+    const int row = q * 32 + lane;
+    const uint32_t rsw = (uint32_t)(row & 7);
+    const bool store_thread = threadIdx.x == 4 * 32;
+    const uint32_t out_row = smem_base + OUT_OFF + (uint32_t)row * 128u;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile / n_tiles) * BM;
+      const int n0 = (tile % n_tiles) * BN;
+      const int ncols = min(BN, p.Cout_p - n0);           // valid output channels of this tile (multiple of 8)
+      const int nslab = (ncols + 63) >> 6;
+      const uint32_t acc = it & 1u;
+      const uint32_t par = (it >> 1) & 1u;
+      const uint32_t res_row = smem_base + RES_OFF + acc * (SLABS * SLAB_BYTES) + (uint32_t)row * 128u;
+      const float* __restrict__ bias = p.bias + n0;
+
+      ptx::mbar_wait(&tfull_bar[acc], par);                // accumulator complete
+      ptx::tc_fence_after();
+      if (has_res) ptx::mbar_wait(&rfull_bar[acc], par);   // residual tile landed
+      if (store_thread) ptx::bulk_wait_read0();            // previous tile's TMA store has finished reading the staging tile
+      ptx::named_bar_sync(1, 128);
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        if (j * 32 >= ncols) break;                        // warp-uniform
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(j * 32), v);
+        ptx::tmem_ld_wait();
+        const uint32_t slab_off = (uint32_t)(j >> 1) * SLAB_BYTES;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {                      // groups of 8 output channels = one 16-byte chunk
+          const int c0 = j * 32 + g * 8;
+          if (c0 < ncols) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
+            float f[8];
+            f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+            f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+            f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+            f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+            epi_act8<GEN>(f, args.e1);
+            const uint32_t chunk = (uint32_t)((j & 1) * 4 + g);          // 16-byte chunk within the 128-byte slab row
+            const uint32_t sw = slab_off + ((chunk ^ rsw) << 4);
+            if (has_res) {
+              const uint4 rv = ptx::ld_shared_v4(res_row + sw);
+              float r[8];
+              unpack2<T>(rv.x, r[0], r[1]); unpack2<T>(rv.y, r[2], r[3]);
+              unpack2<T>(rv.z, r[4], r[5]); unpack2<T>(rv.w, r[6], r[7]);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] += r[e];
+              epi_act8<GEN>(f, args.e2);
+            }
+            ptx::st_shared_v4(out_row + sw, make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7])));
+          }
+        }
+      }
+      // accumulator + residual buffers are free again
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(&tempty_bar[acc]);
+        if (has_res) ptx::mbar_arrive(&rempty_bar[acc]);
+      }
+      ptx::fence_proxy_async();                            // staging writes -> visible to the TMA engine
+      ptx::named_bar_sync(1, 128);
+      if (store_thread) {
+        for (int h = 0; h < nslab; ++h) ptx::tma_store_2d(&args.tm_y, smem_base + OUT_OFF + (uint32_t)h * SLAB_BYTES, n0 + h * 64, m0);
+        ptx::bulk_commit();
+      }
+    }
+    if (store_thread) ptx::bulk_wait_all0();
+  } else if (warp == 8) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(TcType<T>::is_bf16, BM, BN);
+      uint32_t g = 0, it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1u;
+        ptx::mbar_wait(&tempty_bar[acc], ((it >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const int s = (int)(g % STAGES);
+          ptx::mbar_wait(&full_bar[s], (g / STAGES) & 1);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = smem_base + s * STAGE_BYTES;
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = ptx::make_smem_desc_sw128(a_addr + k * 32);
+            const uint64_t db = ptx::make_smem_desc_sw128(b_addr + k * 32);
+            ptx::umma_f16(d_tmem, da, db, idesc, (kb | k) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[s]);     // frees this stage once the MMAs above have read it
+        }
+        ptx::umma_commit(&tfull_bar[acc]);     // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== TMA issuer (one thread): weights, A (GEMM mode), residual =====================
+    if (lane == 0) {
+      uint32_t g = 0, it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int m0 = (tile / n_tiles) * BM;
+        const int n0 = (tile % n_tiles) * BN;
+        if (has_res) {
+          const uint32_t rb = it & 1u;
+          const int ncols = min(BN, p.Cout_p - n0);
+          const int nslab = (ncols + 63) >> 6;
+          ptx::mbar_wait(&rempty_bar[rb], ((it >> 1) & 1u) ^ 1u);
+          ptx::mbar_arrive_expect_tx(&rfull_bar[rb], (uint32_t)nslab * SLAB_BYTES);
+          for (int h = 0; h < nslab; ++h)
+            ptx::tma_load_2d(smem_base + RES_OFF + rb * (SLABS * SLAB_BYTES) + (uint32_t)h * SLAB_BYTES, &args.tm_r, &rfull_bar[rb], n0 + h * 64, m0);
+        }
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const int s = (int)(g % STAGES);
+          ptx::mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
+          const uint32_t a_dst = smem_base + s * STAGE_BYTES;
+          ptx::mbar_arrive_expect_tx(&full_bar[s], a_tma ? (uint32_t)STAGE_BYTES : (uint32_t)B_BYTES);
+          if (a_tma) ptx::tma_load_2d(a_dst, &args.tm_a, &full_bar[s], kb * BK, m0);
+          ptx::tma_load_2d(a_dst + A_BYTES, &args.tm_w, &full_bar[s], kb * BK, n0);
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) ptx::tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 encode_tiled_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess) ptr = nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }();
+  return fn;
+}
+
+// [outer][inner] row-major matrix of 2-byte elements, 128B-swizzled boxes of box_inner x box_outer
+CUtensorMap make_tmap_2d(const void* base, bool bf16, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner,
+                         uint32_t box_outer) {
+  auto enc = encode_tiled_fn();
+  B200_CHECK(enc, B200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  CUtensorMap m;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled failed (" << (int)r << ") for a [" << outer << "][" << inner << "] matrix, pitch "
+                                                                                  << pitch_bytes << " B, base " << base);
+  return m;
+}
+
+int g_sm_count = 0;
+
+EpiAct make_epi(int kind, float a, float b) {
+  EpiAct e;
+  e.kind = kind; e.a = a; e.b = b;
+  e.lo = kind == ACT_RELU ? 0.f : a;
+  e.hi = kind == ACT_RELU ? __builtin_huge_valf() : b;
+  return e;
+}
+
+template <typename T, int BN>
+void launch_tc2(const ConvParams& p, bool bf16, cudaStream_t s) {
+  Tc2Args a;
+  memset(&a, 0, sizeof(a));
+  a.p = p;
+  a.e1 = make_epi(p.act1, p.a1, p.b1);
+  a.e2 = make_epi(p.act2, p.a2, p.b2);
+  const int m_tiles = (p.M + BM - 1) / BM;
+  a.n_tiles = p.Cout_alloc / BN;
+  a.num_tiles = m_tiles * a.n_tiles;
+  a.a_tma = conv_tc2_a_is_matrix(p) ? 1 : 0;
+  a.tm_w = make_tmap_2d(p.w, bf16, (uint64_t)p.Ktot, (uint64_t)p.Cout_alloc, (uint64_t)p.w_ld * 2, BK, BN);
+  a.tm_y = make_tmap_2d(p.y, bf16, (uint64_t)p.Cout_p, (uint64_t)p.M, (uint64_t)p.ldy * 2, 64, BM);
+  a.tm_r = p.res ? make_tmap_2d(p.res, bf16, (uint64_t)p.Cout_p, (uint64_t)p.M, (uint64_t)p.ldy * 2, 64, BM) : a.tm_y;
+  a.tm_a = a.a_tma ? make_tmap_2d(p.x, bf16, (uint64_t)p.Cin_p, (uint64_t)p.M, (uint64_t)p.Cin_p * 2, BK, BM) : a.tm_y;
+  const int grid = std::min(a.num_tiles, g_sm_count > 0 ? g_sm_count : 148);
+  if (conv_acts_are_clamps(p)) conv_tc2_kernel<T, BN, false><<<grid, NUM_THREADS, tc2_smem_bytes<BN>(), s>>>(a);
+  else conv_tc2_kernel<T, BN, true><<<grid, NUM_THREADS, tc2_smem_bytes<BN>(), s>>>(a);
+}
+
+}  // namespace
+
+// A is a plain [M][Cin_p] matrix: FullyConnected, or a 1x1 / stride-1 / unpadded convolution over NHWC
+bool conv_tc2_a_is_matrix(const ConvParams& p) {
+  return p.kh == 1 && p.kw == 1 && p.sh == 1 && p.sw == 1 && p.pt == 0 && p.pl == 0 && p.Ho == p.H && p.Wo == p.W && p.Cin_p % 8 == 0;
+}
+
+bool conv_acts_are_clamps(const ConvParams& p) {
+  auto ok = [](int k) { return k == ACT_NONE || k == ACT_RELU || k == ACT_CLAMP; };
+  return ok(p.act1) && ok(p.act2);
+}
+
+bool conv_tc2_supported(const ConvParams& p) {
+  // one weight matrix for the whole launch (batched activation x activation MatMuls stay on conv_tc.cu), weights fully materialised
+  return p.batch == 1 && !p.out_f32 && p.w_rows == p.Cout_alloc && p.w_k == p.Ktot && p.w_ld == p.Ktot;
+}
+
+void conv_tc2_init_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+  auto opt_in = [](auto kernel, int bytes) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); };
+  opt_in(conv_tc2_kernel<__nv_bfloat16, 64, false>, tc2_smem_bytes<64>());
+  opt_in(conv_tc2_kernel<__nv_bfloat16, 64, true>, tc2_smem_bytes<64>());
+  opt_in(conv_tc2_kernel<__nv_bfloat16, 128, false>, tc2_smem_bytes<128>());
+  opt_in(conv_tc2_kernel<__nv_bfloat16, 128, true>, tc2_smem_bytes<128>());
+  opt_in(conv_tc2_kernel<__half, 64, false>, tc2_smem_bytes<64>());
+  opt_in(conv_tc2_kernel<__half, 64, true>, tc2_smem_bytes<64>());
+  opt_in(conv_tc2_kernel<__half, 128, false>, tc2_smem_bytes<128>());
+  opt_in(conv_tc2_kernel<__half, 128, true>, tc2_smem_bytes<128>());
+}
+
+void launch_conv_tc2(const ConvParams& p, int dtype, int bn, cudaStream_t s) {
+  B200_CHECK(conv_tc2_supported(p), B200_ERR_UNSUPPORTED, "conv_tc2: unsupported launch (batched or partial weights)");
+  B200_CHECK(p.Ktot % BK == 0 && p.Cin_p % 8 == 0 && p.Cout_alloc % bn == 0 && p.Cout_p % 8 == 0 && p.ldy % 8 == 0, B200_ERR_INVALID,
+             "conv_tc2: bad geometry");
+  const bool bf16 = dtype == B200_BF16;
+  B200_CHECK(bf16 || dtype == B200_F16, B200_ERR_UNSUPPORTED, "conv_tc2: dtype must be bf16/f16");
+  if (bf16) {
+    if (bn == 64) launch_tc2<__nv_bfloat16, 64>(p, true, s); else launch_tc2<__nv_bfloat16, 128>(p, true, s);
+  } else {
+    if (bn == 64) launch_tc2<__half, 64>(p, false, s); else launch_tc2<__half, 128>(p, false, s);
+  }
+}
+
+}  // namespace b200

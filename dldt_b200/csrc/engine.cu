@@ -225,6 +225,7 @@ int b200_compile(const b200_graph* g, const b200_compile_options* opts, b200_net
                                                               << ") is not an sm_100 part; kernels are built for sm_100a only");
       B200_CUDA(cudaSetDevice(opts->device));
       conv_tc_init_device();
+      conv_tc2_init_device();
       detect_init_device();
       size_t wb = std::max<size_t>(net->weights_host.size(), 16);
       B200_CUDA(cudaMalloc((void**)&net->weights_dev, wb));

@@ -36,6 +36,13 @@ struct ConvParams {
 void launch_conv_tc(const ConvParams& p, int dtype, int bn, cudaStream_t s);
 int conv_tc_pick_bn(int cout_p);
 void conv_tc_init_device();
+// true when both fused activations are none / ReLU / Clamp (the two-instruction epilogue path of the tcgen05 kernels)
+bool conv_acts_are_clamps(const ConvParams& p);
+// Persistent TMA-fed variant (conv_tc2.cu): used whenever one weight matrix serves the whole launch.
+bool conv_tc2_supported(const ConvParams& p);
+bool conv_tc2_a_is_matrix(const ConvParams& p);
+void launch_conv_tc2(const ConvParams& p, int dtype, int bn, cudaStream_t s);
+void conv_tc2_init_device();
 // CUDA-core fp32 path (fp32 mode: 1e-4 parity; also the reference for tcgen05 unit tests).
 // Same parameter block; x/w/res/y are fp32, weights [Cout_alloc][Ktot] fp32.
 void launch_conv_f32(const ConvParams& p, cudaStream_t s);

@@ -173,3 +173,21 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int is_bf16, int M, int N)
 
 }  // namespace ptx
 }  // namespace b200
+
+// ---- additions for the persistent, TMA-fed kernel (conv_tc2.cu) ---------------------------------------
+namespace b200 {
+namespace ptx {
+
+// 2-D tiled TMA store: smem tile (in the tensor map's swizzle) -> global; OOB parts of the box are clipped.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src_smem), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// named barrier among `count` threads (count % 32 == 0); id 0 is __syncthreads
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+}  // namespace ptx
+}  // namespace b200

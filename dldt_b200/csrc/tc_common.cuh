@@ -1,0 +1,65 @@
+// Small helpers shared by the tcgen05 kernels (conv_tc.cu, conv_tc2.cu): element type traits and bf16/fp16 packing.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cstdint>
+
+#include "act.cuh"
+
+namespace b200 {
+namespace tc {
+
+template <typename T> struct TcType;
+template <> struct TcType<__nv_bfloat16> { static constexpr int is_bf16 = 1; };
+template <> struct TcType<__half> { static constexpr int is_bf16 = 0; };
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+
+template <typename T>
+__device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <typename T>
+__device__ __forceinline__ void unpack2(uint32_t u, float& a, float& b);
+template <> __device__ __forceinline__ void unpack2<__nv_bfloat16>(uint32_t u, float& a, float& b) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  a = __low2float(v); b = __high2float(v);
+}
+template <> __device__ __forceinline__ void unpack2<__half>(uint32_t u, float& a, float& b) {
+  __half2 v = *reinterpret_cast<__half2*>(&u);
+  a = __low2float(v); b = __high2float(v);
+}
+
+
+// Epilogue activation over 8 accumulators.  GENERIC == false covers the activations that are a clamp (none / ReLU / Clamp,
+// i.e. every ResNet / MobileNet / SSD layer) with two instructions per element; GENERIC == true keeps the full table of
+// act.cuh but as ONE rolled loop, so the switch is instantiated once per call site instead of once per element (the fully
+// unrolled form made the kernel 26k instructions long and the epilogue instruction-fetch bound: profiles/r1_run2).
+struct EpiAct {
+  int kind;       // Act code (generic path)
+  float a, b;     // its parameters
+  float lo, hi;   // clamp bounds (fast path)
+};
+template <bool GENERIC>
+__device__ __forceinline__ void epi_act8(float (&f)[8], const EpiAct& s) {
+  if (s.kind == 0) return;   // ACT_NONE (warp-uniform)
+  if constexpr (!GENERIC) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(f[e], s.lo), s.hi);
+  } else {
+#pragma unroll 1
+    for (int e = 0; e < 8; ++e) f[e] = act_apply(f[e], s.kind, s.a, s.b);
+  }
+}
+
+}  // namespace tc
+}  // namespace b200

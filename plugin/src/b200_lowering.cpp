@@ -1,0 +1,347 @@
+// ngraph::Function -> b200_graph.  See b200_lowering.hpp.
+#include "b200_lowering.hpp"
+
+#include <ie_common.h>
+
+#include <map>
+#include <ngraph/graph_util.hpp>
+#include <ngraph/opsets/opset1.hpp>
+#include <ngraph/opsets/opset3.hpp>
+#include <ngraph/opsets/opset4.hpp>
+#include <ngraph/opsets/opset5.hpp>
+#include <ngraph/opsets/opset6.hpp>
+#include <ngraph/opsets/opset7.hpp>
+#include <ngraph/pass/constant_folding.hpp>
+#include <ngraph/pass/manager.hpp>
+#include <transformations/common_optimizations/common_optimizations.hpp>
+#include <transformations/op_conversions/convert_divide.hpp>
+#include <transformations/op_conversions/convert_gelu.hpp>
+#include <transformations/op_conversions/convert_minimum_to_power_and_max.hpp>
+#include <transformations/op_conversions/convert_negative.hpp>
+#include <transformations/op_conversions/convert_reduce_to_pooling.hpp>
+#include <transformations/op_conversions/convert_subtract.hpp>
+#include <transformations/op_conversions/gelu7_downgrade.hpp>
+#include <transformations/op_conversions/hsigmoid_decomposition.hpp>
+#include <transformations/op_conversions/hswish_decomposition.hpp>
+#include <transformations/op_conversions/mvn6_decomposition.hpp>
+#include <utility>
+#include <vector>
+
+namespace B200Plugin {
+
+using ngraph::as_type_ptr;
+using NodePtr = std::shared_ptr<ngraph::Node>;
+
+std::shared_ptr<ngraph::Function> TransformNetwork(const std::shared_ptr<const ngraph::Function>& function) {
+    auto f = ngraph::clone_function(*function);
+    ngraph::pass::Manager manager;
+    manager.register_pass<ngraph::pass::CommonOptimizations>();
+    manager.register_pass<ngraph::pass::ConstantFolding>();
+    // ops the kernel library executes natively must not be decomposed (same stance as mkldnn_plugin.cpp:281-300)
+    auto cfg = manager.get_pass_config();
+    cfg->disable<ngraph::pass::ConvertGELU>();
+    cfg->disable<ngraph::pass::Gelu7Downgrade>();
+    cfg->disable<ngraph::pass::HSwishDecomposition>();
+    cfg->disable<ngraph::pass::HSigmoidDecomposition>();
+    cfg->disable<ngraph::pass::MVN6Decomposition>();
+    cfg->disable<ngraph::pass::ConvertSubtract>();
+    cfg->disable<ngraph::pass::ConvertDivide>();
+    cfg->disable<ngraph::pass::ConvertNegative>();
+    cfg->disable<ngraph::pass::ConvertMinimum>();
+    cfg->disable<ngraph::pass::ConvertReduceMeanToPooling>();
+    cfg->disable<ngraph::pass::ConvertReduceMaxToPooling>();
+    cfg->disable<ngraph::pass::ConvertReduceSumToPooling>();
+    manager.run_passes(f);
+    return f;
+}
+
+namespace {
+
+int ToDtype(const ngraph::element::Type& t) {
+    switch (t) {
+    case ngraph::element::Type_t::f32: return B200_F32;
+    case ngraph::element::Type_t::f16: return B200_F16;
+    case ngraph::element::Type_t::bf16: return B200_BF16;
+    case ngraph::element::Type_t::i32: return B200_I32;
+    case ngraph::element::Type_t::u8: return B200_U8;
+    case ngraph::element::Type_t::i64: return B200_I64;
+    case ngraph::element::Type_t::i8: return B200_I8;
+    case ngraph::element::Type_t::boolean: return B200_BOOL;
+    default: return -1;
+    }
+}
+
+struct OpDesc {
+    int op = -1;
+    std::vector<int> data_inputs;   // which ngraph inputs are graph inputs of the b200 node (the rest are attributes)
+    std::vector<int32_t> i;
+    std::vector<float> f;
+    bool shape_from_output = false; // RESHAPE-like: target shape = static output shape
+    int dtype = B200_F32;
+    std::string reject;             // non-empty: not supported, with the reason
+};
+
+std::vector<int64_t> ConstInts(const NodePtr& n, size_t input, std::string& err) {
+    auto c = as_type_ptr<ngraph::opset1::Constant>(n->get_input_node_shared_ptr(input));
+    if (!c) {
+        err = "input " + std::to_string(input) + " of " + n->get_friendly_name() + " must be a Constant";
+        return {};
+    }
+    return c->cast_vector<int64_t>();
+}
+
+template <typename T>
+void PushSpatial(OpDesc& d, const T& v) {
+    for (auto x : v) d.i.push_back(static_cast<int32_t>(x));
+}
+
+OpDesc Describe(const NodePtr& n) {
+    OpDesc d;
+    auto all_inputs = [&](size_t count) { for (size_t k = 0; k < count; ++k) d.data_inputs.push_back(static_cast<int>(k)); };
+    auto simple = [&](int op, size_t inputs) { d.op = op; all_inputs(inputs); return d; };
+    const auto& ti = n->get_type_info();
+    std::string err;
+
+    if (as_type_ptr<ngraph::opset1::Parameter>(n)) { d.op = B200_OP_PARAMETER; d.dtype = ToDtype(n->get_output_element_type(0)); return d; }
+    if (as_type_ptr<ngraph::opset1::Constant>(n)) { d.op = B200_OP_CONSTANT; d.dtype = ToDtype(n->get_output_element_type(0)); return d; }
+    if (as_type_ptr<ngraph::opset1::Result>(n)) return simple(B200_OP_RESULT, 1);
+
+    if (auto c = as_type_ptr<ngraph::opset1::Convolution>(n)) {
+        if (c->get_input_shape(0).size() != 4) { d.reject = "only 2D convolutions"; return d; }
+        d.op = B200_OP_CONVOLUTION; all_inputs(2);
+        PushSpatial(d, c->get_strides()); PushSpatial(d, c->get_dilations());
+        d.i.push_back(static_cast<int32_t>(c->get_pads_begin()[0])); d.i.push_back(static_cast<int32_t>(c->get_pads_begin()[1]));
+        d.i.push_back(static_cast<int32_t>(c->get_pads_end()[0])); d.i.push_back(static_cast<int32_t>(c->get_pads_end()[1]));
+        return d;
+    }
+    if (auto c = as_type_ptr<ngraph::opset1::GroupConvolution>(n)) {
+        if (c->get_input_shape(0).size() != 4) { d.reject = "only 2D group convolutions"; return d; }
+        d.op = B200_OP_GROUP_CONVOLUTION; all_inputs(2);
+        PushSpatial(d, c->get_strides()); PushSpatial(d, c->get_dilations());
+        d.i.push_back(static_cast<int32_t>(c->get_pads_begin()[0])); d.i.push_back(static_cast<int32_t>(c->get_pads_begin()[1]));
+        d.i.push_back(static_cast<int32_t>(c->get_pads_end()[0])); d.i.push_back(static_cast<int32_t>(c->get_pads_end()[1]));
+        return d;
+    }
+    if (auto bn = as_type_ptr<ngraph::opset5::BatchNormInference>(n)) {   // x, gamma, beta, mean, var
+        d.op = B200_OP_BATCH_NORM; all_inputs(5); d.f.push_back(static_cast<float>(bn->get_eps_value())); return d;
+    }
+    if (auto bn = as_type_ptr<ngraph::opset1::BatchNormInference>(n)) {   // v0 order: gamma, beta, x, mean, var
+        d.op = B200_OP_BATCH_NORM; d.data_inputs = {2, 0, 1, 3, 4}; d.f.push_back(static_cast<float>(bn->get_eps_value())); return d;
+    }
+    if (as_type_ptr<ngraph::opset1::Add>(n)) return simple(B200_OP_ADD, 2);
+    if (as_type_ptr<ngraph::opset1::Subtract>(n)) return simple(B200_OP_SUBTRACT, 2);
+    if (as_type_ptr<ngraph::opset1::Multiply>(n)) return simple(B200_OP_MULTIPLY, 2);
+    if (as_type_ptr<ngraph::opset1::Divide>(n)) return simple(B200_OP_DIVIDE, 2);
+    if (as_type_ptr<ngraph::opset1::Maximum>(n)) return simple(B200_OP_MAXIMUM, 2);
+    if (as_type_ptr<ngraph::opset1::Minimum>(n)) return simple(B200_OP_MINIMUM, 2);
+    if (as_type_ptr<ngraph::opset1::Power>(n)) return simple(B200_OP_POWER, 2);
+    if (as_type_ptr<ngraph::opset1::SquaredDifference>(n)) return simple(B200_OP_SQUARED_DIFFERENCE, 2);
+    if (as_type_ptr<ngraph::opset1::PRelu>(n)) return simple(B200_OP_PRELU, 2);
+    if (as_type_ptr<ngraph::opset1::Relu>(n)) return simple(B200_OP_RELU, 1);
+    if (as_type_ptr<ngraph::opset1::Sigmoid>(n)) return simple(B200_OP_SIGMOID, 1);
+    if (as_type_ptr<ngraph::opset1::Tanh>(n)) return simple(B200_OP_TANH, 1);
+    if (as_type_ptr<ngraph::opset1::Exp>(n)) return simple(B200_OP_EXP, 1);
+    if (as_type_ptr<ngraph::opset1::Sqrt>(n)) return simple(B200_OP_SQRT, 1);
+    if (as_type_ptr<ngraph::opset1::Abs>(n)) return simple(B200_OP_ABS, 1);
+    if (as_type_ptr<ngraph::opset1::Negative>(n)) return simple(B200_OP_NEGATIVE, 1);
+    if (as_type_ptr<ngraph::opset1::Erf>(n)) return simple(B200_OP_ERF, 1);
+    if (as_type_ptr<ngraph::opset4::HSwish>(n)) return simple(B200_OP_HSWISH, 1);
+    if (as_type_ptr<ngraph::opset5::HSigmoid>(n)) return simple(B200_OP_HSIGMOID, 1);
+    if (as_type_ptr<ngraph::opset4::Mish>(n)) return simple(B200_OP_MISH, 1);
+    if (auto c = as_type_ptr<ngraph::opset1::Clamp>(n)) {
+        d.op = B200_OP_CLAMP; all_inputs(1); d.f = {static_cast<float>(c->get_min()), static_cast<float>(c->get_max())}; return d;
+    }
+    if (auto e = as_type_ptr<ngraph::opset1::Elu>(n)) { d.op = B200_OP_ELU; all_inputs(1); d.f = {static_cast<float>(e->get_alpha())}; return d; }
+    if (as_type_ptr<ngraph::opset4::Swish>(n)) {
+        d.op = B200_OP_SWISH; all_inputs(1); d.f = {1.0f};
+        if (n->get_input_size() > 1) {
+            auto c = as_type_ptr<ngraph::opset1::Constant>(n->get_input_node_shared_ptr(1));
+            if (!c) { d.reject = "Swish beta must be a Constant"; return d; }
+            d.f[0] = c->cast_vector<float>()[0];
+        }
+        return d;
+    }
+    if (auto g = as_type_ptr<ngraph::opset7::Gelu>(n)) {
+        d.op = B200_OP_GELU; all_inputs(1); d.i = {g->get_approximation_mode() == ngraph::op::GeluApproximationMode::TANH ? 1 : 0}; return d;
+    }
+    if (as_type_ptr<ngraph::opset1::Gelu>(n)) { d.op = B200_OP_GELU; all_inputs(1); d.i = {0}; return d; }   // v0/v2: erf form
+    if (auto p = as_type_ptr<ngraph::opset1::MaxPool>(n)) {
+        if (p->get_input_shape(0).size() != 4) { d.reject = "only 2D pooling"; return d; }
+        d.op = B200_OP_MAX_POOL; all_inputs(1);
+        PushSpatial(d, p->get_kernel()); PushSpatial(d, p->get_strides()); PushSpatial(d, p->get_pads_begin()); PushSpatial(d, p->get_pads_end());
+        d.i.push_back(p->get_rounding_type() == ngraph::op::RoundingType::CEIL ? 1 : 0);
+        return d;
+    }
+    if (auto p = as_type_ptr<ngraph::opset1::AvgPool>(n)) {
+        if (p->get_input_shape(0).size() != 4) { d.reject = "only 2D pooling"; return d; }
+        d.op = B200_OP_AVG_POOL; all_inputs(1);
+        PushSpatial(d, p->get_kernel()); PushSpatial(d, p->get_strides()); PushSpatial(d, p->get_pads_begin()); PushSpatial(d, p->get_pads_end());
+        d.i.push_back(p->get_rounding_type() == ngraph::op::RoundingType::CEIL ? 1 : 0);
+        d.i.push_back(p->get_exclude_pad() ? 1 : 0);
+        return d;
+    }
+    {
+        int rop = as_type_ptr<ngraph::opset1::ReduceMean>(n) ? B200_OP_REDUCE_MEAN
+                  : as_type_ptr<ngraph::opset1::ReduceSum>(n) ? B200_OP_REDUCE_SUM
+                  : as_type_ptr<ngraph::opset1::ReduceMax>(n) ? B200_OP_REDUCE_MAX : -1;
+        if (rop >= 0) {
+            auto axes = ConstInts(n, 1, err);
+            if (!err.empty()) { d.reject = err; return d; }
+            bool keep = false;
+            if (auto r = std::dynamic_pointer_cast<ngraph::op::util::ArithmeticReductionKeepDims>(n)) keep = r->get_keep_dims();
+            d.op = rop; all_inputs(1);
+            d.i = {keep ? 1 : 0, static_cast<int32_t>(axes.size())};
+            for (auto a : axes) d.i.push_back(static_cast<int32_t>(a));
+            return d;
+        }
+    }
+    if (auto m = as_type_ptr<ngraph::opset1::MatMul>(n)) {
+        d.op = B200_OP_MATMUL; all_inputs(2); d.i = {m->get_transpose_a() ? 1 : 0, m->get_transpose_b() ? 1 : 0}; return d;
+    }
+    if (auto s = as_type_ptr<ngraph::opset1::Softmax>(n)) { d.op = B200_OP_SOFTMAX; all_inputs(1); d.i = {static_cast<int32_t>(s->get_axis())}; return d; }
+    if (auto m = as_type_ptr<ngraph::opset6::MVN>(n)) {
+        auto axes = ConstInts(n, 1, err);
+        if (!err.empty()) { d.reject = err; return d; }
+        d.op = B200_OP_MVN; all_inputs(1);
+        d.i = {m->get_normalize_variance() ? 1 : 0, m->get_eps_mode() == ngraph::op::MVNEpsMode::INSIDE_SQRT ? 0 : 1, static_cast<int32_t>(axes.size())};
+        for (auto a : axes) d.i.push_back(static_cast<int32_t>(a));
+        d.f = {m->get_eps()};
+        return d;
+    }
+    if (as_type_ptr<ngraph::opset1::Reshape>(n) || as_type_ptr<ngraph::opset1::Squeeze>(n) || as_type_ptr<ngraph::opset1::Unsqueeze>(n)) {
+        d.op = B200_OP_RESHAPE; all_inputs(1); d.shape_from_output = true; return d;
+    }
+    if (as_type_ptr<ngraph::opset1::Transpose>(n)) {
+        auto order = ConstInts(n, 1, err);
+        if (!err.empty()) { d.reject = err; return d; }
+        d.op = B200_OP_TRANSPOSE; all_inputs(1);
+        const size_t rank = n->get_input_shape(0).size();
+        if (order.empty()) for (size_t k = 0; k < rank; ++k) order.push_back(static_cast<int64_t>(rank - 1 - k));
+        for (auto a : order) d.i.push_back(static_cast<int32_t>(a));
+        return d;
+    }
+    if (auto c = as_type_ptr<ngraph::opset1::Concat>(n)) {
+        d.op = B200_OP_CONCAT; all_inputs(n->get_input_size()); d.i = {static_cast<int32_t>(c->get_axis())}; return d;
+    }
+    if (auto s = as_type_ptr<ngraph::opset1::Split>(n)) {
+        auto axis = ConstInts(n, 1, err);
+        if (!err.empty()) { d.reject = err; return d; }
+        d.op = B200_OP_SPLIT; all_inputs(1); d.i = {static_cast<int32_t>(axis[0]), static_cast<int32_t>(s->get_num_splits())}; return d;
+    }
+    if (as_type_ptr<ngraph::opset1::Gather>(n) || as_type_ptr<ngraph::opset7::Gather>(n)) {
+        auto axis = ConstInts(n, 2, err);
+        if (!err.empty()) { d.reject = err; return d; }
+        if (auto g7 = as_type_ptr<ngraph::opset7::Gather>(n))
+            if (g7->get_batch_dims() != 0) { d.reject = "Gather batch_dims != 0"; return d; }
+        d.op = B200_OP_GATHER; d.data_inputs = {0, 1}; d.i = {static_cast<int32_t>(axis[0])}; return d;
+    }
+    {
+        auto t1 = as_type_ptr<ngraph::opset1::TopK>(n);
+        auto t3 = as_type_ptr<ngraph::opset3::TopK>(n);
+        if (t1 || t3) {
+            auto k = ConstInts(n, 1, err);
+            if (!err.empty()) { d.reject = err; return d; }
+            const auto mode = t1 ? t1->get_mode() : t3->get_mode();
+            const auto sort = t1 ? t1->get_sort_type() : t3->get_sort_type();
+            const int64_t axis = static_cast<int64_t>(t1 ? t1->get_axis() : t3->get_axis());
+            d.op = B200_OP_TOPK; all_inputs(1);
+            d.i = {static_cast<int32_t>(k[0]), static_cast<int32_t>(axis), mode == ngraph::op::TopKMode::MAX ? 0 : 1,
+                   sort == ngraph::op::TopKSortType::NONE ? 0 : (sort == ngraph::op::TopKSortType::SORT_VALUES ? 1 : 2)};
+            return d;
+        }
+    }
+    if (auto nms = as_type_ptr<ngraph::opset5::NonMaxSuppression>(n)) {
+        for (size_t k = 2; k < n->get_input_size(); ++k)
+            if (!as_type_ptr<ngraph::opset1::Constant>(n->get_input_node_shared_ptr(k))) { d.reject = "NonMaxSuppression thresholds must be Constants"; return d; }
+        d.op = B200_OP_NMS; d.data_inputs = {0, 1};
+        d.i = {static_cast<int32_t>(std::min<int64_t>(nms->max_boxes_output_from_input(), INT32_MAX)),
+               nms->get_box_encoding() == ngraph::opset5::NonMaxSuppression::BoxEncodingType::CENTER ? 1 : 0, nms->get_sort_result_descending() ? 1 : 0};
+        d.f = {nms->iou_threshold_from_input(), nms->score_threshold_from_input(), nms->soft_nms_sigma_from_input()};
+        return d;
+    }
+    if (auto det = as_type_ptr<ngraph::opset1::DetectionOutput>(n)) {
+        if (n->get_input_size() != 3) { d.reject = "DetectionOutput with auxiliary inputs"; return d; }
+        const auto& a = det->get_attrs();
+        d.op = B200_OP_DETECTION_OUTPUT; all_inputs(3);
+        const bool center = a.code_type.size() >= 11 && a.code_type.compare(a.code_type.size() - 11, 11, "CENTER_SIZE") == 0;
+        d.i = {a.num_classes, a.background_label_id, a.top_k, a.keep_top_k.empty() ? -1 : a.keep_top_k[0], center ? 1 : 0, a.share_location ? 1 : 0,
+               a.variance_encoded_in_target ? 1 : 0, a.normalized ? 1 : 0, a.clip_before_nms ? 1 : 0, a.clip_after_nms ? 1 : 0,
+               static_cast<int32_t>(a.input_height), static_cast<int32_t>(a.input_width), a.decrease_label_id ? 1 : 0};
+        d.f = {a.nms_threshold, a.confidence_threshold};
+        return d;
+    }
+    if (auto c = as_type_ptr<ngraph::opset1::Convert>(n)) {
+        d.op = B200_OP_CONVERT; all_inputs(1); d.dtype = ToDtype(c->get_destination_type());
+        if (d.dtype < 0) d.reject = "Convert to " + c->get_destination_type().get_type_name();
+        return d;
+    }
+    d.reject = std::string("no B200 kernel for ") + ti.name + " (opset version " + std::to_string(ti.version) + ")";
+    return d;
+}
+
+}  // namespace
+
+bool IsNodeSupported(const NodePtr& node, std::string* why) {
+    OpDesc d = Describe(node);
+    bool ok = d.reject.empty() && d.op >= 0 && b200_op_supported(d.op) == 1;
+    for (size_t k = 0; ok && k < node->get_output_size(); ++k) {
+        if (node->get_output_partial_shape(k).is_dynamic()) { ok = false; d.reject = "dynamic shapes are not supported"; }
+        else if (ToDtype(node->get_output_element_type(k)) < 0) { ok = false; d.reject = "element type " + node->get_output_element_type(k).get_type_name(); }
+    }
+    if (!ok && why) *why = d.reject.empty() ? "unsupported operation" : d.reject;
+    return ok;
+}
+
+b200_graph* LowerFunction(const std::shared_ptr<ngraph::Function>& function) {
+    b200_graph* g = nullptr;
+    if (b200_graph_create(function->get_friendly_name().c_str(), &g) != B200_OK) IE_THROW() << "B200: " << b200_last_error();
+    std::map<std::pair<ngraph::Node*, size_t>, int32_t> value_of;
+    try {
+        for (const auto& node : function->get_ordered_ops()) {
+            std::string why;
+            if (!IsNodeSupported(node, &why))
+                IE_THROW(NotImplemented) << "B200 plugin: operation '" << node->get_friendly_name() << "' (" << node->get_type_name() << ") is not supported: " << why;
+            OpDesc d = Describe(node);
+            b200_node_desc nd;
+            std::memset(&nd, 0, sizeof(nd));
+            nd.op = d.op;
+            const std::string name = node->get_friendly_name();
+            nd.name = name.c_str();
+            if (d.data_inputs.size() > B200_MAX_INPUTS) IE_THROW(NotImplemented) << "B200 plugin: '" << name << "' has more than " << B200_MAX_INPUTS << " inputs";
+            nd.n_inputs = static_cast<int32_t>(d.data_inputs.size());
+            for (size_t k = 0; k < d.data_inputs.size(); ++k) {
+                auto src = node->input_value(d.data_inputs[k]);
+                auto it = value_of.find({src.get_node(), src.get_index()});
+                if (it == value_of.end()) IE_THROW() << "B200 plugin: input " << k << " of '" << name << "' was not lowered";
+                nd.inputs[k] = it->second;
+            }
+            if (d.i.size() > B200_MAX_IATTR || d.f.size() > B200_MAX_FATTR) IE_THROW(NotImplemented) << "B200 plugin: too many attributes on '" << name << "'";
+            for (size_t k = 0; k < d.i.size(); ++k) nd.i[k] = d.i[k];
+            for (size_t k = 0; k < d.f.size(); ++k) nd.f[k] = d.f[k];
+            nd.dtype = d.dtype;
+            if (d.op == B200_OP_PARAMETER || d.op == B200_OP_CONSTANT || d.shape_from_output) {
+                const auto& shape = node->get_output_shape(0);
+                if (shape.size() > B200_MAX_RANK) IE_THROW(NotImplemented) << "B200 plugin: rank > " << B200_MAX_RANK << " on '" << name << "'";
+                nd.rank = static_cast<int32_t>(shape.size());
+                for (size_t k = 0; k < shape.size(); ++k) nd.shape[k] = static_cast<int64_t>(shape[k]);
+            }
+            if (d.op == B200_OP_CONSTANT) {
+                auto c = as_type_ptr<ngraph::opset1::Constant>(node);
+                nd.data = c->get_data_ptr();
+                nd.data_bytes = ngraph::shape_size(c->get_shape()) * c->get_element_type().size();
+            }
+            int32_t outs[B200_MAX_INPUTS];
+            int32_t n_out = 0;
+            int rc = b200_graph_add(g, &nd, outs, &n_out);
+            if (rc == B200_ERR_UNSUPPORTED) IE_THROW(NotImplemented) << "B200 plugin: '" << name << "': " << b200_last_error();
+            if (rc != B200_OK) IE_THROW() << "B200 plugin: '" << name << "': " << b200_last_error();
+            for (int32_t k = 0; k < n_out && static_cast<size_t>(k) < node->get_output_size(); ++k) value_of[{node.get(), static_cast<size_t>(k)}] = outs[k];
+        }
+    } catch (...) {
+        b200_graph_destroy(g);
+        throw;
+    }
+    return g;
+}
+
+}  // namespace B200Plugin

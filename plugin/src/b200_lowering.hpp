@@ -1,0 +1,25 @@
+// ngraph::Function -> b200_graph (C ABI of libb200kernels.so): the plugin-side half of the graph compiler.
+// Plays the role of MKLDNNGraph::Replicate (inference-engine/src/mkldnn_plugin/mkldnn_graph.cpp:181-320): one
+// b200_graph_add call per ngraph::Node; fusion, layout selection and memory planning happen below the C ABI.
+#pragma once
+#include <memory>
+#include <string>
+
+#include <ngraph/function.hpp>
+
+#include "b200.h"
+
+namespace B200Plugin {
+
+// Runs the reused nGraph pipeline (CommonOptimizations with the decompositions of natively supported ops switched off,
+// the analogue of Transformation() in mkldnn_plugin.cpp:115-383) on a clone of `function`.
+std::shared_ptr<ngraph::Function> TransformNetwork(const std::shared_ptr<const ngraph::Function>& function);
+
+// true if `node` (after TransformNetwork) maps onto a b200_op; `why` receives the reason otherwise.
+bool IsNodeSupported(const std::shared_ptr<ngraph::Node>& node, std::string* why = nullptr);
+
+// Builds the b200_graph; throws InferenceEngine::NotImplemented / GeneralError with the library's message on failure.
+// The caller owns the returned graph (b200_graph_destroy).
+b200_graph* LowerFunction(const std::shared_ptr<ngraph::Function>& function);
+
+}  // namespace B200Plugin

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 # integer-valued inputs: exact in bf16/fp16 too, so the index outputs must still match
 LOWP_SKIP = {"nms_corner_sorted", "nms_center_unsorted", "nms_score_ties", "nms_keep_nothing", "detout_ssd_like", "detout_corner_clip",
              "detout_not_shared", "detout_var_in_target", "net_tiny_ssd", "topk_imagenet_top5"}
-LOWP_TOL = {"net_tiny_resnet": 3e-2, "net_tiny_mobilenet": 3e-2, "net_tiny_bert": 3e-2, "unary_activations": 2e-2, "binary_broadcast": 2e-2}
+LOWP_TOL = {"softmax_last": 3e-2, "softmax_mid": 3e-2, "softmax_ssd": 3e-2, "net_tiny_resnet": 3e-2, "net_tiny_mobilenet": 3e-2, "net_tiny_bert": 3e-2, "unary_activations": 2e-2, "binary_broadcast": 2e-2}
 
 
 @pytest.mark.parametrize("case", sorted(golden_cases.CASES))
