@@ -13,7 +13,10 @@
 #include <ngraph/opsets/opset7.hpp>
 #include <ngraph/pass/constant_folding.hpp>
 #include <ngraph/pass/manager.hpp>
+#include <ngraph_ops/nms_ie_internal.hpp>
 #include <transformations/common_optimizations/common_optimizations.hpp>
+#include <transformations/op_conversions/convert_nms_to_nms_ie_internal.hpp>
+#include <transformations/op_conversions/convert_previous_nms_to_nms_5.hpp>
 #include <transformations/op_conversions/convert_divide.hpp>
 #include <transformations/op_conversions/convert_gelu.hpp>
 #include <transformations/op_conversions/convert_minimum_to_power_and_max.hpp>
@@ -36,6 +39,11 @@ std::shared_ptr<ngraph::Function> TransformNetwork(const std::shared_ptr<const n
     auto f = ngraph::clone_function(*function);
     ngraph::pass::Manager manager;
     manager.register_pass<ngraph::pass::CommonOptimizations>();
+    // NMS-1/3/4 -> NMS-5 -> NonMaxSuppressionIEInternal (static, padded output shapes), as mkldnn_plugin.cpp:150-156 does
+    manager.register_pass<ngraph::pass::ConvertNMS1ToNMS5>();
+    manager.register_pass<ngraph::pass::ConvertNMS3ToNMS5>();
+    manager.register_pass<ngraph::pass::ConvertNMS4ToNMS5>();
+    manager.register_pass<ngraph::pass::ConvertNMSToNMSIEInternal>();
     manager.register_pass<ngraph::pass::ConstantFolding>();
     // ops the kernel library executes natively must not be decomposed (same stance as mkldnn_plugin.cpp:281-300)
     auto cfg = manager.get_pass_config();
@@ -164,7 +172,7 @@ OpDesc Describe(const NodePtr& n) {
     if (auto g = as_type_ptr<ngraph::opset7::Gelu>(n)) {
         d.op = B200_OP_GELU; all_inputs(1); d.i = {g->get_approximation_mode() == ngraph::op::GeluApproximationMode::TANH ? 1 : 0}; return d;
     }
-    if (as_type_ptr<ngraph::opset1::Gelu>(n)) { d.op = B200_OP_GELU; all_inputs(1); d.i = {0}; return d; }   // v0/v2: erf form
+    if (as_type_ptr<ngraph::op::v0::Gelu>(n)) { d.op = B200_OP_GELU; all_inputs(1); d.i = {0}; return d; }   // v0/v2: erf form
     if (auto p = as_type_ptr<ngraph::opset1::MaxPool>(n)) {
         if (p->get_input_shape(0).size() != 4) { d.reject = "only 2D pooling"; return d; }
         d.op = B200_OP_MAX_POOL; all_inputs(1);
@@ -257,6 +265,19 @@ OpDesc Describe(const NodePtr& n) {
         d.i = {static_cast<int32_t>(std::min<int64_t>(nms->max_boxes_output_from_input(), INT32_MAX)),
                nms->get_box_encoding() == ngraph::opset5::NonMaxSuppression::BoxEncodingType::CENTER ? 1 : 0, nms->get_sort_result_descending() ? 1 : 0};
         d.f = {nms->iou_threshold_from_input(), nms->score_threshold_from_input(), nms->soft_nms_sigma_from_input()};
+        return d;
+    }
+    if (auto nms = as_type_ptr<ngraph::op::internal::NonMaxSuppressionIEInternal>(n)) {
+        std::vector<float> thr;
+        for (size_t k = 2; k < n->get_input_size(); ++k) {
+            auto c = as_type_ptr<ngraph::opset1::Constant>(n->get_input_node_shared_ptr(k));
+            if (!c) { d.reject = "NonMaxSuppression thresholds must be Constants"; return d; }
+            thr.push_back(c->cast_vector<float>()[0]);
+        }
+        while (thr.size() < 4) thr.push_back(0.f);
+        d.op = B200_OP_NMS; d.data_inputs = {0, 1};
+        d.i = {static_cast<int32_t>(std::min<float>(thr[0], 2147483520.f)), nms->m_center_point_box ? 1 : 0, nms->m_sort_result_descending ? 1 : 0};
+        d.f = {thr[1], thr[2], thr[3]};
         return d;
     }
     if (auto det = as_type_ptr<ngraph::opset1::DetectionOutput>(n)) {

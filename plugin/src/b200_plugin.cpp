@@ -68,6 +68,10 @@ Configuration::Configuration(const std::map<std::string, std::string>& config, c
                 streams = 0;
             }
             if (streams < 1 || streams > 64) IE_THROW(ParameterMismatch) << "B200 plugin: B200_THROUGHPUT_STREAMS must be in [1, 64], got '" << value << "'";
+        } else if (key == "B200_DRY_COMPILE") {
+            // test hook (not advertised in SUPPORTED_CONFIG_KEYS): lower + plan without touching a device, so that the host side
+            // of LoadNetwork / metrics / exec-graph can be exercised on a machine without a GPU; requests cannot be created
+            dryCompile = value == CONFIG_VALUE(YES);
         } else if (throwOnUnsupported) {
             IE_THROW(NotFound) << "Unsupported property " << key << " by B200 plugin";   // config.cpp:112-114 of the CPU plugin
         }
@@ -200,7 +204,7 @@ ExecutableNetwork::ExecutableNetwork(const std::shared_ptr<const ngraph::Functio
     b200_compile_options opts;
     std::memset(&opts, 0, sizeof(opts));
     opts.abi_version = B200_ABI_VERSION;
-    opts.device = cfg.deviceId;
+    opts.device = cfg.dryCompile ? -1 : cfg.deviceId;
     opts.precision = cfg.precision;
     int rc = b200_compile(graph, &opts, &_net);
     b200_graph_destroy(graph);

@@ -24,6 +24,7 @@ struct Configuration {
     bool perfCount = false;
     int precision = B200_PREC_BF16;
     int streams = 1;
+    bool dryCompile = false;
 
     Configuration() = default;
     // merges `config` over `defaults`; unknown keys throw NotFound (behaviour tests: behavior/config.hpp)
@@ -38,7 +39,7 @@ struct Configuration {
 class Plugin : public InferenceEngine::IInferencePlugin {
 public:
     Plugin();
-    ~Plugin() override;
+    ~Plugin();
     void SetConfig(const std::map<std::string, std::string>& config) override;
     InferenceEngine::Parameter GetConfig(const std::string& name, const std::map<std::string, InferenceEngine::Parameter>& options) const override;
     InferenceEngine::Parameter GetMetric(const std::string& name, const std::map<std::string, InferenceEngine::Parameter>& options) const override;
@@ -58,7 +59,7 @@ private:
 class ExecutableNetwork : public InferenceEngine::ExecutableNetworkThreadSafeDefault {
 public:
     ExecutableNetwork(const std::shared_ptr<const ngraph::Function>& function, const Configuration& cfg, const std::shared_ptr<Plugin>& plugin);
-    ~ExecutableNetwork() override;
+    ~ExecutableNetwork();
 
     InferenceEngine::IInferRequestInternal::Ptr CreateInferRequestImpl(InferenceEngine::InputsDataMap networkInputs,
                                                                        InferenceEngine::OutputsDataMap networkOutputs) override;
@@ -85,7 +86,7 @@ class InferRequest : public InferenceEngine::IInferRequestInternal {
 public:
     InferRequest(const InferenceEngine::InputsDataMap& networkInputs, const InferenceEngine::OutputsDataMap& networkOutputs,
                  const std::shared_ptr<ExecutableNetwork>& network);
-    ~InferRequest() override;
+    ~InferRequest();
 
     void InferImpl() override;
     std::map<std::string, InferenceEngine::InferenceEngineProfileInfo> GetPerformanceCounts() const override;
@@ -107,7 +108,7 @@ class AsyncInferRequest : public InferenceEngine::AsyncInferRequestThreadSafeDef
 public:
     AsyncInferRequest(const std::shared_ptr<InferRequest>& request, const InferenceEngine::ITaskExecutor::Ptr& taskExecutor,
                       const InferenceEngine::ITaskExecutor::Ptr& waitExecutor, const InferenceEngine::ITaskExecutor::Ptr& callbackExecutor);
-    ~AsyncInferRequest() override;
+    ~AsyncInferRequest();
 
 private:
     std::shared_ptr<InferRequest> _request;

@@ -1,0 +1,72 @@
+"""Drop-in check on a real B200: the UNMODIFIED reference Inference Engine (oracle/_ref) loads plugin/lib/libb200Plugin.so as
+device "B200" and runs the golden cases through Core::ReadNetwork / LoadNetwork / CreateInferRequest / StartAsync / Wait
+(tools/ie_run.cpp); also MULTI:B200.0 and the reference's own benchmark_app with -d B200."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from dldt_b200 import ir, zoo
+from tests import golden_cases
+from tests.test_oracle_golden import compare, compare_detections, golden_outputs
+from tools import refrun
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref")
+PLUGIN = os.path.join(ROOT, "plugin", "lib", "libb200Plugin.so")
+needs_ref = pytest.mark.skipif(not (refrun.available() and os.path.exists(PLUGIN)), reason="oracle/_ref or plugin/lib did not travel")
+
+CASES = ["conv_3x3", "conv_7x7_s2_c3", "conv_bn_residual", "depthwise_s2_clamp_pools", "fc_bias_gelu", "matmul_batched_activations", "softmax_ssd",
+         "mvn_layernorm", "unary_activations", "binary_broadcast", "concat_split_transpose", "gather_embedding", "topk_ties_max_value",
+         "nms_corner_sorted", "nms_score_ties", "detout_ssd_like", "net_tiny_resnet", "net_tiny_mobilenet", "net_tiny_bert", "net_tiny_ssd"]
+
+
+@needs_ref
+@pytest.mark.parametrize("case", CASES)
+def test_plugin_fp32_matches_reference_cpu_plugin(case):
+    f, inputs = golden_cases.CASES[case]()
+    ref = golden_outputs("cpu", case)
+    got, _ = refrun.run(f, inputs, device="B200", config={"B200_INFERENCE_PRECISION": "FP32"})
+    assert set(got) == set(ref)
+    for k in ref:
+        if "det" in k and ref[k].shape[-1] == 7:
+            compare_detections(got[k], ref[k], "%s/%s" % (case, k), tol=1e-4)
+        else:
+            compare(got[k], ref[k], "%s/%s" % (case, k), tol=1e-4)
+
+
+@needs_ref
+def test_plugin_bf16_u8_input_and_perf_counters():
+    f = zoo.resnet50(batch=4, image=64, width=16, blocks=(1, 1, 1, 1), num_classes=24)
+    x = np.random.default_rng(3).integers(0, 256, (4, 3, 64, 64), dtype=np.uint8)
+    ref, _ = refrun.run(f, {"data": x}, device="CPU", input_precisions={"data": "U8"})
+    got, _ = refrun.run(f, {"data": x}, device="B200", config={"B200_INFERENCE_PRECISION": "BF16", "PERF_COUNT": "YES"}, input_precisions={"data": "U8"})
+    a, b = got["fc_bias"], ref["fc_bias"]
+    assert np.linalg.norm(a - b) / np.linalg.norm(b) < 3e-2
+    assert (a.argmax(1) == b.argmax(1)).mean() >= 0.75
+
+
+@needs_ref
+def test_multi_device_plugin_schedules_onto_b200():
+    # the reference MULTI plugin re-enters Core::LoadNetwork("B200.0") and needs OPTIMAL_NUMBER_OF_INFER_REQUESTS + PERF_COUNT read-back
+    f, inputs = golden_cases.CASES["net_tiny_resnet"]()
+    ref = golden_outputs("cpu", "net_tiny_resnet")
+    got, _ = refrun.run(f, inputs, device="MULTI:B200.0", config={}, niter=3)
+    for k in ref:
+        compare(got[k], ref[k], k, tol=3e-2)     # default precision of the plugin is BF16
+
+
+@needs_ref
+def test_reference_benchmark_app_runs_on_b200(tmp_path):
+    f = zoo.resnet50(batch=8, image=64, width=16, blocks=(1, 1, 1, 1), num_classes=24)
+    xml = str(tmp_path / "m.xml")
+    ir.serialize(f, xml)
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(REF, "lib") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    p = subprocess.run([os.path.join(REF, "bin", "benchmark_app"), "-m", xml, "-d", "B200", "-niter", "64", "-api", "async"],
+                       env=env, capture_output=True, text=True, cwd=os.path.join(REF, "lib"), timeout=300)
+    assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-1500:]
+    m = re.search(r"Throughput:\s+([0-9.]+)\s+FPS", p.stdout)
+    assert m and float(m.group(1)) > 100, p.stdout[-800:]

@@ -1,0 +1,92 @@
+"""The C++ device plugin (plugin/lib/libb200Plugin.so) loaded by the UNMODIFIED reference Inference Engine
+(oracle/_ref/lib/libinference_engine.so) through plugins.xml - host-side behaviour that needs no GPU:
+registration under the device name "B200", QueryNetwork coverage, metrics, config-key errors, the lowering of an
+ngraph::Function through the C ABI (dry compile) and the loud failure when no device exists."""
+import json
+import os
+import subprocess
+
+import pytest
+
+from dldt_b200 import ir, zoo
+from tests import golden_cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref")
+IE_RUN = os.path.join(REF, "bin", "ie_run")
+PLUGIN = os.path.join(ROOT, "plugin", "lib", "libb200Plugin.so")
+
+pytestmark = pytest.mark.skipif(not (os.path.exists(IE_RUN) and os.path.exists(PLUGIN)),
+                                reason="needs oracle/_ref (oracle/build_ref.sh) and plugin/lib (make -C plugin), both built by __graft_entry__.build()")
+
+
+def ie_run(xml, *args):
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(REF, "lib") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    cmd = [IE_RUN, "--model", xml, "--device", "B200", "--plugins", os.path.join(REF, "lib", "plugins.xml")] + list(args)
+    return subprocess.run(cmd, env=env, capture_output=True, text=True)
+
+
+@pytest.fixture(scope="module")
+def tiny_resnet_xml(tmp_path_factory):
+    d = tmp_path_factory.mktemp("ir")
+    f = zoo.resnet50(batch=2, image=64, width=16, blocks=(1, 1, 1, 1), num_classes=24)
+    xml = str(d / "tiny_resnet.xml")
+    ir.serialize(f, xml)
+    return xml
+
+
+def test_plugin_exports_only_the_factory_symbol():
+    out = subprocess.run(["nm", "-D", "--defined-only", PLUGIN], capture_output=True, text=True).stdout
+    names = [ln.split()[-1] for ln in out.splitlines() if " T " in ln]
+    assert names == ["CreatePluginEngine"]        # ie_iplugin_internal.hpp:319-331
+
+
+def test_query_network_and_metrics(tiny_resnet_xml):
+    p = ie_run(tiny_resnet_xml, "--query")
+    assert p.returncode == 0, p.stderr
+    q = json.loads(p.stdout)
+    assert q["supported_layers"] == q["total_layers"] > 100
+    assert q["capabilities"] == ["FP32", "BF16", "FP16"]
+    assert {"DEVICE_ID", "PERF_COUNT", "B200_INFERENCE_PRECISION", "B200_THROUGHPUT_STREAMS"} <= set(q["config_keys"])
+    assert q["architecture"] == "sm_100a"
+
+
+def test_load_network_lowers_and_fuses(tiny_resnet_xml):
+    p = ie_run(tiny_resnet_xml, "--dry", "--config", "B200_DRY_COMPILE=YES,B200_THROUGHPUT_STREAMS=3")
+    assert p.returncode == 0, p.stderr
+    d = json.loads(p.stdout)
+    assert d["network_name"] == "resnet50_v1.5"
+    assert d["optimal_requests"] == 6                        # 2 per stream
+    assert d["exec_convolutions"] == 17 and d["exec_nodes"] <= 24   # 17 convs with BN/ReLU/residual folded, pools, FC, input/output
+
+
+def test_unknown_config_key_is_not_found(tiny_resnet_xml):
+    p = ie_run(tiny_resnet_xml, "--dry", "--config", "B200_DRY_COMPILE=YES,CPU_THREADS_NUM=4")
+    assert p.returncode != 0 and "NOT_FOUND" in p.stderr and "CPU_THREADS_NUM" in p.stderr
+
+
+def test_bad_precision_value_is_rejected(tiny_resnet_xml):
+    p = ie_run(tiny_resnet_xml, "--dry", "--config", "B200_DRY_COMPILE=YES,B200_INFERENCE_PRECISION=INT4")
+    assert p.returncode != 0 and "B200_INFERENCE_PRECISION" in p.stderr
+
+
+def test_no_device_fails_loudly(tiny_resnet_xml):
+    from dldt_b200 import _capi
+    if _capi.device_count() > 0:
+        pytest.skip("GPU present")
+    p = ie_run(tiny_resnet_xml, "--niter", "1")
+    assert p.returncode != 0 and "no CUDA device" in p.stderr and "no CPU fallback" in p.stderr
+
+
+@pytest.mark.parametrize("case", ["net_tiny_mobilenet", "net_tiny_bert", "net_tiny_ssd", "unary_activations", "topk_ties_min_index", "nms_corner_sorted",
+                                  "concat_split_transpose", "mvn_layernorm", "matmul_batched_activations"])
+def test_every_model_family_lowers_through_the_plugin(case, tmp_path):
+    f, _ = golden_cases.CASES[case]()
+    xml = str(tmp_path / "m.xml")
+    ir.serialize(f, xml)
+    q = ie_run(xml, "--query")
+    assert q.returncode == 0, q.stderr
+    qq = json.loads(q.stdout)
+    assert qq["supported_layers"] == qq["total_layers"], qq
+    p = ie_run(xml, "--dry", "--config", "B200_DRY_COMPILE=YES,B200_INFERENCE_PRECISION=FP32")
+    assert p.returncode == 0, p.stderr

@@ -4,6 +4,8 @@
 // and by the GPU parity tests that drive the B200 plugin through the unmodified Core API
 // (Core::ReadNetwork / LoadNetwork / CreateInferRequest / StartAsync / Wait).
 #include <inference_engine.hpp>
+#include <ngraph/function.hpp>
+#include <ngraph/variant.hpp>
 
 #include <chrono>
 #include <fstream>
@@ -27,6 +29,7 @@ int main(int argc, char** argv) {
   std::string model, device = "CPU", outdir = ".", plugins_xml;
   std::map<std::string, std::string> config, inputs, in_prec;
   int niter = 1;
+  bool query = false, dry = false;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
     auto next = [&]() { return std::string(i + 1 < argc ? argv[++i] : ""); };
@@ -35,6 +38,8 @@ int main(int argc, char** argv) {
     else if (a == "--output-dir") outdir = next();
     else if (a == "--plugins") plugins_xml = next();
     else if (a == "--niter") niter = std::stoi(next());
+    else if (a == "--query") query = true;     // print QueryNetwork coverage + plugin metrics as JSON, no inference
+    else if (a == "--dry") dry = true;         // LoadNetwork + executable-network metrics + exec graph, no inference
     else if (a == "--config") { for (auto& kv : split(next(), ',')) { auto p = kv.find('='); if (p != std::string::npos) config[kv.substr(0, p)] = kv.substr(p + 1); } }
     else if (a == "--input") { auto kv = next(); auto p = kv.find('='); inputs[kv.substr(0, p)] = kv.substr(p + 1); }
     else if (a == "--input-precision") { auto kv = next(); auto p = kv.find('='); in_prec[kv.substr(0, p)] = kv.substr(p + 1); }
@@ -47,8 +52,38 @@ int main(int argc, char** argv) {
       auto it = in_prec.find(in.first);
       if (it != in_prec.end()) in.second->setPrecision(Precision::FromStr(it->second));
     }
+    if (query) {
+      QueryNetworkResult q = core.QueryNetwork(net, device, config);
+      size_t total = net.getFunction()->get_ops().size();
+      std::cout << "{\"supported_layers\": " << q.supportedLayersMap.size() << ", \"total_layers\": " << total;
+      std::string base = device.substr(0, device.find('.'));
+      auto caps = core.GetMetric(base, METRIC_KEY(OPTIMIZATION_CAPABILITIES)).as<std::vector<std::string>>();
+      std::cout << ", \"capabilities\": [";
+      for (size_t k = 0; k < caps.size(); ++k) std::cout << (k ? ", " : "") << "\"" << caps[k] << "\"";
+      auto keys = core.GetMetric(base, METRIC_KEY(SUPPORTED_CONFIG_KEYS)).as<std::vector<std::string>>();
+      std::cout << "], \"config_keys\": [";
+      for (size_t k = 0; k < keys.size(); ++k) std::cout << (k ? ", " : "") << "\"" << keys[k] << "\"";
+      std::cout << "], \"architecture\": \"" << core.GetMetric(base, METRIC_KEY(DEVICE_ARCHITECTURE)).as<std::string>() << "\"}" << std::endl;
+      return 0;
+    }
     auto t0 = std::chrono::steady_clock::now();
     ExecutableNetwork exe = core.LoadNetwork(net, device, config);
+    if (dry) {
+      unsigned nireq = exe.GetMetric(EXEC_NETWORK_METRIC_KEY(OPTIMAL_NUMBER_OF_INFER_REQUESTS)).as<unsigned>();
+      std::string name = exe.GetMetric(EXEC_NETWORK_METRIC_KEY(NETWORK_NAME)).as<std::string>();
+      CNNNetwork eg = exe.GetExecGraphInfo();
+      size_t exec_nodes = 0, convs = 0;
+      for (auto& n : eg.getFunction()->get_ops()) {
+        auto it = n->get_rt_info().find("layerType");
+        if (it == n->get_rt_info().end()) continue;
+        ++exec_nodes;
+        auto v = std::dynamic_pointer_cast<ngraph::VariantImpl<std::string>>(it->second);
+        if (v && v->get() == "Convolution") ++convs;
+      }
+      std::cout << "{\"network_name\": \"" << name << "\", \"optimal_requests\": " << nireq << ", \"exec_nodes\": " << exec_nodes
+                << ", \"exec_convolutions\": " << convs << "}" << std::endl;
+      return 0;
+    }
     auto t1 = std::chrono::steady_clock::now();
     InferRequest req = exe.CreateInferRequest();
     for (auto& in : net.getInputsInfo()) {
