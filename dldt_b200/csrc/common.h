@@ -109,7 +109,9 @@ bool is_binary_eltwise(int op);
 void infer_node(const b200_graph& g, const Node& n, std::vector<Shape>& out_shapes, std::vector<int>& out_dtypes);
 
 // ---- lowered program ------------------------------------------------------------------------
-enum Layout : int { L_ROWMAJOR = 0, L_NHWC8 = 1 };
+// L_S2D16: the network input of a stride-2 stem convolution, stored space-to-depth: padded pixel (hp, wp) = (h + pt, w + pl) lives in
+// block (hp / 2, wp / 2), channel ((hp % 2) * 2 + wp % 2) * C + c of a [N, Hb, Wb, 16] tensor (C <= 4; unused channels are zero)
+enum Layout : int { L_ROWMAJOR = 0, L_NHWC8 = 1, L_S2D16 = 2 };
 
 enum Space : int { SP_NONE = 0, SP_ARENA = 1, SP_WEIGHTS = 2, SP_IO_IN = 3, SP_IO_OUT = 4 };
 struct BufRef {
@@ -123,6 +125,7 @@ struct LTensor {
   Shape shape;          // logical (nGraph) shape
   int dtype = B200_F32; // storage dtype
   int layout = L_ROWMAJOR;
+  int s2d_pt = 0, s2d_pl = 0, s2d_hb = 0, s2d_wb = 0;   // L_S2D16 geometry
   BufRef buf;
   int64_t bytes() const;
   int64_t phys_elems() const;

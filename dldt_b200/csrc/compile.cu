@@ -21,6 +21,7 @@
 namespace b200 {
 
 int64_t LTensor::phys_elems() const {
+  if (layout == L_S2D16) return shape[0] * (int64_t)s2d_hb * s2d_wb * 16;
   if (layout == L_NHWC8 && shape.size() == 4) return shape[0] * shape[2] * shape[3] * round_up(shape[1], 8);
   return numel(shape);
 }
@@ -170,6 +171,8 @@ class Lowerer {
   LTensor to_dtype(const LTensor& t, int dtype, const std::string& why);
   void set(int value, const LTensor& t) { vt_[value] = t; }
   bool prefers_nhwc8(int value) const;
+  bool stem_s2d_applies(int value) const;
+  void lower_stem_s2d(const FusedConv& f, const LTensor& x);
 
   // ---- passes ----
   void fuse();
@@ -201,6 +204,68 @@ bool Lowerer::prefers_nhwc8(int value) const {
       return true;
   }
   return false;
+}
+
+// A network input whose single consumer is a dense 7x7 (or 8x8) stride-2 convolution over <= 4 channels (the ResNet / SSD stem)
+// is ingested space-to-depth so that the stem becomes a 4x4 stride-1 convolution over 16 channels: one filter row = 4 taps x 16
+// channels = 64 contiguous elements per output pixel = exactly one K block, fetched by one im2col-mode TMA box (conv_tc2.cu).
+bool Lowerer::stem_s2d_applies(int value) const {
+  if (!use_tc_ || !conv_tc2_im2col_enabled()) return false;
+  if (opts_.device >= 0 && !conv_tc2_s2d_encode_ok()) return false;
+  const char* off = getenv("B200_STEM_S2D");
+  if (off && off[0] == '0') return false;
+  const Value& v = val(value);
+  if (v.shape.size() != 4 || !dtype_is_float(v.dtype) || v.shape[1] > 4 || v.consumers.size() != 1) return false;
+  const Node& c = node(v.consumers[0]);
+  if (c.op != B200_OP_CONVOLUTION || c.inputs[0] != value || !const_node(c.inputs[1])) return false;
+  const Shape& w = val(c.inputs[1]).shape;
+  const Shape& o = val(c.outputs[0]).shape;
+  const bool k_ok = (w[2] == 7 || w[2] == 8) && (w[3] == 7 || w[3] == 8);
+  // every tap row/column must stay inside the Hb x Wb block grid: padded extent <= 2 * (Ho + 3)
+  const bool fits = v.shape[2] + c.i[4] <= 2 * (o[2] + 3) && v.shape[3] + c.i[5] <= 2 * (o[3] + 3);
+  return k_ok && c.i[0] == 2 && c.i[1] == 2 && c.i[2] == 1 && c.i[3] == 1 && c.i[4] <= 8 && c.i[5] <= 8 && fits && o[2] >= 1 && o[3] >= 1;
+}
+
+void Lowerer::lower_stem_s2d(const FusedConv& f, const LTensor& x) {
+  const Node& n = node(f.root);
+  std::string fused = n.name;
+  for (int a : f.absorbed) fused += "," + node(a).name;
+  const Shape& ws = val(n.inputs[1]).shape;
+  const Shape os = val(n.outputs[0]).shape;
+  const int64_t Cin = x.shape[1], Cout = os[1], kh = ws[2], kw = ws[3], Cout_p = round_up(Cout, 8);
+  const int bn = conv_tc_pick_bn((int)Cout_p);
+  const int64_t Cout_alloc = round_up(Cout_p, bn), Ktot = 256;
+  std::vector<float> wsrc = const_floats(n.inputs[1]);
+  std::vector<uint8_t> wp((size_t)(Cout_alloc * Ktot) * dtype_size(cd_), 0);
+  // K index = block row br (4) x block column bs (4) x channel ((dr * 2 + ds) * Cin + c); taps beyond the 7x7 window stay zero
+  for (int64_t o = 0; o < Cout; ++o)
+    for (int64_t c = 0; c < Cin; ++c)
+      for (int64_t r = 0; r < kh; ++r)
+        for (int64_t s2 = 0; s2 < kw; ++s2) {
+          const int64_t br = r / 2, dr = r % 2, bs = s2 / 2, ds = s2 % 2;
+          store_float(wp.data(), o * Ktot + br * 64 + bs * 16 + (dr * 2 + ds) * Cin + c, wsrc[((o * Cin + c) * kh + r) * kw + s2] * f.scale[o], cd_);
+        }
+  std::vector<float> bias(Cout_alloc, 0.f);
+  for (int64_t o = 0; o < Cout; ++o) bias[o] = f.shift[o];
+  BufRef wref = weights_ref(add_weights(wp.data(), (int64_t)wp.size()));
+  BufRef bref = add_f32_vector(bias);
+  LTensor out = alloc(val(f.out_value).shape, cd_, L_NHWC8);
+  LTensor res;
+  BufRef rref;
+  if (f.res_value >= 0) { res = get(f.res_value, L_NHWC8); rref = res.buf; }
+  ConvParams p;
+  p.N = (int)x.shape[0]; p.H = x.s2d_hb; p.W = (int)os[3]; p.Cin_p = 64; p.Ho = (int)os[2]; p.Wo = (int)os[3]; p.Cout_p = (int)Cout_p;
+  p.kh = 4; p.kw = 1; p.sh = p.sw = p.dh = p.dw = 1; p.pt = p.pl = 0;
+  p.x_sw = 16; p.x_sh = (int64_t)x.s2d_wb * 16; p.x_sn = (int64_t)x.s2d_hb * x.s2d_wb * 16;
+  p.M = (int)(os[0] * os[2] * os[3]); p.Ktot = (int)Ktot; p.Cout_alloc = (int)Cout_alloc; p.ldy = (int)Cout_p;
+  p.w_ld = (int)Ktot; p.w_rows = (int)Cout_alloc; p.w_k = (int)Ktot;
+  p.act1 = f.act1.kind; p.a1 = f.act1.a; p.b1 = f.act1.b; p.act2 = f.act2.kind; p.a2 = f.act2.a; p.b2 = f.act2.b;
+  const double flops = 2.0 * p.M * Cout * Cin * kh * kw;
+  const double bytes = (double)x.bytes() + (double)out.bytes() + (double)Cout * Cin * kh * kw * dtype_size(cd_) + (f.res_value >= 0 ? (double)out.bytes() : 0);
+  conv_launch_step(val(f.out_value).name, "Convolution", fused, p, x.buf, wref, bref, rref, out.buf, &x, f.res_value >= 0 ? &res : nullptr, &out, flops,
+                   bytes, true);
+  net_.steps.back().impl += "_s2d_stem";
+  set(f.out_value, out);
 }
 
 LTensor Lowerer::materialize_const(int value, int layout) {
@@ -448,7 +513,7 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
     const char* force_v1 = getenv("B200_CONV_TC_V1");
     v2 = conv_tc2_supported(p) && !(force_v1 && force_v1[0] == '1');
     s.impl = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_128x" + std::to_string(bn) + "x64" +
-             (v2 ? (conv_tc2_a_is_matrix(p) ? "_persistent_tma" : "_persistent_gather") : "");
+             (v2 ? (conv_tc2_a_is_matrix(p) ? "_persistent_tma" : (conv_tc2_a_is_im2col(p) ? "_persistent_im2col" : "_persistent_gather")) : "");
   } else {
     s.impl = "simt_fp32_128x64x16";
   }
@@ -530,6 +595,10 @@ void Lowerer::lower_conv(const FusedConv& f) {
   }
 
   // ---- Convolution / GroupConvolution ----
+  {
+    auto xi = vt_.find(n.inputs[0]);
+    if (xi != vt_.end() && xi->second.layout == L_S2D16) { lower_stem_s2d(f, xi->second); return; }
+  }
   LTensor x = get(n.inputs[0], L_NHWC8);
   const Shape& xs = x.shape;
   const Shape& ws = val(n.inputs[1]).shape;
@@ -1132,7 +1201,18 @@ void Lowerer::lower_node(const Node& n) {
   switch (n.op) {
     case B200_OP_PARAMETER: {
       const Value& v = val(n.outputs[0]);
-      LTensor t = alloc(v.shape, storage_dtype(v.dtype), prefers_nhwc8(v.id) ? L_NHWC8 : L_ROWMAJOR, /*pinned=*/true);
+      LTensor t;
+      if (stem_s2d_applies(v.id)) {
+        // the only consumer is a 7x7/8x8 stride-2 convolution over <= 4 channels: ingest straight into the space-to-depth layout
+        const Node& cv = node(v.consumers[0]);
+        const Shape os = val(cv.outputs[0]).shape;
+        t.shape = v.shape; t.dtype = cd_; t.layout = L_S2D16;
+        t.s2d_pt = cv.i[4]; t.s2d_pl = cv.i[5]; t.s2d_hb = (int)os[2] + 3; t.s2d_wb = (int)os[3] + 3;
+        t.buf.space = SP_ARENA;
+        t.buf.box = new_box(t.bytes(), /*pinned=*/true);
+      } else {
+        t = alloc(v.shape, storage_dtype(v.dtype), prefers_nhwc8(v.id) ? L_NHWC8 : L_ROWMAJOR, /*pinned=*/true);
+      }
       set(v.id, t);
       IOBinding b;
       b.name = n.name; b.shape = v.shape; b.graph_dtype = v.dtype; b.value_id = v.id;

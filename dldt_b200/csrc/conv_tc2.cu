@@ -42,48 +42,104 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * 128;        // 128 rows x 64 elements x 2 B
 constexpr int SLAB_BYTES = BM * 128;     // one 64-channel slab of the output / residual tile
-constexpr int NUM_A_PRODUCERS = 128;
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_A_PRODUCERS = 128;     // warps 0-3
+constexpr int NUM_EPI_WARPS = 8;         // warps 4-11: TMEM lane quarter = warp % 4, column half = (warp - 4) / 4
+constexpr int MMA_WARP = 12, TMA_WARP = 13;
+constexpr int NUM_THREADS = 448;
 constexpr int LAG = 2;                   // cp.async groups in flight before the oldest is published
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_LIMIT = 232448;       // 227 KB opt-in maximum per CTA on sm_100
 
-template <int BN> struct Cfg2;
-template <> struct Cfg2<64>  { static constexpr int STAGES = 6; };
-template <> struct Cfg2<128> { static constexpr int STAGES = 4; };
-
+// Shared-memory plan (all offsets multiples of 1024 from the aligned base):
+//   [stages x (A tile 16 KB + B tile BN*128 B)] [output staging x2] [residual staging x2, only when a residual is fused] [barriers]
+// The stage count takes whatever is left: 5 (BN=128) / 8 (BN=64) without a residual, 3 / 6 with one.
+struct SmemPlan { int stages; uint32_t out_off, res_off, bar_off, total; };
 template <int BN>
-constexpr int tc2_smem_bytes() {
-  return Cfg2<BN>::STAGES * (A_BYTES + BN * 128) + (BN / 64) * SLAB_BYTES /*out*/ + 2 * (BN / 64) * SLAB_BYTES /*residual x2*/ +
-         1024 /*align slack*/ + 256 /*barriers*/;
+__host__ __device__ inline SmemPlan smem_plan(bool has_res) {
+  const int stage_bytes = A_BYTES + BN * 128, tile_bytes = (BN / 64) * SLAB_BYTES;
+  const int fixed = 2 * tile_bytes + (has_res ? 2 * tile_bytes : 0) + 1024 /*align slack*/ + 1024 /*barriers*/;
+  int stages = (SMEM_LIMIT - fixed) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  SmemPlan pl;
+  pl.stages = stages;
+  pl.out_off = (uint32_t)(stages * stage_bytes);
+  pl.res_off = pl.out_off + 2u * tile_bytes;
+  pl.bar_off = pl.res_off + (has_res ? 2u * tile_bytes : 0u);
+  pl.total = pl.bar_off + 1024u + 1024u;
+  return pl;
 }
 
 struct Tc2Args {
-  CUtensorMap tm_a;   // activations as [M][Cin_p]   (TMA-A mode only)
+  CUtensorMap tm_a;   // activations: [M][Cin_p] matrix (a_tma 1) or {C, W, H, N} im2col tensor (a_tma 2)
   CUtensorMap tm_w;   // packed weights [Cout_alloc][Ktot]
   CUtensorMap tm_y;   // output [M][Cout_p], row pitch ldy
   CUtensorMap tm_r;   // residual, same geometry as the output
   ConvParams p;
   EpiAct e1, e2;      // activation after bias / after the residual sum
-  int a_tma;
+  int a_tma;          // 0: cp.async gather, 1: 2-D TMA (A is a matrix), 2: im2col-mode TMA
   int num_tiles, n_tiles;
 };
 
+// Epilogue of one warp over NCH chunks of 32 accumulator columns of its 32 rows: TMEM -> registers -> + bias -> act -> (+ residual ->
+// act) -> bf16/fp16 -> 128B-swizzled staging rows.  FULL: every column is a valid output channel (no per-group bounds checks).
+template <typename T, int NCH, bool GEN, bool FULL>
+__device__ __forceinline__ void epilogue_warp(uint32_t taddr, const float* __restrict__ bias, uint32_t out_row, uint32_t res_row, uint32_t xsw,
+                                              int col0, int ncols, bool has_res, const EpiAct& e1, const EpiAct& e2) {
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    if (!FULL && col0 + c * 32 >= ncols) break;          // warp-uniform
+    // one 32-column chunk at a time keeps the live accumulator registers at 32 (two chunks in flight spilled at 128 regs/thread);
+    // the other epilogue warp on this scheduler covers the TMEM latency
+    uint32_t v[1][32];
+    ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), v[0]);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int col = col0 + c * 32 + g * 8;            // column within the tile
+      if (FULL || col < ncols) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+        float f[8];
+        f[0] = __uint_as_float(v[0][g * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[0][g * 8 + 1]) + b0.y;
+        f[2] = __uint_as_float(v[0][g * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[0][g * 8 + 3]) + b0.w;
+        f[4] = __uint_as_float(v[0][g * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[0][g * 8 + 5]) + b1.y;
+        f[6] = __uint_as_float(v[0][g * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[0][g * 8 + 7]) + b1.w;
+        epi_act8<GEN>(f, e1);
+        // 16-byte chunk (c*4+g) of this warp's column range, XOR-swizzled by the row (xsw already holds (first chunk & 7) ^ (row & 7))
+        const uint32_t sw = (xsw ^ (uint32_t)(c * 4 + g)) << 4;
+        if (has_res) {
+          const uint4 rv = ptx::ld_shared_v4(res_row + sw);
+          float r[8];
+          unpack2<T>(rv.x, r[0], r[1]); unpack2<T>(rv.y, r[2], r[3]);
+          unpack2<T>(rv.z, r[4], r[5]); unpack2<T>(rv.w, r[6], r[7]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] += r[e];
+          epi_act8<GEN>(f, e2);
+        }
+        ptx::st_shared_v4(out_row + sw, make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7])));
+      }
+    }
+  }
+}
+
 template <typename T, int BN, bool GEN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_constant__ Tc2Args args) {
-  constexpr int STAGES = Cfg2<BN>::STAGES;
   constexpr int B_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int SLABS = BN / 64;
-  constexpr uint32_t OUT_OFF = STAGES * STAGE_BYTES;
-  constexpr uint32_t RES_OFF = OUT_OFF + SLABS * SLAB_BYTES;
-  constexpr uint32_t BAR_OFF = RES_OFF + 2 * SLABS * SLAB_BYTES;
+  constexpr int TILE_BYTES = SLABS * SLAB_BYTES;
+  constexpr int CPW = BN / 2;            // accumulator columns per epilogue warp
   const ConvParams& p = args.p;
+  const bool has_res = p.res != nullptr;
+  const SmemPlan plan = smem_plan<BN>(has_res);
+  const int STAGES = plan.stages;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_al + BAR_OFF);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_al + plan.bar_off);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* rfull_bar = tempty_bar + 2;
   uint64_t* rempty_bar = rfull_bar + 2;
@@ -94,7 +150,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
   const int nkb = p.Ktot / BK;
   const int num_tiles = args.num_tiles, n_tiles = args.n_tiles;
   const bool a_tma = args.a_tma != 0;
-  const bool has_res = p.res != nullptr;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -103,19 +158,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], 4);
+      ptx::mbar_init(&tempty_bar[a], NUM_EPI_WARPS);
       ptx::mbar_init(&rfull_bar[a], 1);
-      ptx::mbar_init(&rempty_bar[a], 4);
+      ptx::mbar_init(&rempty_bar[a], NUM_EPI_WARPS);
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 9 && lane == 0) {
+  if (warp == TMA_WARP && lane == 0) {
     ptx::tma_prefetch_desc(&args.tm_w);
     ptx::tma_prefetch_desc(&args.tm_y);
     if (a_tma) ptx::tma_prefetch_desc(&args.tm_a);
     if (has_res) ptx::tma_prefetch_desc(&args.tm_r);
   }
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     ptx::tmem_alloc(tmem_slot, 2 * BN);
     ptx::tmem_relinquish();
   }
@@ -158,8 +213,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
         for (int kb = 0; kb < nkb + LAG; ++kb) {
           if (kb < nkb) {
             const uint32_t g = kbg + (uint32_t)kb;
-            const int s = (int)(g % STAGES);
-            ptx::mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
+            const int s = (int)(g % (uint32_t)STAGES);
+            ptx::mbar_wait(&empty_bar[s], ((g / (uint32_t)STAGES) & 1) ^ 1);
             const uint32_t a_dst = smem_base + s * STAGE_BYTES + r0 * 128 + sw_off;
             const bool kvalid = tap < taps;
             const int dh_off = fr * p.dh, dw_off = fs * p.dw;
@@ -177,19 +232,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
           if (kb >= LAG) {
             ptx::cp_async_wait<LAG>();
             ptx::fence_proxy_async();
-            ptx::mbar_arrive(&full_bar[(kbg + (uint32_t)(kb - LAG)) % STAGES]);
+            ptx::mbar_arrive(&full_bar[(kbg + (uint32_t)(kb - LAG)) % (uint32_t)STAGES]);
           }
         }
         kbg += (uint32_t)nkb;
       }
     }
-  } else if (warp < 8) {
-    // ===================== epilogue =====================
-    const int q = warp - 4;                     // TMEM lane quarter of this warp (== warp % 4)
+  } else if (warp < 4 + NUM_EPI_WARPS) {
+    // ===================== epilogue (8 warps: 4 TMEM lane quarters x 2 column halves) =====================
+    const int ew = warp - 4;
+    const int q = ew & 3;                       // TMEM lane quarter (== warp % 4)
+    const int half = ew >> 2;                   // which half of the tile's columns
     const int row = q * 32 + lane;
-    const uint32_t rsw = (uint32_t)(row & 7);
+    const int col0 = half * CPW;                // first column of this warp within the tile
+    const uint32_t slab_off = (uint32_t)(col0 >> 6) * SLAB_BYTES;
+    const uint32_t xsw = (uint32_t)(((col0 >> 3) & 7) ^ (row & 7));
     const bool store_thread = threadIdx.x == 4 * 32;
-    const uint32_t out_row = smem_base + OUT_OFF + (uint32_t)row * 128u;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / n_tiles) * BM;
@@ -198,48 +256,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
       const int nslab = (ncols + 63) >> 6;
       const uint32_t acc = it & 1u;
       const uint32_t par = (it >> 1) & 1u;
-      const uint32_t res_row = smem_base + RES_OFF + acc * (SLABS * SLAB_BYTES) + (uint32_t)row * 128u;
-      const float* __restrict__ bias = p.bias + n0;
+      const uint32_t out_tile = smem_base + plan.out_off + acc * TILE_BYTES;
+      const uint32_t out_row = out_tile + slab_off + (uint32_t)row * 128u;
+      const uint32_t res_row = smem_base + plan.res_off + acc * TILE_BYTES + slab_off + (uint32_t)row * 128u;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)col0;
 
       ptx::mbar_wait(&tfull_bar[acc], par);                // accumulator complete
       ptx::tc_fence_after();
       if (has_res) ptx::mbar_wait(&rfull_bar[acc], par);   // residual tile landed
-      if (store_thread) ptx::bulk_wait_read0();            // previous tile's TMA store has finished reading the staging tile
-      ptx::named_bar_sync(1, 128);
-#pragma unroll 1
-      for (int j = 0; j < BN / 32; ++j) {
-        if (j * 32 >= ncols) break;                        // warp-uniform
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(j * 32), v);
-        ptx::tmem_ld_wait();
-        const uint32_t slab_off = (uint32_t)(j >> 1) * SLAB_BYTES;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {                      // groups of 8 output channels = one 16-byte chunk
-          const int c0 = j * 32 + g * 8;
-          if (c0 < ncols) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
-            float f[8];
-            f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
-            f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
-            f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
-            f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
-            epi_act8<GEN>(f, args.e1);
-            const uint32_t chunk = (uint32_t)((j & 1) * 4 + g);          // 16-byte chunk within the 128-byte slab row
-            const uint32_t sw = slab_off + ((chunk ^ rsw) << 4);
-            if (has_res) {
-              const uint4 rv = ptx::ld_shared_v4(res_row + sw);
-              float r[8];
-              unpack2<T>(rv.x, r[0], r[1]); unpack2<T>(rv.y, r[2], r[3]);
-              unpack2<T>(rv.z, r[4], r[5]); unpack2<T>(rv.w, r[6], r[7]);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] += r[e];
-              epi_act8<GEN>(f, args.e2);
-            }
-            ptx::st_shared_v4(out_row + sw, make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7])));
-          }
-        }
-      }
+      if (store_thread) ptx::bulk_wait_read<1>();          // the store issued two tiles ago has finished reading this staging buffer
+      ptx::named_bar_sync(1, NUM_EPI_WARPS * 32);
+      if (ncols == BN) epilogue_warp<T, CPW / 32, GEN, true>(taddr, p.bias + n0, out_row, res_row, xsw, col0, ncols, has_res, args.e1, args.e2);
+      else epilogue_warp<T, CPW / 32, GEN, false>(taddr, p.bias + n0, out_row, res_row, xsw, col0, ncols, has_res, args.e1, args.e2);
       // accumulator + residual buffers are free again
       ptx::tc_fence_before();
       __syncwarp();
@@ -248,26 +276,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
         if (has_res) ptx::mbar_arrive(&rempty_bar[acc]);
       }
       ptx::fence_proxy_async();                            // staging writes -> visible to the TMA engine
-      ptx::named_bar_sync(1, 128);
+      ptx::named_bar_sync(1, NUM_EPI_WARPS * 32);
       if (store_thread) {
-        for (int h = 0; h < nslab; ++h) ptx::tma_store_2d(&args.tm_y, smem_base + OUT_OFF + (uint32_t)h * SLAB_BYTES, n0 + h * 64, m0);
+        for (int h = 0; h < nslab; ++h) ptx::tma_store_2d(&args.tm_y, out_tile + (uint32_t)h * SLAB_BYTES, n0 + h * 64, m0);
         ptx::bulk_commit();
       }
     }
     if (store_thread) ptx::bulk_wait_all0();
-  } else if (warp == 8) {
+  } else if (warp == MMA_WARP) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_f16(TcType<T>::is_bf16, BM, BN);
-      uint32_t g = 0, it = 0;
+      uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const uint32_t acc = it & 1u;
         ptx::mbar_wait(&tempty_bar[acc], ((it >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < nkb; ++kb, ++g) {
-          const int s = (int)(g % STAGES);
-          ptx::mbar_wait(&full_bar[s], (g / STAGES) & 1);
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(&full_bar[s], ph);
           ptx::tc_fence_after();
           const uint32_t a_addr = smem_base + s * STAGE_BYTES;
           const uint32_t b_addr = a_addr + A_BYTES;
@@ -278,17 +307,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
             ptx::umma_f16(d_tmem, da, db, idesc, (kb | k) ? 1u : 0u);
           }
           ptx::umma_commit(&empty_bar[s]);     // frees this stage once the MMAs above have read it
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         ptx::umma_commit(&tfull_bar[acc]);     // accumulator complete -> epilogue
       }
     }
   } else {
-    // ===================== TMA issuer (one thread): weights, A (GEMM mode), residual =====================
+    // ===================== TMA issuer (one thread): weights, A (matrix / im2col modes), residual =====================
     if (lane == 0) {
-      uint32_t g = 0, it = 0;
+      uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      const int cpt = p.Cin_p >> 6;                 // 64-channel chunks per filter tap (im2col mode)
+      const int HoWo = p.Ho * p.Wo;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int m0 = (tile / n_tiles) * BM;
         const int n0 = (tile % n_tiles) * BN;
+        int bn = 0, bh = 0, bw = 0;
+        if (args.a_tma == 2) {                       // first output pixel of the tile -> base pixel of the im2col bounding box
+          bn = m0 / HoWo;
+          const int rem = m0 - bn * HoWo;
+          const int ho = rem / p.Wo;
+          bh = ho * p.sh - p.pt;
+          bw = (rem - ho * p.Wo) * p.sw - p.pl;
+        }
         if (has_res) {
           const uint32_t rb = it & 1u;
           const int ncols = min(BN, p.Cout_p - n0);
@@ -296,15 +338,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
           ptx::mbar_wait(&rempty_bar[rb], ((it >> 1) & 1u) ^ 1u);
           ptx::mbar_arrive_expect_tx(&rfull_bar[rb], (uint32_t)nslab * SLAB_BYTES);
           for (int h = 0; h < nslab; ++h)
-            ptx::tma_load_2d(smem_base + RES_OFF + rb * (SLABS * SLAB_BYTES) + (uint32_t)h * SLAB_BYTES, &args.tm_r, &rfull_bar[rb], n0 + h * 64, m0);
+            ptx::tma_load_2d(smem_base + plan.res_off + rb * TILE_BYTES + (uint32_t)h * SLAB_BYTES, &args.tm_r, &rfull_bar[rb], n0 + h * 64, m0);
         }
-        for (int kb = 0; kb < nkb; ++kb, ++g) {
-          const int s = (int)(g % STAGES);
-          ptx::mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
+        int tap = 0, chunk = 0, fr = 0, fs = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
           const uint32_t a_dst = smem_base + s * STAGE_BYTES;
           ptx::mbar_arrive_expect_tx(&full_bar[s], a_tma ? (uint32_t)STAGE_BYTES : (uint32_t)B_BYTES);
-          if (a_tma) ptx::tma_load_2d(a_dst, &args.tm_a, &full_bar[s], kb * BK, m0);
+          if (args.a_tma == 1) {
+            ptx::tma_load_2d(a_dst, &args.tm_a, &full_bar[s], kb * BK, m0);
+          } else if (args.a_tma == 2) {
+            ptx::tma_load_im2col_4d(a_dst, &args.tm_a, &full_bar[s], chunk * BK, bw, bh, bn, (uint32_t)(fs * p.dw), (uint32_t)(fr * p.dh));
+            if (++chunk == cpt) { chunk = 0; ++tap; if (++fs == p.kw) { fs = 0; ++fr; } }
+          }
           ptx::tma_load_2d(a_dst + A_BYTES, &args.tm_w, &full_bar[s], kb * BK, n0);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -313,7 +361,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
   __syncwarp();
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 8) ptx::tmem_dealloc(tmem_base, 2 * BN);
+  if (warp == MMA_WARP) ptx::tmem_dealloc(tmem_base, 2 * BN);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
@@ -346,7 +394,41 @@ CUtensorMap make_tmap_2d(const void* base, bool bf16, uint64_t inner, uint64_t o
   return m;
 }
 
+PFN_cuTensorMapEncodeIm2col_v12000 encode_im2col_fn() {
+  static PFN_cuTensorMapEncodeIm2col_v12000 fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess) ptr = nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(ptr);
+  }();
+  return fn;
+}
+
+// NHWC activations as a rank-4 {C, W, H, N} tensor traversed in im2col mode: 128 output pixels x 64 channels per box.
+// Bounding box: lower corner = -padding, upper corner chosen so that exactly Wo x Ho base pixels exist per image at the
+// convolution's stride (traversal stride).
+CUtensorMap make_tmap_im2col(const ConvParams& p, bool bf16) {
+  auto enc = encode_im2col_fn();
+  B200_CHECK(enc, B200_ERR_CUDA, "cuTensorMapEncodeIm2col is not available from this driver");
+  const int64_t sw = p.x_sw ? p.x_sw : p.Cin_p, sh = p.x_sh ? p.x_sh : (int64_t)p.W * p.Cin_p, sn = p.x_sn ? p.x_sn : (int64_t)p.H * p.W * p.Cin_p;
+  CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)p.Cin_p, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+  cuuint64_t strides[3] = {(cuuint64_t)sw * 2, (cuuint64_t)sh * 2, (cuuint64_t)sn * 2};
+  int lower[2] = {-p.pl, -p.pt};
+  int upper[2] = {-p.pl + (p.Wo - 1) * p.sw - (p.W - 1), -p.pt + (p.Ho - 1) * p.sh - (p.H - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)p.sw, (cuuint32_t)p.sh, 1};
+  CUresult r = enc(&m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(p.x), dims, strides, lower, upper,
+                   (cuuint32_t)BK, (cuuint32_t)BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeIm2col failed (" << (int)r << ") for a " << p.N << "x" << p.H << "x" << p.W << "x" << p.Cin_p
+                                                                                   << " tensor, corners [" << lower[0] << "," << lower[1] << "]/[" << upper[0]
+                                                                                   << "," << upper[1] << "]");
+  return m;
+}
+
 int g_sm_count = 0;
+int g_im2col = -1;   // -1 unread; B200_IM2COL=0 disables the im2col-mode TMA path (cp.async gather instead)
 
 EpiAct make_epi(int kind, float a, float b) {
   EpiAct e;
@@ -366,21 +448,56 @@ void launch_tc2(const ConvParams& p, bool bf16, cudaStream_t s) {
   const int m_tiles = (p.M + BM - 1) / BM;
   a.n_tiles = p.Cout_alloc / BN;
   a.num_tiles = m_tiles * a.n_tiles;
-  a.a_tma = conv_tc2_a_is_matrix(p) ? 1 : 0;
+  a.a_tma = conv_tc2_a_is_matrix(p) ? 1 : (conv_tc2_a_is_im2col(p) ? 2 : 0);
   a.tm_w = make_tmap_2d(p.w, bf16, (uint64_t)p.Ktot, (uint64_t)p.Cout_alloc, (uint64_t)p.w_ld * 2, BK, BN);
   a.tm_y = make_tmap_2d(p.y, bf16, (uint64_t)p.Cout_p, (uint64_t)p.M, (uint64_t)p.ldy * 2, 64, BM);
   a.tm_r = p.res ? make_tmap_2d(p.res, bf16, (uint64_t)p.Cout_p, (uint64_t)p.M, (uint64_t)p.ldy * 2, 64, BM) : a.tm_y;
-  a.tm_a = a.a_tma ? make_tmap_2d(p.x, bf16, (uint64_t)p.Cin_p, (uint64_t)p.M, (uint64_t)p.Cin_p * 2, BK, BM) : a.tm_y;
+  a.tm_a = a.a_tma == 1 ? make_tmap_2d(p.x, bf16, (uint64_t)p.Cin_p, (uint64_t)p.M, (uint64_t)p.Cin_p * 2, BK, BM)
+                        : (a.a_tma == 2 ? make_tmap_im2col(p, bf16) : a.tm_y);
   const int grid = std::min(a.num_tiles, g_sm_count > 0 ? g_sm_count : 148);
-  if (conv_acts_are_clamps(p)) conv_tc2_kernel<T, BN, false><<<grid, NUM_THREADS, tc2_smem_bytes<BN>(), s>>>(a);
-  else conv_tc2_kernel<T, BN, true><<<grid, NUM_THREADS, tc2_smem_bytes<BN>(), s>>>(a);
+  const unsigned smem = smem_plan<BN>(p.res != nullptr).total;
+  if (conv_acts_are_clamps(p)) conv_tc2_kernel<T, BN, false><<<grid, NUM_THREADS, smem, s>>>(a);
+  else conv_tc2_kernel<T, BN, true><<<grid, NUM_THREADS, smem, s>>>(a);
 }
 
 }  // namespace
 
 // A is a plain [M][Cin_p] matrix: FullyConnected, or a 1x1 / stride-1 / unpadded convolution over NHWC
 bool conv_tc2_a_is_matrix(const ConvParams& p) {
-  return p.kh == 1 && p.kw == 1 && p.sh == 1 && p.sw == 1 && p.pt == 0 && p.pl == 0 && p.Ho == p.H && p.Wo == p.W && p.Cin_p % 8 == 0;
+  return p.kh == 1 && p.kw == 1 && p.sh == 1 && p.sw == 1 && p.pt == 0 && p.pl == 0 && p.Ho == p.H && p.Wo == p.W && p.Cin_p % 8 == 0 && p.x_sw == 0;
+}
+
+bool conv_tc2_im2col_enabled() {
+  if (g_im2col < 0) {
+    const char* e = getenv("B200_IM2COL");
+    g_im2col = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_im2col != 0;
+}
+
+// The space-to-depth stem reads overlapping 64-element windows (pixel stride 32 B < 128 B of channels).  Ask the driver once whether
+// it accepts such a tensor map (a dummy, 1 KiB aligned base address is enough: encoding never dereferences it).
+bool conv_tc2_s2d_encode_ok() {
+  static int ok = -1;
+  if (ok >= 0) return ok != 0;
+  auto enc = encode_im2col_fn();
+  if (!enc) return (ok = 0) != 0;
+  CUtensorMap m;
+  cuuint64_t dims[4] = {64, 112, 115, 2};
+  cuuint64_t strides[3] = {32, 115 * 32, 115 * 115 * 32};
+  int lower[2] = {0, 0}, upper[2] = {0, -3};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, reinterpret_cast<void*>(uintptr_t(1) << 30), dims, strides, lower, upper, 64, 128, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ok = r == CUDA_SUCCESS ? 1 : 0;
+  return ok != 0;
+}
+
+bool conv_tc2_a_is_im2col(const ConvParams& p) {
+  if (!conv_tc2_im2col_enabled() || conv_tc2_a_is_matrix(p)) return false;
+  const int uw = -p.pl + (p.Wo - 1) * p.sw - (p.W - 1), uh = -p.pt + (p.Ho - 1) * p.sh - (p.H - 1);
+  return p.Cin_p % 64 == 0 && p.pl <= 128 && p.pt <= 128 && uw >= -128 && uw <= 127 && uh >= -128 && uh <= 127 && p.sw <= 8 && p.sh <= 8 &&
+         (p.kw - 1) * p.dw < 65536 && (p.kh - 1) * p.dh < 65536;
 }
 
 bool conv_acts_are_clamps(const ConvParams& p) {
@@ -398,14 +515,14 @@ void conv_tc2_init_device() {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
   auto opt_in = [](auto kernel, int bytes) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); };
-  opt_in(conv_tc2_kernel<__nv_bfloat16, 64, false>, tc2_smem_bytes<64>());
-  opt_in(conv_tc2_kernel<__nv_bfloat16, 64, true>, tc2_smem_bytes<64>());
-  opt_in(conv_tc2_kernel<__nv_bfloat16, 128, false>, tc2_smem_bytes<128>());
-  opt_in(conv_tc2_kernel<__nv_bfloat16, 128, true>, tc2_smem_bytes<128>());
-  opt_in(conv_tc2_kernel<__half, 64, false>, tc2_smem_bytes<64>());
-  opt_in(conv_tc2_kernel<__half, 64, true>, tc2_smem_bytes<64>());
-  opt_in(conv_tc2_kernel<__half, 128, false>, tc2_smem_bytes<128>());
-  opt_in(conv_tc2_kernel<__half, 128, true>, tc2_smem_bytes<128>());
+  opt_in(conv_tc2_kernel<__nv_bfloat16, 64, false>, SMEM_LIMIT);
+  opt_in(conv_tc2_kernel<__nv_bfloat16, 64, true>, SMEM_LIMIT);
+  opt_in(conv_tc2_kernel<__nv_bfloat16, 128, false>, SMEM_LIMIT);
+  opt_in(conv_tc2_kernel<__nv_bfloat16, 128, true>, SMEM_LIMIT);
+  opt_in(conv_tc2_kernel<__half, 64, false>, SMEM_LIMIT);
+  opt_in(conv_tc2_kernel<__half, 64, true>, SMEM_LIMIT);
+  opt_in(conv_tc2_kernel<__half, 128, false>, SMEM_LIMIT);
+  opt_in(conv_tc2_kernel<__half, 128, true>, SMEM_LIMIT);
 }
 
 void launch_conv_tc2(const ConvParams& p, int dtype, int bn, cudaStream_t s) {

@@ -60,7 +60,11 @@ static void enqueue_ingest(const b200_request& r, const RunCtx& c, int i) {
   const LTensor& t = r.net->in_tensors[i];
   const IOFormat& f = r.in_fmt[i];
   cudaStream_t s = (cudaStream_t)c.stream;
-  if (t.shape.size() == 4) {
+  if (t.layout == L_S2D16) {
+    int sl = f.layout == B200_LAYOUT_NHWC ? PL_NHWC_DENSE : PL_ROWMAJOR;
+    launch_ingest_s2d(r.in_dev[i], f.dtype, sl, c.ptr(t.buf), t.dtype, (int)t.shape[0], (int)t.shape[1], (int)t.shape[2], (int)t.shape[3], t.s2d_pt,
+                      t.s2d_pl, t.s2d_hb, t.s2d_wb, s);
+  } else if (t.shape.size() == 4) {
     int sl = f.layout == B200_LAYOUT_NHWC ? PL_NHWC_DENSE : PL_ROWMAJOR;
     launch_convert4(r.in_dev[i], f.dtype, sl, c.ptr(t.buf), t.dtype, phys_layout_of(t), (int)t.shape[0], (int)t.shape[1], (int)t.shape[2],
                     (int)t.shape[3], s);

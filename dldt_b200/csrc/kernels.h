@@ -29,6 +29,9 @@ struct ConvParams {
   int act1 = 0, act2 = 0;
   float a1 = 0, b1 = 0, a2 = 0, b2 = 0;
   int out_f32 = 0;             // write fp32 instead of the compute type
+  // activation addressing override (elements; 0 = dense NHWC: Cin_p, W*Cin_p, H*W*Cin_p).  Used by the space-to-depth first
+  // convolution, whose "pixels" are overlapping 64-element windows of a 16-channel image.  TMA paths only.
+  int64_t x_sw = 0, x_sh = 0, x_sn = 0;
   int batch = 1;               // blockIdx.z batches (batched MatMul); strides in elements
   int64_t x_bs = 0, w_bs = 0, y_bs = 0;
 };
@@ -41,6 +44,9 @@ bool conv_acts_are_clamps(const ConvParams& p);
 // Persistent TMA-fed variant (conv_tc2.cu): used whenever one weight matrix serves the whole launch.
 bool conv_tc2_supported(const ConvParams& p);
 bool conv_tc2_a_is_matrix(const ConvParams& p);
+bool conv_tc2_a_is_im2col(const ConvParams& p);
+bool conv_tc2_s2d_encode_ok();                    // the driver accepts the overlapping-window tensor map of the space-to-depth stem
+bool conv_tc2_im2col_enabled();                   // B200_IM2COL != 0 and the driver exports cuTensorMapEncodeIm2col   // A tile by im2col-mode TMA (Cin_p % 64 == 0)
 void launch_conv_tc2(const ConvParams& p, int dtype, int bn, cudaStream_t s);
 void conv_tc2_init_device();
 // CUDA-core fp32 path (fp32 mode: 1e-4 parity; also the reference for tcgen05 unit tests).
@@ -92,6 +98,9 @@ void launch_reduce(const void* x, void* y, int64_t outer, int64_t axis, int64_t 
 enum PhysLayout : int { PL_ROWMAJOR = 0, PL_NHWC8 = 1, PL_NHWC_DENSE = 2 };
 // rank-4 logical [N,C,H,W]; converts dtype and layout in one pass
 void launch_convert4(const void* src, int sdtype, int slayout, void* dst, int ddtype, int dlayout, int N, int C, int H, int W, cudaStream_t s);
+// network input (any blob precision, NCHW or NHWC) -> space-to-depth [N, Hb, Wb, 16] in the compute type (Layout L_S2D16)
+void launch_ingest_s2d(const void* src, int sdtype, int slayout, void* dst, int ddtype, int N, int C, int H, int W, int pt, int pl, int Hb, int Wb,
+                       cudaStream_t s);
 // flat dtype conversion
 void launch_convert_flat(const void* src, int sdtype, void* dst, int ddtype, int64_t n, cudaStream_t s);
 // generic permute of a dense row-major tensor: out[idx] = in[perm(idx)]

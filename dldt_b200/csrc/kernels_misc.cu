@@ -402,6 +402,31 @@ __global__ void convert4_kernel(const S* __restrict__ src, int slayout, D* __res
   float v = c < C ? ldf<S>(src, phys_index(slayout, n, c, h, w, C, H, W)) : 0.f;
   stf<D>(dst, i, v);
 }
+// One thread per 16-channel block: gathers the 2x2 pixel patch (zero outside the image), converts, writes 32 bytes.
+template <typename S, typename D>
+__global__ void ingest_s2d_kernel(const S* __restrict__ src, int slayout, D* __restrict__ dst, int N, int C, int H, int W, int pt, int pl, int Hb,
+                                  int Wb) {
+  const int64_t total = (int64_t)N * Hb * Wb;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int wb = (int)(i % Wb);
+  const int64_t t = i / Wb;
+  const int hb = (int)(t % Hb), n = (int)(t / Hb);
+  __align__(16) D out[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) stf<D>(out, k, 0.f);
+#pragma unroll
+  for (int dr = 0; dr < 2; ++dr)
+#pragma unroll
+    for (int ds = 0; ds < 2; ++ds) {
+      const int h = 2 * hb + dr - pt, w = 2 * wb + ds - pl;
+      if ((unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W)
+        for (int c = 0; c < C; ++c) stf<D>(out, (dr * 2 + ds) * C + c, ldf<S>(src, phys_index(slayout, n, c, h, w, C, H, W)));
+    }
+  uint4* o = reinterpret_cast<uint4*>(dst + i * 16);
+  o[0] = reinterpret_cast<const uint4*>(out)[0];
+  o[1] = reinterpret_cast<const uint4*>(out)[1];
+}
 template <typename S, typename D>
 __global__ void convert_flat_kernel(const S* __restrict__ src, D* __restrict__ dst, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -591,6 +616,26 @@ void launch_convert4(const void* src, int sdtype, int slayout, void* dst, int dd
     case B200_I32: convert4_dst<int32_t>(src, slayout, dst, ddtype, dlayout, N, C, H, W, s); break;
     case B200_U8: convert4_dst<uint8_t>(src, slayout, dst, ddtype, dlayout, N, C, H, W, s); break;
     default: B200_THROW(B200_ERR_UNSUPPORTED, "convert4: src dtype " << sdtype);
+  }
+}
+template <typename S>
+static void ingest_s2d_dst(const void* src, int slayout, void* dst, int ddtype, int N, int C, int H, int W, int pt, int pl, int Hb, int Wb, cudaStream_t s) {
+  const int64_t total = (int64_t)N * Hb * Wb;
+  if (total == 0) return;
+  unsigned g = grid_for(total, 256);
+  if (ddtype == B200_BF16) ingest_s2d_kernel<S, __nv_bfloat16><<<g, 256, 0, s>>>((const S*)src, slayout, (__nv_bfloat16*)dst, N, C, H, W, pt, pl, Hb, Wb);
+  else if (ddtype == B200_F16) ingest_s2d_kernel<S, __half><<<g, 256, 0, s>>>((const S*)src, slayout, (__half*)dst, N, C, H, W, pt, pl, Hb, Wb);
+  else B200_THROW(B200_ERR_UNSUPPORTED, "ingest_s2d: destination must be bf16/f16");
+}
+void launch_ingest_s2d(const void* src, int sdtype, int slayout, void* dst, int ddtype, int N, int C, int H, int W, int pt, int pl, int Hb, int Wb,
+                       cudaStream_t s) {
+  B200_CHECK(C >= 1 && C <= 4, B200_ERR_INVALID, "ingest_s2d: at most 4 channels");
+  switch (sdtype) {
+    case B200_F32: ingest_s2d_dst<float>(src, slayout, dst, ddtype, N, C, H, W, pt, pl, Hb, Wb, s); break;
+    case B200_F16: ingest_s2d_dst<__half>(src, slayout, dst, ddtype, N, C, H, W, pt, pl, Hb, Wb, s); break;
+    case B200_BF16: ingest_s2d_dst<__nv_bfloat16>(src, slayout, dst, ddtype, N, C, H, W, pt, pl, Hb, Wb, s); break;
+    case B200_U8: ingest_s2d_dst<uint8_t>(src, slayout, dst, ddtype, N, C, H, W, pt, pl, Hb, Wb, s); break;
+    default: B200_THROW(B200_ERR_UNSUPPORTED, "ingest_s2d: src dtype " << sdtype);
   }
 }
 template <typename S>

@@ -183,6 +183,18 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src_smem
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src_smem), "r"(c0), "r"(c1)
                : "memory");
 }
+// im2col-mode TMA load of `pixelsPerColumn` pixels x `channelsPerPixel` channels starting at base pixel (w, h, n) of the
+// bounding box, shifted by the filter-tap offsets (off_w, off_h); out-of-image pixels are zero-filled
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst_smem, const void* tmap, uint64_t* bar, int c, int w, int h, int n, uint32_t off_w,
+                                                   uint32_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(
+          dst_smem),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"((unsigned short)off_w), "h"((unsigned short)off_h)
+      : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // named barrier among `count` threads (count % 32 == 0); id 0 is __syncthreads
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) {

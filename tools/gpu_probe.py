@@ -47,7 +47,11 @@ try:
             rows = sorted(((pc[e["name"]]["real_time"], e) for e in eg), key=lambda t: -t[0])
             tot = sum(r[0] for r in rows)
             print("per-kernel total %.3f ms" % (tot / 1e3))
-            for us, e in rows[:12]:
+            for us, e in rows[:14]:
                 print("  %8.1f us %5.1f%% %-14s %-28s %7.1f TFLOP/s %7.1f GB/s  %s" % (us, 100 * us / tot, e["type"], e["impl"], e["flops"] / us / 1e6, e["bytes"] / us / 1e3, e["name"]))
+            print("full schedule (execution order):")
+            for e in eg:
+                us = pc[e["name"]]["real_time"]
+                print("  %8.1f us %-14s %-40s %7.1f TFLOP/s %7.1f GB/s  %s" % (us, e["type"], e["impl"], e["flops"] / us / 1e6, e["bytes"] / us / 1e3, e["name"]))
 except Exception as e:
     traceback.print_exc()

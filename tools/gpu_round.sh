@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/${TAG}_gpu.txt 2>&1
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/${TAG}_pytest_gpu.log
 tail -15 gpurun_out/${TAG}_pytest_gpu.log
-timeout 600 python tools/gpu_probe.py > gpurun_out/${TAG}_probe.log 2>&1; tail -45 gpurun_out/${TAG}_probe.log
+timeout 600 python tools/gpu_probe.py > gpurun_out/${TAG}_probe.log 2>&1; grep -v "^  " gpurun_out/${TAG}_probe.log | tail -30
 timeout 900 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err; cat gpurun_out/${TAG}_bench_ref.json; tail -3 gpurun_out/${TAG}_bench_ref.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 420 --csv --log-file gpurun_out/${TAG}_launches.csv \
