@@ -229,12 +229,15 @@ def run_b200(args, rank, local_rank, world):
     req.wait()
     sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    if not args.no_clock_sampler:
+        sampler.start()
     ms_total = req.time_launches(args.steps)          # b200_request_time: event, K graph launches, event, sync
     barrier()
     clocks = sampler.stop()
     ms_total = max_over_ranks(ms_total)
     ms_step = ms_total / args.steps
+    # diagnostics (outside the timed region): the same launch timed in short bursts, to expose clock drift / interference
+    bursts = [round(req.time_launches(10) / 10, 4) for _ in range(4)]
     value = world * B * 1e3 / ms_step
 
     # ---- e2e: public API, pinned host buffers, 2 requests in flight ----
@@ -289,7 +292,7 @@ def run_b200(args, rank, local_rank, world):
                        "gflop_per_img": round(flops_per_step / B / 1e9, 4)},
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "requests_in_flight": 2},
-            "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "clocks": clocks}
+            "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "clocks": clocks, "burst_ms_per_step": bursts}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             cb = reference_cpu_run(args.ref_batch, 1, args.ref_steps)
@@ -312,6 +315,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=32, help="batch of the CPU reference sample")
     ap.add_argument("--ref-steps", type=int, default=8, help="timed CPU requests of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostic: do not poll nvidia-smi during the timed region")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

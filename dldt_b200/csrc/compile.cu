@@ -109,6 +109,7 @@ class Lowerer {
   std::map<int, FusedConv> fconv_;                  // emit_at -> record
   std::map<int, FusedMvn> fmvn_;
   std::map<int, FusedElt> felt_;
+  std::map<int, int> box_dir_;                      // arena box -> 1 if its producer wrote it last-row-first
 
   // ---- small helpers ----
   const Node& node(int id) const { return g_.nodes[id]; }
@@ -518,6 +519,14 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
     s.impl = "simt_fp32_128x64x16";
   }
   const bool has_res = res.space != SP_NONE;
+  const char* no_alt = getenv("B200_NO_ALTERNATE");
+  // opposite to the direction in which the producer of x wrote it (kernels other than conv_tc2 write first-to-last)
+  {
+    int in_dir = 0;
+    if (tx && tx->buf.space == SP_ARENA) { auto d = box_dir_.find(tx->buf.box); if (d != box_dir_.end()) in_dir = d->second; }
+    p.reverse = (v2 && !(no_alt && no_alt[0] == '1')) ? !in_dir : 0;
+    if (ty && ty->buf.space == SP_ARENA) box_dir_[ty->buf.box] = p.reverse;
+  }
   s.launch = [=](const RunCtx& c) {
     ConvParams q = p;
     q.x = c.ptr(x); q.w = c.ptr(w); q.bias = reinterpret_cast<const float*>(c.ptr(bias));

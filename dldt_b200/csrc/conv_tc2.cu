@@ -78,6 +78,7 @@ struct Tc2Args {
   EpiAct e1, e2;      // activation after bias / after the residual sum
   int a_tma;          // 0: cp.async gather, 1: 2-D TMA (A is a matrix), 2: im2col-mode TMA
   int num_tiles, n_tiles;
+  int reverse;        // walk the tiles from the last row block to the first (see ConvParams::reverse)
 };
 
 // Epilogue of one warp over NCH chunks of 32 accumulator columns of its 32 rows: TMEM -> registers -> + bias -> act -> (+ residual ->
@@ -191,7 +192,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
       const int cpc = p.Cin_p >> 3;       // 16-byte chunks per filter tap
       const int taps = p.kh * p.kw;
       uint32_t kbg = 0;                   // k-blocks issued so far (all tiles)
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int t_ = blockIdx.x; t_ < num_tiles; t_ += gridDim.x) {
+        const int tile = args.reverse ? num_tiles - 1 - t_ : t_;
         const int m0 = (tile / n_tiles) * BM;
         int hi0[8], wi0[8];
         int64_t xoff[8];
@@ -249,7 +251,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
     const uint32_t xsw = (uint32_t)(((col0 >> 3) & 7) ^ (row & 7));
     const bool store_thread = threadIdx.x == 4 * 32;
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int t_ = blockIdx.x; t_ < num_tiles; t_ += gridDim.x, ++it) {
+      const int tile = args.reverse ? num_tiles - 1 - t_ : t_;
       const int m0 = (tile / n_tiles) * BM;
       const int n0 = (tile % n_tiles) * BN;
       const int ncols = min(BN, p.Cout_p - n0);           // valid output channels of this tile (multiple of 8)
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
       uint32_t it = 0;
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int t_ = blockIdx.x; t_ < num_tiles; t_ += gridDim.x, ++it) {
         const uint32_t acc = it & 1u;
         ptx::mbar_wait(&tempty_bar[acc], ((it >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
         ptx::tc_fence_after();
@@ -320,7 +323,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
       uint32_t ph = 0;
       const int cpt = p.Cin_p >> 6;                 // 64-channel chunks per filter tap (im2col mode)
       const int HoWo = p.Ho * p.Wo;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int t_ = blockIdx.x; t_ < num_tiles; t_ += gridDim.x, ++it) {
+        const int tile = args.reverse ? num_tiles - 1 - t_ : t_;
         const int m0 = (tile / n_tiles) * BM;
         const int n0 = (tile % n_tiles) * BN;
         int bn = 0, bh = 0, bw = 0;
@@ -448,6 +452,7 @@ void launch_tc2(const ConvParams& p, bool bf16, cudaStream_t s) {
   const int m_tiles = (p.M + BM - 1) / BM;
   a.n_tiles = p.Cout_alloc / BN;
   a.num_tiles = m_tiles * a.n_tiles;
+  a.reverse = p.reverse;
   a.a_tma = conv_tc2_a_is_matrix(p) ? 1 : (conv_tc2_a_is_im2col(p) ? 2 : 0);
   a.tm_w = make_tmap_2d(p.w, bf16, (uint64_t)p.Ktot, (uint64_t)p.Cout_alloc, (uint64_t)p.w_ld * 2, BK, BN);
   a.tm_y = make_tmap_2d(p.y, bf16, (uint64_t)p.Cout_p, (uint64_t)p.M, (uint64_t)p.ldy * 2, 64, BM);

@@ -217,6 +217,13 @@ int b200_compile(const b200_graph* g, const b200_compile_options* opts, b200_net
     B200_CHECK(opts->abi_version == B200_ABI_VERSION, B200_ERR_INVALID, "ABI version mismatch");
     std::unique_ptr<b200_network> net(new b200_network());
     net->device = opts->device;
+    if (opts->device >= 0) {
+      // bring the runtime + primary context up BEFORE lowering: the compiler asks the driver which tensor maps it can encode
+      // (cudaGetDriverEntryPoint fails on an uninitialised runtime, which silently cost the space-to-depth stem: profiles/README.md)
+      int n0 = 0;
+      if (cudaGetDeviceCount(&n0) == cudaSuccess && opts->device < n0) { cudaSetDevice(opts->device); cudaFree(nullptr); }
+      cudaGetLastError();
+    }
     lower_graph(*g, *opts, *net);
     if (opts->device >= 0) {
       int n = 0;

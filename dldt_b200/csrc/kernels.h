@@ -32,6 +32,9 @@ struct ConvParams {
   // activation addressing override (elements; 0 = dense NHWC: Cin_p, W*Cin_p, H*W*Cin_p).  Used by the space-to-depth first
   // convolution, whose "pixels" are overlapping 64-element windows of a 16-channel image.  TMA paths only.
   int64_t x_sw = 0, x_sh = 0, x_sn = 0;
+  // Walk the output tiles last-to-first.  The compiler alternates the direction from one kernel to the next so that a kernel starts on
+  // the rows its producer wrote last, which are still resident in the 126 MB L2 (the tensors themselves are 100-400 MB at batch 256).
+  int reverse = 0;
   int batch = 1;               // blockIdx.z batches (batched MatMul); strides in elements
   int64_t x_bs = 0, w_bs = 0, y_bs = 0;
 };
