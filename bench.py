@@ -283,6 +283,26 @@ def run_b200(args, rank, local_rank, world):
                 "share_of_step": round(tc_us / all_us, 4) if all_us else None,
                 "step_achieved": round(value / world * GFLOP_PER_IMG / 1e3, 2), "step_frac": round(value / world * GFLOP_PER_IMG / 1e3 / peak, 4)}
 
+    # ---- batch-1 p50 latency (second half of BASELINE.json's metric): sync requests through the public API ----
+    lat = None
+    if not args.no_latency:
+        f1 = zoo.resnet50(batch=1)
+        net1 = core.load_network(f1, "B200.%d" % local_rank, {"B200_INFERENCE_PRECISION": "BF16"})
+        r1 = net1.create_infer_request(input_precisions={"data": "U8"})
+        r1.input_blobs["data"][...] = rng.integers(0, 256, r1.input_blobs["data"].shape, dtype=np.uint8)
+        for _ in range(20):
+            r1.infer()
+        ts = []
+        for _ in range(200):
+            t1 = time.perf_counter()
+            r1.start_async()
+            r1.wait()
+            ts.append((time.perf_counter() - t1) * 1e3)
+        dev_ms = r1.time_launches(50) / 50
+        lat = {"p50_ms": round(statistics.median(ts), 4), "p99_ms": round(sorted(ts)[int(len(ts) * 0.99) - 1], 4), "device_only_ms": round(dev_ms, 4),
+               "how": "200 synchronous StartAsync+Wait of batch 1 (U8 input from pinned host memory, fp32 scores back), median as benchmark_app -api sync"}
+        del r1, net1
+
     line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
@@ -292,7 +312,7 @@ def run_b200(args, rank, local_rank, world):
                        "gflop_per_img": round(flops_per_step / B / 1e9, 4)},
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "requests_in_flight": 2},
-            "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "clocks": clocks, "burst_ms_per_step": bursts}
+            "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "clocks": clocks, "burst_ms_per_step": bursts, "latency_b1": lat}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             cb = reference_cpu_run(args.ref_batch, 1, args.ref_steps)
@@ -315,6 +335,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=32, help="batch of the CPU reference sample")
     ap.add_argument("--ref-steps", type=int, default=8, help="timed CPU requests of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the batch-1 latency leg")
     ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostic: do not poll nvidia-smi during the timed region")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -53,21 +53,27 @@ constexpr int SMEM_LIMIT = 232448;       // 227 KB opt-in maximum per CTA on sm_
 // Shared-memory plan (all offsets multiples of 1024 from the aligned base):
 //   [stages x (A tile 16 KB + B tile BN*128 B)] [output staging x2] [residual staging x2, only when a residual is fused] [barriers]
 // The stage count takes whatever is left: 5 (BN=128) / 8 (BN=64) without a residual, 3 / 6 with one.
-struct SmemPlan { int stages; uint32_t out_off, res_off, bar_off, total; };
+struct SmemPlan { int stages; uint32_t stage_bytes, out_off, res_off, w_off, bar_off, total; };
+// ws_bytes != 0: weight-stationary mode - the whole packed weight matrix (single N tile, <= 96 KB) is loaded once per CTA and the
+// ring stages carry activation tiles only (removes the per-tile re-fetch of the weights from L2, half of the operand traffic of the
+// 3x3 64->64 layers and of the stem).
 template <int BN>
-__host__ __device__ inline SmemPlan smem_plan(bool has_res) {
-  const int stage_bytes = A_BYTES + BN * 128, tile_bytes = (BN / 64) * SLAB_BYTES;
-  const int fixed = 2 * tile_bytes + (has_res ? 2 * tile_bytes : 0) + 1024 /*align slack*/ + 1024 /*barriers*/;
+__host__ __device__ inline SmemPlan smem_plan(bool has_res, int ws_bytes) {
+  const int stage_bytes = ws_bytes ? A_BYTES : A_BYTES + BN * 128, tile_bytes = (BN / 64) * SLAB_BYTES;
+  const int fixed = 2 * tile_bytes + (has_res ? 2 * tile_bytes : 0) + ws_bytes + 1024 /*align slack*/ + 1024 /*barriers*/;
   int stages = (SMEM_LIMIT - fixed) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   SmemPlan pl;
   pl.stages = stages;
+  pl.stage_bytes = (uint32_t)stage_bytes;
   pl.out_off = (uint32_t)(stages * stage_bytes);
   pl.res_off = pl.out_off + 2u * tile_bytes;
-  pl.bar_off = pl.res_off + (has_res ? 2u * tile_bytes : 0u);
+  pl.w_off = pl.res_off + (has_res ? 2u * tile_bytes : 0u);
+  pl.bar_off = pl.w_off + (uint32_t)ws_bytes;
   pl.total = pl.bar_off + 1024u + 1024u;
   return pl;
 }
+constexpr int WS_MAX_BYTES = 96 * 1024;
 
 struct Tc2Args {
   CUtensorMap tm_a;   // activations: [M][Cin_p] matrix (a_tma 1) or {C, W, H, N} im2col tensor (a_tma 2)
@@ -78,6 +84,7 @@ struct Tc2Args {
   EpiAct e1, e2;      // activation after bias / after the residual sum
   int a_tma;          // 0: cp.async gather, 1: 2-D TMA (A is a matrix), 2: im2col-mode TMA
   int num_tiles, n_tiles;
+  int ws;             // weight-stationary mode (see smem_plan)
   int reverse;        // walk the tiles from the last row block to the first (see ConvParams::reverse)
 };
 
@@ -126,14 +133,16 @@ __device__ __forceinline__ void epilogue_warp(uint32_t taddr, const float* __res
 template <typename T, int BN, bool GEN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_constant__ Tc2Args args) {
   constexpr int B_BYTES = BN * 128;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int SLABS = BN / 64;
   constexpr int TILE_BYTES = SLABS * SLAB_BYTES;
   constexpr int CPW = BN / 2;            // accumulator columns per epilogue warp
   const ConvParams& p = args.p;
   const bool has_res = p.res != nullptr;
-  const SmemPlan plan = smem_plan<BN>(has_res);
+  const int nkb = args.p.Ktot / BK;
+  const bool ws = args.ws != 0;
+  const SmemPlan plan = smem_plan<BN>(has_res, ws ? nkb * B_BYTES : 0);
   const int STAGES = plan.stages;
+  const uint32_t stage_bytes = plan.stage_bytes;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -144,11 +153,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* rfull_bar = tempty_bar + 2;
   uint64_t* rempty_bar = rfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty_bar + 2);
+  uint64_t* wfull_bar = rempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int nkb = p.Ktot / BK;
   const int num_tiles = args.num_tiles, n_tiles = args.n_tiles;
   const bool a_tma = args.a_tma != 0;
 
@@ -163,6 +172,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
       ptx::mbar_init(&rfull_bar[a], 1);
       ptx::mbar_init(&rempty_bar[a], NUM_EPI_WARPS);
     }
+    ptx::mbar_init(wfull_bar, 1);
     ptx::fence_mbar_init();
   }
   if (warp == TMA_WARP && lane == 0) {
@@ -217,7 +227,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
             const uint32_t g = kbg + (uint32_t)kb;
             const int s = (int)(g % (uint32_t)STAGES);
             ptx::mbar_wait(&empty_bar[s], ((g / (uint32_t)STAGES) & 1) ^ 1);
-            const uint32_t a_dst = smem_base + s * STAGE_BYTES + r0 * 128 + sw_off;
+            const uint32_t a_dst = smem_base + s * stage_bytes + r0 * 128 + sw_off;
             const bool kvalid = tap < taps;
             const int dh_off = fr * p.dh, dw_off = fs * p.dw;
 #pragma unroll
@@ -298,11 +308,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
         ptx::mbar_wait(&tempty_bar[acc], ((it >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
+        if (ws && it == 0) ptx::mbar_wait(wfull_bar, 0);   // resident weights have landed
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(&full_bar[s], ph);
           ptx::tc_fence_after();
-          const uint32_t a_addr = smem_base + s * STAGE_BYTES;
-          const uint32_t b_addr = a_addr + A_BYTES;
+          const uint32_t a_addr = smem_base + s * stage_bytes;
+          const uint32_t b_addr = ws ? smem_base + plan.w_off + (uint32_t)kb * B_BYTES : a_addr + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = ptx::make_smem_desc_sw128(a_addr + k * 32);
@@ -323,6 +334,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
       uint32_t ph = 0;
       const int cpt = p.Cin_p >> 6;                 // 64-channel chunks per filter tap (im2col mode)
       const int HoWo = p.Ho * p.Wo;
+      if (ws) {                                     // one N tile: fetch the whole weight matrix once
+        ptx::mbar_arrive_expect_tx(wfull_bar, (uint32_t)nkb * B_BYTES);
+        for (int kb = 0; kb < nkb; ++kb) ptx::tma_load_2d(smem_base + plan.w_off + (uint32_t)kb * B_BYTES, &args.tm_w, wfull_bar, kb * BK, 0);
+      }
+      const uint32_t stage_tx = (a_tma ? (uint32_t)A_BYTES : 0u) + (ws ? 0u : (uint32_t)B_BYTES);
       for (int t_ = blockIdx.x; t_ < num_tiles; t_ += gridDim.x, ++it) {
         const int tile = args.reverse ? num_tiles - 1 - t_ : t_;
         const int m0 = (tile / n_tiles) * BM;
@@ -347,15 +363,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
         int tap = 0, chunk = 0, fr = 0, fs = 0;
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
-          const uint32_t a_dst = smem_base + s * STAGE_BYTES;
-          ptx::mbar_arrive_expect_tx(&full_bar[s], a_tma ? (uint32_t)STAGE_BYTES : (uint32_t)B_BYTES);
+          const uint32_t a_dst = smem_base + s * stage_bytes;
+          if (stage_tx) ptx::mbar_arrive_expect_tx(&full_bar[s], stage_tx);
+          else ptx::mbar_arrive(&full_bar[s]);
           if (args.a_tma == 1) {
             ptx::tma_load_2d(a_dst, &args.tm_a, &full_bar[s], kb * BK, m0);
           } else if (args.a_tma == 2) {
             ptx::tma_load_im2col_4d(a_dst, &args.tm_a, &full_bar[s], chunk * BK, bw, bh, bn, (uint32_t)(fs * p.dw), (uint32_t)(fr * p.dh));
             if (++chunk == cpt) { chunk = 0; ++tap; if (++fs == p.kw) { fs = 0; ++fr; } }
           }
-          ptx::tma_load_2d(a_dst + A_BYTES, &args.tm_w, &full_bar[s], kb * BK, n0);
+          if (!ws) ptx::tma_load_2d(a_dst + A_BYTES, &args.tm_w, &full_bar[s], kb * BK, n0);
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
@@ -453,6 +470,11 @@ void launch_tc2(const ConvParams& p, bool bf16, cudaStream_t s) {
   a.n_tiles = p.Cout_alloc / BN;
   a.num_tiles = m_tiles * a.n_tiles;
   a.reverse = p.reverse;
+  {
+    const int ws_bytes = (p.Ktot / BK) * BN * 128;
+    const char* no_ws = getenv("B200_NO_WS");
+    a.ws = (a.n_tiles == 1 && ws_bytes <= WS_MAX_BYTES && smem_plan<BN>(p.res != nullptr, ws_bytes).stages >= 4 && !(no_ws && no_ws[0] == '1')) ? 1 : 0;
+  }
   a.a_tma = conv_tc2_a_is_matrix(p) ? 1 : (conv_tc2_a_is_im2col(p) ? 2 : 0);
   a.tm_w = make_tmap_2d(p.w, bf16, (uint64_t)p.Ktot, (uint64_t)p.Cout_alloc, (uint64_t)p.w_ld * 2, BK, BN);
   a.tm_y = make_tmap_2d(p.y, bf16, (uint64_t)p.Cout_p, (uint64_t)p.M, (uint64_t)p.ldy * 2, 64, BM);
@@ -460,7 +482,7 @@ void launch_tc2(const ConvParams& p, bool bf16, cudaStream_t s) {
   a.tm_a = a.a_tma == 1 ? make_tmap_2d(p.x, bf16, (uint64_t)p.Cin_p, (uint64_t)p.M, (uint64_t)p.Cin_p * 2, BK, BM)
                         : (a.a_tma == 2 ? make_tmap_im2col(p, bf16) : a.tm_y);
   const int grid = std::min(a.num_tiles, g_sm_count > 0 ? g_sm_count : 148);
-  const unsigned smem = smem_plan<BN>(p.res != nullptr).total;
+  const unsigned smem = smem_plan<BN>(p.res != nullptr, a.ws ? (p.Ktot / BK) * BN * 128 : 0).total;
   if (conv_acts_are_clamps(p)) conv_tc2_kernel<T, BN, false><<<grid, NUM_THREADS, smem, s>>>(a);
   else conv_tc2_kernel<T, BN, true><<<grid, NUM_THREADS, smem, s>>>(a);
 }

@@ -11,9 +11,12 @@ timeout 600 python tools/gpu_probe.py > gpurun_out/${TAG}_probe.log 2>&1; grep -
 timeout 900 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err; cat gpurun_out/${TAG}_bench_ref.json; tail -3 gpurun_out/${TAG}_bench_ref.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 420 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_launches.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-latency > gpurun_out/${TAG}_ncu_launches.log 2>&1
 timeout 900 ncu --set full --clock-control none -k regex:${KRE} -s ${SKIP} -c ${CNT} -o gpurun_out/${TAG}_prof \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-latency > gpurun_out/${TAG}_ncu_full.log 2>&1
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,lts__t_bytes.sum \
+    --clock-control none -k regex:conv_tc2 -s 108 -c 54 --csv --log-file gpurun_out/${TAG}_conv_traffic.csv \
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-latency > gpurun_out/${TAG}_ncu_traffic.log 2>&1
 ncu -i gpurun_out/${TAG}_prof.ncu-rep --page raw --csv > gpurun_out/${TAG}_prof_raw.csv 2>/dev/null
 ls -la gpurun_out
 SZ=$(stat -c %s gpurun_out/${TAG}_prof.ncu-rep 2>/dev/null || echo 0)
