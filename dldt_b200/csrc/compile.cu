@@ -508,13 +508,19 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
   s.name = name; s.type = type; s.fused = fused; s.flops = flops; s.bytes = bytes;
   const int dt = cd_;
   int bn = 0;
-  bool v2 = false;
+  bool v2 = false, v3 = false;
   if (tc) {
     bn = conv_tc_pick_bn(p.Cout_p);
     const char* force_v1 = getenv("B200_CONV_TC_V1");
     v2 = conv_tc2_supported(p) && !(force_v1 && force_v1[0] == '1');
-    s.impl = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_128x" + std::to_string(bn) + "x64" +
-             (v2 ? (conv_tc2_a_is_matrix(p) ? "_persistent_tma" : (conv_tc2_a_is_im2col(p) ? "_persistent_im2col" : "_persistent_gather")) : "");
+    v3 = v2 && conv_tc3_preferred(p);
+    if (v3) {
+      bn = conv_tc3_pick_bn(p);
+      s.impl = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_pair256x" + std::to_string(bn) + "x64_" + conv_tc3_mode_name(p);
+    } else {
+      s.impl = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_128x" + std::to_string(bn) + "x64" +
+               (v2 ? (conv_tc2_a_is_matrix(p) ? "_persistent_tma" : (conv_tc2_a_is_im2col(p) ? "_persistent_im2col" : "_persistent_gather")) : "");
+    }
   } else {
     s.impl = "simt_fp32_128x64x16";
   }
@@ -532,7 +538,8 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
     q.x = c.ptr(x); q.w = c.ptr(w); q.bias = reinterpret_cast<const float*>(c.ptr(bias));
     q.res = has_res ? c.ptr(res) : nullptr;
     q.y = c.ptr(y);
-    if (tc && v2) launch_conv_tc2(q, dt, bn, (cudaStream_t)c.stream);
+    if (tc && v3) launch_conv_tc3(q, dt, bn, (cudaStream_t)c.stream);
+    else if (tc && v2) launch_conv_tc2(q, dt, bn, (cudaStream_t)c.stream);
     else if (tc) launch_conv_tc(q, dt, bn, (cudaStream_t)c.stream);
     else launch_conv_f32(q, (cudaStream_t)c.stream);
   };

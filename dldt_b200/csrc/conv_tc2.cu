@@ -385,7 +385,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
   if (warp == MMA_WARP) ptx::tmem_dealloc(tmem_base, 2 * BN);
 }
 
-// ---- host side ------------------------------------------------------------------------------------------
+}  // namespace
+
+// ---- host side (tensor-map builders shared with conv_tc3.cu) -------------------------------------------------
 PFN_cuTensorMapEncodeTiled_v12000 encode_tiled_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
     void* ptr = nullptr;
@@ -448,16 +450,23 @@ CUtensorMap make_tmap_im2col(const ConvParams& p, bool bf16) {
   return m;
 }
 
+namespace {
+
 int g_sm_count = 0;
 int g_im2col = -1;   // -1 unread; B200_IM2COL=0 disables the im2col-mode TMA path (cp.async gather instead)
 
-EpiAct make_epi(int kind, float a, float b) {
-  EpiAct e;
+}  // namespace
+
+tc::EpiAct make_epi(int kind, float a, float b) {
+  tc::EpiAct e;
   e.kind = kind; e.a = a; e.b = b;
   e.lo = kind == ACT_RELU ? 0.f : a;
   e.hi = kind == ACT_RELU ? __builtin_huge_valf() : b;
   return e;
 }
+
+namespace {
+using namespace tc;
 
 template <typename T, int BN>
 void launch_tc2(const ConvParams& p, bool bf16, cudaStream_t s) {

@@ -52,6 +52,14 @@ bool conv_tc2_s2d_encode_ok();                    // the driver accepts the over
 bool conv_tc2_im2col_enabled();                   // B200_IM2COL != 0 and the driver exports cuTensorMapEncodeIm2col   // A tile by im2col-mode TMA (Cin_p % 64 == 0)
 void launch_conv_tc2(const ConvParams& p, int dtype, int bn, cudaStream_t s);
 void conv_tc2_init_device();
+// CTA-pair variant (conv_tc3.cu): tcgen05.mma.cta_group::2 over 256 x {64,128,256} tiles, slab-ring epilogue, weight-stationary and
+// 3x3 "row" modes.  Used for large launches (every SM pair has tiles to walk); B200_TC3=0 disables, =1 forces it wherever supported.
+bool conv_tc3_supported(const ConvParams& p);
+bool conv_tc3_preferred(const ConvParams& p);
+int conv_tc3_pick_bn(const ConvParams& p);
+const char* conv_tc3_mode_name(const ConvParams& p);
+void launch_conv_tc3(const ConvParams& p, int dtype, int bn, cudaStream_t s);
+void conv_tc3_init_device();
 // CUDA-core fp32 path (fp32 mode: 1e-4 parity; also the reference for tcgen05 unit tests).
 // Same parameter block; x/w/res/y are fp32, weights [Cout_alloc][Ktot] fp32.
 void launch_conv_f32(const ConvParams& p, cudaStream_t s);
