@@ -58,22 +58,23 @@ constexpr int NOUT = 2, NRES = 4;        // staging rings, in slabs
 constexpr int SMEM_LIMIT = 232448;
 constexpr int WS_MAX_BYTES = 80 * 1024;  // resident half of the weights, per CTA
 
-enum AMode : int { A_MATRIX = 1, A_IM2COL = 2, A_ROWS = 3 };
+enum AMode : int { A_MATRIX = 1, A_IM2COL = 2, A_ROWS = 3, A_HALO = 4 };
 
 struct Plan3 { int sa, sb; uint32_t a_stage, b_stage, a_off, b_off, out_off, res_off, w_off, bar_off, total; };
 
 template <int BN>
-__host__ __device__ inline Plan3 plan3(bool has_res, int ws_bytes, int a_mode) {
+__host__ __device__ inline Plan3 plan3(bool has_res, int ws_bytes, int a_mode, int rows_p) {
   Plan3 pl;
   pl.a_stage = (uint32_t)(A_BYTES + (a_mode == A_ROWS ? 1024 : 0));   // row mode reads up to 2 pixel rows past the box
+  if (a_mode == A_HALO) pl.a_stage = (uint32_t)((BM + 2 * rows_p) * 128 + 1024);   // R + 2 image rows of P pixels, same overrun
   pl.b_stage = (uint32_t)((BN / 2) * 128);
   const int fixed = NOUT * SLAB_BYTES + (has_res ? NRES * SLAB_BYTES : 0) + ws_bytes + 1024 /*align slack*/ + 1024 /*barriers*/;
   const int budget = SMEM_LIMIT - fixed;
   if (ws_bytes) {
     pl.sb = 0;
     pl.sa = budget / (int)pl.a_stage;
-  } else if (a_mode == A_ROWS) {
-    pl.sa = 3;
+  } else if (a_mode == A_ROWS || a_mode == A_HALO) {
+    pl.sa = a_mode == A_ROWS ? 3 : 2;
     pl.sb = (budget - pl.sa * (int)pl.a_stage) / (int)pl.b_stage;
   } else {
     pl.sa = pl.sb = budget / (int)(pl.a_stage + pl.b_stage);
@@ -141,7 +142,7 @@ struct TilePos { int m0; int img, h0; bool valid; };
 __device__ __forceinline__ TilePos tile_pos(const Tc3Args& a, int tile_m, int rank) {
   TilePos t;
   const int ct = tile_m * 2 + rank;                 // CTA tile index along M
-  if (a.a_mode == A_ROWS) {
+  if (a.a_mode == A_ROWS || a.a_mode == A_HALO) {
     t.img = ct / a.tiles_per_img;
     t.h0 = (ct - t.img * a.tiles_per_img) * a.rows_r;
     t.valid = t.img < a.p.N;
@@ -163,11 +164,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
   const int nkb = p.Ktot / BK;
   const bool ws = args.ws != 0;
   const int a_mode = args.a_mode;
-  const Plan3 plan = plan3<BN>(has_res, ws ? nkb * B_BYTES : 0, a_mode);
+  const Plan3 plan = plan3<BN>(has_res, ws ? nkb * B_BYTES : 0, a_mode, args.rows_p);
   const int SA = plan.sa, SB = plan.sb;
   const int cpt = p.Cin_p >> 6;                               // 64-channel chunks per filter tap
-  const int reuse = a_mode == A_ROWS ? p.kw : 1;              // k-blocks served by one A stage
-  const int n_ablk = a_mode == A_ROWS ? p.kh * cpt : nkb;
+  const int reuse = a_mode == A_ROWS ? p.kw : (a_mode == A_HALO ? p.kh * p.kw : 1);   // k-blocks served by one A stage
+  const int n_ablk = a_mode == A_ROWS ? p.kh * cpt : (a_mode == A_HALO ? cpt : nkb);
+  const uint32_t a_tx = a_mode == A_HALO ? (uint32_t)((BM + 2 * args.rows_p) * 128) : (uint32_t)A_BYTES;   // bytes one CTA's A load delivers
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -259,7 +261,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
         ptx::named_bar_sync(1, NUM_EPI_WARPS * 32);
         if (store_thread) {
           if (tp.valid) {
-            if (a_mode == A_ROWS) ptx::tma_store_3d(&args.tm_y, out_slab, n0 + h * 64, 0, tp.img * p.Ho + tp.h0);
+            if (a_mode == A_ROWS || a_mode == A_HALO) ptx::tma_store_3d(&args.tm_y, out_slab, n0 + h * 64, 0, tp.img * p.Ho + tp.h0);
             else ptx::tma_store_2d(&args.tm_y, out_slab, n0 + h * 64, tp.m0);
           }
           ptx::bulk_commit();
@@ -289,7 +291,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
           const uint32_t a_addr = smem_base + plan.a_off + (uint32_t)sa * plan.a_stage;
           for (int j = 0; j < reuse; ++j) {
             // weight k-block that goes with (A block ab, tap j): K order of the packed weights is (filter row, filter col, channel)
-            const int kb = a_mode == A_ROWS ? ((ab / cpt) * p.kw + j) * cpt + (ab % cpt) : ab;
+            const int kb = a_mode == A_ROWS ? ((ab / cpt) * p.kw + j) * cpt + (ab % cpt) : (a_mode == A_HALO ? j * cpt + ab : ab);
+            // start of the shifted view: one pixel = one 128-byte swizzled row; halo mode also steps whole image rows (P pixels)
+            const uint32_t a_view = a_addr + (a_mode == A_HALO ? (uint32_t)((j / p.kw) * args.rows_p + (j % p.kw)) : (uint32_t)j) * 128u;
             uint32_t b_addr;
             if (ws) {
               b_addr = smem_base + plan.w_off + (uint32_t)kb * B_BYTES;
@@ -300,8 +304,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
             ptx::tc_fence_after();
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              uint64_t da = ptx::make_smem_desc_sw128(a_addr + (uint32_t)j * 128u + k * 32);
-              if (args.desc_base_offset) da |= (uint64_t)(((a_addr + (uint32_t)j * 128u) >> 7) & 7u) << 49;
+              uint64_t da = ptx::make_smem_desc_sw128(a_view + k * 32);
+              if (args.desc_base_offset) da |= (uint64_t)((a_view >> 7) & 7u) << 49;
               const uint64_t db = ptx::make_smem_desc_sw128(b_addr + k * 32);
               ptx::umma_f16_pair(d_tmem, da, db, idesc, first | (uint32_t)k);
             }
@@ -351,13 +355,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
           ptx::mbar_wait(&emptyA[sa], pha ^ 1u);
           const uint32_t a_dst = smem_base + plan.a_off + (uint32_t)sa * plan.a_stage;
           const uint32_t bar = fullA_leader + (uint32_t)sa * 8u;
-          if (leader) ptx::mbar_arrive_expect_tx(&fullA[sa], 2u * A_BYTES);
+          if (leader) ptx::mbar_arrive_expect_tx(&fullA[sa], 2u * a_tx);
           else ptx::mbar_arrive_cluster(bar);
           if (a_mode == A_MATRIX) {
             ptx::tma_load_2d_pair(a_dst, &args.tm_a, bar, ab * BK, tp.m0);
           } else if (a_mode == A_IM2COL) {
             ptx::tma_load_im2col_4d_pair(a_dst, &args.tm_a, bar, chunk * BK, bw, bh, bn, (uint32_t)(fs * p.dw), (uint32_t)(fr * p.dh));
             if (++chunk == cpt) { chunk = 0; if (++fs == p.kw) { fs = 0; ++fr; } }
+          } else if (a_mode == A_HALO) {
+            // all filter rows at once: input rows h0 - pt .. h0 - pt + R + 1 of 64-channel chunk ab
+            ptx::tma_load_4d_pair(a_dst, &args.tm_a, bar, ab * BK, -p.pl, tp.h0 - p.pt, tp.img);
           } else {
             // filter row fr: input rows h0 + fr - pt .., pixels -pl .. P - pl - 1 (out-of-image parts are zero-filled)
             ptx::tma_load_4d_pair(a_dst, &args.tm_a, bar, chunk * BK, -p.pl, tp.h0 + fr - p.pt, tp.img);
@@ -365,7 +372,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
           }
           if (!ws) {
             for (int j = 0; j < reuse; ++j) {
-              const int kb = a_mode == A_ROWS ? ((ab / cpt) * p.kw + j) * cpt + (ab % cpt) : ab;
+              const int kb = a_mode == A_ROWS ? ((ab / cpt) * p.kw + j) * cpt + (ab % cpt) : (a_mode == A_HALO ? j * cpt + ab : ab);
               ptx::mbar_wait(&emptyB[sb], phb ^ 1u);
               const uint32_t barb = fullB_leader + (uint32_t)sb * 8u;
               if (leader) ptx::mbar_arrive_expect_tx(&fullB[sb], 2u * B_BYTES);
@@ -394,7 +401,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
           const uint32_t dst = smem_base + plan.res_off + rslot * SLAB_BYTES;
           if (tp.valid) {
             ptx::mbar_arrive_expect_tx(&rfull[rslot], SLAB_BYTES);
-            if (a_mode == A_ROWS) ptx::tma_load_3d(dst, &args.tm_r, &rfull[rslot], n0 + h * 64, 0, tp.img * p.Ho + tp.h0);
+            if (a_mode == A_ROWS || a_mode == A_HALO) ptx::tma_load_3d(dst, &args.tm_r, &rfull[rslot], n0 + h * 64, 0, tp.img * p.Ho + tp.h0);
             else ptx::tma_load_2d(dst, &args.tm_r, &rfull[rslot], n0 + h * 64, tp.m0);
           } else {
             ptx::mbar_arrive(&rfull[rslot]);                      // rows beyond M: the epilogue reads stale staging and stores nothing
@@ -437,7 +444,9 @@ template <int BN>
 bool ws_applies(const ConvParams& p, int a_mode) {
   const int ws_bytes = (p.Ktot / BK) * (BN / 2) * 128;
   const char* no_ws = getenv("B200_NO_WS");
-  return p.Cout_alloc == BN && ws_bytes <= WS_MAX_BYTES && plan3<BN>(p.res != nullptr, ws_bytes, a_mode).sa >= 4 && !(no_ws && no_ws[0] == '1');
+  const int min_sa = a_mode == A_HALO ? 2 : 4;
+  return p.Cout_alloc == BN && ws_bytes <= WS_MAX_BYTES && plan3<BN>(p.res != nullptr, ws_bytes, a_mode, rows_pitch(p)).sa >= min_sa &&
+         !(no_ws && no_ws[0] == '1');
 }
 
 template <typename T, int BN>
@@ -451,7 +460,7 @@ void launch_tc3(const ConvParams& p, bool bf16, int a_mode, cudaStream_t s) {
   a.n_tiles = p.Cout_alloc / BN;
   a.reverse = p.reverse;
   int cta_tiles_m;
-  if (a_mode == A_ROWS) {
+  if (a_mode == A_ROWS || a_mode == A_HALO) {
     a.rows_p = rows_pitch(p);
     a.rows_r = BM / a.rows_p;
     a.tiles_per_img = (p.Ho + a.rows_r - 1) / a.rows_r;
@@ -463,11 +472,11 @@ void launch_tc3(const ConvParams& p, bool bf16, int a_mode, cudaStream_t s) {
   a.ws = ws_applies<BN>(p, a_mode) ? 1 : 0;
   { const char* e = getenv("B200_TC3_BASEOFF"); a.desc_base_offset = (e && e[0] == '1') ? 1 : 0; }
   a.tm_w = make_tmap_2d(p.w, bf16, (uint64_t)p.Ktot, (uint64_t)p.Cout_alloc, (uint64_t)p.w_ld * 2, BK, BN / 2);
-  if (a_mode == A_ROWS) {
+  if (a_mode == A_ROWS || a_mode == A_HALO) {
     const uint64_t C = (uint64_t)p.Cin_p, pitch = (uint64_t)p.ldy * 2;
     const uint64_t ad[4] = {C, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
     const uint64_t as[3] = {C * 2, (uint64_t)p.W * C * 2, (uint64_t)p.H * p.W * C * 2};
-    const uint32_t ab[4] = {64, (uint32_t)a.rows_p, (uint32_t)a.rows_r, 1};
+    const uint32_t ab[4] = {64, (uint32_t)a.rows_p, (uint32_t)(a.rows_r + (a_mode == A_HALO ? 2 : 0)), 1};
     a.tm_a = make_tmap_tiled(p.x, bf16, 4, ad, as, ab);
     // output / residual: {channels, w, n*h}; rows (w) beyond Wo and image rows beyond Ho of the LAST image are clipped.  A tile never
     // straddles two images because tiles_per_img * R >= Ho rows are walked per image and rows >= Ho ... see the store coordinate:
@@ -484,7 +493,7 @@ void launch_tc3(const ConvParams& p, bool bf16, int a_mode, cudaStream_t s) {
   }
   const int sms = g_sm_count3 > 0 ? g_sm_count3 : 148;
   const int grid = 2 * std::min(a.num_tiles, sms / 2);
-  const unsigned smem = plan3<BN>(p.res != nullptr, a.ws ? (p.Ktot / BK) * (BN / 2) * 128 : 0, a_mode).total;
+  const unsigned smem = plan3<BN>(p.res != nullptr, a.ws ? (p.Ktot / BK) * (BN / 2) * 128 : 0, a_mode, a.rows_p).total;
   if (conv_acts_are_clamps(p)) conv_tc3_kernel<T, BN, false><<<grid, NUM_THREADS, smem, s>>>(a);
   else conv_tc3_kernel<T, BN, true><<<grid, NUM_THREADS, smem, s>>>(a);
 }
@@ -508,7 +517,11 @@ bool conv_tc3_rows_ok(const ConvParams& p) {
 
 int conv_tc3_a_mode(const ConvParams& p) {
   if (conv_tc2_a_is_matrix(p) && p.Cin_p % 64 == 0) return A_MATRIX;
-  if (conv_tc3_rows_ok(p)) return A_ROWS;
+  if (conv_tc3_rows_ok(p)) {
+    const char* e = getenv("B200_TC3_HALO");
+    const bool halo = p.kh == 3 && p.pt == 1 && (e && e[0] == '1');
+    return halo ? A_HALO : A_ROWS;
+  }
   if (conv_tc2_a_is_im2col(p)) return A_IM2COL;
   return 0;
 }
@@ -522,10 +535,10 @@ static double tc3_cost(const ConvParams& p, int bn, int a_mode, int sms) {
   const double fabric = 42.0;                          // B/clk per SM (6.3 KB/clk chip-wide)
   int cta_m;
   double a_scale = 1.0;
-  if (a_mode == A_ROWS) {
+  if (a_mode == A_ROWS || a_mode == A_HALO) {
     int P = 8; while (P < p.W + 2) P <<= 1;
     cta_m = ((p.Ho + BM / P - 1) / (BM / P)) * p.N;
-    a_scale = 1.0 / p.kw;
+    a_scale = a_mode == A_ROWS ? 1.0 / p.kw : (BM / P + 2.0) / (BM / P) / (p.kh * p.kw);
   } else {
     cta_m = (p.M + BM - 1) / BM;
   }
@@ -568,6 +581,7 @@ const char* conv_tc3_mode_name(const ConvParams& p) {
   switch (conv_tc3_a_mode(p)) {
     case A_MATRIX: return "tma";
     case A_ROWS: return "rows";
+    case A_HALO: return "halo";
     case A_IM2COL: return "im2col";
   }
   return "?";

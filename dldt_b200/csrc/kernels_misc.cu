@@ -195,6 +195,53 @@ __global__ void pool_kernel(const PoolParams p) {
   store8<T>(reinterpret_cast<T*>(p.y) + pix * p.Cp + c8 * 8, acc);
 }
 
+
+// Fast path for the ResNet / SSD stem pool: 3x3 / stride-2 MaxPool over 16-bit NHWC8 data.  One thread = two horizontally adjacent output
+// pixels x 8 channels: 15 unconditional 16-byte loads (3 rows x 5 columns, all issued before the first use) instead of 18 guarded ones.
+// Out-of-image taps are clamped to the nearest in-image coordinate, which is always inside the same window (pads <= 1), so the maximum is
+// unchanged (MaxPool ignores padding: reference/max_pool.hpp:74-117); max over packed pairs is exact.
+template <typename T2>
+__device__ __forceinline__ uint4 max8_16b(uint4 a, uint4 b) {
+  uint4 r;
+  T2 x, y, z;
+  x = *reinterpret_cast<T2*>(&a.x); y = *reinterpret_cast<T2*>(&b.x); z = __hmax2(x, y); r.x = *reinterpret_cast<uint32_t*>(&z);
+  x = *reinterpret_cast<T2*>(&a.y); y = *reinterpret_cast<T2*>(&b.y); z = __hmax2(x, y); r.y = *reinterpret_cast<uint32_t*>(&z);
+  x = *reinterpret_cast<T2*>(&a.z); y = *reinterpret_cast<T2*>(&b.z); z = __hmax2(x, y); r.z = *reinterpret_cast<uint32_t*>(&z);
+  x = *reinterpret_cast<T2*>(&a.w); y = *reinterpret_cast<T2*>(&b.w); z = __hmax2(x, y); r.w = *reinterpret_cast<uint32_t*>(&z);
+  return r;
+}
+template <typename T2>
+__global__ void __launch_bounds__(256) maxpool3x3s2_16b_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int cpc, int Ho,
+                                                               int Wo, int pt, int pl, uint32_t total) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int Wo2 = (Wo + 1) >> 1;
+  const uint32_t c8 = idx % (uint32_t)cpc;
+  uint32_t t = idx / (uint32_t)cpc;
+  const int j = (int)(t % (uint32_t)Wo2);
+  t /= (uint32_t)Wo2;
+  const int ho = (int)(t % (uint32_t)Ho);
+  const int n = (int)(t / (uint32_t)Ho);
+  const uint4* xi = x + (size_t)n * H * W * cpc + c8;
+  const int c0 = 4 * j - pl, r0 = 2 * ho - pt;
+  uint4 v[3][5];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int hi = min(max(r0 + r, 0), H - 1);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      const int wi = min(max(c0 + c, 0), W - 1);
+      v[r][c] = __ldg(xi + ((size_t)hi * W + wi) * cpc);
+    }
+  }
+  uint4 col[5];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) col[c] = max8_16b<T2>(max8_16b<T2>(v[0][c], v[1][c]), v[2][c]);
+  uint4* yo = y + (((size_t)n * Ho + ho) * Wo + 2 * j) * cpc + c8;
+  yo[0] = max8_16b<T2>(max8_16b<T2>(col[0], col[1]), col[2]);
+  if (2 * j + 1 < Wo) yo[cpc] = max8_16b<T2>(max8_16b<T2>(col[2], col[3]), col[4]);
+}
+
 template <typename T>
 __global__ void global_avgpool_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int HW, int Cp) {
   const int cpc = Cp >> 3;
@@ -532,6 +579,17 @@ void launch_dwconv(const DwParams& p, int dtype, cudaStream_t s) {
 }
 void launch_pool(const PoolParams& p, int dtype, cudaStream_t s) {
   int64_t total = (int64_t)p.N * p.Ho * p.Wo * (p.Cp / 8);
+  const bool fast = !p.is_avg && (dtype == B200_BF16 || dtype == B200_F16) && p.kh == 3 && p.kw == 3 && p.sh == 2 && p.sw == 2 && p.pt <= 1 && p.pl <= 1 &&
+                    p.pb <= 1 && p.pr <= 1 && (p.Ho - 1) * 2 - p.pt <= p.H - 1 && (p.Wo - 1) * 2 - p.pl <= p.W - 1;
+  const int64_t total2 = (int64_t)p.N * p.Ho * ((p.Wo + 1) / 2) * (p.Cp / 8);
+  if (fast && total2 < (int64_t)1 << 31 && (int64_t)p.N * p.H * p.W * (p.Cp / 8) < (int64_t)1 << 40) {
+    const unsigned grid = grid_for(total2, 256);
+    if (dtype == B200_BF16)
+      maxpool3x3s2_16b_kernel<__nv_bfloat162><<<grid, 256, 0, s>>>((const uint4*)p.x, (uint4*)p.y, p.N, p.H, p.W, p.Cp / 8, p.Ho, p.Wo, p.pt, p.pl, (uint32_t)total2);
+    else
+      maxpool3x3s2_16b_kernel<__half2><<<grid, 256, 0, s>>>((const uint4*)p.x, (uint4*)p.y, p.N, p.H, p.W, p.Cp / 8, p.Ho, p.Wo, p.pt, p.pl, (uint32_t)total2);
+    return;
+  }
   B200_DISPATCH_FLOAT(dtype, T, (pool_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(p)));
 }
 void launch_global_avgpool(const void* x, void* y, int N, int HW, int Cp, int dtype, cudaStream_t s) {
