@@ -1,0 +1,440 @@
+// CTA-pair implicit-GEMM convolution / GEMM kernel on tcgen05 (sm_100a): the device code of conv_tc3 (see conv_tc3.cu for the
+// host side and the design notes).  Included by conv_tc3.cu (bf16 instantiations) and conv_tc3_f16.cu (fp16 instantiations).
+#pragma once
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "act.cuh"
+#include "common.h"
+#include "kernels.h"
+#include "ptx_sm100.cuh"
+#include "tc_common.cuh"
+
+namespace b200 {
+namespace tc3 {
+
+using namespace tc;
+
+constexpr int BM = 128;                  // rows per CTA; the pair tile is 256 rows
+constexpr int BK = 64;
+constexpr int A_BYTES = BM * 128;
+constexpr int SLAB_BYTES = BM * 128;     // one 64-channel slab of the output / residual tile of one CTA
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int MMA_WARP = 8, TMA_WARP = 9, RES_WARP = 10;
+constexpr int NUM_THREADS = 352;
+constexpr int MAX_STAGES = 8;
+constexpr int NOUT = 2, NRES = 4;        // staging rings, in slabs
+constexpr int SMEM_LIMIT = 232448;
+constexpr int WS_MAX_BYTES = 80 * 1024;  // resident half of the weights, per CTA
+
+enum AMode : int { A_MATRIX = 1, A_IM2COL = 2, A_HALO = 4 };
+
+struct Plan3 { int sa, sb; uint32_t a_stage, b_stage, a_off, b_off, out_off, res_off, w_off, bar_off, total; };
+
+// Shared-memory plan.  rows_p = pixel pitch P of the halo box (A_HALO only).
+__host__ __device__ inline Plan3 plan3(int bn, bool has_res, int ws_bytes, int a_mode, int rows_p) {
+  Plan3 pl;
+  pl.a_stage = (uint32_t)A_BYTES;
+  if (a_mode == A_HALO) pl.a_stage = (uint32_t)((BM + 2 * rows_p) * 128 + 1024);   // R + 2 image rows of P pixels; the last taps read 2 rows past
+  pl.b_stage = (uint32_t)((bn / 2) * 128);
+  const int fixed = NOUT * SLAB_BYTES + (has_res ? NRES * SLAB_BYTES : 0) + ws_bytes + 1024 /*align slack*/ + 1024 /*barriers*/;
+  const int budget = SMEM_LIMIT - fixed;
+  if (ws_bytes) {
+    pl.sb = 0;
+    pl.sa = budget / (int)pl.a_stage;
+  } else if (a_mode == A_HALO) {
+    // one A stage feeds nine k-blocks: the weights are the stream, the activations need depth only to hide one TMA latency
+    pl.sb = bn == 256 ? 4 : 6;
+    pl.sa = (budget - pl.sb * (int)pl.b_stage) / (int)pl.a_stage;
+    if (pl.sa > 4) { pl.sa = 4; pl.sb = (budget - pl.sa * (int)pl.a_stage) / (int)pl.b_stage; }
+  } else {
+    pl.sa = pl.sb = budget / (int)(pl.a_stage + pl.b_stage);
+  }
+  if (pl.sa > MAX_STAGES) pl.sa = MAX_STAGES;
+  if (pl.sb > MAX_STAGES) pl.sb = MAX_STAGES;
+  pl.a_off = 0;
+  pl.b_off = pl.a_off + (uint32_t)pl.sa * pl.a_stage;
+  pl.out_off = pl.b_off + (uint32_t)pl.sb * pl.b_stage;
+  pl.res_off = pl.out_off + NOUT * SLAB_BYTES;
+  pl.w_off = pl.res_off + (has_res ? NRES * SLAB_BYTES : 0);
+  pl.bar_off = pl.w_off + (uint32_t)ws_bytes;
+  pl.total = pl.bar_off + 1024u + 1024u;
+  return pl;
+}
+
+struct Tc3Args {
+  CUtensorMap tm_a;   // A_MATRIX: [M][Cin_p]; A_IM2COL: {C, W, H, N} im2col; A_HALO: {C, W, H, N} tiled, box {64, P, 128/P + 2, 1}
+  CUtensorMap tm_w;   // packed weights [Cout_alloc][Ktot], box {64, BN/2}
+  CUtensorMap tm_y;   // output: [M][Cout_p] box {64, 128}; A_HALO: {C, W, N*H} box {64, P, 128/P}
+  CUtensorMap tm_r;   // residual, same geometry as the output
+  ConvParams p;
+  EpiAct e1, e2;
+  int gen;                  // activations outside the clamp family: generic table in the epilogue (selects the GEN instantiation)
+  int num_tiles, n_tiles;   // pair tiles
+  int reverse;
+  int rows_p, rows_r;       // A_HALO: pixel pitch P and image rows per CTA tile R = 128 / P
+  int tiles_per_img;        // A_HALO: CTA tiles per image = Ho / R
+};
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+template <typename T, bool GEN>
+__device__ __forceinline__ void epilogue_chunk(uint32_t taddr, const float* __restrict__ bias, uint32_t out_row, uint32_t res_row, uint32_t rsw,
+                                               int chunk0, bool has_res, const EpiAct& e1, const EpiAct& e2) {
+  uint32_t v[32];
+  ptx::tmem_ld_32x32(taddr, v);
+  ptx::tmem_ld_wait();
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + g * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + g * 8 + 4));
+    float f[8];
+    f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+    f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+    f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+    f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+    epi_act8<GEN>(f, e1);
+    const uint32_t sw = (rsw ^ (uint32_t)(chunk0 + g)) << 4;      // 16-byte chunk index XOR (row & 7)
+    if (has_res) {
+      const uint4 rv = ptx::ld_shared_v4(res_row + sw);
+      float r[8];
+      unpack2<T>(rv.x, r[0], r[1]); unpack2<T>(rv.y, r[2], r[3]);
+      unpack2<T>(rv.z, r[4], r[5]); unpack2<T>(rv.w, r[6], r[7]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] += r[e];
+      epi_act8<GEN>(f, e2);
+    }
+    ptx::st_shared_v4(out_row + sw, make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7])));
+  }
+}
+
+// first output row of CTA `rank` of pair tile `tile_m`, and (halo mode) its image / first image row
+struct TilePos { int m0; int img, h0; bool valid; };
+template <int AMODE>
+__device__ __forceinline__ TilePos tile_pos(const Tc3Args& a, int tile_m, int rank) {
+  TilePos t;
+  const int ct = tile_m * 2 + rank;                 // CTA tile index along M
+  if (AMODE == A_HALO) {
+    t.img = ct / a.tiles_per_img;
+    t.h0 = (ct - t.img * a.tiles_per_img) * a.rows_r;
+    t.valid = t.img < a.p.N;
+    t.m0 = 0;
+  } else {
+    t.m0 = ct * BM;
+    t.valid = t.m0 < a.p.M;
+    t.img = 0; t.h0 = 0;
+  }
+  return t;
+}
+
+// The two single-issuer loops (MMA, operand TMA) run with the whole warp converged and only the instruction that must be issued once
+// behind elect.sync: a loop executed by one diverged lane cannot use the uniform datapath, and the first version of this kernel spent
+// ~1500 cycles of scalar bookkeeping per k-block in the MMA issuer against 512 cycles of tensor work (profiles/r1_call_e).
+template <typename T, int BN, int AMODE, bool WS, bool GEN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv_tc3_kernel(const __grid_constant__ Tc3Args args) {
+  constexpr int B_BYTES = (BN / 2) * 128;     // this CTA's half of a weight k-block
+  constexpr int REUSE = AMODE == A_HALO ? 9 : 1;   // k-blocks served by one A stage (halo: the nine taps of a 3x3)
+  const ConvParams& p = args.p;
+  const bool has_res = p.res != nullptr;
+  const int nkb = p.Ktot / BK;
+  const Plan3 plan = plan3(BN, has_res, WS ? nkb * B_BYTES : 0, AMODE, args.rows_p);
+  const int SA = plan.sa, SB = plan.sb;
+  const int cpt = p.Cin_p >> 6;                               // 64-channel chunks per filter tap
+  const int n_ablk = AMODE == A_HALO ? cpt : nkb;
+  const uint32_t a_tx = AMODE == A_HALO ? (uint32_t)((BM + 2 * args.rows_p) * 128) : (uint32_t)A_BYTES;   // bytes one CTA's A load delivers
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(smem_al + plan.bar_off);
+  uint64_t* emptyA = fullA + MAX_STAGES;
+  uint64_t* fullB = emptyA + MAX_STAGES;
+  uint64_t* emptyB = fullB + MAX_STAGES;
+  uint64_t* tfull = emptyB + MAX_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* rfull = tempty + 2;
+  uint64_t* rempty = rfull + NRES;
+  uint64_t* wfull = rempty + NRES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_tiles = args.num_tiles, n_tiles = args.n_tiles;
+  const int cluster = (int)ptx::cluster_id_x(), nclusters = (int)ptx::num_clusters_x();
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      // full*: ONE arrival, the leader's arrive.expect_tx for the bytes of BOTH CTAs.  The peer only issues its TMA (complete_tx on the
+      // leader's barrier); a remote mbarrier.arrive per stage costs the peer's producer a ~1200-cycle cluster round trip (profiles/r1_call_b).
+      ptx::mbar_init(&fullA[s], 1);
+      ptx::mbar_init(&emptyA[s], 1);
+      ptx::mbar_init(&fullB[s], 1);
+      ptx::mbar_init(&emptyB[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull[a], 1);
+      ptx::mbar_init(&tempty[a], 2);     // one arrival per CTA (after its eight epilogue warps have drained the accumulator)
+    }
+    for (int r = 0; r < NRES; ++r) {
+      ptx::mbar_init(&rfull[r], 1);
+      ptx::mbar_init(&rempty[r], NUM_EPI_WARPS);
+    }
+    ptx::mbar_init(wfull, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == TMA_WARP && lane == 0) {
+    ptx::tma_prefetch_desc(&args.tm_w);
+    ptx::tma_prefetch_desc(&args.tm_a);
+    ptx::tma_prefetch_desc(&args.tm_y);
+    if (has_res) ptx::tma_prefetch_desc(&args.tm_r);
+  }
+  if (warp == MMA_WARP) {
+    ptx::tmem_alloc_pair(tmem_slot, 2 * BN);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();                   // barriers of both CTAs are initialised before any remote arrive / TMA signal
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < NUM_EPI_WARPS) {
+    // ===================== epilogue: this CTA's 128 rows, one 64-channel slab at a time =====================
+    const int q = warp & 3;
+    const int half = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t rsw = (uint32_t)(row & 7);
+    const bool store_thread = threadIdx.x == 0;
+    const uint32_t tempty_leader0 = ptx::mapa(ptx::smem_u32(&tempty[0]), 0), tempty_leader1 = ptx::mapa(ptx::smem_u32(&tempty[1]), 0);
+    uint32_t it = 0, g = 0;                // tiles / slabs processed so far
+    for (int t_ = cluster; t_ < num_tiles; t_ += nclusters, ++it) {
+      const int tile = args.reverse ? num_tiles - 1 - t_ : t_;
+      const TilePos tp = tile_pos<AMODE>(args, tile / n_tiles, (int)rank);
+      const int n0 = (tile % n_tiles) * BN;
+      const int ncols = min(BN, p.Cout_p - n0);
+      const int nslab = (ncols + 63) >> 6;
+      const uint32_t acc = it & 1u;
+      ptx::mbar_wait(&tfull[acc], (it >> 1) & 1u);
+      ptx::tc_fence_after();
+      for (int h = 0; h < nslab; ++h, ++g) {
+        const uint32_t oslot = g % NOUT, rslot = g % NRES;
+        const uint32_t out_slab = smem_base + plan.out_off + oslot * SLAB_BYTES;
+        const uint32_t out_row = out_slab + (uint32_t)row * 128u;
+        const uint32_t res_row = smem_base + plan.res_off + rslot * SLAB_BYTES + (uint32_t)row * 128u;
+        if (has_res) ptx::mbar_wait(&rfull[rslot], (g / NRES) & 1u);
+        if (store_thread) ptx::bulk_wait_read<NOUT - 1>();        // the store that last used this output slab has finished reading it
+        ptx::named_bar_sync(1, NUM_EPI_WARPS * 32);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(h * 64 + half * 32);
+        epilogue_chunk<T, GEN>(taddr, p.bias + n0 + h * 64 + half * 32, out_row, res_row, rsw, half * 4, has_res, args.e1, args.e2);
+        if (has_res) {
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&rempty[rslot]);
+        }
+        ptx::fence_proxy_async();                                 // staging writes -> visible to the TMA engine
+        ptx::tc_fence_before();                                   // this warp's TMEM reads of the slab are complete (tmem_ld_wait above)
+        ptx::named_bar_sync(1, NUM_EPI_WARPS * 32);
+        if (h == nslab - 1 && threadIdx.x == 32) {                // accumulator drained by all eight warps: one arrival per CTA
+          ptx::tc_fence_after();
+          if (leader) ptx::mbar_arrive(&tempty[acc]);
+          else ptx::mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+        }
+        if (store_thread) {
+          if (tp.valid) {
+            if (AMODE == A_HALO) ptx::tma_store_3d(&args.tm_y, out_slab, n0 + h * 64, 0, tp.img * p.Ho + tp.h0);
+            else ptx::tma_store_2d(&args.tm_y, out_slab, n0 + h * 64, tp.m0);
+          }
+          ptx::bulk_commit();
+        }
+      }
+    }
+    if (store_thread) ptx::bulk_wait_all0();
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issuer (leader CTA; whole warp walks the loop, one elected lane issues) =====================
+    if (leader) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(TcType<T>::is_bf16, 2 * BM, BN);
+      // descriptor = DESC_HI | (address >> 4): version 1, SWIZZLE_128B, SBO 1024 B, LBO 16 B (ptx_sm100.cuh make_smem_desc_sw128)
+      constexpr uint64_t DESC_HI = ((uint64_t)2 << 61) | ((uint64_t)1 << 46) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 16);
+      const uint32_t a_lo0 = ((smem_base + plan.a_off) & 0x3FFFFu) >> 4, a_step = plan.a_stage >> 4;
+      const uint32_t b_lo0 = ((smem_base + (WS ? plan.w_off : plan.b_off)) & 0x3FFFFu) >> 4;
+      constexpr uint32_t b_step = B_BYTES >> 4;
+      const uint32_t P8 = (uint32_t)args.rows_p * 8u;             // one image row of the halo box, in 16-byte units
+      uint32_t it = 0;
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      if (WS) ptx::mbar_wait(wfull, 0);
+      for (int t_ = cluster; t_ < num_tiles; t_ += nclusters, ++it) {
+        const uint32_t acc = it & 1u;
+        ptx::mbar_wait(&tempty[acc], ((it >> 1) & 1u) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t accum = 0;
+        for (int ab = 0; ab < n_ablk; ++ab) {
+          ptx::mbar_wait(&fullA[sa], pha);
+          const uint32_t a_lo = a_lo0 + (uint32_t)sa * a_step;
+#pragma unroll
+          for (int j = 0; j < REUSE; ++j) {
+            // halo mode: tap (j / 3, j % 3) reads the box shifted by whole image rows and pixels (one pixel = one 128-byte swizzled row);
+            // its weight k-block is (tap, chunk ab): K order of the packed weights is (filter row, filter col, channel)
+            const uint32_t a_view = AMODE == A_HALO ? a_lo + (uint32_t)(j / 3) * P8 + (uint32_t)(j % 3) * 8u : a_lo;
+            uint32_t b_lo;
+            if (WS) {
+              b_lo = b_lo0 + (uint32_t)(AMODE == A_HALO ? j * cpt + ab : ab) * b_step;
+            } else {
+              ptx::mbar_wait(&fullB[sb], phb);
+              b_lo = b_lo0 + (uint32_t)sb * b_step;
+            }
+            ptx::tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                ptx::umma_f16_pair(d_tmem, DESC_HI | (uint64_t)(a_view + 2u * k), DESC_HI | (uint64_t)(b_lo + 2u * k), idesc, accum | (uint32_t)k);
+              if (!WS) ptx::umma_commit_pair(&emptyB[sb], 3);
+            }
+            __syncwarp();
+            accum = 1;
+            if (!WS) { if (++sb == SB) { sb = 0; phb ^= 1u; } }
+          }
+          if (elect_one()) ptx::umma_commit_pair(&emptyA[sa], 3);
+          __syncwarp();
+          if (++sa == SA) { sa = 0; pha ^= 1u; }
+        }
+        if (elect_one()) ptx::umma_commit_pair(&tfull[acc], 3);
+        __syncwarp();
+      }
+    }
+  } else if (warp == TMA_WARP) {
+    // ===================== operand TMA issuer (one warp per CTA, one elected lane issues) =====================
+    const uint32_t fullA_leader = ptx::smem_u32(&fullA[0]) & ptx::PEER_BIT_MASK;
+    const uint32_t fullB_leader = ptx::smem_u32(&fullB[0]) & ptx::PEER_BIT_MASK;
+    const uint32_t wfull_leader = ptx::smem_u32(wfull) & ptx::PEER_BIT_MASK;
+    const int HoWo = p.Ho * p.Wo;
+    if (WS) {   // this CTA's half of the whole weight matrix, once
+      if (lane == 0) {
+        if (leader) ptx::mbar_arrive_expect_tx(wfull, 2u * (uint32_t)nkb * B_BYTES);
+        for (int kb = 0; kb < nkb; ++kb)
+          ptx::tma_load_2d_pair(smem_base + plan.w_off + (uint32_t)kb * B_BYTES, &args.tm_w, wfull_leader, kb * BK, (int)rank * (BN / 2));
+      }
+      __syncwarp();
+    }
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0;
+    for (int t_ = cluster; t_ < num_tiles; t_ += nclusters) {
+      const int tile = args.reverse ? num_tiles - 1 - t_ : t_;
+      const int tile_m = tile / n_tiles;
+      TilePos tp = tile_pos<AMODE>(args, tile_m, (int)rank);
+      if (!tp.valid) tp = tile_pos<AMODE>(args, tile_m, 0);            // tail: stage the leader's rows again (never stored)
+      const int n0 = (tile - tile_m * n_tiles) * BN + (int)rank * (BN / 2);
+      int bn = 0, bh = 0, bw = 0;
+      if (AMODE == A_IM2COL) {
+        bn = tp.m0 / HoWo;
+        const int rem = tp.m0 - bn * HoWo;
+        const int ho = rem / p.Wo;
+        bh = ho * p.sh - p.pt;
+        bw = (rem - ho * p.Wo) * p.sw - p.pl;
+      }
+      int chunk = 0, fr = 0, fs = 0;
+      for (int ab = 0; ab < n_ablk; ++ab) {
+        ptx::mbar_wait(&emptyA[sa], pha ^ 1u);
+        if (elect_one()) {
+          const uint32_t a_dst = smem_base + plan.a_off + (uint32_t)sa * plan.a_stage;
+          const uint32_t bar = fullA_leader + (uint32_t)sa * 8u;
+          if (leader) ptx::mbar_arrive_expect_tx(&fullA[sa], 2u * a_tx);
+          if (AMODE == A_MATRIX) {
+            ptx::tma_load_2d_pair(a_dst, &args.tm_a, bar, ab * BK, tp.m0);
+          } else if (AMODE == A_IM2COL) {
+            ptx::tma_load_im2col_4d_pair(a_dst, &args.tm_a, bar, chunk * BK, bw, bh, bn, (uint32_t)(fs * p.dw), (uint32_t)(fr * p.dh));
+          } else {
+            // all filter rows at once: input rows h0 - pt .. h0 - pt + R + 1, pixels -pl .. P - pl - 1 of 64-channel chunk ab
+            ptx::tma_load_4d_pair(a_dst, &args.tm_a, bar, ab * BK, -p.pl, tp.h0 - p.pt, tp.img);
+          }
+        }
+        __syncwarp();
+        if (AMODE == A_IM2COL) { if (++chunk == cpt) { chunk = 0; if (++fs == p.kw) { fs = 0; ++fr; } } }
+        if (!WS) {
+#pragma unroll 1
+          for (int j = 0; j < REUSE; ++j) {
+            const int kb = AMODE == A_HALO ? j * cpt + ab : ab;
+            ptx::mbar_wait(&emptyB[sb], phb ^ 1u);
+            if (elect_one()) {
+              const uint32_t barb = fullB_leader + (uint32_t)sb * 8u;
+              if (leader) ptx::mbar_arrive_expect_tx(&fullB[sb], 2u * B_BYTES);
+              ptx::tma_load_2d_pair(smem_base + plan.b_off + (uint32_t)sb * plan.b_stage, &args.tm_w, barb, kb * BK, n0);
+            }
+            __syncwarp();
+            if (++sb == SB) { sb = 0; phb ^= 1u; }
+          }
+        }
+        if (++sa == SA) { sa = 0; pha ^= 1u; }
+      }
+    }
+  } else if (warp == RES_WARP) {
+    // ===================== residual TMA issuer: one slab ahead of the epilogue, ring of NRES =====================
+    if (has_res && lane == 0) {
+      uint32_t g = 0;
+      for (int t_ = cluster; t_ < num_tiles; t_ += nclusters) {
+        const int tile = args.reverse ? num_tiles - 1 - t_ : t_;
+        const TilePos tp = tile_pos<AMODE>(args, tile / n_tiles, (int)rank);
+        const int n0 = (tile % n_tiles) * BN;
+        const int ncols = min(BN, p.Cout_p - n0);
+        const int nslab = (ncols + 63) >> 6;
+        for (int h = 0; h < nslab; ++h, ++g) {
+          const uint32_t rslot = g % NRES;
+          ptx::mbar_wait(&rempty[rslot], ((g / NRES) & 1u) ^ 1u);
+          const uint32_t dst = smem_base + plan.res_off + rslot * SLAB_BYTES;
+          if (tp.valid) {
+            ptx::mbar_arrive_expect_tx(&rfull[rslot], SLAB_BYTES);
+            if (AMODE == A_HALO) ptx::tma_load_3d(dst, &args.tm_r, &rfull[rslot], n0 + h * 64, 0, tp.img * p.Ho + tp.h0);
+            else ptx::tma_load_2d(dst, &args.tm_r, &rfull[rslot], n0 + h * 64, tp.m0);
+          } else {
+            ptx::mbar_arrive(&rfull[rslot]);                      // rows beyond M: the epilogue reads stale staging and stores nothing
+          }
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  ptx::tc_fence_before();
+  ptx::cluster_sync();        // neither CTA may exit (or free TMEM) while the other can still touch its shared memory / barriers
+  if (warp == MMA_WARP) ptx::tmem_dealloc_pair(tmem_base, 2 * BN);
+}
+
+// ---- launch (one instantiation set per element type; defined in conv_tc3.cu / conv_tc3_f16.cu) ---------------------------------
+template <typename T>
+void launch_tc3_typed(const Tc3Args& a, int bn, int a_mode, bool ws, int grid, unsigned smem, cudaStream_t s);
+template <typename T>
+void opt_in_tc3_typed();
+
+#define B200_TC3_FOR_EACH(T, X) \
+  X(T, 64, A_MATRIX, false) X(T, 64, A_MATRIX, true) X(T, 64, A_IM2COL, false) X(T, 64, A_IM2COL, true) X(T, 64, A_HALO, false) X(T, 64, A_HALO, true) \
+  X(T, 128, A_MATRIX, false) X(T, 128, A_MATRIX, true) X(T, 128, A_IM2COL, false) X(T, 128, A_IM2COL, true) X(T, 128, A_HALO, false) X(T, 128, A_HALO, true) \
+  X(T, 256, A_MATRIX, false) X(T, 256, A_MATRIX, true) X(T, 256, A_IM2COL, false) X(T, 256, A_IM2COL, true) X(T, 256, A_HALO, false) X(T, 256, A_HALO, true)
+
+#define B200_TC3_DEFINE_TYPED(T)                                                                                                          \
+  template <> void launch_tc3_typed<T>(const Tc3Args& a, int bn, int a_mode, bool ws, int grid, unsigned smem, cudaStream_t s) {           \
+    bool done = false;                                                                                                                     \
+    B200_TC3_FOR_EACH(T, B200_TC3_LAUNCH_CASE)                                                                                             \
+    B200_CHECK(done, B200_ERR_UNSUPPORTED, "conv_tc3: no kernel for bn " << bn << " mode " << a_mode);                                     \
+  }                                                                                                                                        \
+  template <> void opt_in_tc3_typed<T>() { B200_TC3_FOR_EACH(T, B200_TC3_OPTIN_CASE) }
+#define B200_TC3_LAUNCH_CASE(T, BN_, MODE_, WS_)                                                          \
+  if (!done && bn == BN_ && a_mode == MODE_ && ws == WS_) {                                               \
+    if (a.gen) conv_tc3_kernel<T, BN_, MODE_, WS_, true><<<grid, NUM_THREADS, smem, s>>>(a);              \
+    else conv_tc3_kernel<T, BN_, MODE_, WS_, false><<<grid, NUM_THREADS, smem, s>>>(a);                   \
+    done = true;                                                                                          \
+  }
+#define B200_TC3_OPTIN_CASE(T, BN_, MODE_, WS_)                                                                                 \
+  cudaFuncSetAttribute(conv_tc3_kernel<T, BN_, MODE_, WS_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);     \
+  cudaFuncSetAttribute(conv_tc3_kernel<T, BN_, MODE_, WS_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+
+}  // namespace tc3
+}  // namespace b200

@@ -1,0 +1,12 @@
+#!/usr/bin/env bash
+# GPU call B: pair-kernel grid fix A/B + ncu full capture of pair-kernel launches 15..30 of one ResNet-50 b256 pass
+TAG=${1:-b}
+mkdir -p gpurun_out
+B200_TC3_DEBUG=1 timeout 1200 python tools/gpu_r50_ab.py "B200_TC3=0" "" "B200_TC3_HALO=1" > gpurun_out/${TAG}_ab.log 2>&1
+grep -E "^\[|=====|exit|TIMEOUT|co-resident" gpurun_out/${TAG}_ab.log
+B200_TC3_HALO=1 timeout 900 ncu --set full --import-source on --clock-control none -k regex:conv_tc3 -s 15 -c 16 -o gpurun_out/${TAG}_prof \
+    python tools/gpu_r50_ab.py --one ncu > gpurun_out/${TAG}_ncu.log 2>&1
+tail -3 gpurun_out/${TAG}_ncu.log
+ncu -i gpurun_out/${TAG}_prof.ncu-rep --page raw --csv > gpurun_out/${TAG}_prof_raw.csv 2>/dev/null
+rm -f gpurun_out/ab_ncu.npy
+ls -la gpurun_out

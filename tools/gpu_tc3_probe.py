@@ -14,19 +14,14 @@ CASES = {
     "mat_swish_fp16":      (2, 64, 16, 16, 192, 1, 1, 0, False, "swish", "FP16", {}),
     "im2col_s2":           (2, 128, 30, 30, 256, 3, 2, 1, False, "relu", "BF16", {}),
     "im2col_3x3_7x7":      (5, 512, 7, 7, 512, 3, 1, 1, False, "relu", "BF16", {}),
-    "im2col_norows_56":    (2, 64, 56, 56, 64, 3, 1, 1, False, "relu", "BF16", {"B200_TC3_ROWS": "0"}),
-    "rows_56_ws":          (2, 64, 56, 56, 64, 3, 1, 1, False, "relu", "BF16", {}),
-    "rows_56_ws_baseoff":  (2, 64, 56, 56, 64, 3, 1, 1, False, "relu", "BF16", {"B200_TC3_BASEOFF": "1"}),
-    "rows_28":             (3, 128, 28, 28, 128, 3, 1, 1, False, "relu", "BF16", {}),
-    "rows_28_baseoff":     (3, 128, 28, 28, 128, 3, 1, 1, False, "relu", "BF16", {"B200_TC3_BASEOFF": "1"}),
-    "rows_28_res_nows":    (3, 128, 28, 28, 128, 3, 1, 1, True, "relu", "BF16", {"B200_NO_WS": "1"}),
-    "rows_56_c128_o256":   (1, 128, 56, 56, 256, 3, 1, 1, False, "relu", "BF16", {}),
-    "halo_56_ws":          (2, 64, 56, 56, 64, 3, 1, 1, False, "relu", "BF16", {"B200_TC3_HALO": "1"}),
-    "halo_56_ws_baseoff":  (2, 64, 56, 56, 64, 3, 1, 1, False, "relu", "BF16", {"B200_TC3_HALO": "1", "B200_TC3_BASEOFF": "1"}),
-    "halo_28":             (3, 128, 28, 28, 128, 3, 1, 1, False, "relu", "BF16", {"B200_TC3_HALO": "1"}),
-    "halo_28_baseoff":     (3, 128, 28, 28, 128, 3, 1, 1, False, "relu", "BF16", {"B200_TC3_HALO": "1", "B200_TC3_BASEOFF": "1"}),
-    "halo_14_c256":        (5, 256, 14, 14, 256, 3, 1, 1, False, "relu", "BF16", {"B200_TC3_HALO": "1"}),
-    "halo_28_res_fp16":    (3, 128, 28, 28, 128, 3, 1, 1, True, "relu", "FP16", {"B200_TC3_HALO": "1"}),
+    "im2col_norows_56":    (2, 64, 56, 56, 64, 3, 1, 1, False, "relu", "BF16", {"B200_TC3_HALO": "0"}),
+    "halo_56_c128_o256":   (1, 128, 56, 56, 256, 3, 1, 1, False, "relu", "BF16", {}),
+    "halo_28_res_nows":    (3, 128, 28, 28, 128, 3, 1, 1, True, "relu", "BF16", {"B200_NO_WS": "1"}),
+    "halo_14_c256_b16":    (16, 256, 14, 14, 256, 3, 1, 1, False, "relu", "BF16", {}),
+    "halo_56_ws":          (2, 64, 56, 56, 64, 3, 1, 1, False, "relu", "BF16", {}),
+    "halo_28":             (3, 128, 28, 28, 128, 3, 1, 1, False, "relu", "BF16", {}),
+    "halo_14_c256":        (5, 256, 14, 14, 256, 3, 1, 1, False, "relu", "BF16", {}),
+    "halo_28_res_fp16":    (3, 128, 28, 28, 128, 3, 1, 1, True, "relu", "FP16", {}),
 }
 
 
