@@ -30,10 +30,11 @@ constexpr int MAX_STAGES = 8;
 constexpr int NOUT = 2, NRES = 4;        // staging rings, in slabs
 constexpr int SMEM_LIMIT = 232448;
 constexpr int WS_MAX_BYTES = 80 * 1024;  // resident half of the weights, per CTA
+constexpr int BIAS_SMEM_FLOATS = 2048;   // bias vector staged in shared memory when Cout_alloc fits (else read through L1 per use)
 
 enum AMode : int { A_MATRIX = 1, A_IM2COL = 2, A_HALO = 4 };
 
-struct Plan3 { int sa, sb; uint32_t a_stage, b_stage, a_off, b_off, out_off, res_off, w_off, bar_off, total; };
+struct Plan3 { int sa, sb; uint32_t a_stage, b_stage, a_off, b_off, out_off, res_off, w_off, bias_off, bar_off, total; };
 
 // Shared-memory plan.  rows_p = pixel pitch P of the halo box (A_HALO only).
 __host__ __device__ inline Plan3 plan3(int bn, bool has_res, int ws_bytes, int a_mode, int rows_p) {
@@ -41,7 +42,7 @@ __host__ __device__ inline Plan3 plan3(int bn, bool has_res, int ws_bytes, int a
   pl.a_stage = (uint32_t)A_BYTES;
   if (a_mode == A_HALO) pl.a_stage = (uint32_t)((BM + 2 * rows_p) * 128 + 1024);   // R + 2 image rows of P pixels; the last taps read 2 rows past
   pl.b_stage = (uint32_t)((bn / 2) * 128);
-  const int fixed = NOUT * SLAB_BYTES + (has_res ? NRES * SLAB_BYTES : 0) + ws_bytes + 1024 /*align slack*/ + 1024 /*barriers*/;
+  const int fixed = NOUT * SLAB_BYTES + (has_res ? NRES * SLAB_BYTES : 0) + ws_bytes + BIAS_SMEM_FLOATS * 4 + 1024 /*align slack*/ + 1024 /*barriers*/;
   const int budget = SMEM_LIMIT - fixed;
   if (ws_bytes) {
     pl.sb = 0;
@@ -61,7 +62,8 @@ __host__ __device__ inline Plan3 plan3(int bn, bool has_res, int ws_bytes, int a
   pl.out_off = pl.b_off + (uint32_t)pl.sb * pl.b_stage;
   pl.res_off = pl.out_off + NOUT * SLAB_BYTES;
   pl.w_off = pl.res_off + (has_res ? NRES * SLAB_BYTES : 0);
-  pl.bar_off = pl.w_off + (uint32_t)ws_bytes;
+  pl.bias_off = pl.w_off + (uint32_t)ws_bytes;
+  pl.bar_off = pl.bias_off + BIAS_SMEM_FLOATS * 4;
   pl.total = pl.bar_off + 1024u + 1024u;
   return pl;
 }
@@ -87,15 +89,12 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 template <typename T, bool GEN>
-__device__ __forceinline__ void epilogue_chunk(uint32_t taddr, const float* __restrict__ bias, uint32_t out_row, uint32_t res_row, uint32_t rsw,
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const float* __restrict__ bias, uint32_t out_row, uint32_t res_row, uint32_t rsw,
                                                int chunk0, bool has_res, const EpiAct& e1, const EpiAct& e2) {
-  uint32_t v[32];
-  ptx::tmem_ld_32x32(taddr, v);
-  ptx::tmem_ld_wait();
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + g * 8));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + g * 8 + 4));
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + g * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias + g * 8 + 4);
     float f[8];
     f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
     f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
@@ -183,11 +182,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull[a], 1);
-      ptx::mbar_init(&tempty[a], 2);     // one arrival per CTA (after its eight epilogue warps have drained the accumulator)
+      // accumulator drained: the eight local epilogue warps; in the leader also the peer's forwarder (the peer's otherwise idle MMA warp
+      // waits for ITS eight warps on its local copy and does the one remote arrive, so no epilogue warp pays the cluster round trip)
+      ptx::mbar_init(&tempty[a], leader ? NUM_EPI_WARPS + 1 : NUM_EPI_WARPS);
     }
     for (int r = 0; r < NRES; ++r) {
       ptx::mbar_init(&rfull[r], 1);
-      ptx::mbar_init(&rempty[r], NUM_EPI_WARPS);
+      ptx::mbar_init(&rempty[r], NUM_EPI_WARPS / 2);   // the four warps of the group that consumed the slab
     }
     ptx::mbar_init(wfull, 1);
     ptx::fence_mbar_init();
@@ -209,13 +210,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
 
   if (warp < NUM_EPI_WARPS) {
     // ===================== epilogue: this CTA's 128 rows, one 64-channel slab at a time =====================
+    // Two groups of four warps (one warp per TMEM lane quarter) take alternate slabs, each with its own staging slab and its own
+    // 128-thread named barrier: two slabs are in flight at any time, which is what hides the TMEM -> registers -> staging -> TMA store
+    // latency chain of ~2300 cycles per slab that bounded every layer with few k-blocks per tile (profiles/r1_call_h).
+    const int grp = warp >> 2;
     const int q = warp & 3;
-    const int half = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t rsw = (uint32_t)(row & 7);
-    const bool store_thread = threadIdx.x == 0;
-    const uint32_t tempty_leader0 = ptx::mapa(ptx::smem_u32(&tempty[0]), 0), tempty_leader1 = ptx::mapa(ptx::smem_u32(&tempty[1]), 0);
-    uint32_t it = 0, g = 0;                // tiles / slabs processed so far
+    const bool store_thread = (threadIdx.x & 127) == 0;
+    const uint32_t out_slab = smem_base + plan.out_off + (uint32_t)grp * SLAB_BYTES;
+    const uint32_t out_row = out_slab + (uint32_t)row * 128u;
+    // bias vector -> shared memory (all 256 epilogue threads), else straight from global
+    const bool bias_smem = p.Cout_alloc <= BIAS_SMEM_FLOATS;
+    float* s_bias = reinterpret_cast<float*>(smem_al + plan.bias_off);
+    if (bias_smem) {
+      for (int i = threadIdx.x; i < p.Cout_alloc; i += NUM_EPI_WARPS * 32) s_bias[i] = __ldg(p.bias + i);
+      ptx::named_bar_sync(3, NUM_EPI_WARPS * 32);
+    }
+    const float* bias_base = bias_smem ? s_bias : p.bias;
+    uint32_t it = 0, g = 0;                // tiles / slabs processed so far (all slabs, both groups)
     for (int t_ = cluster; t_ < num_tiles; t_ += nclusters, ++it) {
       const int tile = args.reverse ? num_tiles - 1 - t_ : t_;
       const TilePos tp = tile_pos<AMODE>(args, tile / n_tiles, (int)rank);
@@ -226,27 +239,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
       ptx::mbar_wait(&tfull[acc], (it >> 1) & 1u);
       ptx::tc_fence_after();
       for (int h = 0; h < nslab; ++h, ++g) {
-        const uint32_t oslot = g % NOUT, rslot = g % NRES;
-        const uint32_t out_slab = smem_base + plan.out_off + oslot * SLAB_BYTES;
-        const uint32_t out_row = out_slab + (uint32_t)row * 128u;
+        if ((int)(g & 1u) != grp) continue;
+        const uint32_t rslot = g % NRES;
         const uint32_t res_row = smem_base + plan.res_off + rslot * SLAB_BYTES + (uint32_t)row * 128u;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(h * 64);
+        uint32_t v0[32], v1[32];
+        ptx::tmem_ld_32x32(taddr, v0);
+        ptx::tmem_ld_32x32(taddr + 32, v1);
         if (has_res) ptx::mbar_wait(&rfull[rslot], (g / NRES) & 1u);
-        if (store_thread) ptx::bulk_wait_read<NOUT - 1>();        // the store that last used this output slab has finished reading it
-        ptx::named_bar_sync(1, NUM_EPI_WARPS * 32);
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(h * 64 + half * 32);
-        epilogue_chunk<T, GEN>(taddr, p.bias + n0 + h * 64 + half * 32, out_row, res_row, rsw, half * 4, has_res, args.e1, args.e2);
+        if (store_thread) ptx::bulk_wait_read<0>();               // this group's previous store has finished reading the staging slab
+        ptx::named_bar_sync(1 + grp, 128);
+        ptx::tmem_ld_wait();
+        const float* bias = bias_base + n0 + h * 64;
+        epilogue_chunk<T, GEN>(v0, bias, out_row, res_row, rsw, 0, has_res, args.e1, args.e2);
+        epilogue_chunk<T, GEN>(v1, bias + 32, out_row, res_row, rsw, 4, has_res, args.e1, args.e2);
         if (has_res) {
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&rempty[rslot]);
         }
         ptx::fence_proxy_async();                                 // staging writes -> visible to the TMA engine
-        ptx::tc_fence_before();                                   // this warp's TMEM reads of the slab are complete (tmem_ld_wait above)
-        ptx::named_bar_sync(1, NUM_EPI_WARPS * 32);
-        if (h == nslab - 1 && threadIdx.x == 32) {                // accumulator drained by all eight warps: one arrival per CTA
-          ptx::tc_fence_after();
-          if (leader) ptx::mbar_arrive(&tempty[acc]);
-          else ptx::mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
-        }
+        ptx::named_bar_sync(1 + grp, 128);
         if (store_thread) {
           if (tp.valid) {
             if (AMODE == A_HALO) ptx::tma_store_3d(&args.tm_y, out_slab, n0 + h * 64, 0, tp.img * p.Ho + tp.h0);
@@ -255,10 +267,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
           ptx::bulk_commit();
         }
       }
+      // this warp's TMEM reads of the tile are complete (tmem_ld_wait above): hand the accumulator back
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
     }
     if (store_thread) ptx::bulk_wait_all0();
   } else if (warp == MMA_WARP) {
     // ===================== MMA issuer (leader CTA; whole warp walks the loop, one elected lane issues) =====================
+    if (!leader) {
+      // peer CTA: forward "accumulator drained by my eight epilogue warps" to the leader's barrier, one remote arrive per tile
+      const uint32_t tempty_leader0 = ptx::mapa(ptx::smem_u32(&tempty[0]), 0), tempty_leader1 = ptx::mapa(ptx::smem_u32(&tempty[1]), 0);
+      uint32_t it = 0;
+      for (int t_ = cluster; t_ < num_tiles; t_ += nclusters, ++it) {
+        const uint32_t acc = it & 1u;
+        ptx::mbar_wait(&tempty[acc], (it >> 1) & 1u);
+        if (lane == 0) ptx::mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+        __syncwarp();
+      }
+    }
     if (leader) {
       constexpr uint32_t idesc = ptx::make_idesc_f16(TcType<T>::is_bf16, 2 * BM, BN);
       // descriptor = DESC_HI | (address >> 4): version 1, SWIZZLE_128B, SBO 1024 B, LBO 16 B (ptx_sm100.cuh make_smem_desc_sw128)
