@@ -172,6 +172,9 @@ struct Step {
   std::vector<int> reads, writes;  // arena box ids (for the planner's live ranges)
   LTensor out;           // primary output (for dump)
   std::function<void(const RunCtx&)> launch;
+  // alternative implementations of the same step (name, launcher); the first request of a network times them on its own arena and
+  // keeps the fastest (b200_network::autotune).  Empty = nothing to choose.
+  std::vector<std::pair<std::string, std::function<void(const RunCtx&)>>> alts;
 };
 
 struct IOBinding {

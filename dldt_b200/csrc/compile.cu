@@ -507,20 +507,25 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
   Step s;
   s.name = name; s.type = type; s.fused = fused; s.flops = flops; s.bytes = bytes;
   const int dt = cd_;
-  int bn = 0;
-  bool v2 = false, v3 = false;
+  int bn = 0, bn3 = 0;
+  bool v2 = false, v3 = false, both = false;
+  std::string impl2, impl3;
   if (tc) {
     bn = conv_tc_pick_bn(p.Cout_p);
     const char* force_v1 = getenv("B200_CONV_TC_V1");
+    const char* tune = getenv("B200_AUTOTUNE");
+    const char* force3 = getenv("B200_TC3");
     v2 = conv_tc2_supported(p) && !(force_v1 && force_v1[0] == '1');
     v3 = v2 && conv_tc3_preferred(p);
+    // large launches: both persistent kernels apply, the first request measures which one is faster for this shape
+    both = v3 && !(tune && tune[0] == '0') && !(force3 && force3[0] == '1');
+    impl2 = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_128x" + std::to_string(bn) + "x64" +
+            (v2 ? (conv_tc2_a_is_matrix(p) ? "_persistent_tma" : (conv_tc2_a_is_im2col(p) ? "_persistent_im2col" : "_persistent_gather")) : "");
     if (v3) {
-      bn = conv_tc3_pick_bn(p);
-      s.impl = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_pair256x" + std::to_string(bn) + "x64_" + conv_tc3_mode_name(p);
-    } else {
-      s.impl = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_128x" + std::to_string(bn) + "x64" +
-               (v2 ? (conv_tc2_a_is_matrix(p) ? "_persistent_tma" : (conv_tc2_a_is_im2col(p) ? "_persistent_im2col" : "_persistent_gather")) : "");
+      bn3 = conv_tc3_pick_bn(p);
+      impl3 = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_pair256x" + std::to_string(bn3) + "x64_" + conv_tc3_mode_name(p);
     }
+    s.impl = v3 ? impl3 : impl2;
   } else {
     s.impl = "simt_fp32_128x64x16";
   }
@@ -533,16 +538,25 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
     p.reverse = (v2 && !(no_alt && no_alt[0] == '1')) ? !in_dir : 0;
     if (ty && ty->buf.space == SP_ARENA) box_dir_[ty->buf.box] = p.reverse;
   }
-  s.launch = [=](const RunCtx& c) {
-    ConvParams q = p;
-    q.x = c.ptr(x); q.w = c.ptr(w); q.bias = reinterpret_cast<const float*>(c.ptr(bias));
-    q.res = has_res ? c.ptr(res) : nullptr;
-    q.y = c.ptr(y);
-    if (tc && v3) launch_conv_tc3(q, dt, bn, (cudaStream_t)c.stream);
-    else if (tc && v2) launch_conv_tc2(q, dt, bn, (cudaStream_t)c.stream);
-    else if (tc) launch_conv_tc(q, dt, bn, (cudaStream_t)c.stream);
-    else launch_conv_f32(q, (cudaStream_t)c.stream);
+  // which: 0 = per the static policy, 2 = conv_tc2, 3 = conv_tc3
+  auto make_launch = [=](int which) {
+    return [=](const RunCtx& c) {
+      ConvParams q = p;
+      q.x = c.ptr(x); q.w = c.ptr(w); q.bias = reinterpret_cast<const float*>(c.ptr(bias));
+      q.res = has_res ? c.ptr(res) : nullptr;
+      q.y = c.ptr(y);
+      const bool use3 = which == 3 || (which == 0 && v3);
+      if (tc && use3) launch_conv_tc3(q, dt, bn3, (cudaStream_t)c.stream);
+      else if (tc && v2) launch_conv_tc2(q, dt, bn, (cudaStream_t)c.stream);
+      else if (tc) launch_conv_tc(q, dt, bn, (cudaStream_t)c.stream);
+      else launch_conv_f32(q, (cudaStream_t)c.stream);
+    };
   };
+  s.launch = make_launch(0);
+  if (both) {
+    s.alts.emplace_back(impl3, make_launch(3));
+    s.alts.emplace_back(impl2, make_launch(2));
+  }
   emit(std::move(s), {tx, tres}, {ty});
 }
 

@@ -88,7 +88,7 @@ bool ws_applies(const ConvParams& p, int bn, int a_mode) {
   const int ws_bytes = (p.Ktot / BK) * (bn / 2) * 128;
   const char* no_ws = getenv("B200_NO_WS");
   const int min_sa = a_mode == A_HALO ? 3 : 4;
-  return p.Cout_alloc == bn && ws_bytes <= WS_MAX_BYTES && plan3(bn, p.res != nullptr, ws_bytes, a_mode, rows_pitch(p)).sa >= min_sa &&
+  return p.Cout_alloc == bn && ws_bytes <= WS_MAX_BYTES && plan3(bn, p.res != nullptr, ws_bytes, a_mode, rows_pitch(p), p.Cout_alloc).sa >= min_sa &&
          !(no_ws && no_ws[0] == '1');
 }
 
@@ -102,6 +102,14 @@ void launch_tc3(const ConvParams& p, bool bf16, int bn, int a_mode, cudaStream_t
   a.gen = conv_acts_are_clamps(p) ? 0 : 1;
   a.n_tiles = p.Cout_alloc / bn;
   a.reverse = p.reverse;
+  {
+    // activations are read once per layer (the next reader is a different kernel, long after the tensor has left the 126 MB L2 at batch 256):
+    // let them leave first so that what this kernel WRITES stays resident for its consumer.  B200_TC3_EVICT=0 turns the hints off.
+    const char* e = getenv("B200_TC3_EVICT");
+    const bool on = !(e && e[0] == '0');
+    a.a_policy = on ? ptx::L2_EVICT_FIRST : ptx::L2_EVICT_NORMAL;
+    a.r_policy = on ? ptx::L2_EVICT_FIRST : ptx::L2_EVICT_NORMAL;
+  }
   int cta_tiles_m;
   if (a_mode == A_HALO) {
     a.rows_p = rows_pitch(p);
@@ -132,7 +140,7 @@ void launch_tc3(const ConvParams& p, bool bf16, int bn, int a_mode, cudaStream_t
     a.tm_a = a_mode == A_MATRIX ? make_tmap_2d(p.x, bf16, (uint64_t)p.Cin_p, (uint64_t)p.M, (uint64_t)p.Cin_p * 2, BK, BM) : make_tmap_im2col(p, bf16);
   }
   const int grid = 2 * std::min(a.num_tiles, pair_slots());
-  const unsigned smem = plan3(bn, p.res != nullptr, ws ? (p.Ktot / BK) * (bn / 2) * 128 : 0, a_mode, a.rows_p).total;
+  const unsigned smem = plan3(bn, p.res != nullptr, ws ? (p.Ktot / BK) * (bn / 2) * 128 : 0, a_mode, a.rows_p, p.Cout_alloc).total;
   launch_tc3_typed<T>(a, bn, a_mode, ws, grid, smem, s);
 }
 

@@ -37,12 +37,14 @@ enum AMode : int { A_MATRIX = 1, A_IM2COL = 2, A_HALO = 4 };
 struct Plan3 { int sa, sb; uint32_t a_stage, b_stage, a_off, b_off, out_off, res_off, w_off, bias_off, bar_off, total; };
 
 // Shared-memory plan.  rows_p = pixel pitch P of the halo box (A_HALO only).
-__host__ __device__ inline Plan3 plan3(int bn, bool has_res, int ws_bytes, int a_mode, int rows_p) {
+__host__ __device__ inline int bias_smem_bytes(int cout_alloc) { return cout_alloc <= BIAS_SMEM_FLOATS ? ((cout_alloc * 4 + 1023) & ~1023) : 0; }
+__host__ __device__ inline Plan3 plan3(int bn, bool has_res, int ws_bytes, int a_mode, int rows_p, int cout_alloc) {
   Plan3 pl;
+  const int bias_bytes = bias_smem_bytes(cout_alloc);
   pl.a_stage = (uint32_t)A_BYTES;
   if (a_mode == A_HALO) pl.a_stage = (uint32_t)((BM + 2 * rows_p) * 128 + 1024);   // R + 2 image rows of P pixels; the last taps read 2 rows past
   pl.b_stage = (uint32_t)((bn / 2) * 128);
-  const int fixed = NOUT * SLAB_BYTES + (has_res ? NRES * SLAB_BYTES : 0) + ws_bytes + BIAS_SMEM_FLOATS * 4 + 1024 /*align slack*/ + 1024 /*barriers*/;
+  const int fixed = NOUT * SLAB_BYTES + (has_res ? NRES * SLAB_BYTES : 0) + ws_bytes + bias_bytes + 1024 /*align slack*/ + 1024 /*barriers*/;
   const int budget = SMEM_LIMIT - fixed;
   if (ws_bytes) {
     pl.sb = 0;
@@ -63,7 +65,7 @@ __host__ __device__ inline Plan3 plan3(int bn, bool has_res, int ws_bytes, int a
   pl.res_off = pl.out_off + NOUT * SLAB_BYTES;
   pl.w_off = pl.res_off + (has_res ? NRES * SLAB_BYTES : 0);
   pl.bias_off = pl.w_off + (uint32_t)ws_bytes;
-  pl.bar_off = pl.bias_off + BIAS_SMEM_FLOATS * 4;
+  pl.bar_off = pl.bias_off + (uint32_t)bias_bytes;
   pl.total = pl.bar_off + 1024u + 1024u;
   return pl;
 }
@@ -80,6 +82,7 @@ struct Tc3Args {
   int reverse;
   int rows_p, rows_r;       // A_HALO: pixel pitch P and image rows per CTA tile R = 128 / P
   int tiles_per_img;        // A_HALO: CTA tiles per image = Ho / R
+  uint64_t a_policy, r_policy;   // L2 eviction priority of the activation-matrix loads (A_MATRIX) and of the residual loads
 };
 
 __device__ __forceinline__ bool elect_one() {
@@ -144,7 +147,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
   const ConvParams& p = args.p;
   const bool has_res = p.res != nullptr;
   const int nkb = p.Ktot / BK;
-  const Plan3 plan = plan3(BN, has_res, WS ? nkb * B_BYTES : 0, AMODE, args.rows_p);
+  const Plan3 plan = plan3(BN, has_res, WS ? nkb * B_BYTES : 0, AMODE, args.rows_p, p.Cout_alloc);
   const int SA = plan.sa, SB = plan.sb;
   const int cpt = p.Cin_p >> 6;                               // 64-channel chunks per filter tap
   const int n_ablk = AMODE == A_HALO ? cpt : nkb;
@@ -376,7 +379,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
           const uint32_t bar = fullA_leader + (uint32_t)sa * 8u;
           if (leader) ptx::mbar_arrive_expect_tx(&fullA[sa], 2u * a_tx);
           if (AMODE == A_MATRIX) {
-            ptx::tma_load_2d_pair(a_dst, &args.tm_a, bar, ab * BK, tp.m0);
+            ptx::tma_load_2d_pair_hint(a_dst, &args.tm_a, bar, ab * BK, tp.m0, args.a_policy);
           } else if (AMODE == A_IM2COL) {
             ptx::tma_load_im2col_4d_pair(a_dst, &args.tm_a, bar, chunk * BK, bw, bh, bn, (uint32_t)(fs * p.dw), (uint32_t)(fr * p.dh));
           } else {
@@ -419,8 +422,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
           const uint32_t dst = smem_base + plan.res_off + rslot * SLAB_BYTES;
           if (tp.valid) {
             ptx::mbar_arrive_expect_tx(&rfull[rslot], SLAB_BYTES);
-            if (AMODE == A_HALO) ptx::tma_load_3d(dst, &args.tm_r, &rfull[rslot], n0 + h * 64, 0, tp.img * p.Ho + tp.h0);
-            else ptx::tma_load_2d(dst, &args.tm_r, &rfull[rslot], n0 + h * 64, tp.m0);
+            if (AMODE == A_HALO) ptx::tma_load_3d_hint(dst, &args.tm_r, &rfull[rslot], n0 + h * 64, 0, tp.img * p.Ho + tp.h0, args.r_policy);
+            else ptx::tma_load_2d_hint(dst, &args.tm_r, &rfull[rslot], n0 + h * 64, tp.m0, args.r_policy);
           } else {
             ptx::mbar_arrive(&rfull[rslot]);                      // rows beyond M: the epilogue reads stale staging and stores nothing
           }

@@ -100,9 +100,51 @@ void b200_request::enqueue_all(bool eager_events, std::vector<cudaEvent_t>* evs)
   for (size_t i = 0; i < out_dev.size(); ++i) enqueue_egress(*this, c, (int)i);
 }
 
+// Times every alternative of every step that has some (3 event-bracketed launches after one warm-up, best of 3) with the real shapes
+// and buffers, and keeps the fastest.  The buffers hold whatever the arena holds (nothing has run yet): the tensor-core and copy
+// kernels are data independent in time.  Runs once per network.
+void b200_network::autotune(const b200::RunCtx& c, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lk(tune_mu);
+  if (tuned) return;
+  tuned = true;
+  bool any = false;
+  for (auto& s : steps) any = any || s.alts.size() > 1;
+  if (!any) return;
+  cudaEvent_t e0, e1;
+  B200_CUDA(cudaEventCreate(&e0));
+  B200_CUDA(cudaEventCreate(&e1));
+  const char* dbg = getenv("B200_AUTOTUNE_DEBUG");
+  for (auto& s : steps) {
+    if (s.alts.size() < 2) continue;
+    int best = 0;
+    float best_ms = 0.f;
+    for (size_t a = 0; a < s.alts.size(); ++a) {
+      float ms_min = 1e30f;
+      for (int rep = 0; rep < 4; ++rep) {
+        B200_CUDA(cudaEventRecord(e0, stream));
+        s.alts[a].second(c);
+        B200_CUDA(cudaEventRecord(e1, stream));
+        B200_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        B200_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) ms_min = std::min(ms_min, ms);
+      }
+      if (dbg && dbg[0] == '1') fprintf(stderr, "b200 autotune %-24s %-44s %8.1f us\n", s.name.c_str(), s.alts[a].first.c_str(), ms_min * 1e3f);
+      if (a == 0 || ms_min < best_ms) { best = (int)a; best_ms = ms_min; }
+    }
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) B200_THROW(B200_ERR_CUDA, "autotune launch failed: " << cudaGetErrorString(le));
+    s.impl = s.alts[best].first;
+    s.launch = s.alts[best].second;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+}
+
 void b200_request::finalize() {
   if (finalized) return;
   B200_CUDA(cudaSetDevice(net->device));
+  net->autotune(ctx(), stream);
   for (size_t i = 0; i < in_fmt.size(); ++i) {
     in_fmt[i].bytes = numel(net->in_tensors[i].shape) * (int64_t)dtype_size(in_fmt[i].dtype);
     B200_CUDA(cudaMalloc((void**)&in_dev[i], std::max<int64_t>(in_fmt[i].bytes, 16)));

@@ -29,6 +29,10 @@ struct b200_network {
   std::vector<b200::IOBinding> inputs, outputs;
   std::vector<b200::LTensor> in_tensors, out_tensors;
   double flops = 0, bytes = 0;
+  // kernel selection by measurement: steps that carry alternatives are timed once, on the first request's arena and stream
+  std::mutex tune_mu;
+  bool tuned = false;
+  void autotune(const b200::RunCtx& c, cudaStream_t stream);
   ~b200_network();
 };
 
