@@ -102,6 +102,7 @@ void launch_tc3(const ConvParams& p, bool bf16, int bn, int a_mode, cudaStream_t
   a.gen = conv_acts_are_clamps(p) ? 0 : 1;
   a.n_tiles = p.Cout_alloc / bn;
   a.reverse = p.reverse;
+  { const char* e = getenv("B200_TC3_PREFETCH"); a.prefetch_tiles = e ? atoi(e) : 0; }   // measured: no gain on B200 (profiles/r1 call k)
   {
     // activations are read once per layer (the next reader is a different kernel, long after the tensor has left the 126 MB L2 at batch 256):
     // let them leave first so that what this kernel WRITES stays resident for its consumer.  B200_TC3_EVICT=0 turns the hints off.

@@ -82,6 +82,7 @@ struct Tc3Args {
   int reverse;
   int rows_p, rows_r;       // A_HALO: pixel pitch P and image rows per CTA tile R = 128 / P
   int tiles_per_img;        // A_HALO: CTA tiles per image = Ho / R
+  int prefetch_tiles;       // L2 prefetch distance (tiles of this cluster ahead) for the residual and the activation-matrix loads; 0 = off
   uint64_t a_policy, r_policy;   // L2 eviction priority of the activation-matrix loads (A_MATRIX) and of the residual loads
 };
 
@@ -210,6 +211,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
   ptx::cluster_sync();                   // barriers of both CTAs are initialised before any remote arrive / TMA signal
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) ran while the previous kernel of the stream was
+  // still draining; its outputs are read only below this line.  Our own dependents may start their prologue as our CTAs retire.
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
 
   if (warp < NUM_EPI_WARPS) {
     // ===================== epilogue: this CTA's 128 rows, one 64-channel slab at a time =====================
@@ -371,6 +376,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
         bh = ho * p.sh - p.pt;
         bw = (rem - ho * p.Wo) * p.sw - p.pl;
       }
+      if (AMODE == A_MATRIX && args.prefetch_tiles > 0) {
+        // activation matrix rows of a later tile -> L2 (once per M tile: by the cluster that walks its first N tile)
+        const int tla = t_ + args.prefetch_tiles * nclusters;
+        if (tla < num_tiles) {
+          const int tl = args.reverse ? num_tiles - 1 - tla : tla;
+          const int ml = tl / n_tiles;
+          const TilePos tq = tile_pos<AMODE>(args, ml, (int)rank);
+          if (tl - ml * n_tiles == 0 && tq.valid && lane < n_ablk) {
+            for (int ab = lane; ab < n_ablk; ab += 32) ptx::tma_prefetch_2d(&args.tm_a, ab * BK, tq.m0);
+          }
+          __syncwarp();
+        }
+      }
       int chunk = 0, fr = 0, fs = 0;
       for (int ab = 0; ab < n_ablk; ++ab) {
         ptx::mbar_wait(&emptyA[sa], pha ^ 1u);
@@ -410,12 +428,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
     // ===================== residual TMA issuer: one slab ahead of the epilogue, ring of NRES =====================
     if (has_res && lane == 0) {
       uint32_t g = 0;
+      const int la = args.prefetch_tiles * nclusters;
       for (int t_ = cluster; t_ < num_tiles; t_ += nclusters) {
         const int tile = args.reverse ? num_tiles - 1 - t_ : t_;
         const TilePos tp = tile_pos<AMODE>(args, tile / n_tiles, (int)rank);
         const int n0 = (tile % n_tiles) * BN;
         const int ncols = min(BN, p.Cout_p - n0);
         const int nslab = (ncols + 63) >> 6;
+        if (la > 0 && t_ + la < num_tiles) {
+          // the ring holds NRES slabs (64 KB) per SM, one HBM latency's worth at most: pull the slabs of a later tile into L2 now so
+          // that their ring loads are L2 hits
+          const int tl = args.reverse ? num_tiles - 1 - (t_ + la) : t_ + la;
+          const TilePos tq = tile_pos<AMODE>(args, tl / n_tiles, (int)rank);
+          const int q0 = (tl % n_tiles) * BN;
+          const int qslab = (min(BN, p.Cout_p - q0) + 63) >> 6;
+          if (tq.valid)
+            for (int h = 0; h < qslab; ++h) {
+              if (AMODE == A_HALO) ptx::tma_prefetch_3d(&args.tm_r, q0 + h * 64, 0, tq.img * p.Ho + tq.h0);
+              else ptx::tma_prefetch_2d(&args.tm_r, q0 + h * 64, tq.m0);
+            }
+        }
         for (int h = 0; h < nslab; ++h, ++g) {
           const uint32_t rslot = g % NRES;
           ptx::mbar_wait(&rempty[rslot], ((g / NRES) & 1u) ^ 1u);
@@ -438,6 +470,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
   if (warp == MMA_WARP) ptx::tmem_dealloc_pair(tmem_base, 2 * BN);
 }
 
+// cluster dims are static (__cluster_dims__); the one launch attribute is programmatic stream serialization (B200_PDL=0 turns it off)
+template <typename K>
+inline void launch_pdl(K kernel, int grid, unsigned smem, cudaStream_t s, const Tc3Args& a) {
+  static const bool pdl = [] { const char* e = getenv("B200_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
 // ---- launch (one instantiation set per element type; defined in conv_tc3.cu / conv_tc3_f16.cu) ---------------------------------
 template <typename T>
 void launch_tc3_typed(const Tc3Args& a, int bn, int a_mode, bool ws, int grid, unsigned smem, cudaStream_t s);
@@ -458,8 +508,8 @@ void opt_in_tc3_typed();
   template <> void opt_in_tc3_typed<T>() { B200_TC3_FOR_EACH(T, B200_TC3_OPTIN_CASE) }
 #define B200_TC3_LAUNCH_CASE(T, BN_, MODE_, WS_)                                                          \
   if (!done && bn == BN_ && a_mode == MODE_ && ws == WS_) {                                               \
-    if (a.gen) conv_tc3_kernel<T, BN_, MODE_, WS_, true><<<grid, NUM_THREADS, smem, s>>>(a);              \
-    else conv_tc3_kernel<T, BN_, MODE_, WS_, false><<<grid, NUM_THREADS, smem, s>>>(a);                   \
+    if (a.gen) launch_pdl(conv_tc3_kernel<T, BN_, MODE_, WS_, true>, grid, smem, s, a);                   \
+    else launch_pdl(conv_tc3_kernel<T, BN_, MODE_, WS_, false>, grid, smem, s, a);                        \
     done = true;                                                                                          \
   }
 #define B200_TC3_OPTIN_CASE(T, BN_, MODE_, WS_)                                                                                 \

@@ -331,3 +331,25 @@ __device__ __forceinline__ void tma_load_3d_hint(uint32_t dst_smem, const void* 
 }
 }  // namespace ptx
 }  // namespace b200
+
+// ---- TMA prefetch into L2 (no shared-memory destination, no completion signal) ------------------------------------------------
+namespace b200 {
+namespace ptx {
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+}  // namespace ptx
+}  // namespace b200
+
+// ---- programmatic dependent launch ---------------------------------------------------------------------------------------------
+namespace b200 {
+namespace ptx {
+// blocks until every kernel this launch programmatically depends on has completed and its memory is visible (no-op otherwise)
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// lets the dependent launch start scheduling its CTAs as this kernel's CTAs drain
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+}  // namespace ptx
+}  // namespace b200
