@@ -1,6 +1,8 @@
 // Compiled-network and infer-request objects + the C ABI entry points that touch CUDA.
 // One request = one stream + one arena slice + one captured CUDA graph:
 // start() enqueues H2D copies, a single cudaGraphLaunch and D2H copies; wait() blocks on an event.
+#include <fstream>
+#include <map>
 #include "engine.h"
 
 #include <chrono>
@@ -114,8 +116,29 @@ void b200_network::autotune(const b200::RunCtx& c, cudaStream_t stream) {
   B200_CUDA(cudaEventCreate(&e0));
   B200_CUDA(cudaEventCreate(&e1));
   const char* dbg = getenv("B200_AUTOTUNE_DEBUG");
+  // B200_TUNE_FILE: decisions of an earlier load ("<network>\t<step>\t<impl>" lines) are reused instead of measured again, new ones appended
+  const char* tune_file = getenv("B200_TUNE_FILE");
+  std::map<std::string, std::string> cached;
+  const std::string key = name + "@" + std::to_string((long long)arena_bytes);   // same graph at another batch size is another network
+  if (tune_file) {
+    std::ifstream in(tune_file);
+    std::string line;
+    while (std::getline(in, line)) {
+      size_t a = line.find('\t'), b = a == std::string::npos ? a : line.find('\t', a + 1);
+      if (b == std::string::npos || line.substr(0, a) != key) continue;
+      cached[line.substr(a + 1, b - a - 1)] = line.substr(b + 1);
+    }
+  }
+  std::string fresh;
   for (auto& s : steps) {
     if (s.alts.size() < 2) continue;
+    auto hit = cached.find(s.name);
+    if (hit != cached.end()) {
+      bool found = false;
+      for (auto& alt : s.alts)
+        if (alt.first == hit->second) { s.impl = alt.first; s.launch = alt.second; found = true; break; }
+      if (found) continue;
+    }
     int best = 0;
     float best_ms = 0.f;
     for (size_t a = 0; a < s.alts.size(); ++a) {
@@ -136,6 +159,11 @@ void b200_network::autotune(const b200::RunCtx& c, cudaStream_t stream) {
     if (le != cudaSuccess) B200_THROW(B200_ERR_CUDA, "autotune launch failed: " << cudaGetErrorString(le));
     s.impl = s.alts[best].first;
     s.launch = s.alts[best].second;
+    fresh += key + "\t" + s.name + "\t" + s.impl + "\n";
+  }
+  if (tune_file && !fresh.empty()) {
+    std::ofstream out(tune_file, std::ios::app);
+    out << fresh;
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);

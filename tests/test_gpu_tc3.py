@@ -1,0 +1,92 @@
+"""CTA-pair tcgen05 kernel (dldt_b200/csrc/conv_tc3.cuh) against the numpy oracle, through the C ABI.
+
+At the sizes the oracle finishes in seconds the static policy would pick the single-CTA kernel (too few tiles for 74 SM pairs), so
+B200_TC3=1 forces the pair kernel wherever it is supported; the exec graph is checked to make sure it is the kernel that ran.
+Covers the three A-operand modes (activation matrix, im2col TMA, 3x3 halo box), weight-stationary and streamed weights, residual
++ second activation, ragged M tails, N tiles of 64/128/256, bf16 and fp16, and the load-time autotuner's bookkeeping."""
+import numpy as np
+import pytest
+
+from dldt_b200 import Core, Function
+from oracle import interp
+from tests.util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+# name: (N, C, H, W, O, k, stride, pad, residual, act, precision, extra env, expected mode)
+CASES = {
+    "mat_ws_bn256_tail": (4, 64, 28, 28, 256, 1, 1, 0, False, "relu", "BF16", {}, "tma"),
+    "mat_ws_bn64": (4, 256, 28, 28, 64, 1, 1, 0, False, "relu", "BF16", {}, "tma"),
+    "mat_res_ws_bn256": (3, 256, 20, 20, 256, 1, 1, 0, True, "relu", "BF16", {}, "tma"),
+    "mat_nows_bn256_x2": (2, 512, 14, 14, 512, 1, 1, 0, False, "relu", "BF16", {}, "tma"),
+    "mat_bn128_nows": (2, 128, 14, 14, 128, 1, 1, 0, False, "relu", "BF16", {"B200_NO_WS": "1"}, "tma"),
+    "mat_res_nows": (2, 512, 14, 14, 512, 1, 1, 0, True, "relu", "BF16", {}, "tma"),
+    "mat_swish_fp16": (2, 64, 16, 16, 192, 1, 1, 0, False, "swish", "FP16", {}, "tma"),
+    "mat_k2048_n1000": (3, 2048, 7, 7, 1000, 1, 1, 0, False, "none", "BF16", {}, "tma"),
+    "im2col_s2": (2, 128, 30, 30, 256, 3, 2, 1, False, "relu", "BF16", {}, "im2col"),
+    "im2col_3x3_7x7": (5, 512, 7, 7, 512, 3, 1, 1, False, "relu", "BF16", {}, "im2col"),
+    "im2col_nohalo_56": (2, 64, 56, 56, 64, 3, 1, 1, False, "relu", "BF16", {"B200_TC3_HALO": "0"}, "im2col"),
+    "halo_56_ws": (2, 64, 56, 56, 64, 3, 1, 1, False, "relu", "BF16", {}, "halo"),
+    "halo_56_c128_o256": (1, 128, 56, 56, 256, 3, 1, 1, False, "relu", "BF16", {}, "halo"),
+    "halo_28": (3, 128, 28, 28, 128, 3, 1, 1, False, "relu", "BF16", {}, "halo"),
+    "halo_28_res_nows": (3, 128, 28, 28, 128, 3, 1, 1, True, "relu", "BF16", {"B200_NO_WS": "1"}, "halo"),
+    "halo_28_res_fp16": (3, 128, 28, 28, 128, 3, 1, 1, True, "relu", "FP16", {}, "halo"),
+    "halo_w30_clip": (2, 64, 16, 30, 128, 3, 1, 1, False, "clamp", "BF16", {}, "halo"),
+}
+
+
+def build(name):
+    n, c, h, w, o, k, s, p, res, act, prec, env, mode = CASES[name]
+    rng = np.random.default_rng(sum(map(ord, name)))
+    f = Function("conv")
+    x = f.parameter((n, c, h, w))
+    y = f.convolution(x, (rng.standard_normal((o, c, k, k)) / np.sqrt(c * k * k)).astype(np.float32), (s, s), (p, p), (p, p), (1, 1))
+    y = f.add(y, rng.standard_normal((1, o, 1, 1)).astype(np.float32))
+    if res:
+        y = f.relu(f.add(y, x))
+    elif act == "relu":
+        y = f.relu(y)
+    elif act == "swish":
+        y = f.swish(y)
+    elif act == "clamp":
+        y = f.clamp(y, 0.0, 6.0)
+    f.result(y)
+    return f, rng.standard_normal((n, c, h, w)).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_pair_kernel_matches_oracle(name, monkeypatch):
+    prec, env, mode = CASES[name][10], CASES[name][11], CASES[name][12]
+    monkeypatch.setenv("B200_TC3", "1")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    f, xin = build(name)
+    ref = list(interp.run(f, {"Parameter_0": xin}).values())[0]
+    net = Core().load_network(f, "B200", {"B200_INFERENCE_PRECISION": prec})
+    got = list(net.create_infer_request().infer({"Parameter_0": xin}).values())[0]
+    impl = [e["impl"] for e in net.get_exec_graph_info() if e["type"] == "Convolution"]
+    assert impl and all("pair256" in i and i.endswith(mode) for i in impl), impl
+    tol = 1e-2 if prec == "BF16" else 2e-3      # north star: bf16/fp16 within 1e-2 relative L2
+    assert rel_l2(got, ref) < tol, (name, rel_l2(got, ref))
+
+
+def test_autotuned_selection_is_one_of_the_candidates_and_matches_oracle(monkeypatch):
+    # large enough that both persistent kernels apply (>= 74 pair tiles): the first request times them and keeps one
+    monkeypatch.delenv("B200_TC3", raising=False)
+    rng = np.random.default_rng(5)
+    f = Function("conv")
+    x = f.parameter((24, 64, 28, 28))
+    y = f.relu(f.add(f.convolution(x, (rng.standard_normal((64, 64, 3, 3)) / 24.0).astype(np.float32), (1, 1), (1, 1), (1, 1), (1, 1)),
+                     rng.standard_normal((1, 64, 1, 1)).astype(np.float32)))
+    f.result(y)
+    xin = rng.standard_normal((24, 64, 28, 28)).astype(np.float32)
+    ref = list(interp.run(f, {"Parameter_0": xin}).values())[0]
+    net = Core().load_network(f, "B200", {"B200_INFERENCE_PRECISION": "BF16"})
+    req = net.create_infer_request()
+    got = list(req.infer({"Parameter_0": xin}).values())[0]
+    impl = [e["impl"] for e in net.get_exec_graph_info() if e["type"] == "Convolution"][0]
+    assert "pair256" in impl or "128x" in impl, impl
+    assert rel_l2(got, ref) < 1e-2
+    # a second request of the same network reuses the decision and gives the same bits
+    got2 = list(net.create_infer_request().infer({"Parameter_0": xin}).values())[0]
+    assert np.array_equal(got, got2)
