@@ -538,15 +538,15 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
     p.reverse = (v2 && !(no_alt && no_alt[0] == '1')) ? !in_dir : 0;
     if (ty && ty->buf.space == SP_ARENA) box_dir_[ty->buf.box] = p.reverse;
   }
-  // which: 0 = per the static policy, 2 = conv_tc2, 3 = conv_tc3
+  // which: 0 = per the static policy, 2 = conv_tc2, 3 = conv_tc3 at its modelled N tile, 64/128/256 = conv_tc3 at that N tile
   auto make_launch = [=](int which) {
     return [=](const RunCtx& c) {
       ConvParams q = p;
       q.x = c.ptr(x); q.w = c.ptr(w); q.bias = reinterpret_cast<const float*>(c.ptr(bias));
       q.res = has_res ? c.ptr(res) : nullptr;
       q.y = c.ptr(y);
-      const bool use3 = which == 3 || (which == 0 && v3);
-      if (tc && use3) launch_conv_tc3(q, dt, bn3, (cudaStream_t)c.stream);
+      const bool use3 = which >= 3 || (which == 0 && v3);
+      if (tc && use3) launch_conv_tc3(q, dt, which > 3 ? which : bn3, (cudaStream_t)c.stream);
       else if (tc && v2) launch_conv_tc2(q, dt, bn, (cudaStream_t)c.stream);
       else if (tc) launch_conv_tc(q, dt, bn, (cudaStream_t)c.stream);
       else launch_conv_f32(q, (cudaStream_t)c.stream);
@@ -554,7 +554,13 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
   };
   s.launch = make_launch(0);
   if (both) {
+    // candidates: the pair kernel at its modelled N tile and at the other N tiles that divide the padded Cout, and the single-CTA kernel
     s.alts.emplace_back(impl3, make_launch(3));
+    for (int b : {256, 128, 64}) {
+      if (b == bn3 || p.Cout_alloc % b) continue;
+      std::string nm = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_pair256x" + std::to_string(b) + "x64_" + conv_tc3_mode_name(p);
+      s.alts.emplace_back(nm, make_launch(b));     // which > 3: explicit N tile of the pair kernel
+    }
     s.alts.emplace_back(impl2, make_launch(2));
   }
   emit(std::move(s), {tx, tres}, {ty});

@@ -73,7 +73,7 @@ __host__ __device__ inline Plan3 plan3(int bn, bool has_res, int ws_bytes, int a
 struct Tc3Args {
   CUtensorMap tm_a;   // A_MATRIX: [M][Cin_p]; A_IM2COL: {C, W, H, N} im2col; A_HALO: {C, W, H, N} tiled, box {64, P, 128/P + 2, 1}
   CUtensorMap tm_w;   // packed weights [Cout_alloc][Ktot], box {64, BN/2}
-  CUtensorMap tm_y;   // output: [M][Cout_p] box {64, 128}; A_HALO: {C, W, N*H} box {64, P, 128/P}
+  CUtensorMap tm_y;   // output: [M][Cout_p] box {64, 128}; A_HALO: {C, W, H, N} box {64, P, 128/P, 1}
   CUtensorMap tm_r;   // residual, same geometry as the output
   ConvParams p;
   EpiAct e1, e2;
@@ -81,7 +81,7 @@ struct Tc3Args {
   int num_tiles, n_tiles;   // pair tiles
   int reverse;
   int rows_p, rows_r;       // A_HALO: pixel pitch P and image rows per CTA tile R = 128 / P
-  int tiles_per_img;        // A_HALO: CTA tiles per image = Ho / R
+  int tiles_per_img;        // A_HALO: CTA tiles per image = ceil(Ho / R); the last one may hang over the image (clipped by the 4-D maps)
   int prefetch_tiles;       // L2 prefetch distance (tiles of this cluster ahead) for the residual and the activation-matrix loads; 0 = off
   uint64_t a_policy, r_policy;   // L2 eviction priority of the activation-matrix loads (A_MATRIX) and of the residual loads
 };
@@ -269,7 +269,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
         ptx::named_bar_sync(1 + grp, 128);
         if (store_thread) {
           if (tp.valid) {
-            if (AMODE == A_HALO) ptx::tma_store_3d(&args.tm_y, out_slab, n0 + h * 64, 0, tp.img * p.Ho + tp.h0);
+            if (AMODE == A_HALO) ptx::tma_store_4d(&args.tm_y, out_slab, n0 + h * 64, 0, tp.h0, tp.img);   // rows >= Ho / pixels >= Wo are clipped
             else ptx::tma_store_2d(&args.tm_y, out_slab, n0 + h * 64, tp.m0);
           }
           ptx::bulk_commit();
@@ -444,7 +444,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
           const int qslab = (min(BN, p.Cout_p - q0) + 63) >> 6;
           if (tq.valid)
             for (int h = 0; h < qslab; ++h) {
-              if (AMODE == A_HALO) ptx::tma_prefetch_3d(&args.tm_r, q0 + h * 64, 0, tq.img * p.Ho + tq.h0);
+              if (AMODE == A_HALO) ptx::tma_prefetch_4d(&args.tm_r, q0 + h * 64, 0, tq.h0, tq.img);
               else ptx::tma_prefetch_2d(&args.tm_r, q0 + h * 64, tq.m0);
             }
         }
@@ -454,7 +454,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
           const uint32_t dst = smem_base + plan.res_off + rslot * SLAB_BYTES;
           if (tp.valid) {
             ptx::mbar_arrive_expect_tx(&rfull[rslot], SLAB_BYTES);
-            if (AMODE == A_HALO) ptx::tma_load_3d_hint(dst, &args.tm_r, &rfull[rslot], n0 + h * 64, 0, tp.img * p.Ho + tp.h0, args.r_policy);
+            if (AMODE == A_HALO) ptx::tma_load_4d_hint(dst, &args.tm_r, &rfull[rslot], n0 + h * 64, 0, tp.h0, tp.img, args.r_policy);
             else ptx::tma_load_2d_hint(dst, &args.tm_r, &rfull[rslot], n0 + h * 64, tp.m0, args.r_policy);
           } else {
             ptx::mbar_arrive(&rfull[rslot]);                      // rows beyond M: the epilogue reads stale staging and stores nothing

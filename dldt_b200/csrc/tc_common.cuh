@@ -54,7 +54,11 @@ __device__ __forceinline__ void epi_act8(float (&f)[8], const EpiAct& s) {
   if (s.kind == 0) return;   // ACT_NONE (warp-uniform)
   if constexpr (!GENERIC) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(f[e], s.lo), s.hi);
+    for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], s.lo);
+    if (s.hi < 3.0e38f) {   // Clamp proper; ReLU has hi = +inf and needs one instruction per element (warp-uniform branch)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = fminf(f[e], s.hi);
+    }
   } else {
 #pragma unroll 1
     for (int e = 0; e < 8; ++e) f[e] = act_apply(f[e], s.kind, s.a, s.b);

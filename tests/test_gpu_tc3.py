@@ -31,6 +31,8 @@ CASES = {
     "halo_28": (3, 128, 28, 28, 128, 3, 1, 1, False, "relu", "BF16", {}, "halo"),
     "halo_28_res_nows": (3, 128, 28, 28, 128, 3, 1, 1, True, "relu", "BF16", {"B200_NO_WS": "1"}, "halo"),
     "halo_28_res_fp16": (3, 128, 28, 28, 128, 3, 1, 1, True, "relu", "FP16", {}, "halo"),
+    "halo_14_partial_tile": (5, 256, 14, 14, 256, 3, 1, 1, False, "relu", "BF16", {"B200_TC3_HALO": "2"}, "halo"),
+    "halo_14_partial_res": (3, 128, 14, 14, 128, 3, 1, 1, True, "relu", "BF16", {"B200_NO_WS": "1", "B200_TC3_HALO": "2"}, "halo"),
     "halo_w30_clip": (2, 64, 16, 30, 128, 3, 1, 1, False, "clamp", "BF16", {}, "halo"),
 }
 

@@ -18,6 +18,7 @@ CASES = {
     "halo_56_c128_o256":   (1, 128, 56, 56, 256, 3, 1, 1, False, "relu", "BF16", {}),
     "halo_28_res_nows":    (3, 128, 28, 28, 128, 3, 1, 1, True, "relu", "BF16", {"B200_NO_WS": "1"}),
     "halo_14_c256_b16":    (16, 256, 14, 14, 256, 3, 1, 1, False, "relu", "BF16", {}),
+    "halo_14_partial_res": (3, 128, 14, 14, 128, 3, 1, 1, True, "relu", "BF16", {"B200_NO_WS": "1", "B200_TC3_HALO": "2"}),
     "halo_56_ws":          (2, 64, 56, 56, 64, 3, 1, 1, False, "relu", "BF16", {}),
     "halo_28":             (3, 128, 28, 28, 128, 3, 1, 1, False, "relu", "BF16", {}),
     "halo_14_c256":        (5, 256, 14, 14, 256, 3, 1, 1, False, "relu", "BF16", {}),
