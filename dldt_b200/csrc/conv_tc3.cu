@@ -44,7 +44,8 @@ int g_max_clusters3 = 0;   // CTA pairs that can be co-resident (cudaOccupancyMa
 inline int pair_slots() { return g_max_clusters3 > 0 ? g_max_clusters3 : (g_sm_count3 > 0 ? g_sm_count3 : 148) / 2; }
 
 // rank-3/4 tiled maps over NHWC activations (halo mode)
-CUtensorMap make_tmap_tiled(const void* base, bool bf16, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+CUtensorMap make_tmap_tiled(const void* base, bool bf16, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                            CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   auto enc = encode_tiled_fn();
   B200_CHECK(enc, B200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   CUtensorMap m;
@@ -52,7 +53,7 @@ CUtensorMap make_tmap_tiled(const void* base, bool bf16, int rank, const uint64_
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
   CUresult r = enc(&m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, st, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled (rank " << rank << ") failed (" << (int)r << ")");
   return m;
 }
@@ -82,7 +83,20 @@ bool halo_ok(const ConvParams& p) {
   return p.ldy == p.Cout_p && useful >= ((e && e[0] == '2') ? 0.3 : 0.8);
 }
 
+// The space-to-depth stem (compile.cu lower_stem_s2d): a 4x4 stride-1 window over 16-channel block pixels, described to the single-CTA
+// kernel as "4 taps of 64 overlapping channels".  Here the box of block pixels is loaded ONCE per output row segment and every tap is a
+// shifted 32-byte-swizzled view of it, so the input crosses the L2 -> SM fabric 4x (block rows) instead of 16x.
+bool s2d_ok(const ConvParams& p) {
+  const char* e = getenv("B200_TC3_S2D");
+  if (e && e[0] == '0') return false;
+  // block row pitch a multiple of 16 bytes, groups of 4 output pixels, no residual, one 64-channel N tile (four phase accumulators fill TMEM),
+  // one segment per row (group 31 of the box reads group 32 = the next block row: it must be a dropped one, so Wo <= 124)
+  return p.x_sw == 16 && p.kh == 4 && p.kw == 1 && p.Cin_p == 64 && p.Ktot == 256 && p.sh == 1 && p.sw == 1 && p.dh == 1 && p.pt == 0 && p.pl == 0 &&
+         p.x_sh % 16 == 0 && p.x_sn % p.x_sh == 0 && p.Cout_alloc == 64 && p.ldy == p.Cout_p && p.Cout_p == 64 && p.Wo % 4 == 0 && p.Wo / 4 < S2D_G && p.res == nullptr;
+}
+
 int a_mode_of(const ConvParams& p) {
+  if (s2d_ok(p)) return A_S2D;
   if (conv_tc2_a_is_matrix(p) && p.Cin_p % 64 == 0) return A_MATRIX;
   if (halo_ok(p)) return A_HALO;
   if (conv_tc2_a_is_im2col(p)) return A_IM2COL;
@@ -93,7 +107,7 @@ bool ws_applies(const ConvParams& p, int bn, int a_mode) {
   const int ws_bytes = (p.Ktot / BK) * (bn / 2) * 128;
   const char* no_ws = getenv("B200_NO_WS");
   const int min_sa = a_mode == A_HALO ? 3 : 4;
-  return p.Cout_alloc == bn && ws_bytes <= WS_MAX_BYTES && plan3(bn, p.res != nullptr, ws_bytes, a_mode, rows_pitch(p), p.Cout_alloc).sa >= min_sa &&
+  return p.Cout_alloc == bn && ws_bytes <= WS_MAX_BYTES && plan3(bn, p.res != nullptr, ws_bytes, a_mode, rows_pitch(p), p.Cout_alloc, p.Ktot / BK).sa >= min_sa &&
          !(no_ws && no_ws[0] == '1');
 }
 
@@ -117,7 +131,11 @@ void launch_tc3(const ConvParams& p, bool bf16, int bn, int a_mode, cudaStream_t
     a.r_policy = on ? ptx::L2_EVICT_FIRST : ptx::L2_EVICT_NORMAL;
   }
   int cta_tiles_m;
-  if (a_mode == A_HALO) {
+  if (a_mode == A_S2D) {
+    a.nseg = (p.Wo / 4 + S2D_G - 1) / S2D_G;
+    a.tiles_per_img = ((p.Ho + S2D_R - 1) / S2D_R) * a.nseg;
+    cta_tiles_m = a.tiles_per_img * p.N;
+  } else if (a_mode == A_HALO) {
     a.rows_p = rows_pitch(p);
     a.rows_r = BM / a.rows_p;
     a.tiles_per_img = (p.Ho + a.rows_r - 1) / a.rows_r;
@@ -126,9 +144,23 @@ void launch_tc3(const ConvParams& p, bool bf16, int bn, int a_mode, cudaStream_t
     cta_tiles_m = (p.M + BM - 1) / BM;
   }
   a.num_tiles = ((cta_tiles_m + 1) / 2) * a.n_tiles;
-  const bool ws = ws_applies(p, bn, a_mode);
+  const bool ws = a_mode == A_S2D ? true : ws_applies(p, bn, a_mode);
   a.tm_w = make_tmap_2d(p.w, bf16, (uint64_t)p.Ktot, (uint64_t)p.Cout_alloc, (uint64_t)p.w_ld * 2, BK, bn / 2);
-  if (a_mode == A_HALO) {
+  if (a_mode == A_S2D) {
+    // input: block pixels in groups of 4 (64 elements = one 128-byte row): {64, ceil(Wb / 4), Hb, N}; the last group of a row may run one
+    // pixel into the next row (read only by output pixels the store drops)
+    const uint64_t Wb = (uint64_t)(p.x_sh / 16), Hb = (uint64_t)(p.x_sn / p.x_sh), pitch = (uint64_t)p.ldy * 2;
+    const uint64_t ad[4] = {64, (Wb + 3) / 4, Hb, (uint64_t)p.N};
+    const uint64_t as[3] = {128, Wb * 32, Hb * Wb * 32};
+    const uint32_t ab[4] = {64, (uint32_t)S2D_G, (uint32_t)(S2D_R + 3), 1};
+    a.tm_a = make_tmap_tiled(p.x, bf16, 4, ad, as, ab);
+    // output: {channel, phase (pixel 4 g + f), pixel group g, row, image}
+    const uint64_t yd[5] = {(uint64_t)p.Cout_p, 4, (uint64_t)(p.Wo / 4), (uint64_t)p.Ho, (uint64_t)p.N};
+    const uint64_t ys[4] = {pitch, 4 * pitch, (uint64_t)p.Wo * pitch, (uint64_t)p.Ho * p.Wo * pitch};
+    const uint32_t yb[5] = {64, 1, (uint32_t)S2D_G, (uint32_t)S2D_R, 1};
+    a.tm_y = make_tmap_tiled(p.y, bf16, 5, yd, ys, yb);
+    a.tm_r = a.tm_y;
+  } else if (a_mode == A_HALO) {
     const uint64_t C = (uint64_t)p.Cin_p, pitch = (uint64_t)p.ldy * 2;
     const uint64_t ad[4] = {C, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
     const uint64_t as[3] = {C * 2, (uint64_t)p.W * C * 2, (uint64_t)p.H * p.W * C * 2};
@@ -147,14 +179,14 @@ void launch_tc3(const ConvParams& p, bool bf16, int bn, int a_mode, cudaStream_t
     a.tm_a = a_mode == A_MATRIX ? make_tmap_2d(p.x, bf16, (uint64_t)p.Cin_p, (uint64_t)p.M, (uint64_t)p.Cin_p * 2, BK, BM) : make_tmap_im2col(p, bf16);
   }
   const int grid = 2 * std::min(a.num_tiles, pair_slots());
-  const unsigned smem = plan3(bn, p.res != nullptr, ws ? (p.Ktot / BK) * (bn / 2) * 128 : 0, a_mode, a.rows_p, p.Cout_alloc).total;
+  const unsigned smem = plan3(bn, p.res != nullptr, ws ? (p.Ktot / BK) * (bn / 2) * 128 : 0, a_mode, a.rows_p, p.Cout_alloc, p.Ktot / BK).total;
   launch_tc3_typed<T>(a, bn, a_mode, ws, grid, smem, s);
 }
 
 }  // namespace
 
 bool conv_tc3_supported(const ConvParams& p) {
-  return conv_tc2_supported(p) && a_mode_of(p) != 0 && p.Cout_alloc % 64 == 0 && p.Ktot % BK == 0;
+  return conv_tc2_supported(p) && a_mode_of(p) != 0 && p.Cout_alloc % 64 == 0 && p.Ktot % BK == 0 && p.Cout_alloc <= BIAS_SMEM_FLOATS;
 }
 
 // Estimated cycles of one launch with N tile `bn` on `sms` SMs: rounds x k-blocks x max(MMA, operand bytes / fabric rate) + epilogue traffic.
@@ -181,6 +213,7 @@ static double tc3_cost(const ConvParams& p, int bn, int a_mode, int sms) {
 
 int conv_tc3_pick_bn(const ConvParams& p) {
   const int a_mode = a_mode_of(p);
+  if (a_mode == A_S2D) return p.Cout_alloc;   // weights resident, one N tile
   const int sms = 2 * pair_slots();
   int best = 0;
   double best_c = 0;
@@ -209,6 +242,7 @@ const char* conv_tc3_mode_name(const ConvParams& p) {
     case A_MATRIX: return "tma";
     case A_HALO: return "halo";
     case A_IM2COL: return "im2col";
+    case A_S2D: return "s2d";
   }
   return "?";
 }

@@ -27,28 +27,39 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int MMA_WARP = 8, TMA_WARP = 9, RES_WARP = 10;
 constexpr int NUM_THREADS = 352;
 constexpr int MAX_STAGES = 8;
-constexpr int NOUT = 2, NRES = 4;        // staging rings, in slabs
+constexpr int NRES = 4;                  // residual ring, in slabs; output staging: 1 or 2 slabs per epilogue group (Plan3::nout = 2 or 4)
 constexpr int SMEM_LIMIT = 232448;
 constexpr int WS_MAX_BYTES = 80 * 1024;  // resident half of the weights, per CTA
-constexpr int BIAS_SMEM_FLOATS = 2048;   // bias vector staged in shared memory when Cout_alloc fits (else read through L1 per use)
+constexpr int BIAS_SMEM_FLOATS = 4096;   // the bias vector is staged in shared memory (launches with a larger padded Cout are not supported)
 
-enum AMode : int { A_MATRIX = 1, A_IM2COL = 2, A_HALO = 4 };
+enum AMode : int { A_MATRIX = 1, A_IM2COL = 2, A_HALO = 4, A_S2D = 8 };
+constexpr int S2D_R = 4, S2D_G = 32;     // space-to-depth stem tile: 4 output rows x 32 groups of 4 pixels (one group = 4 x 16 channels = one 128-byte row)
 
-struct Plan3 { int sa, sb; uint32_t a_stage, b_stage, a_off, b_off, out_off, res_off, w_off, bias_off, bar_off, total; };
+struct Plan3 { int sa, sb, nout; uint32_t a_stage, b_stage, a_off, b_off, out_off, res_off, w_off, bias_off, bar_off, total; };
 
 // Shared-memory plan.  rows_p = pixel pitch P of the halo box (A_HALO only).
-__host__ __device__ inline int bias_smem_bytes(int cout_alloc) { return cout_alloc <= BIAS_SMEM_FLOATS ? ((cout_alloc * 4 + 1023) & ~1023) : 0; }
-__host__ __device__ inline Plan3 plan3(int bn, bool has_res, int ws_bytes, int a_mode, int rows_p, int cout_alloc) {
+__host__ __device__ inline int bias_smem_bytes(int cout_alloc) { return (cout_alloc * 4 + 1023) & ~1023; }
+__host__ __device__ inline Plan3 plan3(int bn, bool has_res, int ws_bytes, int a_mode, int rows_p, int cout_alloc, int nkb) {
   Plan3 pl;
   const int bias_bytes = bias_smem_bytes(cout_alloc);
   pl.a_stage = (uint32_t)A_BYTES;
   if (a_mode == A_HALO) pl.a_stage = (uint32_t)((BM + 2 * rows_p) * 128 + 1024);   // R + 2 image rows of P pixels; the last taps read 2 rows past
+  if (a_mode == A_S2D) pl.a_stage = (uint32_t)((S2D_R + 3) * S2D_G * 128 + 1024);   // R + 3 block rows of 32 pixel groups; the last taps read 1 row past
   pl.b_stage = (uint32_t)((bn / 2) * 128);
-  const int fixed = NOUT * SLAB_BYTES + (has_res ? NRES * SLAB_BYTES : 0) + ws_bytes + bias_bytes + 1024 /*align slack*/ + 1024 /*barriers*/;
+  // Two staging slabs per epilogue group (the next slab is converted while the TMA store of the previous one still reads its slab) for
+  // launches with few k-blocks per tile, where the epilogue is what bounds the tile time, if that leaves three operand stages
+  const int fixed2 = 2 * SLAB_BYTES + (has_res ? NRES * SLAB_BYTES : 0) + ws_bytes + bias_bytes + 1024 /*align slack*/ + 1024 /*barriers*/;
+  const int rem4 = SMEM_LIMIT - fixed2 - 2 * SLAB_BYTES;
+  pl.nout = (nkb <= 9 && rem4 >= 3 * (int)(pl.a_stage + (ws_bytes ? 0 : pl.b_stage))) ? 4 : 2;
+  const int fixed = fixed2 + (pl.nout - 2) * SLAB_BYTES;
   const int budget = SMEM_LIMIT - fixed;
   if (ws_bytes) {
     pl.sb = 0;
     pl.sa = budget / (int)pl.a_stage;
+    if (a_mode == A_S2D && pl.sa > 4) pl.sa = 4;
+  } else if (a_mode == A_S2D) {
+    pl.sb = 0;
+    pl.sa = 4;
   } else if (a_mode == A_HALO) {
     // one A stage feeds nine k-blocks: the weights are the stream, the activations need depth only to hide one TMA latency
     pl.sb = bn == 256 ? 4 : 6;
@@ -62,7 +73,7 @@ __host__ __device__ inline Plan3 plan3(int bn, bool has_res, int ws_bytes, int a
   pl.a_off = 0;
   pl.b_off = pl.a_off + (uint32_t)pl.sa * pl.a_stage;
   pl.out_off = pl.b_off + (uint32_t)pl.sb * pl.b_stage;
-  pl.res_off = pl.out_off + NOUT * SLAB_BYTES;
+  pl.res_off = pl.out_off + (uint32_t)pl.nout * SLAB_BYTES;
   pl.w_off = pl.res_off + (has_res ? NRES * SLAB_BYTES : 0);
   pl.bias_off = pl.w_off + (uint32_t)ws_bytes;
   pl.bar_off = pl.bias_off + (uint32_t)bias_bytes;
@@ -81,7 +92,8 @@ struct Tc3Args {
   int num_tiles, n_tiles;   // pair tiles
   int reverse;
   int rows_p, rows_r;       // A_HALO: pixel pitch P and image rows per CTA tile R = 128 / P
-  int tiles_per_img;        // A_HALO: CTA tiles per image = ceil(Ho / R); the last one may hang over the image (clipped by the 4-D maps)
+  int nseg;                 // A_S2D: 128-pixel segments per output row
+  int tiles_per_img;        // A_S2D: ceil(Ho / 4) * nseg.  A_HALO: CTA tiles per image = ceil(Ho / R); the last one may hang over the image (clipped by the 4-D maps)
   int prefetch_tiles;       // L2 prefetch distance (tiles of this cluster ahead) for the residual and the activation-matrix loads; 0 = off
   uint64_t a_policy, r_policy;   // L2 eviction priority of the activation-matrix loads (A_MATRIX) and of the residual loads
 };
@@ -93,17 +105,17 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 template <typename T, bool GEN>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const float* __restrict__ bias, uint32_t out_row, uint32_t res_row, uint32_t rsw,
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint32_t bias /* shared-memory address */, uint32_t out_row, uint32_t res_row, uint32_t rsw,
                                                int chunk0, bool has_res, const EpiAct& e1, const EpiAct& e2) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    const float4 b0 = *reinterpret_cast<const float4*>(bias + g * 8);
-    const float4 b1 = *reinterpret_cast<const float4*>(bias + g * 8 + 4);
+    const uint4 b0 = ptx::ld_shared_v4(bias + (uint32_t)g * 32u);          // all lanes read the same address: broadcast
+    const uint4 b1 = ptx::ld_shared_v4(bias + (uint32_t)g * 32u + 16u);
     float f[8];
-    f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
-    f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
-    f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
-    f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+    f[0] = __uint_as_float(v[g * 8 + 0]) + __uint_as_float(b0.x); f[1] = __uint_as_float(v[g * 8 + 1]) + __uint_as_float(b0.y);
+    f[2] = __uint_as_float(v[g * 8 + 2]) + __uint_as_float(b0.z); f[3] = __uint_as_float(v[g * 8 + 3]) + __uint_as_float(b0.w);
+    f[4] = __uint_as_float(v[g * 8 + 4]) + __uint_as_float(b1.x); f[5] = __uint_as_float(v[g * 8 + 5]) + __uint_as_float(b1.y);
+    f[6] = __uint_as_float(v[g * 8 + 6]) + __uint_as_float(b1.z); f[7] = __uint_as_float(v[g * 8 + 7]) + __uint_as_float(b1.w);
     epi_act8<GEN>(f, e1);
     const uint32_t sw = (rsw ^ (uint32_t)(chunk0 + g)) << 4;      // 16-byte chunk index XOR (row & 7)
     if (has_res) {
@@ -120,14 +132,23 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const fl
 }
 
 // first output row of CTA `rank` of pair tile `tile_m`, and (halo mode) its image / first image row
-struct TilePos { int m0; int img, h0; bool valid; };
+struct TilePos { int m0; int img, h0, w0; bool valid; };
 template <int AMODE>
 __device__ __forceinline__ TilePos tile_pos(const Tc3Args& a, int tile_m, int rank) {
   TilePos t;
   const int ct = tile_m * 2 + rank;                 // CTA tile index along M
+  t.w0 = 0;
   if (AMODE == A_HALO) {
     t.img = ct / a.tiles_per_img;
     t.h0 = (ct - t.img * a.tiles_per_img) * a.rows_r;
+    t.valid = t.img < a.p.N;
+    t.m0 = 0;
+  } else if (AMODE == A_S2D) {
+    t.img = ct / a.tiles_per_img;
+    const int rem = ct - t.img * a.tiles_per_img;
+    const int rt = rem / a.nseg;
+    t.h0 = rt * S2D_R;                              // first output row
+    t.w0 = (rem - rt * a.nseg) * S2D_G;             // first pixel GROUP of the segment (4 output pixels per group)
     t.valid = t.img < a.p.N;
     t.m0 = 0;
   } else {
@@ -144,15 +165,17 @@ __device__ __forceinline__ TilePos tile_pos(const Tc3Args& a, int tile_m, int ra
 template <typename T, int BN, int AMODE, bool WS, bool GEN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv_tc3_kernel(const __grid_constant__ Tc3Args args) {
   constexpr int B_BYTES = (BN / 2) * 128;     // this CTA's half of a weight k-block
-  constexpr int REUSE = AMODE == A_HALO ? 9 : 1;   // k-blocks served by one A stage (halo: the nine taps of a 3x3)
+  constexpr int REUSE = AMODE == A_HALO ? 9 : 1;                // k-blocks served by one A stage (halo: the nine taps of a 3x3)
+  constexpr bool BOX4D = AMODE == A_HALO;                       // output / residual addressed {channel, w, h, n}
+  constexpr int ACC_COLS = AMODE == A_S2D ? 4 * BN : BN;        // s2d stem: four accumulators (output pixel phases 4g + 0..3) per tile
   const ConvParams& p = args.p;
   const bool has_res = p.res != nullptr;
   const int nkb = p.Ktot / BK;
-  const Plan3 plan = plan3(BN, has_res, WS ? nkb * B_BYTES : 0, AMODE, args.rows_p, p.Cout_alloc);
+  const Plan3 plan = plan3(BN, has_res, WS ? nkb * B_BYTES : 0, AMODE, args.rows_p, p.Cout_alloc, nkb);
   const int SA = plan.sa, SB = plan.sb;
   const int cpt = p.Cin_p >> 6;                               // 64-channel chunks per filter tap
-  const int n_ablk = AMODE == A_HALO ? cpt : nkb;
-  const uint32_t a_tx = AMODE == A_HALO ? (uint32_t)((BM + 2 * args.rows_p) * 128) : (uint32_t)A_BYTES;   // bytes one CTA's A load delivers
+  const int n_ablk = AMODE == A_HALO ? cpt : (AMODE == A_S2D ? 1 : nkb);
+  const uint32_t a_tx = AMODE == A_HALO ? (uint32_t)((BM + 2 * args.rows_p) * 128) : (AMODE == A_S2D ? (uint32_t)((S2D_R + 3) * S2D_G * 128) : (uint32_t)A_BYTES);   // bytes one CTA's A load delivers
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -204,7 +227,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
     if (has_res) ptx::tma_prefetch_desc(&args.tm_r);
   }
   if (warp == MMA_WARP) {
-    ptx::tmem_alloc_pair(tmem_slot, 2 * BN);
+    ptx::tmem_alloc_pair(tmem_slot, 2 * ACC_COLS);
     ptx::tmem_relinquish_pair();
   }
   ptx::tc_fence_before();
@@ -226,23 +249,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
     const int row = q * 32 + lane;
     const uint32_t rsw = (uint32_t)(row & 7);
     const bool store_thread = (threadIdx.x & 127) == 0;
-    const uint32_t out_slab = smem_base + plan.out_off + (uint32_t)grp * SLAB_BYTES;
-    const uint32_t out_row = out_slab + (uint32_t)row * 128u;
-    // bias vector -> shared memory (all 256 epilogue threads), else straight from global
-    const bool bias_smem = p.Cout_alloc <= BIAS_SMEM_FLOATS;
-    float* s_bias = reinterpret_cast<float*>(smem_al + plan.bias_off);
-    if (bias_smem) {
+    const uint32_t per_grp = (uint32_t)plan.nout >> 1;       // staging slabs of this group: 1 or 2
+    uint32_t mine = 0;                                       // slabs this group has processed
+    // bias vector -> shared memory (all 256 epilogue threads)
+    {
+      float* s_bias = reinterpret_cast<float*>(smem_al + plan.bias_off);
       for (int i = threadIdx.x; i < p.Cout_alloc; i += NUM_EPI_WARPS * 32) s_bias[i] = __ldg(p.bias + i);
       ptx::named_bar_sync(3, NUM_EPI_WARPS * 32);
     }
-    const float* bias_base = bias_smem ? s_bias : p.bias;
+    const uint32_t bias_base = smem_base + plan.bias_off;
     uint32_t it = 0, g = 0;                // tiles / slabs processed so far (all slabs, both groups)
     for (int t_ = cluster; t_ < num_tiles; t_ += nclusters, ++it) {
       const int tile = args.reverse ? num_tiles - 1 - t_ : t_;
       const TilePos tp = tile_pos<AMODE>(args, tile / n_tiles, (int)rank);
       const int n0 = (tile % n_tiles) * BN;
       const int ncols = min(BN, p.Cout_p - n0);
-      const int nslab = (ncols + 63) >> 6;
+      const int nslab = AMODE == A_S2D ? 4 : (ncols + 63) >> 6;   // s2d stem: slab h = output pixel phase h (BN == 64 channels each)
       const uint32_t acc = it & 1u;
       ptx::mbar_wait(&tfull[acc], (it >> 1) & 1u);
       ptx::tc_fence_after();
@@ -250,17 +272,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
         if ((int)(g & 1u) != grp) continue;
         const uint32_t rslot = g % NRES;
         const uint32_t res_row = smem_base + plan.res_off + rslot * SLAB_BYTES + (uint32_t)row * 128u;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(h * 64);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + (uint32_t)(h * 64);
         uint32_t v0[32], v1[32];
         ptx::tmem_ld_32x32(taddr, v0);
         ptx::tmem_ld_32x32(taddr + 32, v1);
+        const uint32_t out_slab = smem_base + plan.out_off + ((uint32_t)grp * per_grp + (mine & (per_grp - 1u))) * SLAB_BYTES;
+        const uint32_t out_row = out_slab + (uint32_t)row * 128u;
+        ++mine;
         if (has_res) ptx::mbar_wait(&rfull[rslot], (g / NRES) & 1u);
-        if (store_thread) ptx::bulk_wait_read<0>();               // this group's previous store has finished reading the staging slab
+        if (store_thread) {                                       // the store that last used this staging slab has finished reading it
+          if (per_grp == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
+        }
         ptx::named_bar_sync(1 + grp, 128);
         ptx::tmem_ld_wait();
-        const float* bias = bias_base + n0 + h * 64;
+        const uint32_t bias = bias_base + (uint32_t)(n0 + (AMODE == A_S2D ? 0 : h * 64)) * 4u;
         epilogue_chunk<T, GEN>(v0, bias, out_row, res_row, rsw, 0, has_res, args.e1, args.e2);
-        epilogue_chunk<T, GEN>(v1, bias + 32, out_row, res_row, rsw, 4, has_res, args.e1, args.e2);
+        epilogue_chunk<T, GEN>(v1, bias + 128u, out_row, res_row, rsw, 4, has_res, args.e1, args.e2);
         if (has_res) {
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&rempty[rslot]);
@@ -269,7 +296,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
         ptx::named_bar_sync(1 + grp, 128);
         if (store_thread) {
           if (tp.valid) {
-            if (AMODE == A_HALO) ptx::tma_store_4d(&args.tm_y, out_slab, n0 + h * 64, 0, tp.h0, tp.img);   // rows >= Ho / pixels >= Wo are clipped
+            if (AMODE == A_S2D) ptx::tma_store_5d(&args.tm_y, out_slab, 0, h, tp.w0, tp.h0, tp.img);   // {channel, phase, pixel group, row, image}
+            else if (BOX4D) ptx::tma_store_4d(&args.tm_y, out_slab, n0 + h * 64, tp.w0, tp.h0, tp.img);   // rows >= Ho / pixels >= Wo are clipped
             else ptx::tma_store_2d(&args.tm_y, out_slab, n0 + h * 64, tp.m0);
           }
           ptx::bulk_commit();
@@ -310,11 +338,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
         const uint32_t acc = it & 1u;
         ptx::mbar_wait(&tempty[acc], ((it >> 1) & 1u) ^ 1u);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
         uint32_t accum = 0;
         for (int ab = 0; ab < n_ablk; ++ab) {
           ptx::mbar_wait(&fullA[sa], pha);
           const uint32_t a_lo = a_lo0 + (uint32_t)sa * a_step;
+          if (AMODE == A_S2D) {
+            // space-to-depth stem.  A row of the box = one GROUP of 4 block pixels (4 x 16 channels = 128 swizzled bytes), 32 groups per
+            // block row, R + 3 block rows.  MMA row m = (output row m / 32, group m % 32); phase f = output pixel 4 g + f; tap (r, s) of the
+            // 4x4 window reads block pixel 4 g + f + s = group g + (f + s) / 4, K step (f + s) % 4, so every (phase, tap) is ONE MMA over a
+            // shifted view of the same box: 64 MMAs per tile, four accumulators.  Row 32 * y + 31 + 1 wraps into the next block row: those
+            // are pixel groups >= 29 of a 112-pixel row, dropped by the store map.
+            ptx::tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int f = 0; f < 4; ++f) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int off = f + (j % 4);
+                  const uint32_t a_view = a_lo + (uint32_t)(((j / 4) * S2D_G + off / 4) * 8 + (off % 4) * 2);
+                  const uint32_t b_lo = b_lo0 + (uint32_t)(j / 4) * b_step + 2u * (uint32_t)(j % 4);
+                  ptx::umma_f16_pair(d_tmem + (uint32_t)(f * BN), DESC_HI | (uint64_t)a_view, DESC_HI | (uint64_t)b_lo, idesc, (uint32_t)(j > 0));
+                }
+              }
+            }
+            __syncwarp();
+            accum = 1;
+          } else {
 #pragma unroll
           for (int j = 0; j < REUSE; ++j) {
             // halo mode: tap (j / 3, j % 3) reads the box shifted by whole image rows and pixels (one pixel = one 128-byte swizzled row);
@@ -337,6 +387,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
             __syncwarp();
             accum = 1;
             if (!WS) { if (++sb == SB) { sb = 0; phb ^= 1u; } }
+          }
           }
           if (elect_one()) ptx::umma_commit_pair(&emptyA[sa], 3);
           __syncwarp();
@@ -400,6 +451,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
             ptx::tma_load_2d_pair_hint(a_dst, &args.tm_a, bar, ab * BK, tp.m0, args.a_policy);
           } else if (AMODE == A_IM2COL) {
             ptx::tma_load_im2col_4d_pair(a_dst, &args.tm_a, bar, chunk * BK, bw, bh, bn, (uint32_t)(fs * p.dw), (uint32_t)(fr * p.dh));
+          } else if (AMODE == A_S2D) {
+            // block rows h0 .. h0 + R + 2, pixel groups w0 .. w0 + 31; beyond the block grid -> zero fill
+            ptx::tma_load_4d_pair(a_dst, &args.tm_a, bar, 0, tp.w0, tp.h0, tp.img);
           } else {
             // all filter rows at once: input rows h0 - pt .. h0 - pt + R + 1, pixels -pl .. P - pl - 1 of 64-channel chunk ab
             ptx::tma_load_4d_pair(a_dst, &args.tm_a, bar, ab * BK, -p.pl, tp.h0 - p.pt, tp.img);
@@ -410,7 +464,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
         if (!WS) {
 #pragma unroll 1
           for (int j = 0; j < REUSE; ++j) {
-            const int kb = AMODE == A_HALO ? j * cpt + ab : ab;
+            const int kb = AMODE == A_HALO ? j * cpt + ab : (AMODE == A_S2D ? j : ab);
             ptx::mbar_wait(&emptyB[sb], phb ^ 1u);
             if (elect_one()) {
               const uint32_t barb = fullB_leader + (uint32_t)sb * 8u;
@@ -444,7 +498,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
           const int qslab = (min(BN, p.Cout_p - q0) + 63) >> 6;
           if (tq.valid)
             for (int h = 0; h < qslab; ++h) {
-              if (AMODE == A_HALO) ptx::tma_prefetch_4d(&args.tm_r, q0 + h * 64, 0, tq.h0, tq.img);
+              if (BOX4D) ptx::tma_prefetch_4d(&args.tm_r, q0 + h * 64, tq.w0, tq.h0, tq.img);
               else ptx::tma_prefetch_2d(&args.tm_r, q0 + h * 64, tq.m0);
             }
         }
@@ -454,7 +508,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
           const uint32_t dst = smem_base + plan.res_off + rslot * SLAB_BYTES;
           if (tp.valid) {
             ptx::mbar_arrive_expect_tx(&rfull[rslot], SLAB_BYTES);
-            if (AMODE == A_HALO) ptx::tma_load_4d_hint(dst, &args.tm_r, &rfull[rslot], n0 + h * 64, 0, tp.h0, tp.img, args.r_policy);
+            if (BOX4D) ptx::tma_load_4d_hint(dst, &args.tm_r, &rfull[rslot], n0 + h * 64, tp.w0, tp.h0, tp.img, args.r_policy);
             else ptx::tma_load_2d_hint(dst, &args.tm_r, &rfull[rslot], n0 + h * 64, tp.m0, args.r_policy);
           } else {
             ptx::mbar_arrive(&rfull[rslot]);                      // rows beyond M: the epilogue reads stale staging and stores nothing
@@ -467,7 +521,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
   __syncwarp();
   ptx::tc_fence_before();
   ptx::cluster_sync();        // neither CTA may exit (or free TMEM) while the other can still touch its shared memory / barriers
-  if (warp == MMA_WARP) ptx::tmem_dealloc_pair(tmem_base, 2 * BN);
+  if (warp == MMA_WARP) ptx::tmem_dealloc_pair(tmem_base, 2 * ACC_COLS);
 }
 
 // cluster dims are static (__cluster_dims__); the one launch attribute is programmatic stream serialization (B200_PDL=0 turns it off)
@@ -497,7 +551,8 @@ void opt_in_tc3_typed();
 #define B200_TC3_FOR_EACH(T, X) \
   X(T, 64, A_MATRIX, false) X(T, 64, A_MATRIX, true) X(T, 64, A_IM2COL, false) X(T, 64, A_IM2COL, true) X(T, 64, A_HALO, false) X(T, 64, A_HALO, true) \
   X(T, 128, A_MATRIX, false) X(T, 128, A_MATRIX, true) X(T, 128, A_IM2COL, false) X(T, 128, A_IM2COL, true) X(T, 128, A_HALO, false) X(T, 128, A_HALO, true) \
-  X(T, 256, A_MATRIX, false) X(T, 256, A_MATRIX, true) X(T, 256, A_IM2COL, false) X(T, 256, A_IM2COL, true) X(T, 256, A_HALO, false) X(T, 256, A_HALO, true)
+  X(T, 256, A_MATRIX, false) X(T, 256, A_MATRIX, true) X(T, 256, A_IM2COL, false) X(T, 256, A_IM2COL, true) X(T, 256, A_HALO, false) X(T, 256, A_HALO, true) \
+  X(T, 64, A_S2D, true)
 
 #define B200_TC3_DEFINE_TYPED(T)                                                                                                          \
   template <> void launch_tc3_typed<T>(const Tc3Args& a, int bn, int a_mode, bool ws, int grid, unsigned smem, cudaStream_t s) {           \

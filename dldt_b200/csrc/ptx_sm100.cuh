@@ -373,3 +373,13 @@ __device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1
 }
 }  // namespace ptx
 }  // namespace b200
+
+namespace b200 {
+namespace ptx {
+__device__ __forceinline__ void tma_store_5d(const void* tmap, uint32_t src_smem, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(tmap), "r"(src_smem), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+}  // namespace ptx
+}  // namespace b200

@@ -33,6 +33,11 @@ CASES = {
     "halo_28_res_fp16": (3, 128, 28, 28, 128, 3, 1, 1, True, "relu", "FP16", {}, "halo"),
     "halo_14_partial_tile": (5, 256, 14, 14, 256, 3, 1, 1, False, "relu", "BF16", {"B200_TC3_HALO": "2"}, "halo"),
     "halo_14_partial_res": (3, 128, 14, 14, 128, 3, 1, 1, True, "relu", "BF16", {"B200_NO_WS": "1", "B200_TC3_HALO": "2"}, "halo"),
+    "s2d_stem_64": (2, 3, 64, 64, 64, 7, 2, 3, False, "relu", "BF16", {}, "s2d_s2d_stem"),
+    "s2d_stem_w124_widest": (1, 3, 40, 248, 64, 7, 2, 3, False, "relu", "BF16", {}, "s2d_s2d_stem"),
+    "s2d_stem_too_wide_falls_back": (1, 3, 40, 520, 64, 7, 2, 3, False, "relu", "BF16", {}, "im2col_s2d_stem"),
+    "s2d_stem_fp16_partial_rows": (3, 3, 50, 40, 64, 7, 2, 3, False, "relu", "FP16", {}, "s2d_s2d_stem"),
+    "s2d_stem_ssd300_falls_back": (1, 3, 300, 300, 64, 7, 2, 3, False, "relu", "BF16", {}, "im2col_s2d_stem"),
     "halo_w30_clip": (2, 64, 16, 30, 128, 3, 1, 1, False, "clamp", "BF16", {}, "halo"),
 }
 

@@ -19,6 +19,11 @@ CASES = {
     "halo_28_res_nows":    (3, 128, 28, 28, 128, 3, 1, 1, True, "relu", "BF16", {"B200_NO_WS": "1"}),
     "halo_14_c256_b16":    (16, 256, 14, 14, 256, 3, 1, 1, False, "relu", "BF16", {}),
     "halo_14_partial_res": (3, 128, 14, 14, 128, 3, 1, 1, True, "relu", "BF16", {"B200_NO_WS": "1", "B200_TC3_HALO": "2"}),
+    "s2d_stem_64":         (2, 3, 64, 64, 64, 7, 2, 3, False, "relu", "BF16", {}),
+    "s2d_stem_w124":       (1, 3, 40, 248, 64, 7, 2, 3, False, "relu", "BF16", {}),
+    "s2d_stem_3seg_fallbk": (1, 3, 40, 520, 64, 7, 2, 3, False, "relu", "BF16", {}),
+    "s2d_stem_300_fallbk": (1, 3, 300, 300, 64, 7, 2, 3, False, "relu", "BF16", {}),
+    "s2d_stem_fp16_rows":  (3, 3, 50, 40, 64, 7, 2, 3, False, "relu", "FP16", {}),
     "halo_56_ws":          (2, 64, 56, 56, 64, 3, 1, 1, False, "relu", "BF16", {}),
     "halo_28":             (3, 128, 28, 28, 128, 3, 1, 1, False, "relu", "BF16", {}),
     "halo_14_c256":        (5, 256, 14, 14, 256, 3, 1, 1, False, "relu", "BF16", {}),
