@@ -277,9 +277,19 @@ def run_b200(args, rank, local_rank, world):
     n_tc = sum(1 for e in eg if e["impl"].startswith("tcgen05"))
     achieved = tc_flops / (tc_us * 1e-6) / 1e12 if tc_us > 0 else 0.0
     peak = pk["bf16_tflops_sustained"]
-    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM; %d launches/step)" % n_tc,
+    # traffic: DRAM read+write bytes per tcgen05 launch from the committed ncu pass over one step (profiles/r1_traffic.json, written
+    # from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` by tools/summarise_ncu.py; never measured under this run)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        traffic = {"dram_bytes_per_launch": tj["dram_bytes_per_launch"], "algorithmic_bytes_per_launch": tj.get("algorithmic_bytes_per_launch"),
+                   "source": tj.get("source")}
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": "conv_tc3_kernel (CTA-pair) + conv_tc2_kernel, tcgen05 implicit GEMM; all %d Convolution/FullyConnected "
+                                               "launches of a step" % n_tc,
                 "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-                "peak_source": "%s bf16 sustained" % pk["source"], "traffic": None,
+                "peak_source": "%s bf16 sustained" % pk["source"], "traffic": traffic,
                 "share_of_step": round(tc_us / all_us, 4) if all_us else None,
                 "step_achieved": round(value / world * GFLOP_PER_IMG / 1e3, 2), "step_frac": round(value / world * GFLOP_PER_IMG / 1e3 / peak, 4)}
 

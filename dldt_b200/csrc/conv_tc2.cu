@@ -188,6 +188,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  // programmatic dependent launch (see conv_tc3.cuh): the prologue above overlapped the previous kernel's drain
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
@@ -492,8 +495,20 @@ void launch_tc2(const ConvParams& p, bool bf16, cudaStream_t s) {
                         : (a.a_tma == 2 ? make_tmap_im2col(p, bf16) : a.tm_y);
   const int grid = std::min(a.num_tiles, g_sm_count > 0 ? g_sm_count : 148);
   const unsigned smem = smem_plan<BN>(p.res != nullptr, a.ws ? (p.Ktot / BK) * BN * 128 : 0).total;
-  if (conv_acts_are_clamps(p)) conv_tc2_kernel<T, BN, false><<<grid, NUM_THREADS, smem, s>>>(a);
-  else conv_tc2_kernel<T, BN, true><<<grid, NUM_THREADS, smem, s>>>(a);
+  static const bool pdl = [] { const char* e = getenv("B200_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  if (conv_acts_are_clamps(p)) cudaLaunchKernelEx(&cfg, conv_tc2_kernel<T, BN, false>, a);
+  else cudaLaunchKernelEx(&cfg, conv_tc2_kernel<T, BN, true>, a);
 }
 
 }  // namespace

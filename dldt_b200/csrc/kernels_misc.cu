@@ -450,27 +450,34 @@ __global__ void convert4_kernel(const S* __restrict__ src, int slayout, D* __res
   stf<D>(dst, i, v);
 }
 // One thread per 16-channel block: gathers the 2x2 pixel patch (zero outside the image), converts, writes 32 bytes.
-template <typename S, typename D>
-__global__ void ingest_s2d_kernel(const S* __restrict__ src, int slayout, D* __restrict__ dst, int N, int C, int H, int W, int pt, int pl, int Hb,
-                                  int Wb) {
-  const int64_t total = (int64_t)N * Hb * Wb;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+template <typename S, typename D, int C>
+__global__ void __launch_bounds__(256) ingest_s2d_kernel(const S* __restrict__ src, int slayout, D* __restrict__ dst, int N, int H, int W, int pt, int pl,
+                                                         int Hb, int Wb) {
+  // one thread = one block pixel (2x2 input pixels x C channels -> 16 output channels, zero padded); 32-bit index math, C known at compile
+  // time so that the 16 outputs stay in registers (the runtime-C version kept them in local memory and ran at 1/4 of the HBM rate)
+  const uint32_t total = (uint32_t)N * (uint32_t)Hb * (uint32_t)Wb;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int wb = (int)(i % Wb);
-  const int64_t t = i / Wb;
-  const int hb = (int)(t % Hb), n = (int)(t / Hb);
-  __align__(16) D out[16];
+  const int wb = (int)(i % (uint32_t)Wb);
+  const uint32_t t = i / (uint32_t)Wb;
+  const int hb = (int)(t % (uint32_t)Hb), n = (int)(t / (uint32_t)Hb);
+  float v[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) stf<D>(out, k, 0.f);
+  for (int k = 0; k < 16; ++k) v[k] = 0.f;
 #pragma unroll
   for (int dr = 0; dr < 2; ++dr)
 #pragma unroll
     for (int ds = 0; ds < 2; ++ds) {
       const int h = 2 * hb + dr - pt, w = 2 * wb + ds - pl;
-      if ((unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W)
-        for (int c = 0; c < C; ++c) stf<D>(out, (dr * 2 + ds) * C + c, ldf<S>(src, phys_index(slayout, n, c, h, w, C, H, W)));
+      if ((unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[(dr * 2 + ds) * C + c] = ldf<S>(src, phys_index(slayout, n, c, h, w, C, H, W));
+      }
     }
-  uint4* o = reinterpret_cast<uint4*>(dst + i * 16);
+  __align__(16) D out[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) stf<D>(out, k, v[k]);
+  uint4* o = reinterpret_cast<uint4*>(dst + (size_t)i * 16);
   o[0] = reinterpret_cast<const uint4*>(out)[0];
   o[1] = reinterpret_cast<const uint4*>(out)[1];
 }
@@ -681,8 +688,11 @@ static void ingest_s2d_dst(const void* src, int slayout, void* dst, int ddtype, 
   const int64_t total = (int64_t)N * Hb * Wb;
   if (total == 0) return;
   unsigned g = grid_for(total, 256);
-  if (ddtype == B200_BF16) ingest_s2d_kernel<S, __nv_bfloat16><<<g, 256, 0, s>>>((const S*)src, slayout, (__nv_bfloat16*)dst, N, C, H, W, pt, pl, Hb, Wb);
-  else if (ddtype == B200_F16) ingest_s2d_kernel<S, __half><<<g, 256, 0, s>>>((const S*)src, slayout, (__half*)dst, N, C, H, W, pt, pl, Hb, Wb);
+  B200_CHECK(total < ((int64_t)1 << 31), B200_ERR_UNSUPPORTED, "ingest_s2d: tensor too large");
+#define B200_INGEST(D, C_) ingest_s2d_kernel<S, D, C_><<<g, 256, 0, s>>>((const S*)src, slayout, (D*)dst, N, H, W, pt, pl, Hb, Wb)
+#define B200_INGEST_C(D) do { if (C == 1) B200_INGEST(D, 1); else if (C == 2) B200_INGEST(D, 2); else if (C == 3) B200_INGEST(D, 3); else B200_INGEST(D, 4); } while (0)
+  if (ddtype == B200_BF16) B200_INGEST_C(__nv_bfloat16);
+  else if (ddtype == B200_F16) B200_INGEST_C(__half);
   else B200_THROW(B200_ERR_UNSUPPORTED, "ingest_s2d: destination must be bf16/f16");
 }
 void launch_ingest_s2d(const void* src, int sdtype, int slayout, void* dst, int ddtype, int N, int C, int H, int W, int pt, int pl, int Hb, int Wb,
