@@ -73,6 +73,10 @@ struct FusedConv {
   int res_value = -1;
   int out_value = -1;            // value produced by the last absorbed node
   int emit_at = -1;              // node id at whose position the kernel is emitted
+  // K-concatenated projection shortcut (fold_shortcuts): a second 1x1 convolution whose output was this one's residual
+  int dual_root = -1;
+  std::vector<float> dual_scale, dual_shift;
+  std::string dual_fused;
 };
 struct FusedMvn {
   int root = -1;
@@ -177,6 +181,7 @@ class Lowerer {
 
   // ---- passes ----
   void fuse();
+  void fold_shortcuts();
   bool per_channel_const(int value, int64_t C, bool matmul_style, std::vector<float>& out) const;
   void lower_node(const Node& n);
   void lower_conv(const FusedConv& f);
@@ -192,7 +197,7 @@ class Lowerer {
   void lower_detection(const Node& n);
   void conv_launch_step(const std::string& name, const std::string& type, const std::string& fused, ConvParams p, BufRef x, BufRef w,
                         BufRef bias, BufRef res, BufRef y, const LTensor* tx, const LTensor* tres, const LTensor* ty, double flops,
-                        double bytes, bool tc);
+                        double bytes, bool tc, BufRef x2 = BufRef(), const LTensor* tx2 = nullptr);
 };
 
 bool Lowerer::prefers_nhwc8(int value) const {
@@ -498,12 +503,72 @@ void Lowerer::fuse() {
       felt_[f.emit_at] = f;
     }
   }
+  fold_shortcuts();
 }
+
+// ResNet downsampling block: out = ReLU(conv_c(b) + conv_proj(x)), both 1x1 with folded BN.  fuse() made conv_proj its own kernel and
+// its output conv_c's residual: a 100-400 MB tensor written once and read once.  As ONE GEMM over concatenated K,
+//   [b | x at the shortcut's stride] * [Wc ; Wproj]^T + (shift_c + shift_proj),
+// the shortcut kernel, its output tensor and the residual read disappear (conv_tc3's second activation source, ConvParams::x2).
+// The sum is formed in the fp32 accumulator instead of after rounding the shortcut to bf16.  B200_FOLD_SHORTCUT=0 turns it off.
+void Lowerer::fold_shortcuts() {
+  const char* off = getenv("B200_FOLD_SHORTCUT");
+  if (!use_tc_ || (off && off[0] == '0')) return;
+  auto pointwise = [&](const Node& n, bool stride1) {
+    if (n.op != B200_OP_CONVOLUTION) return false;
+    const Shape& w = val(n.inputs[1]).shape;
+    if (w.size() != 4 || w[2] != 1 || w[3] != 1 || w[1] % 64 != 0 || w[0] % 64 != 0) return false;
+    if (n.i[2] != 1 || n.i[3] != 1 || n.i[4] != 0 || n.i[5] != 0 || n.i[6] != 0 || n.i[7] != 0) return false;
+    return !stride1 || (n.i[0] == 1 && n.i[1] == 1);
+  };
+  std::vector<int> erase;
+  for (auto& kv : fconv_) {
+    FusedConv& f = kv.second;
+    if (f.res_value < 0 || f.dual_root >= 0 || f.act1.kind != ACT_NONE) continue;
+    const Node& n = node(f.root);
+    FusedConv* g = nullptr;
+    for (auto& kv2 : fconv_)
+      if (kv2.second.out_value == f.res_value && &kv2.second != &f) g = &kv2.second;
+    if (!g || g->res_value >= 0 || g->dual_root >= 0 || g->act1.kind != ACT_NONE || g->act2.kind != ACT_NONE) continue;
+    const Node& m = node(g->root);
+    if (val(g->out_value).consumers.size() != 1 || val(m.outputs[0]).shape != val(n.outputs[0]).shape) continue;
+    // either of the two convolutions may be the one that absorbed the Add (whichever comes later in the graph); the stride-1 one becomes
+    // the main source (plain activation matrix), the other one (any stride) the second source
+    const bool f_main = pointwise(n, true) && pointwise(m, false);
+    const bool g_main = !f_main && pointwise(m, true) && pointwise(n, false);
+    if (!f_main && !g_main) continue;
+    std::string other_names = (f_main ? m : n).name;
+    if (f_main) {
+      for (int a : g->absorbed) other_names += "," + node(a).name;
+      f.dual_root = g->root;
+      f.dual_scale = g->scale;
+      f.dual_shift = g->shift;
+    } else {
+      // f's own per-channel folds stay with its convolution (now the second source); the Add / activation nodes it absorbed stay absorbed
+      f.dual_root = f.root;
+      f.dual_scale = f.scale;
+      f.dual_shift = f.shift;
+      f.root = g->root;
+      f.scale = g->scale;
+      f.shift = g->shift;
+      std::vector<int> ab = g->absorbed;
+      ab.insert(ab.end(), f.absorbed.begin(), f.absorbed.end());
+      f.absorbed = ab;
+    }
+    f.dual_fused = other_names;
+    f.act1 = f.act2;
+    f.act2 = ActSpec();
+    f.res_value = -1;
+    erase.push_back(g->emit_at);
+  }
+  for (int k : erase) fconv_.erase(k);
+}
+
 
 // --------------------------------------------------------------------------------------------------
 void Lowerer::conv_launch_step(const std::string& name, const std::string& type, const std::string& fused, ConvParams p, BufRef x, BufRef w,
                                BufRef bias, BufRef res, BufRef y, const LTensor* tx, const LTensor* tres, const LTensor* ty, double flops,
-                               double bytes, bool tc) {
+                               double bytes, bool tc, BufRef x2, const LTensor* tx2) {
   Step s;
   s.name = name; s.type = type; s.fused = fused; s.flops = flops; s.bytes = bytes;
   const int dt = cd_;
@@ -517,8 +582,13 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
     const char* force3 = getenv("B200_TC3");
     v2 = conv_tc2_supported(p) && !(force_v1 && force_v1[0] == '1');
     v3 = v2 && conv_tc3_preferred(p);
+    const bool kcat = p.K2 > 0;      // second activation source: the pair kernel is the only implementation
+    if (kcat) {
+      B200_CHECK(conv_tc3_supported(p), B200_ERR_UNSUPPORTED, "K-concatenated convolution '" << name << "' needs the pair kernel");
+      v2 = true; v3 = true;
+    }
     // large launches: both persistent kernels apply, the first request measures which one is faster for this shape
-    both = v3 && !(tune && tune[0] == '0') && !(force3 && force3[0] == '1');
+    both = v3 && !(tune && tune[0] == '0') && !(force3 && force3[0] == '1') && (!kcat || conv_tc3_preferred(p));
     impl2 = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_128x" + std::to_string(bn) + "x64" +
             (v2 ? (conv_tc2_a_is_matrix(p) ? "_persistent_tma" : (conv_tc2_a_is_im2col(p) ? "_persistent_im2col" : "_persistent_gather")) : "");
     if (v3) {
@@ -530,6 +600,7 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
     s.impl = "simt_fp32_128x64x16";
   }
   const bool has_res = res.space != SP_NONE;
+  const bool has_x2 = p.K2 > 0;
   const char* no_alt = getenv("B200_NO_ALTERNATE");
   // opposite to the direction in which the producer of x wrote it (kernels other than conv_tc2 write first-to-last)
   {
@@ -545,6 +616,7 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
       q.x = c.ptr(x); q.w = c.ptr(w); q.bias = reinterpret_cast<const float*>(c.ptr(bias));
       q.res = has_res ? c.ptr(res) : nullptr;
       q.y = c.ptr(y);
+      q.x2 = has_x2 ? c.ptr(x2) : nullptr;
       const bool use3 = which >= 3 || (which == 0 && v3);
       if (tc && use3) launch_conv_tc3(q, dt, which > 3 ? which : bn3, (cudaStream_t)c.stream);
       else if (tc && v2) launch_conv_tc2(q, dt, bn, (cudaStream_t)c.stream);
@@ -561,9 +633,9 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
       std::string nm = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_pair256x" + std::to_string(b) + "x64_" + conv_tc3_mode_name(p);
       s.alts.emplace_back(nm, make_launch(b));     // which > 3: explicit N tile of the pair kernel
     }
-    s.alts.emplace_back(impl2, make_launch(2));
+    if (!has_x2) s.alts.emplace_back(impl2, make_launch(2));
   }
-  emit(std::move(s), {tx, tres}, {ty});
+  emit(std::move(s), {tx, tres, tx2}, {ty});
 }
 
 void Lowerer::lower_conv(const FusedConv& f) {
@@ -680,7 +752,17 @@ void Lowerer::lower_conv(const FusedConv& f) {
   const bool tc = use_tc_;
   const int bn = tc ? conv_tc_pick_bn((int)Cout_p) : 64;
   const int64_t Cout_alloc = round_up(Cout_p, bn);
-  const int64_t Ktot = round_up(kh * kw * Cin_p, 64);
+  // K-concatenated projection shortcut (fold_shortcuts): K = [this conv's channels | the shortcut's input channels]
+  const Node* dn = f.dual_root >= 0 ? &node(f.dual_root) : nullptr;
+  LTensor x2;
+  int64_t K2 = 0;
+  if (dn) {
+    x2 = get(dn->inputs[0], L_NHWC8);
+    K2 = round_up(x2.shape[1], 8);
+    B200_CHECK(tc && K2 % 64 == 0 && Cin_p % 64 == 0 && kh == 1 && kw == 1, B200_ERR_UNSUPPORTED, "shortcut folding: unsupported geometry");
+  }
+  const int64_t K1 = round_up(kh * kw * Cin_p, 64);
+  const int64_t Ktot = K1 + K2;
   std::vector<uint8_t> wp((size_t)(Cout_alloc * Ktot) * dtype_size(cd_), 0);
   // K order = (filter row, filter col, padded input channel); grouped convs become block diagonal
   for (int64_t o = 0; o < Cout; ++o) {
@@ -696,12 +778,22 @@ void Lowerer::lower_conv(const FusedConv& f) {
   }
   std::vector<float> bias(Cout_alloc, 0.f);
   for (int64_t o = 0; o < Cout; ++o) bias[o] = f.shift[o];
+  if (dn) {
+    std::vector<float> w2 = const_floats(dn->inputs[1]);   // [Cout][C2][1][1]
+    const int64_t C2 = x2.shape[1];
+    for (int64_t o = 0; o < Cout; ++o) {
+      for (int64_t c = 0; c < C2; ++c) store_float(wp.data(), o * Ktot + K1 + c, w2[o * C2 + c] * f.dual_scale[o], cd_);
+      bias[o] += f.dual_shift[o];
+    }
+    fused += "," + f.dual_fused;
+  }
   BufRef wref = weights_ref(add_weights(wp.data(), (int64_t)wp.size()));
   BufRef bref = add_f32_vector(bias);
   LTensor res;
   BufRef rref;
   if (f.res_value >= 0) { res = get(f.res_value, L_NHWC8); rref = res.buf; }
   ConvParams p;
+  if (dn) { p.K2 = (int)K2; p.H2 = (int)x2.shape[2]; p.W2 = (int)x2.shape[3]; p.sh2 = dn->i[0]; p.sw2 = dn->i[1]; }
   p.N = (int)xs[0]; p.H = (int)xs[2]; p.W = (int)xs[3]; p.Cin_p = (int)Cin_p; p.Ho = (int)os[2]; p.Wo = (int)os[3]; p.Cout_p = (int)Cout_p;
   p.kh = (int)kh; p.kw = (int)kw; p.sh = n.i[0]; p.sw = n.i[1]; p.dh = n.i[2]; p.dw = n.i[3]; p.pt = n.i[4]; p.pl = n.i[5];
   p.M = (int)Mrows; p.Ktot = (int)Ktot; p.Cout_alloc = (int)Cout_alloc; p.ldy = (int)Cout_p;
@@ -711,8 +803,13 @@ void Lowerer::lower_conv(const FusedConv& f) {
   double flops = 2.0 * Mrows * Cout * (Cin / G) * kh * kw;
   double bytes = (double)x.bytes() + (double)out.bytes() + (double)Cout * (Cin / G) * kh * kw * dtype_size(cd_) +
                  (f.res_value >= 0 ? (double)out.bytes() : 0);
+  if (dn) {
+    flops += 2.0 * Mrows * Cout * x2.shape[1];
+    // the shortcut reads every sh2*sw2-th pixel of x2
+    bytes += (double)x2.bytes() / (dn->i[0] * dn->i[1]) + (double)Cout * x2.shape[1] * dtype_size(cd_);
+  }
   conv_launch_step(out_name, "Convolution", fused, p, x.buf, wref, bref, rref, out.buf, &x, f.res_value >= 0 ? &res : nullptr, &out, flops,
-                   bytes, tc);
+                   bytes, tc, dn ? x2.buf : BufRef(), dn ? &x2 : nullptr);
   set(f.out_value, out);
 }
 

@@ -97,6 +97,7 @@ bool s2d_ok(const ConvParams& p) {
 
 int a_mode_of(const ConvParams& p) {
   if (s2d_ok(p)) return A_S2D;
+  if (p.K2 > 0) return (p.kh == 1 && p.kw == 1 && p.sh == 1 && p.sw == 1 && p.pt == 0 && p.pl == 0 && p.Cin_p % 64 == 0 && p.K2 % 64 == 0 && p.x_sw == 0) ? A_MATRIX : 0;
   if (conv_tc2_a_is_matrix(p) && p.Cin_p % 64 == 0) return A_MATRIX;
   if (halo_ok(p)) return A_HALO;
   if (conv_tc2_a_is_im2col(p)) return A_IM2COL;
@@ -177,7 +178,15 @@ void launch_tc3(const ConvParams& p, bool bf16, int bn, int a_mode, cudaStream_t
     a.tm_y = make_tmap_2d(p.y, bf16, (uint64_t)p.Cout_p, (uint64_t)p.M, (uint64_t)p.ldy * 2, 64, BM);
     a.tm_r = p.res ? make_tmap_2d(p.res, bf16, (uint64_t)p.Cout_p, (uint64_t)p.M, (uint64_t)p.ldy * 2, 64, BM) : a.tm_y;
     a.tm_a = a_mode == A_MATRIX ? make_tmap_2d(p.x, bf16, (uint64_t)p.Cin_p, (uint64_t)p.M, (uint64_t)p.Cin_p * 2, BK, BM) : make_tmap_im2col(p, bf16);
+    if (p.K2 > 0) {
+      B200_CHECK(a_mode == A_MATRIX && p.K2 % BK == 0 && p.Cin_p + p.K2 == p.Ktot, B200_ERR_INVALID, "conv_tc3: bad second-source geometry");
+      ConvParams p2;                     // the shortcut as a 1x1 strided convolution over x2, same output pixels
+      p2.x = p.x2; p2.N = p.N; p2.H = p.H2; p2.W = p.W2; p2.Cin_p = p.K2; p2.Ho = p.Ho; p2.Wo = p.Wo;
+      p2.kh = p2.kw = 1; p2.sh = p.sh2; p2.sw = p.sw2; p2.dh = p2.dw = 1; p2.pt = p2.pl = 0;
+      a.tm_a2 = make_tmap_im2col(p2, bf16);
+    }
   }
+  a.nkb1 = (p.K2 > 0 ? p.Cin_p : p.Ktot) / BK;
   const int grid = 2 * std::min(a.num_tiles, pair_slots());
   const unsigned smem = plan3(bn, p.res != nullptr, ws ? (p.Ktot / BK) * (bn / 2) * 128 : 0, a_mode, a.rows_p, p.Cout_alloc, p.Ktot / BK).total;
   launch_tc3_typed<T>(a, bn, a_mode, ws, grid, smem, s);
@@ -239,7 +248,7 @@ bool conv_tc3_preferred(const ConvParams& p) {
 
 const char* conv_tc3_mode_name(const ConvParams& p) {
   switch (a_mode_of(p)) {
-    case A_MATRIX: return "tma";
+    case A_MATRIX: return p.K2 > 0 ? "tma_kcat" : "tma";
     case A_HALO: return "halo";
     case A_IM2COL: return "im2col";
     case A_S2D: return "s2d";

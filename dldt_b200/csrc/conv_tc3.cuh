@@ -86,6 +86,8 @@ struct Tc3Args {
   CUtensorMap tm_w;   // packed weights [Cout_alloc][Ktot], box {64, BN/2}
   CUtensorMap tm_y;   // output: [M][Cout_p] box {64, 128}; A_HALO: {C, W, H, N} box {64, P, 128/P, 1}
   CUtensorMap tm_r;   // residual, same geometry as the output
+  CUtensorMap tm_a2;  // A_MATRIX with a second source (ConvParams::x2): im2col-mode map {K2, W2, H2, N}, 1x1 window, stride (sw2, sh2)
+  int nkb1;           // k-blocks served by tm_a; the rest come from tm_a2 (== Ktot / 64 when there is no second source)
   ConvParams p;
   EpiAct e1, e2;
   int gen;                  // activations outside the clamp family: generic table in the epilogue (selects the GEN instantiation)
@@ -440,6 +442,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
           __syncwarp();
         }
       }
+      int bn2 = 0, bh2 = 0, bw2 = 0;
+      if (AMODE == A_MATRIX && args.nkb1 < n_ablk) {      // base pixel of this tile in the second source
+        bn2 = tp.m0 / HoWo;
+        const int rem = tp.m0 - bn2 * HoWo;
+        const int ho = rem / p.Wo;
+        bh2 = ho * p.sh2;
+        bw2 = (rem - ho * p.Wo) * p.sw2;
+      }
       int chunk = 0, fr = 0, fs = 0;
       for (int ab = 0; ab < n_ablk; ++ab) {
         ptx::mbar_wait(&emptyA[sa], pha ^ 1u);
@@ -448,7 +458,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
           const uint32_t bar = fullA_leader + (uint32_t)sa * 8u;
           if (leader) ptx::mbar_arrive_expect_tx(&fullA[sa], 2u * a_tx);
           if (AMODE == A_MATRIX) {
-            ptx::tma_load_2d_pair_hint(a_dst, &args.tm_a, bar, ab * BK, tp.m0, args.a_policy);
+            if (ab < args.nkb1) ptx::tma_load_2d_pair_hint(a_dst, &args.tm_a, bar, ab * BK, tp.m0, args.a_policy);
+            else ptx::tma_load_im2col_4d_pair(a_dst, &args.tm_a2, bar, (ab - args.nkb1) * BK, bw2, bh2, bn2, 0u, 0u);   // strided pixels of x2
           } else if (AMODE == A_IM2COL) {
             ptx::tma_load_im2col_4d_pair(a_dst, &args.tm_a, bar, chunk * BK, bw, bh, bn, (uint32_t)(fs * p.dw), (uint32_t)(fr * p.dh));
           } else if (AMODE == A_S2D) {

@@ -35,6 +35,11 @@ struct ConvParams {
   // Walk the output tiles last-to-first.  The compiler alternates the direction from one kernel to the next so that a kernel starts on
   // the rows its producer wrote last, which are still resident in the 126 MB L2 (the tensors themselves are 100-400 MB at batch 256).
   int reverse = 0;
+  // Second activation source of a K-concatenated GEMM (conv_tc3 only): a 1x1 convolution over x2 [N, H2, W2, K2] with stride (sh2, sw2)
+  // producing the same [N, Ho, Wo] pixels.  K blocks [Ktot - K2, Ktot) of the packed weights belong to it.  Used to fold the projection
+  // shortcut of a ResNet downsampling block into the block's last 1x1 convolution: conv_c(b) + conv_proj(x) = [b | x_strided] * [Wc ; Wp].
+  const void* x2 = nullptr;
+  int K2 = 0, H2 = 0, W2 = 0, sh2 = 1, sw2 = 1;
   int batch = 1;               // blockIdx.z batches (batched MatMul); strides in elements
   int64_t x_bs = 0, w_bs = 0, y_bs = 0;
 };

@@ -97,3 +97,39 @@ def test_autotuned_selection_is_one_of_the_candidates_and_matches_oracle(monkeyp
     # a second request of the same network reuses the decision and gives the same bits
     got2 = list(net.create_infer_request().infer({"Parameter_0": xin}).values())[0]
     assert np.array_equal(got, got2)
+
+
+def _bottleneck(f, x, cin, mid, cout, stride, rng, bn_on_shortcut):
+    def conv(v, o, c, k, s, p, name):
+        w = (rng.standard_normal((o, c, k, k)) / np.sqrt(c * k * k)).astype(np.float32)
+        return f.add(f.convolution(v, w, (s, s), (p, p), (p, p), (1, 1)), rng.standard_normal((1, o, 1, 1)).astype(np.float32) * 0.1)
+    a = f.relu(conv(x, mid, cin, 1, 1, 0, "a"))
+    b = f.relu(conv(a, mid, mid, 3, stride, 1, "b"))
+    c = conv(b, cout, mid, 1, 1, 0, "c")
+    sc = conv(x, cout, cin, 1, stride, 0, "proj")
+    if bn_on_shortcut:   # a per-channel scale after the shortcut conv is folded into its weights before the K concatenation
+        sc = f.multiply(sc, rng.uniform(0.5, 1.5, (1, cout, 1, 1)).astype(np.float32))
+    return f.relu(f.add(c, sc))
+
+
+@pytest.mark.parametrize("cin,mid,cout,stride,hw,bn", [(64, 64, 256, 1, 16, False), (128, 64, 256, 2, 16, True), (256, 128, 512, 2, 14, False)])
+def test_projection_shortcut_is_folded_into_the_last_conv(cin, mid, cout, stride, hw, bn, monkeypatch):
+    # ResNet downsampling block: conv_c(b) + conv_proj(x) runs as ONE GEMM over concatenated K (compile.cu fold_shortcuts)
+    monkeypatch.delenv("B200_TC3", raising=False)
+    rng = np.random.default_rng(cin + stride)
+    f = Function("block0")
+    x = f.parameter((3, cin, hw, hw))
+    f.result(_bottleneck(f, x, cin, mid, cout, stride, rng, bn))
+    xin = rng.standard_normal((3, cin, hw, hw)).astype(np.float32)
+    ref = list(interp.run(f, {"Parameter_0": xin}).values())[0]
+    net = Core().load_network(f, "B200", {"B200_INFERENCE_PRECISION": "BF16"})
+    got = list(net.create_infer_request().infer({"Parameter_0": xin}).values())[0]
+    convs = [e["impl"] for e in net.get_exec_graph_info() if e["type"] == "Convolution"]
+    assert len(convs) == 3 and convs[-1].endswith("tma_kcat"), convs
+    assert rel_l2(got, ref) < 1e-2
+    # and with the folding off the same graph gives four kernels and the same answer within bf16 rounding of the shortcut tensor
+    monkeypatch.setenv("B200_FOLD_SHORTCUT", "0")
+    net2 = Core().load_network(f, "B200", {"B200_INFERENCE_PRECISION": "BF16"})
+    got2 = list(net2.create_infer_request().infer({"Parameter_0": xin}).values())[0]
+    assert len([e for e in net2.get_exec_graph_info() if e["type"] == "Convolution"]) == 4
+    assert rel_l2(got2, ref) < 1e-2 and rel_l2(got, got2) < 1e-2

@@ -23,14 +23,23 @@ def test_resnet50_schedule():
     net = dry(zoo.resnet50(batch=256))
     eg = net.get_exec_graph_info()
     k = kinds(net)
-    # 53 convs with BN/ReLU/residual folded in, max pool, global avg pool, FC (+bias)
-    assert k == {"Convolution": 53, "Pooling": 2, "FullyConnected": 1}
+    # 53 convs with BN/ReLU/residual folded in, of which the 4 projection shortcuts ride on the last 1x1 of their block as extra K
+    # (fold_shortcuts); max pool, global avg pool, FC (+bias)
+    assert k == {"Convolution": 49, "Pooling": 2, "FullyConnected": 1}
+    assert sum(1 for e in eg if e["impl"].endswith("tma_kcat")) == 4
     assert all(e["impl"].startswith("tcgen05_bf16") for e in eg if e["type"] in ("Convolution", "FullyConnected"))
     assert sum(1 for e in eg if e["type"] == "Convolution" and any("add" in n.lower() for n in e["fused"])) >= 16  # residual sums
     assert abs(net.stat("flops") / 256 / 1e9 - 8.178) < 0.01
     assert net.stat("arena_bytes") < 2.0e9                              # conv1 out (411 MB) + pool + block buffers, reused
     assert [i[0] for i in net.inputs] == ["data"] and net.inputs[0][1] == (256, 3, 224, 224)
     assert net.outputs[0][1] == (256, 1000)
+
+
+def test_resnet50_schedule_without_shortcut_folding(monkeypatch):
+    monkeypatch.setenv("B200_FOLD_SHORTCUT", "0")
+    net = dry(zoo.resnet50(batch=256))
+    assert kinds(net) == {"Convolution": 53, "Pooling": 2, "FullyConnected": 1}
+    assert abs(net.stat("flops") / 256 / 1e9 - 8.178) < 0.01
 
 
 def test_resnet50_fp32_uses_cuda_core_conv():
