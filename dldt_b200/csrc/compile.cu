@@ -77,6 +77,11 @@ struct FusedConv {
   int dual_root = -1;
   std::vector<float> dual_scale, dual_shift;
   std::string dual_fused;
+  // the next block's 1x1 reduce convolution, computed from this one's output inside the same kernel (fold_next_reduce, conv_tc3f.cu)
+  int next_root = -1, next_out_value = -1;
+  std::vector<float> next_scale, next_shift;
+  ActSpec next_act;
+  std::string next_fused;
 };
 struct FusedMvn {
   int root = -1;
@@ -182,6 +187,7 @@ class Lowerer {
   // ---- passes ----
   void fuse();
   void fold_shortcuts();
+  void fold_next_reduce();
   bool per_channel_const(int value, int64_t C, bool matmul_style, std::vector<float>& out) const;
   void lower_node(const Node& n);
   void lower_conv(const FusedConv& f);
@@ -197,7 +203,8 @@ class Lowerer {
   void lower_detection(const Node& n);
   void conv_launch_step(const std::string& name, const std::string& type, const std::string& fused, ConvParams p, BufRef x, BufRef w,
                         BufRef bias, BufRef res, BufRef y, const LTensor* tx, const LTensor* tres, const LTensor* ty, double flops,
-                        double bytes, bool tc, BufRef x2 = BufRef(), const LTensor* tx2 = nullptr);
+                        double bytes, bool tc, BufRef x2 = BufRef(), const LTensor* tx2 = nullptr, BufRef w2 = BufRef(), BufRef bias2 = BufRef(),
+                        BufRef z = BufRef(), const LTensor* tz = nullptr);
 };
 
 bool Lowerer::prefers_nhwc8(int value) const {
@@ -562,13 +569,64 @@ void Lowerer::fold_shortcuts() {
     erase.push_back(g->emit_at);
   }
   for (int k : erase) fconv_.erase(k);
+  fold_next_reduce();
 }
 
+
+// Bottleneck boundary: the expand convolution of block i (+ residual / folded shortcut, ReLU) produces Y, which is read by the reduce
+// convolution of block i+1 (1x1, stride 1) and, much later, as that block's residual.  conv_tc3f computes the reduce convolution from the
+// Y slabs while they sit in shared memory on their way to the TMA store, so Y is written once and read once (as the residual) instead of
+// twice.  B200_FUSE_NEXT=1 turns it on (see below).
+void Lowerer::fold_next_reduce() {
+  // Measured on B200 (profiles/README.md, calls u-aa): correct, but at parity with / slightly slower than the two separate kernels at
+  // ResNet-50 b256 (3.40 vs 3.14 ms per step): the N tile drops to 128 (TMEM: two Y accumulators + Z), the operand ring to 3 stages, and
+  // every slab adds a cross-CTA hand-shake.  Off by default until it wins; B200_FUSE_NEXT=1 turns it on.
+  const char* on = getenv("B200_FUSE_NEXT");
+  if (!use_tc_ || !(on && on[0] == '1')) return;
+  auto pointwise1 = [&](const Node& n) {
+    if (n.op != B200_OP_CONVOLUTION) return false;
+    const Shape& w = val(n.inputs[1]).shape;
+    return w.size() == 4 && w[2] == 1 && w[3] == 1 && w[1] % 64 == 0 && w[0] % 64 == 0 && n.i[0] == 1 && n.i[1] == 1 && n.i[2] == 1 && n.i[3] == 1 &&
+           n.i[4] == 0 && n.i[5] == 0 && n.i[6] == 0 && n.i[7] == 0;
+  };
+  std::vector<int> erase;
+  for (auto& kv : fconv_) {
+    FusedConv& f = kv.second;
+    if (f.next_root >= 0) continue;
+    const Node& n = node(f.root);
+    if (!pointwise1(n)) continue;
+    const int64_t Cc = val(n.inputs[1]).shape[0];
+    if (Cc % 128 != 0 || Cc > 3072) continue;
+    FusedConv* a = nullptr;
+    for (auto& kv2 : fconv_) {
+      FusedConv& c = kv2.second;
+      if (&c == &f || c.res_value >= 0 || c.dual_root >= 0 || c.next_root >= 0 || c.act2.kind != ACT_NONE) continue;
+      const Node& cn = node(c.root);
+      if (!pointwise1(cn) || cn.inputs[0] != f.out_value) continue;
+      const int64_t Ca = val(cn.inputs[1]).shape[0];
+      if (Ca != 64 && Ca != 128 && Ca != 256) continue;
+      bool taken = false;
+      for (int e : erase) taken = taken || e == c.emit_at;
+      if (!taken) { a = &c; break; }
+    }
+    if (!a) continue;
+    const Node& an = node(a->root);
+    f.next_root = a->root;
+    f.next_out_value = a->out_value;
+    f.next_scale = a->scale;
+    f.next_shift = a->shift;
+    f.next_act = a->act1;
+    f.next_fused = an.name;
+    for (int x : a->absorbed) f.next_fused += "," + node(x).name;
+    erase.push_back(a->emit_at);
+  }
+  for (int k : erase) fconv_.erase(k);
+}
 
 // --------------------------------------------------------------------------------------------------
 void Lowerer::conv_launch_step(const std::string& name, const std::string& type, const std::string& fused, ConvParams p, BufRef x, BufRef w,
                                BufRef bias, BufRef res, BufRef y, const LTensor* tx, const LTensor* tres, const LTensor* ty, double flops,
-                               double bytes, bool tc, BufRef x2, const LTensor* tx2) {
+                               double bytes, bool tc, BufRef x2, const LTensor* tx2, BufRef w2, BufRef bias2, BufRef z, const LTensor* tz) {
   Step s;
   s.name = name; s.type = type; s.fused = fused; s.flops = flops; s.bytes = bytes;
   const int dt = cd_;
@@ -582,13 +640,15 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
     const char* force3 = getenv("B200_TC3");
     v2 = conv_tc2_supported(p) && !(force_v1 && force_v1[0] == '1');
     v3 = v2 && conv_tc3_preferred(p);
-    const bool kcat = p.K2 > 0;      // second activation source: the pair kernel is the only implementation
+    const bool chained = p.N2 > 0;   // a second GEMM rides on this one's output slabs: conv_tc3f is the only implementation
+    if (chained) B200_CHECK(conv_tc3f_supported(p), B200_ERR_UNSUPPORTED, "chained convolution '" << name << "' needs conv_tc3f");
+    const bool kcat = p.K2 > 0 && !chained;      // second activation source: the pair kernel is the only implementation
     if (kcat) {
       B200_CHECK(conv_tc3_supported(p), B200_ERR_UNSUPPORTED, "K-concatenated convolution '" << name << "' needs the pair kernel");
       v2 = true; v3 = true;
     }
     // large launches: both persistent kernels apply, the first request measures which one is faster for this shape
-    both = v3 && !(tune && tune[0] == '0') && !(force3 && force3[0] == '1') && (!kcat || conv_tc3_preferred(p));
+    both = v3 && !chained && !(tune && tune[0] == '0') && !(force3 && force3[0] == '1') && (!kcat || conv_tc3_preferred(p));
     impl2 = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_128x" + std::to_string(bn) + "x64" +
             (v2 ? (conv_tc2_a_is_matrix(p) ? "_persistent_tma" : (conv_tc2_a_is_im2col(p) ? "_persistent_im2col" : "_persistent_gather")) : "");
     if (v3) {
@@ -596,6 +656,8 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
       impl3 = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_pair256x" + std::to_string(bn3) + "x64_" + conv_tc3_mode_name(p);
     }
     s.impl = v3 ? impl3 : impl2;
+    if (chained)
+      s.impl = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_pair256x128x64_tma" + (p.K2 > 0 ? "_kcat" : "") + "+1x1x" + std::to_string(p.N2);
   } else {
     s.impl = "simt_fp32_128x64x16";
   }
@@ -617,6 +679,11 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
       q.res = has_res ? c.ptr(res) : nullptr;
       q.y = c.ptr(y);
       q.x2 = has_x2 ? c.ptr(x2) : nullptr;
+      if (p.N2 > 0) {
+        q.w2 = c.ptr(w2); q.bias2 = reinterpret_cast<const float*>(c.ptr(bias2)); q.z = c.ptr(z);
+        launch_conv_tc3f(q, dt, (cudaStream_t)c.stream);
+        return;
+      }
       const bool use3 = which >= 3 || (which == 0 && v3);
       if (tc && use3) launch_conv_tc3(q, dt, which > 3 ? which : bn3, (cudaStream_t)c.stream);
       else if (tc && v2) launch_conv_tc2(q, dt, bn, (cudaStream_t)c.stream);
@@ -635,7 +702,7 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
     }
     if (!has_x2) s.alts.emplace_back(impl2, make_launch(2));
   }
-  emit(std::move(s), {tx, tres, tx2}, {ty});
+  emit(std::move(s), {tx, tres, tx2}, {ty, tz});
 }
 
 void Lowerer::lower_conv(const FusedConv& f) {
@@ -808,9 +875,31 @@ void Lowerer::lower_conv(const FusedConv& f) {
     // the shortcut reads every sh2*sw2-th pixel of x2
     bytes += (double)x2.bytes() / (dn->i[0] * dn->i[1]) + (double)Cout * x2.shape[1] * dtype_size(cd_);
   }
+  BufRef w2ref, b2ref;
+  LTensor z;
+  if (f.next_root >= 0) {
+    const Node& an = node(f.next_root);
+    const int64_t Ca = val(an.inputs[1]).shape[0];
+    B200_CHECK(tc && Cout_alloc == Cout_p && Cout == Cout_p, B200_ERR_UNSUPPORTED, "chained convolution: unsupported geometry");
+    std::vector<float> wa = const_floats(an.inputs[1]);      // [Ca][Cout][1][1]
+    std::vector<uint8_t> wp2((size_t)(Ca * Cout_p) * dtype_size(cd_), 0);
+    for (int64_t o = 0; o < Ca; ++o)
+      for (int64_t c = 0; c < Cout; ++c) store_float(wp2.data(), o * Cout_p + c, wa[o * Cout + c] * f.next_scale[o], cd_);
+    std::vector<float> bias2(Ca, 0.f);
+    for (int64_t o = 0; o < Ca; ++o) bias2[o] = f.next_shift[o];
+    w2ref = weights_ref(add_weights(wp2.data(), (int64_t)wp2.size()));
+    b2ref = add_f32_vector(bias2);
+    z = alloc(val(f.next_out_value).shape, cd_, L_NHWC8);
+    p.N2 = (int)Ca; p.ldz = (int)Ca;
+    p.act3 = f.next_act.kind; p.a3 = f.next_act.a; p.b3 = f.next_act.b;
+    flops += 2.0 * Mrows * Ca * Cout;
+    bytes += (double)z.bytes() + (double)Ca * Cout * dtype_size(cd_);
+    fused += "," + f.next_fused;
+  }
   conv_launch_step(out_name, "Convolution", fused, p, x.buf, wref, bref, rref, out.buf, &x, f.res_value >= 0 ? &res : nullptr, &out, flops,
-                   bytes, tc, dn ? x2.buf : BufRef(), dn ? &x2 : nullptr);
+                   bytes, tc, dn ? x2.buf : BufRef(), dn ? &x2 : nullptr, w2ref, b2ref, z.buf, f.next_root >= 0 ? &z : nullptr);
   set(f.out_value, out);
+  if (f.next_root >= 0) set(f.next_out_value, z);
 }
 
 // MatMul of two activations (attention scores / context): batched GEMM through the same kernels.

@@ -40,6 +40,14 @@ struct ConvParams {
   // shortcut of a ResNet downsampling block into the block's last 1x1 convolution: conv_c(b) + conv_proj(x) = [b | x_strided] * [Wc ; Wp].
   const void* x2 = nullptr;
   int K2 = 0, H2 = 0, W2 = 0, sh2 = 1, sw2 = 1;
+  // Second GEMM fused behind this one (conv_tc3f only): Z[M, N2] = act3(Y * w2[N2, Cout_p]^T + bias2), Y = this convolution's bf16 output.
+  // Used to run the 1x1 reduce convolution of the next bottleneck block inside the kernel that produces its input.
+  const void* w2 = nullptr;
+  const float* bias2 = nullptr;
+  void* z = nullptr;
+  int N2 = 0, ldz = 0;
+  int act3 = 0;
+  float a3 = 0, b3 = 0;
   int batch = 1;               // blockIdx.z batches (batched MatMul); strides in elements
   int64_t x_bs = 0, w_bs = 0, y_bs = 0;
 };
@@ -65,6 +73,10 @@ int conv_tc3_pick_bn(const ConvParams& p);
 const char* conv_tc3_mode_name(const ConvParams& p);
 void launch_conv_tc3(const ConvParams& p, int dtype, int bn, cudaStream_t s);
 void conv_tc3_init_device();
+// Two chained 1x1 convolutions in one CTA-pair kernel (conv_tc3f.cu): ConvParams::w2 / z / N2 describe the second one.
+bool conv_tc3f_supported(const ConvParams& p);
+void launch_conv_tc3f(const ConvParams& p, int dtype, cudaStream_t s);
+void conv_tc3f_init_device();
 // CUDA-core fp32 path (fp32 mode: 1e-4 parity; also the reference for tcgen05 unit tests).
 // Same parameter block; x/w/res/y are fp32, weights [Cout_alloc][Ktot] fp32.
 void launch_conv_f32(const ConvParams& p, cudaStream_t s);

@@ -116,6 +116,7 @@ def _bottleneck(f, x, cin, mid, cout, stride, rng, bn_on_shortcut):
 def test_projection_shortcut_is_folded_into_the_last_conv(cin, mid, cout, stride, hw, bn, monkeypatch):
     # ResNet downsampling block: conv_c(b) + conv_proj(x) runs as ONE GEMM over concatenated K (compile.cu fold_shortcuts)
     monkeypatch.delenv("B200_TC3", raising=False)
+    monkeypatch.delenv("B200_FUSE_NEXT", raising=False)
     rng = np.random.default_rng(cin + stride)
     f = Function("block0")
     x = f.parameter((3, cin, hw, hw))
@@ -133,3 +134,65 @@ def test_projection_shortcut_is_folded_into_the_last_conv(cin, mid, cout, stride
     got2 = list(net2.create_infer_request().infer({"Parameter_0": xin}).values())[0]
     assert len([e for e in net2.get_exec_graph_info() if e["type"] == "Convolution"]) == 4
     assert rel_l2(got2, ref) < 1e-2 and rel_l2(got, got2) < 1e-2
+
+
+def _identity_block(f, x, c, mid, rng):
+    def conv(v, o, ci, k, p):
+        w = (rng.standard_normal((o, ci, k, k)) / np.sqrt(ci * k * k)).astype(np.float32)
+        return f.add(f.convolution(v, w, (1, 1), (p, p), (p, p), (1, 1)), rng.standard_normal((1, o, 1, 1)).astype(np.float32) * 0.1)
+    a = f.relu(conv(x, mid, c, 1, 0))
+    b = f.relu(conv(a, mid, mid, 3, 1))
+    return f.relu(f.add(conv(b, c, mid, 1, 0), x))
+
+
+# the last case gives some of the 74 clusters two M tiles (the Z accumulator is then drained one tile late, while the next
+# M tile's first Y slabs wait in the staging ring)
+@pytest.mark.parametrize("cin,mid,cout,stride,hw,n", [(64, 64, 256, 1, 16, 3), (256, 128, 512, 2, 14, 5), (512, 256, 1024, 2, 12, 2),
+                                                      (64, 64, 256, 1, 56, 9)])
+def test_next_reduce_conv_rides_on_the_expand_conv(cin, mid, cout, stride, hw, n, monkeypatch):
+    # block 0 (projection shortcut folded as extra K) -> identity block -> identity block: the 1x1 reduce conv of each following block is
+    # computed inside the kernel that produces its input (compile.cu fold_next_reduce, conv_tc3f.cu); odd M tails, 1-8 N tiles, Ca 64-256
+    monkeypatch.delenv("B200_TC3", raising=False)
+    monkeypatch.setenv("B200_FUSE_NEXT", "1")        # opt-in: conv_tc3f
+    rng = np.random.default_rng(cin * 3 + stride)
+    f = Function("blocks")
+    x = f.parameter((n, cin, hw, hw))
+    y = _bottleneck(f, x, cin, mid, cout, stride, rng, False)
+    y = _identity_block(f, y, cout, mid, rng)
+    y = _identity_block(f, y, cout, mid, rng)
+    f.result(y)
+    xin = rng.standard_normal((n, cin, hw, hw)).astype(np.float32)
+    ref = list(interp.run(f, {"Parameter_0": xin}).values())[0]
+    net = Core().load_network(f, "B200", {"B200_INFERENCE_PRECISION": "BF16"})
+    got = list(net.create_infer_request().infer({"Parameter_0": xin}).values())[0]
+    convs = [e["impl"] for e in net.get_exec_graph_info() if e["type"] == "Convolution"]
+    # a, b, out0(+a1) | b1, out1(+a2) | b2, out2
+    assert len(convs) == 7 and sum("+1x1x%d" % mid in c for c in convs) == 2 and "kcat+1x1" in convs[2], convs
+    assert rel_l2(got, ref) < 1.5e-2        # three bottlenecks deep in bf16
+    monkeypatch.setenv("B200_FUSE_NEXT", "0")
+    net2 = Core().load_network(f, "B200", {"B200_INFERENCE_PRECISION": "BF16"})
+    got2 = list(net2.create_infer_request().infer({"Parameter_0": xin}).values())[0]
+    assert len([e for e in net2.get_exec_graph_info() if e["type"] == "Convolution"]) == 9
+    assert rel_l2(got, got2) < 1e-2
+
+
+@pytest.mark.parametrize("cin,cc,ca", [(512, 1024, 256), (128, 512, 128)])
+def test_chained_pointwise_convs_with_several_m_tiles_per_cluster(cin, cc, ca, monkeypatch):
+    # 20 480 rows = 80 pair M tiles on 74 clusters, Ca = 256 -> two Z slabs per epilogue group behind a pending Y slab of the next M tile
+    monkeypatch.delenv("B200_TC3", raising=False)
+    monkeypatch.setenv("B200_FUSE_NEXT", "1")        # opt-in: conv_tc3f
+    rng = np.random.default_rng(cc)
+    f = Function("chain")
+    x = f.parameter((20, cin, 32, 32))
+    y = f.relu(f.add(f.convolution(x, (rng.standard_normal((cc, cin, 1, 1)) / np.sqrt(cin)).astype(np.float32), (1, 1), (0, 0), (0, 0), (1, 1)),
+                     rng.standard_normal((1, cc, 1, 1)).astype(np.float32) * 0.1))
+    z = f.relu(f.add(f.convolution(y, (rng.standard_normal((ca, cc, 1, 1)) / np.sqrt(cc)).astype(np.float32), (1, 1), (0, 0), (0, 0), (1, 1)),
+                     rng.standard_normal((1, ca, 1, 1)).astype(np.float32) * 0.1))
+    f.result(z)
+    xin = rng.standard_normal((20, cin, 32, 32)).astype(np.float32)
+    ref = list(interp.run(f, {"Parameter_0": xin}).values())[0]
+    net = Core().load_network(f, "B200", {"B200_INFERENCE_PRECISION": "BF16"})
+    got = list(net.create_infer_request().infer({"Parameter_0": xin}).values())[0]
+    convs = [e["impl"] for e in net.get_exec_graph_info() if e["type"] == "Convolution"]
+    assert len(convs) == 1 and convs[0].endswith("+1x1x%d" % ca), convs
+    assert rel_l2(got, ref) < 1e-2

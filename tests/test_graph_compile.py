@@ -26,13 +26,23 @@ def test_resnet50_schedule():
     # 53 convs with BN/ReLU/residual folded in, of which the 4 projection shortcuts ride on the last 1x1 of their block as extra K
     # (fold_shortcuts); max pool, global avg pool, FC (+bias)
     assert k == {"Convolution": 49, "Pooling": 2, "FullyConnected": 1}
-    assert sum(1 for e in eg if e["impl"].endswith("tma_kcat")) == 4
+    assert sum(1 for e in eg if "tma_kcat" in e["impl"]) == 4
     assert all(e["impl"].startswith("tcgen05_bf16") for e in eg if e["type"] in ("Convolution", "FullyConnected"))
     assert sum(1 for e in eg if e["type"] == "Convolution" and any("add" in n.lower() for n in e["fused"])) >= 16  # residual sums
     assert abs(net.stat("flops") / 256 / 1e9 - 8.178) < 0.01
     assert net.stat("arena_bytes") < 2.0e9                              # conv1 out (411 MB) + pool + block buffers, reused
     assert [i[0] for i in net.inputs] == ["data"] and net.inputs[0][1] == (256, 3, 224, 224)
     assert net.outputs[0][1] == (256, 1000)
+
+
+def test_resnet50_schedule_with_chained_reduce_convs(monkeypatch):
+    # opt-in (B200_FUSE_NEXT=1): 12 of the 1x1 reduce convs (Ca <= 256) are computed inside the kernel that produces their input
+    monkeypatch.setenv("B200_FUSE_NEXT", "1")
+    net = dry(zoo.resnet50(batch=256))
+    eg = net.get_exec_graph_info()
+    assert kinds(net) == {"Convolution": 37, "Pooling": 2, "FullyConnected": 1}
+    assert sum(1 for e in eg if "+1x1x" in e["impl"]) == 12
+    assert abs(net.stat("flops") / 256 / 1e9 - 8.178) < 0.01
 
 
 def test_resnet50_schedule_without_shortcut_folding(monkeypatch):
