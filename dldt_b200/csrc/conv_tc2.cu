@@ -462,6 +462,7 @@ int g_im2col = -1;   // -1 unread; B200_IM2COL=0 disables the im2col-mode TMA pa
 
 tc::EpiAct make_epi(int kind, float a, float b) {
   tc::EpiAct e;
+  e.relu_in_pack = 0;
   e.kind = kind; e.a = a; e.b = b;
   e.lo = kind == ACT_RELU ? 0.f : a;
   e.hi = kind == ACT_RELU ? __builtin_huge_valf() : b;

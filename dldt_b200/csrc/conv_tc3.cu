@@ -120,6 +120,13 @@ void launch_tc3(const ConvParams& p, bool bf16, int bn, int a_mode, cudaStream_t
   a.e1 = make_epi(p.act1, p.a1, p.b1);
   a.e2 = make_epi(p.act2, p.a2, p.b2);
   a.gen = conv_acts_are_clamps(p) ? 0 : 1;
+  {
+    // a trailing ReLU rides on the float -> bf16/f16 conversion (B200_RELU_PACK=0: explicit max)
+    const char* e = getenv("B200_RELU_PACK");
+    const bool on = !(e && e[0] == '0');
+    if (on && p.res != nullptr && p.act2 == ACT_RELU) a.e2.relu_in_pack = 1;
+    if (on && p.res == nullptr && p.act1 == ACT_RELU) a.e1.relu_in_pack = 1;
+  }
   a.n_tiles = p.Cout_alloc / bn;
   a.reverse = p.reverse;
   { const char* e = getenv("B200_TC3_PREFETCH"); a.prefetch_tiles = e ? atoi(e) : 0; }   // measured: no gain on B200 (profiles/r1 call k)

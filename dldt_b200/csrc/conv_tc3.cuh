@@ -129,7 +129,10 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint32_t
       for (int e = 0; e < 8; ++e) f[e] += r[e];
       epi_act8<GEN>(f, e2);
     }
-    ptx::st_shared_v4(out_row + sw, make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7])));
+    if ((has_res ? e2 : e1).relu_in_pack)
+      ptx::st_shared_v4(out_row + sw, make_uint4(pack2_relu<T>(f[0], f[1]), pack2_relu<T>(f[2], f[3]), pack2_relu<T>(f[4], f[5]), pack2_relu<T>(f[6], f[7])));
+    else
+      ptx::st_shared_v4(out_row + sw, make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7])));
   }
 }
 

@@ -112,7 +112,10 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint32_t
       for (int e = 0; e < 8; ++e) f[e] += r[e];
       epi_act8<GEN>(f, e2);
     }
-    ptx::st_shared_v4(out_row + sw, make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7])));
+    if ((has_res ? e2 : e1).relu_in_pack)
+      ptx::st_shared_v4(out_row + sw, make_uint4(pack2_relu<T>(f[0], f[1]), pack2_relu<T>(f[2], f[3]), pack2_relu<T>(f[4], f[5]), pack2_relu<T>(f[6], f[7])));
+    else
+      ptx::st_shared_v4(out_row + sw, make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7])));
   }
 }
 
@@ -539,6 +542,9 @@ void launch_conv_tc3f(const ConvParams& p, int dtype, cudaStream_t s) {
   a.e1 = make_epi(p.act1, p.a1, p.b1);
   a.e2 = make_epi(p.act2, p.a2, p.b2);
   a.e3 = make_epi(p.act3, p.a3, p.b3);
+  if (p.res != nullptr && p.act2 == ACT_RELU) a.e2.relu_in_pack = 1;
+  if (p.res == nullptr && p.act1 == ACT_RELU) a.e1.relu_in_pack = 1;
+  if (p.act3 == ACT_RELU) a.e3.relu_in_pack = 1;
   a.reverse = p.reverse;
   a.n_tiles = p.Cout_alloc / BN;
   a.m_tiles = ((p.M + BM - 1) / BM + 1) / 2;

@@ -28,6 +28,19 @@ template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) 
   __half2 v = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// pack with ReLU folded into the conversion (cvt.rn.relu): max(x, 0) then round, one instruction per pair instead of three
+template <typename T>
+__device__ __forceinline__ uint32_t pack2_relu(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2_relu<__nv_bfloat16>(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));   // first source -> upper half
+  return d;
+}
+template <> __device__ __forceinline__ uint32_t pack2_relu<__half>(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
 template <typename T>
 __device__ __forceinline__ void unpack2(uint32_t u, float& a, float& b);
 template <> __device__ __forceinline__ void unpack2<__nv_bfloat16>(uint32_t u, float& a, float& b) {
@@ -45,13 +58,14 @@ template <> __device__ __forceinline__ void unpack2<__half>(uint32_t u, float& a
 // act.cuh but as ONE rolled loop, so the switch is instantiated once per call site instead of once per element (the fully
 // unrolled form made the kernel 26k instructions long and the epilogue instruction-fetch bound: profiles/r1_run2).
 struct EpiAct {
+  int relu_in_pack;   // set by the launcher on the LAST activation of the chain when it is a ReLU: the epilogue skips it and packs with cvt.relu
   int kind;       // Act code (generic path)
   float a, b;     // its parameters
   float lo, hi;   // clamp bounds (fast path)
 };
 template <bool GENERIC>
 __device__ __forceinline__ void epi_act8(float (&f)[8], const EpiAct& s) {
-  if (s.kind == 0) return;   // ACT_NONE (warp-uniform)
+  if (s.kind == 0 || s.relu_in_pack) return;   // ACT_NONE, or a trailing ReLU done by the bf16 conversion (warp-uniform)
   if constexpr (!GENERIC) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], s.lo);
