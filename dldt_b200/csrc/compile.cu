@@ -83,6 +83,12 @@ struct FusedConv {
   ActSpec next_act;
   std::string next_fused;
 };
+// Softmax over the last axis with the attention prologue folded in: softmax(x * scale + mask), mask broadcast over rows
+struct FusedSoftmax {
+  int x_value = -1, mask_value = -1;
+  float scale = 1.f;
+  std::string fused;
+};
 struct FusedMvn {
   int root = -1;
   std::vector<int> absorbed;
@@ -116,6 +122,7 @@ class Lowerer {
   std::map<std::pair<int, int>, LTensor> alt_;      // (value, layout) -> converted copy
   std::vector<int> absorbed_by_;                    // node -> fused record owner (-1 none)
   std::map<int, FusedConv> fconv_;                  // emit_at -> record
+  std::map<int, FusedSoftmax> fsm_;                 // Softmax node id -> record
   std::map<int, FusedMvn> fmvn_;
   std::map<int, FusedElt> felt_;
   std::map<int, int> box_dir_;                      // arena box -> 1 if its producer wrote it last-row-first
@@ -393,6 +400,60 @@ void Lowerer::fuse() {
     const Value& v = val(value);
     return v.consumers.size() == 1 ? v.consumers[0] : -1;
   };
+  // Attention scores: Softmax(Add(Multiply|Divide(x, scalar const), mask)) over the last axis with a mask of shape [N,1,..,1,S] or
+  // [1,..,1,S] -> one kernel, one pass (launch_softmax_scale_mask).  Either of the two prologue ops may be missing.
+  for (const Node& n : g_.nodes) {
+    if (n.op != B200_OP_SOFTMAX) continue;
+    const Shape& xs = val(n.inputs[0]).shape;
+    const int rank = (int)xs.size();
+    if (rank < 2 || n.i[0] != rank - 1 || !dtype_is_float(val(n.inputs[0]).dtype)) continue;
+    const int64_t cols = xs.back();
+    if (cols % 8 != 0 || cols > 2048) continue;
+    FusedSoftmax f;
+    f.x_value = n.inputs[0];
+    std::vector<int> absorbed;
+    {   // mask add
+      const Value& v = val(f.x_value);
+      if (v.producer >= 0 && v.consumers.size() == 1 && node(v.producer).op == B200_OP_ADD && absorbed_by_[v.producer] < 0) {
+        const Node& a = node(v.producer);
+        for (int side = 0; side < 2; ++side) {
+          const int mv = a.inputs[side], xv = a.inputs[1 - side];
+          const Shape& ms = val(mv).shape;
+          if (val(xv).shape != xs || (int)ms.size() != rank || ms.back() != cols || const_node(mv)) continue;
+          bool ok = true;
+          for (int d = 1; d + 1 < rank; ++d) ok = ok && ms[d] == 1;
+          ok = ok && (ms[0] == 1 || ms[0] == xs[0]) && dtype_is_float(val(mv).dtype);
+          if (!ok) continue;
+          f.mask_value = mv;
+          f.x_value = xv;
+          absorbed.push_back(a.id);
+          f.fused = a.name;
+          break;
+        }
+      }
+    }
+    {   // scalar scale
+      const Value& v = val(f.x_value);
+      if (v.producer >= 0 && v.consumers.size() == 1 && absorbed_by_[v.producer] < 0 &&
+          (node(v.producer).op == B200_OP_MULTIPLY || node(v.producer).op == B200_OP_DIVIDE)) {
+        const Node& m = node(v.producer);
+        for (int side = 0; side < 2; ++side) {
+          const int cv = m.inputs[side], xv = m.inputs[1 - side];
+          if (!const_node(cv) || numel(val(cv).shape) != 1 || val(xv).shape != xs) continue;
+          if (m.op == B200_OP_DIVIDE && side == 0) continue;   // scalar / x is not a scale
+          const float c = const_floats(cv)[0];
+          f.scale = m.op == B200_OP_MULTIPLY ? c : 1.f / c;
+          f.x_value = xv;
+          absorbed.push_back(m.id);
+          f.fused = m.name + (f.fused.empty() ? "" : "," + f.fused);
+          break;
+        }
+      }
+    }
+    if (absorbed.empty()) continue;
+    for (int a : absorbed) absorbed_by_[a] = n.id;
+    fsm_[n.id] = f;
+  }
   for (const Node& n : g_.nodes) {
     if (absorbed_by_[n.id] >= 0) continue;
     bool is_conv = n.op == B200_OP_CONVOLUTION || n.op == B200_OP_GROUP_CONVOLUTION;
@@ -1456,6 +1517,33 @@ void Lowerer::lower_node(const Node& n) {
     case B200_OP_MAX_POOL: case B200_OP_AVG_POOL: lower_pool(n); break;
     case B200_OP_REDUCE_MEAN: case B200_OP_REDUCE_SUM: case B200_OP_REDUCE_MAX: lower_reduce(n); break;
     case B200_OP_SOFTMAX: {
+      auto fs = fsm_.find(n.id);
+      if (fs != fsm_.end()) {
+        const FusedSoftmax& f = fs->second;
+        LTensor x = get(f.x_value, L_ROWMAJOR);
+        LTensor mk;
+        if (f.mask_value >= 0) mk = get(f.mask_value, L_ROWMAJOR);
+        const Shape& xs = x.shape;
+        const int64_t cols = xs.back(), rows = numel(xs) / cols;
+        // mask [N,1,..,1,S]: one mask row per leading index; [1,..,1,S]: one row for all
+        const int64_t rows_per_mask = (f.mask_value >= 0 && mk.shape[0] == xs[0] && xs[0] > 1) ? rows / xs[0] : rows;
+        LTensor out = alloc(xs, x.dtype, L_ROWMAJOR);
+        BufRef xr = x.buf, mr = mk.buf, yr = out.buf;
+        const bool has_mask = f.mask_value >= 0;
+        const float scale = f.scale;
+        const int dt = x.dtype;
+        B200_CHECK(!has_mask || mk.dtype == x.dtype, B200_ERR_UNSUPPORTED, "softmax mask dtype differs from the scores'");
+        Step s;
+        s.name = n.name; s.type = "Softmax"; s.impl = has_mask ? "softmax_scale_mask_warp_rows" : "softmax_scale_warp_rows";
+        s.fused = f.fused + "," + n.name;
+        s.bytes = 2.0 * (double)x.bytes();
+        s.launch = [=](const RunCtx& c) {
+          launch_softmax_scale_mask(c.ptr(xr), has_mask ? c.ptr(mr) : nullptr, c.ptr(yr), rows, cols, scale, rows_per_mask, dt, (cudaStream_t)c.stream);
+        };
+        emit(std::move(s), {&x, has_mask ? &mk : nullptr}, {&out});
+        set(n.outputs[0], out);
+        break;
+      }
       LTensor x = get(n.inputs[0], L_ROWMAJOR);
       const Shape& xs = x.shape;
       int64_t outer = 1, inner = 1;
@@ -1466,7 +1554,8 @@ void Lowerer::lower_node(const Node& n) {
       int64_t axis = xs[n.i[0]];
       int dt = x.dtype;
       Step s;
-      s.name = n.name; s.type = "Softmax"; s.impl = inner == 1 ? "softmax_rows" : "softmax_strided"; s.fused = n.name;
+      s.name = n.name; s.type = "Softmax"; s.fused = n.name;
+      s.impl = inner == 1 ? ((softmax_fused_supported(axis, dt) && axis >= 64) ? "softmax_warp_rows" : "softmax_rows") : "softmax_strided";
       s.bytes = 2.0 * (double)x.bytes();
       s.launch = [=](const RunCtx& c) { launch_softmax(c.ptr(xr), c.ptr(yr), outer, axis, inner, dt, (cudaStream_t)c.stream); };
       emit(std::move(s), {&x}, {&out});

@@ -116,6 +116,10 @@ void launch_scale_shift(const void* x, const float* scale, const float* shift, v
 
 // ---- softmax / MVN / gather ------------------------------------------------------------------
 void launch_softmax(const void* x, void* y, int64_t outer, int64_t axis, int64_t inner, int dtype, cudaStream_t s);
+// softmax(x * scale + mask[row / rows_per_mask]) over the last axis, one pass (mask may be null); cols % 8 == 0, cols <= 2048
+bool softmax_fused_supported(int64_t cols, int dtype);
+void launch_softmax_scale_mask(const void* x, const void* mask, void* y, int64_t rows, int64_t cols, float scale, int64_t rows_per_mask, int dtype,
+                               cudaStream_t s);
 void launch_mvn(const void* x, void* y, const float* gamma, const float* beta, int64_t rows, int64_t cols, int normalize_variance,
                 int eps_outside, float eps, int dtype, cudaStream_t s);
 void launch_gather_rows(const void* table, const int32_t* idx, void* y, int64_t n_idx, int64_t row_elems, int64_t table_rows,

@@ -45,6 +45,18 @@ template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bflo
 #pragma unroll
   for (int i = 0; i < 4; ++i) { f[2 * i] = __low2float(h[i]); f[2 * i + 1] = __high2float(h[i]); }
 }
+// eight 16-bit values already in registers -> floats
+template <typename T> __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]);
+template <> __device__ __forceinline__ void unpack8<__half>(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __low2float(h[i]); f[2 * i + 1] = __high2float(h[i]); }
+}
+template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __low2float(h[i]); f[2 * i + 1] = __high2float(h[i]); }
+}
 template <typename T> __device__ __forceinline__ void store8(T* p, const float (&f)[8]);
 template <> __device__ __forceinline__ void store8<float>(float* p, const float (&f)[8]) {
   reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
@@ -141,6 +153,62 @@ __global__ void dwconv_kernel(const DwParams p) {
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = act_apply(acc[e], p.act, p.a, p.b);
   store8<T>(reinterpret_cast<T*>(p.y) + pix * p.Cp + c8 * 8, acc);
+}
+
+
+// Fast path of the depthwise kernel for MobileNet-style layers: 3x3, dilation 1, pads <= 1, stride 1 or 2, 16-bit NHWC8 data.
+// One thread = two horizontally adjacent output pixels x 8 channels: the 3 x (2 + S) input vectors are loaded once (all loads issued
+// before the first use, out-of-image taps read as zero), the nine weight vectors once, fp32 accumulate, 32-bit index math.
+template <typename T, int S>
+__global__ void __launch_bounds__(256) dwconv3x3_16b_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w, const float* __restrict__ bias,
+                                                            uint4* __restrict__ y, int N, int H, int W, int cpc, int Ho, int Wo, int pt, int pl, int act,
+                                                            float aa, float ab, uint32_t total) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int Wo2 = (Wo + 1) >> 1;
+  const uint32_t c8 = idx % (uint32_t)cpc;
+  uint32_t t = idx / (uint32_t)cpc;
+  const int j = (int)(t % (uint32_t)Wo2);
+  t /= (uint32_t)Wo2;
+  const int ho = (int)(t % (uint32_t)Ho);
+  const int n = (int)(t / (uint32_t)Ho);
+  constexpr int NC = 2 * S + 1 + (S == 1 ? 1 : 0);      // input columns feeding two outputs: 4 (stride 1) or 5 (stride 2)
+  const uint4* xi = x + (size_t)n * H * W * cpc + c8;
+  const int c0 = 2 * j * S - pl, r0 = ho * S - pt;
+  uint4 v[3][NC];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int hi = r0 + r;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int wi = c0 + c;
+      const bool in = (unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W;
+      v[r][c] = in ? __ldg(xi + ((size_t)hi * W + wi) * cpc) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  float acc0[8], acc1[8];
+  {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + c8 * 2), b1 = __ldg(reinterpret_cast<const float4*>(bias) + c8 * 2 + 1);
+    acc0[0] = acc1[0] = b0.x; acc0[1] = acc1[1] = b0.y; acc0[2] = acc1[2] = b0.z; acc0[3] = acc1[3] = b0.w;
+    acc0[4] = acc1[4] = b1.x; acc0[5] = acc1[5] = b1.y; acc0[6] = acc1[6] = b1.z; acc0[7] = acc1[7] = b1.w;
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      float wv[8], a[8], b[8];
+      const uint4 wq = __ldg(w + (size_t)(r * 3 + s) * cpc + c8);
+      unpack8<T>(wq, wv);
+      unpack8<T>(v[r][s], a);
+      unpack8<T>(v[r][s + S], b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { acc0[e] = fmaf(a[e], wv[e], acc0[e]); acc1[e] = fmaf(b[e], wv[e], acc1[e]); }
+    }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { acc0[e] = act_apply(acc0[e], act, aa, ab); acc1[e] = act_apply(acc1[e], act, aa, ab); }
+  T* yo = reinterpret_cast<T*>(y + (((size_t)n * Ho + ho) * Wo + 2 * j) * cpc + c8);
+  store8<T>(yo, acc0);
+  if (2 * j + 1 < Wo) store8<T>(yo + (size_t)cpc * 8, acc1);
 }
 
 // ---- pooling ------------------------------------------------------------------------------------
@@ -340,6 +408,62 @@ __global__ void scale_shift_kernel(const T* __restrict__ x, const float* __restr
 }
 
 // ---- softmax: exp(x - max) / sum (reference/softmax.hpp:19-47) ----------------------------------
+// y[row, :] = softmax(x[row, :] * scale + mask[row / rows_per_mask, :]) over rows of `cols` (<= 2048, multiple of 8) elements: one warp per
+// row, the row lives in registers between the passes, fp32 math (reference/softmax.hpp:19-47 after the Multiply / Add of the attention
+// pattern).  mask == nullptr: plain (scaled) softmax.  Reads and writes each element once: the HBM-bound form of BERT's
+// scale -> mask-add -> softmax chain (three kernels, five passes over the [N, heads, S, S] scores otherwise).
+template <typename T, int CHUNKS>
+__global__ void __launch_bounds__(256) softmax_warp_rows_kernel(const T* __restrict__ x, const T* __restrict__ mask, T* __restrict__ y, int64_t rows,
+                                                                int cols, float scale, int64_t rows_per_mask) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const T* px = x + row * cols;
+  const T* pm = mask ? mask + (row / rows_per_mask) * cols : nullptr;
+  float v[CHUNKS][8];
+  float m = -FLT_MAX;
+#pragma unroll
+  for (int k = 0; k < CHUNKS; ++k) {
+    const int c = (k * 32 + lane) * 8;
+    if (c < cols) {
+      load8<T>(px + c, v[k]);
+      if (pm) {
+        float mk[8];
+        load8<T>(pm + c, mk);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[k][e] = v[k][e] * scale + mk[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[k][e] *= scale;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) m = fmaxf(m, v[k][e]);
+    }
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < CHUNKS; ++k) {
+    const int c = (k * 32 + lane) * 8;
+    if (c < cols) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { v[k][e] = expf(v[k][e] - m); sum += v[k][e]; }
+    }
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  T* py = y + row * cols;
+#pragma unroll
+  for (int k = 0; k < CHUNKS; ++k) {
+    const int c = (k * 32 + lane) * 8;
+    if (c < cols) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[k][e] *= inv;
+      store8<T>(py + c, v[k]);
+    }
+  }
+}
+
 template <typename T>
 __global__ void softmax_rows_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int64_t cols) {
   __shared__ float sh[32];
@@ -371,6 +495,59 @@ __global__ void softmax_strided_kernel(const T* __restrict__ x, T* __restrict__ 
 }
 
 // ---- MVN / LayerNorm over the last `cols` elements (reference/mvn.hpp:66-118) --------------------
+// MVN / LayerNorm over rows of `cols` (<= 2048, multiple of 8) elements: one warp per row, the row stays in registers between the three
+// passes (reference/mvn.hpp:66-118: biased variance of the centred values; eps inside or outside the square root).
+template <typename T, int CHUNKS>
+__global__ void __launch_bounds__(256) mvn_warp_rows_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, int64_t rows, int cols, int normalize_variance, int eps_outside,
+                                                            float eps) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const T* px = x + row * cols;
+  float v[CHUNKS][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < CHUNKS; ++k) {
+    const int c = (k * 32 + lane) * 8;
+    if (c < cols) {
+      load8<T>(px + c, v[k]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[k][e];
+    }
+  }
+  const float mean = warp_sum(s) / (float)cols;
+  float scale = 1.f;
+  if (normalize_variance) {
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) {
+      const int c = (k * 32 + lane) * 8;
+      if (c < cols) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float d = v[k][e] - mean; q += d * d; }
+      }
+    }
+    const float var = warp_sum(q) / (float)cols;
+    scale = eps_outside ? 1.f / (sqrtf(var) + eps) : 1.f / sqrtf(var + eps);
+  }
+  T* py = y + row * cols;
+#pragma unroll
+  for (int k = 0; k < CHUNKS; ++k) {
+    const int c = (k * 32 + lane) * 8;
+    if (c < cols) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float r = (v[k][e] - mean) * scale;
+        if (gamma) r *= __ldg(gamma + c + e);
+        if (beta) r += __ldg(beta + c + e);
+        v[k][e] = r;
+      }
+      store8<T>(py + c, v[k]);
+    }
+  }
+}
+
 template <typename T>
 __global__ void mvn_rows_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int64_t cols, int normalize_variance, int eps_outside, float eps) {
@@ -491,6 +668,21 @@ __global__ void copy_i32_kernel(const int32_t* __restrict__ src, int32_t* __rest
   if (i < n) dst[i] = src[i];
 }
 
+__global__ void __launch_bounds__(256) permute_vec16_kernel(const PermuteParams p) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (uint32_t)p.n) return;
+  uint32_t rem = i;
+  int64_t so = 0;
+#pragma unroll 1
+  for (int d = p.rank - 1; d >= 0; --d) {
+    const uint32_t od = (uint32_t)p.oshape[d];
+    const uint32_t c = rem % od;
+    rem /= od;
+    so += (int64_t)c * p.istride[d];
+  }
+  reinterpret_cast<uint4*>(p.y)[i] = __ldg(reinterpret_cast<const uint4*>(p.x) + so);
+}
+
 template <typename E>
 __global__ void permute_kernel(const PermuteParams p) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -582,6 +774,17 @@ __global__ void topk_kernel(const float* __restrict__ x, float* __restrict__ val
 // ================================= launchers ==========================================================
 void launch_dwconv(const DwParams& p, int dtype, cudaStream_t s) {
   int64_t total = (int64_t)p.N * p.Ho * p.Wo * (p.Cp / 8);
+  const bool fast = (dtype == B200_BF16 || dtype == B200_F16) && p.kh == 3 && p.kw == 3 && p.dh == 1 && p.dw == 1 && p.sh == p.sw && (p.sh == 1 || p.sh == 2) &&
+                    p.pt >= 0 && p.pt <= 1 && p.pl >= 0 && p.pl <= 1;
+  const int64_t total2 = (int64_t)p.N * p.Ho * ((p.Wo + 1) / 2) * (p.Cp / 8);
+  if (fast && total2 > 0 && total2 < ((int64_t)1 << 31)) {
+    const unsigned grid = grid_for(total2, 256);
+#define B200_DW_LAUNCH(T, S_) dwconv3x3_16b_kernel<T, S_><<<grid, 256, 0, s>>>((const uint4*)p.x, (const uint4*)p.w, p.bias, (uint4*)p.y, p.N, p.H, p.W, p.Cp / 8, \
+                                                                               p.Ho, p.Wo, p.pt, p.pl, p.act, p.a, p.b, (uint32_t)total2)
+    if (dtype == B200_BF16) { if (p.sh == 1) B200_DW_LAUNCH(__nv_bfloat16, 1); else B200_DW_LAUNCH(__nv_bfloat16, 2); }
+    else { if (p.sh == 1) B200_DW_LAUNCH(__half, 1); else B200_DW_LAUNCH(__half, 2); }
+    return;
+  }
   B200_DISPATCH_FLOAT(dtype, T, (dwconv_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(p)));
 }
 void launch_pool(const PoolParams& p, int dtype, cudaStream_t s) {
@@ -623,8 +826,23 @@ void launch_scale_shift(const void* x, const float* scale, const float* shift, v
   B200_DISPATCH_FLOAT(dtype, T,
                       (scale_shift_kernel<T><<<grid_for(total, 256), 256, 0, s>>>((const T*)x, scale, shift, (T*)y, rows, Cp, act, aa, ab)));
 }
+bool softmax_fused_supported(int64_t cols, int dtype) { return cols % 8 == 0 && cols <= 2048 && (dtype == B200_BF16 || dtype == B200_F16 || dtype == B200_F32); }
+void launch_softmax_scale_mask(const void* x, const void* mask, void* y, int64_t rows, int64_t cols, float scale, int64_t rows_per_mask, int dtype,
+                               cudaStream_t s) {
+  if (rows * cols == 0) return;
+  B200_CHECK(softmax_fused_supported(cols, dtype), B200_ERR_UNSUPPORTED, "softmax_scale_mask: unsupported row length " << cols);
+  const unsigned grid = grid_for(rows, 8);
+  const int chunks = (int)((cols + 255) / 256);
+#define B200_SM_LAUNCH(T, C_) softmax_warp_rows_kernel<T, C_><<<grid, 256, 0, s>>>((const T*)x, (const T*)mask, (T*)y, rows, (int)cols, scale, rows_per_mask)
+#define B200_SM_CHUNKS(T) do { if (chunks <= 1) B200_SM_LAUNCH(T, 1); else if (chunks <= 2) B200_SM_LAUNCH(T, 2); else if (chunks <= 4) B200_SM_LAUNCH(T, 4); else B200_SM_LAUNCH(T, 8); } while (0)
+  B200_DISPATCH_FLOAT(dtype, T, B200_SM_CHUNKS(T));
+}
 void launch_softmax(const void* x, void* y, int64_t outer, int64_t axis, int64_t inner, int dtype, cudaStream_t s) {
   if (outer * axis * inner == 0) return;
+  if (inner == 1 && softmax_fused_supported(axis, dtype) && axis >= 64) {   // warp per row, one read + one write per element
+    launch_softmax_scale_mask(x, nullptr, y, outer, axis, 1.f, 1, dtype, s);
+    return;
+  }
   if (inner == 1) {
     int block = axis >= 512 ? 256 : (axis >= 128 ? 128 : 32);
     B200_DISPATCH_FLOAT(dtype, T, (softmax_rows_kernel<T><<<(unsigned)outer, block, 0, s>>>((const T*)x, (T*)y, outer, axis)));
@@ -636,6 +854,14 @@ void launch_softmax(const void* x, void* y, int64_t outer, int64_t axis, int64_t
 void launch_mvn(const void* x, void* y, const float* gamma, const float* beta, int64_t rows, int64_t cols, int normalize_variance,
                 int eps_outside, float eps, int dtype, cudaStream_t s) {
   if (rows * cols == 0) return;
+  if (cols % 8 == 0 && cols <= 2048 && cols >= 64 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0) {
+    const unsigned grid = grid_for(rows, 8);
+    const int chunks = (int)((cols + 255) / 256);
+#define B200_MVN_LAUNCH(T, C_) mvn_warp_rows_kernel<T, C_><<<grid, 256, 0, s>>>((const T*)x, (T*)y, gamma, beta, rows, (int)cols, normalize_variance, eps_outside, eps)
+#define B200_MVN_CHUNKS(T) do { if (chunks <= 1) B200_MVN_LAUNCH(T, 1); else if (chunks <= 2) B200_MVN_LAUNCH(T, 2); else if (chunks <= 4) B200_MVN_LAUNCH(T, 4); else B200_MVN_LAUNCH(T, 8); } while (0)
+    B200_DISPATCH_FLOAT(dtype, T, B200_MVN_CHUNKS(T));
+    return;
+  }
   int block = cols >= 1024 ? 256 : (cols >= 256 ? 128 : 32);
   B200_DISPATCH_FLOAT(dtype, T,
                       (mvn_rows_kernel<T><<<(unsigned)rows, block, 0, s>>>((const T*)x, (T*)y, gamma, beta, cols, normalize_variance,
@@ -735,6 +961,21 @@ void launch_convert_flat(const void* src, int sdtype, void* dst, int ddtype, int
 }
 void launch_permute(const PermuteParams& p, int elem_size, cudaStream_t s) {
   if (p.n == 0) return;
+  // innermost dimension contiguous in the source too (e.g. BERT's [N,S,heads,64] <-> [N,heads,S,64]) and everything 16-byte aligned:
+  // move 16-byte vectors instead of elements (32-bit index math; the element-wise kernel ran at 0.6 TB/s)
+  if (p.rank >= 2 && p.rank <= 8 && p.istride[p.rank - 1] == 1 && elem_size <= 4) {
+    const int64_t vec = 16 / elem_size;
+    bool ok = p.oshape[p.rank - 1] % vec == 0 && (uintptr_t)p.x % 16 == 0 && (uintptr_t)p.y % 16 == 0 && p.n / vec < ((int64_t)1 << 31);
+    for (int d = 0; d + 1 < p.rank; ++d) ok = ok && p.istride[d] % vec == 0;
+    if (ok) {
+      PermuteParams q = p;
+      q.oshape[p.rank - 1] = p.oshape[p.rank - 1] / vec;
+      for (int d = 0; d + 1 < p.rank; ++d) q.istride[d] = p.istride[d] / vec;
+      q.n = p.n / vec;
+      permute_vec16_kernel<<<grid_for(q.n, 256), 256, 0, s>>>(q);
+      return;
+    }
+  }
   unsigned g = grid_for(p.n, 256);
   if (elem_size == 4) permute_kernel<uint32_t><<<g, 256, 0, s>>>(p);
   else if (elem_size == 2) permute_kernel<uint16_t><<<g, 256, 0, s>>>(p);

@@ -1,0 +1,94 @@
+"""The four non-headline configs of BASELINE.json at full size on one B200 (not bench values): compile, run, device-resident time, and
+parity of the low-precision path against the plugin's own fp32 mode on the same weights and inputs at a small batch (the fp32 mode is
+what tests/test_gpu_golden.py pins to the reference CPU plugin at 1e-4).
+usage: python tools/gpu_configs.py [mobilenet|ssd|bert ...]"""
+import sys, time
+import numpy as np
+sys.path.insert(0, ".")
+from dldt_b200 import Core, zoo
+
+
+def inputs_for(net, rng, kind):
+    out = {}
+    for name, shape, _ in net.inputs:
+        if kind == "bert":
+            if "mask" in name:
+                out[name] = np.ones(shape, np.int32)
+            elif "type" in name or "segment" in name:
+                out[name] = np.zeros(shape, np.int32)
+            else:
+                out[name] = rng.integers(0, 30522, shape, dtype=np.int32)
+        else:
+            out[name] = rng.uniform(0, 1, shape).astype(np.float32)
+    return out
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def run(kind):
+    build = {"mobilenet": (lambda b: zoo.mobilenet_v2(batch=b), 64, "BF16", 4),
+             "ssd": (lambda b: zoo.ssd300_resnet34(batch=b), 32, "FP16", 2),
+             "bert": (lambda b: zoo.bert_base(batch=b), 64, "BF16", 2)}[kind]
+    mk, batch, prec, small = build
+    core = Core()
+    # ---- parity at a small batch: low precision vs the plugin's fp32 mode ----
+    fs = mk(small)
+    rng = np.random.default_rng(7)
+    n32 = core.load_network(fs, "B200", {"B200_INFERENCE_PRECISION": "FP32"})
+    nlp = core.load_network(fs, "B200", {"B200_INFERENCE_PRECISION": prec})
+    xin = inputs_for(n32, rng, kind)
+    o32 = n32.create_infer_request().infer(xin)
+    olp = nlp.create_infer_request().infer(xin)
+    for k in o32:
+        a, b = olp[k], o32[k]
+        if kind == "ssd":
+            # detections [1,1,N*keep,7]: compare the kept (image, label) multiset and the boxes of matching rows
+            va, vb = a.reshape(-1, 7), b.reshape(-1, 7)
+            na, nb = int((va[:, 0] >= 0).sum()), int((vb[:, 0] >= 0).sum())
+            print("[%s] %s: detections %s=%d fp32=%d  finite %s" % (kind, k, prec, na, nb, bool(np.isfinite(a).all())), flush=True)
+        else:
+            extra = ""
+            if a.ndim == 2 and a.shape[1] > 1:
+                extra = "  top-1 agreement %.3f" % float((a.argmax(1) == b.argmax(1)).mean())
+            print("[%s] %s: rel-L2 %s vs fp32 mode = %.3e%s  finite %s" % (kind, k, prec, rel_l2(a, b), extra, bool(np.isfinite(a).all())), flush=True)
+    del n32, nlp
+    # ---- full size: compile + time ----
+    t = time.time()
+    f = mk(batch)
+    net = core.load_network(f, "B200", {"B200_INFERENCE_PRECISION": prec})
+    req = net.create_infer_request()
+    for name, arr in inputs_for(net, rng, kind).items():
+        req.set_blob(name, arr)
+    out = req.infer()
+    finite = all(bool(np.isfinite(v).all()) for v in out.values())
+    ms = min(req.time_launches(10) / 10 for _ in range(3))
+    kinds = {}
+    for e in net.get_exec_graph_info():
+        kinds[e["type"]] = kinds.get(e["type"], 0) + 1
+    print("[%s] batch %d %s: compile+first run %.1f s, %d kernels %s, arena %.0f MB, %.3f ms/step -> %.0f items/s (device resident), %.1f TFLOP/s, finite %s"
+          % (kind, batch, prec, time.time() - t, net.num_exec_nodes, kinds, net.stat("arena_bytes") / 1e6, ms, batch / ms * 1e3,
+             net.stat("flops") / ms / 1e9, finite), flush=True)
+    pc = req.get_perf_counts()
+    rows = sorted(((pc[e["name"]]["real_time"], e) for e in net.get_exec_graph_info()), key=lambda r: -r[0])
+    tot = sum(r[0] for r in rows)
+    by = {}
+    for us, e in rows:
+        k = (e["type"], e["impl"])
+        by.setdefault(k, [0, 0.0])
+        by[k][0] += 1; by[k][1] += us
+    for k, v in sorted(by.items(), key=lambda kv: -kv[1][1])[:12]:
+        print("    %9.1f us %5.1f%% x%-3d %-16s %s" % (v[1], 100 * v[1] / tot, v[0], k[0], k[1]), flush=True)
+    for us, e in rows[:4]:
+        print("    %8.1f us %5.1f%% %-16s %-44s %s" % (us, 100 * us / tot, e["type"], e["impl"], e["name"]), flush=True)
+
+
+if __name__ == "__main__":
+    for k in (sys.argv[1:] or ["mobilenet", "ssd", "bert"]):
+        try:
+            run(k)
+        except Exception as ex:
+            import traceback
+            traceback.print_exc()
+            print("[%s] FAILED: %r" % (k, ex), flush=True)
