@@ -17,7 +17,7 @@
 //   warp 8    leader: main MMA issuer.  peer: forwards "Y accumulator drained" / "Z accumulator drained" to the leader
 //   warp 9    operand TMA (activation matrix, optional second source = folded projection shortcut, weights)
 //   warp 10   residual TMA
-//   warp 11   leader: second MMA issuer (Y slab x Wa chunk).  peer: forwards "slab ready"
+//   warp 11   leader: second MMA issuer (Y slab x Wa chunk).  peer: forwards "slab ready" of epilogue group 0 (warp 13: of group 1)
 //   warp 12   Wa chunk loads (ring of 2-8 stages)
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -45,7 +45,7 @@ using namespace tc;
 
 constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int A_BYTES = BM * 128, B_BYTES = (BN / 2) * 128, SLAB_BYTES = BM * 128;
-constexpr int NUM_THREADS = 416;
+constexpr int NUM_THREADS = 448;
 constexpr int MAX_SA = 4, NRES = 3, NSTG = 4, MAX_S2 = 8;
 constexpr int SMEM_LIMIT = 232448;
 constexpr int Z_COL = 2 * BN;            // first TMEM column of the Z accumulator
@@ -417,17 +417,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
         }
       }
     }
-  } else if (warp == 11) {
+  } else if (warp == 11 || warp == 13) {
     // ===================== second GEMM: Z += Yslab * Wa[:, slab]^T =====================
     const uint32_t yr_leader0 = ptx::mapa(ptx::smem_u32(&yready[0]), 0);
     const uint32_t idesc2 = ptx::make_idesc_f16(TcType<T>::is_bf16, 2 * BM, Ca);
     const uint32_t stg_lo0 = ((smem_base + plan.stg_off) & 0x3FFFFu) >> 4, w2_lo0 = ((smem_base + plan.w2_off) & 0x3FFFFu) >> 4;
     const int per_m = n_tiles * (BN / 64);                         // Y slabs (= 64-column chunks of Wa) per M tile
+    // leader: warp 11 issues the second GEMM for every slab.  peer: one forwarder per epilogue group (warp 11: group 0, warp 13: group 1):
+    // a remote arrive stalls its issuer for ~1200 cycles and a CTA finishes a slab every ~1000, so one forwarder could not keep up
+    const uint32_t fwd_grp = warp == 11 ? 0u : 1u;
     uint32_t g = 0, zph = 0;
     uint32_t mineg[2] = {0u, 0u};
     uint32_t yuse[NSTG] = {0u, 0u, 0u, 0u};
     int i2 = 0;
-    for (int it = 0; it < my_tiles; ++it) {
+    for (int it = 0; (leader ? warp == 11 : true) && it < my_tiles; ++it) {
       const int n = it % n_tiles;
       for (int h = 0; h < BN / 64; ++h, ++g, ++i2) {
         const int c = n * (BN / 64) + h;                            // 64-column chunk of Wa = Y slab index inside the M tile
@@ -451,7 +454,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
             if (c == per_m - 1) ptx::umma_commit_pair(zfull, 3);
           }
           __syncwarp();
-        } else {
+        } else if (grp == fwd_grp) {
           ptx::mbar_wait(&yready[sidx], yuse[sidx] & 1u);           // my epilogue group has finished the slab: tell the leader
           if (lane == 0) ptx::mbar_arrive_cluster(yr_leader0 + sidx * 8u);
           __syncwarp();
