@@ -129,6 +129,7 @@ void launch_tc3(const ConvParams& p, bool bf16, int bn, int a_mode, cudaStream_t
   }
   a.n_tiles = p.Cout_alloc / bn;
   a.reverse = p.reverse;
+  { const char* e = getenv("B200_TC3_WARP_STORE"); a.warp_store = (e && e[0] == '0') ? 0 : 1; }
   { const char* e = getenv("B200_TC3_PREFETCH"); a.prefetch_tiles = e ? atoi(e) : 0; }   // measured: no gain on B200 (profiles/r1 call k)
   {
     // activations are read once per layer (the next reader is a different kernel, long after the tensor has left the 126 MB L2 at batch 256):
@@ -168,6 +169,8 @@ void launch_tc3(const ConvParams& p, bool bf16, int bn, int a_mode, cudaStream_t
     const uint32_t yb[5] = {64, 1, (uint32_t)S2D_G, (uint32_t)S2D_R, 1};
     a.tm_y = make_tmap_tiled(p.y, bf16, 5, yd, ys, yb);
     a.tm_r = a.tm_y;
+    const uint32_t ywb[5] = {64, 1, (uint32_t)S2D_G, 1, 1};         // one warp = one output row of the tile
+    a.tm_yw = make_tmap_tiled(p.y, bf16, 5, yd, ys, ywb);
   } else if (a_mode == A_HALO) {
     const uint64_t C = (uint64_t)p.Cin_p, pitch = (uint64_t)p.ldy * 2;
     const uint64_t ad[4] = {C, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
@@ -181,8 +184,12 @@ void launch_tc3(const ConvParams& p, bool bf16, int bn, int a_mode, cudaStream_t
     const uint32_t yb[4] = {64, (uint32_t)a.rows_p, (uint32_t)a.rows_r, 1};
     a.tm_y = make_tmap_tiled(p.y, bf16, 4, yd, ys, yb);
     a.tm_r = p.res ? make_tmap_tiled(p.res, bf16, 4, yd, ys, yb) : a.tm_y;
+    // one warp = 32 consecutive rows of the tile = 32 pixels of one image row (P >= 32) or 32 / P whole image rows
+    const uint32_t ywb[4] = {64, (uint32_t)std::min(a.rows_p, 32), (uint32_t)std::max(1, 32 / a.rows_p), 1};
+    a.tm_yw = make_tmap_tiled(p.y, bf16, 4, yd, ys, ywb);
   } else {
     a.tm_y = make_tmap_2d(p.y, bf16, (uint64_t)p.Cout_p, (uint64_t)p.M, (uint64_t)p.ldy * 2, 64, BM);
+    a.tm_yw = make_tmap_2d(p.y, bf16, (uint64_t)p.Cout_p, (uint64_t)p.M, (uint64_t)p.ldy * 2, 64, 32);
     a.tm_r = p.res ? make_tmap_2d(p.res, bf16, (uint64_t)p.Cout_p, (uint64_t)p.M, (uint64_t)p.ldy * 2, 64, BM) : a.tm_y;
     a.tm_a = a_mode == A_MATRIX ? make_tmap_2d(p.x, bf16, (uint64_t)p.Cin_p, (uint64_t)p.M, (uint64_t)p.Cin_p * 2, BK, BM) : make_tmap_im2col(p, bf16);
     if (p.K2 > 0) {

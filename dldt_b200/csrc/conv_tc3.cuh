@@ -86,6 +86,8 @@ struct Tc3Args {
   CUtensorMap tm_w;   // packed weights [Cout_alloc][Ktot], box {64, BN/2}
   CUtensorMap tm_y;   // output: [M][Cout_p] box {64, 128}; A_HALO: {C, W, H, N} box {64, P, 128/P, 1}
   CUtensorMap tm_r;   // residual, same geometry as the output
+  CUtensorMap tm_yw;  // output, one warp's 32 rows per box (warp_store)
+  int warp_store;     // every epilogue warp stores its own 32 rows (no block-level barrier per slab)
   CUtensorMap tm_a2;  // A_MATRIX with a second source (ConvParams::x2): im2col-mode map {K2, W2, H2, N}, 1x1 window, stride (sw2, sh2)
   int nkb1;           // k-blocks served by tm_a; the rest come from tm_a2 (== Ktot / 64 when there is no second source)
   ConvParams p;
@@ -254,6 +256,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
     const int row = q * 32 + lane;
     const uint32_t rsw = (uint32_t)(row & 7);
     const bool store_thread = (threadIdx.x & 127) == 0;
+    const bool wstore = args.warp_store != 0;
     const uint32_t per_grp = (uint32_t)plan.nout >> 1;       // staging slabs of this group: 1 or 2
     uint32_t mine = 0;                                       // slabs this group has processed
     // bias vector -> shared memory (all 256 epilogue threads)
@@ -285,10 +288,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
         const uint32_t out_row = out_slab + (uint32_t)row * 128u;
         ++mine;
         if (has_res) ptx::mbar_wait(&rfull[rslot], (g / NRES) & 1u);
-        if (store_thread) {                                       // the store that last used this staging slab has finished reading it
-          if (per_grp == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
+        if (wstore) {
+          // per-warp stores: this warp's own previous store from this staging slab has finished reading its 32 rows
+          if (lane == 0) { if (per_grp == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>(); }
+          __syncwarp();
+        } else {
+          if (store_thread) {                                     // the store that last used this staging slab has finished reading it
+            if (per_grp == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
+          }
+          ptx::named_bar_sync(1 + grp, 128);
         }
-        ptx::named_bar_sync(1 + grp, 128);
         ptx::tmem_ld_wait();
         const uint32_t bias = bias_base + (uint32_t)(n0 + (AMODE == A_S2D ? 0 : h * 64)) * 4u;
         epilogue_chunk<T, GEN>(v0, bias, out_row, res_row, rsw, 0, has_res, args.e1, args.e2);
@@ -298,6 +307,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
           if (lane == 0) ptx::mbar_arrive(&rempty[rslot]);
         }
         ptx::fence_proxy_async();                                 // staging writes -> visible to the TMA engine
+        if (wstore) {
+          __syncwarp();
+          if (lane == 0) {
+            if (tp.valid) {
+              const uint32_t src = out_slab + (uint32_t)q * 4096u;      // rows 32 q .. 32 q + 31 of the slab
+              if (AMODE == A_S2D) ptx::tma_store_5d(&args.tm_yw, src, 0, h, tp.w0, tp.h0 + q, tp.img);
+              else if (BOX4D) ptx::tma_store_4d(&args.tm_yw, src, n0 + h * 64, (q * 32) % args.rows_p, tp.h0 + (q * 32) / args.rows_p, tp.img);
+              else ptx::tma_store_2d(&args.tm_yw, src, n0 + h * 64, tp.m0 + q * 32);
+            }
+            ptx::bulk_commit();
+          }
+          continue;
+        }
         ptx::named_bar_sync(1 + grp, 128);
         if (store_thread) {
           if (tp.valid) {
@@ -313,7 +335,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
     }
-    if (store_thread) ptx::bulk_wait_all0();
+    if (wstore ? lane == 0 : store_thread) ptx::bulk_wait_all0();
   } else if (warp == MMA_WARP) {
     // ===================== MMA issuer (leader CTA; whole warp walks the loop, one elected lane issues) =====================
     if (!leader) {
