@@ -108,7 +108,14 @@ bool ws_applies(const ConvParams& p, int bn, int a_mode) {
   const int ws_bytes = (p.Ktot / BK) * (bn / 2) * 128;
   const char* no_ws = getenv("B200_NO_WS");
   const int min_sa = a_mode == A_HALO ? 3 : 4;
-  return p.Cout_alloc == bn && ws_bytes <= WS_MAX_BYTES && plan3(bn, p.res != nullptr, ws_bytes, a_mode, rows_pitch(p), p.Cout_alloc, p.Ktot / BK).sa >= min_sa &&
+  // One N tile: the whole weight matrix is resident.  Several N tiles: with a cluster count that is a multiple of the N tile count every
+  // cluster sees ONE fixed N tile (tile = cluster + k * clusters, n = tile % n_tiles), so its half of THAT tile's weights can be resident
+  // too (launch_tc3 rounds the grid accordingly).  B200_TC3_WSN=0 keeps the single-N-tile rule.
+  const int n_tiles = p.Cout_alloc / bn;
+  const char* wsn = getenv("B200_TC3_WSN");
+  const bool multi_ok = !(wsn && wsn[0] == '0') && n_tiles >= 2 && n_tiles <= 8 && pair_slots() / n_tiles >= 8;
+  return (n_tiles == 1 || multi_ok) && ws_bytes <= WS_MAX_BYTES &&
+         plan3(bn, p.res != nullptr, ws_bytes, a_mode, rows_pitch(p), p.Cout_alloc, p.Ktot / BK).sa >= (n_tiles > 1 ? 3 : min_sa) &&
          !(no_ws && no_ws[0] == '1');
 }
 
@@ -202,7 +209,9 @@ void launch_tc3(const ConvParams& p, bool bf16, int bn, int a_mode, cudaStream_t
     }
   }
   a.nkb1 = (p.K2 > 0 ? p.Cin_p : p.Ktot) / BK;
-  const int grid = 2 * std::min(a.num_tiles, pair_slots());
+  int clusters = std::min(a.num_tiles, pair_slots());
+  if (ws && a.n_tiles > 1) clusters -= clusters % a.n_tiles;      // resident weights of one fixed N tile per cluster (ws_applies)
+  const int grid = 2 * clusters;
   const unsigned smem = plan3(bn, a.p.res != nullptr, ws ? (p.Ktot / BK) * (bn / 2) * 128 : 0, a_mode, a.rows_p, p.Cout_alloc, p.Ktot / BK).total;
   launch_tc3_typed<T>(a, bn, a_mode, ws, grid, smem, s);
 }
@@ -238,6 +247,7 @@ static double tc3_cost(const ConvParams& p, int bn, int a_mode, int sms) {
 int conv_tc3_pick_bn(const ConvParams& p) {
   const int a_mode = a_mode_of(p);
   if (a_mode == A_S2D) return p.Cout_alloc;   // weights resident, one N tile
+  { const char* e = getenv("B200_TC3_FORCE_BN"); const int f = e ? atoi(e) : 0; if ((f == 64 || f == 128 || f == 256) && p.Cout_alloc % f == 0) return f; }   // tests
   const int sms = 2 * pair_slots();
   int best = 0;
   double best_c = 0;

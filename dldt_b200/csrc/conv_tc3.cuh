@@ -430,11 +430,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
     const uint32_t fullB_leader = ptx::smem_u32(&fullB[0]) & ptx::PEER_BIT_MASK;
     const uint32_t wfull_leader = ptx::smem_u32(wfull) & ptx::PEER_BIT_MASK;
     const int HoWo = p.Ho * p.Wo;
-    if (WS) {   // this CTA's half of the whole weight matrix, once
+    if (WS) {   // this CTA's half of the weights of this cluster's (only) N tile, once: the host makes the cluster count a multiple of n_tiles
       if (lane == 0) {
+        const int first = args.reverse ? num_tiles - 1 - cluster : cluster;
+        const int n_fixed = first % n_tiles;
         if (leader) ptx::mbar_arrive_expect_tx(wfull, 2u * (uint32_t)nkb * B_BYTES);
         for (int kb = 0; kb < nkb; ++kb)
-          ptx::tma_load_2d_pair(smem_base + plan.w_off + (uint32_t)kb * B_BYTES, &args.tm_w, wfull_leader, kb * BK, (int)rank * (BN / 2));
+          ptx::tma_load_2d_pair(smem_base + plan.w_off + (uint32_t)kb * B_BYTES, &args.tm_w, wfull_leader, kb * BK, n_fixed * BN + (int)rank * (BN / 2));
       }
       __syncwarp();
     }

@@ -21,6 +21,8 @@ CASES = {
     "mat_nows_bn256_x2": (2, 512, 14, 14, 512, 1, 1, 0, False, "relu", "BF16", {}, "tma"),
     "mat_bn128_nows": (2, 128, 14, 14, 128, 1, 1, 0, False, "relu", "BF16", {"B200_NO_WS": "1"}, "tma"),
     "mat_res_nows": (2, 512, 14, 14, 512, 1, 1, 0, True, "relu", "BF16", {}, "tma"),
+    "mat_ws_two_n_tiles": (4, 64, 28, 28, 512, 1, 1, 0, False, "relu", "BF16", {}, "tma"),
+    "mat_ws_four_n_tiles_res": (3, 256, 20, 20, 256, 1, 1, 0, True, "relu", "BF16", {"B200_TC3_FORCE_BN": "64"}, "tma"),
     "mat_swish_fp16": (2, 64, 16, 16, 192, 1, 1, 0, False, "swish", "FP16", {}, "tma"),
     "mat_k2048_n1000": (3, 2048, 7, 7, 1000, 1, 1, 0, False, "none", "BF16", {}, "tma"),
     "im2col_s2": (2, 128, 30, 30, 256, 3, 2, 1, False, "relu", "BF16", {}, "im2col"),
