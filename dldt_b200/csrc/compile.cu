@@ -692,7 +692,7 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
   s.name = name; s.type = type; s.fused = fused; s.flops = flops; s.bytes = bytes;
   const int dt = cd_;
   int bn = 0, bn3 = 0;
-  bool v2 = false, v3 = false, both = false;
+  bool v2 = false, v3 = false, both = false, small_tune = false;
   std::string impl2, impl3;
   if (tc) {
     bn = conv_tc_pick_bn(p.Cout_p);
@@ -712,7 +712,10 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
     both = v3 && !chained && !(tune && tune[0] == '0') && !(force3 && force3[0] == '1') && (!kcat || conv_tc3_preferred(p));
     impl2 = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_128x" + std::to_string(bn) + "x64" +
             (v2 ? (conv_tc2_a_is_matrix(p) ? "_persistent_tma" : (conv_tc2_a_is_im2col(p) ? "_persistent_im2col" : "_persistent_gather")) : "");
-    if (v3) {
+    // small launches (fewer tiles than SM pairs: batch 1): the static policy keeps the single-CTA kernel, but the time is one operand-latency
+    // chain per k-block, so the N tile (stages that fit, tiles in flight) and the kernel are worth measuring there too
+    small_tune = v2 && !v3 && !chained && !kcat && conv_tc3_supported(p) && !(tune && tune[0] == '0') && !(force3 && (force3[0] == '0' || force3[0] == '1'));
+    if (v3 || small_tune) {
       bn3 = conv_tc3_pick_bn(p);
       impl3 = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_pair256x" + std::to_string(bn3) + "x64_" + conv_tc3_mode_name(p);
     }
@@ -732,7 +735,8 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
     p.reverse = (v2 && !(no_alt && no_alt[0] == '1')) ? !in_dir : 0;
     if (ty && ty->buf.space == SP_ARENA) box_dir_[ty->buf.box] = p.reverse;
   }
-  // which: 0 = per the static policy, 2 = conv_tc2, 3 = conv_tc3 at its modelled N tile, 64/128/256 = conv_tc3 at that N tile
+  // which: 0 = per the static policy, 2 = conv_tc2, 3 = conv_tc3 at its modelled N tile, 64/128/256 = conv_tc3 at that N tile,
+  // 1064 = conv_tc2 at N tile 64
   auto make_launch = [=](int which) {
     return [=](const RunCtx& c) {
       ConvParams q = p;
@@ -745,9 +749,9 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
         launch_conv_tc3f(q, dt, (cudaStream_t)c.stream);
         return;
       }
-      const bool use3 = which >= 3 || (which == 0 && v3);
+      const bool use3 = (which >= 3 && which < 1000) || (which == 0 && v3);
       if (tc && use3) launch_conv_tc3(q, dt, which > 3 ? which : bn3, (cudaStream_t)c.stream);
-      else if (tc && v2) launch_conv_tc2(q, dt, bn, (cudaStream_t)c.stream);
+      else if (tc && v2) launch_conv_tc2(q, dt, which > 1000 ? which - 1000 : bn, (cudaStream_t)c.stream);
       else if (tc) launch_conv_tc(q, dt, bn, (cudaStream_t)c.stream);
       else launch_conv_f32(q, (cudaStream_t)c.stream);
     };
@@ -762,6 +766,18 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
       s.alts.emplace_back(nm, make_launch(b));     // which > 3: explicit N tile of the pair kernel
     }
     if (!has_x2) s.alts.emplace_back(impl2, make_launch(2));
+  } else if (small_tune) {
+    const std::string pre = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16");
+    s.alts.emplace_back(impl2, make_launch(2));                    // the static choice first
+    if (bn == 128) {
+      std::string nm = impl2;
+      nm.replace(nm.find("_128x128x64"), 11, "_128x64x64");
+      s.alts.emplace_back(nm, make_launch(1064));
+    }
+    for (int b : {256, 128, 64}) {
+      if (p.Cout_alloc % b) continue;
+      s.alts.emplace_back(pre + "_pair256x" + std::to_string(b) + "x64_" + conv_tc3_mode_name(p), make_launch(b));
+    }
   }
   emit(std::move(s), {tx, tres, tx2}, {ty, tz});
 }
