@@ -78,7 +78,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -86,12 +86,14 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples whose arrival time falls inside [t0, t1] (the timed region); the sampler itself is started before the warm-up so that
+        nvidia-smi's start-up latency does not eat the window.  Falls back to the samples nearest to the window."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=3)
@@ -99,7 +101,16 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = list(self.lines)
+        if t0 is not None and t1 is not None:
+            inside = [ln for (ts, ln) in lines if t0 - 0.01 <= ts <= t1 + 0.03]
+            if not inside and lines:     # window shorter than the sampling period: the nearest two samples
+                mid = 0.5 * (t0 + t1)
+                inside = [ln for (ts, ln) in sorted(lines, key=lambda p: abs(p[0] - mid))[:2]]
+            sel = inside
+        else:
+            sel = [ln for (_, ln) in lines]
+        for ln in sel:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -225,16 +236,18 @@ def run_b200(args, rank, local_rank, world):
     pk = peaks()
 
     # ---- value: device-resident, CUDA events on the request's stream ----
+    sampler = ClockSampler(local_rank)
+    if not args.no_clock_sampler:
+        sampler.start()                                # before the warm-up: nvidia-smi needs ~100 ms to deliver its first line
     for _ in range(max(args.warmup, 3)):
         req.launch_device()
     req.wait()
-    sampler = ClockSampler(local_rank)
     barrier()
-    if not args.no_clock_sampler:
-        sampler.start()
+    t_begin = time.time()
     ms_total = req.time_launches(args.steps)          # b200_request_time: event, K graph launches, event, sync
+    t_end = time.time()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, t_end)
     ms_total = max_over_ranks(ms_total)
     ms_step = ms_total / args.steps
     # diagnostics (outside the timed region): the same launch timed in short bursts, to expose clock drift / interference
