@@ -204,6 +204,9 @@ def run_b200(args, rank, local_rank, world):
 
     dist = None
     if world > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION (the image's default): rank 0's stdout must be the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
