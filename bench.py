@@ -149,6 +149,8 @@ def reference_cpu_run(batch, warmup, steps, bf16=True):
         x.tofile(xin)
         env = dict(os.environ)
         env["LD_LIBRARY_PATH"] = os.path.join(REF_DIR, "lib") + ":" + env.get("LD_LIBRARY_PATH", "")
+        # all host threads (torchrun exports OMP_NUM_THREADS=1 to its children; only rank 0 runs this leg)
+        env["OMP_NUM_THREADS"] = str(cores)
         cmd = [IE_RUN, "--model", xml, "--device", "CPU", "--output-dir", tmp, "--niter", str(warmup + steps),
                "--plugins", os.path.join(REF_DIR, "lib", "plugins.xml"), "--input", "data=" + xin, "--input-precision", "data=U8",
                "--config", "ENFORCE_BF16=%s" % ("YES" if bf16 else "NO")]
@@ -199,6 +201,11 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 def run_b200(args, rank, local_rank, world):
     import numpy as np
+    # Whatever libraries print on stdout (NCCL's version banner under torchrun) must not reach the driver: fd 1 is pointed at stderr for
+    # the whole run and the one JSON line is written to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     from dldt_b200 import Core, zoo
 
@@ -346,10 +353,11 @@ def run_b200(args, rank, local_rank, world):
             line["cpu_baseline"] = {"value": round(cb["value"], 2), "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
         except Exception as e:  # the baseline is a reported number, never a reason to lose the GPU line
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % str(e)[:200]}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    if rank == 0:
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
 def main():
