@@ -1,0 +1,98 @@
+"""Fast paths of the memory-bound kernels (kernels_misc.cu) at the shapes where they apply, against the numpy oracle through the C ABI:
+fused scale + mask + softmax (BERT attention), plain warp-per-row softmax, warp-per-row MVN with gamma/beta, 16-byte permute, depthwise
+3x3 stride 1/2 with odd widths, packed 3x3/s2 max-pool, warp-per-channel-group global average pool.  The impl strings of the exec graph
+are checked so that a silent fall back to the generic kernels fails the test."""
+import numpy as np
+import pytest
+
+from dldt_b200 import Core, Function
+from oracle import interp
+from tests.util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def run(f, inputs, prec):
+    ref = interp.run(f, inputs)
+    net = Core().load_network(f, "B200", {"B200_INFERENCE_PRECISION": prec})
+    got = net.create_infer_request().infer(inputs)
+    return ref, got, net.get_exec_graph_info()
+
+
+@pytest.mark.parametrize("prec,tol", [("FP32", 1e-5), ("BF16", 1.5e-2)])
+@pytest.mark.parametrize("seq,mask_batch", [(384, True), (128, False), (40, True)])
+def test_attention_softmax_is_one_kernel(prec, tol, seq, mask_batch):
+    rng = np.random.default_rng(seq)
+    n, heads = 2, 3
+    f = Function("attn")
+    x = f.parameter((n, heads, seq, seq), name="scores")
+    m = f.parameter((n if mask_batch else 1, 1, 1, seq), name="mask")
+    y = f.softmax(f.add(f.multiply(x, f.constant(np.float32(0.125))), m), 3)
+    f.result(y)
+    xin = rng.standard_normal((n, heads, seq, seq)).astype(np.float32) * 4
+    mask = np.where(rng.uniform(size=(n if mask_batch else 1, 1, 1, seq)) < 0.2, -10000.0, 0.0).astype(np.float32)
+    ref, got, eg = run(f, {"scores": xin, "mask": mask}, prec)
+    assert [e["impl"] for e in eg if e["type"] in ("Softmax", "Eltwise")] == ["softmax_scale_mask_warp_rows"], eg
+    a, b = list(got.values())[0], list(ref.values())[0]
+    assert rel_l2(a, b) < tol
+    assert np.allclose(a.sum(-1), 1.0, atol=2e-2 if prec == "BF16" else 1e-5)
+
+
+@pytest.mark.parametrize("prec,tol", [("FP32", 1e-5), ("BF16", 1.5e-2)])
+def test_plain_softmax_and_layernorm_rows(prec, tol):
+    rng = np.random.default_rng(11)
+    f = Function("ln")
+    x = f.parameter((6, 50, 768), name="x")
+    g = rng.uniform(0.5, 1.5, (768,)).astype(np.float32)
+    b = rng.uniform(-0.2, 0.2, (768,)).astype(np.float32)
+    y = f.add(f.multiply(f.mvn(x, [2], True, 1e-12, "INSIDE_SQRT"), g), b)
+    f.result(f.softmax(y, 2))
+    xin = rng.standard_normal((6, 50, 768)).astype(np.float32) * 3 + 1
+    ref, got, eg = run(f, {"x": xin}, prec)
+    impls = [e["impl"] for e in eg]
+    assert "softmax_warp_rows" in impls, impls
+    assert rel_l2(list(got.values())[0], list(ref.values())[0]) < tol
+
+
+@pytest.mark.parametrize("prec", ["FP32", "BF16"])
+def test_head_transpose_moves_16_byte_vectors(prec):
+    rng = np.random.default_rng(5)
+    f = Function("perm")
+    x = f.parameter((3, 40, 12, 64), name="x")
+    f.result(f.transpose(f.relu(x), (0, 2, 1, 3)))
+    xin = rng.standard_normal((3, 40, 12, 64)).astype(np.float32)
+    ref, got, eg = run(f, {"x": xin}, prec)
+    a, b = list(got.values())[0], list(ref.values())[0]
+    assert a.shape == (3, 12, 40, 64) and rel_l2(a, b) < (1e-6 if prec == "FP32" else 5e-3)
+
+
+@pytest.mark.parametrize("stride,h,w", [(1, 20, 23), (2, 21, 30), (2, 56, 56)])
+def test_depthwise_3x3_fast_path(stride, h, w):
+    rng = np.random.default_rng(stride * 100 + w)
+    c = 48
+    f = Function("dw")
+    x = f.parameter((2, c, h, w), name="x")
+    wdw = (rng.standard_normal((c, 1, 1, 3, 3)) * 0.4).astype(np.float32)
+    y = f.group_convolution(x, wdw, (stride, stride), (1, 1), (1, 1), (1, 1))
+    y = f.clamp(f.add(y, rng.standard_normal((1, c, 1, 1)).astype(np.float32) * 0.1), 0.0, 6.0)
+    f.result(y)
+    xin = rng.standard_normal((2, c, h, w)).astype(np.float32)
+    ref, got, eg = run(f, {"x": xin}, "BF16")
+    assert any(e["impl"].startswith("dw_") for e in eg)
+    assert rel_l2(list(got.values())[0], list(ref.values())[0]) < 1e-2
+
+
+@pytest.mark.parametrize("h,w", [(28, 28), (15, 21), (7, 7)])
+def test_maxpool_3x3_s2_and_global_average_pool(h, w):
+    rng = np.random.default_rng(h * w)
+    c = 64
+    f = Function("pools")
+    x = f.parameter((3, c, h, w), name="x")
+    p = f.max_pool(f.relu(x), (3, 3), (2, 2), (1, 1), (1, 1))
+    gmean = f.reduce_mean(x, [2, 3], keep_dims=True)
+    f.result(p)
+    f.result(gmean)
+    xin = rng.standard_normal((3, c, h, w)).astype(np.float32)
+    ref, got, eg = run(f, {"x": xin}, "BF16")
+    for k in ref:
+        assert got[k].shape == ref[k].shape and rel_l2(got[k], ref[k]) < 1e-2, k
