@@ -29,7 +29,7 @@ def rel_l2(a, b):
 
 def run(kind):
     build = {"mobilenet": (lambda b: zoo.mobilenet_v2(batch=b), 64, "BF16", 4),
-             "ssd": (lambda b: zoo.ssd300_resnet34(batch=b), 32, "FP16", 2),
+             "ssd": (lambda b: zoo.ssd300_resnet34(batch=b, head_scale=0.02), 32, "FP16", 2),
              "bert": (lambda b: zoo.bert_base(batch=b), 64, "BF16", 2)}[kind]
     mk, batch, prec, small = build
     core = Core()
@@ -47,7 +47,11 @@ def run(kind):
             # detections [1,1,N*keep,7]: compare the kept (image, label) multiset and the boxes of matching rows
             va, vb = a.reshape(-1, 7), b.reshape(-1, 7)
             na, nb = int((va[:, 0] >= 0).sum()), int((vb[:, 0] >= 0).sum())
-            print("[%s] %s: detections %s=%d fp32=%d  finite %s" % (kind, k, prec, na, nb, bool(np.isfinite(a).all())), flush=True)
+            # rows are (image, label, conf, box): compare the (image, label) multisets and the boxes of the rows both runs kept in the same slot
+            same = int(((va[:min(na, nb), 0] == vb[:min(na, nb), 0]) & (va[:min(na, nb), 1] == vb[:min(na, nb), 1])).sum())
+            box_err = rel_l2(va[:min(na, nb), 2:], vb[:min(na, nb), 2:]) if min(na, nb) else 0.0
+            print("[%s] %s: detections %s=%d fp32=%d  same (image,label) in slot %d  rel-L2 of conf+box %.3e  finite %s"
+                  % (kind, k, prec, na, nb, same, box_err, bool(np.isfinite(a).all())), flush=True)
         else:
             extra = ""
             if a.ndim == 2 and a.shape[1] > 1:
