@@ -47,11 +47,11 @@ def run(kind):
             # detections [1,1,N*keep,7]: compare the kept (image, label) multiset and the boxes of matching rows
             va, vb = a.reshape(-1, 7), b.reshape(-1, 7)
             na, nb = int((va[:, 0] >= 0).sum()), int((vb[:, 0] >= 0).sum())
-            # rows are (image, label, conf, box): compare the (image, label) multisets and the boxes of the rows both runs kept in the same slot
-            same = int(((va[:min(na, nb), 0] == vb[:min(na, nb), 0]) & (va[:min(na, nb), 1] == vb[:min(na, nb), 1])).sum())
-            box_err = rel_l2(va[:min(na, nb), 2:], vb[:min(na, nb), 2:]) if min(na, nb) else 0.0
-            print("[%s] %s: detections %s=%d fp32=%d  same (image,label) in slot %d  rel-L2 of conf+box %.3e  finite %s"
-                  % (kind, k, prec, na, nb, same, box_err, bool(np.isfinite(a).all())), flush=True)
+            # with random-init heads the 81 class scores of a prior are nearly tied, so WHICH 200 boxes survive differs between
+            # precisions by construction; DetectionOutput's ordering rules are pinned at op level with identical inputs
+            # (tests/test_gpu_golden.py: detout_* / nms_* cases, bit-exact ids in fp32 mode)
+            print("[%s] %s: detections kept %s=%d fp32=%d, all finite %s (slot-wise comparison not meaningful: near-tied random-init scores)"
+                  % (kind, k, prec, na, nb, bool(np.isfinite(a).all())), flush=True)
         else:
             extra = ""
             if a.ndim == 2 and a.shape[1] > 1:
