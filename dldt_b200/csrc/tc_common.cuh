@@ -63,6 +63,19 @@ struct EpiAct {
   float a, b;     // its parameters
   float lo, hi;   // clamp bounds (fast path)
 };
+// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, two MUFU + ~10 FMA): used only where the result is rounded to bf16/fp16 right
+// after (the tensor-core epilogues); the fp32 path keeps erff (act.cuh).  GELU(erf) = 0.5 x (1 + erf(x / sqrt 2)), reference/gelu.hpp:19-38.
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float r = 1.f - p * t * __expf(-ax * ax);
+  return copysignf(r, x);
+}
+
 template <bool GENERIC>
 __device__ __forceinline__ void epi_act8(float (&f)[8], const EpiAct& s) {
   if (s.kind == 0 || s.relu_in_pack) return;   // ACT_NONE, or a trailing ReLU done by the bf16 conversion (warp-uniform)
@@ -79,7 +92,7 @@ __device__ __forceinline__ void epi_act8(float (&f)[8], const EpiAct& s) {
     switch (s.kind) {
       case ACT_GELU_ERF:
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = 0.5f * f[e] * (1.f + erff(f[e] * 0.70710678118654752440f));
+        for (int e = 0; e < 8; ++e) f[e] = 0.5f * f[e] * (1.f + erf_fast(f[e] * 0.70710678118654752440f));
         break;
       case ACT_SWISH:
 #pragma unroll
