@@ -564,13 +564,11 @@ __global__ void __launch_bounds__(256) mvn_warp_rows_kernel(const T* __restrict_
   for (int k = 0; k < CHUNKS; ++k) {
     const int c = (k * 32 + lane) * 8;
     if (c < cols) {
+      float gm[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, bt[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (gamma) load8<float>(gamma + c, gm);          // two 16-byte loads (c is a multiple of 8: 32-byte aligned)
+      if (beta) load8<float>(beta + c, bt);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float r = (v[k][e] - mean) * scale;
-        if (gamma) r *= __ldg(gamma + c + e);
-        if (beta) r += __ldg(beta + c + e);
-        v[k][e] = r;
-      }
+      for (int e = 0; e < 8; ++e) v[k][e] = fmaf((v[k][e] - mean) * scale, gm[e], bt[e]);
       store8<T>(py + c, v[k]);
     }
   }
