@@ -96,3 +96,16 @@ def test_maxpool_3x3_s2_and_global_average_pool(h, w):
     ref, got, eg = run(f, {"x": xin}, "BF16")
     for k in ref:
         assert got[k].shape == ref[k].shape and rel_l2(got[k], ref[k]) < 1e-2, k
+
+
+@pytest.mark.parametrize("shape", [(3, 4, 40, 64), (2, 3, 384, 64), (2, 2, 70, 34), (1, 2, 37, 50)])
+def test_swap_of_the_last_two_dims(shape):
+    # [N, heads, S, 64] -> [N, heads, 64, S] (V^T of BERT's attention): tiled shared-memory transpose for even sizes, generic permute otherwise
+    rng = np.random.default_rng(shape[2])
+    f = Function("t")
+    x = f.parameter(shape, name="x")
+    f.result(f.transpose(f.relu(x), (0, 1, 3, 2)))
+    xin = rng.standard_normal(shape).astype(np.float32)
+    ref, got, eg = run(f, {"x": xin}, "BF16")
+    a, b = list(got.values())[0], list(ref.values())[0]
+    assert a.shape == b.shape and rel_l2(a, b) < 5e-3
