@@ -1027,6 +1027,17 @@ void Lowerer::lower_matmul_general(const Node& n, const FusedConv* f) {
   p.M = (int)M; p.Ktot = (int)round_up(K, 64); p.Cout_alloc = (int)round_up(Nn, bn); p.ldy = (int)Nn;
   p.w_ld = (int)K; p.w_rows = (int)Nn; p.w_k = (int)K;
   p.batch = (int)batch_a; p.x_bs = M * K; p.w_bs = batch_b == 1 ? 0 : Nn * K; p.y_bs = M * Nn;
+  {
+    // per-batch [M][K] x [N][K]^T with tile-aligned M: the batches are one flat [batch*M][K] activation matrix whose 128-row tiles each
+    // pick their batch's weight rows -- one persistent launch with TMA stores instead of batch x tiles single-tile CTAs
+    const char* flat = getenv("B200_MATMUL_FLAT");
+    if (tc && batch_a > 1 && batch_b == batch_a && M % 128 == 0 && K % 64 == 0 && Nn % 64 == 0 && Nn % bn == 0 && batch_a * M < (int64_t(1) << 31) &&
+        !(flat && flat[0] == '0')) {
+      p.N = p.M = (int)(batch_a * M);
+      p.batch = 1; p.x_bs = p.w_bs = p.y_bs = 0;
+      p.w_grp_m = (int)M; p.w_grp_rows = (int)Nn;
+    }
+  }
   LTensor res;
   BufRef rref;
   std::string fused = n.name;

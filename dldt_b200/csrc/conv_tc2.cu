@@ -346,6 +346,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
         const int tile = args.reverse ? num_tiles - 1 - t_ : t_;
         const int m0 = (tile / n_tiles) * BM;
         const int n0 = (tile % n_tiles) * BN;
+        const int w_row0 = p.w_grp_m ? (m0 / p.w_grp_m) * p.w_grp_rows : 0;   // grouped weights: this tile's weight matrix
         int bn = 0, bh = 0, bw = 0;
         if (args.a_tma == 2) {                       // first output pixel of the tile -> base pixel of the im2col bounding box
           bn = m0 / HoWo;
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
             ptx::tma_load_im2col_4d(a_dst, &args.tm_a, &full_bar[s], chunk * BK, bw, bh, bn, (uint32_t)(fs * p.dw), (uint32_t)(fr * p.dh));
             if (++chunk == cpt) { chunk = 0; ++tap; if (++fs == p.kw) { fs = 0; ++fr; } }
           }
-          if (!ws) ptx::tma_load_2d(a_dst + A_BYTES, &args.tm_w, &full_bar[s], kb * BK, n0);
+          if (!ws) ptx::tma_load_2d(a_dst + A_BYTES, &args.tm_w, &full_bar[s], kb * BK, n0 + w_row0);
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
@@ -486,10 +487,10 @@ void launch_tc2(const ConvParams& p, bool bf16, cudaStream_t s) {
   {
     const int ws_bytes = (p.Ktot / BK) * BN * 128;
     const char* no_ws = getenv("B200_NO_WS");
-    a.ws = (a.n_tiles == 1 && ws_bytes <= WS_MAX_BYTES && smem_plan<BN>(p.res != nullptr, ws_bytes).stages >= 4 && !(no_ws && no_ws[0] == '1')) ? 1 : 0;
+    a.ws = (a.n_tiles == 1 && p.w_grp_m == 0 && ws_bytes <= WS_MAX_BYTES && smem_plan<BN>(p.res != nullptr, ws_bytes).stages >= 4 && !(no_ws && no_ws[0] == '1')) ? 1 : 0;
   }
   a.a_tma = conv_tc2_a_is_matrix(p) ? 1 : (conv_tc2_a_is_im2col(p) ? 2 : 0);
-  a.tm_w = make_tmap_2d(p.w, bf16, (uint64_t)p.Ktot, (uint64_t)p.Cout_alloc, (uint64_t)p.w_ld * 2, BK, BN);
+  a.tm_w = make_tmap_2d(p.w, bf16, (uint64_t)p.Ktot, p.w_grp_m ? (uint64_t)(p.M / p.w_grp_m) * p.w_grp_rows : (uint64_t)p.Cout_alloc, (uint64_t)p.w_ld * 2, BK, BN);
   a.tm_y = make_tmap_2d(p.y, bf16, (uint64_t)p.Cout_p, (uint64_t)p.M, (uint64_t)p.ldy * 2, 64, BM);
   a.tm_r = p.res ? make_tmap_2d(p.res, bf16, (uint64_t)p.Cout_p, (uint64_t)p.M, (uint64_t)p.ldy * 2, 64, BM) : a.tm_y;
   a.tm_a = a.a_tma == 1 ? make_tmap_2d(p.x, bf16, (uint64_t)p.Cin_p, (uint64_t)p.M, (uint64_t)p.Cin_p * 2, BK, BM)
@@ -559,6 +560,7 @@ bool conv_acts_are_clamps(const ConvParams& p) {
 
 bool conv_tc2_supported(const ConvParams& p) {
   // one weight matrix for the whole launch (batched activation x activation MatMuls stay on conv_tc.cu), weights fully materialised
+  if (p.w_grp_m && (p.w_grp_m % 128 || p.M % p.w_grp_m || p.w_grp_rows != p.Cout_alloc)) return false;   // tiles must not straddle groups
   return p.batch == 1 && !p.out_f32 && p.w_rows == p.Cout_alloc && p.w_k == p.Ktot && p.w_ld == p.Ktot;
 }
 

@@ -49,6 +49,9 @@ struct ConvParams {
   int act3 = 0;
   float a3 = 0, b3 = 0;
   int batch = 1;               // blockIdx.z batches (batched MatMul); strides in elements
+  // grouped weights (batched activation x activation MatMul flattened into one launch of the persistent kernel): output rows
+  // [g*w_grp_m, (g+1)*w_grp_m) use weight rows [g*w_grp_rows, (g+1)*w_grp_rows); 0 = one weight matrix
+  int w_grp_m = 0, w_grp_rows = 0;
   int64_t x_bs = 0, w_bs = 0, y_bs = 0;
 };
 // dtype: B200_BF16 or B200_F16.  bn: N tile (64 or 128).

@@ -109,3 +109,30 @@ def test_swap_of_the_last_two_dims(shape):
     ref, got, eg = run(f, {"x": xin}, "BF16")
     a, b = list(got.values())[0], list(ref.values())[0]
     assert a.shape == b.shape and rel_l2(a, b) < 5e-3
+
+
+@pytest.mark.parametrize("prec,tol", [("BF16", 1.5e-2), ("FP16", 4e-3)])
+@pytest.mark.parametrize("seq,dh", [(128, 64), (384, 64), (256, 128)])
+def test_attention_matmuls_run_as_one_grouped_launch(prec, tol, seq, dh, monkeypatch):
+    """scores = Q K^T and context = P V with tile-aligned sequence lengths: every (batch, head) pair is a weight group of one flat
+    persistent launch (ConvParams::w_grp_m), not a blockIdx.z batch of single-tile CTAs; same result as the batched launch"""
+    rng = np.random.default_rng(seq + dh)
+    n, heads = 2, 3
+    f = Function("attn_mm")
+    q = f.parameter((n, heads, seq, dh), name="q")
+    k = f.parameter((n, heads, seq, dh), name="k")
+    v = f.parameter((n, heads, seq, dh), name="v")
+    s = f.matmul(q, k, transpose_b=True)
+    f.result(s)
+    f.result(f.matmul(f.softmax(f.multiply(s, f.constant(np.float32(0.125))), 3), v))
+    ins = {nm: rng.standard_normal((n, heads, seq, dh)).astype(np.float32) for nm in "qkv"}
+    ref, got, eg = run(f, ins, prec)
+    mm = [e["impl"] for e in eg if e["type"] == "MatMul"]
+    assert len(mm) == 2 and all("persistent_tma" in i for i in mm), mm
+    for a, b in zip(got.values(), ref.values()):
+        assert rel_l2(a, b) < tol
+    monkeypatch.setenv("B200_MATMUL_FLAT", "0")
+    _, got0, eg0 = run(f, ins, prec)
+    assert not any("persistent" in e["impl"] for e in eg0 if e["type"] == "MatMul")
+    for a, b in zip(got.values(), got0.values()):
+        assert rel_l2(a, b) < 2e-3
