@@ -440,6 +440,16 @@ __global__ void scale_shift_kernel(const T* __restrict__ x, const float* __restr
 // row, the row lives in registers between the passes, fp32 math (reference/softmax.hpp:19-47 after the Multiply / Add of the attention
 // pattern).  mask == nullptr: plain (scaled) softmax.  Reads and writes each element once: the HBM-bound form of BERT's
 // scale -> mask-add -> softmax chain (three kernels, five passes over the [N, heads, S, S] scores otherwise).
+// 2^x on the MUFU pipe (2 ulp): the row kernels below work in the base-2 domain (inputs pre-multiplied by log2 e), one instruction per
+// exponential instead of expf's range-reduced sequence -- the one-row kernel was ISSUE-bound at 35 instructions per element with expf
+// (ncu: 82% issue slots busy at 3.4 TB/s, profiles/r1_softmax_ncu.txt).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+
 template <typename T, int CHUNKS>
 __global__ void __launch_bounds__(256) softmax_warp_rows_kernel(const T* __restrict__ x, const T* __restrict__ mask, T* __restrict__ y, int64_t rows,
                                                                 int cols, float scale, int64_t rows_per_mask) {
@@ -450,6 +460,7 @@ __global__ void __launch_bounds__(256) softmax_warp_rows_kernel(const T* __restr
   const T* pm = mask ? mask + (row / rows_per_mask) * cols : nullptr;
   float v[CHUNKS][8];
   float m = -FLT_MAX;
+  const float sc2 = scale * kLog2e;                 // base-2 domain: exp(a - m) = 2^((a - m) log2 e)
 #pragma unroll
   for (int k = 0; k < CHUNKS; ++k) {
     const int c = (k * 32 + lane) * 8;
@@ -459,10 +470,10 @@ __global__ void __launch_bounds__(256) softmax_warp_rows_kernel(const T* __restr
         float mk[8];
         load8<T>(pm + c, mk);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[k][e] = v[k][e] * scale + mk[e];
+        for (int e = 0; e < 8; ++e) v[k][e] = fmaf(v[k][e], sc2, mk[e] * kLog2e);
       } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[k][e] *= scale;
+        for (int e = 0; e < 8; ++e) v[k][e] *= sc2;
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) m = fmaxf(m, v[k][e]);
@@ -475,7 +486,7 @@ __global__ void __launch_bounds__(256) softmax_warp_rows_kernel(const T* __restr
     const int c = (k * 32 + lane) * 8;
     if (c < cols) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { v[k][e] = expf(v[k][e] - m); sum += v[k][e]; }
+      for (int e = 0; e < 8; ++e) { v[k][e] = ex2_approx(v[k][e] - m); sum += v[k][e]; }
     }
   }
   sum = warp_sum(sum);
@@ -489,6 +500,70 @@ __global__ void __launch_bounds__(256) softmax_warp_rows_kernel(const T* __restr
       for (int e = 0; e < 8; ++e) v[k][e] *= inv;
       store8<T>(py + c, v[k]);
     }
+  }
+}
+
+// Exact-width variant for 16-bit rows of CHUNKS x 32 x 2W elements (384 = 3 x 32 x 4, 128, 256, 512, 768, 1024): every lane owns the same
+// number of elements (the 8-per-lane layout above leaves half the warp idle on the second chunk of a 384-wide row while still issuing its
+// instructions), no column guards, 32-bit row arithmetic (the 64-bit row / rows_per_mask division alone was ~80 instructions per thread).
+template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t u);
+template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+template <int W> struct WordVec;
+template <> struct WordVec<2> { using type = uint2; };
+template <> struct WordVec<4> { using type = uint4; };
+
+template <typename T, int W, int CHUNKS>
+__global__ void __launch_bounds__(256) softmax_rows_exact_kernel(const T* __restrict__ x, const T* __restrict__ mask, T* __restrict__ y, uint32_t rows,
+                                                                 float scale, uint32_t rows_per_mask) {
+  using Vec = typename WordVec<W>::type;
+  constexpr int COLS = CHUNKS * 32 * 2 * W;
+  const uint32_t row = blockIdx.x * 8u + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const Vec* px = reinterpret_cast<const Vec*>(x + (size_t)row * COLS) + lane;
+  union U { Vec v; uint32_t w[W]; };
+  U raw[CHUNKS], mk[CHUNKS];
+#pragma unroll
+  for (int k = 0; k < CHUNKS; ++k) raw[k].v = __ldg(px + k * 32);
+  if (mask) {
+    const Vec* pm = reinterpret_cast<const Vec*>(mask + (size_t)(row / rows_per_mask) * COLS) + lane;
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) mk[k].v = __ldg(pm + k * 32);
+  }
+  const float sc2 = scale * kLog2e;
+  float v[CHUNKS][2 * W];
+  float m = -FLT_MAX;
+#pragma unroll
+  for (int k = 0; k < CHUNKS; ++k) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      const float2 a = unpack2<T>(raw[k].w[i]);
+      float2 b = make_float2(0.f, 0.f);
+      if (mask) b = unpack2<T>(mk[k].w[i]);
+      v[k][2 * i] = fmaf(a.x, sc2, b.x * kLog2e);
+      v[k][2 * i + 1] = fmaf(a.y, sc2, b.y * kLog2e);
+      m = fmaxf(m, fmaxf(v[k][2 * i], v[k][2 * i + 1]));
+    }
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < CHUNKS; ++k) {
+#pragma unroll
+    for (int e = 0; e < 2 * W; ++e) { v[k][e] = ex2_approx(v[k][e] - m); sum += v[k][e]; }
+  }
+  const float inv = 1.f / warp_sum(sum);
+  Vec* py = reinterpret_cast<Vec*>(y + (size_t)row * COLS) + lane;
+#pragma unroll
+  for (int k = 0; k < CHUNKS; ++k) {
+    U o;
+#pragma unroll
+    for (int i = 0; i < W; ++i) o.w[i] = pack2<T>(v[k][2 * i] * inv, v[k][2 * i + 1] * inv);
+    py[k * 32] = o.v;
   }
 }
 
@@ -914,6 +989,25 @@ void launch_softmax_scale_mask(const void* x, const void* mask, void* y, int64_t
                                cudaStream_t s) {
   if (rows * cols == 0) return;
   B200_CHECK(softmax_fused_supported(cols, dtype), B200_ERR_UNSUPPORTED, "softmax_scale_mask: unsupported row length " << cols);
+  if (dtype != B200_F32 && rows < (int64_t(1) << 31) && rows_per_mask < (int64_t(1) << 31)) {
+    // 16-bit rows whose width splits evenly over the warp: exact-width kernel (B200_SOFTMAX_EXACT=0 keeps the guarded one)
+    static const bool exact = [] { const char* e = getenv("B200_SOFTMAX_EXACT"); return !(e && e[0] == '0'); }();
+    const unsigned g8 = grid_for(rows, 8);
+#define B200_SMX(T, W_, C_) softmax_rows_exact_kernel<T, W_, C_><<<g8, 256, 0, s>>>((const T*)x, (const T*)mask, (T*)y, (uint32_t)rows, scale, (uint32_t)rows_per_mask)
+#define B200_SMX_COLS(T)                                  \
+    switch (exact ? cols : 0) {                            \
+      case 128: B200_SMX(T, 2, 1); return;                 \
+      case 256: B200_SMX(T, 4, 1); return;                 \
+      case 384: B200_SMX(T, 2, 3); return;                 \
+      case 512: B200_SMX(T, 4, 2); return;                 \
+      case 768: B200_SMX(T, 4, 3); return;                 \
+      case 1024: B200_SMX(T, 4, 4); return;                \
+      default: break;                                      \
+    }
+    if (dtype == B200_BF16) { B200_SMX_COLS(__nv_bfloat16) } else { B200_SMX_COLS(__half) }
+#undef B200_SMX_COLS
+#undef B200_SMX
+  }
   const unsigned grid = grid_for(rows, 8);
   const int chunks = (int)((cols + 255) / 256);
 #define B200_SM_LAUNCH(T, C_) softmax_warp_rows_kernel<T, C_><<<grid, 256, 0, s>>>((const T*)x, (const T*)mask, (T*)y, rows, (int)cols, scale, rows_per_mask)

@@ -20,10 +20,11 @@ def run(f, inputs, prec):
 
 
 @pytest.mark.parametrize("prec,tol", [("FP32", 1e-5), ("BF16", 1.5e-2)])
-@pytest.mark.parametrize("seq,mask_batch", [(384, True), (128, False), (40, True)])
-def test_attention_softmax_is_one_kernel(prec, tol, seq, mask_batch):
+@pytest.mark.parametrize("seq,mask_batch,heads", [(384, True, 3), (128, False, 3), (40, True, 3), (384, True, 12), (200, False, 24)])
+def test_attention_softmax_is_one_kernel(prec, tol, seq, mask_batch, heads):
+    # heads = 12 / 24: >= 8192 rows, where 16-bit rows go four to a warp (softmax_warp_multirow_kernel)
     rng = np.random.default_rng(seq)
-    n, heads = 2, 3
+    n = 2
     f = Function("attn")
     x = f.parameter((n, heads, seq, seq), name="scores")
     m = f.parameter((n if mask_batch else 1, 1, 1, seq), name="mask")
