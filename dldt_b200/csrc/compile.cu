@@ -73,6 +73,7 @@ struct FusedConv {
   int res_value = -1;
   int out_value = -1;            // value produced by the last absorbed node
   int emit_at = -1;              // node id at whose position the kernel is emitted
+  int heads_s = 0, heads_h = 0;  // FullyConnected whose [N,S,H*64] -> [N,H,S,64] head split is written by the kernel's stores
   // K-concatenated projection shortcut (fold_shortcuts): a second 1x1 convolution whose output was this one's residual
   int dual_root = -1;
   std::vector<float> dual_scale, dual_shift;
@@ -518,6 +519,27 @@ void Lowerer::fuse() {
         absorbed_by_[u] = n.id;
         cur = U.outputs[0];
       }
+      // attention head split: Reshape [.., S, H*64] -> [N, S, H, 64], Transpose (0,2,1,3).  The pair kernel's epilogue stores 32-row x
+      // 64-channel boxes, i.e. 32 tokens of one head: a 4-D store map writes them at [n][h][s][0..63] and the permute kernel goes away.
+      if (is_fc && use_tc_ && f.res_value < 0) {
+        const char* fh = getenv("B200_FOLD_HEADS");
+        const bool fold_heads = !(fh && fh[0] == '0');
+        const int r = single_consumer(cur);
+        const int t = (fold_heads && r >= 0 && absorbed_by_[r] < 0 && node(r).op == B200_OP_RESHAPE) ? single_consumer(node(r).outputs[0]) : -1;
+        if (t >= 0 && absorbed_by_[t] < 0 && node(t).op == B200_OP_TRANSPOSE) {
+          const Shape& rs = val(node(r).outputs[0]).shape;
+          const Node& T = node(t);
+          const Shape& ws = val(n.inputs[1]).shape;
+          const int64_t K = n.i[1] ? ws[1] : ws[0];
+          if (rs.size() == 4 && rs[3] == 64 && rs[2] * 64 == C && rs[1] % 32 == 0 && T.i[0] == 0 && T.i[1] == 2 && T.i[2] == 1 && T.i[3] == 3 &&
+              K % 64 == 0 && C <= 2048 && val(cur).shape.back() == C) {
+            f.heads_s = (int)rs[1]; f.heads_h = (int)rs[2];
+            f.absorbed.push_back(r); f.absorbed.push_back(t);
+            absorbed_by_[r] = absorbed_by_[t] = n.id;
+            cur = T.outputs[0];
+          }
+        }
+      }
       f.out_value = cur;
       f.emit_at = f.absorbed.empty() ? n.id : f.absorbed.back();
       absorbed_by_[n.id] = n.id;
@@ -708,13 +730,18 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
       B200_CHECK(conv_tc3_supported(p), B200_ERR_UNSUPPORTED, "K-concatenated convolution '" << name << "' needs the pair kernel");
       v2 = true; v3 = true;
     }
+    const bool heads = p.y_heads_s > 0;           // head-split stores: the pair kernel is the only implementation
+    if (heads) {
+      B200_CHECK(conv_tc3_supported(p), B200_ERR_UNSUPPORTED, "head-split FullyConnected '" << name << "' needs the pair kernel");
+      v2 = true; v3 = true;
+    }
     // large launches: both persistent kernels apply, the first request measures which one is faster for this shape
-    both = v3 && !chained && !(tune && tune[0] == '0') && !(force3 && force3[0] == '1') && (!kcat || conv_tc3_preferred(p));
+    both = v3 && !chained && !(tune && tune[0] == '0') && !(force3 && force3[0] == '1') && ((!kcat && !heads) || conv_tc3_preferred(p));
     impl2 = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_128x" + std::to_string(bn) + "x64" +
             (v2 ? (conv_tc2_a_is_matrix(p) ? "_persistent_tma" : (conv_tc2_a_is_im2col(p) ? "_persistent_im2col" : "_persistent_gather")) : "");
     // small launches (fewer tiles than SM pairs: batch 1): the static policy keeps the single-CTA kernel, but the time is one operand-latency
     // chain per k-block, so the N tile (stages that fit, tiles in flight) and the kernel are worth measuring there too
-    small_tune = v2 && !v3 && !chained && !kcat && conv_tc3_supported(p) && !(tune && tune[0] == '0') && !(force3 && (force3[0] == '0' || force3[0] == '1'));
+    small_tune = v2 && !v3 && !chained && !kcat && !heads && conv_tc3_supported(p) && !(tune && tune[0] == '0') && !(force3 && (force3[0] == '0' || force3[0] == '1'));
     if (v3 || small_tune) {
       bn3 = conv_tc3_pick_bn(p);
       impl3 = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_pair256x" + std::to_string(bn3) + "x64_" + conv_tc3_mode_name(p);
@@ -765,7 +792,7 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
       std::string nm = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_pair256x" + std::to_string(b) + "x64_" + conv_tc3_mode_name(p);
       s.alts.emplace_back(nm, make_launch(b));     // which > 3: explicit N tile of the pair kernel
     }
-    if (!has_x2) s.alts.emplace_back(impl2, make_launch(2));
+    if (!has_x2 && p.y_heads_s == 0) s.alts.emplace_back(impl2, make_launch(2));
   } else if (small_tune) {
     const std::string pre = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16");
     s.alts.emplace_back(impl2, make_launch(2));                    // the static choice first
@@ -830,6 +857,7 @@ void Lowerer::lower_conv(const FusedConv& f) {
     p.M = (int)M; p.Ktot = (int)Ktot; p.Cout_alloc = (int)Nalloc; p.ldy = (int)Np;
     p.w_ld = (int)Ktot; p.w_rows = (int)Nalloc; p.w_k = (int)Ktot;
     p.act1 = f.act1.kind; p.a1 = f.act1.a; p.b1 = f.act1.b; p.act2 = f.act2.kind; p.a2 = f.act2.a; p.b2 = f.act2.b;
+    p.y_heads_s = f.heads_s; p.y_heads_h = f.heads_h;
     double flops = 2.0 * M * K * Nn;
     double bytes = (double)x.bytes() + (double)out_dense.bytes() + (double)Nn * K * dtype_size(cd_) + (f.res_value >= 0 ? (double)out_dense.bytes() : 0);
     conv_launch_step(out_name, "FullyConnected", fused, p, x.buf, wref, bref, rref, out_k.buf, &x, f.res_value >= 0 ? &res : nullptr, &out_k,

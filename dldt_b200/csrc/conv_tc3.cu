@@ -198,6 +198,16 @@ void launch_tc3(const ConvParams& p, bool bf16, int bn, int a_mode, cudaStream_t
   } else {
     a.tm_y = make_tmap_2d(p.y, bf16, (uint64_t)p.Cout_p, (uint64_t)p.M, (uint64_t)p.ldy * 2, 64, BM);
     a.tm_yw = make_tmap_2d(p.y, bf16, (uint64_t)p.Cout_p, (uint64_t)p.M, (uint64_t)p.ldy * 2, 64, 32);
+    if (p.y_heads_s) {
+      B200_CHECK(a_mode == A_MATRIX && p.y_heads_s % 32 == 0 && p.M % p.y_heads_s == 0 && p.Cout_p == 64 * p.y_heads_h && !p.res, B200_ERR_INVALID,
+                 "conv_tc3: bad head-split output geometry");
+      const uint64_t S = (uint64_t)p.y_heads_s, H = (uint64_t)p.y_heads_h;
+      const uint64_t yd[4] = {64, S, H, (uint64_t)p.M / S};
+      const uint64_t ys[3] = {128, S * 128, H * S * 128};
+      const uint32_t ywb[4] = {64, 32, 1, 1};
+      a.tm_yw = make_tmap_tiled(p.y, bf16, 4, yd, ys, ywb);
+      a.warp_store = 1;
+    }
     a.tm_r = p.res ? make_tmap_2d(p.res, bf16, (uint64_t)p.Cout_p, (uint64_t)p.M, (uint64_t)p.ldy * 2, 64, BM) : a.tm_y;
     a.tm_a = a_mode == A_MATRIX ? make_tmap_2d(p.x, bf16, (uint64_t)p.Cin_p, (uint64_t)p.M, (uint64_t)p.Cin_p * 2, BK, BM) : make_tmap_im2col(p, bf16);
     if (p.K2 > 0) {
@@ -273,7 +283,7 @@ bool conv_tc3_preferred(const ConvParams& p) {
 
 const char* conv_tc3_mode_name(const ConvParams& p) {
   switch (a_mode_of(p)) {
-    case A_MATRIX: return p.K2 > 0 ? "tma_kcat" : "tma";
+    case A_MATRIX: return p.K2 > 0 ? "tma_kcat" : (p.y_heads_s > 0 ? "tma_heads" : "tma");
     case A_HALO: return "halo";
     case A_IM2COL: return "im2col";
     case A_S2D: return "s2d";

@@ -314,7 +314,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
               const uint32_t src = out_slab + (uint32_t)q * 4096u;      // rows 32 q .. 32 q + 31 of the slab
               if (AMODE == A_S2D) ptx::tma_store_5d(&args.tm_yw, src, 0, h, tp.w0, tp.h0 + q, tp.img);
               else if (BOX4D) ptx::tma_store_4d(&args.tm_yw, src, n0 + h * 64, (q * 32) % args.rows_p, tp.h0 + (q * 32) / args.rows_p, tp.img);
-              else ptx::tma_store_2d(&args.tm_yw, src, n0 + h * 64, tp.m0 + q * 32);
+              else if (args.p.y_heads_s) {                              // head-split output: {64, S, heads, N}
+                const int row = tp.m0 + q * 32, nb = row / args.p.y_heads_s;
+                ptx::tma_store_4d(&args.tm_yw, src, 0, row - nb * args.p.y_heads_s, (n0 + h * 64) >> 6, nb);
+              } else ptx::tma_store_2d(&args.tm_yw, src, n0 + h * 64, tp.m0 + q * 32);
             }
             ptx::bulk_commit();
           }

@@ -198,3 +198,30 @@ def test_chained_pointwise_convs_with_several_m_tiles_per_cluster(cin, cc, ca, m
     convs = [e["impl"] for e in net.get_exec_graph_info() if e["type"] == "Convolution"]
     assert len(convs) == 1 and convs[0].endswith("+1x1x%d" % ca), convs
     assert rel_l2(got, ref) < 1e-2
+
+
+@pytest.mark.parametrize("prec,tol", [("BF16", 1.5e-2), ("FP16", 3e-3)])
+@pytest.mark.parametrize("n,seq,heads,k", [(2, 64, 3, 128), (3, 384, 12, 768), (1, 32, 2, 64)])
+def test_head_split_is_written_by_the_fc_stores(prec, tol, n, seq, heads, k, monkeypatch):
+    """FullyConnected -> Reshape [N,S,H,64] -> Transpose (0,2,1,3): the pair kernel's 32-token x one-head store boxes land at
+    [n][h][s][:], no permute kernel (B200_FOLD_HEADS=0 keeps the three-step form, same numbers)"""
+    rng = np.random.default_rng(seq + heads)
+    f = Function("heads")
+    x = f.parameter((n, seq, k), name="x")
+    w = (rng.standard_normal((heads * 64, k)) / np.sqrt(k)).astype(np.float32)
+    b = rng.uniform(-0.5, 0.5, (heads * 64,)).astype(np.float32)
+    y = f.add(f.matmul(x, w, transpose_b=True), f.constant(b))
+    f.result(f.transpose(f.reshape(y, (n, seq, heads, 64)), (0, 2, 1, 3)))
+    xin = rng.standard_normal((n, seq, k)).astype(np.float32)
+    ref = list(interp.run(f, {"x": xin}).values())[0]
+    net = Core().load_network(f, "B200", {"B200_INFERENCE_PRECISION": prec})
+    got = list(net.create_infer_request().infer({"x": xin}).values())[0]
+    eg = net.get_exec_graph_info()
+    assert [e["type"] for e in eg if e["type"] in ("FullyConnected", "Transpose")] == ["FullyConnected"], eg
+    assert "tma_heads" in [e["impl"] for e in eg if e["type"] == "FullyConnected"][0]
+    assert got.shape == (n, heads, seq, 64) and rel_l2(got, ref) < tol
+    monkeypatch.setenv("B200_FOLD_HEADS", "0")
+    net0 = Core().load_network(f, "B200", {"B200_INFERENCE_PRECISION": prec})
+    got0 = list(net0.create_infer_request().infer({"x": xin}).values())[0]
+    assert any(e["type"] == "Transpose" for e in net0.get_exec_graph_info())
+    assert rel_l2(got, got0) < 2e-3
