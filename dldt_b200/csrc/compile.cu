@@ -540,6 +540,26 @@ void Lowerer::fuse() {
           }
         }
       }
+      // the inverse after the context MatMul: [N,H,S,64] -> Transpose (0,2,1,3) -> [N,S,H,64], written by the grouped launch's stores
+      if (is_mm && use_tc_ && f.res_value < 0 && n.i[0] == 0) {
+        const char* fh = getenv("B200_FOLD_HEADS");
+        const char* flat = getenv("B200_MATMUL_FLAT");
+        const int t = single_consumer(cur);
+        const Shape& cs = val(cur).shape;
+        const Shape& as_ = val(n.inputs[0]).shape;
+        const Shape& bs = val(n.inputs[1]).shape;
+        if (!(fh && fh[0] == '0') && !(flat && flat[0] == '0') && t >= 0 && absorbed_by_[t] < 0 && node(t).op == B200_OP_TRANSPOSE && cs.size() == 4 &&
+            as_.size() == 4 && bs.size() == 4 && cs[3] == 64 && cs[2] % 128 == 0 && as_[3] % 64 == 0 && as_[0] == bs[0] && as_[1] == bs[1] && cs[0] * cs[1] > 1 &&
+            cs[0] * cs[1] * cs[2] < (int64_t(1) << 31)) {
+          const Node& T = node(t);
+          if (T.i[0] == 0 && T.i[1] == 2 && T.i[2] == 1 && T.i[3] == 3) {
+            f.heads_s = (int)cs[2]; f.heads_h = (int)cs[1];
+            f.absorbed.push_back(t);
+            absorbed_by_[t] = n.id;
+            cur = T.outputs[0];
+          }
+        }
+      }
       f.out_value = cur;
       f.emit_at = f.absorbed.empty() ? n.id : f.absorbed.back();
       absorbed_by_[n.id] = n.id;
@@ -730,7 +750,7 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
       B200_CHECK(conv_tc3_supported(p), B200_ERR_UNSUPPORTED, "K-concatenated convolution '" << name << "' needs the pair kernel");
       v2 = true; v3 = true;
     }
-    const bool heads = p.y_heads_s > 0;           // head-split stores: the pair kernel is the only implementation
+    const bool heads = p.y_heads_s > 0 && !p.y_heads_inv;   // head-split stores: the pair kernel is the only implementation
     if (heads) {
       B200_CHECK(conv_tc3_supported(p), B200_ERR_UNSUPPORTED, "head-split FullyConnected '" << name << "' needs the pair kernel");
       v2 = true; v3 = true;
@@ -738,7 +758,8 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
     // large launches: both persistent kernels apply, the first request measures which one is faster for this shape
     both = v3 && !chained && !(tune && tune[0] == '0') && !(force3 && force3[0] == '1') && ((!kcat && !heads) || conv_tc3_preferred(p));
     impl2 = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_128x" + std::to_string(bn) + "x64" +
-            (v2 ? (conv_tc2_a_is_matrix(p) ? "_persistent_tma" : (conv_tc2_a_is_im2col(p) ? "_persistent_im2col" : "_persistent_gather")) : "");
+            (v2 ? (conv_tc2_a_is_matrix(p) ? "_persistent_tma" : (conv_tc2_a_is_im2col(p) ? "_persistent_im2col" : "_persistent_gather")) : "") +
+            (p.y_heads_inv ? "_heads" : "");
     // small launches (fewer tiles than SM pairs: batch 1): the static policy keeps the single-CTA kernel, but the time is one operand-latency
     // chain per k-block, so the N tile (stages that fit, tiles in flight) and the kernel are worth measuring there too
     small_tune = v2 && !v3 && !chained && !kcat && !heads && conv_tc3_supported(p) && !(tune && tune[0] == '0') && !(force3 && (force3[0] == '0' || force3[0] == '1'));
@@ -1064,6 +1085,10 @@ void Lowerer::lower_matmul_general(const Node& n, const FusedConv* f) {
       p.N = p.M = (int)(batch_a * M);
       p.batch = 1; p.x_bs = p.w_bs = p.y_bs = 0;
       p.w_grp_m = (int)M; p.w_grp_rows = (int)Nn;
+    }
+    if (f && f->heads_s) {
+      B200_CHECK(p.w_grp_m == f->heads_s && Nn == 64, B200_ERR_UNSUPPORTED, "MatMul '" << n.name << "': merged-heads store needs the grouped launch");
+      p.y_heads_s = f->heads_s; p.y_heads_h = f->heads_h; p.y_heads_inv = 1;
     }
   }
   LTensor res;

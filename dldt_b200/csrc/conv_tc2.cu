@@ -294,6 +294,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
       ptx::fence_proxy_async();                            // staging writes -> visible to the TMA engine
       ptx::named_bar_sync(1, NUM_EPI_WARPS * 32);
       if (store_thread) {
+        if (p.y_heads_inv) {                               // rows (n, h, s) -> y[n][s][h][:]; the tile's 128 rows share (n, h)
+          const int g = m0 / p.y_heads_s, nb = g / p.y_heads_h;
+          ptx::tma_store_4d(&args.tm_y, out_tile, 0, g - nb * p.y_heads_h, m0 - g * p.y_heads_s, nb);
+        } else
         for (int h = 0; h < nslab; ++h) ptx::tma_store_2d(&args.tm_y, out_tile + (uint32_t)h * SLAB_BYTES, n0 + h * 64, m0);
         ptx::bulk_commit();
       }
@@ -493,6 +497,20 @@ void launch_tc2(const ConvParams& p, bool bf16, cudaStream_t s) {
   a.tm_w = make_tmap_2d(p.w, bf16, (uint64_t)p.Ktot, p.w_grp_m ? (uint64_t)(p.M / p.w_grp_m) * p.w_grp_rows : (uint64_t)p.Cout_alloc, (uint64_t)p.w_ld * 2, BK, BN);
   a.tm_y = make_tmap_2d(p.y, bf16, (uint64_t)p.Cout_p, (uint64_t)p.M, (uint64_t)p.ldy * 2, 64, BM);
   a.tm_r = p.res ? make_tmap_2d(p.res, bf16, (uint64_t)p.Cout_p, (uint64_t)p.M, (uint64_t)p.ldy * 2, 64, BM) : a.tm_y;
+  if (p.y_heads_inv) {
+    B200_CHECK(p.y_heads_s % BM == 0 && p.w_grp_m == p.y_heads_s && p.Cout_p == 64 && p.M % (p.y_heads_s * p.y_heads_h) == 0 && !p.res, B200_ERR_INVALID,
+               "conv_tc2: bad merged-heads output geometry");
+    auto enc = encode_tiled_fn();
+    B200_CHECK(enc, B200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t S = (cuuint64_t)p.y_heads_s, H = (cuuint64_t)p.y_heads_h;
+    cuuint64_t dims[4] = {64, H, S, (cuuint64_t)p.M / (S * H)};
+    cuuint64_t strides[3] = {128, H * 128, S * H * 128};
+    cuuint32_t box[4] = {64, 1, (cuuint32_t)BM, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&a.tm_y, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(p.y), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled (merged heads) failed (" << (int)r << ")");
+  }
   a.tm_a = a.a_tma == 1 ? make_tmap_2d(p.x, bf16, (uint64_t)p.Cin_p, (uint64_t)p.M, (uint64_t)p.Cin_p * 2, BK, BM)
                         : (a.a_tma == 2 ? make_tmap_im2col(p, bf16) : a.tm_y);
   const int grid = std::min(a.num_tiles, g_sm_count > 0 ? g_sm_count : 148);
@@ -580,7 +598,8 @@ void conv_tc2_init_device() {
 }
 
 void launch_conv_tc2(const ConvParams& p, int dtype, int bn, cudaStream_t s) {
-  B200_CHECK(conv_tc2_supported(p), B200_ERR_UNSUPPORTED, "conv_tc2: unsupported launch (batched or partial weights)");
+  B200_CHECK(conv_tc2_supported(p) && !(p.y_heads_s && !p.y_heads_inv), B200_ERR_UNSUPPORTED,
+             "conv_tc2: unsupported launch (batched or partial weights, head-split stores)");
   B200_CHECK(p.Ktot % BK == 0 && p.Cin_p % 8 == 0 && p.Cout_alloc % bn == 0 && p.Cout_p % 8 == 0 && p.ldy % 8 == 0, B200_ERR_INVALID,
              "conv_tc2: bad geometry");
   const bool bf16 = dtype == B200_BF16;

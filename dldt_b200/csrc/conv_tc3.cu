@@ -229,7 +229,7 @@ void launch_tc3(const ConvParams& p, bool bf16, int bn, int a_mode, cudaStream_t
 }  // namespace
 
 bool conv_tc3_supported(const ConvParams& p) {
-  return conv_tc2_supported(p) && p.w_grp_m == 0 && a_mode_of(p) != 0 && p.Cout_alloc % 64 == 0 && p.Ktot % BK == 0 && p.Cout_alloc <= BIAS_SMEM_FLOATS;
+  return conv_tc2_supported(p) && p.w_grp_m == 0 && !p.y_heads_inv && a_mode_of(p) != 0 && p.Cout_alloc % 64 == 0 && p.Ktot % BK == 0 && p.Cout_alloc <= BIAS_SMEM_FLOATS;
 }
 
 // Estimated cycles of one launch with N tile `bn` on `sms` SMs: rounds x k-blocks x max(MMA, operand bytes / fabric rate) + epilogue traffic.

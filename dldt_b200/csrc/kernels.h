@@ -55,6 +55,9 @@ struct ConvParams {
   // head-split output (BERT's Reshape [N,S,H*64] -> [N,S,H,64] + Transpose (0,2,1,3) folded into the producing FullyConnected): row
   // n*S + s, columns [64 h, 64 h + 64) are stored at y[n][h][s][0..63]; 0 = plain [M][ldy] output.  Pair kernel only.
   int y_heads_s = 0, y_heads_h = 0;
+  // the inverse (context MatMul + Transpose (0,2,1,3)): flat rows (n, h, s) of 64 columns are stored at y[n][s][h][0..63].  Single-CTA
+  // kernel with grouped weights only (w_grp_m == y_heads_s).
+  int y_heads_inv = 0;
   int64_t x_bs = 0, w_bs = 0, y_bs = 0;
 };
 // dtype: B200_BF16 or B200_F16.  bn: N tile (64 or 128).

@@ -137,3 +137,26 @@ def test_attention_matmuls_run_as_one_grouped_launch(prec, tol, seq, dh, monkeyp
     assert not any("persistent" in e["impl"] for e in eg0 if e["type"] == "MatMul")
     for a, b in zip(got.values(), got0.values()):
         assert rel_l2(a, b) < 2e-3
+
+
+@pytest.mark.parametrize("prec,tol", [("BF16", 1.5e-2), ("FP16", 4e-3)])
+@pytest.mark.parametrize("n,heads,seq", [(2, 3, 128), (2, 12, 384), (1, 2, 256)])
+def test_context_matmul_writes_the_merged_heads_layout(prec, tol, n, heads, seq, monkeypatch):
+    """context = P V followed by Transpose (0,2,1,3) + Reshape [N,S,H*64]: the grouped launch's 128-row stores land at [n][s][h][:]"""
+    rng = np.random.default_rng(seq + heads)
+    f = Function("ctx")
+    pr = f.parameter((n, heads, seq, seq), name="p")
+    v = f.parameter((n, heads, seq, 64), name="v")
+    c = f.matmul(f.softmax(pr, 3), v)
+    f.result(f.reshape(f.transpose(c, (0, 2, 1, 3)), (n, seq, heads * 64)))
+    ins = {"p": rng.standard_normal((n, heads, seq, seq)).astype(np.float32), "v": rng.standard_normal((n, heads, seq, 64)).astype(np.float32)}
+    ref, got, eg = run(f, ins, prec)
+    mm = [e["impl"] for e in eg if e["type"] == "MatMul"]
+    assert len(mm) == 1 and mm[0].endswith("_heads"), mm
+    assert len([e for e in eg if e["type"] == "Transpose"]) == 1, eg      # V^T only
+    a, b = list(got.values())[0], list(ref.values())[0]
+    assert a.shape == (n, seq, heads * 64) and rel_l2(a, b) < tol
+    monkeypatch.setenv("B200_FOLD_HEADS", "0")
+    _, got0, eg0 = run(f, ins, prec)
+    assert len([e for e in eg0 if e["type"] == "Transpose"]) == 2
+    assert rel_l2(a, list(got0.values())[0]) < 2e-3
