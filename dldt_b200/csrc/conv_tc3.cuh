@@ -138,6 +138,42 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint32_t
   }
 }
 
+// The generic-activation form of the two calls above for one whole 64-column slab: bias, ONE activation switch over the 64 accumulators,
+// residual, one more switch, pack + swizzled staging store.
+template <typename T>
+__device__ __forceinline__ void epilogue_slab_generic(const uint32_t (&v0)[32], const uint32_t (&v1)[32], uint32_t bias, uint32_t out_row, uint32_t res_row,
+                                                      uint32_t rsw, bool has_res, const EpiAct& e1, const EpiAct& e2) {
+  float f[64];
+#pragma unroll
+  for (int g = 0; g < 16; ++g) {
+    const uint4 b = ptx::ld_shared_v4(bias + (uint32_t)g * 16u);
+    const uint32_t* v = g < 8 ? &v0[g * 4] : &v1[(g - 8) * 4];
+    f[g * 4 + 0] = __uint_as_float(v[0]) + __uint_as_float(b.x); f[g * 4 + 1] = __uint_as_float(v[1]) + __uint_as_float(b.y);
+    f[g * 4 + 2] = __uint_as_float(v[2]) + __uint_as_float(b.z); f[g * 4 + 3] = __uint_as_float(v[3]) + __uint_as_float(b.w);
+  }
+  if (e1.kind != 0 && !e1.relu_in_pack) epi_act_generic<64>(f, e1);
+  if (has_res) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const uint4 rv = ptx::ld_shared_v4(res_row + ((rsw ^ (uint32_t)g) << 4));
+      float r[8];
+      unpack2<T>(rv.x, r[0], r[1]); unpack2<T>(rv.y, r[2], r[3]);
+      unpack2<T>(rv.z, r[4], r[5]); unpack2<T>(rv.w, r[6], r[7]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[g * 8 + e] += r[e];
+    }
+    if (e2.kind != 0 && !e2.relu_in_pack) epi_act_generic<64>(f, e2);
+  }
+  const bool relu_pack = (has_res ? e2 : e1).relu_in_pack != 0;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const uint32_t sw = (rsw ^ (uint32_t)g) << 4;
+    const float* h = &f[g * 8];
+    if (relu_pack) ptx::st_shared_v4(out_row + sw, make_uint4(pack2_relu<T>(h[0], h[1]), pack2_relu<T>(h[2], h[3]), pack2_relu<T>(h[4], h[5]), pack2_relu<T>(h[6], h[7])));
+    else ptx::st_shared_v4(out_row + sw, make_uint4(pack2<T>(h[0], h[1]), pack2<T>(h[2], h[3]), pack2<T>(h[4], h[5]), pack2<T>(h[6], h[7])));
+  }
+}
+
 // first output row of CTA `rank` of pair tile `tile_m`, and (halo mode) its image / first image row
 struct TilePos { int m0; int img, h0, w0; bool valid; };
 template <int AMODE>
@@ -300,8 +336,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
         }
         ptx::tmem_ld_wait();
         const uint32_t bias = bias_base + (uint32_t)(n0 + (AMODE == A_S2D ? 0 : h * 64)) * 4u;
-        epilogue_chunk<T, GEN>(v0, bias, out_row, res_row, rsw, 0, has_res, args.e1, args.e2);
-        epilogue_chunk<T, GEN>(v1, bias + 128u, out_row, res_row, rsw, 4, has_res, args.e1, args.e2);
+        if constexpr (GEN) {
+          epilogue_slab_generic<T>(v0, v1, bias, out_row, res_row, rsw, has_res, args.e1, args.e2);
+        } else {
+          epilogue_chunk<T, GEN>(v0, bias, out_row, res_row, rsw, 0, has_res, args.e1, args.e2);
+          epilogue_chunk<T, GEN>(v1, bias + 128u, out_row, res_row, rsw, 4, has_res, args.e1, args.e2);
+        }
         if (has_res) {
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&rempty[rslot]);

@@ -76,6 +76,68 @@ __device__ __forceinline__ float erf_fast(float x) {
   return copysignf(r, x);
 }
 
+// Generic (non-clamp) activation over N accumulators: ONE warp-uniform switch, fully unrolled bodies for the activations the model zoo uses
+// (a rolled loop indexes f[] dynamically, which puts the accumulators in local memory).  The pair kernel calls it once per 64-column slab:
+// with one switch per 8 values the GELU path hopped through sixteen copies of the whole switch per slab and the epilogue warps sat in
+// instruction-fetch stalls (ncu: stall_no_inst 43% of their samples, BERT's FC + GELU at 0.4x the plain FC, profiles/r1_gelu_ncu.txt).
+// GELU(erf) with the same polynomial, rearranged: erf(z) = sign(z) (1 - q), q = p(t) t exp(-z^2), z = x / sqrt 2, so
+// 0.5 x (1 + erf z) = relu(x) - 0.5 |x| q.  14 FP32 instructions + 2 MUFU per value (the composed form above takes 19).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.f)));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);      // the 0.5 of "0.5 |x| q" folded into the coefficients
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * (ax * -0.72134752044448170368f)));   // exp(-x^2 / 2) = 2^(-x^2 log2(e) / 2)
+  return fmaf(-(ax * t), p * e, fmaxf(x, 0.f));
+}
+
+template <int N>
+__device__ __forceinline__ void epi_act_generic(float (&f)[N], const EpiAct& s) {
+  switch (s.kind) {
+    case ACT_GELU_ERF:
+#pragma unroll
+      for (int e = 0; e < N; ++e) f[e] = gelu_erf_fast(f[e]);
+      break;
+    case ACT_SWISH:
+#pragma unroll
+      for (int e = 0; e < N; ++e) f[e] = __fdividef(f[e], 1.f + __expf(-s.a * f[e]));
+      break;
+    case ACT_SIGMOID:
+#pragma unroll
+      for (int e = 0; e < N; ++e) f[e] = __fdividef(1.f, 1.f + __expf(-f[e]));
+      break;
+    case ACT_TANH:
+#pragma unroll
+      for (int e = 0; e < N; ++e) f[e] = tanhf(f[e]);
+      break;
+    case ACT_HSWISH:
+#pragma unroll
+      for (int e = 0; e < N; ++e) f[e] = f[e] * fminf(fmaxf(f[e] + 3.f, 0.f), 6.f) * (1.f / 6.f);
+      break;
+    case ACT_RELU:
+#pragma unroll
+      for (int e = 0; e < N; ++e) f[e] = fmaxf(f[e], 0.f);
+      break;
+    case ACT_CLAMP:
+#pragma unroll
+      for (int e = 0; e < N; ++e) f[e] = fminf(fmaxf(f[e], s.a), s.b);
+      break;
+    default: {
+      float g[N];
+#pragma unroll
+      for (int e = 0; e < N; ++e) g[e] = f[e];
+#pragma unroll 1
+      for (int e = 0; e < N; ++e) g[e] = act_apply(g[e], s.kind, s.a, s.b);
+#pragma unroll
+      for (int e = 0; e < N; ++e) f[e] = g[e];
+    }
+  }
+}
+
 template <bool GENERIC>
 __device__ __forceinline__ void epi_act8(float (&f)[8], const EpiAct& s) {
   if (s.kind == 0 || s.relu_in_pack) return;   // ACT_NONE, or a trailing ReLU done by the bf16 conversion (warp-uniform)
@@ -87,47 +149,7 @@ __device__ __forceinline__ void epi_act8(float (&f)[8], const EpiAct& s) {
       for (int e = 0; e < 8; ++e) f[e] = fminf(f[e], s.hi);
     }
   } else {
-    // one (warp-uniform) switch, fully unrolled bodies for the activations the model zoo uses: a rolled loop indexes f[] dynamically, which
-    // puts the accumulators in local memory (BERT's FC + GELU ran at a third of the plain FC's rate)
-    switch (s.kind) {
-      case ACT_GELU_ERF:
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = 0.5f * f[e] * (1.f + erf_fast(f[e] * 0.70710678118654752440f));
-        break;
-      case ACT_SWISH:
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = f[e] / (1.f + expf(-s.a * f[e]));
-        break;
-      case ACT_SIGMOID:
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = 1.f / (1.f + expf(-f[e]));
-        break;
-      case ACT_TANH:
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = tanhf(f[e]);
-        break;
-      case ACT_HSWISH:
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = f[e] * fminf(fmaxf(f[e] + 3.f, 0.f), 6.f) / 6.f;
-        break;
-      case ACT_RELU:
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
-        break;
-      case ACT_CLAMP:
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(f[e], s.a), s.b);
-        break;
-      default: {
-        float g[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) g[e] = f[e];
-#pragma unroll 1
-        for (int e = 0; e < 8; ++e) g[e] = act_apply(g[e], s.kind, s.a, s.b);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = g[e];
-      }
-    }
+    epi_act_generic<8>(f, s);
   }
 }
 
