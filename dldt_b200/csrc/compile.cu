@@ -759,7 +759,7 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
     both = v3 && !chained && !(tune && tune[0] == '0') && !(force3 && force3[0] == '1') && ((!kcat && !heads) || conv_tc3_preferred(p));
     impl2 = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_128x" + std::to_string(bn) + "x64" +
             (v2 ? (conv_tc2_a_is_matrix(p) ? "_persistent_tma" : (conv_tc2_a_is_im2col(p) ? "_persistent_im2col" : "_persistent_gather")) : "") +
-            (p.y_heads_inv ? "_heads" : "");
+            (p.w_mn_major ? "_bmn" : "") + (p.y_heads_inv ? "_heads" : "");
     // small launches (fewer tiles than SM pairs: batch 1): the static policy keeps the single-CTA kernel, but the time is one operand-latency
     // chain per k-block, so the N tile (stages that fit, tiles in flight) and the kernel are worth measuring there too
     small_tune = v2 && !v3 && !chained && !kcat && !heads && conv_tc3_supported(p) && !(tune && tune[0] == '0') && !(force3 && (force3[0] == '0' || force3[0] == '1'));
@@ -1058,9 +1058,19 @@ void Lowerer::lower_matmul_general(const Node& n, const FusedConv* f) {
     return o;
   };
   if (n.i[0]) a = permute_last2(a, n.name + "_At");
-  if (!n.i[1]) b = permute_last2(b, n.name + "_Bt");   // need [.., N, K]
-  const int64_t M = a.shape[a.shape.size() - 2], K = a.shape.back(), Nn = b.shape[b.shape.size() - 2];
-  B200_CHECK(b.shape.back() == K, B200_ERR_INVALID, "MatMul '" << n.name << "': K mismatch");
+  // B as [.., K, 64] (attention's V): the grouped launch reads it through an MN-major descriptor, no transpose (B200_MN_MAJOR=0 disables)
+  bool mn = false;
+  if (!n.i[1] && use_tc_) {
+    const char* e1 = getenv("B200_MN_MAJOR");
+    const char* e2 = getenv("B200_MATMUL_FLAT");
+    const int64_t M0 = a.shape[a.shape.size() - 2], K0 = a.shape.back();
+    const int64_t ba = numel(a.shape) / (M0 * K0), bb = numel(b.shape) / (K0 * 64);
+    mn = !(e1 && e1[0] == '0') && !(e2 && e2[0] == '0') && b.shape.back() == 64 && b.shape[b.shape.size() - 2] == K0 && K0 % 64 == 0 && M0 % 128 == 0 &&
+         ba > 1 && ba == bb && ba * M0 < (int64_t(1) << 31);
+  }
+  if (!n.i[1] && !mn) b = permute_last2(b, n.name + "_Bt");   // need [.., N, K]
+  const int64_t M = a.shape[a.shape.size() - 2], K = a.shape.back(), Nn = mn ? b.shape.back() : b.shape[b.shape.size() - 2];
+  B200_CHECK((mn ? b.shape[b.shape.size() - 2] : b.shape.back()) == K, B200_ERR_INVALID, "MatMul '" << n.name << "': K mismatch");
   B200_CHECK(K % 8 == 0 && Nn % 8 == 0, B200_ERR_UNSUPPORTED, "MatMul '" << n.name << "': K and N must be multiples of 8");
   const int64_t batch_a = numel(a.shape) / (M * K), batch_b = numel(b.shape) / (Nn * K);
   B200_CHECK(batch_a == batch_b || batch_b == 1, B200_ERR_UNSUPPORTED, "MatMul '" << n.name << "': unsupported batch broadcast");
@@ -1085,7 +1095,9 @@ void Lowerer::lower_matmul_general(const Node& n, const FusedConv* f) {
       p.N = p.M = (int)(batch_a * M);
       p.batch = 1; p.x_bs = p.w_bs = p.y_bs = 0;
       p.w_grp_m = (int)M; p.w_grp_rows = (int)Nn;
+      p.w_mn_major = mn ? 1 : 0;
     }
+    B200_CHECK(!mn || p.w_mn_major, B200_ERR_UNSUPPORTED, "MatMul '" << n.name << "': MN-major weights need the grouped launch");
     if (f && f->heads_s) {
       B200_CHECK(p.w_grp_m == f->heads_s && Nn == 64, B200_ERR_UNSUPPORTED, "MatMul '" << n.name << "': merged-heads store needs the grouped launch");
       p.y_heads_s = f->heads_s; p.y_heads_h = f->heads_h; p.y_heads_inv = 1;

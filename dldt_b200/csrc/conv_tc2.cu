@@ -306,7 +306,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
   } else if (warp == MMA_WARP) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_f16(TcType<T>::is_bf16, BM, BN);
+      // MN-major B (grouped [K][64] weights): bit 16 of the instruction descriptor; the tile is 64 k-rows of 128 swizzled bytes, the same
+      // 8-row / 1024-byte group structure as the K-major tile, and one K = 16 step is two such groups = 2048 bytes further
+      const uint32_t idesc = ptx::make_idesc_f16(TcType<T>::is_bf16, BM, BN) | (p.w_mn_major ? (1u << 16) : 0u);
+      const uint32_t b_kstep = p.w_mn_major ? 2048u : 32u;
       uint32_t it = 0;
       int s = 0;
       uint32_t ph = 0;
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = ptx::make_smem_desc_sw128(a_addr + k * 32);
-            const uint64_t db = ptx::make_smem_desc_sw128(b_addr + k * 32);
+            const uint64_t db = ptx::make_smem_desc_sw128(b_addr + (uint32_t)k * b_kstep);
             ptx::umma_f16(d_tmem, da, db, idesc, (kb | k) ? 1u : 0u);
           }
           ptx::umma_commit(&empty_bar[s]);     // frees this stage once the MMAs above have read it
@@ -350,7 +353,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
         const int tile = args.reverse ? num_tiles - 1 - t_ : t_;
         const int m0 = (tile / n_tiles) * BM;
         const int n0 = (tile % n_tiles) * BN;
-        const int w_row0 = p.w_grp_m ? (m0 / p.w_grp_m) * p.w_grp_rows : 0;   // grouped weights: this tile's weight matrix
+        const int w_row0 = p.w_grp_m ? (m0 / p.w_grp_m) * (p.w_mn_major ? p.Ktot : p.w_grp_rows) : 0;   // grouped weights: this tile's weight matrix
         int bn = 0, bh = 0, bw = 0;
         if (args.a_tma == 2) {                       // first output pixel of the tile -> base pixel of the im2col bounding box
           bn = m0 / HoWo;
@@ -380,7 +383,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
             ptx::tma_load_im2col_4d(a_dst, &args.tm_a, &full_bar[s], chunk * BK, bw, bh, bn, (uint32_t)(fs * p.dw), (uint32_t)(fr * p.dh));
             if (++chunk == cpt) { chunk = 0; ++tap; if (++fs == p.kw) { fs = 0; ++fr; } }
           }
-          if (!ws) ptx::tma_load_2d(a_dst + A_BYTES, &args.tm_w, &full_bar[s], kb * BK, n0 + w_row0);
+          if (p.w_mn_major) ptx::tma_load_2d(a_dst + A_BYTES, &args.tm_w, &full_bar[s], 0, w_row0 + kb * BK);   // 64 k-rows of 64 channels
+          else if (!ws) ptx::tma_load_2d(a_dst + A_BYTES, &args.tm_w, &full_bar[s], kb * BK, n0 + w_row0);
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
@@ -495,6 +499,10 @@ void launch_tc2(const ConvParams& p, bool bf16, cudaStream_t s) {
   }
   a.a_tma = conv_tc2_a_is_matrix(p) ? 1 : (conv_tc2_a_is_im2col(p) ? 2 : 0);
   a.tm_w = make_tmap_2d(p.w, bf16, (uint64_t)p.Ktot, p.w_grp_m ? (uint64_t)(p.M / p.w_grp_m) * p.w_grp_rows : (uint64_t)p.Cout_alloc, (uint64_t)p.w_ld * 2, BK, BN);
+  if (p.w_mn_major) {
+    B200_CHECK(BN == 64 && p.Cout_p == 64 && p.Cout_alloc == 64 && p.w_grp_m > 0, B200_ERR_INVALID, "conv_tc2: MN-major weights need grouped 64-column launches");
+    a.tm_w = make_tmap_2d(p.w, bf16, 64, (uint64_t)(p.M / p.w_grp_m) * p.Ktot, 128, 64, BK);
+  }
   a.tm_y = make_tmap_2d(p.y, bf16, (uint64_t)p.Cout_p, (uint64_t)p.M, (uint64_t)p.ldy * 2, 64, BM);
   a.tm_r = p.res ? make_tmap_2d(p.res, bf16, (uint64_t)p.Cout_p, (uint64_t)p.M, (uint64_t)p.ldy * 2, 64, BM) : a.tm_y;
   if (p.y_heads_inv) {

@@ -52,6 +52,9 @@ struct ConvParams {
   // grouped weights (batched activation x activation MatMul flattened into one launch of the persistent kernel): output rows
   // [g*w_grp_m, (g+1)*w_grp_m) use weight rows [g*w_grp_rows, (g+1)*w_grp_rows); 0 = one weight matrix
   int w_grp_m = 0, w_grp_rows = 0;
+  // grouped weights given MN-major: group g is a [Ktot][64] matrix (N contiguous; attention's V as it comes out of the head split) read
+  // through an MN-major UMMA descriptor instead of being transposed first.  Single-CTA kernel, Cout == 64.
+  int w_mn_major = 0;
   // head-split output (BERT's Reshape [N,S,H*64] -> [N,S,H,64] + Transpose (0,2,1,3) folded into the producing FullyConnected): row
   // n*S + s, columns [64 h, 64 h + 64) are stored at y[n][h][s][0..63]; 0 = plain [M][ldy] output.  Pair kernel only.
   int y_heads_s = 0, y_heads_h = 0;

@@ -152,11 +152,15 @@ def test_context_matmul_writes_the_merged_heads_layout(prec, tol, n, heads, seq,
     ins = {"p": rng.standard_normal((n, heads, seq, seq)).astype(np.float32), "v": rng.standard_normal((n, heads, seq, 64)).astype(np.float32)}
     ref, got, eg = run(f, ins, prec)
     mm = [e["impl"] for e in eg if e["type"] == "MatMul"]
-    assert len(mm) == 1 and mm[0].endswith("_heads"), mm
-    assert len([e for e in eg if e["type"] == "Transpose"]) == 1, eg      # V^T only
+    assert len(mm) == 1 and mm[0].endswith("_bmn_heads"), mm               # V read MN-major (no V^T), merged-heads stores
+    assert len([e for e in eg if e["type"] == "Transpose"]) == 0, eg
     a, b = list(got.values())[0], list(ref.values())[0]
     assert a.shape == (n, seq, heads * 64) and rel_l2(a, b) < tol
     monkeypatch.setenv("B200_FOLD_HEADS", "0")
     _, got0, eg0 = run(f, ins, prec)
-    assert len([e for e in eg0 if e["type"] == "Transpose"]) == 2
+    assert len([e for e in eg0 if e["type"] == "Transpose"]) == 1          # the context transpose
     assert rel_l2(a, list(got0.values())[0]) < 2e-3
+    monkeypatch.setenv("B200_MN_MAJOR", "0")
+    _, got1, eg1 = run(f, ins, prec)
+    assert len([e for e in eg1 if e["type"] == "Transpose"]) == 2          # + V^T
+    assert rel_l2(a, list(got1.values())[0]) < 2e-3
