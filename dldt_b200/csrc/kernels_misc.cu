@@ -649,6 +649,77 @@ __global__ void __launch_bounds__(256) mvn_warp_rows_kernel(const T* __restrict_
   }
 }
 
+// A copy of a packed word the compiler cannot connect to its source: keeps the passes below from caching the unpacked fp32 values
+// (which would triple the register footprint of the row).
+__device__ __forceinline__ uint32_t opaque(uint32_t u) {
+  asm volatile("" : "+r"(u));
+  return u;
+}
+
+// Exact-width variant for 16-bit rows of CHUNKS x 256 elements (256/512/768/1024: BERT's hidden size): the row stays PACKED in registers
+// (4 registers per 8 elements, unpacked again in each of the three passes) so that the kernel fits 32 registers and all 64 warps of an SM
+// are resident -- one warp-row is a load -> reduce -> reduce -> store latency chain, and the bytes in flight per SM are what bound it.
+template <typename T, int CHUNKS>
+__global__ void __launch_bounds__(256, 8) mvn_rows_exact_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, uint32_t rows, int normalize_variance, int eps_outside,
+                                                                float eps) {
+  constexpr int COLS = CHUNKS * 256;
+  const uint32_t row = blockIdx.x * 8u + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const uint4* px = reinterpret_cast<const uint4*>(x + (size_t)row * COLS) + lane;
+  uint4 raw[CHUNKS];
+#pragma unroll
+  for (int k = 0; k < CHUNKS; ++k) raw[k] = __ldg(px + k * 32);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < CHUNKS; ++k) {
+    const float2 a = unpack2<T>(raw[k].x), b = unpack2<T>(raw[k].y), c = unpack2<T>(raw[k].z), d = unpack2<T>(raw[k].w);
+    s += ((a.x + a.y) + (b.x + b.y)) + ((c.x + c.y) + (d.x + d.y));
+  }
+  const float mean = warp_sum(s) * (1.f / (float)COLS);
+  float scale = 1.f;
+  if (normalize_variance) {
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) {
+      const uint32_t w[4] = {opaque(raw[k].x), opaque(raw[k].y), opaque(raw[k].z), opaque(raw[k].w)};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 a = unpack2<T>(w[i]);
+        const float d0 = a.x - mean, d1 = a.y - mean;
+        q = fmaf(d0, d0, q);
+        q = fmaf(d1, d1, q);
+      }
+    }
+    const float var = warp_sum(q) * (1.f / (float)COLS);
+    scale = eps_outside ? 1.f / (sqrtf(var) + eps) : rsqrtf(var + eps);
+  }
+  uint4* py = reinterpret_cast<uint4*>(y + (size_t)row * COLS) + lane;
+#pragma unroll
+  for (int k = 0; k < CHUNKS; ++k) {
+    const int c = (k * 32 + lane) * 8;
+    uint4 o;
+    {
+      float4 g = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gamma) g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      if (beta) b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      const float2 v0 = unpack2<T>(opaque(raw[k].x)), v1 = unpack2<T>(opaque(raw[k].y));
+      o.x = pack2<T>(fmaf((v0.x - mean) * scale, g.x, b.x), fmaf((v0.y - mean) * scale, g.y, b.y));
+      o.y = pack2<T>(fmaf((v1.x - mean) * scale, g.z, b.z), fmaf((v1.y - mean) * scale, g.w, b.w));
+    }
+    {
+      float4 g = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gamma) g = __ldg(reinterpret_cast<const float4*>(gamma + c) + 1);
+      if (beta) b = __ldg(reinterpret_cast<const float4*>(beta + c) + 1);
+      const float2 v2 = unpack2<T>(opaque(raw[k].z)), v3 = unpack2<T>(opaque(raw[k].w));
+      o.z = pack2<T>(fmaf((v2.x - mean) * scale, g.x, b.x), fmaf((v2.y - mean) * scale, g.y, b.y));
+      o.w = pack2<T>(fmaf((v3.x - mean) * scale, g.z, b.z), fmaf((v3.y - mean) * scale, g.w, b.w));
+    }
+    py[k * 32] = o;
+  }
+}
+
 template <typename T>
 __global__ void mvn_rows_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int64_t cols, int normalize_variance, int eps_outside, float eps) {
@@ -1031,6 +1102,19 @@ void launch_softmax(const void* x, void* y, int64_t outer, int64_t axis, int64_t
 void launch_mvn(const void* x, void* y, const float* gamma, const float* beta, int64_t rows, int64_t cols, int normalize_variance,
                 int eps_outside, float eps, int dtype, cudaStream_t s) {
   if (rows * cols == 0) return;
+  if (dtype != B200_F32 && cols % 256 == 0 && cols <= 1024 && rows < (int64_t(1) << 31) && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0 &&
+      (uintptr_t)gamma % 16 == 0 && (uintptr_t)beta % 16 == 0) {
+    static const bool exact = [] { const char* e = getenv("B200_MVN_EXACT"); return !(e && e[0] == '0'); }();
+    if (exact) {
+      const unsigned g8 = grid_for(rows, 8);
+#define B200_MVNX(T, C_) mvn_rows_exact_kernel<T, C_><<<g8, 256, 0, s>>>((const T*)x, (T*)y, gamma, beta, (uint32_t)rows, normalize_variance, eps_outside, eps)
+#define B200_MVNX_COLS(T) switch (cols / 256) { case 1: B200_MVNX(T, 1); break; case 2: B200_MVNX(T, 2); break; case 3: B200_MVNX(T, 3); break; default: B200_MVNX(T, 4); break; }
+      if (dtype == B200_BF16) { B200_MVNX_COLS(__nv_bfloat16) } else { B200_MVNX_COLS(__half) }
+#undef B200_MVNX_COLS
+#undef B200_MVNX
+      return;
+    }
+  }
   if (cols % 8 == 0 && cols <= 2048 && cols >= 64 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0) {
     const unsigned grid = grid_for(rows, 8);
     const int chunks = (int)((cols + 255) / 256);
