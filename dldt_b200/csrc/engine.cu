@@ -105,20 +105,29 @@ void b200_request::enqueue_all(bool eager_events, std::vector<cudaEvent_t>* evs)
 // Times every alternative of every step that has some (5 event-bracketed launches after one warm-up, best of 5) with the real shapes
 // and buffers, and keeps the fastest.  The buffers hold whatever the arena holds (nothing has run yet): the tensor-core and copy
 // kernels are data independent in time.  Runs once per network.
+namespace {
+struct EventPair {   // RAII: a throwing launch must not leak the two timing events
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  EventPair() {
+    B200_CUDA(cudaEventCreate(&e0));
+    if (cudaEventCreate(&e1) != cudaSuccess) { cudaEventDestroy(e0); e0 = nullptr; B200_THROW(B200_ERR_CUDA, "cudaEventCreate failed"); }
+  }
+  ~EventPair() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+};
+}  // namespace
+
 void b200_network::autotune(const b200::RunCtx& c, cudaStream_t stream) {
   std::lock_guard<std::mutex> lk(tune_mu);
   if (tuned) return;
-  tuned = true;
   bool any = false;
   for (auto& s : steps) any = any || s.alts.size() > 1;
-  if (!any) return;
-  cudaEvent_t e0, e1;
-  B200_CUDA(cudaEventCreate(&e0));
-  B200_CUDA(cudaEventCreate(&e1));
+  if (!any) { tuned = true; return; }
+  EventPair ev;
   const char* dbg = getenv("B200_AUTOTUNE_DEBUG");
-  // B200_TUNE_FILE: decisions of an earlier load ("<network>\t<step>\t<impl>" lines) are reused instead of measured again, new ones appended
+  // Decisions of an earlier load are reused instead of measured again: the table imported with the network (Export/ImportNetwork,
+  // CACHE_DIR) first, then B200_TUNE_FILE ("<network>\t<step>\t<impl>" lines; new decisions are appended to it)
   const char* tune_file = getenv("B200_TUNE_FILE");
-  std::map<std::string, std::string> cached;
+  std::map<std::string, std::string> cached = tune_preset;
   const std::string key = name + "@" + std::to_string((long long)arena_bytes);   // same graph at another batch size is another network
   if (tune_file) {
     std::ifstream in(tune_file);
@@ -126,7 +135,7 @@ void b200_network::autotune(const b200::RunCtx& c, cudaStream_t stream) {
     while (std::getline(in, line)) {
       size_t a = line.find('\t'), b = a == std::string::npos ? a : line.find('\t', a + 1);
       if (b == std::string::npos || line.substr(0, a) != key) continue;
-      cached[line.substr(a + 1, b - a - 1)] = line.substr(b + 1);
+      cached.emplace(line.substr(a + 1, b - a - 1), line.substr(b + 1));
     }
   }
   std::string fresh;
@@ -144,12 +153,12 @@ void b200_network::autotune(const b200::RunCtx& c, cudaStream_t stream) {
     for (size_t a = 0; a < s.alts.size(); ++a) {
       float ms_min = 1e30f;
       for (int rep = 0; rep < 6; ++rep) {
-        B200_CUDA(cudaEventRecord(e0, stream));
+        B200_CUDA(cudaEventRecord(ev.e0, stream));
         s.alts[a].second(c);
-        B200_CUDA(cudaEventRecord(e1, stream));
-        B200_CUDA(cudaEventSynchronize(e1));
+        B200_CUDA(cudaEventRecord(ev.e1, stream));
+        B200_CUDA(cudaEventSynchronize(ev.e1));
         float ms = 0.f;
-        B200_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        B200_CUDA(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
         if (rep > 0) ms_min = std::min(ms_min, ms);
       }
       if (dbg && dbg[0] == '1') fprintf(stderr, "b200 autotune %-24s %-44s %8.1f us\n", s.name.c_str(), s.alts[a].first.c_str(), ms_min * 1e3f);
@@ -166,21 +175,30 @@ void b200_network::autotune(const b200::RunCtx& c, cudaStream_t stream) {
     std::ofstream out(tune_file, std::ios::app);
     out << fresh;
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
+  tuned = true;   // only after every measurement succeeded: a failed attempt is retried by the next request
+}
+
+std::string b200_network::tuning_text() const {
+  std::string t;
+  for (const auto& s : steps)
+    if (s.alts.size() > 1) t += s.name + "\t" + s.impl + "\n";
+  return t;
 }
 
 void b200_request::finalize() {
   if (finalized) return;
   B200_CUDA(cudaSetDevice(net->device));
   net->autotune(ctx(), stream);
+  // a failed attempt (allocation, capture) leaves `finalized` false: the next start() retries, so staging buffers that already exist are kept
   for (size_t i = 0; i < in_fmt.size(); ++i) {
     in_fmt[i].bytes = numel(net->in_tensors[i].shape) * (int64_t)dtype_size(in_fmt[i].dtype);
+    if (in_dev[i]) continue;
     B200_CUDA(cudaMalloc((void**)&in_dev[i], std::max<int64_t>(in_fmt[i].bytes, 16)));
     B200_CUDA(cudaMemsetAsync(in_dev[i], 0, std::max<int64_t>(in_fmt[i].bytes, 16), stream));
   }
   for (size_t i = 0; i < out_fmt.size(); ++i) {
     out_fmt[i].bytes = numel(net->out_tensors[i].shape) * (int64_t)dtype_size(out_fmt[i].dtype);
+    if (out_dev[i]) continue;
     B200_CUDA(cudaMalloc((void**)&out_dev[i], std::max<int64_t>(out_fmt[i].bytes, 16)));
   }
   launches_per_infer = (int)(net->steps.size() + in_dev.size() + out_dev.size());
@@ -366,6 +384,60 @@ int b200_network_stat(const b200_network* net, const char* key, double* value) {
   });
 }
 
+// Kernel selection now instead of at the first request: a temporary arena + stream, the alternatives of every step timed on it.
+int b200_network_tune(b200_network* net) {
+  return guarded([&] {
+    B200_CHECK(net, B200_ERR_INVALID, "null argument");
+    B200_CHECK(net->device >= 0 && net->weights_dev, B200_ERR_NO_DEVICE, "network was compiled without a device (dry compile)");
+    if (net->tuned) return (int)B200_OK;
+    B200_CUDA(cudaSetDevice(net->device));
+    struct Tmp {
+      cudaStream_t stream = nullptr;
+      char* arena = nullptr;
+      ~Tmp() { if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); } if (arena) cudaFree(arena); }
+    } tmp;
+    B200_CUDA(cudaStreamCreateWithFlags(&tmp.stream, cudaStreamNonBlocking));
+    cudaError_t e = cudaMalloc((void**)&tmp.arena, (size_t)net->arena_bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); B200_THROW(B200_ERR_OOM, "cannot allocate " << net->arena_bytes << " bytes of activation arena"); }
+    B200_CUDA(cudaMemsetAsync(tmp.arena, 0, (size_t)net->arena_bytes, tmp.stream));
+    RunCtx c;
+    c.arena = tmp.arena;
+    c.box_offset = net->box_offsets.data();
+    c.weights = net->weights_dev;
+    c.stream = tmp.stream;
+    net->autotune(c, tmp.stream);
+    return (int)B200_OK;
+  });
+}
+int b200_network_get_tuning(const b200_network* net, char* buf, size_t capacity, size_t* needed) {
+  return guarded([&] {
+    B200_CHECK(net && needed, B200_ERR_INVALID, "null argument");
+    const std::string t = net->tuning_text();
+    *needed = t.size() + 1;
+    if (buf && capacity >= t.size() + 1) memcpy(buf, t.c_str(), t.size() + 1);
+    return (int)B200_OK;
+  });
+}
+int b200_network_set_tuning(b200_network* net, const char* text) {
+  return guarded([&] {
+    B200_CHECK(net && text, B200_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(net->tune_mu);
+    B200_CHECK(!net->tuned, B200_ERR_BUSY, "kernel selection already done");
+    std::string all = text;
+    size_t pos = 0;
+    while (pos < all.size()) {
+      size_t nl = all.find('\n', pos);
+      if (nl == std::string::npos) nl = all.size();
+      const std::string line = all.substr(pos, nl - pos);
+      pos = nl + 1;
+      const size_t tab = line.find('\t');
+      if (tab == std::string::npos) continue;
+      net->tune_preset[line.substr(0, tab)] = line.substr(tab + 1);
+    }
+    return (int)B200_OK;
+  });
+}
+
 int b200_request_create(b200_network* net, b200_request** out) {
   return guarded([&] {
     B200_CHECK(net && out, B200_ERR_INVALID, "null argument");
@@ -439,7 +511,7 @@ int b200_request_wait(b200_request* req, int64_t timeout_ms) {
   return guarded([&] {
     B200_CHECK(req, B200_ERR_INVALID, "null argument");
     B200_CUDA(cudaSetDevice(req->net->device));
-    if (!req->started) return (int)B200_OK;
+    if (!req->started.load()) return (int)B200_OK;
     if (timeout_ms < 0) {
       B200_CUDA(cudaEventSynchronize(req->done));
       return (int)B200_OK;

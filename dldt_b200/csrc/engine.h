@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <map>
 #include <mutex>
 
 #include "common.h"
@@ -32,7 +34,9 @@ struct b200_network {
   // kernel selection by measurement: steps that carry alternatives are timed once, on the first request's arena and stream
   std::mutex tune_mu;
   bool tuned = false;
+  std::map<std::string, std::string> tune_preset;   // step name -> impl: decisions imported with the network (b200_network_set_tuning)
   void autotune(const b200::RunCtx& c, cudaStream_t stream);
+  std::string tuning_text() const;                  // "step\timpl\n" for every step that had alternatives
   ~b200_network();
 };
 
@@ -52,7 +56,7 @@ struct b200_request {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
   cudaEvent_t done = nullptr;
-  bool started = false;
+  std::atomic<bool> started{false};
   int launches_per_infer = 0;
   std::mutex mu;
   ~b200_request();

@@ -196,11 +196,12 @@ def _ssd_priors(fmaps, image, aspect, rng):
 
 
 def ssd300_resnet34(batch=1, image=300, width=64, num_classes=81, seed=4, trunk_blocks=(3, 4, 6), keep_top_k=200, top_k=200,
-                    input_dtype=np.float32, head_scale=0.5):
+                    input_dtype=np.float32, head_scale=0.5, conf_scale=None):
     """SSD300 with a ResNet-34 trunk to conv4_x (stride-1 variant), 5 extra blocks, 6 heads and
     DetectionOutput.  head_scale multiplies the He-initialised head weights: at full width the default 0.5 (what
     the committed golden cases were generated with) lets the random-init location head overflow exp() in the box decoder; the full-size
-    runs of tools/gpu_configs.py use 0.02."""
+    runs of tools/gpu_configs.py use 0.02.  conf_scale (default: head_scale) scales the confidence heads separately so that the full-size
+    parity fixtures (tools/make_config_golden.py) get a softmax that is neither saturated nor uniform."""
     f = Function("ssd300_resnet34")
     init = _Init(seed)
     x = f.parameter((batch, 3, image, image), input_dtype, name="data")
@@ -237,7 +238,8 @@ def ssd300_resnet34(batch=1, image=300, width=64, num_classes=81, seed=4, trunk_
     for hi, (ft, na) in enumerate(zip(feats, anchors)):
         c = ft.shape[1]
         for kind, ch, lst in (("loc", na * 4, locs), ("conf", na * num_classes, confs)):
-            h = f.add(f.convolution(ft, init.conv(ch, c, 3, 3) * head_scale, (1, 1), (1, 1), (1, 1), name="head%d_%s" % (hi, kind)),
+            hsc = head_scale if (kind == "loc" or conf_scale is None) else conf_scale
+            h = f.add(f.convolution(ft, init.conv(ch, c, 3, 3) * hsc, (1, 1), (1, 1), (1, 1), name="head%d_%s" % (hi, kind)),
                       init.vec(ch).reshape(1, -1, 1, 1), name="head%d_%s_bias" % (hi, kind))
             h = f.transpose(h, (0, 2, 3, 1), name="head%d_%s_perm" % (hi, kind))
             lst.append(f.reshape(h, (batch, -1), name="head%d_%s_flat" % (hi, kind)))

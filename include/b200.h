@@ -195,6 +195,15 @@ B200_API int b200_network_exec_node(const b200_network* net, int index, b200_exe
 /* key in {"arena_bytes","weight_bytes","flops","bytes","num_kernels","device","precision"} */
 B200_API int b200_network_stat(const b200_network* net, const char* key, double* value);
 
+/* Kernel selection (the per-layer choice between alternative kernels is MEASURED once per network, engine.cu autotune):
+ * _tune runs it now on a temporary arena instead of at the first request; _get_tuning returns the decisions as text
+ * ("<exec node>\t<impl>\n" lines; *needed = bytes including the terminator, buf may be NULL to query); _set_tuning installs
+ * decisions of an earlier load so they are not measured again.  This table is what ExecutableNetwork::Export carries besides the IR
+ * (docs/template_plugin/src/template_executable_network.cpp:179-200; inference-engine/src/inference_engine/ie_core.cpp:265-340). */
+B200_API int b200_network_tune(b200_network* net);
+B200_API int b200_network_get_tuning(const b200_network* net, char* buf, size_t capacity, size_t* needed);
+B200_API int b200_network_set_tuning(b200_network* net, const char* text);
+
 /* The static activation-memory planner on its own: boxes (first, last, bytes) over execution indices,
  * last < 0 = lives to the end; writes the offset of every box and the arena size.  Replaces
  * MemorySolver::solve/getOffset (inference-engine/src/mkldnn_plugin/mkldnn_memory_solver.cpp:51-96,126-131). */
