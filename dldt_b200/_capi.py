@@ -73,6 +73,9 @@ SYMBOLS = {
     "b200_network_num_exec_nodes": (C.c_int, [_P]),
     "b200_network_exec_node": (C.c_int, [_P, C.c_int, C.POINTER(ExecNodeInfo)]),
     "b200_network_stat": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double)]),
+    "b200_network_tune": (C.c_int, [_P]),
+    "b200_network_get_tuning": (C.c_int, [_P, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "b200_network_set_tuning": (C.c_int, [_P, C.c_char_p]),
     "b200_plan_arena": (C.c_int, [C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
                                   C.POINTER(C.c_int64)]),
     "b200_request_create": (C.c_int, [_P, C.POINTER(_P)]),

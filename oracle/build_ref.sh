@@ -83,7 +83,7 @@ cat > "$OUT/lib/plugins.xml" <<XML
 XML
 # ie_run: the small driver (tools/ie_run.cpp, OUR source) that feeds raw inputs through the reference's public API;
 # compiled against the reference headers where they lie, linked to the libraries built above
-/usr/bin/g++ -O2 -std=c++14 -include cstdint -w -I"$REF/inference-engine/include" -I"$REF/ngraph/core/include" \
+/usr/bin/g++ -O2 -std=c++14 -include cstdint -w -I"$REF/inference-engine/include" -I"$REF/ngraph/core/include" -I"$REF/inference-engine/src/plugin_api" \
     "$HERE/../tools/ie_run.cpp" -o "$OUT/bin/ie_run" -L"$OUT/lib" -linference_engine -lngraph -Wl,-rpath,'$ORIGIN/../lib'
 echo "$WORK/src" > "$OUT/BUILT_FROM.txt"
 date -u +%FT%TZ >> "$OUT/BUILT_FROM.txt"

@@ -63,6 +63,40 @@ std::shared_ptr<ngraph::Function> TransformNetwork(const std::shared_ptr<const n
     return f;
 }
 
+std::shared_ptr<ngraph::Function> ShardBatch(const std::shared_ptr<const ngraph::Function>& function, size_t shards) {
+    auto f = ngraph::clone_function(*function);
+    if (shards <= 1) return f;
+    const auto& params = f->get_parameters();
+    if (params.empty() || params[0]->get_shape().empty()) IE_THROW(ParameterMismatch) << "B200 plugin: network has no batched input to shard";
+    const size_t batch = params[0]->get_shape()[0];
+    if (batch % shards != 0) IE_THROW(ParameterMismatch) << "B200 plugin: batch " << batch << " does not divide over " << shards << " devices";
+    const size_t part = batch / shards;
+    for (const auto& p : params) {
+        auto shape = p->get_shape();
+        if (!shape.empty() && shape[0] == batch) {
+            shape[0] = part;
+            p->set_partial_shape(ngraph::PartialShape(shape));
+        }
+    }
+    for (const auto& node : f->get_ordered_ops()) {
+        if (auto reshape = as_type_ptr<ngraph::opset1::Reshape>(node)) {
+            auto target = as_type_ptr<ngraph::opset1::Constant>(reshape->input_value(1).get_node_shared_ptr());
+            const auto& in = reshape->get_input_partial_shape(0);
+            if (target && in.rank().is_static() && in.rank().get_length() > 0 && in[0].is_static() && static_cast<size_t>(in[0].get_length()) == part) {
+                auto dims = target->cast_vector<int64_t>();
+                if (!dims.empty() && dims[0] == static_cast<int64_t>(batch)) {
+                    dims[0] = static_cast<int64_t>(part);
+                    auto replacement = ngraph::opset1::Constant::create(target->get_element_type(), target->get_shape(), dims);
+                    replacement->set_friendly_name(target->get_friendly_name());
+                    reshape->input(1).replace_source_output(replacement->output(0));
+                }
+            }
+        }
+        node->revalidate_and_infer_types();
+    }
+    return f;
+}
+
 namespace {
 
 int ToDtype(const ngraph::element::Type& t) {

@@ -15,6 +15,11 @@ namespace B200Plugin {
 // the analogue of Transformation() in mkldnn_plugin.cpp:115-383) on a clone of `function`.
 std::shared_ptr<ngraph::Function> TransformNetwork(const std::shared_ptr<const ngraph::Function>& function);
 
+// Clone of `function` whose batch (dim 0 of the first Parameter) is divided by `shards`: every Parameter that carries the batch is
+// re-shaped, Reshape target-shape constants that spell the batch out are rewritten, and the clone is re-validated node by node (the
+// plugin-side analogue of CNNNetwork::setBatchSize / reshape).  Throws ParameterMismatch if the batch does not divide.
+std::shared_ptr<ngraph::Function> ShardBatch(const std::shared_ptr<const ngraph::Function>& function, size_t shards);
+
 // true if `node` (after TransformNetwork) maps onto a b200_op; `why` receives the reason otherwise.
 bool IsNodeSupported(const std::shared_ptr<ngraph::Node>& node, std::string* why = nullptr);
 

@@ -4,6 +4,7 @@
 #include <blob_factory.hpp>
 #include <exec_graph_info.hpp>
 #include <ie_algorithm.hpp>
+#include <ie_icore.hpp>
 #include <ie_metric_helpers.hpp>
 #include <ie_ngraph_utils.hpp>
 #include <ie_plugin_config.hpp>
@@ -12,6 +13,9 @@
 #include <ngraph/opsets/opset1.hpp>
 #include <ngraph/variant.hpp>
 #include <transformations/rt_info/fused_names_attribute.hpp>
+#include <transformations/serialize.hpp>
+#include <cstdlib>
+#include <sstream>
 #include <unordered_set>
 
 #include "b200/b200_config.hpp"
@@ -45,14 +49,9 @@ Configuration::Configuration(const std::map<std::string, std::string>& config, c
         const auto& key = kv.first;
         const auto& value = kv.second;
         if (key == CONFIG_KEY(DEVICE_ID)) {
-            try {
-                deviceId = value.empty() ? 0 : std::stoi(value);
-            } catch (...) {
-                IE_THROW(ParameterMismatch) << "B200 plugin: bad DEVICE_ID '" << value << "'";
-            }
-            int count = 0;
-            b200_device_count(&count);
-            if (deviceId < 0 || (count > 0 && deviceId >= count)) IE_THROW(NotFound) << "B200 plugin: DEVICE_ID " << deviceId << " out of range (" << count << " devices)";
+            deviceId = value.empty() ? "0" : value;
+        } else if (key == B200ConfigParams::KEY_B200_DEVICES) {
+            deviceList = value;
         } else if (key == CONFIG_KEY(PERF_COUNT)) {
             if (value != CONFIG_VALUE(YES) && value != CONFIG_VALUE(NO)) IE_THROW(ParameterMismatch) << "B200 plugin: PERF_COUNT must be YES or NO";
             perfCount = value == CONFIG_VALUE(YES);
@@ -76,16 +75,49 @@ Configuration::Configuration(const std::map<std::string, std::string>& config, c
             IE_THROW(NotFound) << "Unsupported property " << key << " by B200 plugin";   // config.cpp:112-114 of the CPU plugin
         }
     }
+    // resolve the device set: B200_DEVICES ("0,1,2,3") wins over DEVICE_ID ("3" | "ALL"); a dry compile touches no device
+    int count = 0;
+    b200_device_count(&count);
+    devices.clear();
+    auto add = [&](const std::string& text) {
+        int id = -1;
+        try {
+            size_t used = 0;
+            id = std::stoi(text, &used);
+            if (used != text.size()) id = -1;
+        } catch (...) {
+            id = -1;
+        }
+        if (id < 0) IE_THROW(ParameterMismatch) << "B200 plugin: bad device id '" << text << "'";
+        if (!dryCompile && count > 0 && id >= count) IE_THROW(NotFound) << "B200 plugin: DEVICE_ID " << id << " out of range (" << count << " devices)";
+        devices.push_back(id);    // a device may be listed twice (two replicas on one GPU): legal, and how a 1-GPU box tests the scatter/gather
+    };
+    if (!deviceList.empty()) {
+        std::stringstream ss(deviceList);
+        std::string item;
+        while (std::getline(ss, item, ',')) add(item);
+    } else if (deviceId == "ALL") {
+        for (int k = 0; k < std::max(count, 1); ++k) devices.push_back(k);
+    } else {
+        add(deviceId);
+    }
+    if (devices.empty()) IE_THROW(ParameterMismatch) << "B200 plugin: empty device list";
 }
 
 std::string Configuration::PrecisionName() const { return precision == B200_PREC_FP32 ? "FP32" : (precision == B200_PREC_BF16 ? "BF16" : "FP16"); }
 
 std::vector<std::string> Configuration::SupportedKeys() {
-    return {CONFIG_KEY(DEVICE_ID), CONFIG_KEY(PERF_COUNT), B200ConfigParams::KEY_B200_INFERENCE_PRECISION, B200ConfigParams::KEY_B200_THROUGHPUT_STREAMS};
+    return {CONFIG_KEY(DEVICE_ID), CONFIG_KEY(PERF_COUNT), B200ConfigParams::KEY_B200_INFERENCE_PRECISION, B200ConfigParams::KEY_B200_THROUGHPUT_STREAMS,
+            B200ConfigParams::KEY_B200_DEVICES};
 }
 
 Parameter Configuration::Get(const std::string& name) const {
-    if (name == CONFIG_KEY(DEVICE_ID)) return {std::to_string(deviceId)};
+    if (name == CONFIG_KEY(DEVICE_ID)) return {deviceId};
+    if (name == B200ConfigParams::KEY_B200_DEVICES) {
+        std::string list;
+        for (size_t k = 0; k < devices.size(); ++k) list += (k ? "," : "") + std::to_string(devices[k]);
+        return {list};
+    }
     if (name == CONFIG_KEY(PERF_COUNT)) return {std::string(perfCount ? CONFIG_VALUE(YES) : CONFIG_VALUE(NO))};
     if (name == B200ConfigParams::KEY_B200_INFERENCE_PRECISION) return {PrecisionName()};
     if (name == B200ConfigParams::KEY_B200_THROUGHPUT_STREAMS) return {std::to_string(streams)};
@@ -96,7 +128,8 @@ Parameter Configuration::Get(const std::string& name) const {
 Plugin::Plugin() {
     _pluginName = "B200";
     // wait stages block a thread on a CUDA event: they get their own executor so that start stages are never starved
-    _waitExecutor = ExecutorManager::getInstance()->getIdleCPUStreamsExecutor({"B200WaitExecutor", 4});
+    // (RANGE_FOR_ASYNC_INFER_REQUESTS advertises up to 16 requests in flight: one blocked thread each at worst)
+    _waitExecutor = ExecutorManager::getInstance()->getIdleCPUStreamsExecutor({"B200WaitExecutor", 16});
 }
 
 Plugin::~Plugin() {
@@ -115,7 +148,9 @@ Parameter Plugin::GetMetric(const std::string& name, const std::map<std::string,
         IE_SET_METRIC_RETURN(SUPPORTED_METRICS, std::vector<std::string>{METRIC_KEY(AVAILABLE_DEVICES), METRIC_KEY(SUPPORTED_METRICS), METRIC_KEY(SUPPORTED_CONFIG_KEYS),
                                                                          METRIC_KEY(FULL_DEVICE_NAME), METRIC_KEY(DEVICE_ARCHITECTURE),
                                                                          METRIC_KEY(OPTIMIZATION_CAPABILITIES), METRIC_KEY(RANGE_FOR_ASYNC_INFER_REQUESTS),
-                                                                         METRIC_KEY(RANGE_FOR_STREAMS)});
+                                                                         METRIC_KEY(RANGE_FOR_STREAMS), METRIC_KEY(IMPORT_EXPORT_SUPPORT)});
+    } else if (name == METRIC_KEY(IMPORT_EXPORT_SUPPORT)) {
+        IE_SET_METRIC_RETURN(IMPORT_EXPORT_SUPPORT, true);
     } else if (name == METRIC_KEY(SUPPORTED_CONFIG_KEYS)) {
         IE_SET_METRIC_RETURN(SUPPORTED_CONFIG_KEYS, Configuration::SupportedKeys());
     } else if (name == METRIC_KEY(AVAILABLE_DEVICES)) {
@@ -125,9 +160,15 @@ Parameter Plugin::GetMetric(const std::string& name, const std::map<std::string,
         for (int k = 0; k < count; ++k) ids.push_back(std::to_string(k));
         IE_SET_METRIC_RETURN(AVAILABLE_DEVICES, ids);
     } else if (name == METRIC_KEY(FULL_DEVICE_NAME)) {
-        int dev = _cfg.deviceId;
+        int dev = _cfg.devices.front();
         auto it = options.find(CONFIG_KEY(DEVICE_ID));
-        if (it != options.end()) dev = std::stoi(it->second.as<std::string>());
+        if (it != options.end()) {
+            try {
+                dev = std::stoi(it->second.as<std::string>());
+            } catch (...) {
+                dev = _cfg.devices.front();   // "ALL"
+            }
+        }
         char buf[256] = "NVIDIA B200 (no device visible)";
         b200_device_name(dev, buf, sizeof(buf));
         IE_SET_METRIC_RETURN(FULL_DEVICE_NAME, std::string(buf));
@@ -154,6 +195,123 @@ IExecutableNetworkInternal::Ptr Plugin::LoadExeNetworkImpl(const CNNNetwork& net
     }
     Configuration cfg{config, _cfg};
     return std::make_shared<ExecutableNetwork>(function, cfg, std::static_pointer_cast<Plugin>(shared_from_this()));
+}
+
+// ---- Export / Import (docs/template_plugin/src/template_executable_network.cpp:179-200, template_plugin.cpp:108-112; the Core drives
+// them for CACHE_DIR: inference-engine/src/inference_engine/ie_core.cpp:265-340).  Stream layout:
+//   "B200NET1" | precision,streams (i32) | device id text, device list text | inputs: name, precision, layout | outputs: name, precision |
+//   IR v10 xml | IR weights | kernel-selection table (b200_network_get_tuning).
+// The IR is the network as loaded; what the export saves on import is the measured part of LoadNetwork: the per-layer kernel selection.
+namespace {
+const char kMagic[8] = {'B', '2', '0', '0', 'N', 'E', 'T', '1'};
+
+void putString(std::ostream& os, const std::string& v) {
+    const uint64_t n = v.size();
+    os.write(reinterpret_cast<const char*>(&n), sizeof(n));
+    os.write(v.data(), static_cast<std::streamsize>(n));
+}
+std::string getString(std::istream& is) {
+    uint64_t n = 0;
+    is.read(reinterpret_cast<char*>(&n), sizeof(n));
+    if (!is || n > (uint64_t(1) << 34)) IE_THROW(NetworkNotRead) << "B200 plugin: truncated or corrupt exported network";
+    std::string v(static_cast<size_t>(n), '\0');
+    is.read(&v[0], static_cast<std::streamsize>(n));
+    if (!is) IE_THROW(NetworkNotRead) << "B200 plugin: truncated exported network";
+    return v;
+}
+void putInt(std::ostream& os, int32_t v) { os.write(reinterpret_cast<const char*>(&v), sizeof(v)); }
+int32_t getInt(std::istream& is) {
+    int32_t v = 0;
+    is.read(reinterpret_cast<char*>(&v), sizeof(v));
+    if (!is) IE_THROW(NetworkNotRead) << "B200 plugin: truncated exported network";
+    return v;
+}
+}  // namespace
+
+void ExecutableNetwork::Export(std::ostream& model) {
+    model.write(kMagic, sizeof(kMagic));
+    putInt(model, _cfg.precision);
+    putInt(model, _cfg.streams);
+    putString(model, _cfg.deviceId);
+    putString(model, _cfg.deviceList);
+    putInt(model, static_cast<int32_t>(_networkInputs.size()));
+    for (const auto& in : _networkInputs) {
+        putString(model, in.first);
+        putInt(model, static_cast<int32_t>(in.second->getPrecision()));
+        putInt(model, static_cast<int32_t>(in.second->getLayout()));
+    }
+    putInt(model, static_cast<int32_t>(_networkOutputs.size()));
+    for (const auto& out : _networkOutputs) {
+        putString(model, out.first);
+        putInt(model, static_cast<int32_t>(out.second->getPrecision()));
+    }
+    std::map<std::string, ngraph::OpSet> custom_opsets;
+    std::stringstream xml, bin;
+    ngraph::pass::Serialize serializer(xml, bin, ngraph::pass::Serialize::Version::IR_V10, custom_opsets);
+    serializer.run_on_function(_function);
+    putString(model, xml.str());
+    putString(model, bin.str());
+    size_t need = 0;
+    std::string tuning;
+    if (!_cfg.dryCompile && b200_network_get_tuning(_nets[0], nullptr, 0, &need) == B200_OK && need > 1) {
+        tuning.resize(need);
+        b200_network_get_tuning(_nets[0], &tuning[0], need, &need);
+        tuning.resize(need - 1);
+    }
+    putString(model, tuning);
+}
+
+IExecutableNetworkInternal::Ptr Plugin::ImportNetwork(std::istream& model, const std::map<std::string, std::string>& config) {
+    char magic[sizeof(kMagic)] = {};
+    model.read(magic, sizeof(magic));
+    if (!model || std::memcmp(magic, kMagic, sizeof(kMagic)) != 0) IE_THROW(NetworkNotRead) << "B200 plugin: not an exported B200 network";
+    Configuration stored = _cfg;
+    stored.precision = getInt(model);
+    stored.streams = getInt(model);
+    std::map<std::string, std::string> storedDevices;
+    storedDevices[CONFIG_KEY(DEVICE_ID)] = getString(model);
+    const std::string list = getString(model);
+    if (!list.empty()) storedDevices[B200ConfigParams::KEY_B200_DEVICES] = list;
+    std::vector<std::tuple<std::string, int, int>> ins;
+    std::vector<std::pair<std::string, int>> outs;
+    for (int k = 0, n = getInt(model); k < n; ++k) {
+        std::string name = getString(model);
+        const int prec = getInt(model), layout = getInt(model);
+        ins.emplace_back(name, prec, layout);
+    }
+    for (int k = 0, n = getInt(model); k < n; ++k) {
+        std::string name = getString(model);
+        outs.emplace_back(name, getInt(model));
+    }
+    const std::string xml = getString(model);
+    const std::string bin = getString(model);
+    const std::string tuning = getString(model);
+    // what the caller passes now wins over what was stored (the Core hashes the config into the cache key, so for CACHE_DIR they agree)
+    std::map<std::string, std::string> merged = storedDevices;
+    for (const auto& kv : config) merged[kv.first] = kv.second;
+    Configuration cfg{merged, stored};
+    auto core = GetCore();
+    if (!core) IE_THROW(GeneralError) << "B200 plugin: ImportNetwork needs the Core (IR reader)";
+    auto weights = make_shared_blob<uint8_t>(TensorDesc(Precision::U8, {bin.size()}, Layout::C));
+    weights->allocate();
+    if (!bin.empty()) std::memcpy(weights->buffer().as<uint8_t*>(), bin.data(), bin.size());
+    CNNNetwork network = core->ReadNetwork(xml, weights);
+    for (const auto& in : ins) {
+        auto it = network.getInputsInfo().find(std::get<0>(in));
+        if (it == network.getInputsInfo().end()) IE_THROW(NetworkNotRead) << "B200 plugin: exported network names an unknown input '" << std::get<0>(in) << "'";
+        it->second->setPrecision(Precision(static_cast<Precision::ePrecision>(std::get<1>(in))));
+        it->second->setLayout(static_cast<Layout>(std::get<2>(in)));
+    }
+    for (const auto& out : outs) {
+        auto it = network.getOutputsInfo().find(out.first);
+        if (it == network.getOutputsInfo().end()) IE_THROW(NetworkNotRead) << "B200 plugin: exported network names an unknown output '" << out.first << "'";
+        it->second->setPrecision(Precision(static_cast<Precision::ePrecision>(out.second)));
+    }
+    auto exe = std::make_shared<ExecutableNetwork>(network.getFunction(), cfg, std::static_pointer_cast<Plugin>(shared_from_this()), tuning);
+    exe->setNetworkInputs(network.getInputsInfo());
+    exe->setNetworkOutputs(network.getOutputsInfo());
+    exe->SetPointerToPlugin(shared_from_this());
+    return exe;
 }
 
 // docs/template_plugin/src/template_plugin.cpp:117-195 describes the recipe: transform a clone, mark an original layer supported
@@ -197,26 +355,92 @@ QueryNetworkResult Plugin::QueryNetwork(const CNNNetwork& network, const std::ma
 }
 
 // ---- executable network -----------------------------------------------------------------------------------------------
-ExecutableNetwork::ExecutableNetwork(const std::shared_ptr<const ngraph::Function>& function, const Configuration& cfg, const std::shared_ptr<Plugin>& plugin)
+ExecutableNetwork::ExecutableNetwork(const std::shared_ptr<const ngraph::Function>& function, const Configuration& cfg, const std::shared_ptr<Plugin>& plugin,
+                                     const std::string& tuning)
     : ExecutableNetworkThreadSafeDefault(nullptr, nullptr), _cfg(cfg), _pluginRef(plugin), _name(function->get_friendly_name()) {
-    auto transformed = TransformNetwork(function);
+    _function = ngraph::clone_function(*function);
+    const int shards = static_cast<int>(cfg.devices.size());
+    // batch sharding: the replica every device runs is the same function at batch N / G (ShardBatch re-validates the clone)
+    auto replica = shards > 1 ? ShardBatch(function, static_cast<size_t>(shards)) : _function;
+    auto transformed = TransformNetwork(replica);
     b200_graph* graph = LowerFunction(transformed);
-    b200_compile_options opts;
-    std::memset(&opts, 0, sizeof(opts));
-    opts.abi_version = B200_ABI_VERSION;
-    opts.device = cfg.dryCompile ? -1 : cfg.deviceId;
-    opts.precision = cfg.precision;
-    int rc = b200_compile(graph, &opts, &_net);
+    std::string table = tuning;
+    try {
+        for (int g = 0; g < shards; ++g) {
+            b200_compile_options opts;
+            std::memset(&opts, 0, sizeof(opts));
+            opts.abi_version = B200_ABI_VERSION;
+            opts.device = cfg.dryCompile ? -1 : cfg.devices[g];
+            opts.precision = cfg.precision;
+            b200_network* net = nullptr;
+            int rc = b200_compile(graph, &opts, &net);
+            if (rc < 0) ThrowFromStatus(rc, "cannot compile network '" + _name + "'" + (shards > 1 ? " for device " + std::to_string(cfg.devices[g]) : ""));
+            _nets.push_back(net);
+            if (cfg.dryCompile) continue;
+            // kernel selection is measured once (first device, or imported with the network) and installed on the other replicas:
+            // the devices of one box are identical parts
+            if (!table.empty()) B200_CALL(b200_network_set_tuning(net, table.c_str()), "kernel-selection table");
+            B200_CALL(b200_network_tune(net), "kernel selection");
+            if (table.empty()) {
+                size_t need = 0;
+                if (b200_network_get_tuning(net, nullptr, 0, &need) == B200_OK && need > 1) {
+                    table.resize(need);
+                    b200_network_get_tuning(net, &table[0], need, &need);
+                    table.resize(need - 1);
+                }
+            }
+        }
+    } catch (...) {
+        b200_graph_destroy(graph);
+        for (auto* n : _nets) b200_network_destroy(n);
+        _nets.clear();
+        throw;
+    }
     b200_graph_destroy(graph);
-    if (rc < 0) ThrowFromStatus(rc, "cannot compile network '" + _name + "'");
     b200_tensor_info info;
-    for (int k = 0; k < b200_network_num_inputs(_net); ++k) {
-        B200_CALL(b200_network_io_info(_net, 0, k, &info), "io info");
+    for (int k = 0; k < b200_network_num_inputs(_nets[0]); ++k) {
+        B200_CALL(b200_network_io_info(_nets[0], 0, k, &info), "io info");
         _inputIndex[info.name] = k;
     }
-    for (int k = 0; k < b200_network_num_outputs(_net); ++k) {
-        B200_CALL(b200_network_io_info(_net, 1, k, &info), "io info");
+    for (int k = 0; k < b200_network_num_outputs(_nets[0]); ++k) {
+        B200_CALL(b200_network_io_info(_nets[0], 1, k, &info), "io info");
         _outputIndex[info.name] = k;
+    }
+    // scatter / gather plan: compare every parameter / result of the network as loaded with the replica's
+    _inPlan.assign(_inputIndex.size(), IoPlan());
+    _outPlan.assign(_outputIndex.size(), IoPlan());
+    if (shards > 1) {
+        const auto& fullParams = _function->get_parameters();
+        const auto& partParams = replica->get_parameters();
+        for (size_t k = 0; k < fullParams.size(); ++k) {
+            const auto fs = fullParams[k]->get_shape(), ps = partParams[k]->get_shape();
+            auto it = _inputIndex.find(fullParams[k]->get_friendly_name());
+            if (it == _inputIndex.end()) continue;
+            IoPlan& plan = _inPlan[it->second];
+            if (fs == ps) plan.kind = IoPlan::Replicated;
+            else if (!fs.empty() && fs[0] == ps[0] * shards && std::equal(fs.begin() + 1, fs.end(), ps.begin() + 1)) plan.kind = IoPlan::Sliced;
+            else IE_THROW(NotImplemented) << "B200 plugin: input '" << it->first << "' cannot be sharded over " << shards << " devices";
+        }
+        const size_t batch = fullParams.empty() || fullParams[0]->get_shape().empty() ? 0 : fullParams[0]->get_shape()[0];
+        const auto& fullRes = _function->get_results();
+        const auto& partRes = replica->get_results();
+        for (size_t k = 0; k < fullRes.size(); ++k) {
+            const auto fs = fullRes[k]->get_shape(), ps = partRes[k]->get_shape();
+            auto src = fullRes[k]->get_input_source_output(0);
+            std::string oname = src.get_node()->get_friendly_name();
+            if (src.get_node()->get_output_size() > 1) oname += "." + std::to_string(src.get_index());
+            auto it = _outputIndex.find(oname);
+            if (it == _outputIndex.end()) continue;
+            IoPlan& plan = _outPlan[it->second];
+            if (fs == ps) plan.kind = IoPlan::Replicated;
+            else if (!fs.empty() && fs[0] == ps[0] * shards && std::equal(fs.begin() + 1, fs.end(), ps.begin() + 1)) plan.kind = IoPlan::Sliced;
+            else if (fs.size() == 4 && fs[0] == 1 && fs[1] == 1 && fs[3] == 7 && ps[3] == 7 && fs[2] == ps[2] * shards) {
+                plan.kind = IoPlan::Detections;      // DetectionOutput [1,1,N*keep_top_k,7]: rows re-packed on the host after the wait
+                plan.images_per_shard = static_cast<int>(batch / shards);
+            } else {
+                IE_THROW(NotImplemented) << "B200 plugin: output '" << it->first << "' cannot be gathered from " << shards << " devices";
+            }
+        }
     }
     // start stages are cheap host work (enqueue); one executor thread per stream keeps submission order per stream
     auto streamsConfig = IStreamsExecutor::Config{"B200StreamsExecutor", std::max(1, cfg.streams)};
@@ -225,7 +449,7 @@ ExecutableNetwork::ExecutableNetwork(const std::shared_ptr<const ngraph::Functio
 }
 
 ExecutableNetwork::~ExecutableNetwork() {
-    if (_net) b200_network_destroy(_net);
+    for (auto* n : _nets) b200_network_destroy(n);
 }
 
 int ExecutableNetwork::inputIndex(const std::string& name) const {
@@ -279,10 +503,10 @@ CNNNetwork ExecutableNetwork::GetExecGraphInfo() {
     src->get_rt_info()[EXECUTION_ORDER] = std::make_shared<ngraph::VariantWrapper<std::string>>("0");
     params.push_back(src);
     ngraph::Output<ngraph::Node> prev = src;
-    const int n = b200_network_num_exec_nodes(_net);
+    const int n = b200_network_num_exec_nodes(_nets[0]);
     b200_exec_node_info info;
     for (int k = 0; k < n; ++k) {
-        B200_CALL(b200_network_exec_node(_net, k, &info), "exec node info");
+        B200_CALL(b200_network_exec_node(_nets[0], k, &info), "exec node info");
         auto node = std::make_shared<ExecutionNode>(ngraph::OutputVector{prev}, 1);
         node->set_friendly_name(info.name);
         auto set = [&](const char* key, const std::string& v) { node->get_rt_info()[key] = std::make_shared<ngraph::VariantWrapper<std::string>>(v); };
@@ -332,71 +556,176 @@ const void* BlobData(const Blob::Ptr& blob) {
     return mem->rmap().as<const uint8_t*>();   // includes the ROI / padding offset of the descriptor
 }
 
+// Default blobs own pinned host memory (cudaHostAlloc, portable across the devices of the box) through the IAllocator interface
+// (inference-engine/include/ie_allocator.hpp:26-40): a Blob::Ptr obtained with GetBlob stays valid after the request is gone, and
+// the H2D / D2H copies of start() are asynchronous and run at PCIe speed.
+class PinnedAllocator : public IAllocator {
+public:
+    void* lock(void* handle, LockOp = LOCK_FOR_WRITE) noexcept override { return handle; }
+    void unlock(void*) noexcept override {}
+    void* alloc(size_t size) noexcept override {
+        void* ptr = nullptr;
+        return b200_host_alloc(&ptr, std::max<size_t>(size, 16)) == B200_OK ? ptr : nullptr;
+    }
+    bool free(void* handle) noexcept override { return b200_host_free(handle) == B200_OK; }
+};
+
 }  // namespace
 
 InferRequest::InferRequest(const InputsDataMap& networkInputs, const OutputsDataMap& networkOutputs, const std::shared_ptr<ExecutableNetwork>& network)
-    : IInferRequestInternal(networkInputs, networkOutputs), _network(network) {
-    B200_CALL(b200_request_create(network->handle(), &_req), "cannot create infer request");
+    : IInferRequestInternal(networkInputs, networkOutputs), _network(network), _allocator(std::make_shared<PinnedAllocator>()) {
+    const int shards = network->numShards();
+    for (int g = 0; g < shards; ++g) {
+        b200_request* r = nullptr;
+        B200_CALL(b200_request_create(network->handle(g), &r), "cannot create infer request");
+        _reqs.push_back(r);
+    }
     _inputNames.resize(_networkInputs.size());
     _outputNames.resize(_networkOutputs.size());
-    // default blobs (GetBlob before SetBlob must work: ie_iinfer_request_internal.cpp:111-143) live in pinned host memory so
-    // the H2D/D2H copies of start() are asynchronous and run at PCIe speed
+    _inShardBytes.assign(_networkInputs.size(), 0);
+    _outShardBytes.assign(_networkOutputs.size(), 0);
+    _outStage.assign(_networkOutputs.size(), std::vector<void*>(static_cast<size_t>(shards), nullptr));
     for (const auto& in : _networkInputs) {
         const int idx = network->inputIndex(in.first);
         const TensorDesc& desc = in.second->getTensorDesc();
-        B200_CALL(b200_request_set_io_format(_req, 0, idx, BlobDtype(desc.getPrecision(), in.first), BlobLayout(desc, in.first)), "input format");
+        for (auto* r : _reqs) B200_CALL(b200_request_set_io_format(r, 0, idx, BlobDtype(desc.getPrecision(), in.first), BlobLayout(desc, in.first)), "input format");
+        B200_CALL(b200_request_io_bytes(_reqs[0], 0, idx, &_inShardBytes[idx]), "io size");
         _inputNames[idx] = in.first;
         _inputs[in.first] = allocatePinned(desc);
     }
     for (const auto& out : _networkOutputs) {
         const int idx = network->outputIndex(out.first);
         const TensorDesc& desc = out.second->getTensorDesc();
-        B200_CALL(b200_request_set_io_format(_req, 1, idx, BlobDtype(desc.getPrecision(), out.first), BlobLayout(desc, out.first)), "output format");
+        for (auto* r : _reqs) B200_CALL(b200_request_set_io_format(r, 1, idx, BlobDtype(desc.getPrecision(), out.first), BlobLayout(desc, out.first)), "output format");
+        B200_CALL(b200_request_io_bytes(_reqs[0], 1, idx, &_outShardBytes[idx]), "io size");
         _outputNames[idx] = out.first;
         _outputs[out.first] = allocatePinned(desc);
+        // outputs that are not plain dim-0 slices land in per-shard staging first
+        const IoPlan& plan = network->outputPlan(idx);
+        for (int g = 0; g < shards; ++g) {
+            if (plan.kind == IoPlan::Sliced || (plan.kind == IoPlan::Replicated && g == 0)) continue;
+            void* ptr = nullptr;
+            B200_CALL(b200_host_alloc(&ptr, std::max<size_t>(_outShardBytes[idx], 16)), "pinned staging");
+            _stageAllocs.push_back(ptr);
+            _outStage[idx][g] = ptr;
+        }
     }
 }
 
 InferRequest::~InferRequest() {
-    if (_req) b200_request_destroy(_req);   // drains the stream first
-    _inputs.clear();
-    _outputs.clear();
-    for (void* p : _pinned) b200_host_free(p);
+    for (auto* r : _reqs) b200_request_destroy(r);   // drains the stream first
+    for (void* p : _stageAllocs) b200_host_free(p);
+    for (const auto& kv : _registered) b200_host_unregister(const_cast<void*>(kv.first));
 }
 
 Blob::Ptr InferRequest::allocatePinned(const TensorDesc& desc) {
-    size_t elems = 1;
-    for (auto d : desc.getDims()) elems *= d;
-    void* ptr = nullptr;
-    B200_CALL(b200_host_alloc(&ptr, std::max<size_t>(elems * desc.getPrecision().size(), 16)), "pinned allocation");
-    _pinned.push_back(ptr);
-    return make_blob_with_precision(desc, ptr);
+    Blob::Ptr blob = make_blob_with_precision(desc, _allocator);
+    blob->allocate();
+    if (!blob->buffer().as<void*>()) IE_THROW(GeneralError) << "B200 plugin: pinned allocation failed: " << b200_last_error();
+    return blob;
+}
+
+// Memory the user brought through SetBlob is page-locked on first use (cudaHostRegister) so that its copies are asynchronous too;
+// a failure (already registered, foreign mapping) only costs the synchronous fallback of cudaMemcpyAsync.
+void InferRequest::pinUserMemory(const void* ptr, size_t bytes) {
+    if (!ptr || bytes < (64u << 10)) return;
+    auto it = _registered.find(ptr);
+    if (it != _registered.end() && it->second >= bytes) return;
+    if (it != _registered.end()) {
+        b200_host_unregister(const_cast<void*>(ptr));
+        _registered.erase(it);
+    }
+    if (_registered.size() >= 32) {   // a caller that cycles through many buffers: forget the oldest registrations
+        for (const auto& kv : _registered) b200_host_unregister(const_cast<void*>(kv.first));
+        _registered.clear();
+    }
+    if (b200_host_register(const_cast<void*>(ptr), bytes) == B200_OK) _registered[ptr] = bytes;
+}
+
+void InferRequest::SetBlob(const std::string& name, const Blob::Ptr& data) {
+    IInferRequestInternal::SetBlob(name, data);   // size / precision checks, pre-processing set-up (layout conversion of inputs on the host)
+    // outputs are written by the device in the layout the network was loaded with: a blob that asks for another one is refused
+    auto out = _networkOutputs.find(name);
+    if (out != _networkOutputs.end() && data && data->getTensorDesc().getDims().size() == 4 &&
+        data->getTensorDesc().getLayout() != out->second->getTensorDesc().getLayout())
+        IE_THROW(ParameterMismatch) << "B200 plugin: output blob '" << name << "' has layout " << data->getTensorDesc().getLayout()
+                                    << ", the network was loaded with " << out->second->getTensorDesc().getLayout();
 }
 
 void InferRequest::preprocessAndStart() {
     execDataPreprocessing(_inputs);     // resize / colour conversion requested through PreProcessInfo (host, reused from the reference)
-    std::vector<const void*> ins(_inputNames.size(), nullptr);
-    std::vector<void*> outs(_outputNames.size(), nullptr);
+    const int shards = static_cast<int>(_reqs.size());
+    std::vector<const uint8_t*> inBase(_inputNames.size(), nullptr);
+    std::vector<uint8_t*> outBase(_outputNames.size(), nullptr);
     for (size_t k = 0; k < _inputNames.size(); ++k) {
         const Blob::Ptr& blob = _inputs.at(_inputNames[k]);
-        uint64_t expect = 0;
-        B200_CALL(b200_request_io_bytes(_req, 0, static_cast<int>(k), &expect), "io size");
+        const uint64_t expect = _inShardBytes[k] * (_network->inputPlan(static_cast<int>(k)).kind == IoPlan::Sliced ? shards : 1);
         if (blob->byteSize() != expect)
             IE_THROW(ParameterMismatch) << "B200 plugin: input blob '" << _inputNames[k] << "' has " << blob->byteSize() << " bytes, the network expects " << expect;
-        ins[k] = BlobData(blob);
+        inBase[k] = static_cast<const uint8_t*>(BlobData(blob));
+        pinUserMemory(inBase[k], blob->byteSize());
     }
+    _mergeDst.assign(_outputNames.size(), nullptr);
     for (size_t k = 0; k < _outputNames.size(); ++k) {
         const Blob::Ptr& blob = _outputs.at(_outputNames[k]);
-        uint64_t expect = 0;
-        B200_CALL(b200_request_io_bytes(_req, 1, static_cast<int>(k), &expect), "io size");
+        const IoPlan& plan = _network->outputPlan(static_cast<int>(k));
+        const uint64_t expect = _outShardBytes[k] * (plan.kind == IoPlan::Replicated ? 1 : shards);
         if (blob->byteSize() != expect)
             IE_THROW(ParameterMismatch) << "B200 plugin: output blob '" << _outputNames[k] << "' has " << blob->byteSize() << " bytes, the network produces " << expect;
-        outs[k] = const_cast<void*>(BlobData(blob));
+        outBase[k] = const_cast<uint8_t*>(static_cast<const uint8_t*>(BlobData(blob)));
+        pinUserMemory(outBase[k], blob->byteSize());
+        _mergeDst[k] = outBase[k];
     }
-    B200_CALL(b200_request_start(_req, ins.data(), outs.data()), "start");
+    // scatter + launch on every device before anyone waits: the devices run concurrently
+    std::vector<const void*> ins(_inputNames.size(), nullptr);
+    std::vector<void*> outs(_outputNames.size(), nullptr);
+    for (int g = 0; g < shards; ++g) {
+        for (size_t k = 0; k < ins.size(); ++k)
+            ins[k] = inBase[k] + (_network->inputPlan(static_cast<int>(k)).kind == IoPlan::Sliced ? _inShardBytes[k] * g : 0);
+        for (size_t k = 0; k < outs.size(); ++k) {
+            const IoPlan& plan = _network->outputPlan(static_cast<int>(k));
+            if (plan.kind == IoPlan::Sliced) outs[k] = outBase[k] + _outShardBytes[k] * g;
+            else if (plan.kind == IoPlan::Replicated && g == 0) outs[k] = outBase[k];
+            else outs[k] = _outStage[k][g];
+        }
+        B200_CALL(b200_request_start(_reqs[g], ins.data(), outs.data()), "start");
+    }
 }
 
-void InferRequest::waitDevice() { B200_CALL(b200_request_wait(_req, -1), "wait"); }
+void InferRequest::waitDevice() {
+    int failed = 0;
+    for (auto* r : _reqs) {     // every device is drained even if one reports an error: the blobs must not be in use afterwards
+        const int rc = b200_request_wait(r, -1);
+        if (rc < 0 && !failed) failed = rc;
+    }
+    if (failed) ThrowFromStatus(failed, "wait");
+    const int shards = static_cast<int>(_reqs.size());
+    if (shards == 1) return;
+    // gather step of DetectionOutput: every shard produced [1,1,R,7] rows [image_id, label, conf, box] for ITS images, terminated by a
+    // row with image_id -1 (mkldnn_detection_output_node.cpp:505-536); the unsharded tensor has the valid rows of all shards in image
+    // order, ids renumbered, one terminator, zeros after it
+    for (size_t k = 0; k < _outputNames.size(); ++k) {
+        const IoPlan& plan = _network->outputPlan(static_cast<int>(k));
+        if (plan.kind != IoPlan::Detections || !_mergeDst[k]) continue;
+        const Blob::Ptr& blob = _outputs.at(_outputNames[k]);
+        if (blob->getTensorDesc().getPrecision() != Precision::FP32) IE_THROW(NotImplemented) << "B200 plugin: sharded DetectionOutput needs an FP32 output blob";
+        float* dst = reinterpret_cast<float*>(_mergeDst[k]);
+        const size_t rowsPerShard = static_cast<size_t>(_outShardBytes[k] / (7 * sizeof(float)));
+        const size_t total = rowsPerShard * shards;
+        size_t w = 0;
+        for (int g = 0; g < shards; ++g) {
+            const float* src = static_cast<const float*>(_outStage[k][g]);
+            for (size_t r = 0; r < rowsPerShard && src[r * 7] >= 0.f; ++r, ++w) {
+                std::memcpy(dst + w * 7, src + r * 7, 7 * sizeof(float));
+                dst[w * 7] += static_cast<float>(g * plan.images_per_shard);
+            }
+        }
+        if (w < total) {
+            std::memset(dst + w * 7, 0, (total - w) * 7 * sizeof(float));
+            dst[w * 7] = -1.f;
+        }
+    }
+}
 
 void InferRequest::InferImpl() {
     preprocessAndStart();
@@ -408,7 +737,7 @@ std::map<std::string, InferenceEngineProfileInfo> InferRequest::GetPerformanceCo
     if (!_network->config().perfCount) return perf;   // same as the reference: empty unless PERF_COUNT=YES
     const int n = b200_network_num_exec_nodes(_network->handle());
     std::vector<float> usec(static_cast<size_t>(std::max(n, 1)), 0.f);
-    B200_CALL(b200_request_perf_counts(_req, usec.data(), n), "perf counters");
+    B200_CALL(b200_request_perf_counts(_reqs[0], usec.data(), n), "perf counters");
     b200_exec_node_info info;
     for (int k = 0; k < n; ++k) {
         B200_CALL(b200_network_exec_node(_network->handle(), k, &info), "exec node info");
@@ -428,8 +757,11 @@ std::map<std::string, InferenceEngineProfileInfo> InferRequest::GetPerformanceCo
 AsyncInferRequest::AsyncInferRequest(const std::shared_ptr<InferRequest>& request, const ITaskExecutor::Ptr& taskExecutor,
                                      const ITaskExecutor::Ptr& waitExecutor, const ITaskExecutor::Ptr& callbackExecutor)
     : AsyncInferRequestThreadSafeDefault(request, taskExecutor, callbackExecutor), _request(request), _waitExecutor(waitExecutor) {
-    _pipeline = {{taskExecutor, [this] { _request->preprocessAndStart(); }},   // enqueue only, returns immediately
-                 {_waitExecutor, [this] { _request->waitDevice(); }}};         // D2H lands in the user's blobs: no third stage needed
+    // Cancel() (ie_infer_async_request_thread_safe_default.hpp:262-267) marks a busy request; the reference checks the mark between
+    // nodes (mkldnn_graph.cpp:814-816, mkldnn_infer_request.cpp:519-523).  Here a request is one CUDA graph: the mark is honoured before
+    // the enqueue, and after the device has drained (the buffers must not be in flight when Wait() reports INFER_CANCELLED).
+    _pipeline = {{taskExecutor, [this] { ThrowIfCanceled(); _request->preprocessAndStart(); }},   // enqueue only, returns immediately
+                 {_waitExecutor, [this] { _request->waitDevice(); ThrowIfCanceled(); }}};        // D2H lands in the user's blobs
 }
 
 AsyncInferRequest::~AsyncInferRequest() { StopAndWait(); }

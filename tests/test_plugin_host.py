@@ -91,3 +91,62 @@ def test_every_model_family_lowers_through_the_plugin(case, tmp_path):
     assert qq["supported_layers"] == qq["total_layers"], qq
     p = ie_run(xml, "--dry", "--config", "B200_DRY_COMPILE=YES,B200_INFERENCE_PRECISION=FP32")
     assert p.returncode == 0, p.stderr
+
+
+# ---- batch sharding / Export / Import: host logic that needs no device (dry compile) --------------------------------------------
+def test_sharded_load_divides_the_batch(tmp_path):
+    """B200_DEVICES=0,1: the replica is the same function at batch N/2 (ShardBatch re-validates the clone incl. the Reshape targets that
+    spell the batch out - the BERT head split); a malformed list and DEVICE_ID=ALL without devices are handled at LoadNetwork."""
+    f = zoo.bert_base(batch=4, seq=32, hidden=64, heads=2, layers=1, ffn=128, vocab=100, max_pos=64)
+    xml = str(tmp_path / "bert.xml")
+    ir.serialize(f, xml)
+    p = ie_run(xml, "--dry", "--config", "B200_DRY_COMPILE=YES", "--config-kv", "B200_DEVICES=0,1")
+    assert p.returncode == 0, p.stderr
+    assert json.loads(p.stdout)["network_name"] == "bert_base"
+    p = ie_run(xml, "--dry", "--config", "B200_DRY_COMPILE=YES", "--config-kv", "B200_DEVICES=0+1")
+    assert p.returncode != 0 and "bad device id" in p.stderr           # the separator is a comma
+    p = ie_run(xml, "--dry", "--config", "B200_DRY_COMPILE=YES,DEVICE_ID=ALL")   # no visible device: ALL resolves to one replica
+    assert p.returncode == 0, p.stderr
+
+
+def test_sharded_dry_compile_two_devices(tiny_resnet_xml):
+    p = ie_run(tiny_resnet_xml, "--dry", "--config", "B200_DRY_COMPILE=YES", "--config-kv", "B200_DEVICES=0,1")
+    assert p.returncode == 0, p.stderr
+    d = json.loads(p.stdout)
+    assert d["exec_convolutions"] == 15                      # same schedule, batch 1 per device
+    p = ie_run(tiny_resnet_xml, "--dry", "--config", "B200_DRY_COMPILE=YES", "--config-kv", "B200_DEVICES=0,1,2")
+    assert p.returncode != 0 and "does not divide" in p.stderr
+
+
+def test_export_import_round_trip(tiny_resnet_xml, tmp_path):
+    blob = str(tmp_path / "net.blob")
+    p = ie_run(tiny_resnet_xml, "--dry", "--export", blob, "--config", "B200_DRY_COMPILE=YES,B200_INFERENCE_PRECISION=FP16", "--input-precision", "data=U8")
+    assert p.returncode == 0, p.stderr
+    first = json.loads(p.stdout)
+    assert open(blob, "rb").read(8) == b"B200NET1"
+    p = ie_run(tiny_resnet_xml, "--dry", "--import", blob, "--config", "B200_DRY_COMPILE=YES")
+    assert p.returncode == 0, p.stderr
+    again = json.loads(p.stdout)
+    assert again == first
+    assert again["input_precisions"] == {"data": "U8"}       # user-side precision travels with the export
+    assert again["config_precision"] == "FP16"               # and so does the arithmetic the network was compiled for
+    # a foreign stream is refused with NetworkNotRead
+    bad = str(tmp_path / "bad.blob")
+    open(bad, "wb").write(b"not a network")
+    p = ie_run(tiny_resnet_xml, "--dry", "--import", bad, "--config", "B200_DRY_COMPILE=YES")
+    assert p.returncode != 0 and "not an exported B200 network" in p.stderr
+
+
+def test_core_cache_dir_drives_export_and_import(tiny_resnet_xml, tmp_path):
+    """IMPORT_EXPORT_SUPPORT is advertised, so Core::LoadNetwork with CACHE_DIR exports on the first load and imports on the second
+    (inference-engine/src/inference_engine/ie_core.cpp:265-340)."""
+    cache = tmp_path / "cache"
+    cache.mkdir()
+    p = ie_run(tiny_resnet_xml, "--dry", "--cache-dir", str(cache), "--config", "B200_DRY_COMPILE=YES")
+    assert p.returncode == 0, p.stderr
+    blobs = list(cache.iterdir())
+    assert len(blobs) == 1 and blobs[0].stat().st_size > 100000
+    stamp = blobs[0].stat().st_mtime_ns
+    p = ie_run(tiny_resnet_xml, "--dry", "--cache-dir", str(cache), "--config", "B200_DRY_COMPILE=YES")
+    assert p.returncode == 0, p.stderr
+    assert [b.stat().st_mtime_ns for b in cache.iterdir()] == [stamp]      # second load read the entry, did not rewrite it

@@ -4,6 +4,7 @@
 // and by the GPU parity tests that drive the B200 plugin through the unmodified Core API
 // (Core::ReadNetwork / LoadNetwork / CreateInferRequest / StartAsync / Wait).
 #include <inference_engine.hpp>
+#include <blob_factory.hpp>
 #include <ngraph/function.hpp>
 #include <ngraph/variant.hpp>
 
@@ -28,8 +29,9 @@ static std::vector<std::string> split(const std::string& s, char d) {
 int main(int argc, char** argv) {
   std::string model, device = "CPU", outdir = ".", plugins_xml;
   std::map<std::string, std::string> config, inputs, in_prec;
+  std::string export_path, import_path, cache_dir;
   int niter = 1;
-  bool query = false, dry = false;
+  bool query = false, dry = false, user_blobs = false, cancel = false, callback = false;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
     auto next = [&]() { return std::string(i + 1 < argc ? argv[++i] : ""); };
@@ -40,17 +42,28 @@ int main(int argc, char** argv) {
     else if (a == "--niter") niter = std::stoi(next());
     else if (a == "--query") query = true;     // print QueryNetwork coverage + plugin metrics as JSON, no inference
     else if (a == "--dry") dry = true;         // LoadNetwork + executable-network metrics + exec graph, no inference
+    else if (a == "--export") export_path = next();   // ExecutableNetwork::Export(file) after LoadNetwork
+    else if (a == "--import") import_path = next();   // Core::ImportNetwork(file, device, config) instead of ReadNetwork + LoadNetwork
+    else if (a == "--cache-dir") cache_dir = next();  // Core::SetConfig({CACHE_DIR}): the Core drives Export / ImportNetwork itself
+    else if (a == "--user-blobs") user_blobs = true;  // inputs and outputs in caller-owned (pageable) memory through SetBlob
+    else if (a == "--cancel") cancel = true;          // StartAsync, Cancel, Wait: the status is written to the manifest
+    else if (a == "--callback") callback = true;      // SetCompletionCallback: the number of calls is written to the manifest
     else if (a == "--config") { for (auto& kv : split(next(), ',')) { auto p = kv.find('='); if (p != std::string::npos) config[kv.substr(0, p)] = kv.substr(p + 1); } }
+    else if (a == "--config-kv") { auto kv = next(); auto p = kv.find('='); if (p != std::string::npos) config[kv.substr(0, p)] = kv.substr(p + 1); }  // one key whose value has commas
     else if (a == "--input") { auto kv = next(); auto p = kv.find('='); inputs[kv.substr(0, p)] = kv.substr(p + 1); }
     else if (a == "--input-precision") { auto kv = next(); auto p = kv.find('='); in_prec[kv.substr(0, p)] = kv.substr(p + 1); }
     else { std::cerr << "unknown argument " << a << "\n"; return 2; }
   }
   try {
     Core core(plugins_xml);
-    CNNNetwork net = core.ReadNetwork(model);
-    for (auto& in : net.getInputsInfo()) {
-      auto it = in_prec.find(in.first);
-      if (it != in_prec.end()) in.second->setPrecision(Precision::FromStr(it->second));
+    if (!cache_dir.empty()) core.SetConfig({{CONFIG_KEY(CACHE_DIR), cache_dir}});
+    CNNNetwork net;
+    if (import_path.empty()) {
+      net = core.ReadNetwork(model);
+      for (auto& in : net.getInputsInfo()) {
+        auto it = in_prec.find(in.first);
+        if (it != in_prec.end()) in.second->setPrecision(Precision::FromStr(it->second));
+      }
     }
     if (query) {
       QueryNetworkResult q = core.QueryNetwork(net, device, config);
@@ -67,7 +80,8 @@ int main(int argc, char** argv) {
       return 0;
     }
     auto t0 = std::chrono::steady_clock::now();
-    ExecutableNetwork exe = core.LoadNetwork(net, device, config);
+    ExecutableNetwork exe = import_path.empty() ? core.LoadNetwork(net, device, config) : core.ImportNetwork(import_path, device, config);
+    if (!export_path.empty()) exe.Export(export_path);
     if (dry) {
       unsigned nireq = exe.GetMetric(EXEC_NETWORK_METRIC_KEY(OPTIMAL_NUMBER_OF_INFER_REQUESTS)).as<unsigned>();
       std::string name = exe.GetMetric(EXEC_NETWORK_METRIC_KEY(NETWORK_NAME)).as<std::string>();
@@ -81,12 +95,39 @@ int main(int argc, char** argv) {
         if (v && v->get() == "Convolution") ++convs;
       }
       std::cout << "{\"network_name\": \"" << name << "\", \"optimal_requests\": " << nireq << ", \"exec_nodes\": " << exec_nodes
-                << ", \"exec_convolutions\": " << convs << "}" << std::endl;
+                << ", \"exec_convolutions\": " << convs << ", \"input_precisions\": {";
+      bool first_in = true;
+      for (auto& in : exe.GetInputsInfo()) {
+        std::cout << (first_in ? "" : ", ") << "\"" << in.first << "\": \"" << in.second->getPrecision().name() << "\"";
+        first_in = false;
+      }
+      std::string prec;
+      try { prec = exe.GetConfig("B200_INFERENCE_PRECISION").as<std::string>(); } catch (...) {}
+      std::cout << "}, \"config_precision\": \"" << prec << "\"}" << std::endl;
       return 0;
     }
     auto t1 = std::chrono::steady_clock::now();
     InferRequest req = exe.CreateInferRequest();
-    for (auto& in : net.getInputsInfo()) {
+    std::vector<std::vector<char>> user_mem;   // caller-owned, pageable
+    if (user_blobs) {
+      for (auto& in : exe.GetInputsInfo()) {
+        const TensorDesc& d = in.second->getTensorDesc();
+        size_t n = d.getPrecision().size();
+        for (auto v : d.getDims()) n *= v;
+        user_mem.emplace_back(n);
+        req.SetBlob(in.first, make_blob_with_precision(d, user_mem.back().data()));
+      }
+      for (auto& out : exe.GetOutputsInfo()) {
+        const TensorDesc& d = out.second->getTensorDesc();
+        size_t n = d.getPrecision().size();
+        for (auto v : d.getDims()) n *= v;
+        user_mem.emplace_back(n);
+        req.SetBlob(out.first, make_blob_with_precision(d, user_mem.back().data()));
+      }
+    }
+    int callbacks = 0;
+    if (callback) req.SetCompletionCallback([&callbacks] { ++callbacks; });
+    for (auto& in : exe.GetInputsInfo()) {
       Blob::Ptr b = req.GetBlob(in.first);
       auto mb = as<MemoryBlob>(b);
       auto h = mb->wmap();
@@ -98,18 +139,26 @@ int main(int argc, char** argv) {
       if ((size_t)f.gcount() != b->byteSize()) { std::cerr << "input " << in.first << ": expected " << b->byteSize() << " bytes, got " << f.gcount() << "\n"; return 2; }
     }
     std::vector<double> ms;
+    int cancel_status = -100;
     for (int it = 0; it < niter; ++it) {
       auto a0 = std::chrono::steady_clock::now();
       req.StartAsync();
+      if (cancel && it == 0) {
+        req.Cancel();
+        StatusCode st = OK;
+        try { st = req.Wait(InferRequest::WaitMode::RESULT_READY); } catch (const InferCancelled&) { st = INFER_CANCELLED; }
+        cancel_status = (int)st;
+        req.StartAsync();     // a cancelled request must be reusable
+      }
       req.Wait(InferRequest::WaitMode::RESULT_READY);
       ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a0).count());
     }
     std::ofstream man(outdir + "/manifest.json");
     man << "{\"device\": \"" << device << "\", \"load_ms\": " << std::chrono::duration<double, std::milli>(t1 - t0).count() << ", \"infer_ms\": [";
     for (size_t k = 0; k < ms.size(); ++k) man << (k ? ", " : "") << ms[k];
-    man << "], \"outputs\": {";
+    man << "], \"callbacks\": " << callbacks << ", \"cancel_status\": " << cancel_status << ", \"outputs\": {";
     bool first = true;
-    for (auto& out : net.getOutputsInfo()) {
+    for (auto& out : exe.GetOutputsInfo()) {
       Blob::Ptr b = req.GetBlob(out.first);
       auto mb = as<MemoryBlob>(b);
       auto h = mb->rmap();
