@@ -14,12 +14,17 @@ max-over-ranks reduction of the timings.
 Numbers on the JSON line:
   value      images/s with the U8 input already resident in HBM: K CUDA-graph replays (ingest ->
              53 conv + pool + FC kernels -> egress) timed with CUDA events on the request's stream.
-  e2e        images/s through the public API (InferRequest.start_async / wait) with three requests in
-             flight: every step copies the U8 NCHW batch from pinned host memory to the device and
-             reads the fp32 [B,1000] scores back (wall clock between synchronisations).
-  roofline   the tcgen05 implicit-GEMM kernel (all Convolution/FullyConnected launches of one step):
-             algorithmic FLOPs / sum of their CUDA-event durations, against the measured bf16 peak.
-  cpu_baseline  the reference CPU plugin on this box's host cores, bounded sample (rank 0, N = 1).
+  e2e        images/s through the DROP-IN boundary: the UNMODIFIED reference benchmark_app (oracle/_ref/bin/benchmark_app,
+             samples/benchmark_app/main.cpp:457-629) loads plugin/lib/libb200Plugin.so through InferenceEngine::Core and runs
+             `-d B200 -b 256 -api async`: every request copies the U8 NCHW batch from pinned host memory to the device and
+             reads the fp32 [B,1000] scores back.  N > 1: rank 0 runs ONE benchmark_app process over `-d MULTI:B200.0,..,B200.N-1`
+             (the reference's own scheduler: whole requests to idle devices) while the other ranks idle.
+             `e2e_python_mirror` keeps the same measurement through the Python ctypes mirror (diagnostic).
+  strong     the batch-sharding scheduler of the plugin: ONE process, `-d B200.ALL`-style device set of N GPUs, global batch 256
+             split into N contiguous slices per request ("scaling": "strong"), measured by the same benchmark_app.
+  roofline   the tcgen05 implicit-GEMM kernel (all Convolution/FullyConnected launches of one step): algorithmic FLOPs /
+             (their share of the step x ms_per_step of the timed CUDA-graph replay), against the measured bf16 peak.
+  cpu_baseline  the reference CPU plugin on this box's host cores through the same benchmark_app, bounded sample (rank 0, N = 1).
 """
 import argparse
 import json
@@ -129,45 +134,65 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
-IE_RUN = os.path.join(REF_DIR, "bin", "ie_run")
+BENCHMARK_APP = os.path.join(REF_DIR, "bin", "benchmark_app")
+PLUGIN_SO = os.path.join(ROOT, "plugin", "lib", "libb200Plugin.so")
 
 
-def reference_cpu_run(batch, warmup, steps, bf16=True):
-    """Times the UNMODIFIED reference CPU plugin (oracle/_ref: libinference_engine + libMKLDNNPlugin built
-    by oracle/build_ref.sh) on ResNet-50 through Core::LoadNetwork(net,"CPU") + StartAsync/Wait
-    (tools/ie_run.cpp).  Returns dict(value img/s, ms_per_step, cores, kind, sample)."""
-    import numpy as np
+def write_ir(batch, tmp):
+    """ResNet-50 IR v10 at `batch`, written by a HELPER process: the process that times the reference arm never imports dldt_b200
+    (and so never maps libb200kernels.so)."""
+    xml = os.path.join(tmp, "resnet50_b%d.xml" % batch)
+    code = "import sys; sys.path.insert(0, %r); from dldt_b200 import ir, zoo; ir.serialize(zoo.resnet50(batch=%d), %r)" % (ROOT, batch, xml)
+    subprocess.run([sys.executable, "-c", code], check=True, stdout=subprocess.DEVNULL, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    return xml
+
+
+def benchmark_app(xml, device, seconds, extra=(), api="async", threads=None, visible=None):
+    """Runs the reference's own benchmark_app and parses its report.  Returns dict(fps, latency_ms, nireq, out)."""
+    import re
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.path.join(REF_DIR, "lib") + ":" + env.get("LD_LIBRARY_PATH", "")
+    if visible is not None:
+        env["CUDA_VISIBLE_DEVICES"] = visible
+    if threads:
+        env["OMP_NUM_THREADS"] = str(threads)      # torchrun exports OMP_NUM_THREADS=1 to its children
+    else:
+        env.pop("OMP_NUM_THREADS", None)
+    cmd = [BENCHMARK_APP, "-m", xml, "-d", device, "-api", api, "-t", str(seconds)] + list(extra)
+    p = subprocess.run(cmd, env=env, capture_output=True, text=True, cwd=os.path.join(REF_DIR, "lib"), timeout=900)
+    if p.returncode != 0:
+        raise RuntimeError("benchmark_app failed (%d): %s" % (p.returncode, (p.stdout[-800:] + p.stderr[-800:]).strip()))
+    fps = re.search(r"Throughput:\s+([0-9.]+)\s+FPS", p.stdout)
+    lat = re.search(r"Latency:\s+([0-9.]+)\s+ms", p.stdout)
+    nireq = re.search(r"(\d+) inference requests", p.stdout)
+    cnt = re.search(r"Count:\s+(\d+) iterations", p.stdout)
+    return {"fps": float(fps.group(1)) if fps else None, "latency_ms": float(lat.group(1)) if lat else None,
+            "nireq": int(nireq.group(1)) if nireq else None, "iterations": int(cnt.group(1)) if cnt else None, "out": p.stdout}
+
+
+def reference_cpu_run(batch, seconds, tmp=None):
+    """Times the UNMODIFIED reference CPU plugin (oracle/_ref: libinference_engine + libMKLDNNPlugin built by oracle/build_ref.sh) with the
+    reference's own benchmark_app: `-d CPU -api async` (automatic streams and request count, all host cores, bf16 where the host has
+    avx512_bf16 - the CPU plugin's default), U8 image input, on ResNet-50 at `batch`; plus BASELINE.json config 1: batch 1 fp32 sync
+    latency.  Returns dict(value img/s, ms_per_step, cores, kind, sample, latency_b1_fp32_ms)."""
     cores = os.cpu_count() or 1
-    if os.path.exists(IE_RUN) and os.path.exists(os.path.join(REF_DIR, "lib", "libMKLDNNPlugin.so")):
-        from dldt_b200 import ir, zoo
-        f = zoo.resnet50(batch=batch)
-        tmp = tempfile.mkdtemp(prefix="b200_bench_ref_")
-        xml = os.path.join(tmp, "resnet50.xml")
-        ir.serialize(f, xml)
-        x = np.random.default_rng(0).integers(0, 256, (batch, 3, 224, 224), dtype=np.uint8)
-        xin = os.path.join(tmp, "data.bin")
-        x.tofile(xin)
-        env = dict(os.environ)
-        env["LD_LIBRARY_PATH"] = os.path.join(REF_DIR, "lib") + ":" + env.get("LD_LIBRARY_PATH", "")
-        # all host threads (torchrun exports OMP_NUM_THREADS=1 to its children; only rank 0 runs this leg)
-        env["OMP_NUM_THREADS"] = str(cores)
-        cmd = [IE_RUN, "--model", xml, "--device", "CPU", "--output-dir", tmp, "--niter", str(warmup + steps),
-               "--plugins", os.path.join(REF_DIR, "lib", "plugins.xml"), "--input", "data=" + xin, "--input-precision", "data=U8",
-               "--config", "ENFORCE_BF16=%s" % ("YES" if bf16 else "NO")]
-        p = subprocess.run(cmd, env=env, capture_output=True, text=True)
-        if p.returncode != 0 and bf16:   # host without avx512_bf16: the CPU plugin rejects ENFORCE_BF16=YES
-            cmd[-1] = "ENFORCE_BF16=NO"
-            bf16 = False
-            p = subprocess.run(cmd, env=env, capture_output=True, text=True)
-        if p.returncode != 0:
-            raise RuntimeError("reference run failed: " + p.stderr[-1500:])
-        man = json.load(open(os.path.join(tmp, "manifest.json")))
-        ms = man["infer_ms"][warmup:]
-        per = sum(ms) / len(ms)
-        return {"value": batch * 1e3 / per, "unit": UNIT, "cores": cores, "kind": "reference", "ms_per_step": per,
-                "sample": "reference MKLDNNPlugin (oracle/_ref), ResNet-50 v1.5 %s, U8 input, %d sync requests of batch %d after %d warm-up, "
-                          "1 stream x %d OMP threads" % ("bf16 (ENFORCE_BF16=YES)" if bf16 else "fp32", len(ms), batch, warmup, cores)}
+    if os.path.exists(BENCHMARK_APP) and os.path.exists(os.path.join(REF_DIR, "lib", "libMKLDNNPlugin.so")):
+        tmp = tmp or tempfile.mkdtemp(prefix="b200_bench_ref_")
+        r = benchmark_app(write_ir(batch, tmp), "CPU", seconds)
+        bf16 = "avx512_bf16" in open("/proc/cpuinfo").read()
+        lat1 = None
+        try:
+            l1 = benchmark_app(write_ir(1, tmp), "CPU", 4, extra=["-enforcebf16=false"], api="sync")
+            lat1 = l1["latency_ms"]
+        except Exception:
+            pass
+        per = batch * 1e3 / r["fps"]
+        return {"value": r["fps"], "unit": UNIT, "cores": cores, "kind": "reference", "ms_per_step": per, "latency_b1_fp32_ms": lat1,
+                "sample": "reference benchmark_app -d CPU -api async -b %d -t %d (MKLDNNPlugin from oracle/_ref, ResNet-50 v1.5 %s, U8 input, %s requests, "
+                          "automatic streams, %d host threads, %s iterations)" % (batch, seconds, "bf16 (plugin default on avx512_bf16)" if bf16 else "fp32",
+                                                                                 r["nireq"], cores, r["iterations"])}
     # the reference build did not travel: time the numpy restatement instead (single process, numpy's BLAS threads)
+    import numpy as np
     from dldt_b200 import zoo
     from oracle import interp
     b = min(batch, 4)
@@ -175,24 +200,27 @@ def reference_cpu_run(batch, warmup, steps, bf16=True):
     x = np.random.default_rng(0).uniform(0, 255, (b, 3, 224, 224)).astype(np.float32)
     interp.run(f, {"data": x})
     t0 = time.perf_counter()
-    n = max(1, min(steps, 3))
+    n = 2
     for _ in range(n):
         interp.run(f, {"data": x})
     per = (time.perf_counter() - t0) / n * 1e3
-    return {"value": b * 1e3 / per, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": per,
+    return {"value": b * 1e3 / per, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": per, "latency_b1_fp32_ms": None,
             "sample": "numpy oracle port (oracle/interp.py), ResNet-50 v1.5 fp32, %d passes of batch %d" % (n, b)}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    cb = reference_cpu_run(args.ref_batch, args.warmup, args.steps)
+    # steps/warmup scale the bounded sample: about 1 s of CPU time per requested step, clamped to [10, 60] s
+    seconds = int(min(60, max(10, args.steps)))
+    cb = reference_cpu_run(args.ref_batch, seconds)
     line = {"impl": "reference", "metric": METRIC, "value": round(cb["value"], 2), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(cb["ms_per_step"], 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if "bf16" in cb["sample"] else "f32", "data": "synthetic",
-            "config": {"workload": "ResNet-50 v1.5 224x224 random-init, U8 NCHW input, CPU plugin, batch %d per step (bounded sample of the b256 workload; "
-                                   "throughput is per image)" % args.ref_batch},
+            "config": {"workload": "ResNet-50 v1.5 224x224 random-init, U8 NCHW input, reference CPU plugin through benchmark_app -api async, batch %d per "
+                                   "request (bounded sample: %d s)" % (args.ref_batch, seconds)},
             "cpu_baseline": {"value": round(cb["value"], 2), "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]},
+            "latency_b1_fp32_ms": cb["latency_b1_fp32_ms"],
             "e2e": {"value": round(cb["value"], 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -282,9 +310,39 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.synchronize(local_rank)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    e2e_value = world * B * args.steps / e2e_s
+    e2e_mirror = world * B * args.steps / e2e_s
     h2d = int(sum(b.nbytes for b in req.input_blobs.values()))
     d2h = int(sum(b.nbytes for b in req.output_blobs.values()))
+
+    # ---- e2e through the drop-in boundary: the reference's own benchmark_app over libb200Plugin.so (rank 0; the other ranks idle) ----
+    e2e_app, strong = None, None
+    have_app = os.path.exists(BENCHMARK_APP) and os.path.exists(PLUGIN_SO)
+    barrier()
+    if rank == 0 and have_app and not args.no_benchmark_app:
+        tmp = tempfile.mkdtemp(prefix="b200_bench_")
+        xml = write_ir(B, tmp)
+        try:
+            dev = "B200.%d" % local_rank if world == 1 else "MULTI:" + ",".join("B200.%d" % k for k in range(world))
+            r = benchmark_app(xml, dev, args.app_seconds)
+            e2e_app = {"value": r["fps"], "latency_ms": r["latency_ms"], "nireq": r["nireq"], "iterations": r["iterations"],
+                       "how": "oracle/_ref/bin/benchmark_app -m resnet50.xml -d %s -b %d -api async -t %d (unmodified reference app + Core + "
+                              "plugin/lib/libb200Plugin.so)" % (dev, B, args.app_seconds)}
+        except Exception as e:
+            e2e_app = {"value": None, "error": str(e)[:300]}
+        try:
+            # batch sharding inside the plugin: one process, global batch B split over the N GPUs of this run
+            # (-d B200.ALL = DEVICE_ID=ALL = every visible GPU; the set is narrowed to this run's N GPUs through CUDA_VISIBLE_DEVICES)
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            ids = [v for v in vis.split(",") if v][:world] if vis else [str(k) for k in range(world)]
+            r = benchmark_app(xml, "B200.ALL", args.app_seconds, visible=",".join(ids))
+            strong = {"value": r["fps"], "unit": UNIT, "scaling": "strong", "global_batch": B, "n_gpus": world, "latency_ms": r["latency_ms"],
+                      "nireq": r["nireq"], "iterations": r["iterations"],
+                      "how": "benchmark_app -d B200.ALL (%d visible GPUs) -b %d -api async -t %d: every request of batch %d is scattered as %d contiguous "
+                             "slices of %d images, one CUDA graph per GPU, gathered on completion" % (world, B, args.app_seconds, B, world, B // world)}
+        except Exception as e:
+            strong = {"value": None, "scaling": "strong", "error": str(e)[:300]}
+    barrier()
+    e2e_value = e2e_app["value"] if (e2e_app and e2e_app.get("value")) else e2e_mirror
 
     # ---- roofline of the dominant kernel class (tcgen05 implicit GEMM), CUDA events per launch ----
     eg = net.get_exec_graph_info()
@@ -299,13 +357,20 @@ def run_b200(args, rank, local_rank, world):
                 tc_us += us
                 tc_flops += e["flops"]
     n_tc = sum(1 for e in eg if e["impl"].startswith("tcgen05"))
-    achieved = tc_flops / (tc_us * 1e-6) / 1e12 if tc_us > 0 else 0.0
+    # per-kernel times come from an eager, event-bracketed pass (no overlap between kernels); the timed region replays the captured
+    # CUDA graph (programmatic dependent launch overlaps prologues).  The tcgen05 launches' duration inside the timed step is therefore
+    # taken as their SHARE of the eager pass x ms_per_step, so that the figure follows from the line's own ms_per_step.
+    tc_share = tc_us / all_us if all_us else 0.0
+    tc_ms_in_step = tc_share * ms_step
+    achieved = (tc_flops / passes) / (tc_ms_in_step * 1e-3) / 1e12 if tc_ms_in_step > 0 else 0.0
+    achieved_eager = tc_flops / (tc_us * 1e-6) / 1e12 if tc_us > 0 else 0.0
     peak = pk["bf16_tflops_sustained"]
     # traffic: DRAM read+write bytes per tcgen05 launch from the committed ncu pass over one step (profiles/r1_traffic.json, written
     # from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` by tools/summarise_ncu.py; never measured under this run)
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+        tj = json.load(open(tpath if os.path.exists(tpath) else os.path.join(ROOT, "profiles", "r1_traffic.json")))
         traffic = {"dram_bytes_per_launch": tj["dram_bytes_per_launch"], "algorithmic_bytes_per_launch": tj.get("algorithmic_bytes_per_launch"),
                    "source": tj.get("source")}
     except Exception:
@@ -314,7 +379,8 @@ def run_b200(args, rank, local_rank, world):
                                                "launches of a step" % n_tc,
                 "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                 "peak_source": "%s bf16 sustained" % pk["source"], "traffic": traffic,
-                "share_of_step": round(tc_us / all_us, 4) if all_us else None,
+                "share_of_step": round(tc_share, 4), "achieved_eager_event_sum": round(achieved_eager, 2),
+                "how": "sum of algorithmic FLOPs of the tcgen05 launches / (their share of an eager event-bracketed pass x ms_per_step of the timed graph replay)",
                 "step_achieved": round(value / world * GFLOP_PER_IMG / 1e3, 2), "step_frac": round(value / world * GFLOP_PER_IMG / 1e3 / peak, 4)}
 
     # ---- batch-1 p50 latency (second half of BASELINE.json's metric): sync requests through the public API ----
@@ -345,12 +411,18 @@ def run_b200(args, rank, local_rank, world):
                        "l2": "no explicit flush: one step streams a %.0f MB activation arena (> 126 MB L2)" % (net.stat("arena_bytes") / 1e6),
                        "gflop_per_img": round(flops_per_step / B / 1e9, 4)},
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "requests_in_flight": nreq},
+                    "through": "reference benchmark_app + InferenceEngine::Core + libb200Plugin.so" if (e2e_app and e2e_app.get("value")) else
+                               "python ctypes mirror (benchmark_app or the plugin did not travel)",
+                    "benchmark_app": e2e_app},
+            "e2e_python_mirror": {"value": round(e2e_mirror, 1), "unit": UNIT, "requests_in_flight": nreq,
+                                  "how": "dldt_b200.InferRequest.start_async/wait, one process per GPU, same C ABI underneath"},
+            "strong": strong,
             "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "clocks": clocks, "burst_ms_per_step": bursts, "latency_b1": lat}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            cb = reference_cpu_run(args.ref_batch, 1, args.ref_steps)
-            line["cpu_baseline"] = {"value": round(cb["value"], 2), "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
+            cb = reference_cpu_run(args.ref_batch, args.ref_seconds)
+            line["cpu_baseline"] = {"value": round(cb["value"], 2), "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"],
+                                    "latency_b1_fp32_ms": cb["latency_b1_fp32_ms"]}
         except Exception as e:  # the baseline is a reported number, never a reason to lose the GPU line
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % str(e)[:200]}
     if dist is not None:
@@ -367,8 +439,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (the metric is quoted on 256)")
-    ap.add_argument("--ref-batch", type=int, default=32, help="batch of the CPU reference sample")
-    ap.add_argument("--ref-steps", type=int, default=8, help="timed CPU requests of the cpu_baseline leg")
+    ap.add_argument("--ref-batch", type=int, default=256, help="batch of the CPU reference requests (the workload's own)")
+    ap.add_argument("--ref-seconds", type=int, default=12, help="duration of the cpu_baseline leg (benchmark_app -t)")
+    ap.add_argument("--app-seconds", type=int, default=5, help="duration of each benchmark_app leg on the B200 plugin")
+    ap.add_argument("--no-benchmark-app", action="store_true", help="skip the benchmark_app legs (e2e falls back to the Python mirror)")
     ap.add_argument("--inflight", type=int, default=3, help="infer requests in flight in the e2e leg (measured on B200: 2 -> 74.4k, 3 -> 76.6k, 4 -> 76.6k img/s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the batch-1 latency leg")
