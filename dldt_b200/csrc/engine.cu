@@ -294,10 +294,26 @@ int b200_host_free(void* ptr) {
   return guarded([&] { if (ptr) B200_CUDA(cudaFreeHost(ptr)); return B200_OK; });
 }
 int b200_host_register(void* ptr, size_t bytes) {
-  return guarded([&] { B200_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable)); return B200_OK; });
+  return guarded([&] {
+    B200_CHECK(ptr && bytes, B200_ERR_INVALID, "null argument");
+    // memory that is already page-locked (b200_host_alloc, or registered by somebody else) is left alone
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, ptr) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered) return (int)B200_ALREADY_PINNED;
+    cudaGetLastError();
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+      cudaGetLastError();   // not sticky: must not surface later as a "kernel launch failed"
+      B200_THROW(B200_ERR_CUDA, "cudaHostRegister(" << bytes << " bytes) failed: " << cudaGetErrorString(e));
+    }
+    return (int)B200_OK;
+  });
 }
 int b200_host_unregister(void* ptr) {
-  return guarded([&] { B200_CUDA(cudaHostUnregister(ptr)); return B200_OK; });
+  return guarded([&] {
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); B200_THROW(B200_ERR_CUDA, "cudaHostUnregister failed: " << cudaGetErrorString(e)); }
+    return (int)B200_OK;
+  });
 }
 
 int b200_compile(const b200_graph* g, const b200_compile_options* opts, b200_network** out) {

@@ -58,7 +58,8 @@ typedef enum b200_status {
   B200_ERR_NO_DEVICE = -4,    /* no sm_100 device / bad DEVICE_ID         -> IE NotFound               */
   B200_ERR_BUSY = -5,         /* request already running                  -> IE RequestBusy            */
   B200_ERR_OOM = -6,
-  B200_NOT_READY = 1          /* wait() timed out                          -> IE RESULT_NOT_READY       */
+  B200_NOT_READY = 1,         /* wait() timed out                          -> IE RESULT_NOT_READY       */
+  B200_ALREADY_PINNED = 2     /* host_register(): the memory is page-locked already, nothing to undo        */
 } b200_status;
 
 typedef enum b200_dtype {
@@ -171,6 +172,7 @@ B200_API int b200_device_props(int device, int* sm_count, int* cc_major, int* cc
 /* ---- pinned host memory ----------------------------------------------------------------- */
 B200_API int b200_host_alloc(void** ptr, size_t bytes);
 B200_API int b200_host_free(void* ptr);
+/* Page-locks caller-owned memory (B200_OK: undo with b200_host_unregister; B200_ALREADY_PINNED: nothing was done). */
 B200_API int b200_host_register(void* ptr, size_t bytes);
 B200_API int b200_host_unregister(void* ptr);
 

@@ -1,6 +1,6 @@
 """The CUDA path (through the C ABI) against the committed reference outputs (tests/golden/ref_cases.npz, produced
 by the unmodified reference CPU plugin).  fp32 mode: rel-L2 <= 1e-4 and bit-exact indices (north star); bf16: <= 1e-2
-(3e-2 on the deep tiny nets, whose random-init logits are small differences of large sums)."""
+(one documented exception: LOWP_TOL)."""
 import json
 import os
 
@@ -16,7 +16,10 @@ pytestmark = pytest.mark.gpu
 # integer-valued inputs: exact in bf16/fp16 too, so the index outputs must still match
 LOWP_SKIP = {"nms_corner_sorted", "nms_center_unsorted", "nms_score_ties", "nms_keep_nothing", "detout_ssd_like", "detout_corner_clip",
              "detout_not_shared", "detout_var_in_target", "net_tiny_ssd", "topk_imagenet_top5"}
-LOWP_TOL = {"softmax_last": 3e-2, "softmax_mid": 3e-2, "softmax_ssd": 3e-2, "net_tiny_resnet": 3e-2, "net_tiny_mobilenet": 3e-2, "net_tiny_bert": 3e-2, "unary_activations": 2e-2, "binary_broadcast": 2e-2}
+# The north star's 1e-2 holds on every case but one.  softmax_last feeds +-10 logits: rounding them to bf16 (2^-9 relative) moves exp() by
+# up to 4 %; the reference's OWN bf16 mode loses 1.62e-2 on this case (tests/golden/ref_bf16_calibration.json), this path 1.60e-2
+# (profiles/r2_lowp_errors.jsonl), fp16 1.7e-3.
+LOWP_TOL = {("softmax_last", "BF16"): 2e-2}
 
 
 @pytest.mark.parametrize("case", sorted(golden_cases.CASES))

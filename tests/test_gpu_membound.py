@@ -19,7 +19,7 @@ def run(f, inputs, prec):
     return ref, got, net.get_exec_graph_info()
 
 
-@pytest.mark.parametrize("prec,tol", [("FP32", 1e-5), ("BF16", 1.5e-2)])
+@pytest.mark.parametrize("prec,tol", [("FP32", 1e-5), ("BF16", 1e-2)])
 @pytest.mark.parametrize("seq,mask_batch,heads", [(384, True, 3), (128, False, 3), (40, True, 3), (384, True, 12), (200, False, 24)])
 def test_attention_softmax_is_one_kernel(prec, tol, seq, mask_batch, heads):
     # heads = 12 / 24: >= 8192 rows, where 16-bit rows go four to a warp (softmax_warp_multirow_kernel)
@@ -39,7 +39,7 @@ def test_attention_softmax_is_one_kernel(prec, tol, seq, mask_batch, heads):
     assert np.allclose(a.sum(-1), 1.0, atol=2e-2 if prec == "BF16" else 1e-5)
 
 
-@pytest.mark.parametrize("prec,tol", [("FP32", 1e-5), ("BF16", 1.5e-2)])
+@pytest.mark.parametrize("prec,tol", [("FP32", 1e-5), ("BF16", 1e-2)])
 def test_plain_softmax_and_layernorm_rows(prec, tol):
     rng = np.random.default_rng(11)
     f = Function("ln")
@@ -112,7 +112,7 @@ def test_swap_of_the_last_two_dims(shape):
     assert a.shape == b.shape and rel_l2(a, b) < 5e-3
 
 
-@pytest.mark.parametrize("prec,tol", [("BF16", 1.5e-2), ("FP16", 4e-3)])
+@pytest.mark.parametrize("prec,tol", [("BF16", 1e-2), ("FP16", 4e-3)])
 @pytest.mark.parametrize("seq,dh", [(128, 64), (384, 64), (256, 128)])
 def test_attention_matmuls_run_as_one_grouped_launch(prec, tol, seq, dh, monkeypatch):
     """scores = Q K^T and context = P V with tile-aligned sequence lengths: every (batch, head) pair is a weight group of one flat
@@ -139,7 +139,7 @@ def test_attention_matmuls_run_as_one_grouped_launch(prec, tol, seq, dh, monkeyp
         assert rel_l2(a, b) < 2e-3
 
 
-@pytest.mark.parametrize("prec,tol", [("BF16", 1.5e-2), ("FP16", 4e-3)])
+@pytest.mark.parametrize("prec,tol", [("BF16", 1e-2), ("FP16", 4e-3)])
 @pytest.mark.parametrize("n,heads,seq", [(2, 3, 128), (2, 12, 384), (1, 2, 256)])
 def test_context_matmul_writes_the_merged_heads_layout(prec, tol, n, heads, seq, monkeypatch):
     """context = P V followed by Transpose (0,2,1,3) + Reshape [N,S,H*64]: the grouped launch's 128-row stores land at [n][s][h][:]"""

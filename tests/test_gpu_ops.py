@@ -99,7 +99,7 @@ def test_fc_softmax_topk(precision):
 def test_tiny_resnet(precision):
     f = zoo.resnet50(batch=2, image=64, width=16, blocks=(1, 1, 1, 1), num_classes=24)
     rng = np.random.default_rng(11)
-    _check(f, {"data": rng.uniform(0, 1, (2, 3, 64, 64)).astype(np.float32)}, precision, tol=None if precision == "FP32" else 2e-2)
+    _check(f, {"data": rng.uniform(0, 1, (2, 3, 64, 64)).astype(np.float32)}, precision, tol=None if precision == "FP32" else 1e-2)
 
 
 @pytest.mark.parametrize("precision", ["FP32", "BF16"])
@@ -107,7 +107,7 @@ def test_tiny_mobilenet(precision):
     f = zoo.mobilenet_v2(batch=2, image=64, width_mult=0.25, num_classes=16,
                          settings=[(1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 2, 2), (6, 64, 1, 1)])
     rng = np.random.default_rng(12)
-    _check(f, {"data": rng.uniform(0, 1, (2, 3, 64, 64)).astype(np.float32)}, precision, tol=None if precision == "FP32" else 2e-2)
+    _check(f, {"data": rng.uniform(0, 1, (2, 3, 64, 64)).astype(np.float32)}, precision, tol=None if precision == "FP32" else 1e-2)
 
 
 @pytest.mark.parametrize("precision", ["FP32", "BF16"])
@@ -117,7 +117,7 @@ def test_tiny_bert(precision):
     ins = {"input_ids": rng.integers(0, 100, (2, 32)).astype(np.int32), "attention_mask": np.ones((2, 32), np.int32),
            "token_type_ids": rng.integers(0, 2, (2, 32)).astype(np.int32)}
     ins["attention_mask"][1, 20:] = 0
-    _check(f, ins, precision, tol=None if precision == "FP32" else 3e-2)
+    _check(f, ins, precision, tol=None if precision == "FP32" else 1e-2)
 
 
 def test_tiny_ssd_fp32():
