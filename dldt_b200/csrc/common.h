@@ -52,6 +52,19 @@ inline const char* dtype_name(int dt) {
 inline bool dtype_is_float(int dt) { return dt == B200_F32 || dt == B200_F16 || dt == B200_BF16; }
 
 using Shape = std::vector<int64_t>;
+// PRelu: a rank-1 slope whose size equals the channel extent of x is per-channel, i.e. [1,C,1,..] (nGraph reference
+// ngraph/core/reference/include/ngraph/runtime/reference/prelu.hpp:27-34; the CPU plugin's ReshapePRelu pass,
+// mkldnn_plugin/ngraph_transformations/convert_to_cpu_specific_opset.hpp:36).  Model Optimizer emits slope [C].
+inline std::vector<int64_t> prelu_slope_shape(const std::vector<int64_t>& x, const std::vector<int64_t>& slope) {
+  const size_t ch = x.size() > 1 ? 1 : 0;
+  if (slope.size() == 1 && !x.empty() && x[ch] == slope[0]) {
+    std::vector<int64_t> r(x.size(), 1);
+    r[ch] = slope[0];
+    return r;
+  }
+  return slope;
+}
+
 inline int64_t numel(const Shape& s) {
   int64_t n = 1;
   for (auto d : s) n *= d;

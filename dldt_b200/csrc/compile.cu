@@ -837,7 +837,9 @@ void Lowerer::lower_conv(const FusedConv& f) {
   const std::string out_name = val(f.out_value).name;
 
   if (n.op == B200_OP_MATMUL) {
-    if (!const_node(n.inputs[1])) { lower_matmul_general(n, &f); return; }
+    // activation x activation, or a transposed first operand (A^T * W): the batched-GEMM path (which materialises A^T); the
+    // FullyConnected path below reads A as [M][K] rows and never looks at transpose_a
+    if (!const_node(n.inputs[1]) || n.i[0] != 0) { lower_matmul_general(n, &f); return; }
     // ---- FullyConnected: Y[M,N] = X[M,K] * W^T (+bias, act, residual) ----
     LTensor x = get(n.inputs[0], L_ROWMAJOR);
     const Shape& ws = val(n.inputs[1]).shape;
@@ -1074,6 +1076,13 @@ void Lowerer::lower_matmul_general(const Node& n, const FusedConv* f) {
   B200_CHECK(K % 8 == 0 && Nn % 8 == 0, B200_ERR_UNSUPPORTED, "MatMul '" << n.name << "': K and N must be multiples of 8");
   const int64_t batch_a = numel(a.shape) / (M * K), batch_b = numel(b.shape) / (Nn * K);
   B200_CHECK(batch_a == batch_b || batch_b == 1, B200_ERR_UNSUPPORTED, "MatMul '" << n.name << "': unsupported batch broadcast");
+  if (batch_b != 1) {
+    // equal products are not enough: A batch [2,1] x B batch [1,2] has 4 output batches.  Only identical batch dims are taken.
+    Shape ba(a.shape.begin(), a.shape.end() - 2), bb(b.shape.begin(), b.shape.end() - 2);
+    while (!ba.empty() && ba.front() == 1) ba.erase(ba.begin());
+    while (!bb.empty() && bb.front() == 1) bb.erase(bb.begin());
+    B200_CHECK(ba == bb, B200_ERR_UNSUPPORTED, "MatMul '" << n.name << "': broadcast between batch dimensions is not supported");
+  }
   B200_CHECK(batch_a <= 65535, B200_ERR_UNSUPPORTED, "MatMul batch too large");
   const int out_value = f ? f->out_value : n.outputs[0];
   LTensor out = alloc(val(out_value).shape, cd_, L_ROWMAJOR);
@@ -1219,7 +1228,7 @@ void Lowerer::lower_binary(const Node& n, const ActSpec& act, int out_value) {
   };
   for (int d = 0; d < bp.rank; ++d) bp.oshape[d] = os[d];
   fill(a.shape, bp.astride);
-  fill(b.shape, bp.bstride);
+  fill(n.op == B200_OP_PRELU ? prelu_slope_shape(a.shape, b.shape) : b.shape, bp.bstride);   // slope [C] is per-channel
   bp.op = n.op; bp.act = act.kind; bp.aa = act.a; bp.ab = act.b;
   BufRef ar = a.buf, br = b.buf, yr = out.buf;
   int dt = cd_;
@@ -1508,6 +1517,7 @@ void Lowerer::lower_detection(const Node& n) {
     p.iou_thr = n.f[0]; p.score_thr = n.f[1]; p.soft_sigma = n.f[2];
     LTensor o0 = alloc(val(n.outputs[0]).shape, B200_I32, L_ROWMAJOR), o1 = alloc(val(n.outputs[1]).shape, B200_F32, L_ROWMAJOR),
             o2 = alloc(val(n.outputs[2]).shape, B200_I32, L_ROWMAJOR);
+    nms_check(p);     // unsupported geometry fails LoadNetwork / QueryNetwork, not the first inference
     int64_t wsb = nms_workspace_bytes(p.B, p.C, p.Nb, p.max_out);
     Shape wshape = {wsb};
     LTensor ws = alloc(wshape, B200_U8, L_ROWMAJOR);
@@ -1544,6 +1554,7 @@ void Lowerer::lower_detection(const Node& n) {
   B200_CHECK(conf.shape[1] == (int64_t)p.num_priors * p.num_classes, B200_ERR_INVALID, "DetectionOutput '" << n.name << "': conf size mismatch");
   const Shape os = val(n.outputs[0]).shape;
   p.out_rows = os[2];
+  detection_output_check(p);     // e.g. SSD512's 24564 priors with top_k = -1: refused here, at compile time
   LTensor out = alloc(os, B200_F32, L_ROWMAJOR);
   int64_t wsb = detout_workspace_bytes(p);
   Shape wshape = {wsb};

@@ -142,9 +142,13 @@ void infer_node(const b200_graph& g, const Node& n, std::vector<Shape>& os, std:
       break;
     case B200_OP_ADD: case B200_OP_SUBTRACT: case B200_OP_MULTIPLY: case B200_OP_DIVIDE:
     case B200_OP_MAXIMUM: case B200_OP_MINIMUM: case B200_OP_POWER: case B200_OP_SQUARED_DIFFERENCE:
-    case B200_OP_PRELU:
       need_inputs(2);
       os.push_back(broadcast_shapes(in(0).shape, in(1).shape, n.name));
+      od.push_back(in(0).dtype);
+      break;
+    case B200_OP_PRELU:
+      need_inputs(2);
+      os.push_back(broadcast_shapes(in(0).shape, prelu_slope_shape(in(0).shape, in(1).shape), n.name));
       od.push_back(in(0).dtype);
       break;
     case B200_OP_RELU: case B200_OP_SIGMOID: case B200_OP_TANH: case B200_OP_CLAMP: case B200_OP_SWISH:
@@ -169,6 +173,7 @@ void infer_node(const b200_graph& g, const Node& n, std::vector<Shape>& os, std:
       const Shape& x = in(0).shape;
       bool keep = n.i[0] != 0;
       int na = n.i[1];
+      B200_CHECK(na >= 0 && na <= B200_MAX_IATTR - 2, B200_ERR_INVALID, "reduce '" << n.name << "': bad axis count " << na);
       std::vector<bool> red(x.size(), false);
       for (int k = 0; k < na; ++k) {
         int a = n.i[2 + k];
@@ -214,6 +219,7 @@ void infer_node(const b200_graph& g, const Node& n, std::vector<Shape>& os, std:
       break;
     case B200_OP_MVN:
       B200_CHECK(n.inputs.size() >= 1, B200_ERR_INVALID, "MVN without input");
+      B200_CHECK(n.i[2] >= 0 && n.i[2] <= B200_MAX_IATTR - 3, B200_ERR_INVALID, "MVN '" << n.name << "': bad axis count " << n.i[2]);
       os.push_back(in(0).shape);
       od.push_back(in(0).dtype);
       break;

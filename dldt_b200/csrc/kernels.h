@@ -166,6 +166,7 @@ struct NmsParams {
 };
 int64_t nms_workspace_bytes(int B, int C, int Nb, int max_out);
 void launch_nms(const NmsParams& p, cudaStream_t s);
+void nms_check(const NmsParams& p);                     // throws B200_ERR_UNSUPPORTED for geometry without a kernel (compile time)
 struct DetOutParams {
   const float* loc; const float* conf; const float* priors; float* out;
   int N, num_priors, num_classes, background, top_k, keep_top_k, code_center, share_location, var_in_target, normalized,
@@ -175,6 +176,7 @@ struct DetOutParams {
   void* workspace; int64_t workspace_bytes;
 };
 int64_t detout_workspace_bytes(const DetOutParams& p);
+void detection_output_check(const DetOutParams& p);   // throws B200_ERR_UNSUPPORTED for geometry without a kernel (compile time)
 void launch_detection_output(const DetOutParams& p, cudaStream_t s);
 void detect_init_device();
 

@@ -4,9 +4,14 @@
 //         :240-273 (intersectionOverUnion), :336-376 (nmsWithoutSoftSigma)
 //   DetectionOutput: nodes/mkldnn_detection_output_node.cpp:129-352 (execute), :366-401 (JaccardOverlap),
 //         :403-503 (decodeBBoxes), :505-536 (nms_cf)
-// Per (image, class) the candidates are ordered by a block-wide bitonic sort of 64-bit keys
-// (orderable score bits << 32 | ~index) in shared memory - score descending, index ascending - and
-// the greedy suppression runs on one warp with the kept list checked 32 boxes at a time.
+// Candidates are ordered by 64-bit keys (orderable score bits << 32 | ~index): score descending, index ascending; keys are distinct.
+// DetectionOutput fast path (top_k <= 512, the SSD case): confidences are transposed to [image][class][prior] once (coalesced, as
+// the reference reorders them), then one block per (image, class) radix-SELECTS the top_k keys (8-bit digits, shared-memory
+// histograms) instead of sorting all priors, rank-sorts those <= 512 keys, builds the pairwise-overlap BITMASK of the selected boxes
+// in parallel and replays the greedy suppression as a serial scan over that mask (a box is dropped iff an earlier KEPT box overlaps
+// it: the same recurrence as nms_cf, the overlaps computed by the same expression).  keep_top_k per image is a radix select too.
+// NMS-5 and the DetectionOutput fall-back (top_k = -1 or > 512) sort all candidates with a block-wide bitonic sort in shared memory
+// and run the greedy pass on one warp, the kept list checked 32 boxes at a time.
 #include <algorithm>
 #include <cfloat>
 
@@ -334,6 +339,291 @@ __global__ void detout_pack_kernel(DetOutParams p, const float* boxes, int max_k
   }
 }
 
+
+// ---- fast path ------------------------------------------------------------------------------------
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_KMAX = 512;        // candidates that enter the greedy pass on the fast path (top_k)
+constexpr int KEEP_KMAX = 1024;      // keep_top_k on the fast path
+
+// conf [N][prior][class] -> [N][class][prior] (32 x 32 tiles through shared memory, both sides coalesced)
+__global__ void detout_transpose_conf_kernel(const float* __restrict__ in, float* __restrict__ out, int P, int C) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, c0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
+  const float* src = in + (int64_t)n * P * C;
+  float* dst = out + (int64_t)n * P * C;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int pr = p0 + r, c = c0 + threadIdx.x;
+    if (pr < P && c < C) tile[r][threadIdx.x] = src[(int64_t)pr * C + c];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r, pr = p0 + threadIdx.x;
+    if (pr < P && c < C) dst[(int64_t)c * P + pr] = tile[threadIdx.x][r];
+  }
+}
+
+struct SelectShared {
+  unsigned hist[256];
+  unsigned long long prefix;
+  int need, done, count;
+};
+
+// Threshold T such that exactly min(k, nonzero) of the DISTINCT keys key_at(0..n) are >= T (0 = absent key).  MSB-first radix select
+// with 8-bit digits; stops as soon as the bucket that holds the k-th key is needed whole.  Every thread of the block calls it.
+template <typename KeyAt>
+__device__ uint64_t radix_select_desc(KeyAt key_at, int n, int k, int nonzero, SelectShared& sh) {
+  if (nonzero <= k) return 1ull;
+  if (threadIdx.x == 0) { sh.prefix = 0ull; sh.need = k; sh.done = 0; }
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sh.hist[i] = 0u;
+    __syncthreads();
+    const unsigned long long prefix = sh.prefix;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint64_t key = key_at(i);
+      if (key != 0ull && (shift == 56 || ((key ^ prefix) >> (shift + 8)) == 0ull)) atomicAdd(&sh.hist[(unsigned)(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      // lane l owns bins 255-8l .. 248-8l (descending); find the bin in which the running count reaches `need`
+      const int lane = threadIdx.x, top = 255 - 8 * lane;
+      unsigned local[8], lsum = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) { local[b] = sh.hist[top - b]; lsum += local[b]; }
+      unsigned incl = lsum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const unsigned need = (unsigned)sh.need, before = incl - lsum;
+      const unsigned hit = __ballot_sync(0xffffffffu, incl >= need);
+      if (hit != 0u && lane == __ffs(hit) - 1) {
+        unsigned cum = before;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          if (cum + local[b] >= need) {
+            sh.prefix = prefix | ((unsigned long long)(top - b) << shift);
+            sh.need = (int)(need - cum);
+            sh.done = (local[b] == need - cum) ? 1 : 0;
+            break;
+          }
+          cum += local[b];
+        }
+      }
+    }
+    __syncthreads();
+    if (sh.done) break;
+  }
+  return sh.prefix;
+}
+
+// keys[0..m) (distinct) -> sorted[0..m) descending: every key counts the keys above it (m <= 1024: shared-memory broadcast reads)
+__device__ void rank_sort_desc(const uint64_t* keys, uint64_t* sorted, int m) {
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const uint64_t mine = keys[i];
+    int rank = 0;
+    for (int j = 0; j < m; ++j) rank += keys[j] > mine ? 1 : 0;
+    sorted[rank] = mine;
+  }
+}
+
+// one block per (image, class): select top_k, rank sort, overlap bitmask, greedy scan
+// dynamic shared memory: scores [P] | keys [kcap] | sorted [kcap] | box [kcap][4] | size [kcap] | mask [kcap][kcap/32]
+__global__ void __launch_bounds__(SEL_THREADS) detout_nms_fast_kernel(DetOutParams p, const float* __restrict__ conf_t, const float* __restrict__ boxes,
+                                                                      const float* __restrict__ sizes, int kcap, int max_keep, int32_t* kept, int32_t* cnt) {
+  extern __shared__ __align__(16) unsigned char det_smem[];
+  __shared__ SelectShared sh;
+  const int n = blockIdx.x / p.num_classes, c = blockIdx.x % p.num_classes;
+  if (c == p.background) { if (threadIdx.x == 0) cnt[blockIdx.x] = 0; return; }
+  const int P = p.num_priors, words = kcap / 32;
+  float* sc = reinterpret_cast<float*>(det_smem);
+  uint64_t* keys = reinterpret_cast<uint64_t*>(det_smem + (((int64_t)P * 4 + 15) / 16) * 16);
+  uint64_t* sorted = keys + kcap;
+  float4* sbox = reinterpret_cast<float4*>(sorted + kcap);
+  float* ssz = reinterpret_cast<float*>(sbox + kcap);
+  unsigned* mask = reinterpret_cast<unsigned*>(ssz + kcap);
+  const float* conf = conf_t + ((int64_t)n * p.num_classes + c) * P;
+  const int lc = p.share_location ? 0 : c;
+  const float* bb = boxes + ((int64_t)n * p.num_loc_classes + lc) * P * 4;
+  const float* sz = sizes + ((int64_t)n * p.num_loc_classes + lc) * P;
+  if (threadIdx.x == 0) sh.count = 0;
+  __syncthreads();
+  int local = 0;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const float v = conf[i];
+    sc[i] = v;
+    local += v > p.conf_thr ? 1 : 0;
+  }
+  if (local) atomicAdd(&sh.count, local);
+  __syncthreads();
+  const int count = sh.count;
+  const int m = min(p.top_k, count);        // top_k in [1, SEL_KMAX] on this path
+  if (m == 0) { if (threadIdx.x == 0) cnt[blockIdx.x] = 0; return; }
+  const float thr = p.conf_thr;
+  auto key_at = [&](int i) -> uint64_t { const float v = sc[i]; return v > thr ? make_key(v, (uint32_t)i) : 0ull; };
+  const uint64_t T = radix_select_desc(key_at, P, m, count, sh);
+  if (threadIdx.x == 0) sh.count = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const uint64_t key = key_at(i);
+    if (key >= T && key != 0ull) keys[atomicAdd(&sh.count, 1)] = key;
+  }
+  __syncthreads();
+  rank_sort_desc(keys, sorted, m);
+  __syncthreads();
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const int idx = (int)key_idx(sorted[i]);
+    sbox[i] = *reinterpret_cast<const float4*>(bb + (int64_t)idx * 4);
+    ssz[i] = sz[idx];
+  }
+  __syncthreads();
+  // mask[i][w] bit b: candidate j = 32 w + b (j > i) overlaps candidate i by more than the threshold (JaccardOverlap(j, i))
+  const float* fb = reinterpret_cast<const float*>(sbox);
+  for (int cell = threadIdx.x; cell < m * words; cell += blockDim.x) {
+    const int i = cell / words, w = cell % words;
+    unsigned bits = 0u;
+    const int j0 = max(w * 32, i + 1), j1 = min(w * 32 + 32, m);
+    for (int j = j0; j < j1; ++j)
+      if (jaccard(fb, ssz, j, i) > p.nms_thr) bits |= 1u << (j & 31);
+    mask[cell] = bits;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    unsigned removed = 0u;          // lane w holds word w of the "suppressed" set (words <= 16)
+    int32_t* my = kept + (int64_t)blockIdx.x * max_keep;
+    int det = 0;
+    for (int i = 0; i < m; ++i) {
+      const unsigned word = __shfl_sync(0xffffffffu, removed, i >> 5);
+      if (!((word >> (i & 31)) & 1u)) {
+        if (lane == 0) my[det] = (int)key_idx(sorted[i]);
+        ++det;
+        if (lane < words) removed |= mask[i * words + lane];
+      }
+    }
+    if (lane == 0) cnt[blockIdx.x] = det;
+  }
+}
+
+// one block per image: keep_top_k across classes by radix select; lists re-stored per class in score order
+// dynamic shared memory: keys [cap] | sel [KEEP_KMAX] | sorted [KEEP_KMAX] | counts [num_classes] | bases [num_classes]
+__global__ void __launch_bounds__(1024) detout_keep_fast_kernel(DetOutParams p, const float* __restrict__ conf_t, int cap, int max_keep, int32_t* kept,
+                                                                int32_t* cnt, int32_t* totals) {
+  extern __shared__ __align__(16) unsigned char keep_smem[];
+  __shared__ SelectShared sh;
+  uint64_t* keys = reinterpret_cast<uint64_t*>(keep_smem);
+  uint64_t* sel = keys + cap;
+  uint64_t* sorted = sel + KEEP_KMAX;
+  int* counts = reinterpret_cast<int*>(sorted + KEEP_KMAX);
+  int* bases = counts + p.num_classes;
+  const int n = blockIdx.x, C = p.num_classes, P = p.num_priors;
+  int32_t* my_cnt = cnt + (int64_t)n * C;
+  int32_t* my_kept = kept + (int64_t)n * C * max_keep;
+  const float* conf = conf_t + (int64_t)n * C * P;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) counts[c] = my_cnt[c];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int c = 0; c < C; ++c) { bases[c] = t; t += counts[c]; }
+    sh.count = t;
+  }
+  __syncthreads();
+  const int total = sh.count;
+  if (!(p.keep_top_k > -1 && total > p.keep_top_k)) {
+    if (threadIdx.x == 0) totals[n] = total;
+    return;
+  }
+  for (int c = 0; c < C; ++c)
+    for (int k = threadIdx.x; k < counts[c]; k += blockDim.x) {
+      const int idx = my_kept[(int64_t)c * max_keep + k];
+      keys[bases[c] + k] = make_key(conf[(int64_t)c * P + idx], (uint32_t)(c * P + idx));
+    }
+  __syncthreads();
+  auto key_at = [&](int i) -> uint64_t { return keys[i]; };
+  const uint64_t T = radix_select_desc(key_at, total, p.keep_top_k, total, sh);
+  if (threadIdx.x == 0) sh.count = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < total; i += blockDim.x)
+    if (keys[i] >= T) sel[atomicAdd(&sh.count, 1)] = keys[i];
+  __syncthreads();
+  rank_sort_desc(sel, sorted, p.keep_top_k);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) counts[c] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int j = 0; j < p.keep_top_k; ++j) {
+      const uint32_t lin = key_idx(sorted[j]);
+      const int label = (int)(lin / (uint32_t)P), idx = (int)(lin % (uint32_t)P);
+      my_kept[(int64_t)label * max_keep + counts[label]++] = idx;
+    }
+    totals[n] = p.keep_top_k;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) my_cnt[c] = counts[c];
+}
+
+// rows [image_id, label, conf, xmin, ymin, xmax, ymax] grouped by image, class, list order.  One block per image; the row offset of
+// every (image, class) list comes from prefix sums held in shared memory.  conf_t: scores as [image][class][prior].
+__global__ void detout_pack_fast_kernel(DetOutParams p, const float* __restrict__ conf_t, const float* __restrict__ boxes, int max_keep,
+                                        const int32_t* __restrict__ kept, const int32_t* __restrict__ cnt, const int32_t* __restrict__ totals) {
+  extern __shared__ int pack_smem[];      // [num_classes + 1] row offsets of this image's class lists
+  __shared__ int s_base, s_all;
+  const int n = blockIdx.x, C = p.num_classes, P = p.num_priors;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) pack_smem[c + 1] = cnt[n * C + c];
+  if (threadIdx.x == 0) {
+    int b = 0, all = 0;
+    for (int i = 0; i < p.N; ++i) { const int t = totals[i]; if (i < n) b += t; all += t; }
+    s_base = b; s_all = all;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    pack_smem[0] = 0;
+    for (int c = 0; c < C; ++c) pack_smem[c + 1] += pack_smem[c];
+  }
+  __syncthreads();
+  const int base = s_base, mine = pack_smem[C];
+  const float* conf = conf_t + (int64_t)n * C * P;
+  for (int c = 0; c < C; ++c) {
+    const int lc = p.share_location ? 0 : c;
+    const float* bb = boxes + ((int64_t)n * p.num_loc_classes + lc) * P * 4;
+    const int first = pack_smem[c], len = pack_smem[c + 1] - first;
+    for (int k = threadIdx.x; k < len; k += blockDim.x) {
+      const int64_t row = (int64_t)base + first + k;
+      if (row >= p.out_rows) break;
+      const int idx = kept[((int64_t)n * C + c) * max_keep + k];
+      float xmin = bb[idx * 4 + 0], ymin = bb[idx * 4 + 1], xmax = bb[idx * 4 + 2], ymax = bb[idx * 4 + 3];
+      if (p.clip_after) {
+        xmin = fmaxf(0.f, fminf(1.f, xmin)); ymin = fmaxf(0.f, fminf(1.f, ymin));
+        xmax = fmaxf(0.f, fminf(1.f, xmax)); ymax = fmaxf(0.f, fminf(1.f, ymax));
+      }
+      float* o = p.out + row * 7;
+      o[0] = (float)n; o[1] = (float)c; o[2] = conf[(int64_t)c * P + idx];
+      o[3] = xmin; o[4] = ymin; o[5] = xmax; o[6] = ymax;
+    }
+  }
+  // the last image also clears the unused tail and writes the end-of-list marker
+  if (n == p.N - 1) {
+    const int64_t used = min((int64_t)s_all, p.out_rows);
+    for (int64_t i = used * 7 + threadIdx.x; i < p.out_rows * 7; i += blockDim.x) p.out[i] = (i == used * 7) ? -1.f : 0.f;
+  }
+  (void)mine;
+}
+
+bool detout_fast_path(const DetOutParams& p) {
+  const char* off = getenv("B200_DETOUT_FAST");
+  if (off && off[0] == '0') return false;
+  const int max_keep = p.top_k > 0 ? std::min(p.top_k, p.num_priors) : p.num_priors;
+  return p.top_k > 0 && p.top_k <= SEL_KMAX && (p.keep_top_k < 0 || p.keep_top_k <= KEEP_KMAX) && (int64_t)p.num_classes * max_keep <= SORT_MAX &&
+         p.num_priors <= 32768;
+}
+int detout_kcap(const DetOutParams& p) { return (int)round_up((int64_t)std::min(p.top_k, p.num_priors), 32); }
+size_t detout_nms_fast_smem(const DetOutParams& p) {
+  const int64_t k = detout_kcap(p);
+  return (size_t)(round_up((int64_t)p.num_priors * 4, 16) + k * 8 * 2 + k * 16 + k * 4 + k * (k / 32) * 4);
+}
+size_t detout_keep_fast_smem(const DetOutParams& p, int max_keep) {
+  return (size_t)((int64_t)p.num_classes * max_keep * 8 + KEEP_KMAX * 8 * 2 + p.num_classes * 8 + 16);
+}
+
 int detout_max_keep(const DetOutParams& p) { return p.top_k > 0 ? std::min(p.top_k, p.num_priors) : p.num_priors; }
 
 }  // namespace
@@ -342,6 +632,8 @@ void detect_init_device() {
   cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM);
   cudaFuncSetAttribute(detout_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM);
   cudaFuncSetAttribute(detout_keep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM);
+  cudaFuncSetAttribute(detout_nms_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(detout_keep_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
 int64_t nms_workspace_bytes(int B, int C, int Nb, int max_out) {
@@ -352,9 +644,7 @@ int64_t nms_workspace_bytes(int B, int C, int Nb, int max_out) {
 }
 
 void launch_nms(const NmsParams& p, cudaStream_t s) {
-  B200_CHECK(p.soft_sigma == 0.f, B200_ERR_UNSUPPORTED, "NonMaxSuppression: soft_nms_sigma > 0 is not supported");
-  B200_CHECK(p.Nb <= SORT_MAX, B200_ERR_UNSUPPORTED, "NonMaxSuppression: more than " << SORT_MAX << " boxes per batch");
-  B200_CHECK((int64_t)p.B * p.C * p.Nb < (1ll << 32), B200_ERR_UNSUPPORTED, "NonMaxSuppression: problem too large");
+  nms_check(p);
   if (p.B * p.C == 0 || p.max_out == 0) return;
   char* ws = (char*)p.workspace;
   int32_t* sel = (int32_t*)ws;
@@ -375,24 +665,49 @@ int64_t detout_workspace_bytes(const DetOutParams& p) {
   int64_t kept = round_up((int64_t)p.N * p.num_classes * detout_max_keep(p) * 4, 256);
   int64_t cnt = round_up((int64_t)p.N * p.num_classes * 4, 256);
   int64_t totals = round_up((int64_t)p.N * 4, 256);
-  return boxes + sizes + kept + cnt + totals + 1024;
+  int64_t conf_t = detout_fast_path(p) ? round_up((int64_t)p.N * p.num_priors * p.num_classes * 4, 256) : 0;
+  return boxes + sizes + kept + cnt + totals + conf_t + 1024;
+}
+
+// Geometry the kernels cannot run: reported at COMPILE time (b200_compile -> LoadNetwork / QueryNetwork), not at the first inference
+void detection_output_check(const DetOutParams& p) {
+  B200_CHECK(!p.decrease_label_id, B200_ERR_UNSUPPORTED, "DetectionOutput: decrease_label_id (MXNet style) is not supported");
+  if (detout_fast_path(p)) {
+    B200_CHECK(detout_nms_fast_smem(p) <= 200 * 1024, B200_ERR_UNSUPPORTED, "DetectionOutput: " << p.num_priors << " priors x top_k " << p.top_k << " exceed shared memory");
+    return;
+  }
+  B200_CHECK(p.num_priors <= SORT_MAX, B200_ERR_UNSUPPORTED, "DetectionOutput: more than " << SORT_MAX << " priors with top_k = " << p.top_k);
+  B200_CHECK(p.keep_top_k < 0 || (int64_t)p.num_classes * detout_max_keep(p) <= SORT_MAX, B200_ERR_UNSUPPORTED,
+             "DetectionOutput: num_classes*top_k > " << SORT_MAX);
+}
+void nms_check(const NmsParams& p) {
+  B200_CHECK(p.soft_sigma == 0.f, B200_ERR_UNSUPPORTED, "NonMaxSuppression: soft_nms_sigma > 0 is not supported");
+  B200_CHECK(p.Nb <= SORT_MAX, B200_ERR_UNSUPPORTED, "NonMaxSuppression: more than " << SORT_MAX << " boxes per batch");
+  B200_CHECK((int64_t)p.B * p.C * p.Nb < (1ll << 32), B200_ERR_UNSUPPORTED, "NonMaxSuppression: problem too large");
 }
 
 void launch_detection_output(const DetOutParams& p, cudaStream_t s) {
-  B200_CHECK(!p.decrease_label_id, B200_ERR_UNSUPPORTED, "DetectionOutput: decrease_label_id (MXNet style) is not supported");
-  B200_CHECK(p.num_priors <= SORT_MAX, B200_ERR_UNSUPPORTED, "DetectionOutput: more than " << SORT_MAX << " priors");
+  detection_output_check(p);
   const int max_keep = detout_max_keep(p);
   const int64_t all = (int64_t)p.num_classes * max_keep;
-  B200_CHECK(p.keep_top_k < 0 || all <= SORT_MAX, B200_ERR_UNSUPPORTED, "DetectionOutput: num_classes*top_k > " << SORT_MAX);
   char* ws = (char*)p.workspace;
   int64_t off = 0;
   float* boxes = (float*)(ws + off); off += round_up((int64_t)p.N * p.num_loc_classes * p.num_priors * 16, 256);
   float* sizes = (float*)(ws + off); off += round_up((int64_t)p.N * p.num_loc_classes * p.num_priors * 4, 256);
   int32_t* kept = (int32_t*)(ws + off); off += round_up((int64_t)p.N * p.num_classes * max_keep * 4, 256);
   int32_t* cnt = (int32_t*)(ws + off); off += round_up((int64_t)p.N * p.num_classes * 4, 256);
-  int32_t* totals = (int32_t*)(ws + off);
+  int32_t* totals = (int32_t*)(ws + off); off += round_up((int64_t)p.N * 4, 256);
   int64_t nd = (int64_t)p.N * p.num_loc_classes * p.num_priors;
   detout_decode_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, s>>>(p, boxes, sizes);
+  if (detout_fast_path(p)) {
+    float* conf_t = (float*)(ws + off);
+    dim3 tg((unsigned)((p.num_classes + 31) / 32), (unsigned)((p.num_priors + 31) / 32), (unsigned)p.N);
+    detout_transpose_conf_kernel<<<tg, dim3(32, 8), 0, s>>>(p.conf, conf_t, p.num_priors, p.num_classes);
+    detout_nms_fast_kernel<<<p.N * p.num_classes, SEL_THREADS, detout_nms_fast_smem(p), s>>>(p, conf_t, boxes, sizes, detout_kcap(p), max_keep, kept, cnt);
+    detout_keep_fast_kernel<<<p.N, 1024, detout_keep_fast_smem(p, max_keep), s>>>(p, conf_t, (int)all, max_keep, kept, cnt, totals);
+    detout_pack_fast_kernel<<<p.N, 256, (size_t)(p.num_classes + 1) * 4, s>>>(p, conf_t, boxes, max_keep, kept, cnt, totals);
+    return;
+  }
   const int n_pad = next_pow2(std::max(p.num_priors, 2));
   detout_nms_kernel<<<p.N * p.num_classes, 512, (size_t)n_pad * 8, s>>>(p, boxes, sizes, n_pad, max_keep, kept, cnt);
   const int keep_pad = next_pow2((int)std::max<int64_t>(std::min<int64_t>(all, SORT_MAX), 2));

@@ -145,6 +145,11 @@ class Function:
     def power(self, a, b, name=None): return self._binary("Power", a, b, name)
     def squared_difference(self, a, b, name=None): return self._binary("SquaredDifference", a, b, name)
 
+    def prelu(self, x, slope, name=None):
+        """opset1 PRelu; a rank-1 slope of size C is per-channel (what Model Optimizer emits)."""
+        slope = slope if isinstance(slope, Output) else self.constant(np.asarray(slope, np.float32))
+        return self._add("PRelu", [x, slope], name).outputs[0]
+
     def relu(self, x, name=None): return self._add("Relu", [x], name).outputs[0]
     def sigmoid(self, x, name=None): return self._add("Sigmoid", [x], name).outputs[0]
     def tanh(self, x, name=None): return self._add("Tanh", [x], name).outputs[0]

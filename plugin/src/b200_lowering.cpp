@@ -347,6 +347,49 @@ bool IsNodeSupported(const NodePtr& node, std::string* why) {
     return ok;
 }
 
+// QueryNetwork: the op id alone does not say whether the kernels take THIS geometry (DetectionOutput with too many priors, TopK with a
+// huge k, a MatMul batch broadcast, ...).  The node is rebuilt on its own - Parameters for its non-constant inputs, its constants
+// kept - and pushed through the real compiler without a device (b200_compile, device -1); what LoadNetwork would refuse is refused here,
+// so HETERO can place the node elsewhere (the reference fails such layers at LoadNetwork too, never at the first Infer).
+bool DryCompileNode(const NodePtr& node, std::string* why) {
+    if (ngraph::op::is_parameter(node) || ngraph::op::is_constant(node) || ngraph::op::is_output(node)) return true;
+    try {
+        ngraph::OutputVector inputs;
+        ngraph::ParameterVector params;
+        for (const auto& in : node->input_values()) {
+            if (ngraph::op::is_constant(in.get_node())) {
+                inputs.push_back(in);
+            } else {
+                auto p = std::make_shared<ngraph::opset1::Parameter>(in.get_element_type(), in.get_partial_shape());
+                params.push_back(p);
+                inputs.push_back(p->output(0));
+            }
+        }
+        auto clone = node->clone_with_new_inputs(inputs);
+        ngraph::ResultVector results;
+        for (const auto& out : clone->outputs()) results.push_back(std::make_shared<ngraph::opset1::Result>(out));
+        auto f = std::make_shared<ngraph::Function>(results, params, "query_" + node->get_friendly_name());
+        b200_graph* g = LowerFunction(f);
+        b200_compile_options opts;
+        std::memset(&opts, 0, sizeof(opts));
+        opts.abi_version = B200_ABI_VERSION;
+        opts.device = -1;
+        opts.precision = B200_PREC_BF16;
+        b200_network* net = nullptr;
+        const int rc = b200_compile(g, &opts, &net);
+        b200_graph_destroy(g);
+        if (net) b200_network_destroy(net);
+        if (rc < 0) {
+            if (why) *why = b200_last_error();
+            return false;
+        }
+        return true;
+    } catch (const std::exception& e) {
+        if (why) *why = e.what();
+        return false;
+    }
+}
+
 b200_graph* LowerFunction(const std::shared_ptr<ngraph::Function>& function) {
     b200_graph* g = nullptr;
     if (b200_graph_create(function->get_friendly_name().c_str(), &g) != B200_OK) IE_THROW() << "B200: " << b200_last_error();

@@ -23,6 +23,9 @@ std::shared_ptr<ngraph::Function> ShardBatch(const std::shared_ptr<const ngraph:
 // true if `node` (after TransformNetwork) maps onto a b200_op; `why` receives the reason otherwise.
 bool IsNodeSupported(const std::shared_ptr<ngraph::Node>& node, std::string* why = nullptr);
 
+// true if the kernels take the node's actual geometry: the node alone is compiled without a device (QueryNetwork).
+bool DryCompileNode(const std::shared_ptr<ngraph::Node>& node, std::string* why = nullptr);
+
 // Builds the b200_graph; throws InferenceEngine::NotImplemented / GeneralError with the library's message on failure.
 // The caller owns the returned graph (b200_graph_destroy).
 b200_graph* LowerFunction(const std::shared_ptr<ngraph::Function>& function);

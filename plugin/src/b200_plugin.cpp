@@ -326,7 +326,10 @@ QueryNetworkResult Plugin::QueryNetwork(const CNNNetwork& network, const std::ma
     auto transformed = TransformNetwork(function);
     std::unordered_set<std::string> supported, unsupported;
     for (const auto& node : transformed->get_ops()) {
-        const bool ok = IsNodeSupported(node);
+        // op-level check, then the node's own geometry through the compiler (cheap ops and weight-heavy convolutions are trusted to the
+        // op-level check: their lowering has no shape-dependent refusal)
+        bool ok = IsNodeSupported(node);
+        if (ok && !ngraph::is_type<ngraph::opset1::Convolution>(node) && !ngraph::is_type<ngraph::opset1::GroupConvolution>(node)) ok = DryCompileNode(node);
         for (const auto& fused : ngraph::getFusedNamesVector(node))
             if (original.count(fused)) (ok ? supported : unsupported).insert(fused);
     }

@@ -354,6 +354,20 @@ def detout_not_shared(): return _detout_case("detout_not_shared", 2, 40, 3, 8, 6
 def detout_var_in_target(): return _detout_case("detout_var_in_target", 1, 64, 5, -1, 12, var_in_target=True)
 
 
+@case
+def prelu_per_channel_slope():
+    """PRelu with the slope Model Optimizer emits: rank 1, one value per channel ([C], not [1,C,1,1]); C == W on purpose, so a plain numpy
+    broadcast would silently scale along W.  Also after a convolution (the conv output stays NHWC on the device)."""
+    r = _rng("prelu_per_channel_slope")
+    f = Function("prelu_per_channel_slope")
+    x = f.parameter((2, 8, 5, 8), name="x")
+    f.result(f.prelu(x, _f32(r.uniform(0.05, 0.5, 8)), name="prelu"))
+    y = f.convolution(x, _f32(r.standard_normal((16, 8, 3, 3)) / np.sqrt(72)), (1, 1), (1, 1), (1, 1), name="conv")
+    f.result(f.prelu(y, _f32(r.uniform(0.05, 0.5, 16)), name="conv_prelu"))
+    f.result(f.prelu(x, _f32([0.25]), name="prelu_scalar"))
+    return f, {"x": _f32(r.standard_normal((2, 8, 5, 8)))}
+
+
 # ---- whole (tiny) networks of the four model families -----------------------------------------------------
 @case
 def net_tiny_resnet():

@@ -132,3 +132,35 @@ def test_tiny_ssd_fp32():
     g, r = got["detection_out"].reshape(-1, 7), ref["detection_out"].reshape(-1, 7)
     np.testing.assert_array_equal(g[:, :2], r[:, :2])          # image ids + labels (and the -1 terminator)
     assert rel_l2(g[:, 2:], r[:, 2:]) < 1e-4
+
+
+@pytest.mark.parametrize("priors,classes,top_k,keep_top_k,n", [(8732, 21, 200, 200, 2), (3000, 81, 400, 100, 1), (700, 5, 64, -1, 3)])
+def test_detection_output_select_path_equals_sort_path(priors, classes, top_k, keep_top_k, n, monkeypatch):
+    """The radix-select + overlap-bitmask DetectionOutput (SSD sizes) against the full-sort fall-back of the same library and the
+    numpy restatement, with heavily quantised scores so that equal scores are ordered by prior index on every path."""
+    from dldt_b200 import Function
+    rng = np.random.default_rng(priors + classes)
+    f = Function("detout_big")
+    loc = f.parameter((n, priors * 4), name="loc")
+    conf = f.parameter((n, priors * classes), name="conf")
+    cx, cy = rng.uniform(0.1, 0.9, priors), rng.uniform(0.1, 0.9, priors)
+    w, h = rng.uniform(0.05, 0.3, priors), rng.uniform(0.05, 0.3, priors)
+    pb = np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1).astype(np.float32)
+    var = np.tile(np.asarray([0.1, 0.1, 0.2, 0.2], np.float32), (priors, 1))
+    pri = np.stack([pb.reshape(-1), var.reshape(-1)])[None]
+    det = f.detection_output(loc, conf, pri, classes, 0, top_k, keep_top_k, "caffe.PriorBoxParameter.CENTER_SIZE", True, 0.45, 0.02, name="det")
+    f.result(det)
+    logits = rng.standard_normal((n, priors, classes)) * 2
+    p = np.exp(logits - logits.max(-1, keepdims=True))
+    p /= p.sum(-1, keepdims=True)
+    p = np.round(p * 64) / 64            # many exact ties
+    ins = {"loc": (rng.standard_normal((n, priors * 4)) * 0.5).astype(np.float32), "conf": p.reshape(n, -1).astype(np.float32)}
+    fast, _ = run_b200(f, ins, "FP32")
+    monkeypatch.setenv("B200_DETOUT_FAST", "0")
+    slow, _ = run_b200(f, ins, "FP32")
+    monkeypatch.delenv("B200_DETOUT_FAST")
+    np.testing.assert_array_equal(fast["det"], slow["det"])
+    ref = run_oracle(f, ins)["det"].reshape(-1, 7)
+    g = fast["det"].reshape(-1, 7)
+    np.testing.assert_array_equal(g[:, :2], ref[:, :2])
+    assert rel_l2(g[:, 2:], ref[:, 2:]) < 1e-5

@@ -150,3 +150,35 @@ def test_core_cache_dir_drives_export_and_import(tiny_resnet_xml, tmp_path):
     p = ie_run(tiny_resnet_xml, "--dry", "--cache-dir", str(cache), "--config", "B200_DRY_COMPILE=YES")
     assert p.returncode == 0, p.stderr
     assert [b.stat().st_mtime_ns for b in cache.iterdir()] == [stamp]      # second load read the entry, did not rewrite it
+
+
+def test_unsupported_geometry_fails_at_load_not_at_first_infer(tmp_path):
+    """DetectionOutput over 20000 priors with top_k = -1 has no kernel (the fall-back sorts at most 16384 keys in shared memory):
+    QueryNetwork leaves the layer out (so HETERO could place it elsewhere) and LoadNetwork refuses it - the reference fails at
+    LoadNetwork too, never inside the first Infer."""
+    import numpy as np
+    from dldt_b200 import Function
+    priors, classes = 20000, 3
+    f = Function("detout_too_big")
+    loc = f.parameter((1, priors * 4), name="loc")
+    conf = f.parameter((1, priors * classes), name="conf")
+    pri = np.zeros((1, 2, priors * 4), np.float32)
+    det = f.detection_output(loc, conf, pri, classes, 0, -1, 10, "caffe.PriorBoxParameter.CENTER_SIZE", True, 0.45, 0.01, name="det")
+    f.result(det)
+    xml = str(tmp_path / "d.xml")
+    ir.serialize(f, xml)
+    q = ie_run(xml, "--query")
+    assert q.returncode == 0, q.stderr
+    q = json.loads(q.stdout)
+    assert q["supported_layers"] < q["total_layers"]
+    p = ie_run(xml, "--dry", "--config", "B200_DRY_COMPILE=YES")
+    assert p.returncode != 0 and "priors" in p.stderr
+    # the same layer with top_k = 200 takes the radix-select path (up to 32768 priors)
+    f2 = Function("detout_select")
+    loc = f2.parameter((1, priors * 4), name="loc")
+    conf = f2.parameter((1, priors * classes), name="conf")
+    f2.result(f2.detection_output(loc, conf, pri, classes, 0, 200, 10, "caffe.PriorBoxParameter.CENTER_SIZE", True, 0.45, 0.01, name="det"))
+    xml2 = str(tmp_path / "d2.xml")
+    ir.serialize(f2, xml2)
+    p = ie_run(xml2, "--dry", "--config", "B200_DRY_COMPILE=YES")
+    assert p.returncode == 0, p.stderr
