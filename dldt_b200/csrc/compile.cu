@@ -1003,6 +1003,22 @@ void Lowerer::lower_conv(const FusedConv& f) {
     // the shortcut reads every sh2*sw2-th pixel of x2
     bytes += (double)x2.bytes() / (dn->i[0] * dn->i[1]) + (double)Cout * x2.shape[1] * dtype_size(cd_);
   }
+  // <= 4 input channels (the C = 3 first layer of MobileNet-style networks; ResNet/SSD stems are space-to-depth, above): as an implicit GEMM
+  // K = taps x 8 padded channels is mostly zeros and ran in the tensor-core kernel's gather mode; a direct CUDA-core kernel is HBM-bound
+  if (tc && !grouped && !dn && f.next_root < 0 && f.res_value < 0 && f.act2.kind == ACT_NONE && conv_small_cin_supported(p, (int)Cin, cd_)) {
+    Step s;
+    s.name = out_name; s.type = "Convolution"; s.impl = "direct_small_cin_cuda_core"; s.fused = fused; s.flops = flops; s.bytes = bytes;
+    BufRef xr = x.buf, yr = out.buf;
+    const int dt = cd_, cin = (int)Cin;
+    s.launch = [=](const RunCtx& c) {
+      ConvParams q = p;
+      q.x = c.ptr(xr); q.w = c.ptr(wref); q.bias = reinterpret_cast<const float*>(c.ptr(bref)); q.y = c.ptr(yr);
+      launch_conv_small_cin(q, cin, dt, (cudaStream_t)c.stream);
+    };
+    emit(std::move(s), {&x}, {&out});
+    set(f.out_value, out);
+    return;
+  }
   BufRef w2ref, b2ref;
   LTensor z;
   if (f.next_root >= 0) {

@@ -100,6 +100,11 @@ struct DwParams {
   int act; float a, b;
 };
 void launch_dwconv(const DwParams& p, int dtype, cudaStream_t s);
+bool dwconv_strip_supported(const DwParams& p, int dtype);      // kernels_dw.cu: 3x3 stride 1/2, 16-bit data
+void launch_dwconv_strip(const DwParams& p, int dtype, cudaStream_t s);
+struct ConvParams;
+bool conv_small_cin_supported(const ConvParams& p, int cin, int dtype);   // kernels_dw.cu: dense convolution over <= 4 input channels
+void launch_conv_small_cin(const ConvParams& p, int cin, int dtype, cudaStream_t s);
 
 // ---- pooling ---------------------------------------------------------------------------------
 struct PoolParams {

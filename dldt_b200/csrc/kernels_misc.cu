@@ -998,6 +998,7 @@ __global__ void topk_kernel(const float* __restrict__ x, float* __restrict__ val
 
 // ================================= launchers ==========================================================
 void launch_dwconv(const DwParams& p, int dtype, cudaStream_t s) {
+  if (dwconv_strip_supported(p, dtype)) { launch_dwconv_strip(p, dtype, s); return; }
   int64_t total = (int64_t)p.N * p.Ho * p.Wo * (p.Cp / 8);
   const bool fast = (dtype == B200_BF16 || dtype == B200_F16) && p.kh == 3 && p.kw == 3 && p.dh == 1 && p.dw == 1 && p.sh == p.sw && (p.sh == 1 || p.sh == 2) &&
                     p.pt >= 0 && p.pt <= 1 && p.pl >= 0 && p.pl <= 1;

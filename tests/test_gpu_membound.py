@@ -67,20 +67,40 @@ def test_head_transpose_moves_16_byte_vectors(prec):
     assert a.shape == (3, 12, 40, 64) and rel_l2(a, b) < (1e-6 if prec == "FP32" else 5e-3)
 
 
-@pytest.mark.parametrize("stride,h,w", [(1, 20, 23), (2, 21, 30), (2, 56, 56)])
-def test_depthwise_3x3_fast_path(stride, h, w):
+@pytest.mark.parametrize("prec", ["BF16", "FP16"])
+@pytest.mark.parametrize("stride,h,w,c,pad", [(1, 20, 23, 48, 1), (2, 21, 30, 48, 1), (2, 56, 56, 48, 1), (1, 7, 7, 40, 1), (1, 9, 5, 24, 0), (2, 14, 14, 96, 0),
+                                              (1, 3, 3, 8, 1), (2, 5, 6, 20, 1)])
+def test_depthwise_3x3_fast_path(stride, h, w, c, pad, prec):
+    # strips of 4 / 2 output rows, two output columns per thread: odd widths, heights that are not a multiple of the strip, channel counts
+    # that are not a multiple of 8 (padded lanes), no padding, maps smaller than one strip
     rng = np.random.default_rng(stride * 100 + w)
-    c = 48
     f = Function("dw")
     x = f.parameter((2, c, h, w), name="x")
     wdw = (rng.standard_normal((c, 1, 1, 3, 3)) * 0.4).astype(np.float32)
-    y = f.group_convolution(x, wdw, (stride, stride), (1, 1), (1, 1), (1, 1))
+    y = f.group_convolution(x, wdw, (stride, stride), (pad, pad), (pad, pad), (1, 1))
     y = f.clamp(f.add(y, rng.standard_normal((1, c, 1, 1)).astype(np.float32) * 0.1), 0.0, 6.0)
     f.result(y)
     xin = rng.standard_normal((2, c, h, w)).astype(np.float32)
-    ref, got, eg = run(f, {"x": xin}, "BF16")
+    ref, got, eg = run(f, {"x": xin}, prec)
     assert any(e["impl"].startswith("dw_") for e in eg)
-    assert rel_l2(list(got.values())[0], list(ref.values())[0]) < 1e-2
+    assert rel_l2(list(got.values())[0], list(ref.values())[0]) < (1e-2 if prec == "BF16" else 2e-3)
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,pad,dil,h,w", [(3, 32, 3, 2, 1, 1, 64, 64), (3, 32, 3, 2, 1, 1, 33, 47), (1, 16, 5, 1, 2, 1, 20, 20), (4, 24, 3, 1, 1, 2, 17, 19),
+                                                        (2, 64, 1, 1, 0, 1, 9, 9)])
+def test_first_convolution_over_few_input_channels(cin, cout, k, stride, pad, dil, h, w):
+    """Dense convolution over <= 4 input channels (MobileNet's C = 3 first layer) runs as the direct CUDA-core kernel, BN and ReLU6 folded."""
+    rng = np.random.default_rng(cin * 1000 + cout)
+    f = Function("first")
+    x = f.parameter((2, cin, h, w), name="x")
+    y = f.convolution(x, (rng.standard_normal((cout, cin, k, k)) / np.sqrt(cin * k * k)).astype(np.float32), (stride, stride), (pad, pad), (pad, pad), (dil, dil))
+    y = f.clamp(f.add(y, rng.standard_normal((1, cout, 1, 1)).astype(np.float32) * 0.1), 0.0, 6.0)
+    f.result(y)
+    xin = rng.uniform(0, 1, (2, cin, h, w)).astype(np.float32)
+    for prec, tol in (("BF16", 1e-2), ("FP16", 2e-3)):
+        ref, got, eg = run(f, {"x": xin}, prec)
+        assert [e["impl"] for e in eg if e["type"] == "Convolution"] == ["direct_small_cin_cuda_core"]
+        assert rel_l2(list(got.values())[0], list(ref.values())[0]) < tol
 
 
 @pytest.mark.parametrize("h,w", [(28, 28), (15, 21), (7, 7)])
