@@ -1,0 +1,325 @@
+// Fused scaled-dot-product attention for the BERT path (sm_100a, tcgen05 + TMEM + TMA): softmax(Q K^T * scale + mask) V for one
+// (image, head, 128-query tile) per CTA, the scores never leaving the SM.
+//
+// What it replaces in the schedule: MatMul (Q K^T) -> Multiply -> Add(mask) -> Softmax -> MatMul (P V) -> Transpose, i.e. the reference's
+// nodes/mkldnn_matmul_node.cpp:225-262 (gemm looped over batch x heads), mkldnn_softmax_node.cpp and the eltwise nodes between them; as
+// separate kernels the [N, heads, S, S] scores made three HBM round trips (Q K^T store, softmax read + write, P V load): 2.7 ms of a
+// 6.9 ms BERT-base step at batch 64, S = 384.
+//
+// One CTA, 32 x (1 + S/32) threads:
+//   warp 0 .. S/32-1   softmax: warp w owns TMEM lanes 32 (w % 4) .. +31 (the hardware's lane quarter rule) = 32 query rows, and the 128
+//                      key columns [128 (w / 4), +128): one tcgen05.ld pass (the whole row segment stays in registers: 128 fp32), scale +
+//                      mask in the log2 domain, row max / row sum exchanged between the S/128 column groups through shared memory,
+//                      ex2.approx, bf16 pack, swizzled store of P as the K-major A operand of the second MMA.
+//                      Warps 0-3 then read O (64 fp32 columns), divide by the row sum, pack, stage and TMA-store it.
+//   last warp          one elected lane: TMA loads (Q 16 KB, K and V S x 128 B each), MMA 1: S[128 x S] = Q K^T as S/128 MMAs of
+//                      128 x 128 x 64 into TMEM columns [0, S), MMA 2: O[128 x 64] = P V over K = S with V read MN-major
+//                      (no transpose: V is [key][64], the descriptor's "B is N-contiguous" bit) into TMEM columns [S, S + 64).
+// Shared memory: Q 16 KB (reused as the output staging tile) | K S x 128 B | V S x 128 B | P 128 x S bf16 | mask, row max / sum, barriers:
+// 210 KB at S = 384.  TMEM: S + 64 <= 512 columns.
+// Normalisation is applied to O in fp32 (O / sum) rather than to P before its bf16 rounding; scores stay fp32 until P is formed, where
+// the unfused path rounded them to bf16 twice (Q K^T output and softmax output).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.h"
+#include "kernels.h"
+#include "ptx_sm100.cuh"
+#include "tc_common.cuh"
+
+namespace b200 {
+
+CUtensorMap make_tmap_2d(const void* base, bool bf16, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer);
+
+namespace {
+
+using namespace tc;
+
+constexpr int QT = 128;             // query rows per CTA
+constexpr int DH = 64;              // head size
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttnArgs {
+  CUtensorMap tm_q, tm_k, tm_v;     // [N*H*S][64], boxes {64, 128}
+  CUtensorMap tm_y;                 // [N*S][H*64], box {64, 128}
+  const void* mask;                 // [mask_batch][S] in the compute type, or null
+  int N, H, S, mask_batch;
+  float scale_log2;                 // scale * log2(e)
+};
+
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int S>
+struct AttnSmem {
+  static constexpr uint32_t q_off = 0;                               // 16 KB, also the output staging tile
+  static constexpr uint32_t k_off = QT * 128;
+  static constexpr uint32_t v_off = k_off + S * 128;
+  static constexpr uint32_t p_off = v_off + S * 128;                 // S/64 K-blocks of 128 rows x 128 B
+  static constexpr uint32_t mask_off = p_off + QT * S * 2;           // S floats
+  static constexpr uint32_t red_off = mask_off + S * 4;              // row max [S/128][128] then row sum [S/128][128]
+  static constexpr uint32_t bar_off = red_off + 2 * (S / 128) * QT * 4;
+  static constexpr uint32_t total = bar_off + 128 + 1024;            // + alignment slack
+};
+
+template <typename T, int S>
+__global__ void __launch_bounds__(32 * (S / 32 + 1), 1) attention_kernel(const __grid_constant__ AttnArgs args) {
+  constexpr int NG = S / 128;                 // column groups (softmax warps / 4)
+  constexpr int NSW = 4 * NG;                 // softmax warps
+  constexpr uint32_t TMEM_COLS = (S + DH) <= 256 ? 256u : 512u;
+  using L = AttnSmem<S>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + L::bar_off);
+  uint64_t* bar_v = bar_qk + 1;
+  uint64_t* bar_s = bar_qk + 2;               // MMA 1 complete
+  uint64_t* bar_p = bar_qk + 3;               // P written by all softmax warps
+  uint64_t* bar_o = bar_qk + 4;               // MMA 2 complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 5);
+  float* s_mask = reinterpret_cast<float*>(smem + L::mask_off);
+  float* s_max = reinterpret_cast<float*>(smem + L::red_off);
+  float* s_sum = s_max + NG * QT;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // tile -> (image, head, query tile); consecutive CTAs share K / V of one (image, head) in L2
+  const int qt = blockIdx.x % NG, nh = blockIdx.x / NG;
+  const int n = nh / args.H, h = nh - n * args.H;
+  const int row0 = nh * S + qt * QT;          // first row of the Q tile in the [N*H*S][64] matrices
+
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(bar_qk, 1);
+    ptx::mbar_init(bar_v, 1);
+    ptx::mbar_init(bar_s, 1);
+    ptx::mbar_init(bar_p, NSW);
+    ptx::mbar_init(bar_o, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == NSW) {
+    if (lane == 0) {
+      ptx::tma_prefetch_desc(&args.tm_q);
+      ptx::tma_prefetch_desc(&args.tm_k);
+      ptx::tma_prefetch_desc(&args.tm_v);
+      ptx::tma_prefetch_desc(&args.tm_y);
+    }
+    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  ptx::grid_dependency_wait();                // programmatic dependent launch: the Q / K / V producers have completed
+  ptx::grid_launch_dependents();
+
+  if (warp == NSW) {
+    // ===================== TMA + MMA issuer =====================
+    if (elect_one_sync()) {
+      ptx::mbar_arrive_expect_tx(bar_qk, (uint32_t)(QT * 128 + S * 128));
+      ptx::tma_load_2d(smem_base + L::q_off, &args.tm_q, bar_qk, 0, row0);
+      for (int b = 0; b < NG; ++b) ptx::tma_load_2d(smem_base + L::k_off + (uint32_t)b * (128 * 128), &args.tm_k, bar_qk, 0, nh * S + b * 128);
+      ptx::mbar_arrive_expect_tx(bar_v, (uint32_t)(S * 128));
+      for (int b = 0; b < NG; ++b) ptx::tma_load_2d(smem_base + L::v_off + (uint32_t)b * (128 * 128), &args.tm_v, bar_v, 0, nh * S + b * 128);
+      // ---- S = Q K^T: K-major A (Q) and B (K), N = 128 key rows per MMA ----
+      ptx::mbar_wait(bar_qk, 0);
+      ptx::tc_fence_after();
+      constexpr uint32_t idesc1 = ptx::make_idesc_f16(TcType<T>::is_bf16, QT, 128);
+#pragma unroll
+      for (int b = 0; b < NG; ++b) {
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) {
+          const uint64_t da = ptx::make_smem_desc_sw128(smem_base + L::q_off + (uint32_t)k * 32u);
+          const uint64_t db = ptx::make_smem_desc_sw128(smem_base + L::k_off + (uint32_t)b * (128 * 128) + (uint32_t)k * 32u);
+          ptx::umma_f16(tmem_base + (uint32_t)(b * 128), da, db, idesc1, k ? 1u : 0u);
+        }
+      }
+      ptx::umma_commit(bar_s);
+      // ---- O = P V: A = P (K-major, S/64 blocks of 128 x 64), B = V as [key][64] (MN-major: bit 16, 2048 B per K = 16 step) ----
+      ptx::mbar_wait(bar_v, 0);
+      ptx::mbar_wait(bar_p, 0);
+      ptx::tc_fence_after();
+      constexpr uint32_t idesc2 = ptx::make_idesc_f16(TcType<T>::is_bf16, QT, DH) | (1u << 16);
+#pragma unroll
+      for (int kb = 0; kb < S / 64; ++kb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = ptx::make_smem_desc_sw128(smem_base + L::p_off + (uint32_t)kb * (QT * 128) + (uint32_t)k * 32u);
+          const uint64_t db = ptx::make_smem_desc_sw128(smem_base + L::v_off + (uint32_t)kb * (64 * 128) + (uint32_t)k * 2048u);
+          ptx::umma_f16(tmem_base + (uint32_t)S, da, db, idesc2, (kb | k) ? 1u : 0u);
+        }
+      }
+      ptx::umma_commit(bar_o);
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax warps =====================
+    const int q = warp & 3, cg = warp >> 2;
+    const int row = q * 32 + lane;
+    // mask row of this image -> shared memory, fp32, in the log2 domain
+    {
+      const T* mrow = args.mask ? reinterpret_cast<const T*>(args.mask) + (size_t)(args.mask_batch > 1 ? n : 0) * S : nullptr;
+      for (int i = threadIdx.x; i < S; i += NSW * 32) s_mask[i] = mrow ? to_f32<T>(mrow[i]) * LOG2E : 0.f;
+      ptx::named_bar_sync(1, NSW * 32);
+    }
+    ptx::mbar_wait(bar_s, 0);
+    ptx::tc_fence_after();
+    float x[128];
+    {
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 128);
+      uint32_t(&xu)[128] = reinterpret_cast<uint32_t(&)[128]>(x);
+      ptx::tmem_ld_32x32(taddr, reinterpret_cast<uint32_t(&)[32]>(xu[0]));
+      ptx::tmem_ld_32x32(taddr + 32, reinterpret_cast<uint32_t(&)[32]>(xu[32]));
+      ptx::tmem_ld_32x32(taddr + 64, reinterpret_cast<uint32_t(&)[32]>(xu[64]));
+      ptx::tmem_ld_32x32(taddr + 96, reinterpret_cast<uint32_t(&)[32]>(xu[96]));
+      ptx::tmem_ld_wait();
+    }
+    const float sc = args.scale_log2;
+    float mx = -3.0e38f;
+    const uint32_t mask_addr = smem_base + L::mask_off + (uint32_t)(cg * 128) * 4u;
+#pragma unroll
+    for (int c = 0; c < 128; c += 4) {
+      const uint4 mv = ptx::ld_shared_v4(mask_addr + (uint32_t)c * 4u);     // same address in every lane: broadcast
+      x[c + 0] = fmaf(x[c + 0], sc, __uint_as_float(mv.x)); x[c + 1] = fmaf(x[c + 1], sc, __uint_as_float(mv.y));
+      x[c + 2] = fmaf(x[c + 2], sc, __uint_as_float(mv.z)); x[c + 3] = fmaf(x[c + 3], sc, __uint_as_float(mv.w));
+      mx = fmaxf(fmaxf(mx, fmaxf(x[c + 0], x[c + 1])), fmaxf(x[c + 2], x[c + 3]));
+    }
+    if (NG > 1) {
+      s_max[cg * QT + row] = mx;
+      ptx::named_bar_sync(1, NSW * 32);
+#pragma unroll
+      for (int g = 0; g < NG; ++g) mx = fmaxf(mx, s_max[g * QT + row]);
+    }
+    // P = 2^(x - max) as bf16/fp16, written as the K-major SWIZZLE_128B A operand: key column c lives in K-block c / 64 (128 rows x
+    // 128 B), 16-byte chunk (c % 64) / 8 XOR (row & 7) of this row
+    float sum = 0.f;
+    const uint32_t rsw = (uint32_t)(row & 7);
+#pragma unroll
+    for (int ch = 0; ch < 16; ++ch) {
+      float e[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { e[i] = ex2_approx(x[ch * 8 + i] - mx); }
+      const uint32_t p0 = pack2<T>(e[0], e[1]), p1 = pack2<T>(e[2], e[3]), p2 = pack2<T>(e[4], e[5]), p3 = pack2<T>(e[6], e[7]);
+      // the row sum is taken over the ROUNDED probabilities, the values the second MMA actually multiplies
+      float r0, r1;
+      unpack2<T>(p0, r0, r1); sum += r0 + r1;
+      unpack2<T>(p1, r0, r1); sum += r0 + r1;
+      unpack2<T>(p2, r0, r1); sum += r0 + r1;
+      unpack2<T>(p3, r0, r1); sum += r0 + r1;
+      const int col = cg * 128 + ch * 8;
+      const uint32_t dst = smem_base + L::p_off + (uint32_t)(col >> 6) * (QT * 128) + (uint32_t)row * 128u + ((((uint32_t)(col & 63) >> 3) ^ rsw) << 4);
+      ptx::st_shared_v4(dst, make_uint4(p0, p1, p2, p3));
+    }
+    s_sum[cg * QT + row] = sum;
+    ptx::fence_proxy_async();                 // P (generic-proxy stores) -> visible to the tensor core's async proxy
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(bar_p);
+    if (cg == 0) {
+      // ===================== output: O / sum -> bf16 -> staging (the Q tile's memory) -> TMA store into [N, S, H*64] =====================
+      ptx::mbar_wait(bar_o, 0);
+      ptx::tc_fence_after();
+      uint32_t o0[32], o1[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)S;
+      ptx::tmem_ld_32x32(taddr, o0);
+      ptx::tmem_ld_32x32(taddr + 32, o1);
+      float total = 0.f;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) total += s_sum[g * QT + row];
+      const float inv = 1.f / total;
+      ptx::tmem_ld_wait();
+      const uint32_t out_row = smem_base + L::q_off + (uint32_t)row * 128u;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const uint32_t* v = ch < 4 ? &o0[ch * 8] : &o1[(ch - 4) * 8];
+        const uint4 pk = make_uint4(pack2<T>(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv), pack2<T>(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv),
+                                    pack2<T>(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv), pack2<T>(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv));
+        ptx::st_shared_v4(out_row + (((uint32_t)ch ^ rsw) << 4), pk);
+      }
+      ptx::fence_proxy_async();
+      ptx::named_bar_sync(2, 128);
+      if (threadIdx.x == 0) {
+        ptx::tma_store_2d(&args.tm_y, smem_base + L::q_off, h * DH, n * S + qt * QT);
+        ptx::bulk_commit();
+        ptx::bulk_wait_all0();
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == NSW) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <typename K>
+void launch_attn_pdl(K kernel, int grid, int threads, unsigned smem, cudaStream_t s, const AttnArgs& a) {
+  static const bool pdl = [] { const char* e = getenv("B200_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
+template <typename T, int S>
+void launch_typed(const AttnArgs& a, cudaStream_t s) {
+  launch_attn_pdl(attention_kernel<T, S>, a.N * a.H * (S / 128), 32 * (S / 32 + 1), AttnSmem<S>::total, s, a);
+}
+template <typename T>
+void opt_in() {
+  cudaFuncSetAttribute(attention_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AttnSmem<128>::total);
+  cudaFuncSetAttribute(attention_kernel<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AttnSmem<256>::total);
+  cudaFuncSetAttribute(attention_kernel<T, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AttnSmem<384>::total);
+}
+
+}  // namespace
+
+void attention_init_device() {
+  opt_in<__nv_bfloat16>();
+  opt_in<__half>();
+}
+
+bool attention_supported(const AttnParams& p, int dtype) {
+  const char* off = getenv("B200_FUSED_ATTENTION");
+  if (off && off[0] == '0') return false;
+  return (dtype == B200_BF16 || dtype == B200_F16) && p.dh == DH && (p.S == 128 || p.S == 256 || p.S == 384) && p.N >= 1 && p.H >= 1 &&
+         (int64_t)p.N * p.H * p.S < ((int64_t)1 << 31) && (p.mask_batch == 1 || p.mask_batch == p.N || !p.mask);
+}
+
+void launch_attention(const AttnParams& p, int dtype, cudaStream_t s) {
+  B200_CHECK(attention_supported(p, dtype), B200_ERR_UNSUPPORTED, "fused attention: unsupported geometry");
+  const bool bf16 = dtype == B200_BF16;
+  AttnArgs a;
+  const uint64_t rows = (uint64_t)p.N * p.H * p.S;
+  a.tm_q = make_tmap_2d(p.q, bf16, DH, rows, DH * 2, DH, 128);
+  a.tm_k = make_tmap_2d(p.k, bf16, DH, rows, DH * 2, DH, 128);
+  a.tm_v = make_tmap_2d(p.v, bf16, DH, rows, DH * 2, DH, 128);
+  a.tm_y = make_tmap_2d(p.y, bf16, (uint64_t)p.H * DH, (uint64_t)p.N * p.S, (uint64_t)p.H * DH * 2, DH, 128);
+  a.mask = p.mask;
+  a.N = p.N; a.H = p.H; a.S = p.S; a.mask_batch = p.mask_batch;
+  a.scale_log2 = p.scale * LOG2E;
+#define B200_ATTN(T)                                      \
+  switch (p.S) {                                          \
+    case 128: launch_typed<T, 128>(a, s); break;          \
+    case 256: launch_typed<T, 256>(a, s); break;          \
+    default: launch_typed<T, 384>(a, s); break;           \
+  }
+  if (bf16) { B200_ATTN(__nv_bfloat16) } else { B200_ATTN(__half) }
+#undef B200_ATTN
+}
+
+}  // namespace b200

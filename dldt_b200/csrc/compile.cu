@@ -90,6 +90,13 @@ struct FusedSoftmax {
   float scale = 1.f;
   std::string fused;
 };
+// softmax(Q K^T * scale + mask) V (+ the merged-heads transpose) as ONE kernel (attention.cu); emitted at the context MatMul's position
+struct FusedAttn {
+  int q_value = -1, k_value = -1, v_value = -1, mask_value = -1;
+  float scale = 1.f;
+  int out_value = -1;
+  std::string fused;
+};
 struct FusedMvn {
   int root = -1;
   std::vector<int> absorbed;
@@ -124,6 +131,7 @@ class Lowerer {
   std::vector<int> absorbed_by_;                    // node -> fused record owner (-1 none)
   std::map<int, FusedConv> fconv_;                  // emit_at -> record
   std::map<int, FusedSoftmax> fsm_;                 // Softmax node id -> record
+  std::map<int, FusedAttn> fattn_;                  // emit_at -> record
   std::map<int, FusedMvn> fmvn_;
   std::map<int, FusedElt> felt_;
   std::map<int, int> box_dir_;                      // arena box -> 1 if its producer wrote it last-row-first
@@ -196,6 +204,8 @@ class Lowerer {
   void fuse();
   void fold_shortcuts();
   void fold_next_reduce();
+  void fold_attention();
+  void lower_attention(const FusedAttn& f);
   bool per_channel_const(int value, int64_t C, bool matmul_style, std::vector<float>& out) const;
   void lower_node(const Node& n);
   void lower_conv(const FusedConv& f);
@@ -614,6 +624,90 @@ void Lowerer::fuse() {
     }
   }
   fold_shortcuts();
+  fold_attention();
+}
+
+// Attention: MatMul(Q, K^T) -> [x scalar] -> [+ mask] -> Softmax(last axis) -> MatMul(P, V) -> Transpose (0,2,1,3), all on [N, H, S, 64]
+// tensors.  fuse() has already folded the scale / mask into the softmax record (fsm_) and the transpose into the context MatMul's stores
+// (FusedConv::heads_s); this pass replaces the three kernels by the fused one when attention.cu takes the geometry.  The [N,H,S,S]
+// scores then never exist in HBM.  B200_FUSED_ATTENTION=0 keeps the three kernels.
+void Lowerer::fold_attention() {
+  if (!use_tc_) return;
+  std::vector<int> erase;
+  for (auto& kv : fsm_) {
+    const Node& sm = node(kv.first);
+    const FusedSoftmax& fs = kv.second;
+    // producer of the scores: an activation x activation MatMul with transpose_b, nothing absorbed
+    const Value& xv = val(fs.x_value);
+    if (xv.producer < 0 || xv.consumers.size() != 1) continue;
+    FusedConv* mm1 = nullptr;
+    for (auto& c : fconv_) if (c.second.out_value == fs.x_value && c.second.root == xv.producer) mm1 = &c.second;
+    if (!mm1 || !mm1->absorbed.empty() || mm1->res_value >= 0) continue;
+    const Node& m1 = node(mm1->root);
+    if (m1.op != B200_OP_MATMUL || m1.i[0] != 0 || m1.i[1] != 1 || const_node(m1.inputs[0]) || const_node(m1.inputs[1])) continue;
+    // consumer of the probabilities: MatMul(P, V), P first, no transposes
+    const Value& pv = val(sm.outputs[0]);
+    if (pv.consumers.size() != 1) continue;
+    const Node& m2 = node(pv.consumers[0]);
+    if (m2.op != B200_OP_MATMUL || m2.inputs[0] != sm.outputs[0] || m2.i[0] != 0 || m2.i[1] != 0 || const_node(m2.inputs[1])) continue;
+    FusedConv* mm2 = nullptr;
+    for (auto& c : fconv_) if (c.second.root == m2.id) mm2 = &c.second;
+    if (!mm2 || mm2->res_value >= 0 || mm2->act1.kind != ACT_NONE || mm2->act2.kind != ACT_NONE) continue;
+    const Shape& qs = val(m1.inputs[0]).shape;
+    const Shape& ks = val(m1.inputs[1]).shape;
+    const Shape& vs = val(m2.inputs[1]).shape;
+    if (qs.size() != 4 || ks != qs || vs != qs) continue;
+    // the output must be the merged-heads layout [N, S, H, 64] (Transpose folded by fuse()): that is what the kernel stores
+    if (mm2->heads_s != (int)qs[2] || mm2->heads_h != (int)qs[1]) continue;
+    AttnParams ap{};
+    ap.N = (int)qs[0]; ap.H = (int)qs[1]; ap.S = (int)qs[2]; ap.dh = (int)qs[3];
+    ap.mask_batch = 1;
+    if (fs.mask_value >= 0) {
+      const Shape& ms = val(fs.mask_value).shape;
+      ap.mask_batch = (int)ms[0];
+      ap.mask = reinterpret_cast<const void*>(1);    // "present" for the support query
+    }
+    if (!attention_supported(ap, cd_)) continue;
+    FusedAttn fa;
+    fa.q_value = m1.inputs[0]; fa.k_value = m1.inputs[1]; fa.v_value = m2.inputs[1]; fa.mask_value = fs.mask_value;
+    fa.scale = fs.scale;
+    fa.out_value = mm2->out_value;
+    fa.fused = m1.name + "," + (fs.fused.empty() ? "" : fs.fused + ",") + sm.name + "," + m2.name;
+    for (int a : mm2->absorbed) fa.fused += "," + node(a).name;
+    const int emit_at = mm2->emit_at;
+    erase.push_back(mm1->emit_at);
+    erase.push_back(emit_at);
+    absorbed_by_[sm.id] = m2.id;      // the Softmax node itself is no longer lowered on its own
+    fattn_[emit_at] = fa;
+  }
+  for (int k : erase) fconv_.erase(k);
+}
+
+void Lowerer::lower_attention(const FusedAttn& f) {
+  LTensor q = get(f.q_value, L_ROWMAJOR), k = get(f.k_value, L_ROWMAJOR), v = get(f.v_value, L_ROWMAJOR);
+  LTensor mk;
+  if (f.mask_value >= 0) mk = get(f.mask_value, L_ROWMAJOR);
+  B200_CHECK(f.mask_value < 0 || mk.dtype == q.dtype, B200_ERR_UNSUPPORTED, "attention mask dtype differs from the scores'");
+  LTensor out = alloc(val(f.out_value).shape, cd_, L_ROWMAJOR);
+  AttnParams ap{};
+  ap.N = (int)q.shape[0]; ap.H = (int)q.shape[1]; ap.S = (int)q.shape[2]; ap.dh = (int)q.shape[3];
+  ap.mask_batch = f.mask_value >= 0 ? (int)mk.shape[0] : 1;
+  ap.scale = f.scale;
+  const bool has_mask = f.mask_value >= 0;
+  BufRef qr = q.buf, kr = k.buf, vr = v.buf, mr = mk.buf, yr = out.buf;
+  const int dt = cd_;
+  Step s;
+  s.name = val(f.out_value).name; s.type = "Attention"; s.impl = "tcgen05_fused_attention_s" + std::to_string(ap.S); s.fused = f.fused;
+  s.flops = 4.0 * ap.N * ap.H * (double)ap.S * ap.S * ap.dh;
+  s.bytes = (double)q.bytes() * 3 + (double)out.bytes();
+  s.launch = [=](const RunCtx& c) {
+    AttnParams p = ap;
+    p.q = c.ptr(qr); p.k = c.ptr(kr); p.v = c.ptr(vr); p.mask = has_mask ? c.ptr(mr) : nullptr; p.y = c.ptr(yr);
+    launch_attention(p, dt, (cudaStream_t)c.stream);
+  };
+  emit(std::move(s), {&q, &k, &v}, {&out});
+  if (has_mask && mk.buf.space == SP_ARENA) net_.steps.back().reads.push_back(mk.buf.box);   // emit() records three reads; the mask lives on too
+  set(f.out_value, out);
 }
 
 // ResNet downsampling block: out = ReLU(conv_c(b) + conv_proj(x)), both 1x1 with folded BN.  fuse() made conv_proj its own kernel and
@@ -1592,6 +1686,8 @@ void Lowerer::lower_detection(const Node& n) {
 
 void Lowerer::lower_node(const Node& n) {
   // fused records are emitted at the position of their last absorbed node
+  auto fat = fattn_.find(n.id);
+  if (fat != fattn_.end()) { lower_attention(fat->second); return; }
   auto fc = fconv_.find(n.id);
   if (fc != fconv_.end()) { lower_conv(fc->second); return; }
   auto fm = fmvn_.find(n.id);

@@ -345,6 +345,7 @@ int b200_compile(const b200_graph* g, const b200_compile_options* opts, b200_net
       conv_tc3_init_device();
       conv_tc3f_init_device();
       detect_init_device();
+      attention_init_device();
       size_t wb = std::max<size_t>(net->weights_host.size(), 16);
       B200_CUDA(cudaMalloc((void**)&net->weights_dev, wb));
       if (!net->weights_host.empty())

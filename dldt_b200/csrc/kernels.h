@@ -172,6 +172,17 @@ struct NmsParams {
 int64_t nms_workspace_bytes(int B, int C, int Nb, int max_out);
 void launch_nms(const NmsParams& p, cudaStream_t s);
 void nms_check(const NmsParams& p);                     // throws B200_ERR_UNSUPPORTED for geometry without a kernel (compile time)
+// ---- fused attention (attention.cu) ---------------------------------------------------------------
+struct AttnParams {
+  const void* q; const void* k; const void* v;   // [N, H, S, dh] in the compute type (head-split layout)
+  const void* mask;                              // [mask_batch, S] additive mask in the compute type, or null
+  void* y;                                       // [N, S, H * dh] (heads merged)
+  int N, H, S, dh, mask_batch;
+  float scale;
+};
+bool attention_supported(const AttnParams& p, int dtype);
+void launch_attention(const AttnParams& p, int dtype, cudaStream_t s);
+void attention_init_device();
 struct DetOutParams {
   const float* loc; const float* conf; const float* priors; float* out;
   int N, num_priors, num_classes, background, top_k, keep_top_k, code_center, share_location, var_in_target, normalized,

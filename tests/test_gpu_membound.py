@@ -184,3 +184,35 @@ def test_context_matmul_writes_the_merged_heads_layout(prec, tol, n, heads, seq,
     _, got1, eg1 = run(f, ins, prec)
     assert len([e for e in eg1 if e["type"] == "Transpose"]) == 2          # + V^T
     assert rel_l2(a, list(got1.values())[0]) < 2e-3
+
+
+@pytest.mark.parametrize("prec,tol", [("BF16", 1e-2), ("FP16", 2e-3)])
+@pytest.mark.parametrize("n,heads,seq,mask_batch", [(2, 3, 384, True), (1, 2, 128, False), (3, 4, 256, True), (2, 12, 384, True)])
+def test_fused_attention_kernel(prec, tol, n, heads, seq, mask_batch, monkeypatch):
+    """softmax(Q K^T / 8 + mask) V + merged-heads transpose as ONE tcgen05 kernel (attention.cu): scores in TMEM, P in shared memory, V read
+    MN-major.  Checked against the numpy restatement and against the three-kernel schedule of the same library; one padded sequence per
+    batch exercises the -10000 mask (whole key ranges with probability 0)."""
+    rng = np.random.default_rng(seq * heads + n)
+    f = Function("attention")
+    q = f.parameter((n, heads, seq, 64), name="q")
+    k = f.parameter((n, heads, seq, 64), name="k")
+    v = f.parameter((n, heads, seq, 64), name="v")
+    m = f.parameter((n if mask_batch else 1, 1, 1, seq), name="mask")
+    s = f.add(f.multiply(f.matmul(q, k, transpose_b=True), np.float32(0.125)), m)
+    c = f.matmul(f.softmax(s, 3), v)
+    f.result(f.reshape(f.transpose(c, (0, 2, 1, 3)), (n, seq, heads * 64)))
+    mask = np.zeros((n if mask_batch else 1, 1, 1, seq), np.float32)
+    mask[-1, 0, 0, seq - seq // 3:] = -10000.0
+    ins = {"q": rng.standard_normal((n, heads, seq, 64)).astype(np.float32) * 1.5, "k": rng.standard_normal((n, heads, seq, 64)).astype(np.float32) * 1.5,
+           "v": rng.standard_normal((n, heads, seq, 64)).astype(np.float32), "mask": mask}
+    ref, got, eg = run(f, ins, prec)
+    kinds = [e["type"] for e in eg]
+    assert kinds.count("Attention") == 1 and "MatMul" not in kinds and "Softmax" not in kinds and "Transpose" not in kinds, eg
+    a, b = list(got.values())[0], list(ref.values())[0]
+    assert a.shape == (n, seq, heads * 64) and np.isfinite(a).all()
+    assert rel_l2(a, b) < tol, rel_l2(a, b)
+    monkeypatch.setenv("B200_FUSED_ATTENTION", "0")
+    _, got0, eg0 = run(f, ins, prec)
+    assert [e["type"] for e in eg0].count("MatMul") == 2
+    # the fused kernel keeps the scores in fp32 until P is formed: it must not be further from the fp32 oracle than the unfused schedule
+    assert rel_l2(a, b) <= rel_l2(list(got0.values())[0], b) * 1.25 + 1e-4

@@ -134,7 +134,7 @@ def test_tiny_ssd_fp32():
     assert rel_l2(g[:, 2:], r[:, 2:]) < 1e-4
 
 
-@pytest.mark.parametrize("priors,classes,top_k,keep_top_k,n", [(8732, 21, 200, 200, 2), (3000, 81, 400, 100, 1), (700, 5, 64, -1, 3)])
+@pytest.mark.parametrize("priors,classes,top_k,keep_top_k,n", [(8732, 21, 200, 200, 2), (3000, 40, 400, 100, 1), (700, 5, 64, -1, 3)])
 def test_detection_output_select_path_equals_sort_path(priors, classes, top_k, keep_top_k, n, monkeypatch):
     """The radix-select + overlap-bitmask DetectionOutput (SSD sizes) against the full-sort fall-back of the same library and the
     numpy restatement, with heavily quantised scores so that equal scores are ordered by prior index on every path."""
