@@ -245,11 +245,19 @@ def run_b200(args, rank, local_rank, world):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # a second, CPU-only group for the long waits: an NCCL barrier parks a spinning kernel on every waiting rank's GPU, which would
+        # steal SMs from the one process that drives all N GPUs in the benchmark_app legs below
+        cpu_group = dist.new_group(backend="gloo")
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(local_rank)
+
+    def host_barrier():
+        torch.cuda.synchronize(local_rank)
+        if dist is not None:
+            dist.barrier(group=cpu_group)
 
     def max_over_ranks(v):
         if dist is None:
@@ -317,7 +325,7 @@ def run_b200(args, rank, local_rank, world):
     # ---- e2e through the drop-in boundary: the reference's own benchmark_app over libb200Plugin.so (rank 0; the other ranks idle) ----
     e2e_app, strong = None, None
     have_app = os.path.exists(BENCHMARK_APP) and os.path.exists(PLUGIN_SO)
-    barrier()
+    host_barrier()
     if rank == 0 and have_app and not args.no_benchmark_app:
         tmp = tempfile.mkdtemp(prefix="b200_bench_")
         xml = write_ir(B, tmp)
@@ -341,7 +349,7 @@ def run_b200(args, rank, local_rank, world):
                              "slices of %d images, one CUDA graph per GPU, gathered on completion" % (world, B, args.app_seconds, B, world, B // world)}
         except Exception as e:
             strong = {"value": None, "scaling": "strong", "error": str(e)[:300]}
-    barrier()
+    host_barrier()
     e2e_value = e2e_app["value"] if (e2e_app and e2e_app.get("value")) else e2e_mirror
 
     # ---- roofline of the dominant kernel class (tcgen05 implicit GEMM), CUDA events per launch ----
