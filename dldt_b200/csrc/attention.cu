@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(32 * (S / 32 + 1), 1) attention_kernel(const _
     ptx::mbar_init(bar_sfree, NSW);
     ptx::mbar_init(bar_p, NSW);
     ptx::mbar_init(bar_o, 1);
-    ptx::mbar_init(bar_ofree, 4);
+    ptx::mbar_init(bar_ofree, NG >= 2 ? 8 : 4);
     ptx::fence_mbar_init();
   }
   if (warp == NSW) {
@@ -211,10 +211,42 @@ __global__ void __launch_bounds__(32 * (S / 32 + 1), 1) attention_kernel(const _
     const float sc = args.scale_log2;
     const uint32_t rsw = (uint32_t)(row & 7);
     int cur_n = -1;
+    // ===================== output of tile ge: O / sum -> bf16 -> y[n][s][h][..]; column groups 0 (and 1) take 64 / EG columns each ============
+    constexpr int EG = NG >= 2 ? 2 : 1;       // warps that share the output work per lane quarter
+    constexpr int ECOLS = DH / EG;
+    auto epilogue = [&](int ge) {
+      if (cg >= EG) return;
+      const uint32_t phe = (uint32_t)ge & 1u;
+      const int nhe = (int)blockIdx.x + (ge / NG) * (int)gridDim.x, qte = ge % NG;
+      const int ne = nhe / args.H, he = nhe - ne * args.H;
+      ptx::mbar_wait(bar_o, phe);
+      ptx::tc_fence_after();
+      uint32_t o0[32], o1[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)S + (uint32_t)(cg * ECOLS);
+      ptx::tmem_ld_32x32(taddr, o0);
+      if (EG == 1) ptx::tmem_ld_32x32(taddr + 32, o1);
+      const float* e_sum = s_sum + phe * (NG * QT);
+      float total = 0.f;
+#pragma unroll
+      for (int gg = 0; gg < NG; ++gg) total += e_sum[gg * QT + row];
+      const float inv = 1.f / total;
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_ofree);   // MMA2 of the next tile may overwrite O
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<T*>(args.y) + ((size_t)(ne * S + qte * QT + row) * args.H + he) * DH + cg * ECOLS);
+#pragma unroll
+      for (int ch = 0; ch < ECOLS / 8; ++ch) {
+        const uint32_t* v = ch < 4 ? &o0[ch * 8] : &o1[(ch - 4) * 8];
+        dst[ch] = make_uint4(pack2<T>(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv), pack2<T>(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv),
+                             pack2<T>(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv), pack2<T>(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv));
+      }
+    };
     for (int g = 0; g < G; ++g) {
       const uint32_t ph = (uint32_t)g & 1u;
       const int nh = (int)blockIdx.x + (g / NG) * (int)gridDim.x, qt = g % NG;
-      const int n = nh / args.H, h = nh - n * args.H;
+      const int n = nh / args.H;
+      (void)qt;
       if (n != cur_n) {
         // mask row of this image -> shared memory, fp32, in the log2 domain (every warp is past the previous tile's mask reads: they
         // precede that tile's row-max barrier)
@@ -280,31 +312,11 @@ __global__ void __launch_bounds__(32 * (S / 32 + 1), 1) attention_kernel(const _
       ptx::fence_proxy_async();               // P (generic-proxy stores) -> visible to the tensor core's async proxy
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_p);
-      if (cg == 0) {
-        // ===================== output: O / sum -> bf16 -> y[n][s][h][0..63], one 128-byte row per thread =====================
-        ptx::mbar_wait(bar_o, ph);
-        ptx::tc_fence_after();
-        uint32_t o0[32], o1[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)S;
-        ptx::tmem_ld_32x32(taddr, o0);
-        ptx::tmem_ld_32x32(taddr + 32, o1);
-        float total = 0.f;
-#pragma unroll
-        for (int gg = 0; gg < NG; ++gg) total += t_sum[gg * QT + row];
-        const float inv = 1.f / total;
-        ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar_ofree);   // MMA2 of the next tile may overwrite O
-        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<T*>(args.y) + ((size_t)(n * S + qt * QT + row) * args.H + h) * DH);
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          const uint32_t* v = ch < 4 ? &o0[ch * 8] : &o1[(ch - 4) * 8];
-          dst[ch] = make_uint4(pack2<T>(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv), pack2<T>(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv),
-                               pack2<T>(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv), pack2<T>(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv));
-        }
-      }
+      // the output of the PREVIOUS tile: by now its MMA2 has long completed, so nobody waits for the tensor core here, and the next
+      // tile's LDTM / scale / max phase of every warp overlaps this tile's MMA2
+      if (g > 0) epilogue(g - 1);
     }
+    if (G > 0) epilogue(G - 1);
   }
   ptx::tc_fence_before();
   __syncthreads();

@@ -378,9 +378,19 @@ __device__ uint64_t radix_select_desc(KeyAt key_at, int n, int k, int nonzero, S
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sh.hist[i] = 0u;
     __syncthreads();
     const unsigned long long prefix = sh.prefix;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint64_t key = key_at(i);
-      if (key != 0ull && (shift == 56 || ((key ^ prefix) >> (shift + 8)) == 0ull)) atomicAdd(&sh.hist[(unsigned)(key >> shift) & 255u], 1u);
+    // warp-aggregated histogram: scores of one class crowd into a few bins (softmax outputs share their exponent; saturated heads give
+    // thousands of EQUAL scores), and 32 shared-memory atomics on one address serialise.  Lanes with the same digit elect one to add.
+    const int lane = threadIdx.x & 31;
+    for (int base = threadIdx.x - lane; base < n; base += blockDim.x) {
+      const int i = base + lane;
+      const uint64_t key = i < n ? key_at(i) : 0ull;
+      const bool counts = key != 0ull && (shift == 56 || ((key ^ prefix) >> (shift + 8)) == 0ull);
+      const unsigned digit = (unsigned)(key >> shift) & 255u;
+      const unsigned voters = __ballot_sync(0xffffffffu, counts);
+      if (counts) {
+        const unsigned peers = __match_any_sync(voters, digit);
+        if (lane == __ffs(peers) - 1) atomicAdd(&sh.hist[digit], (unsigned)__popc(peers));
+      }
     }
     __syncthreads();
     if (threadIdx.x < 32) {

@@ -102,9 +102,86 @@ __global__ void __launch_bounds__(256) dwconv3x3_strip_kernel(const uint2* __res
   }
 }
 
-// Dense convolution, Cin_p == 8 (one uint4 per input pixel), Cout_p % 8 == 0.  One thread = one output pixel x 8 output channels.
+// Stride-1 layers (13 of MobileNetV2's 17): the three input rows of the window stay UNPACKED in registers and roll down a strip of R
+// output rows - every input value is converted once (the strip kernel above re-converts a row for each of the three output rows that
+// use it), the next two input rows are in flight while a row is computed, and the activation is a branch-free clamp.  ncu on the strip
+// kernel: 49 % issue-slot utilisation at 24 % occupancy, 40 instructions per output value; this form needs ~16.
+template <typename T, int R>
+__global__ void __launch_bounds__(256, 2) dwconv3x3_roll_kernel(const uint2* __restrict__ x, const uint2* __restrict__ w, const float* __restrict__ bias,
+                                                             uint2* __restrict__ y, int H, int W, int cq, int Ho, int Wo, int strips, int pt, int pl, float lo,
+                                                             float hi, uint32_t total) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int Wo2 = (Wo + 1) >> 1;
+  const uint32_t c4 = idx % (uint32_t)cq;
+  uint32_t t = idx / (uint32_t)cq;
+  const int j = (int)(t % (uint32_t)Wo2);
+  t /= (uint32_t)Wo2;
+  const int strip = (int)(t % (uint32_t)strips);
+  const int n = (int)(t / (uint32_t)strips);
+  constexpr int NR = R + 2;
+  const uint2* xi = x + (size_t)n * H * W * cq + c4;
+  const int ho0 = strip * R;
+  const int c0 = 2 * j - pl, r0 = ho0 - pt;
+  bool cin[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) cin[c] = (unsigned)(c0 + c) < (unsigned)W;
+  auto load_row = [&](int i, uint2 (&dst)[4]) {      // input row r0 + i, columns c0 .. c0 + 3; outside the image: zeros
+    const int hi_ = r0 + i;
+    const bool rin = (unsigned)hi_ < (unsigned)H;
+    const uint2* row = xi + (size_t)(rin ? hi_ : 0) * W * cq;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dst[c] = (rin && cin[c]) ? __ldg(row + (size_t)(c0 + c) * cq) : make_uint2(0u, 0u);
+  };
+  uint2 first[3][4], pf[2][4];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) load_row(i, first[i]);
+  load_row(3, pf[0]);
+  if (NR > 4) load_row(4, pf[1]);
+  float wv[9][4];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) unpack4<T>(__ldg(w + (size_t)k * cq + c4), wv[k]);
+  const float4 bq = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+  float win[3][4][4];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) unpack4<T>(first[i][c], win[i][c]);
+  uint2* yo = y + (((size_t)n * Ho + ho0) * Wo + 2 * j) * cq + c4;
+  const bool second = 2 * j + 1 < Wo;
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    if (ho0 + k >= Ho) break;
+    float acc0[4] = {bq.x, bq.y, bq.z, bq.w}, acc1[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int slot = (k + r) % 3;
+#pragma unroll
+      for (int s_ = 0; s_ < 3; ++s_)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc0[e] = fmaf(win[slot][s_][e], wv[r * 3 + s_][e], acc0[e]);
+          acc1[e] = fmaf(win[slot][s_ + 1][e], wv[r * 3 + s_][e], acc1[e]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { acc0[e] = fminf(fmaxf(acc0[e], lo), hi); acc1[e] = fminf(fmaxf(acc1[e], lo), hi); }
+    yo[(size_t)k * Wo * cq] = pack4<T>(acc0);
+    if (second) yo[(size_t)k * Wo * cq + cq] = pack4<T>(acc1);
+    if (k + 1 < R) {
+      // row k + 3 arrives in the slot of row k; the prefetch buffer it came from takes row k + 5
+#pragma unroll
+      for (int c = 0; c < 4; ++c) unpack4<T>(pf[k & 1][c], win[k % 3][c]);
+      if (k + 5 < NR) load_row(k + 5, pf[k & 1]);
+    }
+  }
+}
+
+// Dense convolution, Cin_p == 8 (one uint4 per input pixel), Cout_p % 8 == 0.  One thread = PX horizontally adjacent output pixels x 8
+// output channels: a weight vector read from shared memory serves PX pixels.  (One pixel per thread saturated the shared-memory
+// pipe - ncu: L1/TEX 91 % busy, 97 M warp instructions, 145 us for MobileNetV2's first layer at batch 64.)
 // wsm: fp32 weights [tap][ci][Cout_p] for the CIN real input channels.
-template <typename T, int CIN>
+template <typename T, int CIN, int PX>
 __global__ void __launch_bounds__(256) conv_small_cin_kernel(const uint4* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
                                                              uint4* __restrict__ y, int N, int H, int W, int Ho, int Wo, int Cout_p, int ldy8, int kh, int kw,
                                                              int sh, int sw, int dh, int dw, int pt, int pl, int w_ld, int act, float aa, float ab,
@@ -118,46 +195,60 @@ __global__ void __launch_bounds__(256) conv_small_cin_kernel(const uint4* __rest
   __syncthreads();
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
+  const int Wg = (Wo + PX - 1) / PX;
   const int co8 = (int)(idx % (uint32_t)co8n);
   uint32_t t = idx / (uint32_t)co8n;
-  const int wo = (int)(t % (uint32_t)Wo);
-  t /= (uint32_t)Wo;
+  const int wg = (int)(t % (uint32_t)Wg);
+  t /= (uint32_t)Wg;
   const int ho = (int)(t % (uint32_t)Ho);
   const int n = (int)(t / (uint32_t)Ho);
-  float acc[8];
+  const int wo0 = wg * PX;
+  float acc[PX][8];
   {
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + co8 * 2), b1 = __ldg(reinterpret_cast<const float4*>(bias) + co8 * 2 + 1);
-    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      acc[p][0] = b0.x; acc[p][1] = b0.y; acc[p][2] = b0.z; acc[p][3] = b0.w; acc[p][4] = b1.x; acc[p][5] = b1.y; acc[p][6] = b1.z; acc[p][7] = b1.w;
+    }
   }
   const uint4* xi = x + (size_t)n * H * W;
   for (int r = 0; r < kh; ++r) {
     const int hi = ho * sh - pt + r * dh;
     if ((unsigned)hi >= (unsigned)H) continue;
     for (int s = 0; s < kw; ++s) {
-      const int wi = wo * sw - pl + s * dw;
-      if ((unsigned)wi >= (unsigned)W) continue;
-      const uint4 q = __ldg(xi + (size_t)hi * W + wi);
-      float v[8];
-      {
-        const uint2 lo = make_uint2(q.x, q.y), hi2 = make_uint2(q.z, q.w);
-        float a[4], b[4];
-        unpack4<T>(lo, a); unpack4<T>(hi2, b);
-        v[0] = a[0]; v[1] = a[1]; v[2] = a[2]; v[3] = a[3]; v[4] = b[0]; v[5] = b[1]; v[6] = b[2]; v[7] = b[3];
+      float v[PX][CIN];
+#pragma unroll
+      for (int p = 0; p < PX; ++p) {
+        const int wi = (wo0 + p) * sw - pl + s * dw;
+        const bool in = (unsigned)wi < (unsigned)W;
+        const uint4 q = in ? __ldg(xi + (size_t)hi * W + wi) : make_uint4(0u, 0u, 0u, 0u);
+        float a[4];
+        unpack4<T>(make_uint2(q.x, q.y), a);
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) v[p][ci] = a[ci];
       }
       const float* wt = wsm + (size_t)(r * kw + s) * CIN * Cout_p + co8 * 8;
 #pragma unroll
       for (int ci = 0; ci < CIN; ++ci) {
         const float4 w0 = *reinterpret_cast<const float4*>(wt + ci * Cout_p), w1 = *reinterpret_cast<const float4*>(wt + ci * Cout_p + 4);
-        acc[0] = fmaf(v[ci], w0.x, acc[0]); acc[1] = fmaf(v[ci], w0.y, acc[1]); acc[2] = fmaf(v[ci], w0.z, acc[2]); acc[3] = fmaf(v[ci], w0.w, acc[3]);
-        acc[4] = fmaf(v[ci], w1.x, acc[4]); acc[5] = fmaf(v[ci], w1.y, acc[5]); acc[6] = fmaf(v[ci], w1.z, acc[6]); acc[7] = fmaf(v[ci], w1.w, acc[7]);
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+          acc[p][0] = fmaf(v[p][ci], w0.x, acc[p][0]); acc[p][1] = fmaf(v[p][ci], w0.y, acc[p][1]); acc[p][2] = fmaf(v[p][ci], w0.z, acc[p][2]);
+          acc[p][3] = fmaf(v[p][ci], w0.w, acc[p][3]); acc[p][4] = fmaf(v[p][ci], w1.x, acc[p][4]); acc[p][5] = fmaf(v[p][ci], w1.y, acc[p][5]);
+          acc[p][6] = fmaf(v[p][ci], w1.z, acc[p][6]); acc[p][7] = fmaf(v[p][ci], w1.w, acc[p][7]);
+        }
       }
     }
   }
-  float lo[4], hi[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) { lo[e] = act_apply(acc[e], act, aa, ab); hi[e] = act_apply(acc[4 + e], act, aa, ab); }
-  const uint2 a = pack4<T>(lo), b = pack4<T>(hi);
-  y[(((size_t)n * Ho + ho) * Wo + wo) * ldy8 + co8] = make_uint4(a.x, a.y, b.x, b.y);
+  for (int p = 0; p < PX; ++p) {
+    if (wo0 + p >= Wo) break;
+    float lo[4], hi[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { lo[e] = act_apply(acc[p][e], act, aa, ab); hi[e] = act_apply(acc[p][4 + e], act, aa, ab); }
+    const uint2 a = pack4<T>(lo), b = pack4<T>(hi);
+    y[(((size_t)n * Ho + ho) * Wo + wo0 + p) * ldy8 + co8] = make_uint4(a.x, a.y, b.x, b.y);
+  }
 }
 
 }  // namespace
@@ -171,6 +262,26 @@ bool dwconv_strip_supported(const DwParams& p, int dtype) {
 
 void launch_dwconv_strip(const DwParams& p, int dtype, cudaStream_t s) {
   const int cq = p.Cp / 4, Wo2 = (p.Wo + 1) / 2;
+  {
+    // stride 1 with an activation that is a clamp (none / ReLU / Clamp - every MobileNet layer): the rolling-window kernel
+    const char* off = getenv("B200_DW_ROLL");
+    const bool clampish = p.act == ACT_NONE || p.act == ACT_RELU || p.act == ACT_CLAMP;
+    if (p.sh == 1 && clampish && !(off && off[0] == '0')) {
+      const float lo = p.act == ACT_NONE ? -3.4e38f : (p.act == ACT_RELU ? 0.f : p.a), hi = p.act == ACT_CLAMP ? p.b : 3.4e38f;
+      const int R = p.Ho >= 16 ? 8 : (p.Ho >= 8 ? 4 : 2);
+      const int strips = (p.Ho + R - 1) / R;
+      const int64_t total = (int64_t)p.N * strips * Wo2 * cq;
+      B200_CHECK(total > 0 && total < ((int64_t)1 << 31) && (int64_t)p.N * p.H * p.W * cq < ((int64_t)1 << 40), B200_ERR_UNSUPPORTED, "depthwise convolution too large");
+      const unsigned grid = (unsigned)((total + 255) / 256);
+#define B200_DWR(T, R_)                                                                                                                        \
+  dwconv3x3_roll_kernel<T, R_><<<grid, 256, 0, s>>>((const uint2*)p.x, (const uint2*)p.w, p.bias, (uint2*)p.y, p.H, p.W, cq, p.Ho, p.Wo, strips, p.pt, p.pl, \
+                                                    lo, hi, (uint32_t)total)
+      if (dtype == B200_BF16) { if (R == 8) B200_DWR(__nv_bfloat16, 8); else if (R == 4) B200_DWR(__nv_bfloat16, 4); else B200_DWR(__nv_bfloat16, 2); }
+      else { if (R == 8) B200_DWR(__half, 8); else if (R == 4) B200_DWR(__half, 4); else B200_DWR(__half, 2); }
+#undef B200_DWR
+      return;
+    }
+  }
   // rows per strip: 4 at stride 1 (6 x 4 vectors in flight per thread), 2 at stride 2 (5 x 5); short maps keep the strip count >= 2
   const int R = p.sh == 1 ? (p.Ho >= 8 ? 4 : 2) : 2;
   const int strips = (p.Ho + R - 1) / R;
@@ -201,11 +312,12 @@ bool conv_small_cin_supported(const ConvParams& p, int cin, int dtype) {
 
 void launch_conv_small_cin(const ConvParams& p, int cin, int dtype, cudaStream_t s) {
   B200_CHECK(conv_small_cin_supported(p, cin, dtype), B200_ERR_UNSUPPORTED, "conv_small_cin: unsupported launch");
-  const int64_t total = (int64_t)p.M * (p.Cout_p / 8);
+  constexpr int PX = 4;
+  const int64_t total = (int64_t)p.N * p.Ho * ((p.Wo + PX - 1) / PX) * (p.Cout_p / 8);
   const unsigned grid = (unsigned)((total + 255) / 256);
   const size_t smem = (size_t)p.kh * p.kw * cin * p.Cout_p * 4;
 #define B200_SC(T, C_)                                                                                                                             \
-  conv_small_cin_kernel<T, C_><<<grid, 256, smem, s>>>((const uint4*)p.x, (const T*)p.w, p.bias, (uint4*)p.y, p.N, p.H, p.W, p.Ho, p.Wo, p.Cout_p, p.ldy / 8, \
+  conv_small_cin_kernel<T, C_, PX><<<grid, 256, smem, s>>>((const uint4*)p.x, (const T*)p.w, p.bias, (uint4*)p.y, p.N, p.H, p.W, p.Ho, p.Wo, p.Cout_p, p.ldy / 8, \
                                                        p.kh, p.kw, p.sh, p.sw, p.dh, p.dw, p.pt, p.pl, p.w_ld, p.act1, p.a1, p.b1, (uint32_t)total)
 #define B200_SC_T(T)                                                                     \
   switch (cin) {                                                                         \
