@@ -171,16 +171,22 @@ __global__ void __launch_bounds__(32 * (S / 32 + 1), 1) attention_kernel(const _
       ptx::mbar_wait(bar_qk, 0);
       ptx::tc_fence_after();
       mma1();
+      if (G > 1) {                            // Q(1) goes out as soon as MMA1(0) has read Q(0): a TMA round trip ahead of its use
+        ptx::mbar_wait(bar_q1, 0);
+        load_qk(1);
+      }
       uint32_t n_v = 0;                       // V loads consumed so far (phase of bar_v)
       for (int g = 0; g < G; ++g) {
         const uint32_t ph = (uint32_t)g & 1u;
         if (g + 1 < G) {
-          ptx::mbar_wait(bar_q1, ph);         // MMA1(g) has read Q (and K): prefetch the next tile's
-          load_qk(g + 1);
           ptx::mbar_wait(bar_sfree, ph);      // S(g) is in registers: the accumulator may be overwritten
           ptx::mbar_wait(bar_qk, ph ^ 1u);
           ptx::tc_fence_after();
           mma1();
+          if (g + 2 < G) {                    // prefetch the tile after next the moment MMA1(g+1) has read Q (and K)
+            ptx::mbar_wait(bar_q1, ph ^ 1u);
+            load_qk(g + 2);
+          }
         }
         // ---- O = P V: A = P (K-major, S/64 blocks of 128 x 64), B = V as [key][64] (MN-major: bit 16, 2048 B per K = 16 step) ----
         if (g % NG == 0) { ptx::mbar_wait(bar_v, n_v & 1u); ++n_v; }

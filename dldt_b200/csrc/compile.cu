@@ -1770,7 +1770,7 @@ void Lowerer::lower_node(const Node& n) {
       int dt = x.dtype;
       Step s;
       s.name = n.name; s.type = "Softmax"; s.fused = n.name;
-      s.impl = inner == 1 ? ((softmax_fused_supported(axis, dt) && axis >= 64) ? "softmax_warp_rows" : "softmax_rows") : "softmax_strided";
+      s.impl = inner == 1 ? ((softmax_fused_supported(axis, dt) && axis >= 64) ? "softmax_warp_rows" : (axis <= 128 ? "softmax_short_rows" : "softmax_rows")) : "softmax_strided";
       s.bytes = 2.0 * (double)x.bytes();
       s.launch = [=](const RunCtx& c) { launch_softmax(c.ptr(xr), c.ptr(yr), outer, axis, inner, dt, (cudaStream_t)c.stream); };
       emit(std::move(s), {&x}, {&out});

@@ -582,6 +582,41 @@ __global__ void softmax_rows_kernel(const T* __restrict__ x, T* __restrict__ y, 
   float inv = 1.f / s;
   for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) stf<T>(py, c, expf(ldf<T>(px, c) - m) * inv);
 }
+// Short rows (SSD's per-prior class scores: 81 columns, 279 k rows at batch 32): one WARP per row, the row in registers (<= 4 values per
+// lane), one read and one write per element.  The block-per-row kernel above launched one 32-thread block per row and read it three times.
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_short_rows_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int cols) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const T* px = x + row * cols;
+  T* py = y + row * cols;
+  float v[4];
+  float m = -FLT_MAX;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = lane + 32 * k;
+    v[k] = c < cols ? ldf<T>(px, c) : -FLT_MAX;
+    m = fmaxf(m, v[k]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    v[k] = (lane + 32 * k) < cols ? expf(v[k] - m) : 0.f;
+    sum += v[k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = lane + 32 * k;
+    if (c < cols) stf<T>(py, c, v[k] * inv);
+  }
+}
+
 template <typename T>
 __global__ void softmax_strided_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t outer, int64_t axis, int64_t inner) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1090,6 +1125,10 @@ void launch_softmax(const void* x, void* y, int64_t outer, int64_t axis, int64_t
   if (outer * axis * inner == 0) return;
   if (inner == 1 && softmax_fused_supported(axis, dtype) && axis >= 64) {   // warp per row, one read + one write per element
     launch_softmax_scale_mask(x, nullptr, y, outer, axis, 1.f, 1, dtype, s);
+    return;
+  }
+  if (inner == 1 && axis <= 128) {
+    B200_DISPATCH_FLOAT(dtype, T, (softmax_short_rows_kernel<T><<<(unsigned)((outer + 7) / 8), 256, 0, s>>>((const T*)x, (T*)y, outer, (int)axis)));
     return;
   }
   if (inner == 1) {
