@@ -73,6 +73,9 @@ SYMBOLS = {
     "b200_network_num_exec_nodes": (C.c_int, [_P]),
     "b200_network_exec_node": (C.c_int, [_P, C.c_int, C.POINTER(ExecNodeInfo)]),
     "b200_network_stat": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double)]),
+    "b200_device_alloc": (C.c_int, [C.c_int, C.POINTER(_P), C.c_size_t]),
+    "b200_device_free": (C.c_int, [C.c_int, _P]),
+    "b200_device_copy": (C.c_int, [C.c_int, _P, _P, C.c_size_t, C.c_int]),
     "b200_network_tune": (C.c_int, [_P]),
     "b200_network_get_tuning": (C.c_int, [_P, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "b200_network_set_tuning": (C.c_int, [_P, C.c_char_p]),

@@ -1628,13 +1628,13 @@ void Lowerer::lower_detection(const Node& n) {
     LTensor o0 = alloc(val(n.outputs[0]).shape, B200_I32, L_ROWMAJOR), o1 = alloc(val(n.outputs[1]).shape, B200_F32, L_ROWMAJOR),
             o2 = alloc(val(n.outputs[2]).shape, B200_I32, L_ROWMAJOR);
     nms_check(p);     // unsupported geometry fails LoadNetwork / QueryNetwork, not the first inference
-    int64_t wsb = nms_workspace_bytes(p.B, p.C, p.Nb, p.max_out);
+    int64_t wsb = nms_workspace_bytes(p.B, p.C, p.Nb, p.max_out, p.soft_sigma > 0.f);
     Shape wshape = {wsb};
     LTensor ws = alloc(wshape, B200_U8, L_ROWMAJOR);
     p.workspace_bytes = wsb;
     BufRef br = boxes.buf, sr = scores.buf, r0 = o0.buf, r1 = o1.buf, r2 = o2.buf, wr = ws.buf;
     Step s;
-    s.name = n.name; s.type = "NonMaxSuppression"; s.impl = "nms5_sort_greedy"; s.fused = n.name;
+    s.name = n.name; s.type = "NonMaxSuppression"; s.impl = p.soft_sigma > 0.f ? "nms5_soft_queue" : "nms5_sort_greedy"; s.fused = n.name;
     s.bytes = (double)boxes.bytes() + (double)scores.bytes();
     s.launch = [=](const RunCtx& c) {
       NmsParams q = p;

@@ -316,6 +316,32 @@ int b200_host_unregister(void* ptr) {
   });
 }
 
+int b200_device_alloc(int device, void** dptr, size_t bytes) {
+  return guarded([&] {
+    B200_CHECK(dptr, B200_ERR_INVALID, "null argument");
+    B200_CUDA(cudaSetDevice(device));
+    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 16);
+    if (e != cudaSuccess) { cudaGetLastError(); B200_THROW(B200_ERR_OOM, "cannot allocate " << bytes << " bytes of device memory"); }
+    return (int)B200_OK;
+  });
+}
+int b200_device_free(int device, void* dptr) {
+  return guarded([&] {
+    if (!dptr) return (int)B200_OK;
+    B200_CUDA(cudaSetDevice(device));
+    B200_CUDA(cudaFree(dptr));
+    return (int)B200_OK;
+  });
+}
+int b200_device_copy(int device, void* dst, const void* src, size_t bytes, int direction) {
+  return guarded([&] {
+    B200_CHECK(dst && src, B200_ERR_INVALID, "null argument");
+    B200_CUDA(cudaSetDevice(device));
+    B200_CUDA(cudaMemcpy(dst, src, bytes, direction == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost));
+    return (int)B200_OK;
+  });
+}
+
 int b200_compile(const b200_graph* g, const b200_compile_options* opts, b200_network** out) {
   return guarded([&] {
     B200_CHECK(g && opts && out, B200_ERR_INVALID, "null argument");
@@ -511,12 +537,12 @@ int b200_request_start(b200_request* req, const void* const* host_inputs, void* 
     req->finalize();
     for (size_t i = 0; i < req->in_dev.size(); ++i) {
       B200_CHECK(host_inputs && host_inputs[i], B200_ERR_INVALID, "missing host input " << i);
-      B200_CUDA(cudaMemcpyAsync(req->in_dev[i], host_inputs[i], (size_t)req->in_fmt[i].bytes, cudaMemcpyHostToDevice, req->stream));
+      B200_CUDA(cudaMemcpyAsync(req->in_dev[i], host_inputs[i], (size_t)req->in_fmt[i].bytes, cudaMemcpyDefault, req->stream));
     }
     launch_graph_or_eager(req);
     for (size_t i = 0; i < req->out_dev.size(); ++i) {
       B200_CHECK(host_outputs && host_outputs[i], B200_ERR_INVALID, "missing host output " << i);
-      B200_CUDA(cudaMemcpyAsync(host_outputs[i], req->out_dev[i], (size_t)req->out_fmt[i].bytes, cudaMemcpyDeviceToHost, req->stream));
+      B200_CUDA(cudaMemcpyAsync(host_outputs[i], req->out_dev[i], (size_t)req->out_fmt[i].bytes, cudaMemcpyDefault, req->stream));
     }
     B200_CUDA(cudaEventRecord(req->done, req->stream));
     req->started = true;
@@ -587,12 +613,12 @@ int b200_request_time(b200_request* req, int iters, int mode, const void* const*
     for (int it = 0; it < iters; ++it) {
       if (mode == 1) {
         for (size_t i = 0; i < req->in_dev.size(); ++i)
-          B200_CUDA(cudaMemcpyAsync(req->in_dev[i], host_inputs[i], (size_t)req->in_fmt[i].bytes, cudaMemcpyHostToDevice, req->stream));
+          B200_CUDA(cudaMemcpyAsync(req->in_dev[i], host_inputs[i], (size_t)req->in_fmt[i].bytes, cudaMemcpyDefault, req->stream));
       }
       launch_graph_or_eager(req);
       if (mode == 1) {
         for (size_t i = 0; i < req->out_dev.size(); ++i)
-          B200_CUDA(cudaMemcpyAsync(host_outputs[i], req->out_dev[i], (size_t)req->out_fmt[i].bytes, cudaMemcpyDeviceToHost, req->stream));
+          B200_CUDA(cudaMemcpyAsync(host_outputs[i], req->out_dev[i], (size_t)req->out_fmt[i].bytes, cudaMemcpyDefault, req->stream));
       }
     }
     B200_CUDA(cudaEventRecord(e1, req->stream));

@@ -169,7 +169,7 @@ struct NmsParams {
   int B, C, Nb, max_out, center_format, sort_desc; float iou_thr, score_thr, soft_sigma;
   void* workspace; int64_t workspace_bytes;
 };
-int64_t nms_workspace_bytes(int B, int C, int Nb, int max_out);
+int64_t nms_workspace_bytes(int B, int C, int Nb, int max_out, bool soft = false);
 void launch_nms(const NmsParams& p, cudaStream_t s);
 void nms_check(const NmsParams& p);                     // throws B200_ERR_UNSUPPORTED for geometry without a kernel (compile time)
 // ---- fused attention (attention.cu) ---------------------------------------------------------------

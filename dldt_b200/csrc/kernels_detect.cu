@@ -107,8 +107,80 @@ __global__ void nms_select_kernel(NmsParams p, int n_pad, int32_t* sel, int32_t*
   }
 }
 
-// single block: gather, (optionally) global sort, write padded outputs
-__global__ void nms_finalize_kernel(NmsParams p, const int32_t* sel, const int32_t* cnt, uint64_t* keys, int n_pad, int64_t out_rows) {
+// Soft-NMS (soft_nms_sigma > 0): nodes/mkldnn_non_max_suppression_node.cpp:275-334.  The reference pops a priority queue (score
+// descending, index ascending), decays the popped score by exp(scale * iou^2) against the boxes selected since the box was last looked
+// at (suppress_begin_index), and either selects the box (score unchanged), re-inserts it (decayed, still above the threshold) or drops it.
+// One block per (batch, class): the pop is a block-wide arg-max over the current scores (kept in the workspace), the inherently serial
+// decay loop runs on thread 0.
+__global__ void nms_soft_select_kernel(NmsParams p, float scale, float* cur, int32_t* sbi, int32_t* sel, float* sel_sc, int32_t* cnt) {
+  __shared__ unsigned long long s_warp[32];
+  __shared__ unsigned long long s_top;
+  __shared__ int s_nsel;
+  const int b = blockIdx.x / p.C;
+  const float* scores = p.scores + (int64_t)blockIdx.x * p.Nb;
+  const float* boxes = p.boxes + (int64_t)b * p.Nb * 4;
+  float* my_cur = cur + (int64_t)blockIdx.x * p.Nb;
+  int32_t* my_sbi = sbi + (int64_t)blockIdx.x * p.Nb;
+  int32_t* my_sel = sel + (int64_t)blockIdx.x * p.max_out;
+  float* my_sc = sel_sc + (int64_t)blockIdx.x * p.max_out;
+  for (int i = threadIdx.x; i < p.Nb; i += blockDim.x) {
+    const float v = scores[i];
+    my_cur[i] = v > p.score_thr ? v : -INFINITY;
+    my_sbi[i] = 0;
+  }
+  if (threadIdx.x == 0) s_nsel = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  while (true) {
+    unsigned long long best = 0ull;
+    for (int i = threadIdx.x; i < p.Nb; i += blockDim.x) {
+      const float v = my_cur[i];
+      if (v > -INFINITY) best = max(best, (unsigned long long)make_key(v, (uint32_t)i));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) s_warp[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long top = 0ull;
+      for (int w = 0; w < nwarps; ++w) top = max(top, s_warp[w]);
+      int nsel = s_nsel;
+      if (top != 0ull && nsel < p.max_out) {
+        const int idx = (int)key_idx(top);
+        float score = my_cur[idx];
+        const float orig = score;
+        bool selected = true;
+        for (int k = nsel - 1; k >= my_sbi[idx]; --k) {
+          const float iou = nms_iou(boxes + (int64_t)idx * 4, boxes + (int64_t)my_sel[k] * 4, p.center_format);
+          const float weight = iou <= p.iou_thr ? expf(scale * iou * iou) : 0.0f;
+          score *= weight;
+          if (iou >= p.iou_thr) { selected = false; break; }
+          if (score <= p.score_thr) break;
+        }
+        my_sbi[idx] = nsel;
+        if (selected && score == orig) {
+          my_sel[nsel] = idx; my_sc[nsel] = score;
+          s_nsel = nsel + 1;
+          my_cur[idx] = -INFINITY;
+        } else if (selected && score > p.score_thr) {
+          my_cur[idx] = score;            // back into the queue with the decayed score
+        } else {
+          my_cur[idx] = -INFINITY;
+        }
+      } else {
+        top = 0ull;
+      }
+      s_top = top;
+    }
+    __syncthreads();
+    if (s_top == 0ull) break;
+  }
+  if (threadIdx.x == 0) cnt[blockIdx.x] = s_nsel;
+}
+
+// single block: gather, (optionally) global sort, write padded outputs.  sel_sc: scores of the selections (soft-NMS decays them), or null
+__global__ void nms_finalize_kernel(NmsParams p, const int32_t* sel, const int32_t* cnt, uint64_t* keys, int n_pad, int64_t out_rows, const float* sel_sc,
+                                    float* out_sc) {
   __shared__ int s_total;
   const int BC = p.B * p.C;
   if (threadIdx.x == 0) {
@@ -125,7 +197,8 @@ __global__ void nms_finalize_kernel(NmsParams p, const int32_t* sel, const int32
     for (int i = 0; i < bc; ++i) base += cnt[i];
     for (int k = 0; k < cnt[bc]; ++k) {
       int box = sel[(int64_t)bc * p.max_out + k];
-      float sc = p.scores[(int64_t)bc * p.Nb + box];
+      float sc = sel_sc ? sel_sc[(int64_t)bc * p.max_out + k] : p.scores[(int64_t)bc * p.Nb + box];
+      if (out_sc) out_sc[(int64_t)bc * p.Nb + box] = sc;       // decayed score, addressable by (batch, class, box) after the sort
       uint32_t lin = (uint32_t)((int64_t)bc * p.Nb + box);
       keys[base + k] = p.sort_desc ? make_key(sc, lin) : (((uint64_t)(0xFFFFFFFFu - (uint32_t)(base + k))) << 32) | (uint64_t)lin;
     }
@@ -140,7 +213,8 @@ __global__ void nms_finalize_kernel(NmsParams p, const int32_t* sel, const int32
       int bc = (int)(lin / (uint32_t)p.Nb);
       int bb = bc / p.C, cc = bc % p.C;
       p.sel_idx[r * 3 + 0] = bb; p.sel_idx[r * 3 + 1] = cc; p.sel_idx[r * 3 + 2] = box;
-      p.sel_scores[r * 3 + 0] = (float)bb; p.sel_scores[r * 3 + 1] = (float)cc; p.sel_scores[r * 3 + 2] = p.scores[(int64_t)bc * p.Nb + box];
+      p.sel_scores[r * 3 + 0] = (float)bb; p.sel_scores[r * 3 + 1] = (float)cc;
+      p.sel_scores[r * 3 + 2] = out_sc ? out_sc[(int64_t)bc * p.Nb + box] : p.scores[(int64_t)bc * p.Nb + box];
     } else {
       p.sel_idx[r * 3 + 0] = -1; p.sel_idx[r * 3 + 1] = -1; p.sel_idx[r * 3 + 2] = -1;
       p.sel_scores[r * 3 + 0] = -1.f; p.sel_scores[r * 3 + 1] = -1.f; p.sel_scores[r * 3 + 2] = -1.f;
@@ -665,11 +739,13 @@ void detect_init_device() {
   cudaFuncSetAttribute(detout_keep_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
-int64_t nms_workspace_bytes(int B, int C, int Nb, int max_out) {
+int64_t nms_workspace_bytes(int B, int C, int Nb, int max_out, bool soft) {
   int64_t sel = round_up((int64_t)B * C * max_out * 4, 256);
   int64_t cnt = round_up((int64_t)B * C * 4, 256);
   int64_t keys = (int64_t)next_pow2((int)std::min<int64_t>((int64_t)B * C * max_out, 1 << 30)) * 8;
-  return sel + cnt + keys + 1024;
+  // soft-NMS: current score + suppress_begin_index + decayed score per (batch, class, box), decayed score per selection
+  int64_t soft_bytes = soft ? 3 * round_up((int64_t)B * C * Nb * 4, 256) + round_up((int64_t)B * C * max_out * 4, 256) : 0;
+  return sel + cnt + keys + soft_bytes + 1024;
 }
 
 void launch_nms(const NmsParams& p, cudaStream_t s) {
@@ -681,11 +757,23 @@ void launch_nms(const NmsParams& p, cudaStream_t s) {
   int32_t* cnt = (int32_t*)(ws + off);
   off += round_up((int64_t)p.B * p.C * 4, 256);
   uint64_t* keys = (uint64_t*)(ws + off);
-  const int n_pad = next_pow2(std::max(p.Nb, 2));
-  nms_select_kernel<<<p.B * p.C, 512, (size_t)n_pad * 8, s>>>(p, n_pad, sel, cnt);
   const int64_t out_rows = (int64_t)p.B * p.C * p.max_out;
   const int tot_pad = next_pow2((int)std::max<int64_t>(out_rows, 2));
-  nms_finalize_kernel<<<1, 1024, 0, s>>>(p, sel, cnt, keys, tot_pad, out_rows);
+  if (p.soft_sigma > 0.f) {
+    off += (int64_t)tot_pad * 8;
+    const int64_t per = round_up((int64_t)p.B * p.C * p.Nb * 4, 256);
+    float* cur = (float*)(ws + off); off += per;
+    int32_t* sbi = (int32_t*)(ws + off); off += per;
+    float* out_sc = (float*)(ws + off); off += per;
+    float* sel_sc = (float*)(ws + off);
+    const float scale = (float)(-0.5 / p.soft_sigma);      // mkldnn_non_max_suppression_node.cpp:158-160
+    nms_soft_select_kernel<<<p.B * p.C, 256, 0, s>>>(p, scale, cur, sbi, sel, sel_sc, cnt);
+    nms_finalize_kernel<<<1, 1024, 0, s>>>(p, sel, cnt, keys, tot_pad, out_rows, sel_sc, out_sc);
+    return;
+  }
+  const int n_pad = next_pow2(std::max(p.Nb, 2));
+  nms_select_kernel<<<p.B * p.C, 512, (size_t)n_pad * 8, s>>>(p, n_pad, sel, cnt);
+  nms_finalize_kernel<<<1, 1024, 0, s>>>(p, sel, cnt, keys, tot_pad, out_rows, nullptr, nullptr);
 }
 
 int64_t detout_workspace_bytes(const DetOutParams& p) {
@@ -710,7 +798,7 @@ void detection_output_check(const DetOutParams& p) {
              "DetectionOutput: num_classes*top_k > " << SORT_MAX);
 }
 void nms_check(const NmsParams& p) {
-  B200_CHECK(p.soft_sigma == 0.f, B200_ERR_UNSUPPORTED, "NonMaxSuppression: soft_nms_sigma > 0 is not supported");
+  B200_CHECK(p.soft_sigma >= 0.f, B200_ERR_INVALID, "NonMaxSuppression: negative soft_nms_sigma");
   B200_CHECK(p.Nb <= SORT_MAX, B200_ERR_UNSUPPORTED, "NonMaxSuppression: more than " << SORT_MAX << " boxes per batch");
   B200_CHECK((int64_t)p.B * p.C * p.Nb < (1ll << 32), B200_ERR_UNSUPPORTED, "NonMaxSuppression: problem too large");
 }

@@ -176,6 +176,13 @@ B200_API int b200_host_free(void* ptr);
 B200_API int b200_host_register(void* ptr, size_t bytes);
 B200_API int b200_host_unregister(void* ptr);
 
+/* ---- device memory for remote blobs (inference-engine/include/ie_remote_context.hpp:58-178): the pointers b200_request_start takes
+ * may be DEVICE addresses (any GPU of the box), in which case the "copy" is device to device and nothing crosses PCIe.
+ * direction: 0 = host -> device, 1 = device -> host; synchronous. */
+B200_API int b200_device_alloc(int device, void** dptr, size_t bytes);
+B200_API int b200_device_free(int device, void* dptr);
+B200_API int b200_device_copy(int device, void* dst, const void* src, size_t bytes, int direction);
+
 /* ---- graph construction (host only, no CUDA) -------------------------------------------- */
 B200_API int b200_graph_create(const char* name, b200_graph** out);
 B200_API void b200_graph_destroy(b200_graph* g);
@@ -221,7 +228,8 @@ B200_API int b200_request_set_io_format(b200_request* req, int is_output, int in
 B200_API int b200_request_io_bytes(const b200_request* req, int is_output, int index, uint64_t* bytes);
 /* Enqueue H2D of every input from host_inputs[i], the captured CUDA graph, and D2H of every output
  * into host_outputs[i] on the request's stream.  Returns immediately. Host buffers should be pinned
- * (b200_host_alloc / b200_host_register) for the copies to be asynchronous. */
+ * (b200_host_alloc / b200_host_register) for the copies to be asynchronous; device addresses (b200_device_alloc,
+ * or any CUDA allocation of this process) are accepted too (unified addressing picks the copy direction). */
 B200_API int b200_request_start(b200_request* req, const void* const* host_inputs, void* const* host_outputs);
 /* Block until the request's stream is drained.  timeout_ms < 0: forever; 0: poll. */
 B200_API int b200_request_wait(b200_request* req, int64_t timeout_ms);

@@ -76,7 +76,7 @@ def run(func, inputs, return_all=False):
         elif n.op == "NonMaxSuppression":
             c = n.ir_consts
             out = list(ops.non_max_suppression(x[0], x[1], int(c[0]), float(c[1]), float(c[2]), a["box_encoding"] == "center",
-                                               a["sort_result_descending"] == "true"))
+                                               a["sort_result_descending"] == "true", float(c[3]) if len(c) > 3 else 0.0))
         elif n.op == "DetectionOutput":
             t = lambda k: a[k] == "true"
             out = [ops.detection_output(x[0], x[1], x[2], a["num_classes"], a["background_label_id"], a["top_k"], a["keep_top_k"][0],

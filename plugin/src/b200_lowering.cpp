@@ -63,6 +63,44 @@ std::shared_ptr<ngraph::Function> TransformNetwork(const std::shared_ptr<const n
     return f;
 }
 
+void AddMeanScale(const std::shared_ptr<ngraph::Function>& function, const InferenceEngine::InputsDataMap& inputs) {
+    for (const auto& param : function->get_parameters()) {
+        auto it = inputs.find(param->get_friendly_name());
+        if (it == inputs.end()) continue;
+        const InferenceEngine::PreProcessInfo& info = it->second->getPreProcess();
+        const size_t channels = info.getNumberOfChannels();
+        if (channels == 0) continue;
+        std::vector<float> mean(channels), scale(channels);
+        bool has_mean = false, has_scale = false;
+        for (size_t c = 0; c < channels; ++c) {
+            if (info[c]->meanData) IE_THROW(NotImplemented) << "B200 plugin: mean-image pre-processing of input '" << it->first << "' is not supported (use mean values)";
+            mean[c] = info[c]->meanValue;
+            scale[c] = info[c]->stdScale;
+            has_mean = has_mean || mean[c] != 0.f;
+            has_scale = has_scale || scale[c] != 1.f;
+        }
+        if (!has_mean && !has_scale) continue;
+        const auto& shape = param->get_shape();
+        if (shape.size() < 2 || shape[1] != channels) IE_THROW(ParameterMismatch) << "B200 plugin: " << channels << " pre-processing channels for input '" << it->first << "'";
+        ngraph::Shape cshape(shape.size(), 1);
+        cshape[1] = channels;
+        const auto consumers = param->output(0).get_target_inputs();
+        // (x - mean) / scale as ONE per-channel scale + shift: BatchNormInference with gamma 1, beta 0, variance scale^2, eps 0 - the
+        // compiler runs it as a single channels-last kernel (a Subtract + Divide pair would be two kernels and a layout conversion)
+        std::vector<float> ones(channels, 1.f), zeros(channels, 0.f), var(channels);
+        for (size_t c = 0; c < channels; ++c) var[c] = scale[c] * scale[c];
+        const ngraph::Shape vshape{channels};
+        auto bn = std::make_shared<ngraph::opset5::BatchNormInference>(param->output(0), ngraph::opset1::Constant::create(ngraph::element::f32, vshape, ones),
+                                                                      ngraph::opset1::Constant::create(ngraph::element::f32, vshape, zeros),
+                                                                      ngraph::opset1::Constant::create(ngraph::element::f32, vshape, mean),
+                                                                      ngraph::opset1::Constant::create(ngraph::element::f32, vshape, var), 0.0);
+        bn->set_friendly_name(param->get_friendly_name() + "/mean_scale");
+        ngraph::Output<ngraph::Node> cur = bn->output(0);
+        (void)cshape;
+        for (auto consumer : consumers) consumer.replace_source_output(cur);
+    }
+}
+
 std::shared_ptr<ngraph::Function> ShardBatch(const std::shared_ptr<const ngraph::Function>& function, size_t shards) {
     auto f = ngraph::clone_function(*function);
     if (shards <= 1) return f;

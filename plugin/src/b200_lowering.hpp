@@ -5,6 +5,7 @@
 #include <memory>
 #include <string>
 
+#include <ie_input_info.hpp>
 #include <ngraph/function.hpp>
 
 #include "b200.h"
@@ -19,6 +20,12 @@ std::shared_ptr<ngraph::Function> TransformNetwork(const std::shared_ptr<const n
 // re-shaped, Reshape target-shape constants that spell the batch out are rewritten, and the clone is re-validated node by node (the
 // plugin-side analogue of CNNNetwork::setBatchSize / reshape).  Throws ParameterMismatch if the batch does not divide.
 std::shared_ptr<ngraph::Function> ShardBatch(const std::shared_ptr<const ngraph::Function>& function, size_t shards);
+
+// PreProcessInfo mean / scale (ie_preprocess.hpp:23-40: per-channel meanValue and stdScale) become (x - mean) / scale nodes behind the
+// Parameter, so they run on the device inside the request's CUDA graph (the CPU plugin normalises in MKLDNNGraph::PushInputData,
+// mkldnn_graph.cpp:708-760; the template plugin inserts the same nodes, docs/template_plugin/src/transformations/preprocessing).
+// Resize and colour conversion stay with the reference's host pre-processing library.  Mean IMAGES are refused (NotImplemented).
+void AddMeanScale(const std::shared_ptr<ngraph::Function>& function, const InferenceEngine::InputsDataMap& inputs);
 
 // true if `node` (after TransformNetwork) maps onto a b200_op; `why` receives the reason otherwise.
 bool IsNodeSupported(const std::shared_ptr<ngraph::Node>& node, std::string* why = nullptr);

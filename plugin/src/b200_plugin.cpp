@@ -194,7 +194,44 @@ IExecutableNetworkInternal::Ptr Plugin::LoadExeNetworkImpl(const CNNNetwork& net
             IE_THROW(NotImplemented) << "B200 plugin: input '" << in.first << "' has unsupported precision " << p;
     }
     Configuration cfg{config, _cfg};
-    return std::make_shared<ExecutableNetwork>(function, cfg, std::static_pointer_cast<Plugin>(shared_from_this()));
+    return std::make_shared<ExecutableNetwork>(function, network.getInputsInfo(), cfg, std::static_pointer_cast<Plugin>(shared_from_this()));
+}
+
+// ---- remote context (ie_remote_context.hpp:58-178; the Core forwards Core::CreateContext / GetDefaultContext / LoadNetwork(net, ctx)) -------
+std::shared_ptr<InferenceEngine::RemoteContext> Plugin::CreateContext(const ParamMap& params) {
+    int device = _cfg.devices.front();
+    auto it = params.find(B200_PARAM_DEVICE_ID);
+    if (it != params.end()) {
+        if (it->second.is<int>()) device = it->second.as<int>();
+        else device = std::stoi(it->second.as<std::string>());
+    }
+    int count = 0;
+    b200_device_count(&count);
+    if (device < 0 || device >= count) IE_THROW(NotFound) << "B200 plugin: no device " << device << " for a remote context (" << count << " devices)";
+    return std::make_shared<RemoteContext>(device);
+}
+
+std::shared_ptr<InferenceEngine::RemoteContext> Plugin::GetDefaultContext(const ParamMap& params) {
+    int device = _cfg.devices.front();
+    auto it = params.find(B200_PARAM_DEVICE_ID);
+    if (it != params.end()) device = it->second.is<int>() ? it->second.as<int>() : std::stoi(it->second.as<std::string>());
+    std::lock_guard<std::mutex> lk(_ctxMutex);
+    auto& ctx = _defaultContexts[device];
+    if (!ctx) ctx = std::dynamic_pointer_cast<RemoteContext>(CreateContext({{B200_PARAM_DEVICE_ID, device}}));
+    return ctx;
+}
+
+IExecutableNetworkInternal::Ptr Plugin::LoadExeNetworkImpl(const CNNNetwork& network, const std::shared_ptr<InferenceEngine::RemoteContext>& context,
+                                                           const std::map<std::string, std::string>& config) {
+    auto ctx = std::dynamic_pointer_cast<RemoteContext>(context);
+    if (!ctx) IE_THROW(ParameterMismatch) << "B200 plugin: LoadNetwork was given a remote context of another device";
+    auto cfg = config;
+    cfg[CONFIG_KEY(DEVICE_ID)] = std::to_string(ctx->device());     // the network is compiled for the context's device
+    return LoadExeNetworkImpl(network, cfg);
+}
+
+std::shared_ptr<InferenceEngine::RemoteContext> ExecutableNetwork::GetContext() const {
+    return _pluginRef->GetDefaultContext({{B200_PARAM_DEVICE_ID, _cfg.devices.front()}});
 }
 
 // ---- Export / Import (docs/template_plugin/src/template_executable_network.cpp:179-200, template_plugin.cpp:108-112; the Core drives
@@ -239,6 +276,14 @@ void ExecutableNetwork::Export(std::ostream& model) {
         putString(model, in.first);
         putInt(model, static_cast<int32_t>(in.second->getPrecision()));
         putInt(model, static_cast<int32_t>(in.second->getLayout()));
+        // PreProcessInfo mean values / scales (they are part of what was compiled: AddMeanScale)
+        const PreProcessInfo& pre = in.second->getPreProcess();
+        const int32_t channels = static_cast<int32_t>(pre.getNumberOfChannels());
+        putInt(model, channels);
+        for (int32_t c = 0; c < channels; ++c) {
+            const float mv[2] = {pre[c]->meanValue, pre[c]->stdScale};
+            model.write(reinterpret_cast<const char*>(mv), sizeof(mv));
+        }
     }
     putInt(model, static_cast<int32_t>(_networkOutputs.size()));
     for (const auto& out : _networkOutputs) {
@@ -273,11 +318,18 @@ IExecutableNetworkInternal::Ptr Plugin::ImportNetwork(std::istream& model, const
     const std::string list = getString(model);
     if (!list.empty()) storedDevices[B200ConfigParams::KEY_B200_DEVICES] = list;
     std::vector<std::tuple<std::string, int, int>> ins;
+    std::vector<std::vector<float>> inMeanScale;
     std::vector<std::pair<std::string, int>> outs;
     for (int k = 0, n = getInt(model); k < n; ++k) {
         std::string name = getString(model);
         const int prec = getInt(model), layout = getInt(model);
         ins.emplace_back(name, prec, layout);
+        const int channels = getInt(model);
+        if (channels < 0 || channels > 65536) IE_THROW(NetworkNotRead) << "B200 plugin: corrupt exported network";
+        std::vector<float> ms(static_cast<size_t>(2 * channels));
+        if (channels) model.read(reinterpret_cast<char*>(ms.data()), static_cast<std::streamsize>(ms.size() * sizeof(float)));
+        if (!model) IE_THROW(NetworkNotRead) << "B200 plugin: truncated exported network";
+        inMeanScale.push_back(std::move(ms));
     }
     for (int k = 0, n = getInt(model); k < n; ++k) {
         std::string name = getString(model);
@@ -301,13 +353,25 @@ IExecutableNetworkInternal::Ptr Plugin::ImportNetwork(std::istream& model, const
         if (it == network.getInputsInfo().end()) IE_THROW(NetworkNotRead) << "B200 plugin: exported network names an unknown input '" << std::get<0>(in) << "'";
         it->second->setPrecision(Precision(static_cast<Precision::ePrecision>(std::get<1>(in))));
         it->second->setLayout(static_cast<Layout>(std::get<2>(in)));
+        const auto& ms = inMeanScale[static_cast<size_t>(&in - &ins[0])];
+        if (!ms.empty()) {
+            PreProcessInfo& pre = it->second->getPreProcess();
+            pre.init(ms.size() / 2);
+            bool any = false;
+            for (size_t c = 0; c < ms.size() / 2; ++c) {
+                pre[c]->meanValue = ms[2 * c];
+                pre[c]->stdScale = ms[2 * c + 1];
+                any = any || ms[2 * c] != 0.f || ms[2 * c + 1] != 1.f;
+            }
+            if (any) pre.setVariant(MEAN_VALUE);
+        }
     }
     for (const auto& out : outs) {
         auto it = network.getOutputsInfo().find(out.first);
         if (it == network.getOutputsInfo().end()) IE_THROW(NetworkNotRead) << "B200 plugin: exported network names an unknown output '" << out.first << "'";
         it->second->setPrecision(Precision(static_cast<Precision::ePrecision>(out.second)));
     }
-    auto exe = std::make_shared<ExecutableNetwork>(network.getFunction(), cfg, std::static_pointer_cast<Plugin>(shared_from_this()), tuning);
+    auto exe = std::make_shared<ExecutableNetwork>(network.getFunction(), network.getInputsInfo(), cfg, std::static_pointer_cast<Plugin>(shared_from_this()), tuning);
     exe->setNetworkInputs(network.getInputsInfo());
     exe->setNetworkOutputs(network.getOutputsInfo());
     exe->SetPointerToPlugin(shared_from_this());
@@ -358,13 +422,14 @@ QueryNetworkResult Plugin::QueryNetwork(const CNNNetwork& network, const std::ma
 }
 
 // ---- executable network -----------------------------------------------------------------------------------------------
-ExecutableNetwork::ExecutableNetwork(const std::shared_ptr<const ngraph::Function>& function, const Configuration& cfg, const std::shared_ptr<Plugin>& plugin,
-                                     const std::string& tuning)
+ExecutableNetwork::ExecutableNetwork(const std::shared_ptr<const ngraph::Function>& function, const InputsDataMap& inputs, const Configuration& cfg,
+                                     const std::shared_ptr<Plugin>& plugin, const std::string& tuning)
     : ExecutableNetworkThreadSafeDefault(nullptr, nullptr), _cfg(cfg), _pluginRef(plugin), _name(function->get_friendly_name()) {
     _function = ngraph::clone_function(*function);
     const int shards = static_cast<int>(cfg.devices.size());
     // batch sharding: the replica every device runs is the same function at batch N / G (ShardBatch re-validates the clone)
-    auto replica = shards > 1 ? ShardBatch(function, static_cast<size_t>(shards)) : _function;
+    auto replica = shards > 1 ? ShardBatch(function, static_cast<size_t>(shards)) : ngraph::clone_function(*function);
+    AddMeanScale(replica, inputs);      // PreProcessInfo mean / scale run on the device (Export keeps the network as loaded)
     auto transformed = TransformNetwork(replica);
     b200_graph* graph = LowerFunction(transformed);
     std::string table = tuning;
@@ -555,6 +620,11 @@ int BlobLayout(const TensorDesc& desc, const std::string& name) {
 }
 
 const void* BlobData(const Blob::Ptr& blob) {
+    if (auto remote = std::dynamic_pointer_cast<RemoteBlob>(blob)) {
+        // a blob that lives in HBM (b200_remote.hpp): the C ABI takes the device address, the "copy" is device to device
+        if (!remote->devicePtr()) IE_THROW(NotAllocated) << "B200 plugin: remote blob has no device memory";
+        return remote->devicePtr();
+    }
     auto mem = as<MemoryBlob>(blob);
     if (!mem) IE_THROW(NotImplemented) << "B200 plugin: only MemoryBlob inputs/outputs are supported";
     return mem->rmap().as<const uint8_t*>();   // includes the ROI / padding offset of the descriptor
@@ -676,6 +746,8 @@ void InferRequest::preprocessAndStart() {
         const uint64_t expect = _outShardBytes[k] * (plan.kind == IoPlan::Replicated ? 1 : shards);
         if (blob->byteSize() != expect)
             IE_THROW(ParameterMismatch) << "B200 plugin: output blob '" << _outputNames[k] << "' has " << blob->byteSize() << " bytes, the network produces " << expect;
+        if (plan.kind == IoPlan::Detections && blob->is<InferenceEngine::RemoteBlob>())
+            IE_THROW(NotImplemented) << "B200 plugin: a sharded DetectionOutput is re-packed on the host and cannot land in a remote blob";
         outBase[k] = const_cast<uint8_t*>(static_cast<const uint8_t*>(BlobData(blob)));
         pinUserMemory(outBase[k], blob->byteSize());
         _mergeDst[k] = outBase[k];

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "b200.h"
+#include "b200_remote.hpp"
 
 namespace B200Plugin {
 
@@ -55,7 +56,12 @@ public:
                                                      const std::map<std::string, std::string>& config) const override;
     InferenceEngine::IExecutableNetworkInternal::Ptr LoadExeNetworkImpl(const InferenceEngine::CNNNetwork& network,
                                                                         const std::map<std::string, std::string>& config) override;
+    InferenceEngine::IExecutableNetworkInternal::Ptr LoadExeNetworkImpl(const InferenceEngine::CNNNetwork& network,
+                                                                        const std::shared_ptr<InferenceEngine::RemoteContext>& context,
+                                                                        const std::map<std::string, std::string>& config) override;
     InferenceEngine::IExecutableNetworkInternal::Ptr ImportNetwork(std::istream& model, const std::map<std::string, std::string>& config) override;
+    std::shared_ptr<InferenceEngine::RemoteContext> CreateContext(const InferenceEngine::ParamMap& params) override;
+    std::shared_ptr<InferenceEngine::RemoteContext> GetDefaultContext(const InferenceEngine::ParamMap& params) override;
     void AddExtension(const std::shared_ptr<InferenceEngine::IExtension>& extension) override;
 
     InferenceEngine::ITaskExecutor::Ptr waitExecutor() const { return _waitExecutor; }
@@ -63,6 +69,8 @@ public:
 private:
     Configuration _cfg;
     InferenceEngine::ITaskExecutor::Ptr _waitExecutor;
+    std::mutex _ctxMutex;
+    std::map<int, std::shared_ptr<RemoteContext>> _defaultContexts;   // one per device
 };
 
 // How one network input / output maps onto the per-device replicas
@@ -73,8 +81,8 @@ struct IoPlan {
 
 class ExecutableNetwork : public InferenceEngine::ExecutableNetworkThreadSafeDefault {
 public:
-    ExecutableNetwork(const std::shared_ptr<const ngraph::Function>& function, const Configuration& cfg, const std::shared_ptr<Plugin>& plugin,
-                      const std::string& tuning = std::string());
+    ExecutableNetwork(const std::shared_ptr<const ngraph::Function>& function, const InferenceEngine::InputsDataMap& inputs, const Configuration& cfg,
+                      const std::shared_ptr<Plugin>& plugin, const std::string& tuning = std::string());
     ~ExecutableNetwork();
 
     InferenceEngine::IInferRequestInternal::Ptr CreateInferRequestImpl(InferenceEngine::InputsDataMap networkInputs,
@@ -84,6 +92,7 @@ public:
     InferenceEngine::Parameter GetConfig(const std::string& name) const override;
     InferenceEngine::CNNNetwork GetExecGraphInfo() override;
     void Export(std::ostream& model) override;
+    std::shared_ptr<InferenceEngine::RemoteContext> GetContext() const override;
 
     int numShards() const { return static_cast<int>(_nets.size()); }
     b200_network* handle(int shard = 0) const { return _nets[shard]; }

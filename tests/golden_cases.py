@@ -300,12 +300,12 @@ def _boxes(r, b, n, center):
     return _f32(np.concatenate([xy, xy + wh], axis=2))
 
 
-def _nms_case(name, b, c, n, max_out, iou, score_thr, center=False, sort=True, ties=False):
+def _nms_case(name, b, c, n, max_out, iou, score_thr, center=False, sort=True, ties=False, soft=0.0):
     r = _rng(name)
     f = Function(name)
     boxes = f.parameter((b, n, 4), name="boxes")
     scores = f.parameter((b, c, n), name="scores")
-    i, s, v = f.non_max_suppression(boxes, scores, max_out, iou, score_thr, 0.0, "center" if center else "corner", sort, name="nms")
+    i, s, v = f.non_max_suppression(boxes, scores, max_out, iou, score_thr, soft, "center" if center else "corner", sort, name="nms")
     f.result(i)
     f.result(s)
     f.result(v)
@@ -323,6 +323,10 @@ def nms_center_unsorted(): return _nms_case("nms_center_unsorted", 1, 2, 45, 6, 
 def nms_score_ties(): return _nms_case("nms_score_ties", 2, 2, 50, 8, 0.5, 0.25, ties=True)
 @case
 def nms_keep_nothing(): return _nms_case("nms_keep_nothing", 1, 1, 20, 5, 0.5, 2.0)
+@case
+def nms_soft_sigma(): return _nms_case("nms_soft_sigma", 2, 2, 40, 12, 0.6, 0.15, soft=0.5)
+@case
+def nms_soft_center_unsorted(): return _nms_case("nms_soft_center_unsorted", 1, 3, 30, 8, 0.5, 0.1, center=True, sort=False, soft=0.25)
 
 
 def _detout_case(name, n, priors, classes, top_k, keep_top_k, center=True, share=True, var_in_target=False, clip=False, conf_thr=0.05):

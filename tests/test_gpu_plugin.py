@@ -132,3 +132,35 @@ def test_reference_benchmark_app_full_size_resnet50(tmp_path):
     fps_all, _ = _benchmark_app(xml, "B200.ALL", ["-t", "3"])
     print("benchmark_app -d B200.ALL -b 256: %.0f FPS" % fps_all)
     assert fps_all > 20000
+
+
+@needs_ref
+@pytest.mark.parametrize("case", ["net_tiny_resnet", "net_tiny_bert"])
+def test_remote_context_and_remote_blobs(case):
+    """Core::GetDefaultContext("B200") -> LoadNetwork(net, context) -> RemoteContext::CreateBlob for every input and output (device memory,
+    filled through wmap(), read through rmap()): same result as with host blobs, nothing crosses PCIe inside the request."""
+    f, inputs = golden_cases.CASES[case]()
+    host, _ = refrun.run(f, inputs, device="B200", config={"B200_INFERENCE_PRECISION": "FP32"})
+    dev, _ = refrun.run(f, inputs, device="B200", config={"B200_INFERENCE_PRECISION": "FP32"}, niter=2, extra=["--remote"])
+    assert set(host) == set(dev)
+    for k in host:
+        np.testing.assert_array_equal(dev[k], host[k])
+
+
+@needs_ref
+def test_mean_scale_preprocessing_runs_on_the_device(tmp_path):
+    """PreProcessInfo mean values / scales set through the API: the CPU plugin normalises in PushInputData, the B200 plugin compiles
+    (x - mean) / scale into the request's CUDA graph; U8 input, same numbers (fp32 mode).  The settings survive Export / Import."""
+    f = zoo.resnet50(batch=2, image=64, width=16, blocks=(1, 1, 1, 1), num_classes=24)
+    x = np.random.default_rng(5).integers(0, 256, (2, 3, 64, 64), dtype=np.uint8)
+    ms = {"data": ([123.675, 116.28, 103.53], [58.395, 57.12, 57.375])}
+    ref, _ = refrun.run(f, {"data": x}, device="CPU", input_precisions={"data": "U8"}, mean_scale=ms)
+    plain, _ = refrun.run(f, {"data": x}, device="CPU", input_precisions={"data": "U8"})
+    assert np.abs(ref["fc_bias"] - plain["fc_bias"]).max() > 1e-3                # the pre-processing does something
+    blob = str(tmp_path / "net.blob")
+    got, _ = refrun.run(f, {"data": x}, device="B200", config={"B200_INFERENCE_PRECISION": "FP32"}, input_precisions={"data": "U8"}, mean_scale=ms,
+                        extra=["--export", blob])
+    a, b = got["fc_bias"], ref["fc_bias"]
+    assert np.linalg.norm(a - b) / np.linalg.norm(b) < 1e-4
+    again, _ = refrun.run(f, {"data": x}, device="B200", extra=["--import", blob])
+    np.testing.assert_array_equal(again["fc_bias"], a)

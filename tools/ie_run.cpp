@@ -28,10 +28,10 @@ static std::vector<std::string> split(const std::string& s, char d) {
 
 int main(int argc, char** argv) {
   std::string model, device = "CPU", outdir = ".", plugins_xml;
-  std::map<std::string, std::string> config, inputs, in_prec;
+  std::map<std::string, std::string> config, inputs, in_prec, mean_scale;
   std::string export_path, import_path, cache_dir;
   int niter = 1;
-  bool query = false, dry = false, user_blobs = false, cancel = false, callback = false;
+  bool query = false, dry = false, user_blobs = false, cancel = false, callback = false, remote = false;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
     auto next = [&]() { return std::string(i + 1 < argc ? argv[++i] : ""); };
@@ -46,11 +46,13 @@ int main(int argc, char** argv) {
     else if (a == "--import") import_path = next();   // Core::ImportNetwork(file, device, config) instead of ReadNetwork + LoadNetwork
     else if (a == "--cache-dir") cache_dir = next();  // Core::SetConfig({CACHE_DIR}): the Core drives Export / ImportNetwork itself
     else if (a == "--user-blobs") user_blobs = true;  // inputs and outputs in caller-owned (pageable) memory through SetBlob
+    else if (a == "--remote") remote = true;          // RemoteContext + RemoteBlob inputs and outputs (device memory, filled / read through wmap / rmap)
     else if (a == "--cancel") cancel = true;          // StartAsync, Cancel, Wait: the status is written to the manifest
     else if (a == "--callback") callback = true;      // SetCompletionCallback: the number of calls is written to the manifest
     else if (a == "--config") { for (auto& kv : split(next(), ',')) { auto p = kv.find('='); if (p != std::string::npos) config[kv.substr(0, p)] = kv.substr(p + 1); } }
     else if (a == "--config-kv") { auto kv = next(); auto p = kv.find('='); if (p != std::string::npos) config[kv.substr(0, p)] = kv.substr(p + 1); }  // one key whose value has commas
     else if (a == "--input") { auto kv = next(); auto p = kv.find('='); inputs[kv.substr(0, p)] = kv.substr(p + 1); }
+    else if (a == "--mean-scale") { auto kv = next(); auto p = kv.find('='); mean_scale[kv.substr(0, p)] = kv.substr(p + 1); }   // name=m0:m1:m2/s0:s1:s2 (PreProcessInfo)
     else if (a == "--input-precision") { auto kv = next(); auto p = kv.find('='); in_prec[kv.substr(0, p)] = kv.substr(p + 1); }
     else { std::cerr << "unknown argument " << a << "\n"; return 2; }
   }
@@ -63,6 +65,15 @@ int main(int argc, char** argv) {
       for (auto& in : net.getInputsInfo()) {
         auto it = in_prec.find(in.first);
         if (it != in_prec.end()) in.second->setPrecision(Precision::FromStr(it->second));
+        auto ms = mean_scale.find(in.first);
+        if (ms != mean_scale.end()) {
+          auto halves = split(ms->second, '/');
+          auto means = split(halves.at(0), ':'), scales = split(halves.at(1), ':');
+          PreProcessInfo& pre = in.second->getPreProcess();
+          pre.init(means.size());
+          for (size_t c = 0; c < means.size(); ++c) { pre[c]->meanValue = std::stof(means[c]); pre[c]->stdScale = std::stof(scales.at(c)); }
+          pre.setVariant(MEAN_VALUE);
+        }
       }
     }
     if (query) {
@@ -80,7 +91,10 @@ int main(int argc, char** argv) {
       return 0;
     }
     auto t0 = std::chrono::steady_clock::now();
-    ExecutableNetwork exe = import_path.empty() ? core.LoadNetwork(net, device, config) : core.ImportNetwork(import_path, device, config);
+    RemoteContext::Ptr ctx;
+    if (remote) ctx = core.GetDefaultContext(device);
+    ExecutableNetwork exe = remote ? core.LoadNetwork(net, ctx, config)
+                                   : (import_path.empty() ? core.LoadNetwork(net, device, config) : core.ImportNetwork(import_path, device, config));
     if (!export_path.empty()) exe.Export(export_path);
     if (dry) {
       unsigned nireq = exe.GetMetric(EXEC_NETWORK_METRIC_KEY(OPTIMAL_NUMBER_OF_INFER_REQUESTS)).as<unsigned>();
@@ -124,6 +138,11 @@ int main(int argc, char** argv) {
         user_mem.emplace_back(n);
         req.SetBlob(out.first, make_blob_with_precision(d, user_mem.back().data()));
       }
+    }
+    if (remote) {
+      if (exe.GetContext()->getDeviceName() != ctx->getDeviceName()) { std::cerr << "executable network reports another context\n"; return 2; }
+      for (auto& in : exe.GetInputsInfo()) req.SetBlob(in.first, ctx->CreateBlob(in.second->getTensorDesc()));
+      for (auto& out : exe.GetOutputsInfo()) req.SetBlob(out.first, ctx->CreateBlob(out.second->getTensorDesc()));
     }
     int callbacks = 0;
     if (callback) req.SetCompletionCallback([&callbacks] { ++callbacks; });

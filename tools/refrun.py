@@ -18,7 +18,7 @@ def available():
     return os.path.exists(IE_RUN) and os.path.exists(os.path.join(REF, "lib", "libMKLDNNPlugin.so"))
 
 
-def run(func, inputs, device="CPU", config=None, input_precisions=None, niter=1, workdir=None, config_kv=None, extra=None):
+def run(func, inputs, device="CPU", config=None, input_precisions=None, niter=1, workdir=None, config_kv=None, extra=None, mean_scale=None):
     """Returns (outputs dict, manifest).  fp32 oracle runs must pass ENFORCE_BF16=NO."""
     from dldt_b200 import ir
     config = dict(config or {})
@@ -33,6 +33,8 @@ def run(func, inputs, device="CPU", config=None, input_precisions=None, niter=1,
         cmd += ["--config", ",".join("%s=%s" % kv for kv in config.items())]
     for kv in (config_kv or {}).items():       # values that contain commas (B200_DEVICES=0,1)
         cmd += ["--config-kv", "%s=%s" % kv]
+    for name, (means, scales) in (mean_scale or {}).items():     # PreProcessInfo mean values / scales per channel
+        cmd += ["--mean-scale", "%s=%s/%s" % (name, ":".join(repr(float(v)) for v in means), ":".join(repr(float(v)) for v in scales))]
     cmd += list(extra or [])
     for name, arr in inputs.items():
         path = os.path.join(tmp, "in_%s.bin" % name)
