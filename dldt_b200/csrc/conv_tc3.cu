@@ -138,6 +138,17 @@ void launch_tc3(const ConvParams& p, bool bf16, int bn, int a_mode, cudaStream_t
   a.n_tiles = p.Cout_alloc / bn;
   a.reverse = p.reverse;
   { const char* e = getenv("B200_TC3_WARP_STORE"); a.warp_store = (e && e[0] == '0') ? 0 : 1; }
+  {
+    // TMEM accumulator ring: as many accumulators as 512 columns hold (at most 4), so that the MMAs of the next tiles never wait for the
+    // epilogue's latency chain of an earlier one.  B200_TC3_NACC=2 restores the double buffer, B200_TC3_EARLY=0 the late hand-back.
+    const int acc_cols = a_mode == A_S2D ? 4 * bn : bn;
+    int nacc = std::min(MAX_ACC, 512 / acc_cols);
+    const char* e = getenv("B200_TC3_NACC");
+    if (e && atoi(e) >= 2 && atoi(e) < nacc) nacc = atoi(e) >= 4 ? 4 : 2;
+    a.acc_log2 = nacc >= 4 ? 2 : 1;
+    const char* er = getenv("B200_TC3_EARLY");
+    a.early_release = (er && er[0] == '0') ? 0 : 1;
+  }
   { const char* e = getenv("B200_TC3_PREFETCH"); a.prefetch_tiles = e ? atoi(e) : 0; }   // measured: no gain on B200 (profiles/r1 call k)
   {
     // activations are read once per layer (the next reader is a different kernel, long after the tensor has left the 126 MB L2 at batch 256):

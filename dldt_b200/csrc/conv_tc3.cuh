@@ -27,6 +27,7 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int MMA_WARP = 8, TMA_WARP = 9, RES_WARP = 10;
 constexpr int NUM_THREADS = 352;
 constexpr int MAX_STAGES = 8;
+constexpr int MAX_ACC = 4;               // TMEM accumulator ring (512 columns / accumulator columns, at most this)
 constexpr int NRES = 4;                  // residual ring, in slabs; output staging: 1 or 2 slabs per epilogue group (Plan3::nout = 2 or 4)
 constexpr int SMEM_LIMIT = 232448;
 constexpr int WS_MAX_BYTES = 80 * 1024;  // resident half of the weights, per CTA
@@ -98,6 +99,8 @@ struct Tc3Args {
   int rows_p, rows_r;       // A_HALO: pixel pitch P and image rows per CTA tile R = 128 / P
   int nseg;                 // A_S2D: 128-pixel segments per output row
   int tiles_per_img;        // A_S2D: ceil(Ho / 4) * nseg.  A_HALO: CTA tiles per image = ceil(Ho / R); the last one may hang over the image (clipped by the 4-D maps)
+  int acc_log2;             // log2 of the TMEM accumulator ring depth (1 = two accumulators; up to 512 / accumulator columns, at most 4)
+  int early_release;        // epilogue warps hand the accumulator back right after their last tcgen05.ld of the tile
   int prefetch_tiles;       // L2 prefetch distance (tiles of this cluster ahead) for the residual and the activation-matrix loads; 0 = off
   uint64_t a_policy, r_policy;   // L2 eviction priority of the activation-matrix loads (A_MATRIX) and of the residual loads
 };
@@ -228,8 +231,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
   uint64_t* fullB = emptyA + MAX_STAGES;
   uint64_t* emptyB = fullB + MAX_STAGES;
   uint64_t* tfull = emptyB + MAX_STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* rfull = tempty + 2;
+  uint64_t* tempty = tfull + MAX_ACC;
+  uint64_t* rfull = tempty + MAX_ACC;
   uint64_t* rempty = rfull + NRES;
   uint64_t* wfull = rempty + NRES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
@@ -240,6 +243,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
   const bool leader = rank == 0;
   const int num_tiles = args.num_tiles, n_tiles = args.n_tiles;
   const int cluster = (int)ptx::cluster_id_x(), nclusters = (int)ptx::num_clusters_x();
+  const uint32_t acc_sh = (uint32_t)args.acc_log2, acc_mask = (1u << acc_sh) - 1u;   // accumulator of tile `it`: it & acc_mask, phase (it >> acc_sh) & 1
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) {
@@ -250,7 +254,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
       ptx::mbar_init(&fullB[s], 1);
       ptx::mbar_init(&emptyB[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < MAX_ACC; ++a) {
       ptx::mbar_init(&tfull[a], 1);
       // accumulator drained: the eight local epilogue warps; in the leader also the peer's forwarder (the peer's otherwise idle MMA warp
       // waits for ITS eight warps on its local copy and does the one remote arrive, so no epilogue warp pays the cluster round trip)
@@ -270,7 +274,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
     if (has_res) ptx::tma_prefetch_desc(&args.tm_r);
   }
   if (warp == MMA_WARP) {
-    ptx::tmem_alloc_pair(tmem_slot, 2 * ACC_COLS);
+    ptx::tmem_alloc_pair(tmem_slot, (uint32_t)ACC_COLS << args.acc_log2);
     ptx::tmem_relinquish_pair();
   }
   ptx::tc_fence_before();
@@ -309,9 +313,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
       const int n0 = (tile % n_tiles) * BN;
       const int ncols = min(BN, p.Cout_p - n0);
       const int nslab = AMODE == A_S2D ? 4 : (ncols + 63) >> 6;   // s2d stem: slab h = output pixel phase h (BN == 64 channels each)
-      const uint32_t acc = it & 1u;
-      ptx::mbar_wait(&tfull[acc], (it >> 1) & 1u);
+      const uint32_t acc = it & acc_mask;
+      ptx::mbar_wait(&tfull[acc], (it >> acc_sh) & 1u);
       ptx::tc_fence_after();
+      bool released = false;
       for (int h = 0; h < nslab; ++h, ++g) {
         if ((int)(g & 1u) != grp) continue;
         const uint32_t rslot = g % NRES;
@@ -335,6 +340,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
           ptx::named_bar_sync(1 + grp, 128);
         }
         ptx::tmem_ld_wait();
+        if (args.early_release && h + 2 >= nslab) {
+          // the last slab of the tile this group reads is in registers: hand the accumulator back now, a whole slab latency (conversion,
+          // staging, store issue) earlier than at the end of the tile
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+          released = true;
+        }
         const uint32_t bias = bias_base + (uint32_t)(n0 + (AMODE == A_S2D ? 0 : h * 64)) * 4u;
         if constexpr (GEN) {
           epilogue_slab_generic<T>(v0, v1, bias, out_row, res_row, rsw, has_res, args.e1, args.e2);
@@ -374,21 +387,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
         }
       }
       // this warp's TMEM reads of the tile are complete (tmem_ld_wait above): hand the accumulator back
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+      if (!released) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+      }
     }
     if (wstore ? lane == 0 : store_thread) ptx::bulk_wait_all0();
   } else if (warp == MMA_WARP) {
     // ===================== MMA issuer (leader CTA; whole warp walks the loop, one elected lane issues) =====================
     if (!leader) {
       // peer CTA: forward "accumulator drained by my eight epilogue warps" to the leader's barrier, one remote arrive per tile
-      const uint32_t tempty_leader0 = ptx::mapa(ptx::smem_u32(&tempty[0]), 0), tempty_leader1 = ptx::mapa(ptx::smem_u32(&tempty[1]), 0);
+      const uint32_t tempty_leader0 = ptx::mapa(ptx::smem_u32(&tempty[0]), 0);
       uint32_t it = 0;
       for (int t_ = cluster; t_ < num_tiles; t_ += nclusters, ++it) {
-        const uint32_t acc = it & 1u;
-        ptx::mbar_wait(&tempty[acc], (it >> 1) & 1u);
-        if (lane == 0) ptx::mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+        const uint32_t acc = it & acc_mask;
+        ptx::mbar_wait(&tempty[acc], (it >> acc_sh) & 1u);
+        if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader0 + acc * 8u);
         __syncwarp();
       }
     }
@@ -405,8 +420,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
       uint32_t pha = 0, phb = 0;
       if (WS) ptx::mbar_wait(wfull, 0);
       for (int t_ = cluster; t_ < num_tiles; t_ += nclusters, ++it) {
-        const uint32_t acc = it & 1u;
-        ptx::mbar_wait(&tempty[acc], ((it >> 1) & 1u) ^ 1u);
+        const uint32_t acc = it & acc_mask;
+        ptx::mbar_wait(&tempty[acc], ((it >> acc_sh) & 1u) ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
         uint32_t accum = 0;
@@ -602,7 +617,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
   __syncwarp();
   ptx::tc_fence_before();
   ptx::cluster_sync();        // neither CTA may exit (or free TMEM) while the other can still touch its shared memory / barriers
-  if (warp == MMA_WARP) ptx::tmem_dealloc_pair(tmem_base, 2 * ACC_COLS);
+  if (warp == MMA_WARP) ptx::tmem_dealloc_pair(tmem_base, (uint32_t)ACC_COLS << args.acc_log2);
 }
 
 // cluster dims are static (__cluster_dims__); the one launch attribute is programmatic stream serialization (B200_PDL=0 turns it off)
