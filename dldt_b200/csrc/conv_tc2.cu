@@ -124,8 +124,59 @@ __device__ __forceinline__ void epilogue_warp(uint32_t taddr, const float* __res
           for (int e = 0; e < 8; ++e) f[e] += r[e];
           epi_act8<GEN>(f, e2);
         }
-        ptx::st_shared_v4(out_row + sw, make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7])));
+        if ((has_res ? e2 : e1).relu_in_pack)
+          ptx::st_shared_v4(out_row + sw, make_uint4(pack2_relu<T>(f[0], f[1]), pack2_relu<T>(f[2], f[3]), pack2_relu<T>(f[4], f[5]), pack2_relu<T>(f[6], f[7])));
+        else
+          ptx::st_shared_v4(out_row + sw, make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7])));
       }
+    }
+  }
+}
+
+// The clamp-family epilogue (none / ReLU / Clamp) of a FULL tile as straight-line code (see conv_tc3.cuh epilogue_slab for the why): all
+// loads of a 32-column chunk - eight bias vectors, four residual vectors - are issued while the TMEM load is in flight.
+template <typename T, int NCH, bool HAS_RES, bool CLAMP, bool RELU>
+__device__ __forceinline__ void epilogue_warp_fast(uint32_t taddr, const float* __restrict__ bias /* + first column of this warp */, uint32_t out_row,
+                                                   uint32_t res_row, uint32_t xsw, const EpiBounds& eb) {
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    uint32_t v[32];
+    ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+    float4 bb[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) bb[g] = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + g * 4));
+    uint4 rv[4];
+    if constexpr (HAS_RES) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) rv[g] = ptx::ld_shared_v4(res_row + ((xsw ^ (uint32_t)(c * 4 + g)) << 4));
+    }
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float4 b0 = bb[2 * g], b1 = bb[2 * g + 1];
+      float f[8];
+      f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+      f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+      f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+      f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+      if constexpr (CLAMP) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(f[e], eb.lo1), eb.hi1);
+      }
+      if constexpr (HAS_RES) {
+        float r[8];
+        unpack2<T>(rv[g].x, r[0], r[1]); unpack2<T>(rv[g].y, r[2], r[3]);
+        unpack2<T>(rv[g].z, r[4], r[5]); unpack2<T>(rv[g].w, r[6], r[7]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] += r[e];
+        if constexpr (CLAMP) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(f[e], eb.lo2), eb.hi2);
+        }
+      }
+      const uint32_t dst = out_row + ((xsw ^ (uint32_t)(c * 4 + g)) << 4);
+      if constexpr (RELU) ptx::st_shared_v4(dst, make_uint4(pack2_relu<T>(f[0], f[1]), pack2_relu<T>(f[2], f[3]), pack2_relu<T>(f[4], f[5]), pack2_relu<T>(f[6], f[7])));
+      else ptx::st_shared_v4(dst, make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7])));
     }
   }
 }
@@ -263,6 +314,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
     const uint32_t slab_off = (uint32_t)(col0 >> 6) * SLAB_BYTES;
     const uint32_t xsw = (uint32_t)(((col0 >> 3) & 7) ^ (row & 7));
     const bool store_thread = threadIdx.x == 4 * 32;
+    EpiBounds eb;
+    const int variant = epi_variant(has_res, args.e1, args.e2, eb);
     uint32_t it = 0;
     for (int t_ = blockIdx.x; t_ < num_tiles; t_ += gridDim.x, ++it) {
       const int tile = args.reverse ? num_tiles - 1 - t_ : t_;
@@ -282,7 +335,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
       if (has_res) ptx::mbar_wait(&rfull_bar[acc], par);   // residual tile landed
       if (store_thread) ptx::bulk_wait_read<1>();          // the store issued two tiles ago has finished reading this staging buffer
       ptx::named_bar_sync(1, NUM_EPI_WARPS * 32);
-      if (ncols == BN) epilogue_warp<T, CPW / 32, GEN, true>(taddr, p.bias + n0, out_row, res_row, xsw, col0, ncols, has_res, args.e1, args.e2);
+      if (!GEN && ncols == BN) {
+        const float* bw = p.bias + n0 + col0;
+        if (has_res) {
+          if (variant == 0) epilogue_warp_fast<T, CPW / 32, true, false, false>(taddr, bw, out_row, res_row, xsw, eb);
+          else if (variant == 1) epilogue_warp_fast<T, CPW / 32, true, false, true>(taddr, bw, out_row, res_row, xsw, eb);
+          else epilogue_warp_fast<T, CPW / 32, true, true, false>(taddr, bw, out_row, res_row, xsw, eb);
+        } else {
+          if (variant == 0) epilogue_warp_fast<T, CPW / 32, false, false, false>(taddr, bw, out_row, res_row, xsw, eb);
+          else if (variant == 1) epilogue_warp_fast<T, CPW / 32, false, false, true>(taddr, bw, out_row, res_row, xsw, eb);
+          else epilogue_warp_fast<T, CPW / 32, false, true, false>(taddr, bw, out_row, res_row, xsw, eb);
+        }
+      } else if (ncols == BN) epilogue_warp<T, CPW / 32, GEN, true>(taddr, p.bias + n0, out_row, res_row, xsw, col0, ncols, has_res, args.e1, args.e2);
       else epilogue_warp<T, CPW / 32, GEN, false>(taddr, p.bias + n0, out_row, res_row, xsw, col0, ncols, has_res, args.e1, args.e2);
       // accumulator + residual buffers are free again
       ptx::tc_fence_before();
@@ -488,6 +552,13 @@ void launch_tc2(const ConvParams& p, bool bf16, cudaStream_t s) {
   a.p = p;
   a.e1 = make_epi(p.act1, p.a1, p.b1);
   a.e2 = make_epi(p.act2, p.a2, p.b2);
+  {
+    // a trailing ReLU rides on the float -> bf16/f16 conversion (B200_RELU_PACK=0: explicit max), as in the pair kernel
+    const char* e = getenv("B200_RELU_PACK");
+    const bool on = !(e && e[0] == '0');
+    if (on && p.res != nullptr && p.act2 == ACT_RELU) a.e2.relu_in_pack = 1;
+    if (on && p.res == nullptr && p.act1 == ACT_RELU) a.e1.relu_in_pack = 1;
+  }
   const int m_tiles = (p.M + BM - 1) / BM;
   a.n_tiles = p.Cout_alloc / BN;
   a.num_tiles = m_tiles * a.n_tiles;

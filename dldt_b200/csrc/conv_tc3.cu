@@ -107,7 +107,11 @@ int a_mode_of(const ConvParams& p) {
 bool ws_applies(const ConvParams& p, int bn, int a_mode) {
   const int ws_bytes = (p.Ktot / BK) * (bn / 2) * 128;
   const char* no_ws = getenv("B200_NO_WS");
-  const int min_sa = a_mode == A_HALO ? 3 : 4;
+  // halo mode: one A stage feeds nine k-blocks (2300+ cycles of MMA), two stages are a full double buffer
+  const char* big = getenv("B200_TC3_WS_BIG");
+  const bool big_ok = !(big && big[0] == '0');
+  if (!big_ok && ws_bytes > 80 * 1024) return false;
+  const int min_sa = a_mode == A_HALO ? (big_ok ? 2 : 3) : 4;
   // One N tile: the whole weight matrix is resident.  Several N tiles: with a cluster count that is a multiple of the N tile count every
   // cluster sees ONE fixed N tile (tile = cluster + k * clusters, n = tile % n_tiles), so its half of THAT tile's weights can be resident
   // too (launch_tc3 rounds the grid accordingly).  B200_TC3_WSN=0 keeps the single-N-tile rule.

@@ -30,7 +30,7 @@ constexpr int MAX_STAGES = 8;
 constexpr int MAX_ACC = 4;               // TMEM accumulator ring (512 columns / accumulator columns, at most this)
 constexpr int NRES = 4;                  // residual ring, in slabs; output staging: 1 or 2 slabs per epilogue group (Plan3::nout = 2 or 4)
 constexpr int SMEM_LIMIT = 232448;
-constexpr int WS_MAX_BYTES = 80 * 1024;  // resident half of the weights, per CTA
+constexpr int WS_MAX_BYTES = 144 * 1024; // resident half of the weights, per CTA (144 KB = the 3x3 x 128 -> 128 layer at N tile 128, beside two halo stages)
 constexpr int BIAS_SMEM_FLOATS = 4096;   // the bias vector is staged in shared memory (launches with a larger padded Cout are not supported)
 
 enum AMode : int { A_MATRIX = 1, A_IM2COL = 2, A_HALO = 4, A_S2D = 8 };
@@ -44,7 +44,9 @@ __host__ __device__ inline Plan3 plan3(int bn, bool has_res, int ws_bytes, int a
   Plan3 pl;
   const int bias_bytes = bias_smem_bytes(cout_alloc);
   pl.a_stage = (uint32_t)A_BYTES;
-  if (a_mode == A_HALO) pl.a_stage = (uint32_t)((BM + 2 * rows_p) * 128 + 1024);   // R + 2 image rows of P pixels; the last taps read 2 rows past
+  // R + 2 image rows of P pixels.  The last taps of MMA rows 126/127 read 2 box rows past the stage: whatever follows it in shared memory
+  // (the next stage, the weight ring, the staging slabs) - those rows are pixel slots P - 2 / P - 1 >= W of the last image row, never stored
+  if (a_mode == A_HALO) pl.a_stage = (uint32_t)((BM + 2 * rows_p) * 128);
   if (a_mode == A_S2D) pl.a_stage = (uint32_t)((S2D_R + 3) * S2D_G * 128 + 1024);   // R + 3 block rows of 32 pixel groups; the last taps read 1 row past
   pl.b_stage = (uint32_t)((bn / 2) * 128);
   // Two staging slabs per epilogue group (the next slab is converted while the TMA store of the previous one still reads its slab) for
@@ -111,37 +113,55 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-template <typename T, bool GEN>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint32_t bias /* shared-memory address */, uint32_t out_row, uint32_t res_row, uint32_t rsw,
-                                               int chunk0, bool has_res, const EpiAct& e1, const EpiAct& e2) {
+// One 64-column slab of the clamp-family epilogue (none / ReLU / Clamp activations: every ResNet / MobileNet / SSD layer), as ONE straight
+// line of code per (residual, clamp, trailing-ReLU) combination: + bias, [clamp], [+ residual, [clamp]], pack, swizzled staging store.
+// The first version tested the activation kinds per 8 values (warp-uniform branches), which cut the slab into ~30 basic blocks: every
+// shared-memory load sat directly in front of its first use and the epilogue warps spent 7 cycles per instruction (ncu, ResNet-50 stage-4
+// expand layer: 31 % short-scoreboard, 21 % fixed-latency, 18 % instruction-fetch stalls, 2200 cycles per slab against ~350 instructions).
+// Here the loads of chunk c + 1 (two bias vectors, one residual vector) are issued before the arithmetic of chunk c.
+template <typename T, bool HAS_RES, bool CLAMP, bool RELU>
+__device__ __forceinline__ void epilogue_slab(const uint32_t (&v0)[32], const uint32_t (&v1)[32], uint32_t bias /* shared-memory address */, uint32_t out_row,
+                                              uint32_t res_row, uint32_t rsw, const EpiBounds& eb) {
+  uint4 b0 = ptx::ld_shared_v4(bias), b1 = ptx::ld_shared_v4(bias + 16u);   // all lanes read the same address: broadcast
+  uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+  if constexpr (HAS_RES) rv = ptx::ld_shared_v4(res_row + (rsw << 4));          // 16-byte chunk index XOR (row & 7)
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const uint4 b0 = ptx::ld_shared_v4(bias + (uint32_t)g * 32u);          // all lanes read the same address: broadcast
-    const uint4 b1 = ptx::ld_shared_v4(bias + (uint32_t)g * 32u + 16u);
+  for (int c = 0; c < 8; ++c) {
+    uint4 nb0 = b0, nb1 = b1, nrv = rv;
+    if (c < 7) {
+      nb0 = ptx::ld_shared_v4(bias + (uint32_t)(c + 1) * 32u);
+      nb1 = ptx::ld_shared_v4(bias + (uint32_t)(c + 1) * 32u + 16u);
+      if constexpr (HAS_RES) nrv = ptx::ld_shared_v4(res_row + ((rsw ^ (uint32_t)(c + 1)) << 4));
+    }
+    const uint32_t* v = c < 4 ? &v0[c * 8] : &v1[(c - 4) * 8];
     float f[8];
-    f[0] = __uint_as_float(v[g * 8 + 0]) + __uint_as_float(b0.x); f[1] = __uint_as_float(v[g * 8 + 1]) + __uint_as_float(b0.y);
-    f[2] = __uint_as_float(v[g * 8 + 2]) + __uint_as_float(b0.z); f[3] = __uint_as_float(v[g * 8 + 3]) + __uint_as_float(b0.w);
-    f[4] = __uint_as_float(v[g * 8 + 4]) + __uint_as_float(b1.x); f[5] = __uint_as_float(v[g * 8 + 5]) + __uint_as_float(b1.y);
-    f[6] = __uint_as_float(v[g * 8 + 6]) + __uint_as_float(b1.z); f[7] = __uint_as_float(v[g * 8 + 7]) + __uint_as_float(b1.w);
-    epi_act8<GEN>(f, e1);
-    const uint32_t sw = (rsw ^ (uint32_t)(chunk0 + g)) << 4;      // 16-byte chunk index XOR (row & 7)
-    if (has_res) {
-      const uint4 rv = ptx::ld_shared_v4(res_row + sw);
+    f[0] = __uint_as_float(v[0]) + __uint_as_float(b0.x); f[1] = __uint_as_float(v[1]) + __uint_as_float(b0.y);
+    f[2] = __uint_as_float(v[2]) + __uint_as_float(b0.z); f[3] = __uint_as_float(v[3]) + __uint_as_float(b0.w);
+    f[4] = __uint_as_float(v[4]) + __uint_as_float(b1.x); f[5] = __uint_as_float(v[5]) + __uint_as_float(b1.y);
+    f[6] = __uint_as_float(v[6]) + __uint_as_float(b1.z); f[7] = __uint_as_float(v[7]) + __uint_as_float(b1.w);
+    if constexpr (CLAMP) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(f[e], eb.lo1), eb.hi1);
+    }
+    if constexpr (HAS_RES) {
       float r[8];
       unpack2<T>(rv.x, r[0], r[1]); unpack2<T>(rv.y, r[2], r[3]);
       unpack2<T>(rv.z, r[4], r[5]); unpack2<T>(rv.w, r[6], r[7]);
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[e] += r[e];
-      epi_act8<GEN>(f, e2);
+      if constexpr (CLAMP) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(f[e], eb.lo2), eb.hi2);
+      }
     }
-    if ((has_res ? e2 : e1).relu_in_pack)
-      ptx::st_shared_v4(out_row + sw, make_uint4(pack2_relu<T>(f[0], f[1]), pack2_relu<T>(f[2], f[3]), pack2_relu<T>(f[4], f[5]), pack2_relu<T>(f[6], f[7])));
-    else
-      ptx::st_shared_v4(out_row + sw, make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7])));
+    const uint32_t dst = out_row + ((rsw ^ (uint32_t)c) << 4);
+    if constexpr (RELU) ptx::st_shared_v4(dst, make_uint4(pack2_relu<T>(f[0], f[1]), pack2_relu<T>(f[2], f[3]), pack2_relu<T>(f[4], f[5]), pack2_relu<T>(f[6], f[7])));
+    else ptx::st_shared_v4(dst, make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7])));
+    b0 = nb0; b1 = nb1; rv = nrv;
   }
 }
 
-// The generic-activation form of the two calls above for one whole 64-column slab: bias, ONE activation switch over the 64 accumulators,
+// The generic-activation form for one whole 64-column slab: bias, ONE activation switch over the 64 accumulators,
 // residual, one more switch, pack + swizzled staging store.
 template <typename T>
 __device__ __forceinline__ void epilogue_slab_generic(const uint32_t (&v0)[32], const uint32_t (&v1)[32], uint32_t bias, uint32_t out_row, uint32_t res_row,
@@ -306,6 +326,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
       ptx::named_bar_sync(3, NUM_EPI_WARPS * 32);
     }
     const uint32_t bias_base = smem_base + plan.bias_off;
+    EpiBounds eb;
+    const int variant = epi_variant(has_res, args.e1, args.e2, eb);
     uint32_t it = 0, g = 0;                // tiles / slabs processed so far (all slabs, both groups)
     for (int t_ = cluster; t_ < num_tiles; t_ += nclusters, ++it) {
       const int tile = args.reverse ? num_tiles - 1 - t_ : t_;
@@ -352,8 +374,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
         if constexpr (GEN) {
           epilogue_slab_generic<T>(v0, v1, bias, out_row, res_row, rsw, has_res, args.e1, args.e2);
         } else {
-          epilogue_chunk<T, GEN>(v0, bias, out_row, res_row, rsw, 0, has_res, args.e1, args.e2);
-          epilogue_chunk<T, GEN>(v1, bias + 128u, out_row, res_row, rsw, 4, has_res, args.e1, args.e2);
+          if (has_res) {
+            if (variant == 0) epilogue_slab<T, true, false, false>(v0, v1, bias, out_row, res_row, rsw, eb);
+            else if (variant == 1) epilogue_slab<T, true, false, true>(v0, v1, bias, out_row, res_row, rsw, eb);
+            else epilogue_slab<T, true, true, false>(v0, v1, bias, out_row, res_row, rsw, eb);
+          } else {
+            if (variant == 0) epilogue_slab<T, false, false, false>(v0, v1, bias, out_row, res_row, rsw, eb);
+            else if (variant == 1) epilogue_slab<T, false, false, true>(v0, v1, bias, out_row, res_row, rsw, eb);
+            else epilogue_slab<T, false, true, false>(v0, v1, bias, out_row, res_row, rsw, eb);
+          }
         }
         if (has_res) {
           __syncwarp();

@@ -153,5 +153,20 @@ __device__ __forceinline__ void epi_act8(float (&f)[8], const EpiAct& s) {
   }
 }
 
+// Clamp-family epilogues (none / ReLU / Clamp) run as straight-line code, one variant per launch (conv_tc3.cuh epilogue_slab, conv_tc2.cu
+// epilogue_warp_fast): bounds of the two activation slots, (-inf, +inf) where a slot is empty.
+struct EpiBounds { float lo1, hi1, lo2, hi2; };
+// which of the straight-line variants a launch runs (warp-uniform, fixed for the launch): 0 = plain, 1 = trailing ReLU in the pack, 2 = clamps
+__device__ __forceinline__ int epi_variant(bool has_res, const EpiAct& e1, const EpiAct& e2, EpiBounds& eb) {
+  const float inf = __int_as_float(0x7f800000);
+  const bool n1 = e1.kind == 0, n2 = e2.kind == 0;
+  // an activation that is "none" clamps to (-inf, +inf); a trailing ReLU the launcher moved into the pack is the clamp (0, +inf) here
+  eb.lo1 = n1 ? -inf : (e1.relu_in_pack ? 0.f : e1.lo); eb.hi1 = (n1 || e1.relu_in_pack) ? inf : e1.hi;
+  eb.lo2 = n2 ? -inf : (e2.relu_in_pack ? 0.f : e2.lo); eb.hi2 = (n2 || e2.relu_in_pack) ? inf : e2.hi;
+  if (!has_res) return n1 ? 0 : (e1.relu_in_pack ? 1 : 2);
+  if (!n1) return 2;
+  return n2 ? 0 : (e2.relu_in_pack ? 1 : 2);
+}
+
 }  // namespace tc
 }  // namespace b200
