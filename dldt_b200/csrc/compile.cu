@@ -1205,6 +1205,7 @@ void Lowerer::lower_matmul_general(const Node& n, const FusedConv* f) {
   p.M = (int)M; p.Ktot = (int)round_up(K, 64); p.Cout_alloc = (int)round_up(Nn, bn); p.ldy = (int)Nn;
   p.w_ld = (int)K; p.w_rows = (int)Nn; p.w_k = (int)K;
   p.batch = (int)batch_a; p.x_bs = M * K; p.w_bs = batch_b == 1 ? 0 : Nn * K; p.y_bs = M * Nn;
+  p.w_dynamic = 1;
   {
     // per-batch [M][K] x [N][K]^T with tile-aligned M: the batches are one flat [batch*M][K] activation matrix whose 128-row tiles each
     // pick their batch's weight rows -- one persistent launch with TMA stores instead of batch x tiles single-tile CTAs

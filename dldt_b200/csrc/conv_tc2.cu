@@ -239,9 +239,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  // programmatic dependent launch (see conv_tc3.cuh): the prologue above overlapped the previous kernel's drain
-  ptx::grid_dependency_wait();
+  // programmatic dependent launch (see conv_tc3.cuh): the prologue above overlapped the previous kernel's drain; every role waits for the
+  // dependency itself, the TMA issuer only after it has fetched the resident (constant) weights
   ptx::grid_launch_dependents();
+  if (warp != TMA_WARP) ptx::grid_dependency_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
         ptx::bulk_commit();
       }
     }
-    if (store_thread) ptx::bulk_wait_all0();
+    if (store_thread) ptx::bulk_wait_read<0>();   // the staging tiles outlive the stores' reads; the writes complete with the grid
   } else if (warp == MMA_WARP) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
@@ -408,10 +409,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
       uint32_t ph = 0;
       const int cpt = p.Cin_p >> 6;                 // 64-channel chunks per filter tap (im2col mode)
       const int HoWo = p.Ho * p.Wo;
+      if (p.w_dynamic || p.w_grp_m) ptx::grid_dependency_wait();
       if (ws) {                                     // one N tile: fetch the whole weight matrix once
         ptx::mbar_arrive_expect_tx(wfull_bar, (uint32_t)nkb * B_BYTES);
         for (int kb = 0; kb < nkb; ++kb) ptx::tma_load_2d(smem_base + plan.w_off + (uint32_t)kb * B_BYTES, &args.tm_w, wfull_bar, kb * BK, 0);
       }
+      ptx::grid_dependency_wait();
       const uint32_t stage_tx = (a_tma ? (uint32_t)A_BYTES : 0u) + (ws ? 0u : (uint32_t)B_BYTES);
       for (int t_ = blockIdx.x; t_ < num_tiles; t_ += gridDim.x, ++it) {
         const int tile = args.reverse ? num_tiles - 1 - t_ : t_;

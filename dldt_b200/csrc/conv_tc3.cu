@@ -129,6 +129,7 @@ void launch_tc3(const ConvParams& p, bool bf16, int bn, int a_mode, cudaStream_t
   memset(&a, 0, sizeof(a));
   a.p = p;
   { const char* e = getenv("B200_DEBUG_NO_RES"); if (e && e[0] == '1') a.p.res = nullptr; }   // timing experiment only: wrong results
+  { const char* e = getenv("B200_DEBUG_TC3"); a.debug = e ? atoi(e) : 0; }                        // timing experiments only: wrong results
   a.e1 = make_epi(p.act1, p.a1, p.b1);
   a.e2 = make_epi(p.act2, p.a2, p.b2);
   a.gen = conv_acts_are_clamps(p) ? 0 : 1;

@@ -103,6 +103,7 @@ struct Tc3Args {
   int tiles_per_img;        // A_S2D: ceil(Ho / 4) * nseg.  A_HALO: CTA tiles per image = ceil(Ho / R); the last one may hang over the image (clipped by the 4-D maps)
   int acc_log2;             // log2 of the TMEM accumulator ring depth (1 = two accumulators; up to 512 / accumulator columns, at most 4)
   int early_release;        // epilogue warps hand the accumulator back right after their last tcgen05.ld of the tile
+  int debug;                // timing experiments only (B200_DEBUG_TC3; results are wrong): bit 0 = no output stores, bit 1 = no epilogue arithmetic
   int prefetch_tiles;       // L2 prefetch distance (tiles of this cluster ahead) for the residual and the activation-matrix loads; 0 = off
   uint64_t a_policy, r_policy;   // L2 eviction priority of the activation-matrix loads (A_MATRIX) and of the residual loads
 };
@@ -303,7 +304,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) ran while the previous kernel of the stream was
   // still draining; its outputs are read only below this line.  Our own dependents may start their prologue as our CTAs retire.
-  ptx::grid_dependency_wait();
+  // Each role waits for the dependency itself, right before its first access to memory the previous kernel may have written: the constant
+  // operands (bias vector, resident weights) are fetched BEFORE the wait, while the producer's last tiles drain.
   ptx::grid_launch_dependents();
 
   if (warp < NUM_EPI_WARPS) {
@@ -325,6 +327,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
       for (int i = threadIdx.x; i < p.Cout_alloc; i += NUM_EPI_WARPS * 32) s_bias[i] = __ldg(p.bias + i);
       ptx::named_bar_sync(3, NUM_EPI_WARPS * 32);
     }
+    ptx::grid_dependency_wait();
     const uint32_t bias_base = smem_base + plan.bias_off;
     EpiBounds eb;
     const int variant = epi_variant(has_res, args.e1, args.e2, eb);
@@ -371,7 +374,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
           released = true;
         }
         const uint32_t bias = bias_base + (uint32_t)(n0 + (AMODE == A_S2D ? 0 : h * 64)) * 4u;
-        if constexpr (GEN) {
+        if (args.debug & 2) {
+        } else if constexpr (GEN) {
           epilogue_slab_generic<T>(v0, v1, bias, out_row, res_row, rsw, has_res, args.e1, args.e2);
         } else {
           if (has_res) {
@@ -392,7 +396,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
         if (wstore) {
           __syncwarp();
           if (lane == 0) {
-            if (tp.valid) {
+            if (tp.valid && !(args.debug & 1)) {
               const uint32_t src = out_slab + (uint32_t)q * 4096u;      // rows 32 q .. 32 q + 31 of the slab
               if (AMODE == A_S2D) ptx::tma_store_5d(&args.tm_yw, src, 0, h, tp.w0, tp.h0 + q, tp.img);
               else if (BOX4D) ptx::tma_store_4d(&args.tm_yw, src, n0 + h * 64, (q * 32) % args.rows_p, tp.h0 + (q * 32) / args.rows_p, tp.img);
@@ -407,7 +411,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
         }
         ptx::named_bar_sync(1 + grp, 128);
         if (store_thread) {
-          if (tp.valid) {
+          if (tp.valid && !(args.debug & 1)) {
             if (AMODE == A_S2D) ptx::tma_store_5d(&args.tm_y, out_slab, 0, h, tp.w0, tp.h0, tp.img);   // {channel, phase, pixel group, row, image}
             else if (BOX4D) ptx::tma_store_4d(&args.tm_y, out_slab, n0 + h * 64, tp.w0, tp.h0, tp.img);   // rows >= Ho / pixels >= Wo are clipped
             else ptx::tma_store_2d(&args.tm_y, out_slab, n0 + h * 64, tp.m0);
@@ -422,7 +426,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
         if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
       }
     }
-    if (wstore ? lane == 0 : store_thread) ptx::bulk_wait_all0();
+    // the staging slabs must outlive the stores' READS of them; the writes complete with the grid (every consumer waits on grid completion)
+    if (wstore ? lane == 0 : store_thread) ptx::bulk_wait_read<0>();
   } else if (warp == MMA_WARP) {
     // ===================== MMA issuer (leader CTA; whole warp walks the loop, one elected lane issues) =====================
     if (!leader) {
@@ -517,6 +522,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
     const uint32_t fullB_leader = ptx::smem_u32(&fullB[0]) & ptx::PEER_BIT_MASK;
     const uint32_t wfull_leader = ptx::smem_u32(wfull) & ptx::PEER_BIT_MASK;
     const int HoWo = p.Ho * p.Wo;
+    if (p.w_dynamic) ptx::grid_dependency_wait();
     if (WS) {   // this CTA's half of the weights of this cluster's (only) N tile, once: the host makes the cluster count a multiple of n_tiles
       if (lane == 0) {
         const int first = args.reverse ? num_tiles - 1 - cluster : cluster;
@@ -527,6 +533,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
       }
       __syncwarp();
     }
+    ptx::grid_dependency_wait();
     int sa = 0, sb = 0;
     uint32_t pha = 0, phb = 0;
     for (int t_ = cluster; t_ < num_tiles; t_ += nclusters) {
@@ -606,6 +613,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
   } else if (warp == RES_WARP) {
     // ===================== residual TMA issuer: one slab ahead of the epilogue, ring of NRES =====================
     if (has_res && lane == 0) {
+      ptx::grid_dependency_wait();
       uint32_t g = 0;
       const int la = args.prefetch_tiles * nclusters;
       for (int t_ = cluster; t_ < num_tiles; t_ += nclusters) {

@@ -55,6 +55,9 @@ struct ConvParams {
   // grouped weights given MN-major: group g is a [Ktot][64] matrix (N contiguous; attention's V as it comes out of the head split) read
   // through an MN-major UMMA descriptor instead of being transposed first.  Single-CTA kernel, Cout == 64.
   int w_mn_major = 0;
+  // the "weights" are an activation tensor written by an earlier kernel of the step (activation x activation MatMul): the kernels may not
+  // read them before the programmatic-launch dependency has resolved (constant weights and bias are fetched while the producer drains)
+  int w_dynamic = 0;
   // head-split output (BERT's Reshape [N,S,H*64] -> [N,S,H,64] + Transpose (0,2,1,3) folded into the producing FullyConnected): row
   // n*S + s, columns [64 h, 64 h + 64) are stored at y[n][h][s][0..63]; 0 = plain [M][ldy] output.  Pair kernel only.
   int y_heads_s = 0, y_heads_h = 0;
