@@ -280,7 +280,6 @@ void Lowerer::lower_stem_s2d(const FusedConv& f, const LTensor& x) {
   for (int64_t o = 0; o < Cout; ++o) bias[o] = f.shift[o];
   BufRef wref = weights_ref(add_weights(wp.data(), (int64_t)wp.size()));
   BufRef bref = add_f32_vector(bias);
-  LTensor out = alloc(val(f.out_value).shape, cd_, L_NHWC8);
   LTensor res;
   BufRef rref;
   if (f.res_value >= 0) { res = get(f.res_value, L_NHWC8); rref = res.buf; }
@@ -291,12 +290,41 @@ void Lowerer::lower_stem_s2d(const FusedConv& f, const LTensor& x) {
   p.M = (int)(os[0] * os[2] * os[3]); p.Ktot = (int)Ktot; p.Cout_alloc = (int)Cout_alloc; p.ldy = (int)Cout_p;
   p.w_ld = (int)Ktot; p.w_rows = (int)Cout_alloc; p.w_k = (int)Ktot;
   p.act1 = f.act1.kind; p.a1 = f.act1.a; p.b1 = f.act1.b; p.act2 = f.act2.kind; p.a2 = f.act2.a; p.b2 = f.act2.b;
+  // ReLU -> MaxPool 3x3 / stride 2 / pad 1 behind the stem (ResNet's pool1): taken in the stem's epilogue, which max-reduces its pooled
+  // rows into the zero-filled pooled tensor; the stem's own output (411 MB at batch 256) is never written.  B200_FUSE_POOL=0 turns it off.
+  int pool_node = -1;
+  {
+    const Value& ov = val(f.out_value);
+    const int u = ov.consumers.size() == 1 ? ov.consumers[0] : -1;
+    if (u >= 0 && absorbed_by_[u] < 0 && node(u).op == B200_OP_MAX_POOL && f.res_value < 0) {
+      const Node& pn = node(u);
+      const Shape& ps = val(pn.outputs[0]).shape;
+      const bool geom = pn.i[0] == 3 && pn.i[1] == 3 && pn.i[2] == 2 && pn.i[3] == 2 && pn.i[4] == 1 && pn.i[5] == 1 && pn.i[6] <= 1 && pn.i[7] <= 1 && ps[2] * 2 == os[2] && ps[3] * 2 == os[3];
+      ConvParams q = p;
+      q.pool = 1;
+      if (geom && conv_tc3_preferred(p) && conv_tc3_s2d_pool_ok(q)) pool_node = u;
+    }
+  }
+  const int out_value = pool_node >= 0 ? node(pool_node).outputs[0] : f.out_value;
+  LTensor out = alloc(val(out_value).shape, cd_, L_NHWC8);
   const double flops = 2.0 * p.M * Cout * Cin * kh * kw;
   const double bytes = (double)x.bytes() + (double)out.bytes() + (double)Cout * Cin * kh * kw * dtype_size(cd_) + (f.res_value >= 0 ? (double)out.bytes() : 0);
-  conv_launch_step(val(f.out_value).name, "Convolution", fused, p, x.buf, wref, bref, rref, out.buf, &x, f.res_value >= 0 ? &res : nullptr, &out, flops,
+  if (pool_node >= 0) {
+    p.pool = 1;
+    fused += "," + node(pool_node).name;
+    absorbed_by_[pool_node] = n.id;
+    BufRef yr = out.buf;
+    const size_t nbytes = (size_t)out.bytes();
+    Step z;
+    z.name = val(out_value).name + "/zero"; z.type = "Fill"; z.impl = "memset"; z.fused = z.name;
+    z.bytes = (double)nbytes;
+    z.launch = [=](const RunCtx& c) { cudaMemsetAsync(c.ptr(yr), 0, nbytes, (cudaStream_t)c.stream); };
+    emit(std::move(z), {}, {&out});
+  }
+  conv_launch_step(val(out_value).name, "Convolution", fused, p, x.buf, wref, bref, rref, out.buf, &x, f.res_value >= 0 ? &res : nullptr, &out, flops,
                    bytes, true);
-  net_.steps.back().impl += "_s2d_stem";
-  set(f.out_value, out);
+  net_.steps.back().impl += pool_node >= 0 ? "_s2d_stem_maxpool" : "_s2d_stem";
+  set(out_value, out);
 }
 
 LTensor Lowerer::materialize_const(int value, int layout) {
@@ -844,19 +872,24 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
       B200_CHECK(conv_tc3_supported(p), B200_ERR_UNSUPPORTED, "K-concatenated convolution '" << name << "' needs the pair kernel");
       v2 = true; v3 = true;
     }
+    const bool pooled = p.pool != 0;                        // stem + max-pool fusion: the pair kernel is the only implementation
+    if (pooled) {
+      B200_CHECK(conv_tc3_supported(p) && conv_tc3_s2d_pool_ok(p), B200_ERR_UNSUPPORTED, "pooled stem '" << name << "' needs the pair kernel");
+      v2 = true; v3 = true;
+    }
     const bool heads = p.y_heads_s > 0 && !p.y_heads_inv;   // head-split stores: the pair kernel is the only implementation
     if (heads) {
       B200_CHECK(conv_tc3_supported(p), B200_ERR_UNSUPPORTED, "head-split FullyConnected '" << name << "' needs the pair kernel");
       v2 = true; v3 = true;
     }
     // large launches: both persistent kernels apply, the first request measures which one is faster for this shape
-    both = v3 && !chained && !(tune && tune[0] == '0') && !(force3 && force3[0] == '1') && ((!kcat && !heads) || conv_tc3_preferred(p));
+    both = v3 && !chained && !pooled && !(tune && tune[0] == '0') && !(force3 && force3[0] == '1') && ((!kcat && !heads) || conv_tc3_preferred(p));
     impl2 = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_128x" + std::to_string(bn) + "x64" +
             (v2 ? (conv_tc2_a_is_matrix(p) ? "_persistent_tma" : (conv_tc2_a_is_im2col(p) ? "_persistent_im2col" : "_persistent_gather")) : "") +
             (p.w_mn_major ? "_bmn" : "") + (p.y_heads_inv ? "_heads" : "");
     // small launches (fewer tiles than SM pairs: batch 1): the static policy keeps the single-CTA kernel, but the time is one operand-latency
     // chain per k-block, so the N tile (stages that fit, tiles in flight) and the kernel are worth measuring there too
-    small_tune = v2 && !v3 && !chained && !kcat && !heads && conv_tc3_supported(p) && !(tune && tune[0] == '0') && !(force3 && (force3[0] == '0' || force3[0] == '1'));
+    small_tune = v2 && !v3 && !chained && !kcat && !heads && !pooled && conv_tc3_supported(p) && !(tune && tune[0] == '0') && !(force3 && (force3[0] == '0' || force3[0] == '1'));
     if (v3 || small_tune) {
       bn3 = conv_tc3_pick_bn(p);
       impl3 = std::string("tcgen05_") + (dt == B200_BF16 ? "bf16" : "f16") + "_pair256x" + std::to_string(bn3) + "x64_" + conv_tc3_mode_name(p);

@@ -85,6 +85,7 @@ struct Tc2Args {
   int a_tma;          // 0: cp.async gather, 1: 2-D TMA (A is a matrix), 2: im2col-mode TMA
   int num_tiles, n_tiles;
   int ws;             // weight-stationary mode (see smem_plan)
+  int debug;          // timing experiments only (B200_DEBUG_TC3 bit 2: no programmatic-launch wait; results are wrong)
   int reverse;        // walk the tiles from the last row block to the first (see ConvParams::reverse)
 };
 
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
   // programmatic dependent launch (see conv_tc3.cuh): the prologue above overlapped the previous kernel's drain; every role waits for the
   // dependency itself, the TMA issuer only after it has fetched the resident (constant) weights
   ptx::grid_launch_dependents();
-  if (warp != TMA_WARP) ptx::grid_dependency_wait();
+  if (warp != TMA_WARP && !(args.debug & 4)) ptx::grid_dependency_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
@@ -409,12 +410,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc2_kernel(const __grid_c
       uint32_t ph = 0;
       const int cpt = p.Cin_p >> 6;                 // 64-channel chunks per filter tap (im2col mode)
       const int HoWo = p.Ho * p.Wo;
-      if (p.w_dynamic || p.w_grp_m) ptx::grid_dependency_wait();
+      if ((p.w_dynamic || p.w_grp_m) && !(args.debug & 4)) ptx::grid_dependency_wait();
       if (ws) {                                     // one N tile: fetch the whole weight matrix once
         ptx::mbar_arrive_expect_tx(wfull_bar, (uint32_t)nkb * B_BYTES);
         for (int kb = 0; kb < nkb; ++kb) ptx::tma_load_2d(smem_base + plan.w_off + (uint32_t)kb * B_BYTES, &args.tm_w, wfull_bar, kb * BK, 0);
       }
-      ptx::grid_dependency_wait();
+      if (!(args.debug & 4)) ptx::grid_dependency_wait();
       const uint32_t stage_tx = (a_tma ? (uint32_t)A_BYTES : 0u) + (ws ? 0u : (uint32_t)B_BYTES);
       for (int t_ = blockIdx.x; t_ < num_tiles; t_ += gridDim.x, ++it) {
         const int tile = args.reverse ? num_tiles - 1 - t_ : t_;
@@ -566,6 +567,7 @@ void launch_tc2(const ConvParams& p, bool bf16, cudaStream_t s) {
   a.n_tiles = p.Cout_alloc / BN;
   a.num_tiles = m_tiles * a.n_tiles;
   a.reverse = p.reverse;
+  { const char* e = getenv("B200_DEBUG_TC3"); a.debug = e ? atoi(e) : 0; }
   {
     const int ws_bytes = (p.Ktot / BK) * BN * 128;
     const char* no_ws = getenv("B200_NO_WS");

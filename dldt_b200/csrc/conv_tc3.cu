@@ -95,6 +95,22 @@ bool s2d_ok(const ConvParams& p) {
          p.x_sh % 16 == 0 && p.x_sn % p.x_sh == 0 && p.Cout_alloc == 64 && p.ldy == p.Cout_p && p.Cout_p == 64 && p.Wo % 4 == 0 && p.Wo / 4 < S2D_G && p.res == nullptr;
 }
 
+}  // namespace
+
+// Stem + max-pool fusion (ConvParams::pool): whole 4-row tiles, pooled rows of at most 64 pixels (one staging slab per output row), a ReLU
+// as the only activation (the pooled tensor is zero-filled and max-reduced into), four staging slabs (two tiles x 4 rows x 8 KB).
+bool conv_tc3_s2d_pool_ok(const ConvParams& p) {
+  const char* e = getenv("B200_FUSE_POOL");
+  if (e && e[0] == '0') return false;
+  ConvParams q = p;
+  q.pool = 0;
+  if (!s2d_ok(q)) return false;
+  return p.Ho % 4 == 0 && p.Wo % 4 == 0 && p.Wo / 2 <= 64 && p.act1 == ACT_RELU && p.act2 == ACT_NONE && p.res == nullptr &&
+         plan3(p.Cout_alloc, false, (p.Ktot / BK) * (p.Cout_alloc / 2) * 128, A_S2D, 0, p.Cout_alloc, p.Ktot / BK).nout == 4;
+}
+
+namespace {
+
 int a_mode_of(const ConvParams& p) {
   if (s2d_ok(p)) return A_S2D;
   if (p.K2 > 0) return (p.kh == 1 && p.kw == 1 && p.sh == 1 && p.sw == 1 && p.pt == 0 && p.pl == 0 && p.Cin_p % 64 == 0 && p.K2 % 64 == 0 && p.x_sw == 0) ? A_MATRIX : 0;
@@ -195,6 +211,16 @@ void launch_tc3(const ConvParams& p, bool bf16, int bn, int a_mode, cudaStream_t
     a.tm_r = a.tm_y;
     const uint32_t ywb[5] = {64, 1, (uint32_t)S2D_G, 1, 1};         // one warp = one output row of the tile
     a.tm_yw = make_tmap_tiled(p.y, bf16, 5, yd, ys, ywb);
+    if (p.pool) {
+      // y is the pooled tensor {channel, Wo / 2, Ho / 2, image}; one box = one pooled row of 64 pixel slots (clipped at Wo / 2)
+      B200_CHECK(conv_tc3_s2d_pool_ok(p), B200_ERR_INVALID, "conv_tc3: stem + max-pool fusion does not apply to this launch");
+      const uint64_t pd[4] = {(uint64_t)p.Cout_p, (uint64_t)(p.Wo / 2), (uint64_t)(p.Ho / 2), (uint64_t)p.N};
+      const uint64_t ps[3] = {pitch, (uint64_t)(p.Wo / 2) * pitch, (uint64_t)(p.Ho / 2) * (p.Wo / 2) * pitch};
+      const uint32_t pb[4] = {64, 64, 1, 1};
+      a.tm_y = make_tmap_tiled(p.y, bf16, 4, pd, ps, pb);
+      a.tm_yw = a.tm_r = a.tm_y;
+      a.pool = 1;
+    }
   } else if (a_mode == A_HALO) {
     const uint64_t C = (uint64_t)p.Cin_p, pitch = (uint64_t)p.ldy * 2;
     const uint64_t ad[4] = {C, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};

@@ -103,7 +103,8 @@ struct Tc3Args {
   int tiles_per_img;        // A_S2D: ceil(Ho / 4) * nseg.  A_HALO: CTA tiles per image = ceil(Ho / R); the last one may hang over the image (clipped by the 4-D maps)
   int acc_log2;             // log2 of the TMEM accumulator ring depth (1 = two accumulators; up to 512 / accumulator columns, at most 4)
   int early_release;        // epilogue warps hand the accumulator back right after their last tcgen05.ld of the tile
-  int debug;                // timing experiments only (B200_DEBUG_TC3; results are wrong): bit 0 = no output stores, bit 1 = no epilogue arithmetic
+  int pool;                 // A_S2D: fused 3x3 / stride-2 / pad-1 max pool, tm_y = pooled tensor {C, Wo / 2, Ho / 2, N}, box {64, 64, 1, 1}
+  int debug;                // timing experiments only (B200_DEBUG_TC3; results are wrong): bit 0 = no output stores, bit 1 = no epilogue arithmetic, bit 2 = no programmatic-launch wait
   int prefetch_tiles;       // L2 prefetch distance (tiles of this cluster ahead) for the residual and the activation-matrix loads; 0 = off
   uint64_t a_policy, r_policy;   // L2 eviction priority of the activation-matrix loads (A_MATRIX) and of the residual loads
 };
@@ -327,10 +328,78 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
       for (int i = threadIdx.x; i < p.Cout_alloc; i += NUM_EPI_WARPS * 32) s_bias[i] = __ldg(p.bias + i);
       ptx::named_bar_sync(3, NUM_EPI_WARPS * 32);
     }
-    ptx::grid_dependency_wait();
+    if (!(args.debug & 4)) ptx::grid_dependency_wait();
     const uint32_t bias_base = smem_base + plan.bias_off;
     EpiBounds eb;
     const int variant = epi_variant(has_res, args.e1, args.e2, eb);
+    if (AMODE == A_S2D && args.pool) {
+      // ===== stem + 3x3 / stride-2 / pad-1 max pool (ConvParams::pool).  Warp (q, grp) owns output row h0 + q of the tile and channels
+      // [32 grp, 32 grp + 32); lane = pixel group g (pixels 4g .. 4g + 3 = the four phase accumulators).  Per tile: the four phases -> bias,
+      // ReLU, 16-bit pack (64 registers); pooled columns 2g = max(pixel 4g - 1 from lane g - 1, 4g, 4g + 1) and 2g + 1 = max(4g + 1, 4g + 2,
+      // 4g + 3) in packed arithmetic; the two warps of a row fill one swizzled [64 pooled pixels][64 channels] slab, and one TMA max-REDUCE
+      // per pooled row it belongs to (row r even: r / 2; r odd: (r - 1) / 2 and (r + 1) / 2) folds it into the zero-filled pooled tensor.
+      // The 411 MB stem output and its re-read by a pooling kernel never exist (ResNet-50 b256: stem 137 us + pool 88 us before).
+      const int half = grp;
+      const bool issuer = half == 0 && lane == 0;
+      const int Hp = p.Ho >> 1;
+      uint32_t it = 0;
+      for (int t_ = cluster; t_ < num_tiles; t_ += nclusters, ++it) {
+        const int tile = args.reverse ? num_tiles - 1 - t_ : t_;
+        const TilePos tp = tile_pos<AMODE>(args, tile / n_tiles, (int)rank);
+        const uint32_t acc = it & acc_mask;
+        ptx::mbar_wait(&tfull[acc], (it >> acc_sh) & 1u);
+        ptx::tc_fence_after();
+        uint32_t pk[4][16];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + (uint32_t)(f * BN + half * 32), v);
+          uint4 b[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) b[j] = ptx::ld_shared_v4(bias_base + (uint32_t)(half * 32 + j * 4) * 4u);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            pk[f][2 * j] = pack2_relu<T>(__uint_as_float(v[4 * j]) + __uint_as_float(b[j].x), __uint_as_float(v[4 * j + 1]) + __uint_as_float(b[j].y));
+            pk[f][2 * j + 1] = pack2_relu<T>(__uint_as_float(v[4 * j + 2]) + __uint_as_float(b[j].z), __uint_as_float(v[4 * j + 3]) + __uint_as_float(b[j].w));
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+        // staging slab of (tile parity, row q): 8 KB.  The reduce that read it two tiles ago has finished reading
+        const uint32_t slab = smem_base + plan.out_off + (it & 1u) * 32768u + (uint32_t)q * 8192u;
+        if (issuer) ptx::bulk_wait_read<1>();
+        ptx::named_bar_sync(4 + q, 64);
+        const uint32_t px0 = 2u * (uint32_t)lane, px1 = px0 + 1u;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          uint32_t o0[4], o1[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = jj * 4 + e;
+            uint32_t left = __shfl_up_sync(0xffffffffu, pk[3][j], 1);
+            if (lane == 0) left = 0u;                                  // pixel -1 is padding; every value is >= 0
+            o0[e] = max2<T>(max2<T>(left, pk[0][j]), pk[1][j]);
+            o1[e] = max2<T>(max2<T>(pk[1][j], pk[2][j]), pk[3][j]);
+          }
+          const uint32_t ch = (uint32_t)(half * 4 + jj);              // 16-byte chunk of the 128-byte pixel row
+          ptx::st_shared_v4(slab + px0 * 128u + ((ch ^ (px0 & 7u)) << 4), make_uint4(o0[0], o0[1], o0[2], o0[3]));
+          ptx::st_shared_v4(slab + px1 * 128u + ((ch ^ (px1 & 7u)) << 4), make_uint4(o1[0], o1[1], o1[2], o1[3]));
+        }
+        ptx::fence_proxy_async();
+        ptx::named_bar_sync(4 + q, 64);
+        if (issuer) {
+          const int r = tp.h0 + q;
+          if (tp.valid && r < p.Ho && !(args.debug & 1)) {
+            ptx::tma_reduce_max_4d(&args.tm_y, slab, 0, 0, r >> 1, tp.img);
+            if ((r & 1) && ((r + 1) >> 1) < Hp) ptx::tma_reduce_max_4d(&args.tm_y, slab, 0, 0, (r + 1) >> 1, tp.img);
+          }
+          ptx::bulk_commit();
+        }
+      }
+      if (issuer) ptx::bulk_wait_read<0>();
+    } else {
     uint32_t it = 0, g = 0;                // tiles / slabs processed so far (all slabs, both groups)
     for (int t_ = cluster; t_ < num_tiles; t_ += nclusters, ++it) {
       const int tile = args.reverse ? num_tiles - 1 - t_ : t_;
@@ -428,6 +497,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
     }
     // the staging slabs must outlive the stores' READS of them; the writes complete with the grid (every consumer waits on grid completion)
     if (wstore ? lane == 0 : store_thread) ptx::bulk_wait_read<0>();
+    }
   } else if (warp == MMA_WARP) {
     // ===================== MMA issuer (leader CTA; whole warp walks the loop, one elected lane issues) =====================
     if (!leader) {
@@ -522,7 +592,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
     const uint32_t fullB_leader = ptx::smem_u32(&fullB[0]) & ptx::PEER_BIT_MASK;
     const uint32_t wfull_leader = ptx::smem_u32(wfull) & ptx::PEER_BIT_MASK;
     const int HoWo = p.Ho * p.Wo;
-    if (p.w_dynamic) ptx::grid_dependency_wait();
+    if (p.w_dynamic && !(args.debug & 4)) ptx::grid_dependency_wait();
     if (WS) {   // this CTA's half of the weights of this cluster's (only) N tile, once: the host makes the cluster count a multiple of n_tiles
       if (lane == 0) {
         const int first = args.reverse ? num_tiles - 1 - cluster : cluster;
@@ -533,7 +603,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
       }
       __syncwarp();
     }
-    ptx::grid_dependency_wait();
+    if (!(args.debug & 4)) ptx::grid_dependency_wait();
     int sa = 0, sb = 0;
     uint32_t pha = 0, phb = 0;
     for (int t_ = cluster; t_ < num_tiles; t_ += nclusters) {
@@ -613,7 +683,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
   } else if (warp == RES_WARP) {
     // ===================== residual TMA issuer: one slab ahead of the epilogue, ring of NRES =====================
     if (has_res && lane == 0) {
-      ptx::grid_dependency_wait();
+      if (!(args.debug & 4)) ptx::grid_dependency_wait();
       uint32_t g = 0;
       const int la = args.prefetch_tiles * nclusters;
       for (int t_ = cluster; t_ < num_tiles; t_ += nclusters) {

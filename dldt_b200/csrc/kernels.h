@@ -58,6 +58,9 @@ struct ConvParams {
   // the "weights" are an activation tensor written by an earlier kernel of the step (activation x activation MatMul): the kernels may not
   // read them before the programmatic-launch dependency has resolved (constant weights and bias are fetched while the producer drains)
   int w_dynamic = 0;
+  // space-to-depth stem only (pair kernel): the 3x3 / stride-2 / pad-1 max pool that follows the ReLU is taken in the epilogue; y is the
+  // POOLED tensor [N][Ho / 2][Wo / 2][Cout_p], zero-filled before the launch (the epilogue max-reduces into it; ReLU outputs are >= 0)
+  int pool = 0;
   // head-split output (BERT's Reshape [N,S,H*64] -> [N,S,H,64] + Transpose (0,2,1,3) folded into the producing FullyConnected): row
   // n*S + s, columns [64 h, 64 h + 64) are stored at y[n][h][s][0..63]; 0 = plain [M][ldy] output.  Pair kernel only.
   int y_heads_s = 0, y_heads_h = 0;
@@ -84,6 +87,8 @@ void conv_tc2_init_device();
 // 3x3 "row" modes.  Used for large launches (every SM pair has tiles to walk); B200_TC3=0 disables, =1 forces it wherever supported.
 bool conv_tc3_supported(const ConvParams& p);
 bool conv_tc3_preferred(const ConvParams& p);
+// the stem + max-pool fusion (ConvParams::pool) applies to this launch (geometry without the pool flag set)
+bool conv_tc3_s2d_pool_ok(const ConvParams& p);
 int conv_tc3_pick_bn(const ConvParams& p);
 const char* conv_tc3_mode_name(const ConvParams& p);
 void launch_conv_tc3(const ConvParams& p, int dtype, int bn, cudaStream_t s);

@@ -361,6 +361,13 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src_smem
                "r"(c2), "r"(c3)
                : "memory");
 }
+// element-wise max of the staged box into global memory (the element type comes from the tensor map; bf16 / f16 probed on B200:
+// tools/probes/tma_reduce_max_probe.cu)
+__device__ __forceinline__ void tma_reduce_max_4d(const void* tmap, uint32_t src_smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.max.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap), "r"(src_smem), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_4d_hint(uint32_t dst_smem, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3, uint64_t policy) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(

@@ -52,6 +52,17 @@ template <> __device__ __forceinline__ void unpack2<__half>(uint32_t u, float& a
   a = __low2float(v); b = __high2float(v);
 }
 
+// element-wise max of two packed pairs
+template <typename T>
+__device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b);
+template <> __device__ __forceinline__ uint32_t max2<__nv_bfloat16>(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+template <> __device__ __forceinline__ uint32_t max2<__half>(uint32_t a, uint32_t b) {
+  __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
 
 // Epilogue activation over 8 accumulators.  GENERIC == false covers the activations that are a clamp (none / ReLU / Clamp,
 // i.e. every ResNet / MobileNet / SSD layer) with two instructions per element; GENERIC == true keeps the full table of

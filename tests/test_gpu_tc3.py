@@ -79,6 +79,40 @@ def test_pair_kernel_matches_oracle(name, monkeypatch):
     assert rel_l2(got, ref) < tol, (name, rel_l2(got, ref))
 
 
+# name: (N, H, W, precision, pads_end, fused?)
+STEM_POOL = {
+    "pool_64": (2, 64, 64, "BF16", (1, 1), True),
+    "pool_odd_tiles_fp16": (3, 48, 80, "FP16", (1, 1), True),          # 3 x 6 CTA tiles: the last pair tile has one valid half
+    "pool_widest_pads_end0": (1, 40, 248, "BF16", (0, 0), True),       # 124 output pixels = 31 pixel groups, 62 pooled columns
+    "pool_rows_not_x4_stays_separate": (3, 50, 40, "BF16", (1, 1), False),
+}
+
+
+@pytest.mark.parametrize("name", sorted(STEM_POOL))
+def test_stem_with_max_pool_in_the_epilogue(name, monkeypatch):
+    # ResNet's conv1 -> ReLU -> MaxPool 3x3 / 2 / pad 1: the pool is taken in the stem's epilogue (TMA max-reduce into a zero-filled tensor)
+    n, h, w, prec, pe, fused = STEM_POOL[name]
+    monkeypatch.setenv("B200_TC3", "1")
+    rng = np.random.default_rng(sum(map(ord, name)))
+    f = Function("stem")
+    x = f.parameter((n, 3, h, w))
+    y = f.convolution(x, (rng.standard_normal((64, 3, 7, 7)) / np.sqrt(147.0)).astype(np.float32), (2, 2), (3, 3), (3, 3), (1, 1))
+    y = f.relu(f.add(y, rng.standard_normal((1, 64, 1, 1)).astype(np.float32)))
+    f.result(f.max_pool(y, (3, 3), (2, 2), (1, 1), pe))
+    xin = rng.standard_normal((n, 3, h, w)).astype(np.float32)
+    ref = list(interp.run(f, {"Parameter_0": xin}).values())[0]
+    net = Core().load_network(f, "B200", {"B200_INFERENCE_PRECISION": prec})
+    req = net.create_infer_request()
+    got = list(req.infer({"Parameter_0": xin}).values())[0]
+    eg = net.get_exec_graph_info()
+    assert any(e["impl"].endswith("_s2d_stem_maxpool") for e in eg) == fused, [e["impl"] for e in eg]
+    assert any(e["type"] == "Pooling" for e in eg) == (not fused)
+    assert got.shape == ref.shape
+    assert rel_l2(got, ref) < (1e-2 if prec == "BF16" else 2e-3), (name, rel_l2(got, ref))
+    # the pooled tensor is zero-filled by every run: a second inference gives the same bits
+    assert np.array_equal(got, list(req.infer({"Parameter_0": xin}).values())[0])
+
+
 def test_autotuned_selection_is_one_of_the_candidates_and_matches_oracle(monkeypatch):
     # large enough that both persistent kernels apply (>= 74 pair tiles): the first request times them and keeps one
     monkeypatch.delenv("B200_TC3", raising=False)

@@ -24,8 +24,10 @@ def test_resnet50_schedule():
     eg = net.get_exec_graph_info()
     k = kinds(net)
     # 53 convs with BN/ReLU/residual folded in, of which the 4 projection shortcuts ride on the last 1x1 of their block as extra K
-    # (fold_shortcuts); max pool, global avg pool, FC (+bias)
-    assert k == {"Convolution": 49, "Pooling": 2, "FullyConnected": 1}
+    # (fold_shortcuts); the max pool rides in the stem's epilogue (max-reduce into a zero-filled tensor); global avg pool, FC (+bias)
+    assert k == {"Fill": 1, "Convolution": 49, "Pooling": 1, "FullyConnected": 1}
+    stem = [e for e in eg if e["impl"].endswith("_s2d_stem_maxpool")]
+    assert len(stem) == 1 and any("pool" in n.lower() for n in stem[0]["fused"])
     assert sum(1 for e in eg if "tma_kcat" in e["impl"]) == 4
     assert all(e["impl"].startswith("tcgen05_bf16") for e in eg if e["type"] in ("Convolution", "FullyConnected"))
     assert sum(1 for e in eg if e["type"] == "Convolution" and any("add" in n.lower() for n in e["fused"])) >= 16  # residual sums
@@ -40,13 +42,14 @@ def test_resnet50_schedule_with_chained_reduce_convs(monkeypatch):
     monkeypatch.setenv("B200_FUSE_NEXT", "1")
     net = dry(zoo.resnet50(batch=256))
     eg = net.get_exec_graph_info()
-    assert kinds(net) == {"Convolution": 37, "Pooling": 2, "FullyConnected": 1}
+    assert kinds(net) == {"Fill": 1, "Convolution": 37, "Pooling": 1, "FullyConnected": 1}
     assert sum(1 for e in eg if "+1x1x" in e["impl"]) == 12
     assert abs(net.stat("flops") / 256 / 1e9 - 8.178) < 0.01
 
 
 def test_resnet50_schedule_without_shortcut_folding(monkeypatch):
     monkeypatch.setenv("B200_FOLD_SHORTCUT", "0")
+    monkeypatch.setenv("B200_FUSE_POOL", "0")
     net = dry(zoo.resnet50(batch=256))
     assert kinds(net) == {"Convolution": 53, "Pooling": 2, "FullyConnected": 1}
     assert abs(net.stat("flops") / 256 / 1e9 - 8.178) < 0.01
