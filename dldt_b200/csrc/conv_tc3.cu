@@ -127,7 +127,9 @@ bool ws_applies(const ConvParams& p, int bn, int a_mode) {
   const char* big = getenv("B200_TC3_WS_BIG");
   const bool big_ok = !(big && big[0] == '0');
   if (!big_ok && ws_bytes > 80 * 1024) return false;
-  const int min_sa = a_mode == A_HALO ? (big_ok ? 2 : 3) : 4;
+  // im2col / matrix mode with large resident weights (3x3 stride-2 128 -> 128: 144 KB): three A stages of one k-block each still cover the
+  // TMA latency once the weight stream is gone (the launch was L2->SM-bound at 24 KB per k-block, 16 KB without the weights)
+  const int min_sa = a_mode == A_HALO ? (big_ok ? 2 : 3) : ((big_ok && ws_bytes > 80 * 1024) ? 3 : 4);
   // One N tile: the whole weight matrix is resident.  Several N tiles: with a cluster count that is a multiple of the N tile count every
   // cluster sees ONE fixed N tile (tile = cluster + k * clusters, n = tile % n_tiles), so its half of THAT tile's weights can be resident
   // too (launch_tc3 rounds the grid accordingly).  B200_TC3_WSN=0 keeps the single-N-tile rule.
