@@ -251,9 +251,19 @@ bool Lowerer::stem_s2d_applies(int value) const {
   if (c.op != B200_OP_CONVOLUTION || c.inputs[0] != value || !const_node(c.inputs[1])) return false;
   const Shape& w = val(c.inputs[1]).shape;
   const Shape& o = val(c.outputs[0]).shape;
-  const bool k_ok = (w[2] == 7 || w[2] == 8) && (w[3] == 7 || w[3] == 8);
+  // 7x7 / 8x8 (ResNet, SSD) and 3x3 / 5x5 (MobileNet's first convolution: 3x3 stride 2 over 3 channels) windows all sit inside the 4x4 window
+  // of 2x2-pixel blocks; the unused taps of the packed weights stay zero
+  const bool k_ok = w[2] >= 3 && w[2] <= 8 && w[3] >= 3 && w[3] <= 8;
   // every tap row/column must stay inside the Hb x Wb block grid: padded extent <= 2 * (Ho + 3)
   const bool fits = v.shape[2] + c.i[4] <= 2 * (o[2] + 3) && v.shape[3] + c.i[5] <= 2 * (o[3] + 3);
+  // windows smaller than 7x7 waste most of the 4x4-block MMAs: worth it only where the pair kernel's stem mode runs (every SM pair has a tile);
+  // small launches keep the direct CUDA-core kernel for few input channels
+  if (w[2] < 7 || w[3] < 7) {
+    const char* f3 = getenv("B200_TC3");
+    const bool forced = f3 && f3[0] == '1';
+    if (!forced && o[0] * ((o[2] + 3) / 4) < 148) return false;
+    if (f3 && f3[0] == '0') return false;
+  }
   return k_ok && c.i[0] == 2 && c.i[1] == 2 && c.i[2] == 1 && c.i[3] == 1 && c.i[4] <= 8 && c.i[5] <= 8 && fits && o[2] >= 1 && o[3] >= 1;
 }
 

@@ -92,7 +92,7 @@ bool s2d_ok(const ConvParams& p) {
   // block row pitch a multiple of 16 bytes, groups of 4 output pixels, no residual, one 64-channel N tile (four phase accumulators fill TMEM),
   // one segment per row (group 31 of the box reads group 32 = the next block row: it must be a dropped one, so Wo <= 124)
   return p.x_sw == 16 && p.kh == 4 && p.kw == 1 && p.Cin_p == 64 && p.Ktot == 256 && p.sh == 1 && p.sw == 1 && p.dh == 1 && p.pt == 0 && p.pl == 0 &&
-         p.x_sh % 16 == 0 && p.x_sn % p.x_sh == 0 && p.Cout_alloc == 64 && p.ldy == p.Cout_p && p.Cout_p == 64 && p.Wo % 4 == 0 && p.Wo / 4 < S2D_G && p.res == nullptr;
+         p.x_sh % 16 == 0 && p.x_sn % p.x_sh == 0 && p.Cout_alloc == 64 && p.ldy == p.Cout_p && p.Cout_p <= 64 && p.Cout_p % 8 == 0 && p.Wo % 4 == 0 && p.Wo / 4 < S2D_G && p.res == nullptr;
 }
 
 }  // namespace
@@ -127,9 +127,8 @@ bool ws_applies(const ConvParams& p, int bn, int a_mode) {
   const char* big = getenv("B200_TC3_WS_BIG");
   const bool big_ok = !(big && big[0] == '0');
   if (!big_ok && ws_bytes > 80 * 1024) return false;
-  // im2col / matrix mode with large resident weights (3x3 stride-2 128 -> 128: 144 KB): three A stages of one k-block each still cover the
-  // TMA latency once the weight stream is gone (the launch was L2->SM-bound at 24 KB per k-block, 16 KB without the weights)
-  const int min_sa = a_mode == A_HALO ? (big_ok ? 2 : 3) : ((big_ok && ws_bytes > 80 * 1024) ? 3 : 4);
+  // (im2col mode with 144 KB of resident weights and three A stages measured slower than the streamed ring: res3_0_b 83 -> 88+ us)
+  const int min_sa = a_mode == A_HALO ? (big_ok ? 2 : 3) : 4;
   // One N tile: the whole weight matrix is resident.  Several N tiles: with a cluster count that is a multiple of the N tile count every
   // cluster sees ONE fixed N tile (tile = cluster + k * clusters, n = tile % n_tiles), so its half of THAT tile's weights can be resident
   // too (launch_tc3 rounds the grid accordingly).  B200_TC3_WSN=0 keeps the single-N-tile rule.

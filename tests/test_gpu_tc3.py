@@ -40,6 +40,8 @@ CASES = {
     "s2d_stem_too_wide_falls_back": (1, 3, 40, 520, 64, 7, 2, 3, False, "relu", "BF16", {}, "im2col_s2d_stem"),
     "s2d_stem_fp16_partial_rows": (3, 3, 50, 40, 64, 7, 2, 3, False, "relu", "FP16", {}, "s2d_s2d_stem"),
     "s2d_stem_ssd300_falls_back": (1, 3, 300, 300, 64, 7, 2, 3, False, "relu", "BF16", {}, "im2col_s2d_stem"),
+    "s2d_stem_3x3_c32_relu6": (2, 3, 64, 64, 32, 3, 2, 1, False, "clamp", "BF16", {}, "s2d_s2d_stem"),      # MobileNet's first convolution
+    "s2d_stem_5x5_c48_fp16": (3, 3, 48, 80, 48, 5, 2, 2, False, "relu", "FP16", {}, "s2d_s2d_stem"),
     "halo_w30_clip": (2, 64, 16, 30, 128, 3, 1, 1, False, "clamp", "BF16", {}, "halo"),
 }
 
