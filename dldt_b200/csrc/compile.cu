@@ -209,6 +209,8 @@ class Lowerer {
   bool per_channel_const(int value, int64_t C, bool matmul_style, std::vector<float>& out) const;
   void lower_node(const Node& n);
   void lower_conv(const FusedConv& f);
+  bool try_lower_mbconv(const FusedConv& f);
+  std::set<int> mb_done_;                           // emit positions of convolutions already computed by an mbconv kernel
   void lower_matmul_general(const Node& n, const FusedConv* f);
   void lower_binary(const Node& n, const ActSpec& act, int out_value);
   void lower_unary(const Node& n, const ActSpec& act);
@@ -967,6 +969,149 @@ void Lowerer::conv_launch_step(const std::string& name, const std::string& type,
   emit(std::move(s), {tx, tres, tx2}, {ty, tz});
 }
 
+// MobileNetV2-style inverted-residual block: expand 1x1 (+BN, clamp) -> depthwise 3x3 (+BN, clamp) -> project 1x1 (+BN) [+ block input] as ONE
+// kernel (mbconv.cu): the expanded tensor (6x the block's input at every resolution) is never written.  Also the expand-less first block
+// (depthwise -> project).  Called with the FIRST convolution of the chain; the later ones are marked done.  B200_FUSE_MBCONV=0 turns it off.
+bool Lowerer::try_lower_mbconv(const FusedConv& f) {
+  if (!use_tc_ || (cd_ != B200_BF16 && cd_ != B200_F16)) return false;
+  { const char* e = getenv("B200_FUSE_MBCONV"); if (e && e[0] == '0') return false; }
+  auto plain = [&](const FusedConv& c) { return c.dual_root < 0 && c.next_root < 0 && c.heads_s == 0; };
+  auto clampish = [&](const ActSpec& a) { return a.kind == ACT_NONE || a.kind == ACT_RELU || a.kind == ACT_CLAMP; };
+  auto pointwise = [&](const FusedConv& c) {
+    const Node& m = node(c.root);
+    if (m.op != B200_OP_CONVOLUTION || !plain(c) || !const_node(m.inputs[1])) return false;
+    const Shape& w = val(m.inputs[1]).shape;
+    return w.size() == 4 && w[2] == 1 && w[3] == 1 && m.i[0] == 1 && m.i[1] == 1 && m.i[2] == 1 && m.i[3] == 1 && !(m.i[4] | m.i[5] | m.i[6] | m.i[7]);
+  };
+  auto depthwise3 = [&](const FusedConv& c) {
+    const Node& m = node(c.root);
+    if (m.op != B200_OP_GROUP_CONVOLUTION || !plain(c) || !const_node(m.inputs[1]) || c.res_value >= 0 || c.act2.kind != ACT_NONE || !clampish(c.act1)) return false;
+    const Shape& w = val(m.inputs[1]).shape;
+    return w.size() == 5 && w[1] == 1 && w[2] == 1 && w[3] == 3 && w[4] == 3 && m.i[0] == m.i[1] && (m.i[0] == 1 || m.i[0] == 2) && m.i[2] == 1 && m.i[3] == 1 &&
+           m.i[4] >= 0 && m.i[4] <= 1 && m.i[5] >= 0 && m.i[5] <= 1 && m.i[6] <= 1 && m.i[7] <= 1;
+  };
+  // the one fused record that consumes `value` (and nothing else does)
+  auto sole_consumer = [&](int value) -> const FusedConv* {
+    const Value& v = val(value);
+    if (v.consumers.size() != 1) return nullptr;
+    for (auto& kv : fconv_)
+      if (kv.second.root == v.consumers[0] && node(kv.second.root).inputs[0] == value && !mb_done_.count(kv.first)) return &kv.second;
+    return nullptr;
+  };
+  const FusedConv *fe = nullptr, *fd = nullptr;
+  if (pointwise(f)) {
+    if (f.res_value >= 0 || f.act2.kind != ACT_NONE || !clampish(f.act1)) return false;
+    fe = &f;
+    fd = sole_consumer(f.out_value);
+    if (!fd || !depthwise3(*fd)) return false;
+  } else if (depthwise3(f)) {
+    fd = &f;
+  } else {
+    return false;
+  }
+  const FusedConv* fp = sole_consumer(fd->out_value);
+  if (!fp || !pointwise(*fp) || fp->act1.kind != ACT_NONE || fp->act2.kind != ACT_NONE) return false;
+  const int in_value = node((fe ? fe : fd)->root).inputs[0];
+  if (fp->res_value >= 0 && !(fe && fp->res_value == in_value)) return false;
+  auto xi = vt_.find(in_value);
+  if (xi == vt_.end() || xi->second.layout != L_NHWC8 || xi->second.dtype != cd_) return false;
+  const LTensor x = xi->second;
+  const Node& nd = node(fd->root);
+  const Node& np = node(fp->root);
+  const Shape& hs = val(nd.inputs[0]).shape;          // hidden tensor [N, Ch, H, W]
+  const Shape os = val(np.outputs[0]).shape;          // [N, Cout, Ho, Wo]
+  if (hs[2] != x.shape[2] || hs[3] != x.shape[3]) return false;
+  MbParams p{};
+  p.N = (int)x.shape[0]; p.H = (int)x.shape[2]; p.W = (int)x.shape[3];
+  const int64_t Cin = x.shape[1], Ch = hs[1], Cout = os[1];
+  p.Cin_p = (int)round_up(Cin, 8); p.Ch_p = (int)round_up(Ch, 64); p.Cout_p = (int)round_up(Cout, 8); p.Cout_alloc = (int)round_up(p.Cout_p, 16);
+  p.Ho = (int)os[2]; p.Wo = (int)os[3]; p.stride = nd.i[0]; p.pt = nd.i[4]; p.pl = nd.i[5];
+  p.has_expand = fe ? 1 : 0; p.has_res = fp->res_value >= 0 ? 1 : 0;
+  auto bounds = [&](const ActSpec& a, float& lo, float& hi) {
+    lo = a.kind == ACT_NONE ? -INFINITY : (a.kind == ACT_RELU ? 0.f : a.a);
+    hi = a.kind == ACT_CLAMP ? a.b : INFINITY;
+  };
+  bounds(fe ? fe->act1 : ActSpec{}, p.lo1, p.hi1);
+  bounds(fd->act1, p.lo2, p.hi2);
+  if (val(nd.outputs[0]).shape[2] != os[2] || val(nd.outputs[0]).shape[3] != os[3] || (int64_t)(p.H + p.pt + nd.i[6] - 3) / p.stride + 1 != p.Ho) return false;
+  // zero-padded hidden channels must stay zero through the expand clamp
+  if (fe && Ch != p.Ch_p && !(p.lo1 <= 0.f && p.hi1 >= 0.f)) return false;
+  if (!mbconv_supported(p, cd_)) return false;
+
+  const int es = dtype_size(cd_);
+  const int64_t K1 = round_up(p.Cin_p, 64);
+  BufRef w1ref, b1ref;
+  std::string fused;
+  double flops = 0, wbytes = 0;
+  if (fe) {
+    const Node& ne = node(fe->root);
+    std::vector<float> w = const_floats(ne.inputs[1]);                     // [Ch][Cin][1][1]
+    std::vector<uint8_t> wp((size_t)(p.Ch_p * K1) * es, 0);
+    for (int64_t o = 0; o < Ch; ++o)
+      for (int64_t c = 0; c < Cin; ++c) store_float(wp.data(), o * K1 + c, w[o * Cin + c] * fe->scale[o], cd_);
+    std::vector<float> b(p.Ch_p, 0.f);
+    for (int64_t o = 0; o < Ch; ++o) b[o] = fe->shift[o];
+    w1ref = weights_ref(add_weights(wp.data(), (int64_t)wp.size()));
+    b1ref = add_f32_vector(b);
+    fused = ne.name;
+    for (int a : fe->absorbed) fused += "," + node(a).name;
+    fused += ",";
+    flops += 2.0 * p.N * p.H * p.W * Ch * Cin;
+    wbytes += (double)wp.size();
+  }
+  BufRef wdref, bdref, w2ref, b2ref;
+  {
+    std::vector<float> w = const_floats(nd.inputs[1]);                     // [Ch][1][1][3][3]
+    std::vector<uint8_t> wp((size_t)(9 * p.Ch_p) * es, 0);
+    for (int64_t c = 0; c < Ch; ++c)
+      for (int t = 0; t < 9; ++t) store_float(wp.data(), (int64_t)t * p.Ch_p + c, w[c * 9 + t] * fd->scale[c], cd_);
+    std::vector<float> b(p.Ch_p, 0.f);
+    for (int64_t c = 0; c < Ch; ++c) b[c] = fd->shift[c];
+    wdref = weights_ref(add_weights(wp.data(), (int64_t)wp.size()));
+    bdref = add_f32_vector(b);
+    fused += nd.name;
+    for (int a : fd->absorbed) fused += "," + node(a).name;
+    flops += 2.0 * p.N * p.Ho * p.Wo * Ch * 9;
+    wbytes += (double)wp.size();
+  }
+  {
+    std::vector<float> w = const_floats(np.inputs[1]);                     // [Cout][Ch][1][1]
+    std::vector<uint8_t> wp((size_t)(p.Cout_alloc * p.Ch_p) * es, 0);
+    for (int64_t o = 0; o < Cout; ++o)
+      for (int64_t c = 0; c < Ch; ++c) store_float(wp.data(), o * p.Ch_p + c, w[o * Ch + c] * fp->scale[o], cd_);
+    std::vector<float> b(p.Cout_alloc, 0.f);
+    for (int64_t o = 0; o < Cout; ++o) b[o] = fp->shift[o];
+    w2ref = weights_ref(add_weights(wp.data(), (int64_t)wp.size()));
+    b2ref = add_f32_vector(b);
+    fused += "," + np.name;
+    for (int a : fp->absorbed) fused += "," + node(a).name;
+    flops += 2.0 * p.N * p.Ho * p.Wo * Cout * Ch;
+    wbytes += (double)wp.size();
+  }
+  LTensor out = alloc(val(fp->out_value).shape, cd_, L_NHWC8);
+  Step s;
+  s.name = val(fp->out_value).name; s.type = "Convolution"; s.fused = fused;
+  s.impl = std::string("tcgen05_") + (cd_ == B200_BF16 ? "bf16" : "f16") + "_mbconv_s" + std::to_string(p.stride) + (fe ? "" : "_noexpand") + (p.has_res ? "_res" : "");
+  s.flops = flops;
+  s.bytes = (double)x.bytes() + (double)out.bytes() + wbytes;
+  BufRef xr = x.buf, yr = out.buf;
+  const int dt = cd_;
+  const bool has_e = fe != nullptr;
+  s.launch = [=](const RunCtx& c) {
+    MbParams q = p;
+    q.x = c.ptr(xr); q.y = c.ptr(yr);
+    q.w1 = has_e ? c.ptr(w1ref) : nullptr; q.b1 = has_e ? reinterpret_cast<const float*>(c.ptr(b1ref)) : nullptr;
+    q.wd = c.ptr(wdref); q.bd = reinterpret_cast<const float*>(c.ptr(bdref));
+    q.w2 = c.ptr(w2ref); q.b2 = reinterpret_cast<const float*>(c.ptr(b2ref));
+    launch_mbconv(q, dt, (cudaStream_t)c.stream);
+  };
+  emit(std::move(s), {&x}, {&out});
+  set(fp->out_value, out);
+  if (fe) mb_done_.insert(fd->emit_at);
+  mb_done_.insert(fp->emit_at);
+  return true;
+}
+
 void Lowerer::lower_conv(const FusedConv& f) {
   const Node& n = node(f.root);
   std::string fused = n.name;
@@ -1039,6 +1184,7 @@ void Lowerer::lower_conv(const FusedConv& f) {
     auto xi = vt_.find(n.inputs[0]);
     if (xi != vt_.end() && xi->second.layout == L_S2D16) { lower_stem_s2d(f, xi->second); return; }
   }
+  if (try_lower_mbconv(f)) return;
   LTensor x = get(n.inputs[0], L_NHWC8);
   const Shape& xs = x.shape;
   const Shape& ws = val(n.inputs[1]).shape;
@@ -1733,7 +1879,7 @@ void Lowerer::lower_node(const Node& n) {
   auto fat = fattn_.find(n.id);
   if (fat != fattn_.end()) { lower_attention(fat->second); return; }
   auto fc = fconv_.find(n.id);
-  if (fc != fconv_.end()) { lower_conv(fc->second); return; }
+  if (fc != fconv_.end()) { if (!mb_done_.count(n.id)) lower_conv(fc->second); return; }
   auto fm = fmvn_.find(n.id);
   if (fm != fmvn_.end()) { lower_mvn(node(fm->second.root), &fm->second); return; }
   auto fe = felt_.find(n.id);

@@ -369,6 +369,7 @@ int b200_compile(const b200_graph* g, const b200_compile_options* opts, b200_net
       conv_tc_init_device();
       conv_tc2_init_device();
       conv_tc3_init_device();
+      mbconv_init_device();
       conv_tc3f_init_device();
       detect_init_device();
       attention_init_device();

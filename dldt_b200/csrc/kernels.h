@@ -114,6 +114,20 @@ struct ConvParams;
 bool conv_small_cin_supported(const ConvParams& p, int cin, int dtype);   // kernels_dw.cu: dense convolution over <= 4 input channels
 void launch_conv_small_cin(const ConvParams& p, int cin, int dtype, cudaStream_t s);
 
+// ---- fused inverted-residual block (mbconv.cu): expand 1x1 -> depthwise 3x3 -> project 1x1 (+ residual) in one tcgen05 kernel ----
+struct MbParams {
+  const void* x; void* y;              // NHWC8: [N][H][W][Cin_p] -> [N][Ho][Wo][Cout_p]
+  const void* w1; const float* b1;     // expand weights [Ch_p][64 * ceil(Cin_p / 64)] (K-major, zero padded), bias [Ch_p]; unused without expand
+  const void* wd; const float* bd;     // depthwise weights [9][Ch_p] in the compute type, bias [Ch_p]
+  const void* w2; const float* b2;     // project weights [Cout_alloc][Ch_p], bias [Cout_alloc]
+  int N, H, W, Cin_p, Ch_p, Cout_p, Cout_alloc, Ho, Wo, stride, pt, pl;   // Ch_p: hidden channels padded to a multiple of 64
+  int has_expand, has_res;             // has_res: y += x (stride 1, Cin_p == Cout_p)
+  float lo1, hi1, lo2, hi2;            // clamp bounds of the expand / depthwise activations (-inf / +inf: none)
+};
+bool mbconv_supported(const MbParams& p, int dtype);
+void launch_mbconv(const MbParams& p, int dtype, cudaStream_t s);
+void mbconv_init_device();
+
 // ---- pooling ---------------------------------------------------------------------------------
 struct PoolParams {
   const void* x; void* y;
