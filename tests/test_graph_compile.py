@@ -64,10 +64,23 @@ def test_resnet50_fp32_uses_cuda_core_conv():
 def test_mobilenet_schedule():
     net = dry(zoo.mobilenet_v2(batch=64))
     eg = net.get_exec_graph_info()
+    # 14 of the 17 inverted-residual blocks run as ONE kernel each (expand -> depthwise -> project (+ add), mbconv.cu); the three 7x7 blocks
+    # (160 -> 960 channels: the X tile, the weight chunks and the staging do not fit 227 KB) keep their three kernels
+    mb = [e for e in eg if "_mbconv_" in e["impl"]]
     dw = [e for e in eg if e["impl"].startswith("dw_")]
-    assert len(dw) == 17 and kinds(net)["Convolution"] == 52
+    assert len(mb) == 14 and len(dw) == 3 and kinds(net)["Convolution"] == 26
+    assert sum(1 for e in mb if e["impl"].endswith("_res")) == 8        # residual adds taken from the block input tile in shared memory
     assert all(len(e["fused"]) >= 2 for e in dw)                        # BN (+Clamp) folded into the depthwise kernel
     assert not any(e["type"] == "Eltwise" for e in eg)                  # the 10 residual adds ride on the project convs
+    assert net.get_exec_graph_info()[0]["impl"].endswith("_s2d_stem")   # 3x3 / stride-2 first convolution on the space-to-depth stem path
+
+
+def test_mobilenet_schedule_without_block_fusion(monkeypatch):
+    monkeypatch.setenv("B200_FUSE_MBCONV", "0")
+    net = dry(zoo.mobilenet_v2(batch=64))
+    eg = net.get_exec_graph_info()
+    dw = [e for e in eg if e["impl"].startswith("dw_")]
+    assert len(dw) == 17 and kinds(net)["Convolution"] == 52
 
 
 def test_bert_schedule():
