@@ -15,7 +15,12 @@
 // and after the last chunk D_p + b2 (+ the centre pixels of the X tile: the residual) goes out through one TMA store.  Without an expand
 // convolution (the first block, t = 1) step 1/2 is a TMA load of the chunk straight into the step-2 layout.
 //
-//   warp 0-7  compute (TMEM lane quarter = warp % 4, column half = warp / 4)     warp 8  TMA producer     warp 9  MMA issuer + TMEM alloc
+//   warp 0-3  tile epilogue (the compute warps go straight on to the next tile)      warp 12  TMA producer (X tile double-buffered, weights
+//   warp 4-11 compute: expand accumulators -> hidden chunk -> depthwise -> A2                  resident, where they fit)
+//   warp 13   MMA issuer + TMEM alloc
+// (Variants measured on MobileNetV2 b64: dedicated warps for step 2 running ahead of the depthwise warps were SLOWER (0.91 vs 0.84 ms): one
+// warp per scheduler is latency-bound on the TMEM -> clamp -> pack chain; ncu shows the kernel issue-bound at ~11k warp instructions per
+// 64-channel chunk, 23 per depthwise output.)
 //
 // HBM bytes per block: x + y + weights (MobileNetV2 b64: 1.72 GB -> ~0.4 GB per inference batch), 17 x 3 kernels -> 17.
 #include <cuda.h>
@@ -39,9 +44,11 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_tiled_fn();
 namespace {
 using namespace tc;
 
-constexpr int MB_THREADS = 320;
-constexpr int MB_COMPUTE_WARPS = 8;
-constexpr int MB_TMA_WARP = 8, MB_MMA_WARP = 9;
+constexpr int MB_E_WARPS = 4;             // warps 0-3: expand accumulators -> hidden chunk (TMEM lane quarter = warp)
+constexpr int MB_D_WARPS = 8;             // warps 4-11: depthwise stage + tile epilogue (TMEM lane quarter = warp % 4)
+constexpr int MB_TMA_WARP = 12, MB_MMA_WARP = 13;
+constexpr int MB_THREADS = 448;
+constexpr int MB_D_THREADS = MB_D_WARPS * 32;
 constexpr int MB_TW = 16;
 constexpr int MB_SMEM_LIMIT = 232448;
 
@@ -58,18 +65,22 @@ __host__ __device__ inline MbGeom mb_geom(int stride, int Cin_p, int Ch_p) {
   return g;
 }
 
-struct MbPlan { uint32_t xa_kb, xa_off, h_bytes, h_off, w1_bytes, w1_off, w2_bytes, w2_off, a2_off, out_off, out_bytes, wd_off, b1_off, bd_off, b2_off, bar_off, total; };
-__host__ __device__ inline MbPlan mb_plan(const MbGeom& g, int has_expand, int Ch_p, int Cout_p, int Cout_alloc) {
+constexpr int MB_MAXW = 8;                // weight ring: at most this many 64-channel chunks of W1 / W2 in shared memory
+struct MbPlan { uint32_t nxb, nw, xa_kb, xa_bytes, xa_off, h_bytes, h_off, w1_bytes, w1_off, w2_bytes, w2_off, a2_off, out_off, out_bytes, wd_off, b1_off, bd_off, b2_off, bar_off, total; };
+__host__ __device__ inline MbPlan mb_plan_n(const MbGeom& g, int has_expand, int Ch_p, int Cout_p, int Cout_alloc, uint32_t nxb, uint32_t nw) {
   MbPlan p;
   uint32_t o = 0;
+  p.nxb = nxb;
+  p.nw = nw;
   p.xa_kb = (uint32_t)g.MT * 128u * 128u;                    // one 64-channel k-block of the X tile: MT x 128 rows of 128 bytes
-  p.xa_off = o; o += has_expand ? (uint32_t)g.kb1 * p.xa_kb : 0u;
+  p.xa_bytes = (uint32_t)g.kb1 * p.xa_kb;
+  p.xa_off = o; o += has_expand ? nxb * p.xa_bytes : 0u;
   p.h_bytes = ((uint32_t)g.rows_in * 128u + 1023u) & ~1023u;
   p.h_off = o; o += 2u * p.h_bytes;
   p.w1_bytes = (uint32_t)g.kb1 * 64u * 128u;
-  p.w1_off = o; o += has_expand ? 2u * p.w1_bytes : 0u;
+  p.w1_off = o; o += has_expand ? nw * p.w1_bytes : 0u;
   p.w2_bytes = (uint32_t)Cout_alloc * 128u;
-  p.w2_off = o; o += 2u * p.w2_bytes;
+  p.w2_off = o; o += nw * p.w2_bytes;
   o = (o + 1023u) & ~1023u;
   p.a2_off = o; o += 128u * 128u;
   p.out_bytes = (128u * (uint32_t)Cout_p * 2u + 127u) & ~127u;
@@ -79,9 +90,26 @@ __host__ __device__ inline MbPlan mb_plan(const MbGeom& g, int has_expand, int C
   p.bd_off = o; o += (uint32_t)Ch_p * 4u;
   p.b2_off = o; o += (uint32_t)Cout_alloc * 4u;
   o = (o + 15u) & ~15u;
-  p.bar_off = o; o += 256u;
+  p.bar_off = o; o += 512u;
   p.total = o + 1024u;                                       // alignment slack of the dynamic shared-memory base
   return p;
+}
+// Shared-memory budget, in order of what it buys: (1) ALL weight chunks resident (nw == chunks: loaded once per CTA instead of once per
+// tile, and no chunk ever waits for the round trip "project MMAs of chunk c - nw done -> TMA -> expand MMAs of chunk c"), (2) two X tiles
+// (the next tile's load overlaps this tile's chunks), (3) as deep a weight ring as fits.
+__host__ __device__ inline MbPlan mb_plan(const MbGeom& g, int has_expand, int Ch_p, int Cout_p, int Cout_alloc) {
+  const uint32_t nwmax = (uint32_t)(g.nchunk < MB_MAXW ? g.nchunk : MB_MAXW);
+  const bool resident_possible = g.nchunk <= MB_MAXW;
+  for (uint32_t nw = nwmax; nw >= 1u; --nw) {
+    if (nw == 1u && nwmax > 1u) break;
+    for (uint32_t nxb = 2u; nxb >= 1u; --nxb) {
+      if (nxb == 2u && !has_expand) continue;
+      const MbPlan p = mb_plan_n(g, has_expand, Ch_p, Cout_p, Cout_alloc, nxb, nw);
+      if (p.total <= (uint32_t)MB_SMEM_LIMIT) return p;
+    }
+    (void)resident_possible;
+  }
+  return mb_plan_n(g, has_expand, Ch_p, Cout_p, Cout_alloc, 1u, nwmax > 1u ? 2u : 1u);      // does not fit: mbconv_supported() rejects it
 }
 
 struct MbArgs {
@@ -111,42 +139,44 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
   constexpr int TH = STRIDE == 1 ? 8 : 4;
   constexpr int IH = (TH - 1) * STRIDE + 3, IW = (MB_TW - 1) * STRIDE + 3;
   constexpr int ROWS_IN = IH * IW;
-  constexpr int MT = (ROWS_IN + 127) / 128;
-  constexpr int ACC_E_COLS = MT * 64;                         // expand accumulators (one per 128-row M tile of the halo tile)
+  constexpr int MT = (ROWS_IN + 127) / 128;                   // 128-row M tiles of the halo tile (expand accumulators: MT x 64 TMEM columns)
   const MbGeom g = mb_geom(STRIDE, p.Cin_p, p.Ch_p);
   const MbPlan plan = mb_plan(g, EXPAND ? 1 : 0, p.Ch_p, p.Cout_p, p.Cout_alloc);
   const int kb1 = g.kb1, nchunk = g.nchunk;
+  const bool two_x = plan.nxb == 2u;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + plan.bar_off);
-  uint64_t* xfull = bars + 0;      // X tile landed (TMA)
-  uint64_t* xempty = bars + 1;     // X tile no longer read (expand MMAs complete, residual read)
-  uint64_t* wfull = bars + 2;      // [2] weight chunk landed
-  uint64_t* wempty = bars + 4;     // [2] weight chunk consumed (project MMAs of the chunk complete)
-  uint64_t* efull = bars + 6;      // expand accumulators of the chunk complete
-  uint64_t* eempty = bars + 7;     // ... drained by the eight compute warps
-  uint64_t* hfull = bars + 8;      // [2] (no expand) hidden chunk landed (TMA)
-  uint64_t* hempty = bars + 10;    // [2] (no expand) hidden chunk consumed by the depthwise stage
-  uint64_t* a2full = bars + 12;    // depthwise output chunk staged as the project A operand
-  uint64_t* a2empty = bars + 13;   // ... consumed by the project MMAs
-  uint64_t* pfull = bars + 14;     // project accumulator of the tile complete
-  uint64_t* pempty = bars + 15;    // ... drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* xfull = bars + 0;      // [2] X tile landed (TMA)
+  uint64_t* xempty = bars + 2;     // [2] X tile no longer read (expand MMAs complete, residual read)
+  uint64_t* efull = bars + 4;      // expand accumulators of the chunk complete
+  uint64_t* eempty = bars + 5;     // ... drained by the four E warps
+  uint64_t* hfull = bars + 6;      // [2] hidden chunk in shared memory (E warps, or the TMA without an expand convolution)
+  uint64_t* hempty = bars + 8;     // [2] hidden chunk consumed by the depthwise stage
+  uint64_t* a2full = bars + 10;    // depthwise output chunk staged as the project A operand
+  uint64_t* a2empty = bars + 11;   // ... consumed by the project MMAs
+  uint64_t* pfull = bars + 12;     // project accumulator of the tile complete
+  uint64_t* pempty = bars + 13;    // ... drained
+  uint64_t* wfull = bars + 16;     // [MB_MAXW] weight chunk landed
+  uint64_t* wempty = bars + 24;    // [MB_MAXW] weight chunk consumed (project MMAs of the chunk complete)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  const uint32_t nw = plan.nw;
+  const bool w_resident = nw >= (uint32_t)nchunk;               // every chunk has its own stage: loaded during the first tile only
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = args.num_tiles;
 
   if (threadIdx.x == 0) {
-    ptx::mbar_init(xfull, 1); ptx::mbar_init(xempty, 1);
     for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&wfull[i], 1); ptx::mbar_init(&wempty[i], 1);
-      ptx::mbar_init(&hfull[i], 1); ptx::mbar_init(&hempty[i], MB_COMPUTE_WARPS);
+      ptx::mbar_init(&xfull[i], 1); ptx::mbar_init(&xempty[i], 1);
+      ptx::mbar_init(&hfull[i], 1); ptx::mbar_init(&hempty[i], MB_D_WARPS);
     }
-    ptx::mbar_init(efull, 1); ptx::mbar_init(eempty, MB_COMPUTE_WARPS);
-    ptx::mbar_init(a2full, MB_COMPUTE_WARPS); ptx::mbar_init(a2empty, 1);
-    ptx::mbar_init(pfull, 1); ptx::mbar_init(pempty, MB_COMPUTE_WARPS);
+    for (int i = 0; i < MB_MAXW; ++i) { ptx::mbar_init(&wfull[i], 1); ptx::mbar_init(&wempty[i], 1); }
+    ptx::mbar_init(efull, 1); ptx::mbar_init(eempty, MB_D_WARPS);
+    ptx::mbar_init(a2full, MB_D_WARPS); ptx::mbar_init(a2empty, 1);
+    ptx::mbar_init(pfull, 1); ptx::mbar_init(pempty, MB_E_WARPS);
     ptx::fence_mbar_init();
   }
   if (warp == MB_TMA_WARP && lane == 0) {
@@ -159,6 +189,18 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
     ptx::tmem_alloc(tmem_slot, 512);
     ptx::tmem_relinquish();
   }
+  if (warp < MB_E_WARPS + MB_D_WARPS) {
+    // constants -> shared memory (not written by any kernel: fetched before the programmatic-launch dependency resolves)
+    const int t = threadIdx.x;
+    const uint32_t* wd_g = reinterpret_cast<const uint32_t*>(p.wd);
+    uint32_t* wd_s = reinterpret_cast<uint32_t*>(smem_al + plan.wd_off);
+    for (int i = t; i < 9 * p.Ch_p / 2; i += 384) wd_s[i] = __ldg(wd_g + i);
+    float* b1_s = reinterpret_cast<float*>(smem_al + plan.b1_off);
+    float* bd_s = reinterpret_cast<float*>(smem_al + plan.bd_off);
+    float* b2_s = reinterpret_cast<float*>(smem_al + plan.b2_off);
+    for (int i = t; i < p.Ch_p; i += 384) { b1_s[i] = EXPAND ? __ldg(p.b1 + i) : 0.f; bd_s[i] = __ldg(p.bd + i); }
+    for (int i = t; i < p.Cout_alloc; i += 384) b2_s[i] = __ldg(p.b2 + i);
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -166,23 +208,74 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
   const uint32_t acc_e = tmem_base, acc_p = tmem_base + 256u;      // columns [0, 192) expand, [256, 512) project
   ptx::grid_launch_dependents();
 
-  if (warp < MB_COMPUTE_WARPS) {
-    // ======================================= compute warps =======================================
-    const int q = warp & 3, half = warp >> 2;
-    const int t = threadIdx.x;
-    // constants -> shared memory (before the dependency wait: they are not written by any kernel)
-    {
-      const uint32_t* wd_g = reinterpret_cast<const uint32_t*>(p.wd);
-      uint32_t* wd_s = reinterpret_cast<uint32_t*>(smem_al + plan.wd_off);
-      for (int i = t; i < 9 * p.Ch_p / 2; i += 256) wd_s[i] = __ldg(wd_g + i);
-      float* b1_s = reinterpret_cast<float*>(smem_al + plan.b1_off);
-      float* bd_s = reinterpret_cast<float*>(smem_al + plan.bd_off);
-      float* b2_s = reinterpret_cast<float*>(smem_al + plan.b2_off);
-      for (int i = t; i < p.Ch_p; i += 256) { b1_s[i] = EXPAND ? __ldg(p.b1 + i) : 0.f; bd_s[i] = __ldg(p.bd + i); }
-      for (int i = t; i < p.Cout_alloc; i += 256) b2_s[i] = __ldg(p.b2 + i);
-      ptx::named_bar_sync(1, 256);
-    }
+  if (warp < MB_E_WARPS) {
+    // ======================================= epilogue warps =======================================
+    const int q = warp;
+    const int te = threadIdx.x;                                 // 0 .. 127
     ptx::grid_dependency_wait();
+    // ---- tile epilogue (these warps, so that the depthwise warps go straight on to the next tile): project accumulator + b2 (+ residual =
+    // centre pixels of the X tile) -> staging -> one TMA store ----
+    auto tile_epilogue = [&](int tile, uint32_t it) {
+      const int n = tile / (args.tiles_h * args.tiles_w);
+      const int rem = tile - n * args.tiles_h * args.tiles_w;
+      const int th = rem / args.tiles_w;
+      const int oh0 = th * TH, ow0 = (rem - th * args.tiles_w) * MB_TW;
+      ptx::mbar_wait(pfull, it & 1u);
+      ptx::tc_fence_after();
+      if (te == 0) ptx::bulk_wait_read<0>();                     // the previous tile's store has finished reading the staging tile
+      ptx::named_bar_sync(2, MB_E_WARPS * 32);
+      const int prow = q * 32 + lane;                            // output pixel of the tile (row-major TH x 16)
+      const uint32_t stage_row = smem_base + plan.out_off + (uint32_t)prow * (uint32_t)p.Cout_p * 2u;
+      const int poh = prow / MB_TW, pow_ = prow - poh * MB_TW;
+      const uint32_t xr = (uint32_t)((poh * STRIDE + p.pt) * IW + pow_ * STRIDE + p.pl);     // its centre pixel in the halo tile
+      const uint32_t xbuf = smem_base + plan.xa_off + (two_x ? (it & 1u) : 0u) * plan.xa_bytes;
+      for (int col = 0; col < p.Cout_alloc; col += 16) {
+        uint32_t v[2][8];
+        tmem_ld_32x8(acc_p + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v[0]);
+        tmem_ld_32x8(acc_p + ((uint32_t)(q * 32) << 16) + (uint32_t)col + 8u, v[1]);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int cl = col + hh * 8;
+          const uint32_t b2a = smem_base + plan.b2_off + (uint32_t)cl * 4u;
+          const uint4 ba = ptx::ld_shared_v4(b2a), bb = ptx::ld_shared_v4(b2a + 16u);
+          float f[8];
+          f[0] = __uint_as_float(v[hh][0]) + __uint_as_float(ba.x); f[1] = __uint_as_float(v[hh][1]) + __uint_as_float(ba.y);
+          f[2] = __uint_as_float(v[hh][2]) + __uint_as_float(ba.z); f[3] = __uint_as_float(v[hh][3]) + __uint_as_float(ba.w);
+          f[4] = __uint_as_float(v[hh][4]) + __uint_as_float(bb.x); f[5] = __uint_as_float(v[hh][5]) + __uint_as_float(bb.y);
+          f[6] = __uint_as_float(v[hh][6]) + __uint_as_float(bb.z); f[7] = __uint_as_float(v[hh][7]) + __uint_as_float(bb.w);
+          if (cl < p.Cout_p && prow < TH * MB_TW) {
+            if (EXPAND && p.has_res) {
+              float rr[8];
+              const uint32_t kb = (uint32_t)cl >> 6, ch = ((uint32_t)cl & 63u) >> 3;
+              unpack8<T>(ptx::ld_shared_v4(xbuf + kb * plan.xa_kb + xr * 128u + ((ch ^ (xr & 7u)) << 4)), rr);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] += rr[e];
+            }
+            ptx::st_shared_v4(stage_row + (uint32_t)cl * 2u, make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7])));
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(pempty);
+      ptx::fence_proxy_async();
+      ptx::named_bar_sync(2, MB_E_WARPS * 32);
+      if (te == 0) {
+        if (EXPAND && p.has_res) ptx::mbar_arrive(&xempty[two_x ? (it & 1u) : 0u]);   // residual read: the producer may refill this X tile
+        ptx::tma_store_4d(&args.tm_y, smem_base + plan.out_off, 0, ow0, oh0, n);
+        ptx::bulk_commit();
+      }
+    };
+    {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) tile_epilogue(tile, it);
+    }
+    if (te == 0) ptx::bulk_wait_read<0>();
+  } else if (warp < MB_E_WARPS + MB_D_WARPS) {
+    // ======================================= compute warps: expand accumulators -> hidden chunk -> depthwise -> project A operand =======================================
+    const int t = threadIdx.x - MB_E_WARPS * 32;
+    const int q = warp & 3, half = (warp - MB_E_WARPS) >> 2;    // TMEM lane quarter, column half of the expand accumulators
     // depthwise work split: 16-byte channel group cc (8 channels) x pixel group pg
     constexpr int PXT = STRIDE == 1 ? 4 : 2;                    // output pixels per thread (adjacent in a row)
     constexpr int NIN = (PXT - 1) * STRIDE + 3;                 // input columns they read
@@ -190,16 +283,13 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
     const int orow = STRIDE == 1 ? (pg >> 2) : (pg >> 3);
     const int ocol0 = STRIDE == 1 ? (pg & 3) * 4 : (pg & 7) * 2;
     uint32_t gc = 0;                                            // chunks processed so far (all tiles)
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int n = tile / (args.tiles_h * args.tiles_w);
-      const int rem = tile - n * args.tiles_h * args.tiles_w;
-      const int th = rem / args.tiles_w;
-      const int oh0 = th * TH, ow0 = (rem - th * args.tiles_w) * MB_TW;
-      const int ih0 = oh0 * STRIDE - p.pt, iw0 = ow0 * STRIDE - p.pl;     // image coordinates of halo-tile pixel (0, 0)
-      // which of this thread's halo-tile rows (one per M tile) lie inside the image
-      uint32_t inside = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      uint32_t inside = 0;                                      // which of this thread's halo rows (one per M tile) lie inside the image
       if (EXPAND) {
+        const int n = tile / (args.tiles_h * args.tiles_w);
+        const int rem = tile - n * args.tiles_h * args.tiles_w;
+        const int th = rem / args.tiles_w;
+        const int ih0 = th * TH * STRIDE - p.pt, iw0 = (rem - th * args.tiles_w) * MB_TW * STRIDE - p.pl;   // image coordinates of halo pixel (0, 0)
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
           const int r = m * 128 + q * 32 + lane;
@@ -211,7 +301,8 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
         const uint32_t hb = gc & 1u;
         const uint32_t hbuf = smem_base + plan.h_off + hb * plan.h_bytes;
         if (EXPAND) {
-          // ---- expand accumulators -> + b1, clamp, zero outside the image -> 16-bit hidden chunk in shared memory ----
+          // ---- expand accumulators -> + b1, clamp, zero outside the image (the depthwise's zero padding is padding of the EXPANDED
+          // tensor) -> 16-bit hidden chunk in the 128-byte-swizzled pixel-row layout the depthwise stage reads ----
           ptx::mbar_wait(efull, gc & 1u);
           ptx::tc_fence_after();
           const uint32_t b1a = smem_base + plan.b1_off + (uint32_t)(c * 64 + half * 32) * 4u;
@@ -221,6 +312,11 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
             uint32_t v[32];
             ptx::tmem_ld_32x32(acc_e + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * 64 + half * 32), v);
             ptx::tmem_ld_wait();
+            if (m == MT - 1) {                                  // this warp's part of the chunk is in registers
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(eempty);
+            }
             const bool in = (inside >> m) & 1u;
             if (r < ROWS_IN) {
 #pragma unroll
@@ -238,10 +334,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
               }
             }
           }
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(eempty);
-          ptx::named_bar_sync(1, 256);                            // the whole chunk is in shared memory
+          ptx::named_bar_sync(1, MB_D_THREADS);                   // the whole chunk is in shared memory (two buffers: the chunk before last is read out)
         } else {
           ptx::mbar_wait(&hfull[hb], (gc >> 1) & 1u);
         }
@@ -295,81 +388,51 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(a2full);
       }
-      // ---- tile epilogue: project accumulator + b2 (+ residual = centre pixels of the X tile) -> staging -> TMA store ----
-      ptx::mbar_wait(pfull, it & 1u);
-      ptx::tc_fence_after();
-      if (t == 0) ptx::bulk_wait_read<0>();                       // the previous tile's store has finished reading the staging tile
-      ptx::named_bar_sync(1, 256);
-      {
-        const int prow = q * 32 + lane;                          // output pixel of the tile (row-major TH x 16)
-        const int ncol_h = p.Cout_alloc >> 1;                    // columns of this warp's half (multiple of 8)
-        const uint32_t stage_row = smem_base + plan.out_off + (uint32_t)prow * (uint32_t)p.Cout_p * 2u;
-        const int poh = prow / MB_TW, pow_ = prow - poh * MB_TW;
-        const uint32_t xr = (uint32_t)((poh * STRIDE + p.pt) * IW + pow_ * STRIDE + p.pl);     // its centre pixel in the halo tile
-        for (int j = 0; j < ncol_h; j += 8) {
-          const int col = half * ncol_h + j;
-          uint32_t v[8];
-          tmem_ld_32x8(acc_p + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
-          const uint32_t b2a = smem_base + plan.b2_off + (uint32_t)col * 4u;
-          const uint4 ba = ptx::ld_shared_v4(b2a), bb = ptx::ld_shared_v4(b2a + 16u);
-          ptx::tmem_ld_wait();
-          float f[8];
-          f[0] = __uint_as_float(v[0]) + __uint_as_float(ba.x); f[1] = __uint_as_float(v[1]) + __uint_as_float(ba.y);
-          f[2] = __uint_as_float(v[2]) + __uint_as_float(ba.z); f[3] = __uint_as_float(v[3]) + __uint_as_float(ba.w);
-          f[4] = __uint_as_float(v[4]) + __uint_as_float(bb.x); f[5] = __uint_as_float(v[5]) + __uint_as_float(bb.y);
-          f[6] = __uint_as_float(v[6]) + __uint_as_float(bb.z); f[7] = __uint_as_float(v[7]) + __uint_as_float(bb.w);
-          if (col < p.Cout_p && prow < TH * MB_TW) {
-            if (EXPAND && p.has_res) {
-              float rr[8];
-              const uint32_t kb = (uint32_t)col >> 6, ch = ((uint32_t)col & 63u) >> 3;
-              unpack8<T>(ptx::ld_shared_v4(smem_base + plan.xa_off + kb * plan.xa_kb + xr * 128u + ((ch ^ (xr & 7u)) << 4)), rr);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] += rr[e];
-            }
-            ptx::st_shared_v4(stage_row + (uint32_t)col * 2u, make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7])));
-          }
-        }
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(pempty);
-      ptx::fence_proxy_async();
-      ptx::named_bar_sync(1, 256);
-      if (t == 0) {
-        if (EXPAND && p.has_res) ptx::mbar_arrive(xempty);        // residual read: the producer may load the next X tile
-        ptx::tma_store_4d(&args.tm_y, smem_base + plan.out_off, 0, ow0, oh0, n);
-        ptx::bulk_commit();
-      }
     }
-    if (t == 0) ptx::bulk_wait_read<0>();
   } else if (warp == MB_TMA_WARP) {
     // ======================================= TMA producer =======================================
     if (lane == 0) {
       ptx::grid_dependency_wait();
       uint32_t gc = 0, it = 0;
+      uint32_t ws = 0, wph = 0;                                  // weight ring stage / phase
+      auto load_x = [&](int tile, uint32_t k) {                  // X tile of the k-th tile of this CTA
+        const int n = tile / (args.tiles_h * args.tiles_w);
+        const int rem = tile - n * args.tiles_h * args.tiles_w;
+        const int th = rem / args.tiles_w;
+        const int ih0 = th * TH * STRIDE - p.pt, iw0 = (rem - th * args.tiles_w) * MB_TW * STRIDE - p.pl;
+        const uint32_t xb = two_x ? (k & 1u) : 0u, use = two_x ? (k >> 1) : k;
+        ptx::mbar_wait(&xempty[xb], (use & 1u) ^ 1u);
+        ptx::mbar_arrive_expect_tx(&xfull[xb], (uint32_t)(kb1 * ROWS_IN * 128));
+        for (int kb = 0; kb < kb1; ++kb)
+          ptx::tma_load_4d(smem_base + plan.xa_off + xb * plan.xa_bytes + (uint32_t)kb * plan.xa_kb, &args.tm_x, &xfull[xb], kb * 64, iw0, ih0, n);
+      };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int n = tile / (args.tiles_h * args.tiles_w);
         const int rem = tile - n * args.tiles_h * args.tiles_w;
         const int th = rem / args.tiles_w;
         const int ih0 = th * TH * STRIDE - p.pt, iw0 = (rem - th * args.tiles_w) * MB_TW * STRIDE - p.pl;
-        if (EXPAND) {
-          ptx::mbar_wait(xempty, (it & 1u) ^ 1u);
-          ptx::mbar_arrive_expect_tx(xfull, (uint32_t)(kb1 * ROWS_IN * 128));
-          for (int kb = 0; kb < kb1; ++kb) ptx::tma_load_4d(smem_base + plan.xa_off + (uint32_t)kb * plan.xa_kb, &args.tm_x, xfull, kb * 64, iw0, ih0, n);
-        }
+        if (EXPAND && (it == 0 || !two_x)) load_x(tile, it);
         for (int c = 0; c < nchunk; ++c, ++gc) {
-          const uint32_t wb = gc & 1u;
-          ptx::mbar_wait(&wempty[wb], ((gc >> 1) & 1u) ^ 1u);
-          ptx::mbar_arrive_expect_tx(&wfull[wb], (EXPAND ? plan.w1_bytes : 0u) + plan.w2_bytes);
-          if (EXPAND)
-            for (int kb = 0; kb < kb1; ++kb)
-              ptx::tma_load_2d(smem_base + plan.w1_off + wb * plan.w1_bytes + (uint32_t)kb * 8192u, &args.tm_w1, &wfull[wb], kb * 64, c * 64);
-          ptx::tma_load_2d(smem_base + plan.w2_off + wb * plan.w2_bytes, &args.tm_w2, &wfull[wb], c * 64, 0);
-          if (!EXPAND) {
-            ptx::mbar_wait(&hempty[wb], ((gc >> 1) & 1u) ^ 1u);
-            ptx::mbar_arrive_expect_tx(&hfull[wb], (uint32_t)(ROWS_IN * 128));
-            ptx::tma_load_4d(smem_base + plan.h_off + wb * plan.h_bytes, &args.tm_x, &hfull[wb], c * 64, iw0, ih0, n);
+          if (!w_resident || it == 0) {
+            if (!w_resident) ptx::mbar_wait(&wempty[ws], wph ^ 1u);
+            ptx::mbar_arrive_expect_tx(&wfull[ws], (EXPAND ? plan.w1_bytes : 0u) + plan.w2_bytes);
+            if (EXPAND)
+              for (int kb = 0; kb < kb1; ++kb)
+                ptx::tma_load_2d(smem_base + plan.w1_off + ws * plan.w1_bytes + (uint32_t)kb * 8192u, &args.tm_w1, &wfull[ws], kb * 64, c * 64);
+            ptx::tma_load_2d(smem_base + plan.w2_off + ws * plan.w2_bytes, &args.tm_w2, &wfull[ws], c * 64, 0);
+            if (++ws == nw) { ws = 0; wph ^= 1u; }
           }
+          if (!EXPAND) {
+            const uint32_t hb = gc & 1u;
+            ptx::mbar_wait(&hempty[hb], ((gc >> 1) & 1u) ^ 1u);
+            ptx::mbar_arrive_expect_tx(&hfull[hb], (uint32_t)(ROWS_IN * 128));
+            ptx::tma_load_4d(smem_base + plan.h_off + hb * plan.h_bytes, &args.tm_x, &hfull[hb], c * 64, iw0, ih0, n);
+          }
+          // The next tile's X tile goes into the other buffer while this tile's last chunks are computed.  Only AFTER the tile's last weight
+          // chunk: the buffer is released by the epilogue of the tile before this one, which the E warps take after producing this tile's
+          // first two chunks - a producer waiting for it earlier would hold back the very weights those chunks need (seen as a hang with
+          // >= 3 tiles per CTA and a residual)
+          if (EXPAND && two_x && c + 1 == nchunk && tile + (int)gridDim.x < num_tiles) load_x(tile + (int)gridDim.x, it + 1u);
         }
       }
     }
@@ -379,16 +442,19 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
       constexpr uint32_t idesc_e = ptx::make_idesc_f16(TcType<T>::is_bf16, 128, 64);
       const uint32_t idesc_p = ptx::make_idesc_f16(TcType<T>::is_bf16, 128, p.Cout_alloc);
       uint32_t gc = 0, it = 0;
-      // issue the expand MMAs of global chunk `k` (tile-local chunk index does not matter: the X tile is the tile's, the weights the chunk's)
+      uint32_t xoff = 0;                                         // X tile of the current tile
+      uint32_t es = 0, eph = 0, ps = 0, pph = 0;                 // weight ring position of the expand / project streams (resident: phase stays 0)
+      // expand MMAs of global chunk k (the X tile is the current tile's, the weights the chunk's)
       auto expand = [&](uint32_t k) {
-        const uint32_t wb = k & 1u;
-        ptx::mbar_wait(&wfull[wb], (k >> 1) & 1u);
+        const uint32_t wb = es;
+        ptx::mbar_wait(&wfull[wb], eph);
+        if (++es == nw) { es = 0; if (!w_resident) eph ^= 1u; }
         ptx::mbar_wait(eempty, (k & 1u) ^ 1u);
         ptx::tc_fence_after();
 #pragma unroll
         for (int m = 0; m < MT; ++m)
           for (int kb = 0; kb < kb1; ++kb) {
-            const uint64_t da = ptx::make_smem_desc_sw128(smem_base + plan.xa_off + (uint32_t)kb * plan.xa_kb + (uint32_t)m * 16384u);
+            const uint64_t da = ptx::make_smem_desc_sw128(smem_base + plan.xa_off + xoff + (uint32_t)kb * plan.xa_kb + (uint32_t)m * 16384u);
             const uint64_t db = ptx::make_smem_desc_sw128(smem_base + plan.w1_off + wb * plan.w1_bytes + (uint32_t)kb * 8192u);
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16) ptx::umma_f16(acc_e + (uint32_t)(m * 64), da + 2u * k16, db + 2u * k16, idesc_e, (uint32_t)(kb | k16));
@@ -396,16 +462,19 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
         ptx::umma_commit(efull);
       };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t xb = two_x ? (it & 1u) : 0u, xuse = two_x ? (it >> 1) : it;
         if (EXPAND) {
-          ptx::mbar_wait(xfull, it & 1u);
+          xoff = xb * plan.xa_bytes;
+          ptx::mbar_wait(&xfull[xb], xuse & 1u);
           expand(gc);
         }
         for (int c = 0; c < nchunk; ++c, ++gc) {
-          const uint32_t wb = gc & 1u;
-          // the next chunk's expand MMAs go out BEFORE this chunk's project MMAs are waited for: the compute warps find the next expand
-          // accumulator ready when they come back from the depthwise stage
+          const uint32_t wb = ps;
+          // the next chunk's expand MMAs go out BEFORE this chunk's project MMAs are waited for: the E warps find the next expand
+          // accumulator ready as soon as they have drained this one
           if (EXPAND && c + 1 < nchunk) expand(gc + 1);
-          if (!EXPAND) ptx::mbar_wait(&wfull[wb], (gc >> 1) & 1u);
+          if (!EXPAND) ptx::mbar_wait(&wfull[wb], pph);
+          if (++ps == nw) { ps = 0; if (!w_resident) pph ^= 1u; }
           if (c == 0) ptx::mbar_wait(pempty, (it & 1u) ^ 1u);     // the previous tile's epilogue has drained the project accumulator
           ptx::mbar_wait(a2full, gc & 1u);
           ptx::tc_fence_after();
@@ -414,10 +483,10 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
 #pragma unroll
           for (int k16 = 0; k16 < 4; ++k16) ptx::umma_f16(acc_p, da + 2u * k16, db + 2u * k16, idesc_p, (uint32_t)(c | k16));
           ptx::umma_commit(a2empty);
-          ptx::umma_commit(&wempty[wb]);
+          if (!w_resident) ptx::umma_commit(&wempty[wb]);
           if (c + 1 == nchunk) {
             ptx::umma_commit(pfull);
-            if (EXPAND && !p.has_res) ptx::umma_commit(xempty);   // (with a residual the epilogue releases the X tile)
+            if (EXPAND && !p.has_res) ptx::umma_commit(&xempty[xb]);   // (with a residual the epilogue releases the X tile)
           }
         }
       }
@@ -469,6 +538,12 @@ void launch_mb(const MbParams& p, bool bf16, cudaStream_t s) {
   }
   if (p.has_expand) a.tm_w1 = make_tmap_2d(p.w1, bf16, (uint64_t)g.kb1 * 64, (uint64_t)p.Ch_p, (uint64_t)g.kb1 * 128, 64, 64);
   a.tm_w2 = make_tmap_2d(p.w2, bf16, (uint64_t)p.Ch_p, (uint64_t)p.Cout_alloc, (uint64_t)p.Ch_p * 2, 64, (uint32_t)p.Cout_alloc);
+  {
+    static const bool dbg = [] { const char* e = getenv("B200_DEBUG_MBCONV"); return e && e[0] == '1'; }();
+    if (dbg)
+      fprintf(stderr, "b200 mbconv: %dx%dx%d -> hidden %d -> %d, stride %d, expand %d res %d: tiles %d, chunks %d, weight stages %u, X tiles %u, smem %u\n", p.H, p.W,
+              p.Cin_p, p.Ch_p, p.Cout_p, p.stride, p.has_expand, p.has_res, a.num_tiles, g.nchunk, plan.nw, plan.nxb, plan.total);
+  }
   const int grid = std::min(a.num_tiles, g_mb_sms > 0 ? g_mb_sms : 148);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

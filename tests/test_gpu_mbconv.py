@@ -19,6 +19,9 @@ CASES = {
     "s1_res_two_k_blocks_c96": (2, 96, 6, 96, 14, 14, 1, (1, 1), (1, 1), "BF16"),
     "s1_res_many_tiles_per_cta": (20, 32, 6, 32, 28, 28, 1, (1, 1), (1, 1), "BF16"),
     "s1_res_56_tiles_224": (8, 24, 6, 24, 56, 56, 1, (1, 1), (1, 1), "BF16"),
+    "s1_res_five_tiles_per_cta": (24, 24, 6, 24, 56, 56, 1, (1, 1), (1, 1), "BF16"),      # 672 tiles on 148 CTAs: X-tile ring wraps, deferred epilogues
+    "s1_noexpand_many_tiles": (16, 32, 1, 16, 56, 56, 1, (1, 1), (1, 1), "BF16"),         # 448 tiles
+    "s2_three_tiles_per_cta": (16, 16, 6, 24, 64, 64, 2, (1, 1), (1, 1), "BF16"),         # 512 tiles
     "s2_c16_to_24": (2, 16, 6, 24, 32, 32, 2, (1, 1), (1, 1), "BF16"),
     "s2_odd_size_many_tiles": (12, 24, 6, 32, 57, 57, 2, (1, 1), (1, 1), "BF16"),
     "s2_pads_begin0_end1": (2, 24, 6, 32, 30, 30, 2, (0, 0), (1, 1), "BF16"),
