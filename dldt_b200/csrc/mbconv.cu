@@ -66,7 +66,7 @@ __host__ __device__ inline MbGeom mb_geom(int stride, int Cin_p, int Ch_p) {
 }
 
 constexpr int MB_MAXW = 8;                // weight ring: at most this many 64-channel chunks of W1 / W2 in shared memory
-struct MbPlan { uint32_t nxb, nw, xa_kb, xa_bytes, xa_off, h_bytes, h_off, w1_bytes, w1_off, w2_bytes, w2_off, a2_off, out_off, out_bytes, wd_off, b1_off, bd_off, b2_off, bar_off, total; };
+struct MbPlan { uint32_t nxb, nw, nh, xa_kb, xa_bytes, xa_off, h_bytes, h_off, w1_bytes, w1_off, w2_bytes, w2_off, a2_off, out_off, out_bytes, wd_off, b1_off, bd_off, b2_off, bar_off, total; };
 __host__ __device__ inline MbPlan mb_plan_n(const MbGeom& g, int has_expand, int Ch_p, int Cout_p, int Cout_alloc, uint32_t nxb, uint32_t nw) {
   MbPlan p;
   uint32_t o = 0;
@@ -76,7 +76,11 @@ __host__ __device__ inline MbPlan mb_plan_n(const MbGeom& g, int has_expand, int
   p.xa_bytes = (uint32_t)g.kb1 * p.xa_kb;
   p.xa_off = o; o += has_expand ? nxb * p.xa_bytes : 0u;
   p.h_bytes = ((uint32_t)g.rows_in * 128u + 1023u) & ~1023u;
-  p.h_off = o; o += 2u * p.h_bytes;
+  // hidden-chunk ring: two buffers behind the expand stage (the compute warps fill and read them themselves); four when the TMA fills
+  // them (no expand convolution): with two, ONE load was in flight and every tile waited out a full TMA + DRAM latency (ncu / timing:
+  // 3350 cycles per tile whatever the depthwise stage cost)
+  p.nh = has_expand ? 2u : 4u;
+  p.h_off = o; o += p.nh * p.h_bytes;
   p.w1_bytes = (uint32_t)g.kb1 * 64u * 128u;
   p.w1_off = o; o += has_expand ? nw * p.w1_bytes : 0u;
   p.w2_bytes = (uint32_t)Cout_alloc * 128u;
@@ -85,12 +89,12 @@ __host__ __device__ inline MbPlan mb_plan_n(const MbGeom& g, int has_expand, int
   p.a2_off = o; o += 128u * 128u;
   p.out_bytes = (128u * (uint32_t)Cout_p * 2u + 127u) & ~127u;
   p.out_off = o; o += p.out_bytes;
-  p.wd_off = o; o += (uint32_t)(9 * Ch_p * 2);               // depthwise weights [9][Ch_p], 16-bit
+  p.wd_off = o; o += (uint32_t)(9 * Ch_p * 2);               // depthwise weights [9][Ch_p], 16-bit (fp32 copies: no faster, and the 576-wide blocks no longer fit)
   p.b1_off = o; o += (uint32_t)Ch_p * 4u;
   p.bd_off = o; o += (uint32_t)Ch_p * 4u;
   p.b2_off = o; o += (uint32_t)Cout_alloc * 4u;
   o = (o + 15u) & ~15u;
-  p.bar_off = o; o += 512u;
+  p.bar_off = o; o += 512u;                                  // 40 mbarriers + the TMEM slot
   p.total = o + 1024u;                                       // alignment slack of the dynamic shared-memory base
   return p;
 }
@@ -153,15 +157,15 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
   uint64_t* xempty = bars + 2;     // [2] X tile no longer read (expand MMAs complete, residual read)
   uint64_t* efull = bars + 4;      // expand accumulators of the chunk complete
   uint64_t* eempty = bars + 5;     // ... drained by the four E warps
-  uint64_t* hfull = bars + 6;      // [2] hidden chunk in shared memory (E warps, or the TMA without an expand convolution)
-  uint64_t* hempty = bars + 8;     // [2] hidden chunk consumed by the depthwise stage
+  uint64_t* hfull = bars + 32;     // [4] hidden chunk in shared memory (TMA, without an expand convolution)
+  uint64_t* hempty = bars + 36;    // [4] hidden chunk consumed by the depthwise stage
   uint64_t* a2full = bars + 10;    // depthwise output chunk staged as the project A operand
   uint64_t* a2empty = bars + 11;   // ... consumed by the project MMAs
   uint64_t* pfull = bars + 12;     // project accumulator of the tile complete
   uint64_t* pempty = bars + 13;    // ... drained
   uint64_t* wfull = bars + 16;     // [MB_MAXW] weight chunk landed
   uint64_t* wempty = bars + 24;    // [MB_MAXW] weight chunk consumed (project MMAs of the chunk complete)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
   const uint32_t nw = plan.nw;
   const bool w_resident = nw >= (uint32_t)nchunk;               // every chunk has its own stage: loaded during the first tile only
 
@@ -171,9 +175,9 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&xfull[i], 1); ptx::mbar_init(&xempty[i], 1);
-      ptx::mbar_init(&hfull[i], 1); ptx::mbar_init(&hempty[i], MB_D_WARPS);
     }
     for (int i = 0; i < MB_MAXW; ++i) { ptx::mbar_init(&wfull[i], 1); ptx::mbar_init(&wempty[i], 1); }
+    for (int i = 0; i < 4; ++i) { ptx::mbar_init(&hfull[i], 1); ptx::mbar_init(&hempty[i], MB_D_WARPS); }
     ptx::mbar_init(efull, 1); ptx::mbar_init(eempty, MB_D_WARPS);
     ptx::mbar_init(a2full, MB_D_WARPS); ptx::mbar_init(a2empty, 1);
     ptx::mbar_init(pfull, 1); ptx::mbar_init(pempty, MB_E_WARPS);
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
         }
       }
       for (int c = 0; c < nchunk; ++c, ++gc) {
-        const uint32_t hb = gc & 1u;
+        const uint32_t hb = EXPAND ? (gc & 1u) : (gc & 3u);
         const uint32_t hbuf = smem_base + plan.h_off + hb * plan.h_bytes;
         if (EXPAND) {
           // ---- expand accumulators -> + b1, clamp, zero outside the image (the depthwise's zero padding is padding of the EXPANDED
@@ -317,7 +321,8 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
               __syncwarp();
               if (lane == 0) ptx::mbar_arrive(eempty);
             }
-            const bool in = (inside >> m) & 1u;
+            // outside the image both bounds are 0: the clamp writes the depthwise's zero padding
+            const float lo = ((inside >> m) & 1u) ? p.lo1 : 0.f, hi = ((inside >> m) & 1u) ? p.hi1 : 0.f;
             if (r < ROWS_IN) {
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) {
@@ -328,7 +333,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
                 f[4] = __uint_as_float(v[jj * 8 + 4]) + __uint_as_float(bb.x); f[5] = __uint_as_float(v[jj * 8 + 5]) + __uint_as_float(bb.y);
                 f[6] = __uint_as_float(v[jj * 8 + 6]) + __uint_as_float(bb.z); f[7] = __uint_as_float(v[jj * 8 + 7]) + __uint_as_float(bb.w);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = in ? fminf(fmaxf(f[e], p.lo1), p.hi1) : 0.f;
+                for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(f[e], lo), hi);
                 ptx::st_shared_v4(hbuf + (uint32_t)r * 128u + ((((uint32_t)(half * 4 + jj)) ^ ((uint32_t)r & 7u)) << 4),
                                   make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7])));
               }
@@ -336,7 +341,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
           }
           ptx::named_bar_sync(1, MB_D_THREADS);                   // the whole chunk is in shared memory (two buffers: the chunk before last is read out)
         } else {
-          ptx::mbar_wait(&hfull[hb], (gc >> 1) & 1u);
+          ptx::mbar_wait(&hfull[hb], (gc >> 2) & 1u);
         }
         // ---- depthwise 3x3: PXT adjacent outputs x 8 channels per thread, fp32 accumulation from the bias ----
         float acc[PXT][8];
@@ -423,8 +428,8 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
             if (++ws == nw) { ws = 0; wph ^= 1u; }
           }
           if (!EXPAND) {
-            const uint32_t hb = gc & 1u;
-            ptx::mbar_wait(&hempty[hb], ((gc >> 1) & 1u) ^ 1u);
+            const uint32_t hb = gc & 3u;
+            ptx::mbar_wait(&hempty[hb], ((gc >> 2) & 1u) ^ 1u);
             ptx::mbar_arrive_expect_tx(&hfull[hb], (uint32_t)(ROWS_IN * 128));
             ptx::tma_load_4d(smem_base + plan.h_off + hb * plan.h_bytes, &args.tm_x, &hfull[hb], c * 64, iw0, ih0, n);
           }
