@@ -25,6 +25,8 @@ __device__ __forceinline__ float act_apply(float v, int kind, float a, float b) 
     case ACT_NEG: return -v;
     case ACT_ERF: return erff(v);
     case ACT_ELU: return v >= 0.f ? v : a * (expf(v) - 1.f);
+    case ACT_ROUND_EVEN: return rintf(v);
+    case ACT_ROUND_AWAY: return roundf(v);
   }
   return v;
 }

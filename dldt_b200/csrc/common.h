@@ -147,7 +147,8 @@ struct LTensor {
 // activation codes used by fused epilogues and the eltwise kernels
 enum Act : int {
   ACT_NONE = 0, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_CLAMP, ACT_SWISH, ACT_GELU_ERF, ACT_GELU_TANH,
-  ACT_HSWISH, ACT_HSIGMOID, ACT_MISH, ACT_EXP, ACT_SQRT, ACT_ABS, ACT_NEG, ACT_ERF, ACT_ELU
+  ACT_HSWISH, ACT_HSIGMOID, ACT_MISH, ACT_EXP, ACT_SQRT, ACT_ABS, ACT_NEG, ACT_ERF, ACT_ELU,
+  ACT_ROUND_EVEN, ACT_ROUND_AWAY   // ngraph reference/round.hpp: HALF_TO_EVEN (nearbyint) / HALF_AWAY_FROM_ZERO (round)
 };
 struct ActSpec {
   int kind = ACT_NONE;

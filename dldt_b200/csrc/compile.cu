@@ -215,6 +215,7 @@ class Lowerer {
   void lower_binary(const Node& n, const ActSpec& act, int out_value);
   void lower_unary(const Node& n, const ActSpec& act);
   void lower_pool(const Node& n);
+  void lower_fake_quantize(const Node& n);
   void lower_reduce(const Node& n);
   void lower_mvn(const Node& n, const FusedMvn* f);
   void lower_concat(const Node& n);
@@ -1560,6 +1561,46 @@ void Lowerer::lower_unary(const Node& n, const ActSpec& act) {
   set(n.outputs[0], out);
 }
 
+// FakeQuantize as one element-wise kernel over whatever layout the input has (the reference CPU plugin's FakeQuantize node in its fp32 form,
+// nodes/mkldnn_fake_quantize_node.cpp; the INT8 execution of LPT-transformed graphs is not built).  The four range constants become one
+// [4][channels] fp32 table in the weight blob; NHWC8 tensors index it by the padded innermost channel, row-major ones by axis 1.
+void Lowerer::lower_fake_quantize(const Node& n) {
+  LTensor x = get(n.inputs[0], -1);
+  B200_CHECK(dtype_is_float(x.dtype), B200_ERR_UNSUPPORTED, "FakeQuantize on a non-float tensor");
+  const int64_t C = x.shape.size() >= 2 ? x.shape[1] : 1;
+  std::vector<float> r[4];
+  bool per_channel = false;
+  for (int k = 0; k < 4; ++k) {
+    B200_CHECK(const_node(n.inputs[1 + k]), B200_ERR_UNSUPPORTED, "FakeQuantize '" << n.name << "': ranges must be constants");
+    r[k] = const_floats(n.inputs[1 + k]);
+    per_channel = per_channel || r[k].size() > 1;
+  }
+  int cdim = 1;
+  int64_t inner = 1;
+  if (per_channel) {
+    if (x.layout == L_NHWC8) { cdim = (int)round_up(C, 8); inner = 1; }
+    else { cdim = (int)C; inner = 1; for (size_t d = 2; d < x.shape.size(); ++d) inner *= x.shape[d]; }
+  }
+  std::vector<float> table((size_t)4 * cdim, 0.f);
+  for (int k = 0; k < 4; ++k)
+    for (int c = 0; c < cdim; ++c) table[(size_t)k * cdim + c] = c < C ? (r[k].size() > 1 ? r[k][c] : r[k][0]) : r[k][0];
+  // padded channels of an NHWC8 tensor must stay what they were for the next kernel: FakeQuantize(0) with these ranges (any value is fine:
+  // every consumer ignores the padding or multiplies it by zero weights)
+  BufRef tref = add_f32_vector(table);
+  LTensor out = alloc(x.shape, x.dtype, x.layout);
+  BufRef xr = x.buf, yr = out.buf;
+  const int64_t cnt = out.phys_elems();
+  const int dt = x.dtype, levels = n.i[0];
+  Step s;
+  s.name = n.name; s.type = "FakeQuantize"; s.impl = per_channel ? "fake_quantize_per_channel" : "fake_quantize_per_tensor"; s.fused = n.name;
+  s.bytes = 2.0 * (double)out.bytes();
+  s.launch = [=](const RunCtx& c) {
+    launch_fake_quantize(c.ptr(xr), c.ptr(yr), cnt, dt, reinterpret_cast<const float*>(c.ptr(tref)), cdim, inner, levels, (cudaStream_t)c.stream);
+  };
+  emit(std::move(s), {&x}, {&out});
+  set(n.outputs[0], out);
+}
+
 void Lowerer::lower_pool(const Node& n) {
   LTensor x = get(n.inputs[0], L_NHWC8);
   const Shape os = val(n.outputs[0]).shape;
@@ -1920,6 +1961,7 @@ void Lowerer::lower_node(const Node& n) {
       break;
     }
     case B200_OP_MAX_POOL: case B200_OP_AVG_POOL: lower_pool(n); break;
+    case B200_OP_FAKE_QUANTIZE: lower_fake_quantize(n); break;
     case B200_OP_REDUCE_MEAN: case B200_OP_REDUCE_SUM: case B200_OP_REDUCE_MAX: lower_reduce(n); break;
     case B200_OP_SOFTMAX: {
       auto fs = fsm_.find(n.id);

@@ -19,7 +19,7 @@ const char* op_name(int op) {
       "Gelu", "HSwish", "HSigmoid", "Mish", "Exp", "Sqrt", "Abs", "Negative", "Erf", "Elu", "MaxPool",
       "AvgPool", "ReduceMean", "MatMul", "Softmax", "MVN", "Reshape", "Transpose", "Concat", "Split",
       "Gather", "TopK", "NonMaxSuppression", "DetectionOutput", "Convert", "Power", "PRelu", "ReduceSum",
-      "ReduceMax", "SquaredDifference"};
+      "ReduceMax", "SquaredDifference", "Round", "FakeQuantize"};
   if (op < 0 || op >= B200_OP__COUNT) return "?";
   return names[op];
 }
@@ -28,7 +28,7 @@ bool is_unary_act(int op) {
   switch (op) {
     case B200_OP_RELU: case B200_OP_SIGMOID: case B200_OP_TANH: case B200_OP_CLAMP: case B200_OP_SWISH:
     case B200_OP_GELU: case B200_OP_HSWISH: case B200_OP_HSIGMOID: case B200_OP_MISH: case B200_OP_EXP:
-    case B200_OP_SQRT: case B200_OP_ABS: case B200_OP_NEGATIVE: case B200_OP_ERF: case B200_OP_ELU:
+    case B200_OP_SQRT: case B200_OP_ABS: case B200_OP_NEGATIVE: case B200_OP_ERF: case B200_OP_ELU: case B200_OP_ROUND:
       return true;
   }
   return false;
@@ -61,6 +61,7 @@ int act_from_op(const Node& n, ActSpec& s) {
     case B200_OP_NEGATIVE: s.kind = ACT_NEG; return 1;
     case B200_OP_ERF: s.kind = ACT_ERF; return 1;
     case B200_OP_ELU: s.kind = ACT_ELU; s.a = n.f[0]; return 1;
+    case B200_OP_ROUND: s.kind = n.i[0] ? ACT_ROUND_AWAY : ACT_ROUND_EVEN; return 1;
   }
   return 0;
 }
@@ -153,11 +154,31 @@ void infer_node(const b200_graph& g, const Node& n, std::vector<Shape>& os, std:
       break;
     case B200_OP_RELU: case B200_OP_SIGMOID: case B200_OP_TANH: case B200_OP_CLAMP: case B200_OP_SWISH:
     case B200_OP_GELU: case B200_OP_HSWISH: case B200_OP_HSIGMOID: case B200_OP_MISH: case B200_OP_EXP:
-    case B200_OP_SQRT: case B200_OP_ABS: case B200_OP_NEGATIVE: case B200_OP_ERF: case B200_OP_ELU:
+    case B200_OP_SQRT: case B200_OP_ABS: case B200_OP_NEGATIVE: case B200_OP_ERF: case B200_OP_ELU: case B200_OP_ROUND:
       B200_CHECK(n.inputs.size() >= 1, B200_ERR_INVALID, "unary op without input");
       os.push_back(in(0).shape);
       od.push_back(in(0).dtype);
       break;
+    case B200_OP_FAKE_QUANTIZE: {
+      // ngraph/core/src/op/fake_quantize.cpp: output = shape / type of the data input; the four range inputs broadcast to it.  Supported
+      // here: every range is one value or one value per channel (axis 1) - what Model Optimizer / POT emit
+      need_inputs(5);
+      B200_CHECK(n.i[0] >= 2, B200_ERR_INVALID, "FakeQuantize '" << n.name << "': levels must be >= 2");
+      const int64_t C = in(0).shape.size() >= 2 ? in(0).shape[1] : 1;
+      for (int k = 1; k < 5; ++k) {
+        const int64_t cnt = numel(in(k).shape);
+        B200_CHECK(cnt == 1 || cnt == C, B200_ERR_UNSUPPORTED, "FakeQuantize '" << n.name << "': range input " << k << " must hold 1 or C = " << C << " values");
+        if (cnt == C && cnt != 1) {
+          const Shape& rs = in(k).shape;
+          const size_t off = in(0).shape.size() - rs.size();
+          for (size_t d = 0; d < rs.size(); ++d)
+            B200_CHECK(rs[d] == 1 || d + off == 1, B200_ERR_UNSUPPORTED, "FakeQuantize '" << n.name << "': per-channel ranges must lie on axis 1");
+        }
+      }
+      os.push_back(in(0).shape);
+      od.push_back(in(0).dtype);
+      break;
+    }
     case B200_OP_MAX_POOL: case B200_OP_AVG_POOL: {
       need_inputs(1);
       const Shape& x = in(0).shape;

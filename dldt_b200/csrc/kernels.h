@@ -140,6 +140,9 @@ void launch_global_avgpool(const void* x, void* y, int N, int HW, int Cp, int dt
 // ---- elementwise -------------------------------------------------------------------------------
 // unary activation over n physical elements
 void launch_unary(const void* x, void* y, int64_t n, int dtype, int act, float a, float b, cudaStream_t s);
+// FakeQuantize (ngraph reference fake_quantize.hpp:176-194) over n physical elements; ranges[4][cdim] = in_low, in_high, out_low, out_high per
+// channel, channel of element i = (i / inner) % cdim (NHWC8: inner 1, cdim Cp; NCHW row-major: inner H*W, cdim C; per-tensor: cdim 1)
+void launch_fake_quantize(const void* x, void* y, int64_t n, int dtype, const float* ranges, int cdim, int64_t inner, int levels, cudaStream_t s);
 // binary with numpy broadcasting over logical row-major tensors (rank <= 8)
 struct BinaryParams {
   const void* a; const void* b; void* y;

@@ -423,6 +423,23 @@ __global__ void unary_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t
   }
 }
 
+// FakeQuantize, element by element as the reference's quantize() (fake_quantize.hpp:176-194): below / at the low bound -> out_low, above the
+// high bound -> out_high, else nearbyint((x - il) / (ih - il) * (levels - 1)) / (levels - 1) * (oh - ol) + ol, in fp32.
+template <typename T>
+__global__ void fake_quantize_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, const float* __restrict__ ranges, int cdim, int64_t inner,
+                                     float lm1) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = cdim == 1 ? 0 : (int)((i / inner) % cdim);
+  const float il = ranges[c], ih = ranges[cdim + c], ol = ranges[2 * cdim + c], oh = ranges[3 * cdim + c];
+  const float v = ldf<T>(x, i);
+  float r;
+  if (v <= fminf(il, ih)) r = ol;
+  else if (v > fmaxf(il, ih)) r = oh;
+  else r = rintf((v - il) / (ih - il) * lm1) / lm1 * (oh - ol) + ol;
+  stf<T>(y, i, r);
+}
+
 template <typename T>
 __global__ void binary_same_kernel(const T* __restrict__ pa, const T* __restrict__ pb, T* __restrict__ y, int64_t n, int op, int act,
                                    float aa, float ab) {
@@ -1113,6 +1130,10 @@ void launch_global_avgpool(const void* x, void* y, int N, int HW, int Cp, int dt
 void launch_unary(const void* x, void* y, int64_t n, int dtype, int act, float a, float b, cudaStream_t s) {
   if (n == 0) return;
   B200_DISPATCH_FLOAT(dtype, T, (unary_kernel<T><<<grid_for((n + 7) / 8, 256), 256, 0, s>>>((const T*)x, (T*)y, n, act, a, b)));
+}
+void launch_fake_quantize(const void* x, void* y, int64_t n, int dtype, const float* ranges, int cdim, int64_t inner, int levels, cudaStream_t s) {
+  if (n == 0) return;
+  B200_DISPATCH_FLOAT(dtype, T, (fake_quantize_kernel<T><<<grid_for(n, 256), 256, 0, s>>>((const T*)x, (T*)y, n, ranges, cdim, inner, (float)(levels - 1))));
 }
 void launch_binary_same(const void* a, const void* b, void* y, int64_t n, int dtype, int op, int act, float aa, float ab, cudaStream_t s) {
   if (n == 0) return;

@@ -67,7 +67,7 @@ __host__ __device__ inline MbGeom mb_geom(int stride, int Cin_p, int Ch_p) {
 
 constexpr int MB_MAXW = 8;                // weight ring: at most this many 64-channel chunks of W1 / W2 in shared memory
 struct MbPlan { uint32_t nxb, nw, nh, xa_kb, xa_bytes, xa_off, h_bytes, h_off, w1_bytes, w1_off, w2_bytes, w2_off, a2_off, out_off, out_bytes, wd_off, b1_off, bd_off, b2_off, bar_off, total; };
-__host__ __device__ inline MbPlan mb_plan_n(const MbGeom& g, int has_expand, int Ch_p, int Cout_p, int Cout_alloc, uint32_t nxb, uint32_t nw) {
+__host__ __device__ inline MbPlan mb_plan_n(const MbGeom& g, int has_expand, int Ch_p, int Cout_p, int Cout_alloc, uint32_t nxb, uint32_t nw, uint32_t nh = 0) {
   MbPlan p;
   uint32_t o = 0;
   p.nxb = nxb;
@@ -79,7 +79,7 @@ __host__ __device__ inline MbPlan mb_plan_n(const MbGeom& g, int has_expand, int
   // hidden-chunk ring: two buffers behind the expand stage (the compute warps fill and read them themselves); four when the TMA fills
   // them (no expand convolution): with two, ONE load was in flight and every tile waited out a full TMA + DRAM latency (ncu / timing:
   // 3350 cycles per tile whatever the depthwise stage cost)
-  p.nh = has_expand ? 2u : 4u;
+  p.nh = nh ? nh : (has_expand ? 2u : 4u);
   p.h_off = o; o += p.nh * p.h_bytes;
   p.w1_bytes = (uint32_t)g.kb1 * 64u * 128u;
   p.w1_off = o; o += has_expand ? nw * p.w1_bytes : 0u;
@@ -110,6 +110,10 @@ __host__ __device__ inline MbPlan mb_plan(const MbGeom& g, int has_expand, int C
       if (nxb == 2u && !has_expand) continue;
       const MbPlan p = mb_plan_n(g, has_expand, Ch_p, Cout_p, Cout_alloc, nxb, nw);
       if (p.total <= (uint32_t)MB_SMEM_LIMIT) return p;
+      if (!has_expand) {                                       // wide TMA-fed chunks (576 channels at stride 2): two hidden buffers instead of four
+        const MbPlan p2 = mb_plan_n(g, has_expand, Ch_p, Cout_p, Cout_alloc, nxb, nw, 2u);
+        if (p2.total <= (uint32_t)MB_SMEM_LIMIT) return p2;
+      }
     }
     (void)resident_possible;
   }
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
         }
       }
       for (int c = 0; c < nchunk; ++c, ++gc) {
-        const uint32_t hb = EXPAND ? (gc & 1u) : (gc & 3u);
+        const uint32_t hb = gc & (plan.nh - 1u);
         const uint32_t hbuf = smem_base + plan.h_off + hb * plan.h_bytes;
         if (EXPAND) {
           // ---- expand accumulators -> + b1, clamp, zero outside the image (the depthwise's zero padding is padding of the EXPANDED
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
           }
           ptx::named_bar_sync(1, MB_D_THREADS);                   // the whole chunk is in shared memory (two buffers: the chunk before last is read out)
         } else {
-          ptx::mbar_wait(&hfull[hb], (gc >> 2) & 1u);
+          ptx::mbar_wait(&hfull[hb], (gc >> (plan.nh == 4u ? 2 : 1)) & 1u);
         }
         // ---- depthwise 3x3: PXT adjacent outputs x 8 channels per thread, fp32 accumulation from the bias ----
         float acc[PXT][8];
@@ -428,8 +432,8 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mbconv_kernel(const __grid_cons
             if (++ws == nw) { ws = 0; wph ^= 1u; }
           }
           if (!EXPAND) {
-            const uint32_t hb = gc & 3u;
-            ptx::mbar_wait(&hempty[hb], ((gc >> 2) & 1u) ^ 1u);
+            const uint32_t hb = gc & (plan.nh - 1u);
+            ptx::mbar_wait(&hempty[hb], ((gc >> (plan.nh == 4u ? 2 : 1)) & 1u) ^ 1u);
             ptx::mbar_arrive_expect_tx(&hfull[hb], (uint32_t)(ROWS_IN * 128));
             ptx::tma_load_4d(smem_base + plan.h_off + hb * plan.h_bytes, &args.tm_x, &hfull[hb], c * 64, iw0, ih0, n);
           }

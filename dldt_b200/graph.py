@@ -173,6 +173,14 @@ class Function:
         return self._add("Gelu", [x], name, i=[0 if approximation.upper() == "ERF" else 1],
                          attrs={"approximation_mode": approximation.upper()}, version="opset7").outputs[0]
 
+    def round(self, x, mode="half_to_even", name=None):
+        return self._add("Round", [x], name, i=[0 if mode == "half_to_even" else 1], attrs={"mode": mode}, version="opset5").outputs[0]
+
+    def fake_quantize(self, x, in_low, in_high, out_low, out_high, levels, name=None):
+        """opset1 FakeQuantize; the four ranges are constants holding one value or one value per channel (shape [1, C, 1, 1] or [C, 1, 1])."""
+        r = [v if isinstance(v, Output) else self.constant(np.asarray(v, np.float32)) for v in (in_low, in_high, out_low, out_high)]
+        return self._add("FakeQuantize", [x] + r, name, i=[int(levels)], attrs={"levels": int(levels), "auto_broadcast": "numpy"}).outputs[0]
+
     def elu(self, x, alpha=1.0, name=None):
         return self._add("Elu", [x], name, f=[alpha], attrs={"alpha": alpha}).outputs[0]
 

@@ -114,6 +114,8 @@ typedef enum b200_op {
   B200_OP_PRELU = 43,        /* in: x, slope (per-channel or scalar)                               */
   B200_OP_REDUCE_SUM = 44, B200_OP_REDUCE_MAX = 45, /* same attrs as REDUCE_MEAN                   */
   B200_OP_SQUARED_DIFFERENCE = 46,
+  B200_OP_ROUND = 47,        /* i={mode: 0 half to even | 1 half away from zero}  (opset5 Round; what FakeQuantize decomposes to) */
+  B200_OP_FAKE_QUANTIZE = 48, /* in: x, in_low, in_high, out_low, out_high (constants: one value, or one per channel = axis 1); i={levels} */
   B200_OP__COUNT
 } b200_op;
 

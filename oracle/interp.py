@@ -46,6 +46,10 @@ def run(func, inputs, return_all=False):
             out = [ops.activation(x[0], "GeluErf" if a["approximation_mode"] == "ERF" else "GeluTanh")]
         elif n.op == "Elu":
             out = [ops.activation(x[0], "Elu", a["alpha"])]
+        elif n.op == "Round":
+            out = [ops.activation(x[0], "RoundEven" if a["mode"] == "half_to_even" else "RoundAway")]
+        elif n.op == "FakeQuantize":
+            out = [ops.fake_quantize(x[0], x[1], x[2], x[3], x[4], a["levels"])]
         elif n.op == "MaxPool":
             out = [ops.max_pool(x[0], a["kernel"], a["strides"], a["pads_begin"], a["pads_end"], a["rounding_type"])]
         elif n.op == "AvgPool":

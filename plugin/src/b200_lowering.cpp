@@ -231,6 +231,16 @@ OpDesc Describe(const NodePtr& n) {
     if (auto c = as_type_ptr<ngraph::opset1::Clamp>(n)) {
         d.op = B200_OP_CLAMP; all_inputs(1); d.f = {static_cast<float>(c->get_min()), static_cast<float>(c->get_max())}; return d;
     }
+    if (auto r = as_type_ptr<ngraph::opset5::Round>(n)) {
+        d.op = B200_OP_ROUND; all_inputs(1); d.i = {r->get_mode() == ngraph::opset5::Round::RoundMode::HALF_TO_EVEN ? 0 : 1}; return d;
+    }
+    if (auto fq = as_type_ptr<ngraph::opset1::FakeQuantize>(n)) {
+        // executed in its fp32 / 16-bit form (one element-wise kernel); LPT's INT8 rewrite of the graph is not applied by this plugin
+        d.op = B200_OP_FAKE_QUANTIZE; all_inputs(5); d.i = {static_cast<int>(fq->get_levels())};
+        for (size_t k = 1; k < 5; ++k)
+            if (!as_type_ptr<ngraph::opset1::Constant>(n->get_input_node_shared_ptr(k))) { d.reject = "FakeQuantize ranges must be Constants"; return d; }
+        return d;
+    }
     if (auto e = as_type_ptr<ngraph::opset1::Elu>(n)) { d.op = B200_OP_ELU; all_inputs(1); d.f = {static_cast<float>(e->get_alpha())}; return d; }
     if (as_type_ptr<ngraph::opset4::Swish>(n)) {
         d.op = B200_OP_SWISH; all_inputs(1); d.f = {1.0f};

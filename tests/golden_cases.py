@@ -217,6 +217,44 @@ def unary_activations():
 
 
 @case
+def round_modes():
+    # opset5 Round, both modes, with exact .5 ties in the data (what FakeQuantize decomposes to: fq_decomposition.cpp)
+    r = _rng("round_modes")
+    f = Function("round")
+    x = f.parameter((3, 40), name="x")
+    f.result(f.round(x, "half_to_even", name="even"))
+    f.result(f.round(x, "half_away_from_zero", name="away"))
+    v = _f32(r.standard_normal((3, 40)) * 4)
+    v[0, :20] = np.arange(-10, 10, dtype=np.float32) + 0.5
+    return f, {"x": v}
+
+
+@case
+def fake_quantize_per_tensor():
+    # opset1 FakeQuantize, 256 levels, one range for the tensor; values below / above the input range saturate to out_low / out_high
+    r = _rng("fake_quantize_per_tensor")
+    f = Function("fq_tensor")
+    x = f.parameter((2, 16, 9, 9), name="x")
+    f.result(f.fake_quantize(x, _f32([-1.5]), _f32([2.0]), _f32([-1.0]), _f32([3.0]), 256, name="fq"))
+    return f, {"x": _f32(r.standard_normal((2, 16, 9, 9)) * 1.5)}
+
+
+@case
+def fake_quantize_per_channel_conv():
+    # the quantised-model pattern: Convolution -> FakeQuantize with per-channel ranges [1, C, 1, 1] -> Convolution (activations in NHWC8 here)
+    r = _rng("fake_quantize_per_channel_conv")
+    f = Function("fq_channel")
+    x = f.parameter((2, 24, 10, 10), name="x")
+    y = f.relu(f.add(f.convolution(x, _f32(r.standard_normal((40, 24, 3, 3)) / np.sqrt(216.0)), (1, 1), (1, 1), (1, 1), (1, 1), name="conv1"),
+                     _f32(r.standard_normal((1, 40, 1, 1)) * 0.2), name="bias1"), name="relu1")
+    hi = _f32(r.uniform(1.0, 3.0, (1, 40, 1, 1)))
+    y = f.fake_quantize(y, _f32(np.zeros((1, 40, 1, 1))), hi, _f32(np.zeros((1, 40, 1, 1))), hi, 256, name="fq")
+    y = f.convolution(y, _f32(r.standard_normal((16, 40, 1, 1)) / np.sqrt(40.0)), (1, 1), (0, 0), (0, 0), (1, 1), name="conv2")
+    f.result(y)
+    return f, {"x": _f32(r.standard_normal((2, 24, 10, 10)))}
+
+
+@case
 def binary_broadcast():
     r = _rng("binary_broadcast")
     f = Function("binary")

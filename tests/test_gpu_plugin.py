@@ -21,7 +21,8 @@ needs_ref = pytest.mark.skipif(not (refrun.available() and os.path.exists(PLUGIN
 
 CASES = ["conv_3x3", "conv_7x7_s2_c3", "conv_bn_residual", "depthwise_s2_clamp_pools", "fc_bias_gelu", "matmul_batched_activations", "softmax_ssd",
          "mvn_layernorm", "unary_activations", "binary_broadcast", "concat_split_transpose", "gather_embedding", "topk_ties_max_value",
-         "nms_corner_sorted", "nms_score_ties", "detout_ssd_like", "net_tiny_resnet", "net_tiny_mobilenet", "net_tiny_bert", "net_tiny_ssd"]
+         "nms_corner_sorted", "nms_score_ties", "detout_ssd_like", "net_tiny_resnet", "net_tiny_mobilenet", "net_tiny_bert", "net_tiny_ssd",
+         "round_modes", "fake_quantize_per_tensor", "fake_quantize_per_channel_conv"]
 
 
 @needs_ref

@@ -80,7 +80,7 @@ def test_no_device_fails_loudly(tiny_resnet_xml):
 
 
 @pytest.mark.parametrize("case", ["net_tiny_mobilenet", "net_tiny_bert", "net_tiny_ssd", "unary_activations", "topk_ties_min_index", "nms_corner_sorted",
-                                  "concat_split_transpose", "mvn_layernorm", "matmul_batched_activations"])
+                                  "concat_split_transpose", "mvn_layernorm", "matmul_batched_activations", "fake_quantize_per_channel_conv", "round_modes"])
 def test_every_model_family_lowers_through_the_plugin(case, tmp_path):
     f, _ = golden_cases.CASES[case]()
     xml = str(tmp_path / "m.xml")

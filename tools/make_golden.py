@@ -22,7 +22,19 @@ from tools import refrun        # noqa: E402
 def main():
     assert refrun.available(), "build the reference first: bash oracle/build_ref.sh"
     out, rejected = {}, {"cpu": {}, "template": {}}
+    path = os.path.join(ROOT, "tests", "golden", "ref_cases.npz")
+    only = set(sys.argv[1:])            # `python tools/make_golden.py case ...`: (re)generate these cases only, keep the rest of the file
+    if only:
+        old = np.load(path)
+        for k in old.files:
+            if k != "__meta__" and k.split("/")[1] not in only:
+                out[k] = old[k]
+        meta = json.loads(bytes(old["__meta__"]).decode())
+        for dev in rejected:
+            rejected[dev] = {k: v for k, v in meta["rejected"].get(dev, {}).items() if k not in only}
     for name, fn in golden_cases.CASES.items():
+        if only and name not in only:
+            continue
         f, inputs = fn()
         for dev, key in (("CPU", "cpu"), ("TEMPLATE", "template")):
             try:
@@ -36,7 +48,6 @@ def main():
             print("%-28s %-8s %s" % (name, dev, {k: v.shape for k, v in res.items()}))
     out["__meta__"] = np.frombuffer(json.dumps({"rejected": rejected, "reference": "opencv/dldt @ /root/reference, built by oracle/build_ref.sh",
                                                 "cpu_config": {"ENFORCE_BF16": "NO"}}).encode(), dtype=np.uint8)
-    path = os.path.join(ROOT, "tests", "golden", "ref_cases.npz")
     np.savez_compressed(path, **out)
     print("wrote %s (%.1f KB, %d arrays)" % (path, os.path.getsize(path) / 1e3, len(out)))
 
