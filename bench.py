@@ -13,7 +13,8 @@ max-over-ranks reduction of the timings.
 
 Numbers on the JSON line:
   value      images/s with the U8 input already resident in HBM: K CUDA-graph replays (ingest ->
-             53 conv + pool + FC kernels -> egress) timed with CUDA events on the request's stream.
+             49 tcgen05 conv kernels (max pool in the stem's epilogue, shortcuts as extra K) + avg pool +
+             FC -> egress) timed with CUDA events on the request's stream.
   e2e        images/s through the DROP-IN boundary: the UNMODIFIED reference benchmark_app (oracle/_ref/bin/benchmark_app,
              samples/benchmark_app/main.cpp:457-629) loads plugin/lib/libb200Plugin.so through InferenceEngine::Core and runs
              `-d B200 -b 256 -api async`: every request copies the U8 NCHW batch from pinned host memory to the device and
