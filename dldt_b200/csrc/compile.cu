@@ -1130,8 +1130,25 @@ void Lowerer::lower_conv(const FusedConv& f) {
     const bool tb = n.i[1] != 0;
     const int64_t K = tb ? ws[1] : ws[0], Nn = tb ? ws[0] : ws[1];
     B200_CHECK(x.shape.back() == K, B200_ERR_INVALID, "MatMul '" << n.name << "': K mismatch");
-    B200_CHECK(K % 8 == 0, B200_ERR_UNSUPPORTED, "MatMul '" << n.name << "': K=" << K << " must be a multiple of 8");
     const int64_t M = numel(x.shape) / K;
+    const int64_t Kp = round_up(K, 8);
+    if (Kp != K) {
+      // the kernels read the activation matrix in 16-byte granules (TMA row pitch): rows whose length is not a multiple of 8 elements
+      // (LeNet's 84 -> 10 layer) are copied into a zero-padded scratch first; the packed weights are zero in the padding columns too
+      Shape ps = {M, Kp};
+      LTensor xp = alloc(ps, x.dtype, L_ROWMAJOR);
+      Step s;
+      s.name = out_name + "_padk"; s.type = "Reorder"; s.impl = "copy2d"; s.fused = s.name;
+      BufRef src = x.buf, dst = xp.buf;
+      const int64_t es = dtype_size(x.dtype), pad_bytes = xp.bytes();
+      s.bytes = (double)x.bytes() + 2.0 * (double)pad_bytes;
+      s.launch = [=](const RunCtx& c) {
+        launch_fill_zero(c.ptr(dst), pad_bytes, (cudaStream_t)c.stream);
+        launch_copy2d(c.ptr(src), K * es, c.ptr(dst), Kp * es, K * es, M, (cudaStream_t)c.stream);
+      };
+      emit(std::move(s), {&x}, {&xp});
+      x = xp;
+    }
     const bool tc = use_tc_;
     const int64_t Np = round_up(Nn, 8);
     const int bn = tc ? conv_tc_pick_bn((int)Np) : 64;
@@ -1159,7 +1176,7 @@ void Lowerer::lower_conv(const FusedConv& f) {
       rref = res.buf;
     }
     ConvParams p;
-    p.N = (int)M; p.H = p.W = p.Ho = p.Wo = 1; p.Cin_p = (int)K; p.Cout_p = (int)Np;
+    p.N = (int)M; p.H = p.W = p.Ho = p.Wo = 1; p.Cin_p = (int)Kp; p.Cout_p = (int)Np;
     p.M = (int)M; p.Ktot = (int)Ktot; p.Cout_alloc = (int)Nalloc; p.ldy = (int)Np;
     p.w_ld = (int)Ktot; p.w_rows = (int)Nalloc; p.w_k = (int)Ktot;
     p.act1 = f.act1.kind; p.a1 = f.act1.a; p.b1 = f.act1.b; p.act2 = f.act2.kind; p.a2 = f.act2.a; p.b2 = f.act2.b;

@@ -509,13 +509,27 @@ int b200_request_set_io_format(b200_request* req, int is_output, int index, int3
   return guarded([&] {
     B200_CHECK(req, B200_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lk(req->mu);
-    B200_CHECK(!req->finalized, B200_ERR_BUSY, "I/O format must be set before the first inference");
     auto& v = is_output ? req->out_fmt : req->in_fmt;
     B200_CHECK(index >= 0 && index < (int)v.size(), B200_ERR_INVALID, "io index out of range");
     B200_CHECK(dtype == B200_F32 || dtype == B200_F16 || dtype == B200_BF16 || dtype == B200_I32 || dtype == B200_U8, B200_ERR_UNSUPPORTED,
                "unsupported blob precision " << dtype);
+    const int new_layout = layout == B200_LAYOUT_NHWC ? B200_LAYOUT_NHWC : B200_LAYOUT_NCHW;
+    if (v[index].dtype == dtype && v[index].layout == new_layout) return B200_OK;
+    if (req->finalized) {
+      // a blob with another layout / precision arrived after the first inference (SetBlob in the reference may change both at any time,
+      // ie_iinfer_request_internal.cpp:96-150): the edge-conversion kernels are part of the captured graph, so the capture is dropped and
+      // the next start() records it again with the new format.  Only an idle request may change.
+      B200_CHECK(!req->started.load(), B200_ERR_BUSY, "I/O format cannot change while the request is running");
+      B200_CUDA(cudaSetDevice(req->net->device));
+      B200_CUDA(cudaStreamSynchronize(req->stream));
+      if (req->graph_exec) { cudaGraphExecDestroy(req->graph_exec); req->graph_exec = nullptr; }
+      if (req->graph) { cudaGraphDestroy(req->graph); req->graph = nullptr; }
+      auto& dev = is_output ? req->out_dev : req->in_dev;
+      if (dtype_size(dtype) != dtype_size(v[index].dtype) && dev[index]) { cudaFree(dev[index]); dev[index] = nullptr; }
+      req->finalized = false;
+    }
     v[index].dtype = dtype;
-    v[index].layout = layout == B200_LAYOUT_NHWC ? B200_LAYOUT_NHWC : B200_LAYOUT_NCHW;
+    v[index].layout = new_layout;
     return B200_OK;
   });
 }

@@ -57,6 +57,15 @@ if [ ! -f build.ninja ]; then
 fi
 nice -n 5 ninja -j"$JOBS" MKLDNNPlugin inference_engine inference_engine_ir_reader \
     MultiDevicePlugin templatePlugin benchmark_app > "$WORK/build.log" 2>&1
+# The reference's own conformance binary (docs/template_plugin/tests/functional: the behaviour suites, the hetero / single-layer
+# instances and the op_reference tests a device plugin is expected to pass), UNMODIFIED.  tools/run_conformance.sh runs it against
+# libb200Plugin.so by registering that library under the name the binary asks for.  ~430 extra translation units (funcSharedTests,
+# sharedTestClasses, ngraphFunctions, gtest), ~15 min on 8 cores; CONFORMANCE=0 skips it.
+if [ "${CONFORMANCE:-1}" = 1 ]; then
+  OMP="$WORK/fakeomp" cmake . -DENABLE_TESTS=ON -DENABLE_FUNCTIONAL_TESTS=ON -DENABLE_BEH_TESTS=ON -DENABLE_DATA=OFF \
+      -DNGRAPH_UNIT_TEST_ENABLE=OFF -DENABLE_GAPI_TESTS=OFF > "$WORK/configure_tests.log" 2>&1
+  nice -n 5 ninja -j"$JOBS" templateFuncTests > "$WORK/build_tests.log" 2>&1
+fi
 
 BIN="$WORK/src/bin/intel64/Release"
 mkdir -p "$OUT/lib" "$OUT/bin"
@@ -64,10 +73,11 @@ for f in libinference_engine.so libinference_engine_transformations.so libinfere
          libinference_engine_lp_transformations.so libinference_engine_preproc.so \
          libinference_engine_ir_reader.so libinference_engine_ir_v7_reader.so libngraph.so \
          libMKLDNNPlugin.so libMultiDevicePlugin.so libtemplatePlugin.so libngraph_backend.so \
-         libinterpreter_backend.so libformat_reader.so libfrontend_manager.so; do
+         libinterpreter_backend.so libformat_reader.so libfrontend_manager.so libHeteroPlugin.so libmock_engine.so; do
   [ -f "$BIN/lib/$f" ] && cp -f "$BIN/lib/$f" "$OUT/lib/"
 done
 cp -f "$BIN/benchmark_app" "$OUT/bin/"
+[ -f "$BIN/templateFuncTests" ] && cp -f "$BIN/templateFuncTests" "$OUT/bin/"
 strip --strip-unneeded "$OUT"/lib/*.so "$OUT/bin/benchmark_app" || true
 # plugins.xml: the reference's own registry + one line for the drop-in (location is relative to
 # libinference_engine.so, ie_core.cpp:421-433)
@@ -76,6 +86,7 @@ cat > "$OUT/lib/plugins.xml" <<XML
     <plugins>
         <plugin name="CPU" location="libMKLDNNPlugin.so"></plugin>
         <plugin name="MULTI" location="libMultiDevicePlugin.so"></plugin>
+        <plugin name="HETERO" location="libHeteroPlugin.so"></plugin>
         <plugin name="TEMPLATE" location="libtemplatePlugin.so"></plugin>
         <plugin name="B200" location="../../../plugin/lib/libb200Plugin.so"></plugin>
     </plugins>

@@ -71,32 +71,56 @@ void AddMeanScale(const std::shared_ptr<ngraph::Function>& function, const Infer
         const size_t channels = info.getNumberOfChannels();
         if (channels == 0) continue;
         std::vector<float> mean(channels), scale(channels);
-        bool has_mean = false, has_scale = false;
+        bool has_mean = false, has_scale = false, has_image = false;
         for (size_t c = 0; c < channels; ++c) {
-            if (info[c]->meanData) IE_THROW(NotImplemented) << "B200 plugin: mean-image pre-processing of input '" << it->first << "' is not supported (use mean values)";
+            has_image = has_image || info[c]->meanData != nullptr;
             mean[c] = info[c]->meanValue;
             scale[c] = info[c]->stdScale;
             has_mean = has_mean || mean[c] != 0.f;
             has_scale = has_scale || scale[c] != 1.f;
         }
-        if (!has_mean && !has_scale) continue;
+        if (!has_mean && !has_scale && !has_image) continue;
         const auto& shape = param->get_shape();
         if (shape.size() < 2 || shape[1] != channels) IE_THROW(ParameterMismatch) << "B200 plugin: " << channels << " pre-processing channels for input '" << it->first << "'";
-        ngraph::Shape cshape(shape.size(), 1);
-        cshape[1] = channels;
         const auto consumers = param->output(0).get_target_inputs();
-        // (x - mean) / scale as ONE per-channel scale + shift: BatchNormInference with gamma 1, beta 0, variance scale^2, eps 0 - the
-        // compiler runs it as a single channels-last kernel (a Subtract + Divide pair would be two kernels and a layout conversion)
-        std::vector<float> ones(channels, 1.f), zeros(channels, 0.f), var(channels);
-        for (size_t c = 0; c < channels; ++c) var[c] = scale[c] * scale[c];
-        const ngraph::Shape vshape{channels};
-        auto bn = std::make_shared<ngraph::opset5::BatchNormInference>(param->output(0), ngraph::opset1::Constant::create(ngraph::element::f32, vshape, ones),
-                                                                      ngraph::opset1::Constant::create(ngraph::element::f32, vshape, zeros),
-                                                                      ngraph::opset1::Constant::create(ngraph::element::f32, vshape, mean),
-                                                                      ngraph::opset1::Constant::create(ngraph::element::f32, vshape, var), 0.0);
-        bn->set_friendly_name(param->get_friendly_name() + "/mean_scale");
-        ngraph::Output<ngraph::Node> cur = bn->output(0);
-        (void)cshape;
+        ngraph::Output<ngraph::Node> cur = param->output(0);
+        if (has_image) {
+            // MEAN_IMAGE (ie_preprocess.hpp:30-45): one FP32 blob of the input's spatial size per channel, subtracted element-wise on the
+            // device (the reference does the same through a Subtract: docs/template_plugin/src/transformations/preprocessing/preprocessing.cpp:67-82,
+            // mkldnn_plugin/normalize_preprocess.cpp)
+            if (has_mean) IE_THROW(ParameterMismatch) << "B200 plugin: input '" << it->first << "' sets both a mean image and mean values";
+            ngraph::Shape ishape(shape);
+            ishape[0] = 1;
+            const size_t plane = ngraph::shape_size(ishape) / channels;
+            std::vector<float> image(channels * plane);
+            for (size_t c = 0; c < channels; ++c) {
+                const auto& blob = info[c]->meanData;
+                if (!blob || blob->getTensorDesc().getPrecision() != InferenceEngine::Precision::FP32 || blob->size() != plane)
+                    IE_THROW(ParameterMismatch) << "B200 plugin: mean image of input '" << it->first << "', channel " << c << ": an FP32 blob of " << plane
+                                                << " elements is required for every channel";
+                auto mem = InferenceEngine::as<InferenceEngine::MemoryBlob>(blob);
+                if (!mem) IE_THROW(ParameterMismatch) << "B200 plugin: mean image of input '" << it->first << "' is not a memory blob";
+                auto locked = mem->rmap();
+                std::memcpy(&image[c * plane], locked.as<const float*>(), plane * sizeof(float));
+            }
+            auto sub = std::make_shared<ngraph::opset1::Subtract>(cur, ngraph::opset1::Constant::create(ngraph::element::f32, ishape, image));
+            sub->set_friendly_name(param->get_friendly_name() + "/mean_image");
+            cur = sub->output(0);
+            std::fill(mean.begin(), mean.end(), 0.f);
+        }
+        if (has_mean || has_scale) {
+            // (x - mean) / scale as ONE per-channel scale + shift: BatchNormInference with gamma 1, beta 0, variance scale^2, eps 0 - the
+            // compiler runs it as a single channels-last kernel (a Subtract + Divide pair would be two kernels and a layout conversion)
+            std::vector<float> ones(channels, 1.f), zeros(channels, 0.f), var(channels);
+            for (size_t c = 0; c < channels; ++c) var[c] = scale[c] * scale[c];
+            const ngraph::Shape vshape{channels};
+            auto bn = std::make_shared<ngraph::opset5::BatchNormInference>(cur, ngraph::opset1::Constant::create(ngraph::element::f32, vshape, ones),
+                                                                          ngraph::opset1::Constant::create(ngraph::element::f32, vshape, zeros),
+                                                                          ngraph::opset1::Constant::create(ngraph::element::f32, vshape, mean),
+                                                                          ngraph::opset1::Constant::create(ngraph::element::f32, vshape, var), 0.0);
+            bn->set_friendly_name(param->get_friendly_name() + "/mean_scale");
+            cur = bn->output(0);
+        }
         for (auto consumer : consumers) consumer.replace_source_output(cur);
     }
 }

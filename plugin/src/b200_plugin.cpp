@@ -1,6 +1,8 @@
 // B200 device plugin: Plugin / ExecutableNetwork / InferRequest / AsyncInferRequest.  See b200_plugin.hpp.
 #include "b200_plugin.hpp"
 
+#include <iostream>
+
 #include <blob_factory.hpp>
 #include <exec_graph_info.hpp>
 #include <ie_algorithm.hpp>
@@ -127,6 +129,11 @@ Parameter Configuration::Get(const std::string& name) const {
 // ---- plugin -------------------------------------------------------------------------------------------------------
 Plugin::Plugin() {
     _pluginName = "B200";
+    // Process-wide default of B200_INFERENCE_PRECISION (a LoadNetwork / SetConfig value still wins).  The reference's CPU plugin has the
+    // same need: its functional-test instances switch the implicit bf16 mode off for the whole run
+    // (inference-engine/tests/functional/plugin/cpu/shared_tests_instances/core_config.cpp), because the behaviour suites compare
+    // fp32 values for equality.  tools/run_conformance.sh sets it to FP32 for the same reason.
+    if (const char* env = std::getenv("B200_INFERENCE_PRECISION")) _cfg = Configuration{{{B200ConfigParams::KEY_B200_INFERENCE_PRECISION, env}}, _cfg};
     // wait stages block a thread on a CUDA event: they get their own executor so that start stages are never starved
     // (RANGE_FOR_ASYNC_INFER_REQUESTS advertises up to 16 requests in flight: one blocked thread each at worst)
     _waitExecutor = ExecutorManager::getInstance()->getIdleCPUStreamsExecutor({"B200WaitExecutor", 16});
@@ -139,7 +146,13 @@ Plugin::~Plugin() {
 
 void Plugin::SetConfig(const std::map<std::string, std::string>& config) { _cfg = Configuration{config, _cfg}; }
 
-Parameter Plugin::GetConfig(const std::string& name, const std::map<std::string, Parameter>&) const { return _cfg.Get(name); }
+// PERF_COUNT has two readers in the reference with two expectations: the behaviour suites read the PLUGIN's value as a bool
+// (core_integration.cpp of the template instances; docs/template_plugin/src/template_config.cpp:44-45 returns one), the MULTI plugin reads
+// the EXECUTABLE NETWORK's value as the string YES / NO (multi_device_plugin.cpp:219-223, as the CPU plugin returns it).  Each gets its own.
+Parameter Plugin::GetConfig(const std::string& name, const std::map<std::string, Parameter>&) const {
+    if (name == CONFIG_KEY(PERF_COUNT)) return {_cfg.perfCount};
+    return _cfg.Get(name);
+}
 
 void Plugin::AddExtension(const std::shared_ptr<IExtension>&) { IE_THROW(NotImplemented) << "B200 plugin does not support extensions"; }
 
@@ -236,11 +249,12 @@ std::shared_ptr<InferenceEngine::RemoteContext> ExecutableNetwork::GetContext() 
 
 // ---- Export / Import (docs/template_plugin/src/template_executable_network.cpp:179-200, template_plugin.cpp:108-112; the Core drives
 // them for CACHE_DIR: inference-engine/src/inference_engine/ie_core.cpp:265-340).  Stream layout:
-//   "B200NET1" | precision,streams (i32) | device id text, device list text | inputs: name, precision, layout | outputs: name, precision |
+//   "B200NET2" | precision,streams (i32) | device id text, device list text | inputs: name, precision, layout, per-channel mean / scale,
+//   mean image (elements per channel, 0 = none; then the planes) | outputs: name, precision |
 //   IR v10 xml | IR weights | kernel-selection table (b200_network_get_tuning).
 // The IR is the network as loaded; what the export saves on import is the measured part of LoadNetwork: the per-layer kernel selection.
 namespace {
-const char kMagic[8] = {'B', '2', '0', '0', 'N', 'E', 'T', '1'};
+const char kMagic[8] = {'B', '2', '0', '0', 'N', 'E', 'T', '2'};
 
 void putString(std::ostream& os, const std::string& v) {
     const uint64_t n = v.size();
@@ -284,6 +298,14 @@ void ExecutableNetwork::Export(std::ostream& model) {
             const float mv[2] = {pre[c]->meanValue, pre[c]->stdScale};
             model.write(reinterpret_cast<const char*>(mv), sizeof(mv));
         }
+        // MEAN_IMAGE: the per-channel planes (AddMeanScale checked that every channel has an FP32 blob of the same size)
+        const int32_t plane = channels && pre[0]->meanData ? static_cast<int32_t>(pre[0]->meanData->size()) : 0;
+        putInt(model, plane);
+        for (int32_t c = 0; plane && c < channels; ++c) {
+            auto mem = as<MemoryBlob>(pre[c]->meanData);
+            auto locked = mem->rmap();
+            model.write(locked.as<const char*>(), static_cast<std::streamsize>(plane * sizeof(float)));
+        }
     }
     putInt(model, static_cast<int32_t>(_networkOutputs.size()));
     for (const auto& out : _networkOutputs) {
@@ -318,7 +340,7 @@ IExecutableNetworkInternal::Ptr Plugin::ImportNetwork(std::istream& model, const
     const std::string list = getString(model);
     if (!list.empty()) storedDevices[B200ConfigParams::KEY_B200_DEVICES] = list;
     std::vector<std::tuple<std::string, int, int>> ins;
-    std::vector<std::vector<float>> inMeanScale;
+    std::vector<std::vector<float>> inMeanScale, inMeanImage;
     std::vector<std::pair<std::string, int>> outs;
     for (int k = 0, n = getInt(model); k < n; ++k) {
         std::string name = getString(model);
@@ -330,6 +352,12 @@ IExecutableNetworkInternal::Ptr Plugin::ImportNetwork(std::istream& model, const
         if (channels) model.read(reinterpret_cast<char*>(ms.data()), static_cast<std::streamsize>(ms.size() * sizeof(float)));
         if (!model) IE_THROW(NetworkNotRead) << "B200 plugin: truncated exported network";
         inMeanScale.push_back(std::move(ms));
+        const int plane = getInt(model);
+        if (plane < 0 || plane > (1 << 28)) IE_THROW(NetworkNotRead) << "B200 plugin: corrupt exported network";
+        std::vector<float> image(static_cast<size_t>(plane) * static_cast<size_t>(channels));
+        if (!image.empty()) model.read(reinterpret_cast<char*>(image.data()), static_cast<std::streamsize>(image.size() * sizeof(float)));
+        if (!model) IE_THROW(NetworkNotRead) << "B200 plugin: truncated exported network";
+        inMeanImage.push_back(std::move(image));
     }
     for (int k = 0, n = getInt(model); k < n; ++k) {
         std::string name = getString(model);
@@ -364,6 +392,17 @@ IExecutableNetworkInternal::Ptr Plugin::ImportNetwork(std::istream& model, const
                 any = any || ms[2 * c] != 0.f || ms[2 * c + 1] != 1.f;
             }
             if (any) pre.setVariant(MEAN_VALUE);
+            const auto& image = inMeanImage[static_cast<size_t>(&in - &ins[0])];
+            if (!image.empty()) {
+                const size_t channels = ms.size() / 2, plane = image.size() / channels;
+                for (size_t c = 0; c < channels; ++c) {
+                    auto blob = make_shared_blob<float>(TensorDesc(Precision::FP32, {plane}, Layout::C));
+                    blob->allocate();
+                    std::memcpy(blob->buffer().as<float*>(), &image[c * plane], plane * sizeof(float));
+                    pre[c]->meanData = blob;
+                }
+                pre.setVariant(MEAN_IMAGE);
+            }
         }
     }
     for (const auto& out : outs) {
@@ -392,8 +431,11 @@ QueryNetworkResult Plugin::QueryNetwork(const CNNNetwork& network, const std::ma
     for (const auto& node : transformed->get_ops()) {
         // op-level check, then the node's own geometry through the compiler (cheap ops and weight-heavy convolutions are trusted to the
         // op-level check: their lowering has no shape-dependent refusal)
+        std::string why = "no lowering for this operation";
         bool ok = IsNodeSupported(node);
-        if (ok && !ngraph::is_type<ngraph::opset1::Convolution>(node) && !ngraph::is_type<ngraph::opset1::GroupConvolution>(node)) ok = DryCompileNode(node);
+        if (ok && !ngraph::is_type<ngraph::opset1::Convolution>(node) && !ngraph::is_type<ngraph::opset1::GroupConvolution>(node)) ok = DryCompileNode(node, &why);
+        if (!ok && std::getenv("B200_QUERY_VERBOSE"))   // diagnostics for HETERO splits: which node was refused and why
+            std::cerr << "[B200 QueryNetwork] " << node->get_type_name() << " '" << node->get_friendly_name() << "' refused: " << why << std::endl;
         for (const auto& fused : ngraph::getFusedNamesVector(node))
             if (original.count(fused)) (ok ? supported : unsupported).insert(fused);
     }
@@ -658,11 +700,14 @@ InferRequest::InferRequest(const InputsDataMap& networkInputs, const OutputsData
     _outputNames.resize(_networkOutputs.size());
     _inShardBytes.assign(_networkInputs.size(), 0);
     _outShardBytes.assign(_networkOutputs.size(), 0);
+    _inFormat.assign(_networkInputs.size(), {0, 0});
+    _outFormat.assign(_networkOutputs.size(), {0, 0});
     _outStage.assign(_networkOutputs.size(), std::vector<void*>(static_cast<size_t>(shards), nullptr));
     for (const auto& in : _networkInputs) {
         const int idx = network->inputIndex(in.first);
         const TensorDesc& desc = in.second->getTensorDesc();
-        for (auto* r : _reqs) B200_CALL(b200_request_set_io_format(r, 0, idx, BlobDtype(desc.getPrecision(), in.first), BlobLayout(desc, in.first)), "input format");
+        _inFormat[idx] = {BlobDtype(desc.getPrecision(), in.first), BlobLayout(desc, in.first)};
+        for (auto* r : _reqs) B200_CALL(b200_request_set_io_format(r, 0, idx, _inFormat[idx].first, _inFormat[idx].second), "input format");
         B200_CALL(b200_request_io_bytes(_reqs[0], 0, idx, &_inShardBytes[idx]), "io size");
         _inputNames[idx] = in.first;
         _inputs[in.first] = allocatePinned(desc);
@@ -670,7 +715,8 @@ InferRequest::InferRequest(const InputsDataMap& networkInputs, const OutputsData
     for (const auto& out : _networkOutputs) {
         const int idx = network->outputIndex(out.first);
         const TensorDesc& desc = out.second->getTensorDesc();
-        for (auto* r : _reqs) B200_CALL(b200_request_set_io_format(r, 1, idx, BlobDtype(desc.getPrecision(), out.first), BlobLayout(desc, out.first)), "output format");
+        _outFormat[idx] = {BlobDtype(desc.getPrecision(), out.first), BlobLayout(desc, out.first)};
+        for (auto* r : _reqs) B200_CALL(b200_request_set_io_format(r, 1, idx, _outFormat[idx].first, _outFormat[idx].second), "output format");
         B200_CALL(b200_request_io_bytes(_reqs[0], 1, idx, &_outShardBytes[idx]), "io size");
         _outputNames[idx] = out.first;
         _outputs[out.first] = allocatePinned(desc);
@@ -717,13 +763,23 @@ void InferRequest::pinUserMemory(const void* ptr, size_t bytes) {
 }
 
 void InferRequest::SetBlob(const std::string& name, const Blob::Ptr& data) {
-    IInferRequestInternal::SetBlob(name, data);   // size / precision checks, pre-processing set-up (layout conversion of inputs on the host)
-    // outputs are written by the device in the layout the network was loaded with: a blob that asks for another one is refused
-    auto out = _networkOutputs.find(name);
-    if (out != _networkOutputs.end() && data && data->getTensorDesc().getDims().size() == 4 &&
-        data->getTensorDesc().getLayout() != out->second->getTensorDesc().getLayout())
-        IE_THROW(ParameterMismatch) << "B200 plugin: output blob '" << name << "' has layout " << data->getTensorDesc().getLayout()
-                                    << ", the network was loaded with " << out->second->getTensorDesc().getLayout();
+    // size / precision checks, pre-processing set-up (resize / colour conversion on the host).  The blob's own layout is honoured at
+    // the next start (syncFormat): a 4-D blob may be NCHW or NHWC whatever the network was loaded with, as in the reference's requests
+    // (template_infer_request.cpp blobCopy, mkldnn_infer_request.cpp:212-240 pushInput with the blob's descriptor)
+    IInferRequestInternal::SetBlob(name, data);
+}
+
+// The device-side edge kernels (ingest / emit) are recorded for one (precision, layout) per input / output; a blob that arrives with
+// another layout re-records them (b200_request_set_io_format drops the captured graph of an idle request).
+void InferRequest::syncFormat(bool output, size_t index, const Blob::Ptr& blob) {
+    const std::string& name = output ? _outputNames[index] : _inputNames[index];
+    const TensorDesc& desc = blob->getTensorDesc();
+    const std::pair<int, int> want{BlobDtype(desc.getPrecision(), name), BlobLayout(desc, name)};
+    auto& have = output ? _outFormat[index] : _inFormat[index];
+    if (want == have || (want.first == have.first && want.second == B200_LAYOUT_ANY)) return;
+    for (auto* r : _reqs) B200_CALL(b200_request_set_io_format(r, output ? 1 : 0, static_cast<int>(index), want.first, want.second), "blob format");
+    B200_CALL(b200_request_io_bytes(_reqs[0], output ? 1 : 0, static_cast<int>(index), output ? &_outShardBytes[index] : &_inShardBytes[index]), "io size");
+    have = want;
 }
 
 void InferRequest::preprocessAndStart() {
@@ -733,6 +789,7 @@ void InferRequest::preprocessAndStart() {
     std::vector<uint8_t*> outBase(_outputNames.size(), nullptr);
     for (size_t k = 0; k < _inputNames.size(); ++k) {
         const Blob::Ptr& blob = _inputs.at(_inputNames[k]);
+        if (!blob->is<InferenceEngine::RemoteBlob>()) syncFormat(false, k, blob);
         const uint64_t expect = _inShardBytes[k] * (_network->inputPlan(static_cast<int>(k)).kind == IoPlan::Sliced ? shards : 1);
         if (blob->byteSize() != expect)
             IE_THROW(ParameterMismatch) << "B200 plugin: input blob '" << _inputNames[k] << "' has " << blob->byteSize() << " bytes, the network expects " << expect;
@@ -743,6 +800,7 @@ void InferRequest::preprocessAndStart() {
     for (size_t k = 0; k < _outputNames.size(); ++k) {
         const Blob::Ptr& blob = _outputs.at(_outputNames[k]);
         const IoPlan& plan = _network->outputPlan(static_cast<int>(k));
+        if (!blob->is<InferenceEngine::RemoteBlob>()) syncFormat(true, k, blob);
         const uint64_t expect = _outShardBytes[k] * (plan.kind == IoPlan::Replicated ? 1 : shards);
         if (blob->byteSize() != expect)
             IE_THROW(ParameterMismatch) << "B200 plugin: output blob '" << _outputNames[k] << "' has " << blob->byteSize() << " bytes, the network produces " << expect;

@@ -136,6 +136,8 @@ private:
     std::shared_ptr<InferenceEngine::IAllocator> _allocator;
     std::vector<std::string> _inputNames, _outputNames;   // in device I/O index order
     std::vector<uint64_t> _inShardBytes, _outShardBytes;
+    std::vector<std::pair<int, int>> _inFormat, _outFormat;   // (dtype, layout) the device side is currently recorded for
+    void syncFormat(bool output, size_t index, const InferenceEngine::Blob::Ptr& blob);
     std::vector<std::vector<void*>> _outStage;             // [output][shard] pinned staging (Detections / Replicated outputs of shards > 0)
     std::vector<void*> _stageAllocs;
     std::map<const void*, size_t> _registered;             // user memory page-locked by this request (cudaHostRegister)

@@ -95,6 +95,21 @@ def test_fc_softmax_topk(precision):
     _check(f, {"Parameter_0": rng.standard_normal((5, 64)).astype(np.float32)}, precision)
 
 
+@pytest.mark.parametrize("precision", ["FP32", "BF16", "FP16"])
+@pytest.mark.parametrize("m,k,n", [(1, 84, 10), (7, 30, 16), (33, 100, 72)])
+def test_fc_k_not_multiple_of_8(m, k, n, precision):
+    """FullyConnected whose reduction length is not a multiple of 8 (LeNet's 84 -> 10; found by the reference's behaviour suite,
+    core_integration.hpp:578-624): the activation rows are zero-padded to the 16-byte granule of the kernels first."""
+    rng = np.random.default_rng(m * 1000 + k)
+    f = Function("fc_k")
+    x = f.parameter((m, k))
+    y = f.matmul(f.relu(x), rng.standard_normal((n, k)).astype(np.float32) / np.sqrt(k), transpose_b=True)
+    y = f.add(y, rng.standard_normal((1, n)).astype(np.float32))
+    f.result(y)
+    net = _check(f, {"Parameter_0": rng.standard_normal((m, k)).astype(np.float32)}, precision)
+    assert any(e["impl"] == "copy2d" for e in net.get_exec_graph_info())
+
+
 @pytest.mark.parametrize("precision", ["FP32", "BF16"])
 def test_tiny_resnet(precision):
     f = zoo.resnet50(batch=2, image=64, width=16, blocks=(1, 1, 1, 1), num_classes=24)

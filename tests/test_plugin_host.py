@@ -123,7 +123,7 @@ def test_export_import_round_trip(tiny_resnet_xml, tmp_path):
     p = ie_run(tiny_resnet_xml, "--dry", "--export", blob, "--config", "B200_DRY_COMPILE=YES,B200_INFERENCE_PRECISION=FP16", "--input-precision", "data=U8")
     assert p.returncode == 0, p.stderr
     first = json.loads(p.stdout)
-    assert open(blob, "rb").read(8) == b"B200NET1"
+    assert open(blob, "rb").read(8) == b"B200NET2"
     p = ie_run(tiny_resnet_xml, "--dry", "--import", blob, "--config", "B200_DRY_COMPILE=YES")
     assert p.returncode == 0, p.stderr
     again = json.loads(p.stdout)
