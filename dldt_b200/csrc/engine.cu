@@ -5,6 +5,8 @@
 #include <map>
 #include "engine.h"
 
+#include <dlfcn.h>
+
 #include <chrono>
 #include <thread>
 
@@ -244,6 +246,18 @@ void fill_info(b200_tensor_info* info, const std::string& name, int dtype, const
   for (size_t k = 0; k < shape.size() && k < B200_MAX_RANK; ++k) info->shape[k] = shape[k];
 }
 
+// The CUDA runtime is linked statically into this library: unloading the library (the Inference Engine unloads a plugin and what it
+// links when the last Core that used it goes away) tears the runtime and the primary context down, and the next Core pays context
+// creation again (0.3 - 3 s on a B200 box; the reference's behaviour suites create a Core per test).  Once a device has been
+// touched the library pins itself in the process (RTLD_NODELETE): contexts, the module and its kernels stay loaded until exit.
+void pin_library_once() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    Dl_info info;
+    if (dladdr(reinterpret_cast<const void*>(&pin_library_once), &info) && info.dli_fname) dlopen(info.dli_fname, RTLD_NOW | RTLD_NODELETE);
+  });
+}
+
 void launch_graph_or_eager(b200_request* r) {
   if (r->graph_exec) B200_CUDA(cudaGraphLaunch(r->graph_exec, r->stream));
   else r->enqueue_all(false, nullptr);
@@ -259,6 +273,7 @@ int b200_device_count(int* count) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    if (n > 0) pin_library_once();
     *count = n;
     return B200_OK;
   });
@@ -352,7 +367,7 @@ int b200_compile(const b200_graph* g, const b200_compile_options* opts, b200_net
       // bring the runtime + primary context up BEFORE lowering: the compiler asks the driver which tensor maps it can encode
       // (cudaGetDriverEntryPoint fails on an uninitialised runtime, which silently cost the space-to-depth stem: profiles/README.md)
       int n0 = 0;
-      if (cudaGetDeviceCount(&n0) == cudaSuccess && opts->device < n0) { cudaSetDevice(opts->device); cudaFree(nullptr); }
+      if (cudaGetDeviceCount(&n0) == cudaSuccess && opts->device < n0) { pin_library_once(); cudaSetDevice(opts->device); cudaFree(nullptr); }
       cudaGetLastError();
     }
     lower_graph(*g, *opts, *net);

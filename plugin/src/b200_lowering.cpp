@@ -13,6 +13,8 @@
 #include <ngraph/opsets/opset7.hpp>
 #include <ngraph/pass/constant_folding.hpp>
 #include <ngraph/pass/manager.hpp>
+#include <ngraph/pass/pass.hpp>
+#include <ngraph/rt_info.hpp>
 #include <ngraph_ops/nms_ie_internal.hpp>
 #include <transformations/common_optimizations/common_optimizations.hpp>
 #include <transformations/op_conversions/convert_nms_to_nms_ie_internal.hpp>
@@ -35,9 +37,122 @@ namespace B200Plugin {
 using ngraph::as_type_ptr;
 using NodePtr = std::shared_ptr<ngraph::Node>;
 
+namespace {
+
+// Convolutions over 1 or 3 spatial dimensions expressed through the 2-D kernels (the tcgen05 implicit GEMM / the fp32 kernel), with
+// nothing but data movement around them:
+//   [N,C,W]      -> Reshape to [N,C,1,W], 2-D convolution with a 1 x kw filter, Reshape back;
+//   [N,C,D,H,W]  -> the depth taps become input channels.  The input is zero-padded along D, a Gather of whole depth slices with the constant index list
+//                   {d' sd + t dd : tap t, output depth d'} stacks the kd depth-shifted copies, Reshape / Transpose make it
+//                   [N D', kd C, H, W], ONE 2-D convolution with the filter re-packed to [O, kd C, kh, kw] follows, and a Reshape /
+//                   Transpose pair returns [N, O, D', H', W'].  Sum order differs from the reference's NCDHW loop only inside the fp32
+//                   accumulation of one output element (ngraph reference/convolution.hpp:89-146 semantics: cross-correlation, zero padding).
+// Found by the reference's conformance binary (single_layer_tests/convolution.cpp of the template instances: 80 NCDHW cases).
+class ConvolutionToTwoD : public ngraph::pass::FunctionPass {
+public:
+    bool run_on_function(std::shared_ptr<ngraph::Function> f) override {
+        bool changed = false;
+        for (const auto& node : f->get_ordered_ops()) {
+            auto conv = as_type_ptr<ngraph::opset1::Convolution>(node);
+            if (!conv || !conv->get_input_partial_shape(0).is_static() || !conv->get_output_partial_shape(0).is_static()) continue;
+            auto weights = as_type_ptr<ngraph::opset1::Constant>(conv->input_value(1).get_node_shared_ptr());
+            const ngraph::Shape xs = conv->get_input_shape(0), os = conv->get_output_shape(0);
+            if (!weights || (xs.size() != 3 && xs.size() != 5)) continue;
+            const ngraph::Shape ws = weights->get_shape();
+            const auto& strides = conv->get_strides();
+            const auto& dil = conv->get_dilations();
+            const auto& pb = conv->get_pads_begin();     // resolved by validate_and_infer_types for SAME_* / VALID
+            const auto& pe = conv->get_pads_end();
+            ngraph::NodeVector made;
+            auto keep = [&](const NodePtr& n) { made.push_back(n); return n; };
+            auto i64 = [&](const std::vector<int64_t>& v) { return keep(ngraph::opset1::Constant::create(ngraph::element::i64, ngraph::Shape{v.size()}, v)); };
+            auto dims = [](const ngraph::Shape& sh) { return std::vector<int64_t>(sh.begin(), sh.end()); };
+            ngraph::Output<ngraph::Node> out;
+            if (xs.size() == 3) {
+                auto x4 = keep(std::make_shared<ngraph::opset1::Reshape>(conv->input_value(0), i64({(int64_t)xs[0], (int64_t)xs[1], 1, (int64_t)xs[2]}), false));
+                auto w4 = keep(std::make_shared<ngraph::opset1::Constant>(weights->get_element_type(), ngraph::Shape{ws[0], ws[1], 1, ws[2]}, weights->get_data_ptr()));
+                auto c2 = keep(std::make_shared<ngraph::opset1::Convolution>(x4, w4, ngraph::Strides{1, strides[0]}, ngraph::CoordinateDiff{0, pb[0]},
+                                                                            ngraph::CoordinateDiff{0, pe[0]}, ngraph::Strides{1, dil[0]}));
+                out = keep(std::make_shared<ngraph::opset1::Reshape>(c2, i64(dims(os)), false));
+            } else {
+                if (pb[0] < 0 || pe[0] < 0) continue;
+                const int64_t N = xs[0], C = xs[1], D = xs[2], H = xs[3], W = xs[4], O = ws[0], kd = ws[2], kh = ws[3], kw = ws[4];
+                const int64_t Dp = D + pb[0] + pe[0], Do = os[2];
+                const auto et = conv->get_input_element_type(0);
+                ngraph::Output<ngraph::Node> x = conv->input_value(0);
+                if (Dp != D) {
+                    ngraph::OutputVector parts;
+                    auto zeros = [&](int64_t d) {
+                        return keep(ngraph::opset1::Constant::create(et, ngraph::Shape{(size_t)N, (size_t)C, (size_t)d, (size_t)H, (size_t)W}, std::vector<float>{0.f}));
+                    };
+                    if (pb[0] > 0) parts.push_back(zeros(pb[0]));
+                    parts.push_back(x);
+                    if (pe[0] > 0) parts.push_back(zeros(pe[0]));
+                    x = keep(std::make_shared<ngraph::opset1::Concat>(parts, 2));
+                }
+                std::vector<int64_t> index;
+                for (int64_t t = 0; t < kd; ++t)
+                    for (int64_t d = 0; d < Do; ++d) index.push_back(d * (int64_t)strides[0] + t * (int64_t)dil[0]);
+                // depth first (the gather kernel takes whole slices along axis 0), gather, then [kd, D', N, C, H, W] -> [N, D', kd, C, H, W]
+                auto dfirst = keep(std::make_shared<ngraph::opset1::Transpose>(x, i64({2, 0, 1, 3, 4})));
+                auto stacked = keep(std::make_shared<ngraph::opset1::Gather>(dfirst, i64(index), keep(ngraph::opset1::Constant::create(ngraph::element::i64, ngraph::Shape{}, {0}))));
+                auto s6 = keep(std::make_shared<ngraph::opset1::Reshape>(stacked, i64({kd, Do, N, C, H, W}), false));
+                auto t6 = keep(std::make_shared<ngraph::opset1::Transpose>(s6, i64({2, 1, 0, 3, 4, 5})));
+                auto x4 = keep(std::make_shared<ngraph::opset1::Reshape>(t6, i64({N * Do, kd * C, H, W}), false));
+                // filter [O, C, kd, kh, kw] -> [O, kd, C, kh, kw] -> [O, kd C, kh, kw], on the host
+                const std::vector<float> wsrc = weights->cast_vector<float>();
+                std::vector<float> w2(wsrc.size());
+                for (int64_t o = 0; o < O; ++o)
+                    for (int64_t c = 0; c < C; ++c)
+                        for (int64_t t = 0; t < kd; ++t)
+                            std::copy_n(&wsrc[(size_t)(((o * C + c) * kd + t) * kh * kw)], (size_t)(kh * kw), &w2[(size_t)(((o * kd + t) * C + c) * kh * kw)]);
+                auto w4 = keep(ngraph::opset1::Constant::create(weights->get_element_type(), ngraph::Shape{(size_t)O, (size_t)(kd * C), (size_t)kh, (size_t)kw}, w2));
+                auto c2 = keep(std::make_shared<ngraph::opset1::Convolution>(x4, w4, ngraph::Strides{strides[1], strides[2]}, ngraph::CoordinateDiff{pb[1], pb[2]},
+                                                                            ngraph::CoordinateDiff{pe[1], pe[2]}, ngraph::Strides{dil[1], dil[2]}));
+                auto r5 = keep(std::make_shared<ngraph::opset1::Reshape>(c2, i64({N, Do, O, (int64_t)os[3], (int64_t)os[4]}), false));
+                out = keep(std::make_shared<ngraph::opset1::Transpose>(r5, i64({0, 2, 1, 3, 4})));
+            }
+            out.get_node_shared_ptr()->set_friendly_name(conv->get_friendly_name());
+            ngraph::copy_runtime_info(conv, made);
+            ngraph::replace_node(conv, out.get_node_shared_ptr());
+            changed = true;
+        }
+        return changed;
+    }
+};
+
+// GRN (global response normalisation across channels, opset1): y = x / sqrt(sum_c x^2 + bias), spelled with the element-wise and
+// reduction kernels the library has (ngraph reference/grn.hpp; the reference CPU plugin runs nodes/mkldnn_grn_node.cpp).
+class GrnDecomposition : public ngraph::pass::FunctionPass {
+public:
+    bool run_on_function(std::shared_ptr<ngraph::Function> f) override {
+        bool changed = false;
+        for (const auto& node : f->get_ordered_ops()) {
+            auto grn = as_type_ptr<ngraph::opset1::GRN>(node);
+            if (!grn || !grn->get_input_partial_shape(0).is_static() || grn->get_input_shape(0).size() < 2) continue;
+            const auto et = grn->get_input_element_type(0);
+            auto x = grn->input_value(0);
+            auto sq = std::make_shared<ngraph::opset1::Multiply>(x, x);
+            auto sum = std::make_shared<ngraph::opset1::ReduceSum>(sq, ngraph::opset1::Constant::create(ngraph::element::i64, ngraph::Shape{1}, {1}), true);
+            auto biased = std::make_shared<ngraph::opset1::Add>(sum, ngraph::opset1::Constant::create(et, ngraph::Shape{}, {grn->get_bias()}));
+            auto norm = std::make_shared<ngraph::opset1::Sqrt>(biased);
+            auto out = std::make_shared<ngraph::opset1::Divide>(x, norm);
+            out->set_friendly_name(grn->get_friendly_name());
+            ngraph::copy_runtime_info(grn, {sq, sum, biased, norm, out});
+            ngraph::replace_node(grn, out);
+            changed = true;
+        }
+        return changed;
+    }
+};
+
+}  // namespace
+
 std::shared_ptr<ngraph::Function> TransformNetwork(const std::shared_ptr<const ngraph::Function>& function) {
     auto f = ngraph::clone_function(*function);
     ngraph::pass::Manager manager;
+    manager.register_pass<ConvolutionToTwoD>();
+    manager.register_pass<GrnDecomposition>();
     manager.register_pass<ngraph::pass::CommonOptimizations>();
     // NMS-1/3/4 -> NMS-5 -> NonMaxSuppressionIEInternal (static, padded output shapes), as mkldnn_plugin.cpp:150-156 does
     manager.register_pass<ngraph::pass::ConvertNMS1ToNMS5>();

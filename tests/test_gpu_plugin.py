@@ -165,3 +165,32 @@ def test_mean_scale_preprocessing_runs_on_the_device(tmp_path):
     assert np.linalg.norm(a - b) / np.linalg.norm(b) < 1e-4
     again, _ = refrun.run(f, {"data": x}, device="B200", extra=["--import", blob])
     np.testing.assert_array_equal(again["fc_bias"], a)
+
+
+CONV_ND = [
+    # x shape, filter shape, strides, pads begin, pads end, dilations  (the NCDHW shapes of the reference's template convolution instances + NCW)
+    ((1, 3, 10, 10, 10), (5, 3, 3, 3, 3), (1, 1, 1), (0, 0, 0), (0, 0, 0), (1, 1, 1)),
+    ((1, 3, 10, 10, 10), (5, 3, 3, 5, 3), (1, 2, 1), (0, 2, 0), (0, 2, 0), (1, 2, 1)),
+    ((2, 8, 7, 9, 6), (16, 8, 2, 3, 3), (2, 1, 2), (1, 1, 1), (0, 1, 2), (2, 1, 1)),
+    ((2, 16, 50), (24, 16, 5), (2,), (2,), (2,), (1,)),
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("precision,tol", [("FP32", 1e-4), ("BF16", 1e-2)])
+@pytest.mark.parametrize("geom", CONV_ND)
+def test_conv_1d_3d_matches_reference_cpu_plugin(geom, precision, tol, tmp_path):
+    """Convolutions over 1 / 3 spatial dimensions (rewritten to the 2-D kernels by ConvolutionToTwoD) against the UNMODIFIED
+    MKLDNNPlugin on the same hand-written IR and inputs."""
+    x_shape, w_shape, strides, pb, pe, dil = geom
+    rng = np.random.default_rng(sum(x_shape) * 31 + len(w_shape))
+    xml = str(tmp_path / "conv_nd.xml")
+    w = (rng.standard_normal(w_shape) / np.sqrt(np.prod(w_shape[1:]))).astype(np.float32)
+    refrun.write_conv_nd_ir(xml, x_shape, w, strides, pb, pe, dil)
+    x = rng.standard_normal(x_shape).astype(np.float32)
+    ref, _ = refrun.run(xml, {"data": x}, device="CPU")
+    got, _ = refrun.run(xml, {"data": x}, device="B200", config={"B200_INFERENCE_PRECISION": precision})
+    (name, r), = ref.items()
+    assert got[name].shape == r.shape
+    err = float(np.linalg.norm(got[name].astype(np.float64) - r) / np.linalg.norm(r))
+    assert err <= tol, "rel-L2 %.3e" % err

@@ -6,6 +6,7 @@ import json
 import os
 import subprocess
 
+import numpy as np
 import pytest
 
 from dldt_b200 import ir, zoo
@@ -182,3 +183,21 @@ def test_unsupported_geometry_fails_at_load_not_at_first_infer(tmp_path):
     ir.serialize(f2, xml2)
     p = ie_run(xml2, "--dry", "--config", "B200_DRY_COMPILE=YES")
     assert p.returncode == 0, p.stderr
+
+
+@pytest.mark.parametrize("x_shape,w_shape,strides,pb,pe,dil", [
+    ((1, 3, 10, 10, 10), (5, 3, 3, 5, 3), (1, 2, 1), (1, 2, 0), (0, 2, 1), (1, 2, 1)),
+    ((2, 16, 50), (24, 16, 5), (2,), (2,), (2,), (1,)),
+])
+def test_convolutions_over_1_and_3_spatial_dims_are_rewritten_to_2d(tmp_path, x_shape, w_shape, strides, pb, pe, dil):
+    """NCW / NCDHW convolutions (single_layer_tests/convolution.cpp of the reference's template instances) reach the 2-D kernels through
+    ConvolutionToTwoD (plugin/src/b200_lowering.cpp): QueryNetwork accepts every layer, the compiled schedule has ONE convolution."""
+    from tools import refrun
+    xml = str(tmp_path / "conv_nd.xml")
+    refrun.write_conv_nd_ir(xml, x_shape, np.ones(w_shape, np.float32), strides, pb, pe, dil)
+    q = ie_run(xml, "--query")
+    assert q.returncode == 0, q.stderr
+    assert json.loads(q.stdout)["supported_layers"] == json.loads(q.stdout)["total_layers"]
+    p = ie_run(xml, "--dry", "--config", "B200_DRY_COMPILE=YES")
+    assert p.returncode == 0, p.stderr
+    assert json.loads(p.stdout)["exec_convolutions"] == 1

@@ -25,8 +25,11 @@ def run(func, inputs, device="CPU", config=None, input_precisions=None, niter=1,
     if device == "CPU":
         config.setdefault("ENFORCE_BF16", "NO")
     tmp = workdir or tempfile.mkdtemp(prefix="refrun_")
-    xml = os.path.join(tmp, "model.xml")
-    ir.serialize(func, xml)
+    if isinstance(func, str):      # an IR that already exists (graphs the recorded-Function front end cannot express, e.g. NCDHW convolutions)
+        xml = func
+    else:
+        xml = os.path.join(tmp, "model.xml")
+        ir.serialize(func, xml)
     cmd = [IE_RUN, "--model", xml, "--device", device, "--output-dir", tmp, "--niter", str(niter),
            "--plugins", os.path.join(REF, "lib", "plugins.xml")]
     if config:
@@ -53,3 +56,36 @@ def run(func, inputs, device="CPU", config=None, input_precisions=None, niter=1,
     for name, o in man["outputs"].items():
         outs[name] = np.fromfile(os.path.join(tmp, o["file"]), dtype=_NP[o["precision"]]).reshape(o["shape"])
     return outs, man
+
+
+def write_conv_nd_ir(xml_path, x_shape, weights, strides, pads_begin, pads_end, dilations, relu=True):
+    """IR v10 of Parameter -> Convolution (1, 2 or 3 spatial dimensions) [-> ReLU] -> Result, written by hand: the recorded-Function
+    front end (and the C ABI behind it) is 2-D only, the plugin accepts the others by rewriting them (ConvolutionToTwoD)."""
+    w = np.ascontiguousarray(weights, np.float32)
+    nd = len(x_shape) - 2
+    out = [x_shape[0], w.shape[0]] + [(x_shape[2 + k] + pads_begin[k] + pads_end[k] - (dilations[k] * (w.shape[2 + k] - 1) + 1)) // strides[k] + 1
+                                      for k in range(nd)]
+
+    def port(pid, shape):
+        return '<port id="%d" precision="FP32">%s</port>' % (pid, "".join("<dim>%d</dim>" % d for d in shape))
+
+    j = lambda v: ", ".join(str(int(a)) for a in v)
+    layers = [
+        '<layer id="0" name="data" type="Parameter" version="opset1"><data element_type="f32" shape="%s"/><output>%s</output></layer>' % (j(x_shape), port(0, x_shape)),
+        '<layer id="1" name="w" type="Const" version="opset1"><data element_type="f32" shape="%s" offset="0" size="%d"/><output>%s</output></layer>'
+        % (j(w.shape), w.nbytes, port(0, w.shape)),
+        '<layer id="2" name="conv" type="Convolution" version="opset1"><data strides="%s" pads_begin="%s" pads_end="%s" dilations="%s" auto_pad="explicit"/>'
+        '<input>%s%s</input><output>%s</output></layer>' % (j(strides), j(pads_begin), j(pads_end), j(dilations), port(0, x_shape), port(1, w.shape), port(2, out)),
+    ]
+    edges = ['<edge from-layer="0" from-port="0" to-layer="2" to-port="0"/>', '<edge from-layer="1" from-port="0" to-layer="2" to-port="1"/>']
+    last = 2
+    if relu:
+        layers.append('<layer id="3" name="relu" type="ReLU" version="opset1"><input>%s</input><output>%s</output></layer>' % (port(0, out), port(1, out)))
+        edges.append('<edge from-layer="2" from-port="2" to-layer="3" to-port="0"/>')
+        last = 3
+    layers.append('<layer id="%d" name="result" type="Result" version="opset1"><input>%s</input></layer>' % (last + 1, port(0, out)))
+    edges.append('<edge from-layer="%d" from-port="%d" to-layer="%d" to-port="0"/>' % (last, 2 if last == 2 else 1, last + 1))
+    with open(xml_path, "w") as f:
+        f.write('<?xml version="1.0"?>\n<net name="conv_nd" version="10"><layers>%s</layers><edges>%s</edges></net>\n' % ("".join(layers), "".join(edges)))
+    w.tofile(xml_path[:-4] + ".bin")
+    return out
