@@ -1,0 +1,169 @@
+"""Seeded random small networks over the ops of the hot path (convolutions of every flavour the compiler distinguishes, pooling, element-wise
+chains, residual adds, concats, a FullyConnected head) for the differential tests: the CUDA path against the numpy oracle
+(tests/test_gpu_random_graphs.py) and, without a GPU, the compiler against itself (tests/test_random_graphs_compile.py: every graph must
+lower, plan and keep its output names).  Shapes are drawn to hit the awkward cases on purpose: channel counts that are not multiples of 8,
+odd spatial sizes, strides / dilations / asymmetric padding, reduction lengths that are not multiples of 8 or 64."""
+import numpy as np
+
+from dldt_b200 import Function
+
+CHANNELS = [1, 3, 4, 5, 8, 13, 16, 24, 32, 40, 48, 64, 72, 96, 128]
+UNARY = ["relu", "sigmoid", "tanh", "hswish", "hsigmoid", "mish", "abs", "swish", "gelu", "clamp", "elu"]
+
+
+def _act(f, rng, y):
+    kind = UNARY[rng.integers(len(UNARY))]
+    if kind == "clamp":
+        return f.clamp(y, 0.0, 6.0)
+    if kind == "swish":
+        return f.swish(y, 1.0)
+    if kind == "gelu":
+        return f.gelu(y, "ERF" if rng.integers(2) else "TANH")
+    if kind == "elu":
+        return f.elu(y, 0.5)
+    return getattr(f, kind)(y)
+
+
+def _conv(f, rng, x, shape):
+    n, c, h, w = shape
+    k = int(rng.choice([1, 1, 3, 3, 5]))
+    s = int(rng.choice([1, 1, 2]))
+    d = int(rng.choice([1, 1, 1, 2])) if k > 1 else 1
+    pb = (int(rng.integers(0, k // 2 + 1)), int(rng.integers(0, k // 2 + 1)))
+    pe = (int(rng.integers(0, k // 2 + 1)), int(rng.integers(0, k // 2 + 1)))
+    eff = d * (k - 1) + 1
+    if h + pb[0] + pe[0] < eff or w + pb[1] + pe[1] < eff:
+        k, d, eff, pb, pe = 1, 1, 1, (0, 0), (0, 0)
+    mode = rng.integers(4)
+    if mode == 0 and c > 1:                        # depthwise
+        wt = (rng.standard_normal((c, 1, 1, k, k)) / k).astype(np.float32)
+        y = f.group_convolution(x, wt, (s, s), pb, pe, (d, d))
+        o = c
+    elif mode == 1 and c % 4 == 0 and c >= 8:      # grouped
+        g = int(rng.choice([2, 4]))
+        o = g * int(rng.choice([1, 2, 3, 4]))
+        wt = (rng.standard_normal((g, o // g, c // g, k, k)) / np.sqrt(c // g * k * k)).astype(np.float32)
+        y = f.group_convolution(x, wt, (s, s), pb, pe, (d, d))
+    else:                                          # dense
+        o = int(rng.choice(CHANNELS))
+        wt = (rng.standard_normal((o, c, k, k)) / np.sqrt(c * k * k)).astype(np.float32)
+        y = f.convolution(x, wt, (s, s), pb, pe, (d, d))
+    ho = (h + pb[0] + pe[0] - eff) // s + 1
+    wo = (w + pb[1] + pe[1] - eff) // s + 1
+    if rng.integers(4):
+        y = f.add(y, rng.standard_normal((1, o, 1, 1)).astype(np.float32) * 0.1)
+    if rng.integers(3):
+        y = _act(f, rng, y)
+    return y, (n, o, ho, wo)
+
+
+def _pool(f, rng, x, shape):
+    n, c, h, w = shape
+    k = int(rng.choice([2, 3]))
+    s = int(rng.choice([1, 2]))
+    p = int(rng.integers(0, 2))
+    if h + 2 * p < k or w + 2 * p < k:
+        return x, shape
+    rounding = "ceil" if rng.integers(3) == 0 else "floor"
+    if rng.integers(2):
+        y = f.max_pool(x, (k, k), (s, s), (p, p), (p, p), rounding=rounding)
+    else:
+        y = f.avg_pool(x, (k, k), (s, s), (p, p), (p, p), exclude_pad=bool(rng.integers(2)), rounding=rounding)
+
+    def out(v):
+        num = v + 2 * p - k
+        o = (-(-num // s) if rounding == "ceil" else num // s) + 1
+        if rounding == "ceil" and (o - 1) * s >= v + p:     # the last window must start inside the input or the left padding
+            o -= 1
+        return o
+    return y, (n, c, out(h), out(w))
+
+
+def _inverted_residual(f, rng, x, shape):
+    """MobileNetV2 block (expand 1x1 + ReLU6 -> depthwise 3x3 + ReLU6 -> project 1x1 [+ input]): the shape the fused block kernel takes."""
+    n, c, h, w = shape
+    t = int(rng.choice([1, 2, 4, 6]))
+    s = int(rng.choice([1, 1, 2]))
+    o = c if rng.integers(2) else int(rng.choice(CHANNELS[4:]))
+    hid = c * t
+    y = x
+    if t > 1:
+        y = f.clamp(f.add(f.convolution(y, (rng.standard_normal((hid, c, 1, 1)) / np.sqrt(c)).astype(np.float32), (1, 1), (0, 0), (0, 0)),
+                          rng.standard_normal((1, hid, 1, 1)).astype(np.float32) * 0.1), 0.0, 6.0)
+    y = f.clamp(f.add(f.group_convolution(y, (rng.standard_normal((hid, 1, 1, 3, 3)) / 3).astype(np.float32), (s, s), (1, 1), (1, 1)),
+                      rng.standard_normal((1, hid, 1, 1)).astype(np.float32) * 0.1), 0.0, 6.0)
+    y = f.add(f.convolution(y, (rng.standard_normal((o, hid, 1, 1)) / np.sqrt(hid)).astype(np.float32), (1, 1), (0, 0), (0, 0)),
+              rng.standard_normal((1, o, 1, 1)).astype(np.float32) * 0.1)
+    ho, wo = (h + 2 - 3) // s + 1, (w + 2 - 3) // s + 1
+    if s == 1 and o == c:
+        y = f.add(y, x)
+    return y, (n, o, ho, wo)
+
+
+def _bottleneck(f, rng, x, shape):
+    """ResNet bottleneck with a projection shortcut (1x1 reduce -> 3x3 -> 1x1 expand, + 1x1 strided shortcut, ReLU): the K-concatenated
+    shortcut fold and the strided second source of the pair kernel."""
+    n, c, h, w = shape
+    mid = int(rng.choice([8, 16, 32, 64]))
+    o = int(rng.choice([32, 64, 128, 256]))
+    s = int(rng.choice([1, 2]))
+
+    def cbr(v, wshape, stride, pad, relu=True):
+        fan = wshape[1] * wshape[2] * wshape[3]
+        v = f.add(f.convolution(v, (rng.standard_normal(wshape) / np.sqrt(fan)).astype(np.float32), (stride, stride), (pad, pad), (pad, pad)),
+                  rng.standard_normal((1, wshape[0], 1, 1)).astype(np.float32) * 0.1)
+        return f.relu(v) if relu else v
+    a = cbr(x, (mid, c, 1, 1), 1, 0)
+    b = cbr(a, (mid, mid, 3, 3), s, 1)
+    cc = cbr(b, (o, mid, 1, 1), 1, 0, relu=False)
+    sc = cbr(x, (o, c, 1, 1), s, 0, relu=False)
+    ho, wo = (h + 2 - 3) // s + 1, (w + 2 - 3) // s + 1
+    return f.relu(f.add(cc, sc)), (n, o, ho, wo)
+
+
+def build(seed):
+    """Returns (Function, {input name: array}).  Seeds >= 1000 draw wider tensors (64-512 channels, up to 28 x 28, batch up to 4): several
+    k-blocks and several tiles per tcgen05 launch."""
+    rng = np.random.default_rng(seed)
+    f = Function("random_%d" % seed)
+    if seed >= 1000:
+        shape = (int(rng.integers(1, 5)), int(rng.choice([64, 96, 128, 192, 256, 320, 512])), int(rng.integers(7, 29)), int(rng.integers(7, 29)))
+    else:
+        shape = (int(rng.integers(1, 4)), int(rng.choice(CHANNELS[:9])), int(rng.integers(6, 21)), int(rng.integers(6, 21)))
+    x = f.parameter(shape)
+    inputs = {"Parameter_0": rng.standard_normal(shape).astype(np.float32)}
+    y = x
+    for _ in range(int(rng.integers(2, 6))):
+        op = rng.integers(8)
+        if op == 6:
+            y, shape = _inverted_residual(f, rng, y, shape)
+        elif op == 7:
+            y, shape = _bottleneck(f, rng, y, shape)
+        elif op <= 2:
+            y, shape = _conv(f, rng, y, shape)
+        elif op == 3:
+            y, shape = _pool(f, rng, y, shape)
+        elif op == 4:                               # residual block: y + act(conv1x1(y))
+            c = shape[1]
+            wt = (rng.standard_normal((c, c, 1, 1)) / np.sqrt(c)).astype(np.float32)
+            z = f.convolution(y, wt, (1, 1), (0, 0), (0, 0))
+            y = f.add(_act(f, rng, z), y)
+            if rng.integers(2):
+                y = f.relu(y)
+        else:                                       # two branches concatenated on channels
+            c = shape[1]
+            o = int(rng.choice(CHANNELS[1:8]))
+            wt = (rng.standard_normal((o, c, 1, 1)) / np.sqrt(c)).astype(np.float32)
+            y = f.concat([y, f.relu(f.convolution(y, wt, (1, 1), (0, 0), (0, 0)))], 1)
+            shape = (shape[0], c + o, shape[2], shape[3])
+        if min(shape[2], shape[3]) < 2:
+            break
+    f.result(y)
+    # head: global average pool -> flatten -> FullyConnected (reduction length = whatever channel count came out) -> softmax
+    n, c = shape[0], shape[1]
+    g = f.reshape(f.reduce_mean(y, (2, 3), keep_dims=False), (n, c))
+    classes = int(rng.choice([10, 17, 100]))
+    logits = f.add(f.matmul(g, (rng.standard_normal((classes, c)) / np.sqrt(c)).astype(np.float32), transpose_b=True),
+                   rng.standard_normal((1, classes)).astype(np.float32) * 0.1)
+    f.result(f.softmax(logits, 1))
+    return f, inputs

@@ -1,0 +1,43 @@
+"""Randomized differential test on the B200: seeded random small networks (tests/random_graphs.py) through the C ABI against the numpy
+oracle.  fp32 mode at the north star's 1e-4; bf16 / fp16 as a sanity bound (3e-2 / 1e-2: depth and activation mix are random, the
+calibrated 16-bit gates live in test_gpu_golden.py / test_gpu_configs.py)."""
+import numpy as np
+import pytest
+
+from tests import random_graphs
+from tests.util import rel_l2, run_b200, run_oracle
+
+pytestmark = pytest.mark.gpu
+TOL = {"FP32": 1e-4, "BF16": 3e-2, "FP16": 1e-2}
+
+
+@pytest.mark.parametrize("seed", list(range(80)) + list(range(1000, 1080)))
+def test_random_graph_matches_oracle(seed):
+    f, inputs = random_graphs.build(seed)
+    ref = run_oracle(f, inputs)
+    for precision in ("FP32", "BF16", "FP16") if seed % 3 == 0 else ("FP32", "BF16"):
+        got, _ = run_b200(f, inputs, precision)
+        assert set(got) == set(ref)
+        for k in ref:
+            assert got[k].shape == ref[k].shape
+            err = rel_l2(got[k], ref[k])
+            assert err <= TOL[precision], "seed %d %s %s: rel-L2 %.3e" % (seed, precision, k, err)
+
+
+@pytest.mark.parametrize("seed", list(range(0, 60, 3)) + list(range(1000, 1030, 3)))
+def test_random_graph_through_the_plugin_matches_the_reference_cpu_plugin(seed):
+    """Same networks as IR v10 through the reference Core: device B200 (libb200Plugin.so: nGraph passes + lowering + C ABI) against device
+    CPU (the UNMODIFIED MKLDNNPlugin, fp32) - the differential test with the real reference on both sides of the drop-in boundary."""
+    import os
+    from tools import refrun
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not (refrun.available() and os.path.exists(os.path.join(root, "plugin", "lib", "libb200Plugin.so"))):
+        pytest.skip("oracle/_ref or plugin/lib did not travel")
+    f, inputs = random_graphs.build(seed)
+    ref, _ = refrun.run(f, inputs, device="CPU")
+    got, _ = refrun.run(f, inputs, device="B200", config={"B200_INFERENCE_PRECISION": "FP32"})
+    assert set(got) == set(ref)
+    for k in ref:
+        assert got[k].shape == ref[k].shape
+        err = rel_l2(got[k], ref[k])
+        assert err <= 1e-4, "seed %d %s: rel-L2 %.3e" % (seed, k, err)
