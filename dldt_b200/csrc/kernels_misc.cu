@@ -212,9 +212,10 @@ __global__ void __launch_bounds__(256) dwconv3x3_16b_kernel(const uint4* __restr
 }
 
 // ---- pooling ------------------------------------------------------------------------------------
-// MaxPool ignores padding; AvgPool divisor = kh*kw iff !exclude_pad and some pad != 0 (window clipped
-// to the padded extent), else the number of in-bounds elements
-// (reference/max_pool.hpp:74-117, reference/avg_pool.hpp:215-262).
+// MaxPool ignores padding; AvgPool divisor = kh*kw iff !exclude_pad and some pad != 0 - the WHOLE window, also where ceil rounding
+// pushed it past the padded extent - else the number of in-bounds elements (reference/max_pool.hpp:74-117,
+// reference/avg_pool.hpp:215-262: "the size of window doesn't change even if the window was clipped"; MKLDNNPlugin's jit pooling agrees.
+// Its single-channel path divides by the clipped window instead: found by the randomized differential test, seed 43).
 template <typename T>
 __global__ void pool_kernel(const PoolParams p) {
   const int cpc = p.Cp >> 3;
@@ -232,16 +233,13 @@ __global__ void pool_kernel(const PoolParams p) {
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = p.is_avg ? 0.f : -FLT_MAX;
   int h0 = ho * p.sh - p.pt, w0 = wo * p.sw - p.pl;
-  int cnt_in = 0, cnt_pad = 0;
+  int cnt_in = 0;
   for (int r = 0; r < p.kh; ++r) {
     int hi = h0 + r;
     bool h_in = (unsigned)hi < (unsigned)p.H;
-    bool h_padded = hi >= -p.pt && hi < p.H + p.pb;   // inside the padded extent
     for (int s = 0; s < p.kw; ++s) {
       int wi = w0 + s;
       bool w_in = (unsigned)wi < (unsigned)p.W;
-      bool w_padded = wi >= -p.pl && wi < p.W + p.pr;
-      if (h_padded && w_padded) ++cnt_pad;
       if (!(h_in && w_in)) continue;
       ++cnt_in;
       float xv[8];
@@ -252,7 +250,7 @@ __global__ void pool_kernel(const PoolParams p) {
   }
   if (p.is_avg) {
     bool any_pad = (p.pt | p.pl | p.pb | p.pr) != 0;
-    int div = (!p.exclude_pad && any_pad) ? cnt_pad : cnt_in;
+    int div = (!p.exclude_pad && any_pad) ? p.kh * p.kw : cnt_in;
     float inv = div > 0 ? 1.f / (float)div : 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] *= inv;

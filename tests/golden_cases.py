@@ -128,6 +128,12 @@ def avgpool_global(): return _pool_case("avgpool_global", "avg", (3, 40, 7, 7), 
 @case
 def avgpool_ceil_nopad(): return _pool_case("avgpool_ceil_nopad", "avg", (1, 8, 10, 10), (3, 3), (2, 2), (0, 0), (0, 0), rounding="ceil", exclude_pad=True)
 
+# ceil rounding pushes the last window PAST the padded extent (rows / cols 3..5 of a 4 x 4 input padded by 1): include-pad still divides by
+# kh * kw (reference/avg_pool.hpp:215-232; MKLDNNPlugin's jit pooling).  Found by the randomized differential test (seed 43).
+@case
+def avgpool_ceil_include_pad_overflow():
+    return _pool_case("avgpool_ceil_include_pad_overflow", "avg", (2, 24, 4, 6), (3, 3), (2, 2), (1, 1), (1, 1), rounding="ceil", exclude_pad=False)
+
 
 # ---- matmul / FC ----------------------------------------------------------------------------------------
 @case

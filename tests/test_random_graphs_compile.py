@@ -19,3 +19,19 @@ def test_random_graph_lowers_in_every_precision(seed):
         assert {name: shape for name, shape, _ in net.outputs} == {k: v.shape for k, v in ref.items()}
     for v in ref.values():
         assert np.isfinite(v).all()
+
+
+@pytest.mark.parametrize("seed", list(range(1, 40, 4)) + list(range(1001, 1020, 4)))
+def test_oracle_matches_the_reference_cpu_plugin_on_random_graphs(seed):
+    """Pins the numpy restatement on graphs nobody wrote by hand: the same random networks on the UNMODIFIED MKLDNNPlugin (oracle/_ref,
+    fp32) - beyond the fixed golden cases of tests/test_oracle_golden.py."""
+    from tools import refrun
+    if not refrun.available():
+        pytest.skip("oracle/_ref not built")
+    f, inputs = random_graphs.build(seed)
+    mine = run_oracle(f, inputs)
+    ref, _ = refrun.run(f, inputs, device="CPU")
+    assert set(mine) == set(ref)
+    for k, v in ref.items():
+        err = float(np.linalg.norm(mine[k].astype(np.float64) - v) / max(np.linalg.norm(v), 1e-30))
+        assert err <= 1e-5, "seed %d %s: %.3e" % (seed, k, err)
