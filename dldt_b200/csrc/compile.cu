@@ -1390,7 +1390,6 @@ void Lowerer::lower_matmul_general(const Node& n, const FusedConv* f) {
   if (!n.i[1] && !mn) b = permute_last2(b, n.name + "_Bt");   // need [.., N, K]
   const int64_t M = a.shape[a.shape.size() - 2], K = a.shape.back(), Nn = mn ? b.shape.back() : b.shape[b.shape.size() - 2];
   B200_CHECK((mn ? b.shape[b.shape.size() - 2] : b.shape.back()) == K, B200_ERR_INVALID, "MatMul '" << n.name << "': K mismatch");
-  B200_CHECK(K % 8 == 0 && Nn % 8 == 0, B200_ERR_UNSUPPORTED, "MatMul '" << n.name << "': K and N must be multiples of 8");
   const int64_t batch_a = numel(a.shape) / (M * K), batch_b = numel(b.shape) / (Nn * K);
   B200_CHECK(batch_a == batch_b || batch_b == 1, B200_ERR_UNSUPPORTED, "MatMul '" << n.name << "': unsupported batch broadcast");
   if (batch_b != 1) {
@@ -1401,17 +1400,51 @@ void Lowerer::lower_matmul_general(const Node& n, const FusedConv* f) {
     B200_CHECK(ba == bb, B200_ERR_UNSUPPORTED, "MatMul '" << n.name << "': broadcast between batch dimensions is not supported");
   }
   B200_CHECK(batch_a <= 65535, B200_ERR_UNSUPPORTED, "MatMul batch too large");
+  // The kernels read operand rows and write output rows in 16-byte granules.  A reduction length or an output width that is not a multiple
+  // of 8 (attention over a sequence of 33 tokens: QK^T has N = 33, PV has K = 33) goes through zero-padded copies of the operands and a
+  // padded output that is compacted afterwards; found by the randomized sequence-model tests.
+  const int64_t Kp = round_up(K, 8), Np = round_up(Nn, 8);
+  B200_CHECK(!mn || (Kp == K && Np == Nn), B200_ERR_UNSUPPORTED, "MatMul '" << n.name << "': MN-major weights need aligned sizes");
+  auto pad_rows = [&](const LTensor& t, int64_t groups, int64_t rows, int64_t new_rows, int64_t k, int64_t new_k, const std::string& nm) {
+    // [groups][rows][k] -> [groups][new_rows][new_k], zero filled
+    Shape ps = {groups, new_rows, new_k};
+    LTensor o = alloc(ps, t.dtype, L_ROWMAJOR);
+    Step s;
+    s.name = nm; s.type = "Reorder"; s.impl = "copy2d"; s.fused = nm;
+    BufRef src = t.buf, dst = o.buf;
+    const int64_t es = dtype_size(t.dtype), total = o.bytes();
+    s.bytes = (double)t.bytes() + 2.0 * (double)total;
+    s.launch = [=](const RunCtx& c) {
+      launch_fill_zero(c.ptr(dst), total, (cudaStream_t)c.stream);
+      if (new_k == k) {   // whole groups are contiguous runs of rows * k elements
+        launch_copy2d(c.ptr(src), rows * k * es, c.ptr(dst), new_rows * new_k * es, rows * k * es, groups, (cudaStream_t)c.stream);
+      } else {
+        for (int64_t g = 0; g < groups; ++g)
+          launch_copy2d(c.ptr(src) + g * rows * k * es, k * es, c.ptr(dst) + g * new_rows * new_k * es, new_k * es, k * es, rows, (cudaStream_t)c.stream);
+      }
+    };
+    emit(std::move(s), {&t}, {&o});
+    return o;
+  };
+  if (Kp != K) a = pad_rows(a, batch_a, M, M, K, Kp, n.name + "_padA");
+  if (Kp != K || Np != Nn) b = pad_rows(b, batch_b, Nn, Np, K, Kp, n.name + "_padB");
   const int out_value = f ? f->out_value : n.outputs[0];
-  LTensor out = alloc(val(out_value).shape, cd_, L_ROWMAJOR);
+  LTensor out_dense = alloc(val(out_value).shape, cd_, L_ROWMAJOR);
+  LTensor out = out_dense;
+  if (Np != Nn) {
+    B200_CHECK(!(f && (f->res_value >= 0 || f->heads_s)), B200_ERR_UNSUPPORTED, "MatMul '" << n.name << "': fused residual / head merge with N % 8 != 0");
+    Shape ps = {batch_a, M, Np};
+    out = alloc(ps, cd_, L_ROWMAJOR);
+  }
   const bool tc = use_tc_;
-  const int bn = tc ? conv_tc_pick_bn((int)Nn) : 64;
-  std::vector<float> bias(round_up(Nn, bn), 0.f);
+  const int bn = tc ? conv_tc_pick_bn((int)Np) : 64;
+  std::vector<float> bias(round_up(Np, bn), 0.f);
   BufRef bref = add_f32_vector(bias);
   ConvParams p;
-  p.N = (int)M; p.H = p.W = p.Ho = p.Wo = 1; p.Cin_p = (int)K; p.Cout_p = (int)Nn;
-  p.M = (int)M; p.Ktot = (int)round_up(K, 64); p.Cout_alloc = (int)round_up(Nn, bn); p.ldy = (int)Nn;
-  p.w_ld = (int)K; p.w_rows = (int)Nn; p.w_k = (int)K;
-  p.batch = (int)batch_a; p.x_bs = M * K; p.w_bs = batch_b == 1 ? 0 : Nn * K; p.y_bs = M * Nn;
+  p.N = (int)M; p.H = p.W = p.Ho = p.Wo = 1; p.Cin_p = (int)Kp; p.Cout_p = (int)Np;
+  p.M = (int)M; p.Ktot = (int)round_up(Kp, 64); p.Cout_alloc = (int)round_up(Np, bn); p.ldy = (int)Np;
+  p.w_ld = (int)Kp; p.w_rows = (int)Np; p.w_k = (int)Kp;
+  p.batch = (int)batch_a; p.x_bs = M * Kp; p.w_bs = batch_b == 1 ? 0 : Np * Kp; p.y_bs = M * Np;
   p.w_dynamic = 1;
   {
     // per-batch [M][K] x [N][K]^T with tile-aligned M: the batches are one flat [batch*M][K] activation matrix whose 128-row tiles each
@@ -1444,7 +1477,16 @@ void Lowerer::lower_matmul_general(const Node& n, const FusedConv* f) {
                    flops, bytes, tc);
   // conv_launch_step only records one extra read; make sure b stays alive too
   net_.steps.back().reads.push_back(b.buf.box);
-  set(out_value, out);
+  if (Np != Nn) {
+    Step s;
+    s.name = val(out_value).name + "_compact"; s.type = "Reorder"; s.impl = "copy2d"; s.fused = s.name;
+    BufRef src = out.buf, dst = out_dense.buf;
+    const int64_t es = dtype_size(cd_), rows = batch_a * M;
+    s.bytes = (double)out.bytes() + (double)out_dense.bytes();
+    s.launch = [=](const RunCtx& c) { launch_copy2d(c.ptr(src), Np * es, c.ptr(dst), Nn * es, Nn * es, rows, (cudaStream_t)c.stream); };
+    emit(std::move(s), {&out}, {&out_dense});
+  }
+  set(out_value, out_dense);
 }
 
 void Lowerer::lower_binary(const Node& n, const ActSpec& act, int out_value) {
@@ -1677,25 +1719,35 @@ void Lowerer::lower_reduce(const Node& n) {
     set(n.outputs[0], d);
     return;
   }
-  // contiguous block of axes over a dense tensor
-  for (size_t k = 1; k < axes.size(); ++k) B200_CHECK(axes[k] == axes[k - 1] + 1, B200_ERR_UNSUPPORTED, "Reduce '" << n.name << "': non-contiguous axes");
+  // contiguous runs of axes over a dense tensor, the last run first (axes {1, 3} of NCHW: W, then C): one strided reduction per run;
+  // sum / max / mean compose across runs (every group of a mean has the same size)
   B200_CHECK(!axes.empty(), B200_ERR_INVALID, "Reduce without axes");
-  LTensor x = get(n.inputs[0], L_ROWMAJOR);
-  int64_t outer = 1, ax = 1, inner = 1;
-  for (int d = 0; d < (int)xs.size(); ++d) {
-    if (d < axes.front()) outer *= xs[d];
-    else if (d <= axes.back()) ax *= xs[d];
-    else inner *= xs[d];
+  std::vector<std::pair<int, int>> runs;
+  for (int a : axes) {
+    if (!runs.empty() && runs.back().second + 1 == a) runs.back().second = a;
+    else runs.emplace_back(a, a);
   }
-  LTensor out = alloc(os, x.dtype, L_ROWMAJOR);
-  BufRef xr = x.buf, yr = out.buf;
-  int dt = x.dtype;
-  Step s;
-  s.name = n.name; s.type = "Reduce"; s.impl = "reduce_strided"; s.fused = n.name;
-  s.bytes = (double)x.bytes() + (double)out.bytes();
-  s.launch = [=](const RunCtx& c) { launch_reduce(c.ptr(xr), c.ptr(yr), outer, ax, inner, dt, kind, (cudaStream_t)c.stream); };
-  emit(std::move(s), {&x}, {&out});
-  set(n.outputs[0], out);
+  LTensor cur = get(n.inputs[0], L_ROWMAJOR);
+  Shape cs = xs;
+  for (int r = (int)runs.size() - 1; r >= 0; --r) {
+    int64_t outer = 1, ax = 1, inner = 1;
+    for (int d = 0; d < (int)cs.size(); ++d) {
+      if (d < runs[r].first) outer *= cs[d];
+      else if (d <= runs[r].second) ax *= cs[d];
+      else inner *= cs[d];
+    }
+    for (int d = runs[r].first; d <= runs[r].second; ++d) cs[d] = 1;
+    LTensor out = alloc(r == 0 ? os : cs, cur.dtype, L_ROWMAJOR);
+    BufRef xr = cur.buf, yr = out.buf;
+    int dt = cur.dtype;
+    Step s;
+    s.name = r == 0 ? n.name : n.name + "_run" + std::to_string(r); s.type = "Reduce"; s.impl = "reduce_strided"; s.fused = n.name;
+    s.bytes = (double)cur.bytes() + (double)out.bytes();
+    s.launch = [=](const RunCtx& c) { launch_reduce(c.ptr(xr), c.ptr(yr), outer, ax, inner, dt, kind, (cudaStream_t)c.stream); };
+    emit(std::move(s), {&cur}, {&out});
+    cur = out;
+  }
+  set(n.outputs[0], cur);
 }
 
 void Lowerer::lower_mvn(const Node& n, const FusedMvn* f) {

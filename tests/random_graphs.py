@@ -168,3 +168,119 @@ def build(seed):
                    rng.standard_normal((1, classes)).astype(np.float32) * 0.1)
     f.result(f.softmax(logits, 1))
     return f, inputs
+
+
+# ---- second family: sequence models (the MatMul + Softmax + LayerNorm path) -------------------------------------------------------------
+def build_sequence(seed):
+    """Random encoder-style network on [B, S, H] tensors: embedding Gather, LayerNorm (MVN-6 + scale + shift), dense layers with awkward
+    sizes, multi-head attention (head split / merge by Reshape + Transpose, QK^T, scale, additive mask, Softmax, PV), GELU FFN, residuals."""
+    rng = np.random.default_rng(seed + 77777)
+    f = Function("random_seq_%d" % seed)
+    batch = int(rng.integers(1, 4))
+    seq = int(rng.choice([5, 8, 16, 24, 33, 64, 128]))
+    heads = int(rng.choice([1, 2, 4]))
+    dh = int(rng.choice([8, 16, 32, 64]))
+    hidden = heads * dh
+    vocab = int(rng.integers(20, 200))
+    ids = f.parameter((batch, seq), np.int32, name="ids")
+    inputs = {"ids": rng.integers(0, vocab, (batch, seq)).astype(np.int32)}
+
+    def vec(n, lo=-0.1, hi=0.1):
+        return rng.uniform(lo, hi, n).astype(np.float32)
+
+    def dense(x, o, i):
+        y = f.matmul(x, (rng.standard_normal((o, i)) / np.sqrt(i)).astype(np.float32), transpose_b=True)
+        return f.add(y, vec(o))
+
+    def layer_norm(x):
+        y = f.mvn(x, [len(x.shape) - 1], True, float(rng.choice([1e-12, 1e-5])), "INSIDE_SQRT")
+        return f.add(f.multiply(y, rng.uniform(0.8, 1.2, hidden).astype(np.float32)), vec(hidden))
+
+    x = f.gather((rng.standard_normal((vocab, hidden)) * 0.5).astype(np.float32), ids, 0)
+    x = layer_norm(f.add(x, f.constant((rng.standard_normal((1, seq, hidden)) * 0.1).astype(np.float32))))
+    use_mask = bool(rng.integers(2))
+    if use_mask:
+        mask = f.parameter((batch, seq), np.int32, name="mask")
+        mv = np.ones((batch, seq), np.int32)
+        for b in range(batch):
+            mv[b, int(rng.integers(seq // 2 + 1, seq + 1)):] = 0
+        inputs["mask"] = mv
+        m = f.reshape(f.multiply(f.subtract(np.float32(1.0), f.convert(mask, np.float32)), np.float32(-10000.0)), (batch, 1, 1, seq))
+    for _ in range(int(rng.integers(1, 3))):
+        def split_heads(t):
+            return f.transpose(f.reshape(t, (batch, seq, heads, dh)), (0, 2, 1, 3))
+        q, k, v = split_heads(dense(x, hidden, hidden)), split_heads(dense(x, hidden, hidden)), split_heads(dense(x, hidden, hidden))
+        s = f.multiply(f.matmul(q, k, transpose_b=True), np.float32(1.0 / np.sqrt(dh)))
+        if use_mask:
+            s = f.add(s, m)
+        c = f.matmul(f.softmax(s, 3), v)
+        c = f.reshape(f.transpose(c, (0, 2, 1, 3)), (batch, seq, hidden))
+        x = layer_norm(f.add(dense(c, hidden, hidden), x))
+        ffn = int(rng.choice([hidden, 2 * hidden, 4 * hidden, 3 * hidden + 8]))
+        act = rng.integers(3)
+        h = dense(x, ffn, hidden)
+        h = f.gelu(h, "ERF") if act == 0 else (f.gelu(h, "TANH") if act == 1 else f.relu(h))
+        x = layer_norm(f.add(dense(h, hidden, ffn), x))
+    f.result(dense(x, int(rng.choice([2, 8, 11])), hidden))
+    return f, inputs
+
+
+# ---- third family: element-wise / data-movement / selection ops around a small feature map ---------------------------------------------------
+def build_misc(seed):
+    rng = np.random.default_rng(seed + 424242)
+    f = Function("random_misc_%d" % seed)
+    n, c, h, w = int(rng.integers(1, 4)), int(rng.choice([2, 4, 6, 8, 12, 16, 20])), int(rng.integers(3, 12)), int(rng.integers(3, 12))
+    x = f.parameter((n, c, h, w))
+    inputs = {"Parameter_0": rng.standard_normal((n, c, h, w)).astype(np.float32)}
+    y = x
+    shape = [n, c, h, w]
+    for _ in range(int(rng.integers(2, 6))):
+        op = int(rng.integers(11))
+        if op == 0:       # binary op with a broadcast constant of a random broadcastable shape
+            bshape = [d if rng.integers(2) else 1 for d in shape]
+            cst = rng.uniform(0.5, 1.5, bshape).astype(np.float32)
+            kind = ["add", "subtract", "multiply", "divide", "maximum", "minimum", "squared_difference"][rng.integers(7)]
+            y = getattr(f, kind)(y, cst) if rng.integers(2) else getattr(f, kind)(f.constant(cst), y)
+        elif op == 1:
+            y = _act(f, rng, y)
+        elif op == 2 and len(shape) == 4:     # per-channel PReLU with the 1-D slope Model Optimizer emits
+            y = f.prelu(y, rng.uniform(0.05, 0.3, shape[1]).astype(np.float32))
+        elif op == 3:
+            perm = list(rng.permutation(len(shape)))
+            y = f.transpose(y, perm)
+            shape = [shape[p] for p in perm]
+        elif op == 4:
+            axis = int(rng.integers(len(shape)))
+            parts = [k for k in (2, 3, 4) if shape[axis] % k == 0]
+            if parts:
+                outs = f.split(y, axis, int(rng.choice(parts)))
+                y = f.concat(list(outs[::-1]), axis)
+        elif op == 5 and len(shape) > 2:
+            axes = sorted(set(int(a) for a in rng.integers(1, len(shape), int(rng.integers(1, 3)))))
+            keep = bool(rng.integers(2))
+            y = [f.reduce_mean, f.reduce_sum, f.reduce_max][rng.integers(3)](y, axes, keep_dims=keep)
+            shape = [1 if k in axes else d for k, d in enumerate(shape)] if keep else [d for k, d in enumerate(shape) if k not in axes]
+        elif op == 6:
+            total = int(np.prod(shape))
+            cands = [s for s in ([shape[0], total // shape[0]], [total], [shape[0], -1, shape[-1]]) if total % max(abs(int(np.prod(s))), 1) == 0]
+            tgt = cands[rng.integers(len(cands))]
+            y = f.reshape(y, tgt)
+            shape = list(y.shape)
+        elif op == 7:
+            y = f.softmax(y, int(rng.integers(len(shape))))
+        elif op == 8 and len(shape) >= 2:
+            axes = [len(shape) - 1] if rng.integers(2) else list(range(max(1, len(shape) - 2), len(shape)))
+            y = f.mvn(y, axes, bool(rng.integers(2)), 1e-6, "INSIDE_SQRT" if rng.integers(2) else "OUTSIDE_SQRT")
+        elif op == 9:
+            y = f.power(f.add(f.abs(y), np.float32(0.5)), np.float32(rng.choice([0.5, 2.0, 3.0, -1.0])))
+        elif op == 10:
+            y = f.concat([y, f.relu(y)], int(rng.integers(len(shape))))
+            shape = list(y.shape)
+        shape = list(y.shape)
+    f.result(y)
+    if shape and shape[-1] >= 2 and rng.integers(2):
+        k = int(rng.integers(1, min(shape[-1], 5) + 1))
+        vals, idx = f.topk(y, k, len(shape) - 1, mode="max" if rng.integers(2) else "min", sort="value")
+        f.result(vals)
+        f.result(idx)
+    return f, inputs

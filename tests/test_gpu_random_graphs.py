@@ -11,17 +11,41 @@ pytestmark = pytest.mark.gpu
 TOL = {"FP32": 1e-4, "BF16": 3e-2, "FP16": 1e-2}
 
 
-@pytest.mark.parametrize("seed", list(range(80)) + list(range(1000, 1080)))
-def test_random_graph_matches_oracle(seed):
-    f, inputs = random_graphs.build(seed)
+def _check(f, inputs, precisions, tag, tol=TOL, indices_exact=("FP32",)):
     ref = run_oracle(f, inputs)
-    for precision in ("FP32", "BF16", "FP16") if seed % 3 == 0 else ("FP32", "BF16"):
+    for precision in precisions:
         got, _ = run_b200(f, inputs, precision)
         assert set(got) == set(ref)
         for k in ref:
             assert got[k].shape == ref[k].shape
+            if ref[k].dtype.kind in "iu":
+                if precision in indices_exact:
+                    np.testing.assert_array_equal(got[k], ref[k], err_msg="%s %s %s" % (tag, precision, k))
+                continue
             err = rel_l2(got[k], ref[k])
-            assert err <= TOL[precision], "seed %d %s %s: rel-L2 %.3e" % (seed, precision, k, err)
+            assert err <= tol[precision], "%s %s %s: rel-L2 %.3e" % (tag, precision, k, err)
+
+
+@pytest.mark.parametrize("seed", list(range(80)) + list(range(1000, 1080)))
+def test_random_graph_matches_oracle(seed):
+    f, inputs = random_graphs.build(seed)
+    _check(f, inputs, ("FP32", "BF16", "FP16") if seed % 3 == 0 else ("FP32", "BF16"), "conv seed %d" % seed)
+
+
+@pytest.mark.parametrize("seed", range(80))
+def test_random_sequence_model_matches_oracle(seed):
+    """Encoder-style networks (Gather, LayerNorm, dense layers, multi-head attention with sequence lengths / head sizes that are not tile
+    multiples, GELU FFN): the MatMul + Softmax + LayerNorm path, including the fused-attention fold where the shapes allow it."""
+    f, inputs = random_graphs.build_sequence(seed)
+    _check(f, inputs, ("FP32", "BF16", "FP16") if seed % 3 == 0 else ("FP32", "BF16"), "sequence seed %d" % seed)
+
+
+@pytest.mark.parametrize("seed", range(120))
+def test_random_elementwise_and_data_movement_matches_oracle(seed):
+    """Broadcast binaries, activations, PReLU, transposes, split / concat, reductions over arbitrary axes, reshapes, softmax / MVN over any
+    axis, TopK (indices bit-exact in fp32 mode)."""
+    f, inputs = random_graphs.build_misc(seed)
+    _check(f, inputs, ("FP32", "BF16"), "misc seed %d" % seed, tol={"FP32": 1e-4, "BF16": 5e-2})
 
 
 @pytest.mark.parametrize("seed", list(range(0, 60, 3)) + list(range(1000, 1030, 3)))

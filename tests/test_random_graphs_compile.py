@@ -21,17 +21,30 @@ def test_random_graph_lowers_in_every_precision(seed):
         assert np.isfinite(v).all()
 
 
-@pytest.mark.parametrize("seed", list(range(1, 40, 4)) + list(range(1001, 1020, 4)))
-def test_oracle_matches_the_reference_cpu_plugin_on_random_graphs(seed):
+@pytest.mark.parametrize("family", ["build_sequence", "build_misc"])
+@pytest.mark.parametrize("seed", range(0, 120, 3))
+def test_random_sequence_and_misc_graphs_lower_in_every_precision(seed, family):
+    f, inputs = getattr(random_graphs, family)(seed)
+    for precision in ("FP32", "BF16", "FP16"):
+        net = Core().load_network(f, "B200", {"B200_INFERENCE_PRECISION": precision}, dry=True)
+        assert len(net.get_exec_graph_info()) > 0
+
+
+@pytest.mark.parametrize("family,seed", [("build", s) for s in list(range(1, 40, 4)) + list(range(1001, 1020, 4))] +
+                         [("build_sequence", s) for s in range(0, 30, 3)] + [("build_misc", s) for s in range(0, 60, 3)])
+def test_oracle_matches_the_reference_cpu_plugin_on_random_graphs(seed, family):
     """Pins the numpy restatement on graphs nobody wrote by hand: the same random networks on the UNMODIFIED MKLDNNPlugin (oracle/_ref,
     fp32) - beyond the fixed golden cases of tests/test_oracle_golden.py."""
     from tools import refrun
     if not refrun.available():
         pytest.skip("oracle/_ref not built")
-    f, inputs = random_graphs.build(seed)
+    f, inputs = getattr(random_graphs, family)(seed)
     mine = run_oracle(f, inputs)
     ref, _ = refrun.run(f, inputs, device="CPU")
     assert set(mine) == set(ref)
     for k, v in ref.items():
+        if v.dtype.kind in "iu":
+            np.testing.assert_array_equal(mine[k], v)
+            continue
         err = float(np.linalg.norm(mine[k].astype(np.float64) - v) / max(np.linalg.norm(v), 1e-30))
         assert err <= 1e-5, "seed %d %s: %.3e" % (seed, k, err)
