@@ -284,3 +284,58 @@ def build_misc(seed):
         f.result(vals)
         f.result(idx)
     return f, inputs
+
+
+# ---- fourth family: selection ops with bit-exact outputs (NonMaxSuppression-5, DetectionOutput) ----------------------------------------------
+def _rand_boxes(rng, b, n, center):
+    xy = rng.uniform(0, 0.8, (b, n, 2))
+    wh = rng.uniform(0.05, 0.4, (b, n, 2))
+    return (np.concatenate([xy + wh / 2, wh], axis=2) if center else np.concatenate([xy, xy + wh], axis=2)).astype(np.float32)
+
+
+def build_nms(seed):
+    rng = np.random.default_rng(seed + 9091)
+    f = Function("random_nms_%d" % seed)
+    b, c, n = int(rng.integers(1, 4)), int(rng.integers(1, 5)), int(rng.integers(4, 150))
+    center = bool(rng.integers(2))
+    boxes = f.parameter((b, n, 4), name="boxes")
+    scores = f.parameter((b, c, n), name="scores")
+    soft = float(rng.choice([0.0, 0.0, 0.25, 0.5, 1.5]))
+    i, s, v = f.non_max_suppression(boxes, scores, int(rng.choice([1, 2, 3, 10, 200])), float(rng.choice([0.0, 0.3, 0.5, 0.7, 1.0])),
+                                    float(rng.choice([0.0, 0.1, 0.4, 0.95])), soft, "center" if center else "corner", bool(rng.integers(2)), name="nms")
+    f.result(i)
+    f.result(s)
+    f.result(v)
+    sc = rng.uniform(0, 1, (b, c, n))
+    if rng.integers(2):
+        sc = np.round(sc * 8) / 8          # score ties: the index order decides
+    bx = _rand_boxes(rng, b, n, center)
+    if rng.integers(3) == 0:
+        bx[:, n // 2:] = bx[:, : n - n // 2]   # duplicate boxes: IoU exactly 1
+    return f, {"boxes": bx, "scores": sc.astype(np.float32)}
+
+
+def build_detection_output(seed):
+    rng = np.random.default_rng(seed + 5150)
+    f = Function("random_detout_%d" % seed)
+    n, priors, classes = int(rng.integers(1, 4)), int(rng.integers(8, 200)), int(rng.integers(2, 8))
+    share = bool(rng.integers(2))
+    var_in_target = bool(rng.integers(2))
+    center = bool(rng.integers(2))
+    nloc = 1 if share else classes
+    loc = f.parameter((n, priors * nloc * 4), name="loc")
+    conf = f.parameter((n, priors * classes), name="conf")
+    pb = _rand_boxes(rng, 1, priors, False)[0]
+    var = np.tile(np.asarray([0.1, 0.1, 0.2, 0.2], np.float32), (priors, 1))
+    pri = pb.reshape(1, 1, -1) if var_in_target else np.stack([pb.reshape(-1), var.reshape(-1)])[None]
+    top_k = int(rng.choice([-1, 5, 20, 400]))
+    keep_top_k = int(rng.choice([-1, 1, 10, 50]))
+    det = f.detection_output(loc, conf, pri.astype(np.float32), classes, int(rng.integers(0, classes)) if rng.integers(2) else -1, top_k, keep_top_k,
+                             "caffe.PriorBoxParameter.CENTER_SIZE" if center else "caffe.PriorBoxParameter.CORNER", share,
+                             float(rng.choice([0.3, 0.45, 0.6])), float(rng.choice([0.01, 0.05, 0.2])), var_in_target, True,
+                             bool(rng.integers(2)), bool(rng.integers(2)), name="det")
+    f.result(det)
+    logits = rng.standard_normal((n, priors, classes)) * 2
+    p = np.exp(logits - logits.max(-1, keepdims=True))
+    p /= p.sum(-1, keepdims=True)
+    return f, {"loc": (rng.standard_normal((n, priors * nloc * 4)) * 0.5).astype(np.float32), "conf": p.reshape(n, -1).astype(np.float32)}

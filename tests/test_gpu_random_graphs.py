@@ -65,3 +65,24 @@ def test_random_graph_through_the_plugin_matches_the_reference_cpu_plugin(seed):
         assert got[k].shape == ref[k].shape
         err = rel_l2(got[k], ref[k])
         assert err <= 1e-4, "seed %d %s: rel-L2 %.3e" % (seed, k, err)
+
+
+@pytest.mark.parametrize("seed", range(120))
+def test_random_nms_is_bit_exact(seed):
+    """NonMaxSuppression-5 with random geometry / thresholds / soft-NMS sigma / score ties / duplicate boxes: selected indices and the
+    valid count bit-exact, scores <= 1e-4 (fp32 mode, as the north star asks for index outputs)."""
+    f, inputs = random_graphs.build_nms(seed)
+    _check(f, inputs, ("FP32",), "nms seed %d" % seed)
+
+
+@pytest.mark.parametrize("seed", range(120))
+def test_random_detection_output_ids_are_exact(seed):
+    """DetectionOutput with random prior counts, class counts, top_k / keep_top_k, code types, shared / per-class locations, variance
+    placement, clipping: the (image, label) sequence incl. the terminator row exact, confidences and boxes <= 1e-4 (fp32 mode)."""
+    f, inputs = random_graphs.build_detection_output(seed)
+    ref = run_oracle(f, inputs)
+    got, _ = run_b200(f, inputs, "FP32")
+    (name, r), = ref.items()
+    g, r = got[name].reshape(-1, 7), r.reshape(-1, 7)
+    np.testing.assert_array_equal(g[:, :2], r[:, :2], err_msg="detout seed %d" % seed)
+    assert rel_l2(g[:, 2:], r[:, 2:]) <= 1e-4
