@@ -533,8 +533,7 @@ int b200_request_set_io_format(b200_request* req, int is_output, int index, int3
     if (req->finalized) {
       // a blob with another layout / precision arrived after the first inference (SetBlob in the reference may change both at any time,
       // ie_iinfer_request_internal.cpp:96-150): the edge-conversion kernels are part of the captured graph, so the capture is dropped and
-      // the next start() records it again with the new format.  Only an idle request may change.
-      B200_CHECK(!req->started.load(), B200_ERR_BUSY, "I/O format cannot change while the request is running");
+      // the next start() records it again with the new format.  A request that is still running is drained first.
       B200_CUDA(cudaSetDevice(req->net->device));
       B200_CUDA(cudaStreamSynchronize(req->stream));
       if (req->graph_exec) { cudaGraphExecDestroy(req->graph_exec); req->graph_exec = nullptr; }

@@ -225,9 +225,9 @@ B200_API int b200_plan_arena(int32_t n_boxes, const int64_t* bytes, const int32_
 B200_API int b200_request_create(b200_network* net, b200_request** out);
 B200_API void b200_request_destroy(b200_request* req);
 /* Host-side blob format of input/output `index` (default: inputs = graph dtype with i64->i32,
- * f16/bf16->f32; outputs f32 / i32; layout NCHW).  Normally called before the first start(); on an idle
- * request it may be called again later (a blob with another layout arrived): the captured graph is
- * dropped and recorded again by the next start().  B200_ERR_BUSY while the request is running. */
+ * f16/bf16->f32; outputs f32 / i32; layout NCHW).  Normally called before the first start(); it may be
+ * called again later (a blob with another layout arrived): the request is drained, the captured graph
+ * is dropped and the next start() records it again. */
 B200_API int b200_request_set_io_format(b200_request* req, int is_output, int index, int32_t dtype, int32_t layout);
 B200_API int b200_request_io_bytes(const b200_request* req, int is_output, int index, uint64_t* bytes);
 /* Enqueue H2D of every input from host_inputs[i], the captured CUDA graph, and D2H of every output

@@ -86,3 +86,40 @@ def test_random_detection_output_ids_are_exact(seed):
     g, r = got[name].reshape(-1, 7), r.reshape(-1, 7)
     np.testing.assert_array_equal(g[:, :2], r[:, :2], err_msg="detout seed %d" % seed)
     assert rel_l2(g[:, 2:], r[:, 2:]) <= 1e-4
+
+
+@pytest.mark.parametrize("seed", list(range(0, 60, 2)) + list(range(1000, 1030, 2)))
+@pytest.mark.parametrize("blob", ["U8", "FP16", "BF16"])
+def test_random_graph_edge_conversions(seed, blob):
+    """User-side blob precisions and layouts converted at the edge (mkldnn_infer_request.cpp:76-127): the same random networks fed U8 / FP16 /
+    BF16 blobs, NCHW or NHWC, changing the layout again AFTER the first inference (the I/O format of an idle request may change)."""
+    from dldt_b200 import Core
+    f, inputs = random_graphs.build(seed)
+    name, x = next(iter(inputs.items()))
+    if blob == "U8":
+        x = np.clip(np.round(x * 40 + 128), 0, 255).astype(np.uint8)
+        xf = x.astype(np.float32)
+    elif blob == "FP16":
+        x = x.astype(np.float16)
+        xf = x.astype(np.float32)
+    else:      # bf16 blobs travel as their 16-bit patterns
+        bits = (x.view(np.uint32) + 0x7FFF + ((x.view(np.uint32) >> 16) & 1)) >> 16
+        xf = (bits.astype(np.uint32) << 16).view(np.float32)
+        x = bits.astype(np.uint16)
+    ref = run_oracle(f, {name: xf})
+    net = Core().load_network(f, "B200", {"B200_INFERENCE_PRECISION": "FP32"})
+    from dldt_b200 import _capi as capi
+    first = "NCHW" if seed % 4 else "NHWC"
+    req = net.create_infer_request(input_precisions={name: blob}, input_layouts={name: first})
+    nhwc = np.ascontiguousarray(x.transpose(0, 2, 3, 1))
+    got = req.infer({name: x if first == "NCHW" else nhwc})
+    for k in ref:
+        assert rel_l2(got[k], ref[k]) <= 1e-4, "seed %d %s %s %s" % (seed, blob, first, k)
+    # the same (idle) request, the other layout: the captured graph is dropped and recorded again
+    second = "NHWC" if first == "NCHW" else "NCHW"
+    capi.check(capi.lib.b200_request_set_io_format(req._h, 0, 0, {"U8": capi.U8, "FP16": capi.F16, "BF16": capi.BF16}[blob],
+                                                   capi.LAYOUT_NHWC if second == "NHWC" else capi.LAYOUT_NCHW))
+    req.input_blobs[name].reshape(-1)[:] = (nhwc if second == "NHWC" else x).reshape(-1)
+    got = req.infer()
+    for k in ref:
+        assert rel_l2(got[k], ref[k]) <= 1e-4, "seed %d %s %s after %s: %s" % (seed, blob, second, first, k)
