@@ -201,3 +201,20 @@ def test_convolutions_over_1_and_3_spatial_dims_are_rewritten_to_2d(tmp_path, x_
     p = ie_run(xml, "--dry", "--config", "B200_DRY_COMPILE=YES")
     assert p.returncode == 0, p.stderr
     assert json.loads(p.stdout)["exec_convolutions"] == 1
+
+
+@pytest.mark.parametrize("family,seed", [("build", s) for s in (0, 7, 19, 43, 1003, 1012, 1040)] + [("build_sequence", s) for s in (2, 8, 19, 31)] +
+                         [("build_misc", s) for s in (5, 37, 61, 90)] + [("build_nms", 3), ("build_detection_output", 4)])
+def test_random_graphs_load_through_the_plugin(tmp_path, family, seed):
+    """The seeded random networks of tests/random_graphs.py as IR v10 through Core::ReadNetwork + LoadNetwork("B200") (nGraph passes,
+    lowering, compile, plan) on a machine without a GPU: every layer supported, the network compiles in fp32 and bf16."""
+    from tests import random_graphs
+    f, _ = getattr(random_graphs, family)(seed)
+    xml = str(tmp_path / "random.xml")
+    ir.serialize(f, xml)
+    q = ie_run(xml, "--query")
+    assert q.returncode == 0, q.stderr
+    assert json.loads(q.stdout)["supported_layers"] == json.loads(q.stdout)["total_layers"]
+    for precision in ("FP32", "BF16"):
+        p = ie_run(xml, "--dry", "--config", "B200_DRY_COMPILE=YES,B200_INFERENCE_PRECISION=" + precision)
+        assert p.returncode == 0, p.stderr
