@@ -48,7 +48,7 @@ def test_random_elementwise_and_data_movement_matches_oracle(seed):
     _check(f, inputs, ("FP32", "BF16"), "misc seed %d" % seed, tol={"FP32": 1e-4, "BF16": 5e-2})
 
 
-@pytest.mark.parametrize("seed", list(range(0, 60, 3)) + list(range(1000, 1030, 3)))
+@pytest.mark.parametrize("seed", list(range(0, 60, 6)) + list(range(1000, 1030, 6)))
 def test_random_graph_through_the_plugin_matches_the_reference_cpu_plugin(seed):
     """Same networks as IR v10 through the reference Core: device B200 (libb200Plugin.so: nGraph passes + lowering + C ABI) against device
     CPU (the UNMODIFIED MKLDNNPlugin, fp32) - the differential test with the real reference on both sides of the drop-in boundary."""
