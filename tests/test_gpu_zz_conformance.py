@@ -7,7 +7,9 @@ convolution / reshape / softmax / split single-layer instances and 684 synthetic
 libb200Plugin.so under the library / device name the binary asks for, so every test lands in the B200 plugin.
 
 Every test must pass except the three classes below, which cannot apply to this plugin; they are matched by NAME so that a new failure
-anywhere else fails this test.  (File name: last in the collection order, a 3-minute run.)"""
+anywhere else fails this test.  The `nightly_*` instances (597 HETERO splits drawn from std::random_device at start-up, 16 more NCDHW
+convolutions) are left to tools/run_conformance.sh (profiles/r2_conformance_run4_fp32.txt: all pass): a test suite should not depend on
+a random draw.  (File name: last in the collection order.)"""
 import os
 import re
 import subprocess
@@ -37,7 +39,7 @@ NOT_APPLICABLE = [
 def test_reference_conformance_binary(tmp_path):
     prefix = str(tmp_path / "conformance")
     env = dict(os.environ, CONFORMANCE_TIMEOUT="600")
-    p = subprocess.run([os.path.join(ROOT, "tools", "run_conformance.sh"), "*", prefix], env=env, capture_output=True, text=True, timeout=900)
+    p = subprocess.run([os.path.join(ROOT, "tools", "run_conformance.sh"), "*-nightly_*", prefix], env=env, capture_output=True, text=True, timeout=900)
     assert os.path.exists(prefix + ".xml"), "no gtest report: the binary died or timed out\n" + p.stdout[-3000:] + p.stderr[-2000:]
     passed, failed, na = 0, [], {}
     for case in ET.parse(prefix + ".xml").getroot().iter("testcase"):
@@ -59,4 +61,4 @@ def test_reference_conformance_binary(tmp_path):
         with open(os.path.join(out, "conformance_pytest.txt"), "w") as f:
             f.write("passed %d\nnot applicable %d %s\nfailed %d\n%s\n" % (passed, sum(na.values()), na, len(failed), "\n".join(failed)))
     assert not failed, "%d conformance failures:\n%s" % (len(failed), "\n".join(failed[:40]))
-    assert passed >= 1400, "only %d conformance tests passed" % passed
+    assert passed >= 800, "only %d conformance tests passed" % passed
