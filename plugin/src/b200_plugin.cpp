@@ -774,8 +774,11 @@ void InferRequest::SetBlob(const std::string& name, const Blob::Ptr& data) {
 void InferRequest::syncFormat(bool output, size_t index, const Blob::Ptr& blob) {
     const std::string& name = output ? _outputNames[index] : _inputNames[index];
     const TensorDesc& desc = blob->getTensorDesc();
-    const std::pair<int, int> want{BlobDtype(desc.getPrecision(), name), BlobLayout(desc, name)};
     auto& have = output ? _outFormat[index] : _inFormat[index];
+    // a 4-D descriptor that names neither NCHW nor NHWC (Layout::ANY, a BLOCKED descriptor with default strides) keeps the layout the
+    // request is recorded for, as before; only an explicit NCHW <-> NHWC difference re-records
+    const bool named = desc.getDims().size() != 4 || desc.getLayout() == Layout::NCHW || desc.getLayout() == Layout::NHWC;
+    const std::pair<int, int> want{BlobDtype(desc.getPrecision(), name), named ? BlobLayout(desc, name) : have.second};
     if (want == have || (want.first == have.first && want.second == B200_LAYOUT_ANY)) return;
     for (auto* r : _reqs) B200_CALL(b200_request_set_io_format(r, output ? 1 : 0, static_cast<int>(index), want.first, want.second), "blob format");
     B200_CALL(b200_request_io_bytes(_reqs[0], output ? 1 : 0, static_cast<int>(index), output ? &_outShardBytes[index] : &_inShardBytes[index]), "io size");
