@@ -23,7 +23,7 @@ OPS = ["Parameter", "Constant", "Result", "Convolution", "GroupConvolution", "Ba
        "Multiply", "Divide", "Maximum", "Minimum", "Relu", "Sigmoid", "Tanh", "Clamp", "Swish", "Gelu", "HSwish",
        "HSigmoid", "Mish", "Exp", "Sqrt", "Abs", "Negative", "Erf", "Elu", "MaxPool", "AvgPool", "ReduceMean", "MatMul",
        "Softmax", "MVN", "Reshape", "Transpose", "Concat", "Split", "Gather", "TopK", "NonMaxSuppression",
-       "DetectionOutput", "Convert", "Power", "PRelu", "ReduceSum", "ReduceMax", "SquaredDifference", "Round", "FakeQuantize"]
+       "DetectionOutput", "Convert", "Power", "PRelu", "ReduceSum", "ReduceMax", "SquaredDifference", "Round", "FakeQuantize", "StridedSlice"]
 OP_ID = {n: i for i, n in enumerate(OPS)}
 
 

@@ -221,6 +221,7 @@ class Lowerer {
   void lower_concat(const Node& n);
   void lower_split(const Node& n);
   void lower_transpose(const Node& n);
+  void lower_strided_slice(const Node& n);
   void lower_detection(const Node& n);
   void conv_launch_step(const std::string& name, const std::string& type, const std::string& fused, ConvParams p, BufRef x, BufRef w,
                         BufRef bias, BufRef res, BufRef y, const LTensor* tx, const LTensor* tres, const LTensor* ty, double flops,
@@ -1846,6 +1847,38 @@ void Lowerer::lower_split(const Node& n) {
   }
 }
 
+// StridedSlice (mkldnn_strided_slice_node.cpp; ngraph reference/strided_slice.hpp via slice_plan): a strided gather of a dense tensor -
+// the permute kernel with the source pointer moved to the first element and per-dimension source strides (negative = reversed)
+void Lowerer::lower_strided_slice(const Node& n) {
+  const Shape os = val(n.outputs[0]).shape;
+  const int r = n.i[0];
+  LTensor x = get(n.inputs[0], L_ROWMAJOR);
+  std::vector<int64_t> xstr(r);
+  int64_t st = 1;
+  for (int d = r - 1; d >= 0; --d) { xstr[d] = st; st *= n.i[1 + d]; }
+  int64_t first = 0;
+  bool whole = true;
+  for (int d = 0; d < r; ++d) {
+    first += (int64_t)n.i[1 + r + d] * xstr[d];
+    whole = whole && n.i[1 + r + d] == 0 && n.i[1 + 2 * r + d] == 1 && n.i[1 + 3 * r + d] == n.i[1 + d];
+  }
+  if (whole) { LTensor v = x; v.shape = os; set(n.outputs[0], v); return; }
+  LTensor out = alloc(os, x.dtype, L_ROWMAJOR);
+  PermuteParams pp{};
+  pp.rank = r;
+  pp.n = numel(os);
+  for (int d = 0; d < r; ++d) { pp.oshape[d] = n.i[1 + 3 * r + d]; pp.istride[d] = (int64_t)n.i[1 + 2 * r + d] * xstr[d]; }
+  BufRef xr = x.buf, yr = out.buf;
+  const int es = (int)dtype_size(x.dtype);
+  const int64_t off = first * es;
+  Step s;
+  s.name = n.name; s.type = "StridedSlice"; s.impl = "permute"; s.fused = n.name;
+  s.bytes = 2.0 * (double)out.bytes();
+  s.launch = [=](const RunCtx& c) { PermuteParams q = pp; q.x = c.ptr(xr) + off; q.y = c.ptr(yr); launch_permute(q, es, (cudaStream_t)c.stream); };
+  emit(std::move(s), {&x}, {&out});
+  set(n.outputs[0], out);
+}
+
 void Lowerer::lower_transpose(const Node& n) {
   const Shape& xs = val(n.inputs[0]).shape;
   const Shape os = val(n.outputs[0]).shape;
@@ -2086,6 +2119,7 @@ void Lowerer::lower_node(const Node& n) {
       break;
     }
     case B200_OP_TRANSPOSE: lower_transpose(n); break;
+    case B200_OP_STRIDED_SLICE: lower_strided_slice(n); break;
     case B200_OP_CONCAT: lower_concat(n); break;
     case B200_OP_SPLIT: lower_split(n); break;
     case B200_OP_GATHER: {

@@ -19,7 +19,7 @@ const char* op_name(int op) {
       "Gelu", "HSwish", "HSigmoid", "Mish", "Exp", "Sqrt", "Abs", "Negative", "Erf", "Elu", "MaxPool",
       "AvgPool", "ReduceMean", "MatMul", "Softmax", "MVN", "Reshape", "Transpose", "Concat", "Split",
       "Gather", "TopK", "NonMaxSuppression", "DetectionOutput", "Convert", "Power", "PRelu", "ReduceSum",
-      "ReduceMax", "SquaredDifference", "Round", "FakeQuantize"};
+      "ReduceMax", "SquaredDifference", "Round", "FakeQuantize", "StridedSlice"};
   if (op < 0 || op >= B200_OP__COUNT) return "?";
   return names[op];
 }
@@ -248,6 +248,24 @@ void infer_node(const b200_graph& g, const Node& n, std::vector<Shape>& os, std:
       B200_CHECK(n.inputs.size() >= 1, B200_ERR_INVALID, "Reshape without input");
       B200_CHECK(numel(n.shape) == numel(in(0).shape), B200_ERR_INVALID,
                  "Reshape '" << n.name << "': " << shape_str(in(0).shape) << " -> " << shape_str(n.shape));
+      os.push_back(n.shape);
+      od.push_back(in(0).dtype);
+      break;
+    }
+    case B200_OP_STRIDED_SLICE: {
+      B200_CHECK(n.inputs.size() >= 1, B200_ERR_INVALID, "StridedSlice without input");
+      const int r = n.i[0];
+      B200_CHECK(r >= 1 && r <= B200_MAX_RANK && 1 + 4 * r <= B200_MAX_IATTR, B200_ERR_INVALID, "StridedSlice '" << n.name << "': bad rank " << r);
+      int64_t vin = 1, vout = 1;
+      for (int d = 0; d < r; ++d) {
+        const int64_t v = n.i[1 + d], b = n.i[1 + r + d], st = n.i[1 + 2 * r + d], cnt = n.i[1 + 3 * r + d];
+        B200_CHECK(v >= 1 && cnt >= 1 && st != 0, B200_ERR_INVALID, "StridedSlice '" << n.name << "': empty dimension or zero stride");
+        const int64_t last = b + (cnt - 1) * st;
+        B200_CHECK(b >= 0 && b < v && last >= 0 && last < v, B200_ERR_INVALID, "StridedSlice '" << n.name << "': dimension " << d << " out of range");
+        vin *= v; vout *= cnt;
+      }
+      B200_CHECK(vin == numel(in(0).shape) && vout == numel(n.shape), B200_ERR_INVALID,
+                 "StridedSlice '" << n.name << "': " << shape_str(in(0).shape) << " -> " << shape_str(n.shape) << " does not match the slice plan");
       os.push_back(n.shape);
       od.push_back(in(0).dtype);
       break;

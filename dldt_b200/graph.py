@@ -235,6 +235,27 @@ class Function:
         order = [int(o) for o in order]
         return self._add("Transpose", [x], name, i=order, ir_consts=[np.asarray(order, np.int64)]).outputs[0]
 
+    def strided_slice(self, x, begin, end, strides=None, name=None):
+        """opset1 StridedSlice with numpy semantics and no new-axis / shrink / ellipsis masks: x[b0:e0:s0, b1:e1:s1, ...].  `None` in begin /
+        end sets the corresponding bit of begin_mask / end_mask (value ignored: the real start / end in the direction of the stride)."""
+        rank = len(x.shape)
+        begin = list(begin) + [None] * (rank - len(begin))
+        end = list(end) + [None] * (rank - len(end))
+        strides = list(strides or []) + [1] * (rank - len(strides or []))
+        starts, counts = [], []
+        for d in range(rank):
+            rng = range(*slice(begin[d], end[d], strides[d]).indices(x.shape[d]))
+            if len(rng) == 0:
+                raise ValueError("strided_slice: empty result along dimension %d" % d)
+            starts.append(rng.start)
+            counts.append(len(rng))
+        i = [rank] + list(x.shape) + starts + [int(v) for v in strides] + counts
+        attrs = {"begin_mask": [1 if v is None else 0 for v in begin], "end_mask": [1 if v is None else 0 for v in end],
+                 "new_axis_mask": [0] * rank, "shrink_axis_mask": [0] * rank, "ellipsis_mask": [0] * rank}
+        consts = [np.asarray([0 if v is None else v for v in begin], np.int64), np.asarray([0 if v is None else v for v in end], np.int64),
+                  np.asarray(strides, np.int64)]
+        return self._add("StridedSlice", [x], name, i=i, shape=counts, attrs=attrs, ir_consts=consts).outputs[0]
+
     def concat(self, xs, axis, name=None):
         return self._add("Concat", list(xs), name, i=[axis], attrs={"axis": axis}).outputs[0]
 

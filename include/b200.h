@@ -116,6 +116,9 @@ typedef enum b200_op {
   B200_OP_SQUARED_DIFFERENCE = 46,
   B200_OP_ROUND = 47,        /* i={mode: 0 half to even | 1 half away from zero}  (opset5 Round; what FakeQuantize decomposes to) */
   B200_OP_FAKE_QUANTIZE = 48, /* in: x, in_low, in_high, out_low, out_high (constants: one value, or one per channel = axis 1); i={levels} */
+  B200_OP_STRIDED_SLICE = 49, /* in: x.  The input is VIEWED as shape v[r] (same element count), element (o0..or-1) of the [n0..nr-1] result is
+                               * v[begin0 + o0 * stride0, ...] (stride may be negative), and the result is viewed as desc.shape.
+                               * i={r, v[r], begin[r], stride[r], n[r]}: what ngraph::make_slice_plan reduces opset1 StridedSlice to */
   B200_OP__COUNT
 } b200_op;
 

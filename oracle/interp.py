@@ -66,6 +66,11 @@ def run(func, inputs, return_all=False):
             out = [x[0].reshape(n.outputs[0].shape)]
         elif n.op == "Transpose":
             out = [np.ascontiguousarray(np.transpose(x[0], [int(v) for v in n.ir_consts[0]]))]
+        elif n.op == "StridedSlice":
+            # x[b:e:s, ...] with the masks of opset1 StridedSlice (bit set = the value is ignored); ngraph reference/strided_slice.hpp
+            b, e, st = ([int(v) for v in c] for c in n.ir_consts)
+            sl = tuple(slice(None if a["begin_mask"][d] else b[d], None if a["end_mask"][d] else e[d], st[d]) for d in range(len(b)))
+            out = [np.ascontiguousarray(x[0][sl])]
         elif n.op == "Concat":
             out = [np.concatenate(x, axis=a["axis"])]
         elif n.op == "Split":

@@ -15,6 +15,7 @@
 #include <ngraph/pass/manager.hpp>
 #include <ngraph/pass/pass.hpp>
 #include <ngraph/rt_info.hpp>
+#include <ngraph/slice_plan.hpp>
 #include <ngraph_ops/nms_ie_internal.hpp>
 #include <transformations/common_optimizations/common_optimizations.hpp>
 #include <transformations/op_conversions/convert_nms_to_nms_ie_internal.hpp>
@@ -146,6 +147,45 @@ public:
     }
 };
 
+// VariadicSplit (axis and lengths constant, one length may be -1) as one StridedSlice per output (mkldnn_split_node.cpp covers both
+// Split and VariadicSplit; here the equal split keeps its own op and the variadic one becomes slices).  Slice k is named "<name>.<k>":
+// the output-naming rule (producer name + "." + port) then gives network outputs the names they had.
+class VariadicSplitToSlices : public ngraph::pass::FunctionPass {
+public:
+    bool run_on_function(std::shared_ptr<ngraph::Function> f) override {
+        bool changed = false;
+        for (const auto& node : f->get_ordered_ops()) {
+            auto vs = as_type_ptr<ngraph::opset1::VariadicSplit>(node);
+            if (!vs || !vs->get_input_partial_shape(0).is_static()) continue;
+            auto axis_c = as_type_ptr<ngraph::opset1::Constant>(vs->input_value(1).get_node_shared_ptr());
+            auto len_c = as_type_ptr<ngraph::opset1::Constant>(vs->input_value(2).get_node_shared_ptr());
+            if (!axis_c || !len_c) continue;
+            const ngraph::Shape xs = vs->get_input_shape(0);
+            int64_t axis = axis_c->cast_vector<int64_t>()[0];
+            if (axis < 0) axis += static_cast<int64_t>(xs.size());
+            if (axis < 0 || axis >= static_cast<int64_t>(xs.size())) continue;
+            ngraph::OutputVector outs;
+            ngraph::NodeVector made;
+            int64_t start = 0;
+            for (size_t k = 0; k < vs->get_output_size(); ++k) {
+                const int64_t len = static_cast<int64_t>(vs->get_output_shape(k)[static_cast<size_t>(axis)]);
+                std::vector<int64_t> b(xs.size(), 0), e(xs.size(), 0), mask(xs.size(), 1);
+                b[axis] = start; e[axis] = start + len; mask[axis] = 0;
+                auto sl = std::make_shared<ngraph::opset1::StridedSlice>(vs->input_value(0), ngraph::opset1::Constant::create(ngraph::element::i64, {xs.size()}, b),
+                                                                        ngraph::opset1::Constant::create(ngraph::element::i64, {xs.size()}, e), mask, mask);
+                sl->set_friendly_name(vs->get_friendly_name() + "." + std::to_string(k));
+                made.push_back(sl);
+                outs.push_back(sl->output(0));
+                start += len;
+            }
+            ngraph::copy_runtime_info(vs, made);
+            ngraph::replace_node(vs, outs);
+            changed = true;
+        }
+        return changed;
+    }
+};
+
 }  // namespace
 
 std::shared_ptr<ngraph::Function> TransformNetwork(const std::shared_ptr<const ngraph::Function>& function) {
@@ -154,6 +194,8 @@ std::shared_ptr<ngraph::Function> TransformNetwork(const std::shared_ptr<const n
     manager.register_pass<ConvolutionToTwoD>();
     manager.register_pass<GrnDecomposition>();
     manager.register_pass<ngraph::pass::CommonOptimizations>();
+    // after CommonOptimizations: its StridedSliceOptimization MERGES neighbouring slices of one tensor into a VariadicSplit
+    manager.register_pass<VariadicSplitToSlices>();
     // NMS-1/3/4 -> NMS-5 -> NonMaxSuppressionIEInternal (static, padded output shapes), as mkldnn_plugin.cpp:150-156 does
     manager.register_pass<ngraph::pass::ConvertNMS1ToNMS5>();
     manager.register_pass<ngraph::pass::ConvertNMS3ToNMS5>();
@@ -439,6 +481,48 @@ OpDesc Describe(const NodePtr& n) {
     }
     if (as_type_ptr<ngraph::opset1::Reshape>(n) || as_type_ptr<ngraph::opset1::Squeeze>(n) || as_type_ptr<ngraph::opset1::Unsqueeze>(n)) {
         d.op = B200_OP_RESHAPE; all_inputs(1); d.shape_from_output = true; return d;
+    }
+    if (auto ss = as_type_ptr<ngraph::opset1::StridedSlice>(n)) {
+        // opset1 StridedSlice -> ngraph::make_slice_plan (what the nGraph reference itself evaluates): a positive-stride slice of the input,
+        // a non-transposing reshape (new axes / shrunk axes) and a reverse of some axes (negative strides).  The C ABI op is the slice
+        // with signed strides + the free reshape; a reverse is folded into a negative stride when the reshape keeps the axes in place
+        auto begin = ConstInts(n, 1, err), end = ConstInts(n, 2, err);
+        std::vector<int64_t> stride(begin.size(), 1);
+        if (n->get_input_size() > 3) stride = ConstInts(n, 3, err);
+        if (!err.empty()) { d.reject = err; return d; }
+        if (!n->get_input_partial_shape(0).is_static() || !n->get_output_partial_shape(0).is_static()) { d.reject = "dynamic StridedSlice"; return d; }
+        auto axes = [](const std::vector<int64_t>& mask) {
+            ngraph::AxisSet set;
+            for (size_t k = 0; k < mask.size(); ++k) if (mask[k] == 1) set.emplace(k);
+            return set;
+        };
+        ngraph::SlicePlan plan;
+        try {
+            plan = ngraph::make_slice_plan(n->get_input_shape(0), begin, end, stride, axes(ss->get_begin_mask()), axes(ss->get_end_mask()),
+                                           axes(ss->get_new_axis_mask()), axes(ss->get_shrink_axis_mask()), axes(ss->get_ellipsis_mask()));
+        } catch (const std::exception& e) {
+            d.reject = std::string("StridedSlice: ") + e.what();
+            return d;
+        }
+        const ngraph::Shape in = n->get_input_shape(0);
+        const size_t r = in.size();
+        if (r < 1 || r > 8 || plan.begins.size() != r || plan.reshape_in_shape.size() != r) { d.reject = "StridedSlice: unsupported rank"; return d; }
+        if (!plan.reverse_axes.empty() && plan.reshape_in_shape != plan.reshape_out_shape) { d.reject = "StridedSlice: negative stride together with new / shrunk axes"; return d; }
+        std::vector<int64_t> b(plan.begins), st(plan.strides);
+        for (size_t k = 0; k < r; ++k) {
+            if (plan.reshape_in_shape[k] == 0) { d.reject = "StridedSlice: empty result"; return d; }
+            if (plan.reverse_axes.count(k)) {
+                b[k] = plan.begins[k] + static_cast<int64_t>(plan.reshape_in_shape[k] - 1) * plan.strides[k];
+                st[k] = -plan.strides[k];
+            }
+        }
+        d.op = B200_OP_STRIDED_SLICE; d.data_inputs = {0}; d.shape_from_output = true;
+        d.i = {static_cast<int32_t>(r)};
+        for (auto v : in) d.i.push_back(static_cast<int32_t>(v));
+        for (auto v : b) d.i.push_back(static_cast<int32_t>(v));
+        for (auto v : st) d.i.push_back(static_cast<int32_t>(v));
+        for (auto v : plan.reshape_in_shape) d.i.push_back(static_cast<int32_t>(v));
+        return d;
     }
     if (as_type_ptr<ngraph::opset1::Transpose>(n)) {
         auto order = ConstInts(n, 1, err);

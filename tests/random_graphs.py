@@ -235,8 +235,22 @@ def build_misc(seed):
     y = x
     shape = [n, c, h, w]
     for _ in range(int(rng.integers(2, 6))):
-        op = int(rng.integers(11))
-        if op == 0:       # binary op with a broadcast constant of a random broadcastable shape
+        op = int(rng.integers(12))
+        if op == 11:      # StridedSlice: random begin / end / stride per axis (negative strides, ignored bounds)
+            begin, end, strides = [], [], []
+            for dim in shape:
+                st = int(rng.choice([1, 1, 1, 2, 3, -1, -2])) if dim > 1 else 1
+                lo = int(rng.integers(0, dim))
+                hi = int(rng.integers(lo + 1, dim + 1))
+                if st > 0:
+                    begin.append(None if rng.integers(4) == 0 else lo)
+                    end.append(None if rng.integers(4) == 0 else hi)
+                else:          # backwards from hi - 1 down to lo (exclusive lo - 1: None when lo == 0)
+                    begin.append(None if rng.integers(4) == 0 else hi - 1)
+                    end.append(None if (lo == 0 or rng.integers(4) == 0) else lo - 1)
+                strides.append(st)
+            y = f.strided_slice(y, begin, end, strides)
+        elif op == 0:       # binary op with a broadcast constant of a random broadcastable shape
             bshape = [d if rng.integers(2) else 1 for d in shape]
             cst = rng.uniform(0.5, 1.5, bshape).astype(np.float32)
             kind = ["add", "subtract", "multiply", "divide", "maximum", "minimum", "squared_difference"][rng.integers(7)]

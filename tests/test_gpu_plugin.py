@@ -194,3 +194,17 @@ def test_conv_1d_3d_matches_reference_cpu_plugin(geom, precision, tol, tmp_path)
     assert got[name].shape == r.shape
     err = float(np.linalg.norm(got[name].astype(np.float64) - r) / np.linalg.norm(r))
     assert err <= tol, "rel-L2 %.3e" % err
+
+
+@needs_ref
+@pytest.mark.parametrize("shape,axis,lengths", [((2, 10, 4, 5), 1, [3, -1, 2]), ((3, 7, 6), 2, [1, 2, 3]), ((4, 9), 0, [-1, 1])])
+def test_variadic_split_matches_reference_cpu_plugin(shape, axis, lengths, tmp_path):
+    """VariadicSplit through the plugin (rewritten into StridedSlices, the strided-gather kernel) against the UNMODIFIED MKLDNNPlugin."""
+    xml = str(tmp_path / "vsplit.xml")
+    refrun.write_variadic_split_ir(xml, shape, axis, lengths)
+    x = np.random.default_rng(len(shape)).standard_normal(shape).astype(np.float32)
+    ref, _ = refrun.run(xml, {"data": x}, device="CPU")
+    got, _ = refrun.run(xml, {"data": x}, device="B200", config={"B200_INFERENCE_PRECISION": "FP32"})
+    assert set(got) == set(ref)
+    for k, r in ref.items():
+        np.testing.assert_array_equal(got[k], r)

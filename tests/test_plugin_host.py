@@ -218,3 +218,16 @@ def test_random_graphs_load_through_the_plugin(tmp_path, family, seed):
     for precision in ("FP32", "BF16"):
         p = ie_run(xml, "--dry", "--config", "B200_DRY_COMPILE=YES,B200_INFERENCE_PRECISION=" + precision)
         assert p.returncode == 0, p.stderr
+
+
+def test_variadic_split_becomes_strided_slices(tmp_path):
+    """VariadicSplit (one length -1) is rewritten into one StridedSlice per output AFTER CommonOptimizations (whose StridedSliceOptimization
+    merges neighbouring slices into a VariadicSplit): every layer supported, output names kept."""
+    from tools import refrun
+    xml = str(tmp_path / "vsplit.xml")
+    refrun.write_variadic_split_ir(xml, (2, 10, 4, 5), 1, [3, -1, 2])
+    q = ie_run(xml, "--query")
+    assert q.returncode == 0, q.stderr
+    assert json.loads(q.stdout)["supported_layers"] == json.loads(q.stdout)["total_layers"]
+    p = ie_run(xml, "--dry", "--config", "B200_DRY_COMPILE=YES")
+    assert p.returncode == 0, p.stderr

@@ -89,3 +89,40 @@ def write_conv_nd_ir(xml_path, x_shape, weights, strides, pads_begin, pads_end, 
         f.write('<?xml version="1.0"?>\n<net name="conv_nd" version="10"><layers>%s</layers><edges>%s</edges></net>\n' % ("".join(layers), "".join(edges)))
     w.tofile(xml_path[:-4] + ".bin")
     return out
+
+
+def write_variadic_split_ir(xml_path, x_shape, axis, lengths):
+    """IR v10 of Parameter -> VariadicSplit(axis, lengths; one length may be -1) -> one ReLU + Result per part (the recorded-Function front
+    end has no VariadicSplit: the plugin rewrites it into StridedSlices).  Returns the output shapes."""
+    lengths = list(lengths)
+    rest = x_shape[axis] - sum(v for v in lengths if v >= 0)
+    sizes = [rest if v < 0 else v for v in lengths]
+    outs = [list(x_shape[:axis]) + [sz] + list(x_shape[axis + 1:]) for sz in sizes]
+    consts = np.asarray([axis] + lengths, np.int64)
+
+    def port(pid, shape, prec="FP32"):
+        return '<port id="%d" precision="%s">%s</port>' % (pid, prec, "".join("<dim>%d</dim>" % d for d in shape))
+
+    j = lambda v: ", ".join(str(int(a)) for a in v)
+    n = len(lengths)
+    layers = [
+        '<layer id="0" name="data" type="Parameter" version="opset1"><data element_type="f32" shape="%s"/><output>%s</output></layer>' % (j(x_shape), port(0, x_shape)),
+        '<layer id="1" name="axis" type="Const" version="opset1"><data element_type="i64" shape="" offset="0" size="8"/><output><port id="0" precision="I64"/></output></layer>',
+        '<layer id="2" name="lengths" type="Const" version="opset1"><data element_type="i64" shape="%d" offset="8" size="%d"/><output>%s</output></layer>'
+        % (n, 8 * n, port(0, [n], "I64")),
+        '<layer id="3" name="vsplit" type="VariadicSplit" version="opset1"><input>%s<port id="1" precision="I64"/>%s</input><output>%s</output></layer>'
+        % (port(0, x_shape), port(2, [n], "I64"), "".join(port(3 + k, outs[k]) for k in range(n))),
+    ]
+    edges = ['<edge from-layer="0" from-port="0" to-layer="3" to-port="0"/>', '<edge from-layer="1" from-port="0" to-layer="3" to-port="1"/>',
+             '<edge from-layer="2" from-port="0" to-layer="3" to-port="2"/>']
+    lid = 4
+    for k in range(n):
+        layers.append('<layer id="%d" name="relu%d" type="ReLU" version="opset1"><input>%s</input><output>%s</output></layer>' % (lid, k, port(0, outs[k]), port(1, outs[k])))
+        layers.append('<layer id="%d" name="result%d" type="Result" version="opset1"><input>%s</input></layer>' % (lid + 1, k, port(0, outs[k])))
+        edges.append('<edge from-layer="3" from-port="%d" to-layer="%d" to-port="0"/>' % (3 + k, lid))
+        edges.append('<edge from-layer="%d" from-port="1" to-layer="%d" to-port="0"/>' % (lid, lid + 1))
+        lid += 2
+    with open(xml_path, "w") as f:
+        f.write('<?xml version="1.0"?>\n<net name="vsplit" version="10"><layers>%s</layers><edges>%s</edges></net>\n' % ("".join(layers), "".join(edges)))
+    consts.tofile(xml_path[:-4] + ".bin")
+    return outs
