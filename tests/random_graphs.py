@@ -353,3 +353,52 @@ def build_detection_output(seed):
     p = np.exp(logits - logits.max(-1, keepdims=True))
     p /= p.sum(-1, keepdims=True)
     return f, {"loc": (rng.standard_normal((n, priors * nloc * 4)) * 0.5).astype(np.float32), "conf": p.reshape(n, -1).astype(np.float32)}
+
+
+# ---- fifth family: pooling corner cases -------------------------------------------------------------------------------------------------------
+def build_pool(seed):
+    """One or two pooling layers with non-square kernels / strides, asymmetric padding, both rounding modes, include / exclude padding,
+    after an optional 1x1 convolution (so the pooled tensor is channels-last on the device) - the divisor and window-clipping rules of
+    reference/avg_pool.hpp and reference/max_pool.hpp.  Windows that lie entirely in the padding are not drawn (undefined: 0 / 0)."""
+    rng = np.random.default_rng(seed + 31337)
+    f = Function("random_pool_%d" % seed)
+    n, c, h, w = int(rng.integers(1, 3)), int(rng.choice([1, 3, 8, 13, 16, 24])), int(rng.integers(4, 18)), int(rng.integers(4, 18))
+    x = f.parameter((n, c, h, w))
+    inputs = {"Parameter_0": rng.standard_normal((n, c, h, w)).astype(np.float32)}
+    y = x
+    if rng.integers(2):
+        o = int(rng.choice([4, 8, 12, 16]))
+        y = f.relu(f.convolution(y, (rng.standard_normal((o, c, 1, 1)) / np.sqrt(c)).astype(np.float32), (1, 1), (0, 0), (0, 0)))
+        c = o
+    for _ in range(int(rng.integers(1, 3))):
+        for _try in range(20):
+            k = (int(rng.integers(1, 6)), int(rng.integers(1, 6)))
+            s = (int(rng.integers(1, 4)), int(rng.integers(1, 4)))
+            pb = (int(rng.integers(0, k[0] // 2 + 1)), int(rng.integers(0, k[1] // 2 + 1)))
+            pe = (int(rng.integers(0, k[0] // 2 + 1)), int(rng.integers(0, k[1] // 2 + 1)))
+            rounding = "ceil" if rng.integers(2) else "floor"
+            dims = []
+            ok = True
+            for d, v in enumerate((h, w)):
+                num = v + pb[d] + pe[d] - k[d]
+                if num < 0:
+                    ok = False
+                    break
+                o_ = (-(-num // s[d]) if rounding == "ceil" else num // s[d]) + 1
+                if (o_ - 1) * s[d] - pb[d] >= v:          # last window starts past the input: only padding inside
+                    ok = False
+                    break
+                dims.append(o_)
+            if ok:
+                break
+        else:
+            break
+        if rng.integers(2):
+            y = f.max_pool(y, k, s, pb, pe, rounding=rounding)
+        else:
+            y = f.avg_pool(y, k, s, pb, pe, exclude_pad=bool(rng.integers(2)), rounding=rounding)
+        h, w = dims
+        if min(h, w) < 2:
+            break
+    f.result(y)
+    return f, inputs

