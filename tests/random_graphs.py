@@ -402,3 +402,50 @@ def build_pool(seed):
             break
     f.result(y)
     return f, inputs
+
+
+# ---- sixth family: convolution geometry corner cases ----------------------------------------------------------------------------------------
+def build_conv_corner(seed):
+    """ONE convolution (+ bias, + activation, sometimes + residual) with everything non-square: kernel (1..7 x 1..7, e.g. the 1x7 / 7x1 pairs of
+    Inception), strides and dilations per axis, asymmetric padding, dense / grouped / depthwise, channel counts on both sides of the
+    tensor-core tile sizes (the implicit-GEMM, halo, small-Cin, depthwise and fp32 kernels all get reached)."""
+    rng = np.random.default_rng(seed + 271828)
+    f = Function("random_conv_%d" % seed)
+    n = int(rng.integers(1, 4))
+    c = int(rng.choice([1, 3, 4, 8, 16, 24, 32, 64, 64, 96, 128, 160, 256]))
+    h, w = int(rng.integers(5, 30)), int(rng.integers(5, 30))
+    x = f.parameter((n, c, h, w))
+    inputs = {"Parameter_0": rng.standard_normal((n, c, h, w)).astype(np.float32)}
+    for _try in range(50):
+        k = (int(rng.choice([1, 1, 2, 3, 3, 5, 7])), int(rng.choice([1, 1, 2, 3, 3, 5, 7])))
+        s = (int(rng.choice([1, 1, 2, 3])), int(rng.choice([1, 1, 2, 3])))
+        d = (int(rng.choice([1, 1, 2, 3])), int(rng.choice([1, 1, 2, 3])))
+        pb = (int(rng.integers(0, k[0])), int(rng.integers(0, k[1])))
+        pe = (int(rng.integers(0, k[0])), int(rng.integers(0, k[1])))
+        if all(v + pb[a] + pe[a] >= d[a] * (k[a] - 1) + 1 for a, v in enumerate((h, w))):
+            break
+    else:
+        k, s, d, pb, pe = (1, 1), (1, 1), (1, 1), (0, 0), (0, 0)
+    mode = int(rng.integers(5))
+    if mode == 0 and c > 1:
+        wt = (rng.standard_normal((c, 1, 1) + k) / np.sqrt(k[0] * k[1])).astype(np.float32)
+        y = f.group_convolution(x, wt, s, pb, pe, d)
+        o = c
+    elif mode == 1 and c % 4 == 0 and c >= 8:
+        g = int(rng.choice([2, 4]))
+        o = g * int(rng.choice([1, 2, 4, 8, 16]))
+        wt = (rng.standard_normal((g, o // g, c // g) + k) / np.sqrt(c // g * k[0] * k[1])).astype(np.float32)
+        y = f.group_convolution(x, wt, s, pb, pe, d)
+    else:
+        o = int(rng.choice([1, 5, 8, 16, 32, 64, 64, 72, 128, 192, 256, 320]))
+        wt = (rng.standard_normal((o, c) + k) / np.sqrt(c * k[0] * k[1])).astype(np.float32)
+        y = f.convolution(x, wt, s, pb, pe, d)
+    if rng.integers(4):
+        y = f.add(y, rng.standard_normal((1, o, 1, 1)).astype(np.float32) * 0.1)
+    if rng.integers(3):
+        y = _act(f, rng, y)
+    if rng.integers(4) == 0:      # a second convolution on top: 1x1 with a residual back to the first one's output
+        wt2 = (rng.standard_normal((o, o, 1, 1)) / np.sqrt(o)).astype(np.float32)
+        y = f.relu(f.add(f.convolution(y, wt2, (1, 1), (0, 0), (0, 0)), y))
+    f.result(y)
+    return f, inputs

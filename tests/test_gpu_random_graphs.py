@@ -132,3 +132,11 @@ def test_random_pooling_corner_cases_match_oracle(seed):
     build_pool; the restatement is pinned to the nGraph reference kernels on 600 of these)."""
     f, inputs = random_graphs.build_pool(seed)
     _check(f, inputs, ("FP32", "BF16"), "pool seed %d" % seed)
+
+
+@pytest.mark.parametrize("seed", range(240))
+def test_random_convolution_geometry_matches_oracle(seed):
+    """One convolution with non-square kernels (1x7, 7x1, 3x5 ...), per-axis strides / dilations, asymmetric padding, dense / grouped /
+    depthwise, 1 - 320 channels (tests/random_graphs.py build_conv_corner; the restatement agrees with MKLDNNPlugin on 500 of these)."""
+    f, inputs = random_graphs.build_conv_corner(seed)
+    _check(f, inputs, ("FP32", "BF16", "FP16") if seed % 3 == 0 else ("FP32", "BF16"), "conv-corner seed %d" % seed)

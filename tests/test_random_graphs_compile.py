@@ -32,7 +32,8 @@ def test_random_sequence_and_misc_graphs_lower_in_every_precision(seed, family):
 
 @pytest.mark.parametrize("family,seed", [("build", s) for s in list(range(1, 40, 4)) + list(range(1001, 1020, 4))] +
                          [("build_sequence", s) for s in range(0, 30, 3)] + [("build_misc", s) for s in range(0, 60, 3)] +
-                         [("build_nms", s) for s in range(0, 60, 2)] + [("build_detection_output", s) for s in range(0, 60, 2)])
+                         [("build_nms", s) for s in range(0, 60, 2)] + [("build_detection_output", s) for s in range(0, 60, 2)] +
+                         [("build_conv_corner", s) for s in range(0, 120, 3)])
 def test_oracle_matches_the_reference_cpu_plugin_on_random_graphs(seed, family):
     """Pins the numpy restatement on graphs nobody wrote by hand: the same random networks on the UNMODIFIED MKLDNNPlugin (oracle/_ref,
     fp32) - beyond the fixed golden cases of tests/test_oracle_golden.py."""
