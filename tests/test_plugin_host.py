@@ -231,3 +231,19 @@ def test_variadic_split_becomes_strided_slices(tmp_path):
     assert json.loads(q.stdout)["supported_layers"] == json.loads(q.stdout)["total_layers"]
     p = ie_run(xml, "--dry", "--config", "B200_DRY_COMPILE=YES")
     assert p.returncode == 0, p.stderr
+
+
+def test_mean_image_survives_export_and_import(tiny_resnet_xml, tmp_path):
+    """PreProcessInfo MEAN_IMAGE is compiled into the network as one element-wise Subtract (AddMeanScale) and travels with the exported
+    stream (per-channel planes after the mean / scale values): the imported network has the same schedule as the loaded one, which is
+    longer than the schedule without a mean image."""
+    plain = json.loads(ie_run(tiny_resnet_xml, "--dry", "--config", "B200_DRY_COMPILE=YES").stdout)
+    blob = str(tmp_path / "mean.blob")
+    p = ie_run(tiny_resnet_xml, "--dry", "--export", blob, "--mean-image", "data=0.5", "--config", "B200_DRY_COMPILE=YES")
+    assert p.returncode == 0, p.stderr
+    loaded = json.loads(p.stdout)
+    assert loaded["exec_nodes"] > plain["exec_nodes"]     # the Subtract (and the layout step in front of the first convolution)
+    p = ie_run(tiny_resnet_xml, "--dry", "--import", blob, "--config", "B200_DRY_COMPILE=YES")
+    assert p.returncode == 0, p.stderr
+    assert json.loads(p.stdout) == loaded
+    assert os.path.getsize(blob) > 3 * 64 * 64 * 4        # the three 64 x 64 fp32 planes are in the stream

@@ -28,7 +28,7 @@ static std::vector<std::string> split(const std::string& s, char d) {
 
 int main(int argc, char** argv) {
   std::string model, device = "CPU", outdir = ".", plugins_xml;
-  std::map<std::string, std::string> config, inputs, in_prec, mean_scale;
+  std::map<std::string, std::string> config, inputs, in_prec, mean_scale, mean_image;
   std::string export_path, import_path, cache_dir;
   int niter = 1;
   bool query = false, dry = false, user_blobs = false, cancel = false, callback = false, remote = false;
@@ -53,6 +53,7 @@ int main(int argc, char** argv) {
     else if (a == "--config-kv") { auto kv = next(); auto p = kv.find('='); if (p != std::string::npos) config[kv.substr(0, p)] = kv.substr(p + 1); }  // one key whose value has commas
     else if (a == "--input") { auto kv = next(); auto p = kv.find('='); inputs[kv.substr(0, p)] = kv.substr(p + 1); }
     else if (a == "--mean-scale") { auto kv = next(); auto p = kv.find('='); mean_scale[kv.substr(0, p)] = kv.substr(p + 1); }   // name=m0:m1:m2/s0:s1:s2 (PreProcessInfo)
+    else if (a == "--mean-image") { auto kv = next(); auto p = kv.find('='); mean_image[kv.substr(0, p)] = kv.substr(p + 1); }   // name=v: MEAN_IMAGE, plane of channel c filled with v * (c + 1)
     else if (a == "--input-precision") { auto kv = next(); auto p = kv.find('='); in_prec[kv.substr(0, p)] = kv.substr(p + 1); }
     else { std::cerr << "unknown argument " << a << "\n"; return 2; }
   }
@@ -73,6 +74,20 @@ int main(int argc, char** argv) {
           pre.init(means.size());
           for (size_t c = 0; c < means.size(); ++c) { pre[c]->meanValue = std::stof(means[c]); pre[c]->stdScale = std::stof(scales.at(c)); }
           pre.setVariant(MEAN_VALUE);
+        }
+        auto mi = mean_image.find(in.first);
+        if (mi != mean_image.end()) {
+          const auto dims = in.second->getTensorDesc().getDims();
+          PreProcessInfo& pre = in.second->getPreProcess();
+          pre.init(dims.at(1));
+          for (size_t c = 0; c < dims.at(1); ++c) {
+            auto blob = make_shared_blob<float>(TensorDesc(Precision::FP32, {dims.at(2), dims.at(3)}, Layout::HW));
+            blob->allocate();
+            float* p = blob->buffer().as<float*>();
+            for (size_t k = 0; k < blob->size(); ++k) p[k] = std::stof(mi->second) * static_cast<float>(c + 1);
+            pre[c]->meanData = blob;
+          }
+          pre.setVariant(MEAN_IMAGE);
         }
       }
     }
